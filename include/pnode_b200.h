@@ -1,0 +1,150 @@
+/*
+ * pnode_b200 -- C ABI of the B200-native neural-ODE integrator / discrete-adjoint engine.
+ *
+ * This is the drop-in boundary: the host side (pnode_b200/petsc_adjoint.py, a mirror of the reference's
+ * pnode/petsc_adjoint.py) binds exactly these entry points through ctypes.  Plain pointers and sizes only; every
+ * pointer named `d_*` is a DEVICE pointer owned by the caller (torch allocations), `stream` is a cudaStream_t passed as
+ * void* (torch.cuda.current_stream().cuda_stream).  No entry point synchronises the stream or allocates memory unless
+ * stated.  Every function returns 0 on success; on failure it returns a non-zero code and pnode_last_error() describes
+ * it (the reference surfaces PETSc error codes as petsc4py.PETSc.Error -- SURVEY.md section 8b "Errors").
+ *
+ * Each entry point cites the reference interface it replaces.  "[PETSc]" marks arithmetic that lives inside the PETSc
+ * library the reference calls (not vendored under the reference tree; see DESIGN.md "Oracle").
+ */
+#ifndef PNODE_B200_H
+#define PNODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNODE_ABI_VERSION 1
+
+/* scalar type of state vectors: the reference requires tensor dtype == PETSc's compiled scalar type
+ * (tests/test_pnode.py:127-130, README.md:27) */
+#define PNODE_F32 0
+#define PNODE_F64 1
+
+#define PNODE_MAX_TERMS 16  /* terms of one stage combination (ARK5: 7 implicit + 7 explicit slopes) */
+#define PNODE_MAX_STAGES 7  /* dopri5 */
+#define PNODE_MAX_SRCS 32   /* parameter tensors per multi-axpy launch */
+
+int pnode_abi_version(void);
+const char *pnode_last_error(void);
+
+/* Number of SMs / device name of the current device (used to size persistent grids; 148 on B200). */
+int pnode_device_sm_count(int *sm_count);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Generic path: the vector arithmetic PETSc performs between callbacks, one launch per stage instead of one per
+ * AXPY term.
+ * -------------------------------------------------------------------------------------------------------------- */
+
+/* out[i] = base_coef * base[i] + sum_j coefs[j] * vecs[j][i],  i < n.   (base may be NULL; out may alias base.)
+ * Replaces [PETSc] VecCopy + VecMAXPY in TSStep_RK / TSStep_ARKIMEX (stage value Y_i = u + h sum a_ij k_j, called
+ * between the reference's evalRHSFunction callbacks, pnode/petsc_adjoint.py:393-412) and VecMAXPY / VecAXPY in
+ * TSAdjointStep_RK (w = lambda + sum_j (a_ji/b_i) lambda_s,j, called before RHSJacShell.multTranspose,
+ * petsc_adjoint.py:52-82).  `vecs` and `coefs` are HOST arrays of nterms device pointers / doubles. */
+int pnode_lincomb(void *d_out, const void *d_base, double base_coef, const void *const *vecs, const double *coefs,
+                  int nterms, int64_t n, int dtype, void *stream);
+
+/* Step completion fused with the embedded error estimate and the weighted RMS norm:
+ *   u_new[i] = u[i] + sum_j bw[j] * k[j][i]                 ([PETSc] TSEvaluateStep_RK, order p)
+ *   x[i]     = u_new[i] + sum_j ew[j] * k[j][i]             ([PETSc] TSEvaluateStep_RK, order p-1; ew = h (bhat - b))
+ *   *d_sumsq = sum_i ((u_new[i]-x[i]) / (atol + rtol*max(|u_new[i]|,|x[i]|)))^2      ([PETSc] TSErrorWeightedNorm2)
+ * d_sumsq is ONE double on the device; the sum is formed in a fixed order (per-block partials in d_work, combined by the
+ * last block) so accept/reject decisions are reproducible.  d_work must hold pnode_wrms_work_bytes() bytes and be
+ * zero-initialised once by the caller (the kernel restores it).  ew == NULL skips the error part (plain completion).
+ * Replaces the launches between the last evalRHSFunction of a step and TSAdaptChoose. */
+int64_t pnode_wrms_work_bytes(void);
+int pnode_rk_complete_wrms(void *d_unew, const void *d_u, const void *const *k, const double *bw, const double *ew,
+                           int nterms, int64_t n, double atol, double rtol, double *d_sumsq, void *d_work, int dtype,
+                           void *stream);
+
+/* mu[off_k + i] += coef * src_k[i] for each of nsrc parameter-gradient tensors laid end to end (off_k = sum of sizes
+ * before k).  Replaces RHSJacPShell.multTranspose / IJacPShell.multTranspose (petsc_adjoint.py:303-363: flatten the cached
+ * per-parameter VJPs) + [PETSc] VecAXPY on mu in TSAdjointStep_*.  srcs may contain NULL (parameter unused => zeros,
+ * pnode/misc.py:9-14).  `srcs`/`sizes` are HOST arrays. */
+int pnode_multi_axpy(void *d_mu, const void *const *srcs, const int64_t *sizes, int nsrc, double coef, int dtype,
+                     void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Fused path for tiny-state MLP right-hand sides  f(t,y) = W2 * tanh(W1 * phi(y) + b1) + b2,  phi = cube | identity
+ * (the spiral model of examples-pnode/ode_demo_petsc.py:207-230: Linear(2,50)-Tanh-Linear(50,2) applied to y**3).
+ * One launch advances every trajectory through ALL steps and stages of a fixed-step explicit RK scheme; weights stay
+ * in shared memory; stage values are checkpointed in HBM for the adjoint (replaces -ts_trajectory_type memory).
+ * -------------------------------------------------------------------------------------------------------------- */
+
+typedef struct pnode_rk_tableau {
+    int32_t s;                                        /* stages */
+    int32_t fsal;                                     /* 1: last stage has b = 0 and nothing depends on it */
+    double a[PNODE_MAX_STAGES][PNODE_MAX_STAGES];     /* strictly lower triangular */
+    double b[PNODE_MAX_STAGES];
+    double c[PNODE_MAX_STAGES];
+} pnode_rk_tableau;
+
+typedef struct pnode_mlp_desc {
+    int32_t dim;        /* state dimension per trajectory (2) */
+    int32_t hidden;     /* hidden width (50) */
+    int32_t phi;        /* 0 identity, 1 cube (y**3) */
+    int32_t dtype;      /* PNODE_F32 | PNODE_F64 */
+    const void *d_w1;   /* [hidden, dim]  row-major (torch nn.Linear.weight) */
+    const void *d_b1;   /* [hidden] */
+    const void *d_w2;   /* [dim, hidden] */
+    const void *d_b2;   /* [dim] */
+} pnode_mlp_desc;
+
+/* 1 if a fused kernel is compiled for (dim, hidden, phi, dtype, stages), else 0 (caller uses the generic path). */
+int pnode_mlp_rk_supported(int dim, int hidden, int phi, int dtype, int stages);
+
+/* One entry of the step schedule the host controller hands to a fused sweep.  In fixed-step runs (-ts_adapt_type none,
+ * or a tableau without an embedded method) every step size is known before the launch: the host applies the reference's
+ * step_size / per-step list semantics (petsc_adjoint.py:518-532, 812-817) and [PETSc] MATCHSTEP clamping. */
+typedef struct pnode_step {
+    double t;          /* step start time t_n */
+    double h;          /* step size */
+    int32_t out_slot;  /* forward: slot of d_sol that receives u_{n+1}, or -1 ([PETSc] TSSetTimeSpan slots) */
+    int32_t in_slot;   /* adjoint: slot of d_gout added to lambda AFTER this step's adjoint (forcing), or -1 */
+} pnode_step;
+
+/* Forward sweep.  Replaces ODEPetsc.odeint's ts.solve(U) (petsc_adjoint.py:777-869) with all of [PETSc] TSStep_RK /
+ * TSEvaluateStep_RK / TSTrajectorySet and the reference's evalRHSFunction callbacks inside one kernel.
+ *   d_u0     [ntraj, dim]                 initial states (C-order flatten of the caller's tensor, petsc_adjoint.py:596)
+ *   d_sched  DEVICE [nsteps] pnode_step   schedule
+ *   d_sol    [nout, ntraj, dim]           span solutions (slots named by out_slot; others untouched)
+ *   d_ckpt   [nsteps, s, dim, ntraj]      stage values Y_i, or NULL when no adjoint will follow
+ */
+int pnode_mlp_rk_forward(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, void *stream);
+
+/* Discrete-adjoint sweep over the same schedule, last step first.  Replaces OdeintAdjointMethod.backward
+ * (petsc_adjoint.py:916-947): lambda <- grad_out[last_slot]; per step [PETSc] TSAdjointStep_RK with the reference's
+ * RHSJacShell.multTranspose / RHSJacPShell.multTranspose callbacks fused in; lambda += grad_out[in_slot] after the
+ * adjoint of a step that starts at an output point (the reference's forcing, petsc_adjoint.py:938).
+ *   d_gout   [nout, ntraj, dim]   dL/d(solution slots)
+ *   d_lambda [ntraj, dim]         out: dL/du0
+ *   d_mu     [np]                 out: dL/dparams, order W1,b1,W2,b2 (func.parameters() order, petsc_adjoint.py:618-620)
+ *   d_work   scratch of pnode_mlp_rk_adjoint_work_bytes() bytes, zero-initialised once by the caller (per-block partial
+ *            mu, combined in a fixed order by the last block so that mu is bit-reproducible)
+ */
+int64_t pnode_mlp_rk_adjoint_work_bytes(const pnode_mlp_desc *mlp);
+int pnode_mlp_rk_adjoint(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                         void *d_lambda, void *d_mu, void *d_work, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): peak FMA issue rate of the CUDA-core pipe in the given dtype, used as the
+ * compute-roofline denominator for the MLP kernels (MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).
+ * Launches a register-resident FMA chain on every SM; *flops = 2 * FMAs executed.  Synchronous.
+ * -------------------------------------------------------------------------------------------------------------- */
+int pnode_peak_fma(int dtype, int iters, double *flops, float *ms);
+
+/* out[i] = tanh(in[i]) evaluated with the kernels' own tanh (unit-test hook for its accuracy). */
+int pnode_tanh_probe(const void *d_in, void *d_out, int64_t n, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNODE_B200_H */

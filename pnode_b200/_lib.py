@@ -1,0 +1,80 @@
+"""ctypes binding of include/pnode_b200.h.  There is NO fallback: if the shared library is missing or a symbol is
+absent, importing the engine fails loudly (the product path never runs on the CPU)."""
+import ctypes as C
+import os
+
+from .errors import Error
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpnode_b200.so")
+
+F32, F64 = 0, 1
+MAX_TERMS, MAX_STAGES, MAX_SRCS = 16, 7, 32
+
+
+class RKTableau(C.Structure):
+    _fields_ = [("s", C.c_int32), ("fsal", C.c_int32), ("a", (C.c_double * MAX_STAGES) * MAX_STAGES),
+                ("b", C.c_double * MAX_STAGES), ("c", C.c_double * MAX_STAGES)]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("hidden", C.c_int32), ("phi", C.c_int32), ("dtype", C.c_int32),
+                ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p)]
+
+
+class Step(C.Structure):
+    _fields_ = [("t", C.c_double), ("h", C.c_double), ("out_slot", C.c_int32), ("in_slot", C.c_int32)]
+
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_SIGNATURES = {
+    "pnode_abi_version": (C.c_int, []),
+    "pnode_last_error": (C.c_char_p, []),
+    "pnode_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "pnode_lincomb": (C.c_int, [_vp, _vp, _d, C.POINTER(_vp), C.POINTER(_d), _i, _i64, _i, _vp]),
+    "pnode_wrms_work_bytes": (_i64, []),
+    "pnode_rk_complete_wrms": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_d), C.POINTER(_d), _i, _i64, _d, _d, _vp,
+                                         _vp, _i, _vp]),
+    "pnode_multi_axpy": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i, _d, _i, _vp]),
+    "pnode_mlp_rk_supported": (C.c_int, [_i, _i, _i, _i, _i]),
+    "pnode_mlp_rk_forward": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _vp, _i64, _vp, _i, _vp, _vp, _vp]),
+    "pnode_mlp_rk_adjoint_work_bytes": (_i64, [C.POINTER(MlpDesc)]),
+    "pnode_mlp_rk_adjoint": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
+                                       _vp, _vp]),
+    "pnode_peak_fma": (C.c_int, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float)]),
+    "pnode_tanh_probe": (C.c_int, [_vp, _vp, _i64, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and type the library.  Raises pnode_b200.Error if it is missing: build it with
+    `python -m pnode_b200.build` (or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Error(-1, "native library %s not built; run `python -m pnode_b200.build`. "
+                        "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise Error(-2, "native library %s lacks symbol %s (stale build?)" % (LIB_PATH, name))
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pnode_abi_version() != 1:
+        raise Error(-3, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Error(rc, load().pnode_last_error().decode("utf-8", "replace"))
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)

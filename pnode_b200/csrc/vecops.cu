@@ -1,0 +1,426 @@
+// Generic-path vector kernels: the arithmetic PETSc TS / TSAdjoint performs between Python callbacks in the
+// reference, fused to one launch per stage.  All HBM-bound streaming kernels:
+// 16-byte vector accesses, grid sized to a multiple of the SM count, grid-stride loops, no shared-memory staging
+// (each element is touched exactly once).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pnode {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cached = n;
+    }
+    return cached;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+
+template <typename T>
+struct TermTable {
+    const T *v[PNODE_MAX_TERMS];
+    T c[PNODE_MAX_TERMS];
+    int n;
+};
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+    typedef float4 type;
+    static constexpr int N = 4;
+};
+template <>
+struct Vec16<double> {
+    typedef double2 type;
+    static constexpr int N = 2;
+};
+
+template <typename T>
+__device__ __forceinline__ void vload(const T *p, T (&r)[Vec16<T>::N]) {
+    typedef typename Vec16<T>::type V;
+    V v = *reinterpret_cast<const V *>(p);
+    memcpy(r, &v, sizeof(V));
+}
+template <typename T>
+__device__ __forceinline__ void vstore(T *p, const T (&r)[Vec16<T>::N]) {
+    typedef typename Vec16<T>::type V;
+    V v;
+    memcpy(&v, r, sizeof(V));
+    *reinterpret_cast<V *>(p) = v;
+}
+
+// out = base_coef*base + sum_j c_j v_j.   VEC: 16-byte path (all pointers 16B aligned); tail handled scalar.
+template <typename T, bool HAS_BASE>
+__global__ void __launch_bounds__(256) lincomb_kernel(T *__restrict__ out, const T *__restrict__ base, T base_coef,
+                                                      const TermTable<T> tt, int64_t n) {
+    constexpr int N = Vec16<T>::N;
+    const int64_t nvec = n / N;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        T acc[N];
+        if (HAS_BASE) {
+            T b[N];
+            vload(base + i * N, b);
+#pragma unroll
+            for (int e = 0; e < N; ++e) acc[e] = base_coef * b[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < N; ++e) acc[e] = T(0);
+        }
+#pragma unroll 4
+        for (int j = 0; j < tt.n; ++j) {
+            T x[N];
+            vload(tt.v[j] + i * N, x);
+#pragma unroll
+            for (int e = 0; e < N; ++e) acc[e] = fma(tt.c[j], x[e], acc[e]);
+        }
+        vstore(out + i * N, acc);
+    }
+    // scalar tail
+    for (int64_t i = nvec * N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T acc = HAS_BASE ? base_coef * base[i] : T(0);
+        for (int j = 0; j < tt.n; ++j) acc = fma(tt.c[j], tt.v[j][i], acc);
+        out[i] = acc;
+    }
+}
+
+template <typename T, bool HAS_BASE>
+__global__ void __launch_bounds__(256) lincomb_scalar_kernel(T *__restrict__ out, const T *__restrict__ base,
+                                                             T base_coef, const TermTable<T> tt, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T acc = HAS_BASE ? base_coef * base[i] : T(0);
+        for (int j = 0; j < tt.n; ++j) acc = fma(tt.c[j], tt.v[j][i], acc);
+        out[i] = acc;
+    }
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm) {
+    int64_t want = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+template <typename T>
+static int lincomb_impl(void *d_out, const void *d_base, double base_coef, const void *const *vecs,
+                        const double *coefs, int nterms, int64_t n, cudaStream_t st) {
+    TermTable<T> tt;
+    tt.n = nterms;
+    bool al = aligned16(d_out) && (d_base == nullptr || aligned16(d_base));
+    for (int j = 0; j < nterms; ++j) {
+        tt.v[j] = static_cast<const T *>(vecs[j]);
+        tt.c[j] = static_cast<T>(coefs[j]);
+        al = al && aligned16(vecs[j]);
+    }
+    if (n == 0) return 0;
+    const int threads = 256;
+    T *out = static_cast<T *>(d_out);
+    const T *base = static_cast<const T *>(d_base);
+    if (al) {
+        int grid = stream_grid(n / Vec16<T>::N + 1, threads, 8);
+        if (base)
+            lincomb_kernel<T, true><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+        else
+            lincomb_kernel<T, false><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+    } else {
+        int grid = stream_grid(n, threads, 8);
+        if (base)
+            lincomb_scalar_kernel<T, true><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+        else
+            lincomb_scalar_kernel<T, false><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+    }
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// completion + embedded error + WRMS partial sums, deterministic two-level reduction in one launch
+
+constexpr int WRMS_MAX_BLOCKS = 148 * 8;
+struct WrmsWork {
+    unsigned int ticket;
+    unsigned int pad[15];
+    double partial[WRMS_MAX_BLOCKS];
+};
+
+template <typename T, bool WITH_ERR>
+__global__ void __launch_bounds__(256) complete_wrms_kernel(T *__restrict__ unew, const T *__restrict__ u,
+                                                            const TermTable<T> bw, const TermTable<T> ew, int64_t n,
+                                                            double atol, double rtol, double *__restrict__ sumsq,
+                                                            WrmsWork *__restrict__ work, int vec_ok) {
+    constexpr int N = Vec16<T>::N;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double local = 0.0;
+    const int64_t nvec = vec_ok ? n / N : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        T acc[N], err[N];
+        vload(u + i * N, acc);
+#pragma unroll
+        for (int e = 0; e < N; ++e) err[e] = T(0);
+#pragma unroll 4
+        for (int j = 0; j < bw.n; ++j) {
+            T x[N];
+            vload(bw.v[j] + i * N, x);
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                acc[e] = fma(bw.c[j], x[e], acc[e]);
+                if (WITH_ERR) err[e] = fma(ew.c[j], x[e], err[e]);
+            }
+        }
+        vstore(unew + i * N, acc);
+        if (WITH_ERR) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                double un = (double)acc[e], x = (double)(acc[e] + err[e]);
+                double tol = atol + rtol * fmax(fabs(un), fabs(x));
+                double r = (un - x) / tol;
+                local = fma(r, r, local);
+            }
+        }
+    }
+    for (int64_t i = nvec * N + tid; i < n; i += stride) {
+        T acc = u[i], err = T(0);
+        for (int j = 0; j < bw.n; ++j) {
+            T x = bw.v[j][i];
+            acc = fma(bw.c[j], x, acc);
+            if (WITH_ERR) err = fma(ew.c[j], x, err);
+        }
+        unew[i] = acc;
+        if (WITH_ERR) {
+            double un = (double)acc, x = (double)(acc + err);
+            double tol = atol + rtol * fmax(fabs(un), fabs(x));
+            double r = (un - x) / tol;
+            local = fma(r, r, local);
+        }
+    }
+    if (!WITH_ERR) return;
+    // block reduction (fixed shape => deterministic)
+    __shared__ double wsum[8];
+    __shared__ bool is_last;
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
+        work->partial[blockIdx.x] = s;
+        __threadfence();
+        unsigned int t = atomicAdd(&work->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += ((volatile double *)work->partial)[b];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) {
+            *sumsq = s;
+            work->ticket = 0u;
+        }
+    }
+}
+
+template <typename T>
+static int complete_impl(void *d_unew, const void *d_u, const void *const *k, const double *bwc, const double *ewc,
+                         int nterms, int64_t n, double atol, double rtol, double *d_sumsq, void *d_work,
+                         cudaStream_t st) {
+    TermTable<T> bw, ew;
+    bw.n = ew.n = nterms;
+    bool al = aligned16(d_unew) && aligned16(d_u);
+    for (int j = 0; j < nterms; ++j) {
+        bw.v[j] = ew.v[j] = static_cast<const T *>(k[j]);
+        bw.c[j] = static_cast<T>(bwc[j]);
+        ew.c[j] = ewc ? static_cast<T>(ewc[j]) : T(0);
+        al = al && aligned16(k[j]);
+    }
+    if (n == 0) {
+        if (ewc) PNODE_CUDA_OK(cudaMemsetAsync(d_sumsq, 0, sizeof(double), st));
+        return 0;
+    }
+    const int threads = 256;
+    int grid = stream_grid(n / Vec16<T>::N + 1, threads, 8);
+    if (grid > WRMS_MAX_BLOCKS) grid = WRMS_MAX_BLOCKS;
+    if (ewc)
+        complete_wrms_kernel<T, true><<<grid, threads, 0, st>>>(static_cast<T *>(d_unew), static_cast<const T *>(d_u),
+                                                                bw, ew, n, atol, rtol, d_sumsq,
+                                                                static_cast<WrmsWork *>(d_work), al ? 1 : 0);
+    else
+        complete_wrms_kernel<T, false><<<grid, threads, 0, st>>>(static_cast<T *>(d_unew), static_cast<const T *>(d_u),
+                                                                 bw, ew, n, atol, rtol, nullptr, nullptr, al ? 1 : 0);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// mu += coef * concat(srcs)
+
+template <typename T>
+struct SrcTable {
+    const T *p[PNODE_MAX_SRCS];
+    int64_t end[PNODE_MAX_SRCS];  // exclusive prefix end of each source in the flattened index space
+    int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) multi_axpy_kernel(T *__restrict__ mu, const SrcTable<T> st, T coef,
+                                                         int64_t total) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int k = 0;
+        while (k < st.n - 1 && i >= st.end[k]) ++k;
+        const T *p = st.p[k];
+        if (p != nullptr) {
+            int64_t off = i - (k == 0 ? 0 : st.end[k - 1]);
+            mu[i] = fma(coef, p[off], mu[i]);
+        }
+    }
+}
+
+template <typename T>
+static int multi_axpy_impl(void *d_mu, const void *const *srcs, const int64_t *sizes, int nsrc, double coef,
+                           cudaStream_t stream) {
+    int64_t base = 0;
+    int k = 0;
+    while (k < nsrc) {
+        SrcTable<T> st;
+        int m = 0;
+        int64_t run = 0;
+        while (k < nsrc && m < PNODE_MAX_SRCS) {
+            st.p[m] = static_cast<const T *>(srcs[k]);
+            run += sizes[k];
+            st.end[m] = run;
+            ++m;
+            ++k;
+        }
+        st.n = m;
+        if (run > 0) {
+            int grid = stream_grid(run, 256, 8);
+            multi_axpy_kernel<T><<<grid, 256, 0, stream>>>(static_cast<T *>(d_mu) + base, st, (T)coef, run);
+            PNODE_CUDA_OK(cudaGetLastError());
+        }
+        base += run;
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// peak FMA issue-rate probe
+
+template <typename T>
+__global__ void __launch_bounds__(512) peak_fma_kernel(T *out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    T s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == (T)123456789) out[0] = s;  // never true; keeps the chain alive
+}
+
+}  // namespace pnode
+
+using namespace pnode;
+
+extern "C" {
+
+int pnode_abi_version(void) { return PNODE_ABI_VERSION; }
+
+const char *pnode_last_error(void) { return g_err; }
+
+int pnode_device_sm_count(int *n) {
+    int dev = 0;
+    PNODE_CUDA_OK(cudaGetDevice(&dev));
+    PNODE_CUDA_OK(cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, dev));
+    return 0;
+}
+
+int pnode_lincomb(void *d_out, const void *d_base, double base_coef, const void *const *vecs, const double *coefs,
+                  int nterms, int64_t n, int dtype, void *stream) {
+    PNODE_REQUIRE(nterms >= 0 && nterms <= PNODE_MAX_TERMS, "pnode_lincomb: nterms=%d out of range", nterms);
+    PNODE_REQUIRE(n >= 0 && (d_out != nullptr || n == 0), "pnode_lincomb: null output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PNODE_F32) return lincomb_impl<float>(d_out, d_base, base_coef, vecs, coefs, nterms, n, st);
+    if (dtype == PNODE_F64) return lincomb_impl<double>(d_out, d_base, base_coef, vecs, coefs, nterms, n, st);
+    PNODE_REQUIRE(false, "pnode_lincomb: unsupported dtype %d", dtype);
+}
+
+int64_t pnode_wrms_work_bytes(void) { return (int64_t)sizeof(WrmsWork); }
+
+int pnode_rk_complete_wrms(void *d_unew, const void *d_u, const void *const *k, const double *bw, const double *ew,
+                           int nterms, int64_t n, double atol, double rtol, double *d_sumsq, void *d_work, int dtype,
+                           void *stream) {
+    PNODE_REQUIRE(nterms >= 0 && nterms <= PNODE_MAX_TERMS, "pnode_rk_complete_wrms: nterms=%d out of range", nterms);
+    PNODE_REQUIRE(ew == nullptr || (d_sumsq != nullptr && d_work != nullptr),
+                  "pnode_rk_complete_wrms: error norm requested without d_sumsq/d_work");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PNODE_F32)
+        return complete_impl<float>(d_unew, d_u, k, bw, ew, nterms, n, atol, rtol, d_sumsq, d_work, st);
+    if (dtype == PNODE_F64)
+        return complete_impl<double>(d_unew, d_u, k, bw, ew, nterms, n, atol, rtol, d_sumsq, d_work, st);
+    PNODE_REQUIRE(false, "pnode_rk_complete_wrms: unsupported dtype %d", dtype);
+}
+
+int pnode_multi_axpy(void *d_mu, const void *const *srcs, const int64_t *sizes, int nsrc, double coef, int dtype,
+                     void *stream) {
+    PNODE_REQUIRE(nsrc >= 0, "pnode_multi_axpy: nsrc=%d", nsrc);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PNODE_F32) return multi_axpy_impl<float>(d_mu, srcs, sizes, nsrc, coef, st);
+    if (dtype == PNODE_F64) return multi_axpy_impl<double>(d_mu, srcs, sizes, nsrc, coef, st);
+    PNODE_REQUIRE(false, "pnode_multi_axpy: unsupported dtype %d", dtype);
+}
+
+int pnode_peak_fma(int dtype, int iters, double *flops, float *ms) {
+    const int threads = 512, blocks = sm_count() * 4;
+    void *d = nullptr;
+    PNODE_CUDA_OK(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    PNODE_CUDA_OK(cudaEventCreate(&e0));
+    PNODE_CUDA_OK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+        PNODE_CUDA_OK(cudaEventRecord(e0));
+        if (dtype == PNODE_F32)
+            peak_fma_kernel<float><<<blocks, threads>>>(static_cast<float *>(d), iters, 0.999f, 0.001f);
+        else
+            peak_fma_kernel<double><<<blocks, threads>>>(static_cast<double *>(d), iters, 0.999, 0.001);
+        PNODE_CUDA_OK(cudaEventRecord(e1));
+        PNODE_CUDA_OK(cudaEventSynchronize(e1));
+    }
+    PNODE_CUDA_OK(cudaEventElapsedTime(ms, e0, e1));
+    *flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"

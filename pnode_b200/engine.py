@@ -1,0 +1,359 @@
+"""Generic-path time stepper: any `nn.Module` right-hand side, evaluated by torch ON THE GPU, with every vector
+operation PETSc would do between callbacks (stage combination, completion + embedded error + weighted norm, adjoint
+stage combination, lambda / mu accumulation) done by the fused kernels of csrc/vecops.cu -- one launch per stage
+instead of one per AXPY term -- and stage checkpoints kept in HBM.
+
+What it replaces: [PETSc] TSSolve / TSStep_RK / TSStep_ARKIMEX / TSStep_Theta / TSAdaptChoose /
+TSTrajectory(memory) / TSAdjointStep_{RK,ARKIMEX,Theta}, and the arithmetic of the reference's callbacks
+evalRHSFunction, evalIFunction, RHSJacShell.multTranspose, IJacShell._vjp, RHSJacPShell / IJacPShell.multTranspose
+(pnode/petsc_adjoint.py:52-82, 179-196, 303-363, 393-441) and torch_linearsolve.PCShell (pnode/torch_linearsolve.py).
+"""
+import math
+
+import torch
+
+from .controller import TimeLoop
+from .errors import Error
+
+
+class Callbacks:
+    """The two closures the engine needs from the user's modules: f(t,u) and vjp(t,u,w) -> (J^T w, Jp^T w)."""
+
+    def __init__(self, func, tensor_size):
+        self.func = func
+        self.tensor_size = tensor_size
+        self.params = [p for p in func.parameters() if p.requires_grad] if isinstance(func, torch.nn.Module) else []
+        self.sizes = [p.numel() for p in self.params]
+        self.nparams = sum(self.sizes)
+        self.nfe = 0
+        self.nvjp = 0
+
+    def f(self, t, u):
+        """evalRHSFunction (petsc_adjoint.py:393-405): t is handed over as a python float."""
+        self.nfe += 1
+        with torch.no_grad():
+            out = self.func(t, u.view(self.tensor_size))
+        out = out.detach().reshape(-1)
+        if out.dtype != u.dtype:
+            out = out.to(u.dtype)
+        return out if out.is_contiguous() else out.contiguous()
+
+    def vjp(self, t, u, w, want_u=True):
+        """RHSJacShell.multTranspose (petsc_adjoint.py:52-82): one autograd.grad gives J^T w and the per-parameter
+        (df/dp)^T w (None for unused parameters, misc.py:9-14)."""
+        self.nvjp += 1
+        with torch.enable_grad():
+            x = u.detach().view(self.tensor_size).requires_grad_(True)
+            out = self.func(t, x)
+            inputs = ([x] if want_u else []) + self.params
+            if not inputs:
+                return None, []
+            g = torch.autograd.grad(out, inputs, w.view(out.shape).to(out.dtype), allow_unused=True)
+        if want_u:
+            vu, gp = g[0], list(g[1:])
+            vu = torch.zeros_like(u) if vu is None else vu.reshape(-1).contiguous()
+        else:
+            vu, gp = None, list(g)
+        return vu, gp
+
+
+class ImplicitSolver:
+    """Solve shift*(Y - Z) - f_I(t, Y) = 0 for one implicit stage, and the transposed linearised system for the adjoint.
+
+    linear_solver == "torch" (torch_linearsolve.PCShell): f_I is sample-independent; the dense [N,N] Jacobian of sample 0
+        (petsc_adjoint.py:479) is inverted once per shift and applied to all samples as ONE GEMM  X <- R @ inv(A)^T
+        ("factor once per step size, inverse-apply as tensor-core GEMM").
+    otherwise: dense Newton on the full state (small systems: ROBER-like), linear solves by LU.
+    """
+
+    DENSE_LIMIT = 8192
+
+    def __init__(self, ops, cb_im, linear_solver, batch_size, ksponly, rtol=1e-8, max_it=50):
+        self.ops = ops
+        self.cb = cb_im
+        self.linear_solver = linear_solver
+        self.batch = max(int(batch_size), 1)
+        self.ksponly = ksponly
+        self.rtol = rtol
+        self.max_it = max_it
+        self.reset()
+
+    def reset(self):
+        """Once per odeint: parameters may have changed (petsc_adjoint.py:792-799)."""
+        self._J0 = None
+        self._inv = {}
+
+    def _block_jacobian(self, t, y):
+        if self._J0 is None:
+            N = y.numel() // self.batch
+            y0 = y.view(self.cb.tensor_size)[0:1].detach().clone()
+            J = torch.autograd.functional.jacobian(lambda v: self.cb.func(t, v), y0)
+            self._J0 = J.reshape(N, N)
+        return self._J0
+
+    def _block_inverse(self, t, y, shift):
+        key = float(shift)
+        if key not in self._inv:
+            J = self._block_jacobian(t, y)
+            A = torch.eye(J.shape[0], dtype=J.dtype, device=J.device).mul_(shift) - J
+            self._inv[key] = torch.linalg.inv(A)
+        return self._inv[key]
+
+    def _dense_matrix(self, t, y, shift):
+        n = y.numel()
+        if n > self.DENSE_LIMIT:
+            raise Error(-20, "implicit stage with a full-state dense Jacobian needs n <= %d (got %d); use "
+                             "linear_solver='torch' for batched sample-independent operators" % (self.DENSE_LIMIT, n))
+        yy = y.detach().clone().view(self.cb.tensor_size)
+        J = torch.autograd.functional.jacobian(lambda v: self.cb.func(t, v), yy).reshape(n, n)
+        return torch.eye(n, dtype=J.dtype, device=J.device).mul_(shift) - J
+
+    def _apply(self, t, y, shift, rhs, transpose):
+        if self.linear_solver == "torch":
+            Ainv = self._block_inverse(t, y, shift)
+            N = Ainv.shape[0]
+            R = rhs.view(-1, N)
+            # per sample x = A^{-1} r  <=>  X = R A^{-T};   transposed solve: X = R A^{-1}
+            return (R @ (Ainv if transpose else Ainv.T)).reshape(-1)
+        A = self._dense_matrix(t, y, shift)
+        return torch.linalg.solve(A.T if transpose else A, rhs.reshape(-1))
+
+    def solve(self, t, Z, shift, guess):
+        y = guess
+        f0 = None
+        for _ in range(self.max_it):
+            F = torch.empty_like(Z)
+            self.ops.lincomb(F, None, 0.0, [y, Z, self.cb.f(t, y)], [shift, -shift, -1.0])
+            if not self.ksponly:
+                fn = float(torch.linalg.vector_norm(F))
+                if f0 is None:
+                    f0 = fn
+                elif fn <= self.rtol * f0 or fn <= 1e-50:
+                    break
+            d = self._apply(t, y, shift, F, transpose=False)
+            ynew = torch.empty_like(Z)
+            self.ops.lincomb(ynew, y, 1.0, [d], [-1.0])
+            y = ynew
+            if self.ksponly:  # -snes_type ksponly: exactly one Newton step
+                break
+            if float(torch.linalg.vector_norm(d)) <= 1e-8 * float(torch.linalg.vector_norm(y)):
+                break
+        return y
+
+    def solve_transpose(self, t, y, shift, rhs):
+        return self._apply(t, y, shift, rhs, transpose=True)
+
+
+class GenericTS:
+    """Host-driven stage loop over device kernels.  `ops` is a pnode_b200.device.DeviceOps."""
+
+    def __init__(self, ops, scheme, kind, atol, rtol, comm=None):
+        self.ops = ops
+        self.scheme = scheme
+        self.kind = kind
+        self.atol = atol
+        self.rtol = rtol
+        self.comm = comm  # optional data-parallel communicator (pnode_b200.parallel.BatchComm)
+        self.traj = []
+
+    # -- forward ----------------------------------------------------------------------------------------------------
+    def solve(self, cb_ex, cb_im, imp, u0, loop: TimeLoop, save_trajectory):
+        ops = self.ops
+        self.traj = []
+        u = u0.reshape(-1).clone()
+        n_local = u.numel()
+        n_global = n_local if self.comm is None else self.comm.global_count(n_local)
+        sols = {0: u} if loop.span is not None else {}
+        k_fsal = None
+        while not loop.done:
+            t, h = loop.t, loop.h
+            if self.kind == "rk":
+                unew, stages, sumsq = self._rk_attempt(cb_ex, t, h, u, k_fsal, loop.adaptive)
+            elif self.kind == "arkimex":
+                unew, stages, sumsq = self._ark_attempt(cb_ex, cb_im, imp, t, h, u, loop.adaptive)
+            else:
+                unew, stages, sumsq = self._theta_attempt(cb_im, imp, t, h, u)
+            enorm = None
+            if loop.adaptive:
+                if self.comm is not None:
+                    self.comm.allreduce_scalar(sumsq)  # one scalar per attempt: identical decision on every rank
+                enorm = math.sqrt(float(sumsq.item()) / n_global)
+            if not loop.report(enorm):
+                k_fsal = None
+                continue
+            if save_trajectory:
+                self.traj.append((t, h, stages))
+            if self.kind == "rk" and self.scheme.fsal:
+                k_fsal = stages[1][-1]
+            u = unew
+            if loop.last_out_slot >= 0:
+                sols[loop.last_out_slot] = u
+        loop.check_complete()
+        return u, sols
+
+    def _rk_attempt(self, cb, t, h, u, k_fsal, adaptive):
+        sc, ops = self.scheme, self.ops
+        s = sc.s
+        Y, K = [], []
+        for i in range(s):
+            if i == 0:
+                y = u
+            else:
+                idx = [j for j in range(i) if sc.A[i][j] != 0.0]
+                y = torch.empty_like(u)
+                ops.lincomb(y, u, 1.0, [K[j] for j in idx], [h * sc.A[i][j] for j in idx])
+            Y.append(y)
+            if i == 0 and k_fsal is not None:
+                K.append(k_fsal)
+            else:
+                K.append(cb.f(t + sc.c[i] * h, y))
+        idx = [j for j in range(s) if sc.b[j] != 0.0 or (adaptive and sc.bembed[j] != 0.0)]
+        unew = torch.empty_like(u)
+        ew = [h * (sc.bembed[j] - sc.b[j]) for j in idx] if adaptive else None
+        sumsq = ops.complete(unew, u, [K[j] for j in idx], [h * sc.b[j] for j in idx], ew, self.atol, self.rtol)
+        return unew, (Y, K), sumsq
+
+    def _ark_attempt(self, cb_ex, cb_im, imp, t, h, u, adaptive):
+        sc, ops = self.scheme, self.ops
+        s = sc.s
+        Y, KI, KE = [], [], []
+        for i in range(s):
+            vecs, coefs = [], []
+            for j in range(i):
+                if sc.At[i][j] != 0.0:
+                    vecs.append(KI[j])
+                    coefs.append(h * sc.At[i][j])
+                if sc.A[i][j] != 0.0:
+                    vecs.append(KE[j])
+                    coefs.append(h * sc.A[i][j])
+            if vecs:
+                Z = torch.empty_like(u)
+                ops.lincomb(Z, u, 1.0, vecs, coefs)
+            else:
+                Z = u
+            if sc.At[i][i] == 0.0:
+                y = Z
+                ki = cb_im.f(t + sc.ct[i] * h, y)
+            else:
+                shift = 1.0 / (h * sc.At[i][i])
+                y = imp.solve(t + sc.ct[i] * h, Z, shift, Y[i - 1] if i > 0 else u)
+                ki = torch.empty_like(u)
+                ops.lincomb(ki, None, 0.0, [y, Z], [shift, -shift])  # K^I_i = shift (Y_i - Z), not re-evaluated
+            Y.append(y)
+            KI.append(ki)
+            KE.append(cb_ex.f(t + sc.c[i] * h, y))
+        vecs, bw, ew = [], [], []
+        for j in range(s):
+            be = sc.bembed[j] if (adaptive and sc.bembed is not None) else sc.b[j]
+            if sc.bt[j] != 0.0 or be != sc.bt[j]:
+                vecs.append(KI[j])
+                bw.append(h * sc.bt[j])
+                ew.append(h * (be - sc.bt[j]))
+            if sc.b[j] != 0.0 or be != sc.b[j]:
+                vecs.append(KE[j])
+                bw.append(h * sc.b[j])
+                ew.append(h * (be - sc.b[j]))
+        unew = torch.empty_like(u)
+        sumsq = ops.complete(unew, u, vecs, bw, ew if adaptive else None, self.atol, self.rtol)
+        return unew, (Y,), sumsq
+
+    def _theta_attempt(self, cb, imp, t, h, u):
+        theta = 0.5 if self.kind == "cn" else 1.0
+        if theta < 1.0:
+            Z = torch.empty_like(u)
+            self.ops.lincomb(Z, u, 1.0, [cb.f(t, u)], [h * (1.0 - theta)])
+        else:
+            Z = u
+        unew = imp.solve(t + h, Z, 1.0 / (h * theta), u)
+        return unew, ([u, unew],), None
+
+    # -- adjoint ----------------------------------------------------------------------------------------------------
+    def adjoint_steps(self, cb_ex, cb_im, imp, nsteps, lam, mu, np_im):
+        for _ in range(nsteps):
+            if not self.traj:
+                raise Error(-30, "adjoint requested more steps than the trajectory holds")
+            t, h, stages = self.traj.pop()
+            if self.kind == "rk":
+                lam = self._rk_adjoint(cb_ex, t, h, stages[0], lam, mu)
+            elif self.kind == "arkimex":
+                lam = self._ark_adjoint(cb_ex, cb_im, imp, t, h, stages[0], lam, mu, np_im)
+            else:
+                lam = self._theta_adjoint(cb_im, imp, t, h, stages[0], lam, mu)
+        return lam
+
+    def _rk_adjoint(self, cb, t, h, Y, lam, mu):
+        sc, ops = self.scheme, self.ops
+        s = sc.s
+        vu = [None] * s   # J^T w of each stage;  lambda_{s,i} = coef[i] * vu[i] (the scaling is folded into later sums)
+        coef = [0.0] * s
+        for i in range(s - 1, -1, -1):
+            if sc.fsal and i == s - 1:
+                continue
+            later = [j for j in range(i + 1, s) if sc.A[j][i] != 0.0 and vu[j] is not None]
+            w = torch.empty_like(lam)
+            if sc.b[i] != 0.0:
+                ops.lincomb(w, lam, 1.0, [vu[j] for j in later], [sc.A[j][i] / sc.b[i] * coef[j] for j in later])
+                coef[i] = h * sc.b[i]
+            else:
+                ops.lincomb(w, None, 0.0, [vu[j] for j in later], [sc.A[j][i] * coef[j] for j in later])
+                coef[i] = h
+            vu[i], gp = cb.vjp(t + sc.c[i] * h, Y[i], w)
+            ops.multi_axpy(mu, gp, cb.sizes, coef[i])
+        live = [i for i in range(s) if vu[i] is not None]
+        lam_n = torch.empty_like(lam)
+        ops.lincomb(lam_n, lam, 1.0, [vu[i] for i in live], [coef[i] for i in live])
+        return lam_n
+
+    def _ark_adjoint(self, cb_ex, cb_im, imp, t, h, Y, lam, mu, np_im):
+        sc, ops = self.scheme, self.ops
+        s = sc.s
+        ls = [None] * s
+        mu_im = mu[:np_im] if np_im > 0 else None
+        mu_ex = mu[np_im:]
+        for i in range(s - 1, -1, -1):
+            later_t = [j for j in range(i + 1, s) if sc.At[j][i] != 0.0]
+            later_e = [j for j in range(i + 1, s) if sc.A[j][i] != 0.0]
+            om = torch.empty_like(lam)
+            ep = torch.empty_like(lam)
+            ops.lincomb(om, lam, sc.bt[i], [ls[j] for j in later_t], [sc.At[j][i] for j in later_t])
+            ops.lincomb(ep, lam, sc.b[i], [ls[j] for j in later_e], [sc.A[j][i] for j in later_e])
+            vu_e, gp_e = cb_ex.vjp(t + sc.c[i] * h, Y[i], ep)
+            ops.multi_axpy(mu_ex, gp_e, cb_ex.sizes, h)
+            vu_i, gp_i0 = cb_im.vjp(t + sc.ct[i] * h, Y[i], om)
+            r = torch.empty_like(lam)
+            if sc.At[i][i] == 0.0:
+                ops.lincomb(r, None, 0.0, [vu_i, vu_e], [h, h])
+                ls[i] = r
+                w_im = om
+            else:
+                ops.lincomb(r, None, 0.0, [vu_i, vu_e], [1.0 / sc.At[i][i], 1.0 / sc.At[i][i]])
+                ls[i] = imp.solve_transpose(t + sc.ct[i] * h, Y[i], 1.0 / (h * sc.At[i][i]), r)
+                w_im = torch.empty_like(lam)
+                ops.lincomb(w_im, om, 1.0, [ls[i]], [sc.At[i][i]])
+            if cb_im.nparams > 0:
+                if w_im is om:
+                    gp_i = gp_i0
+                else:  # the j = i term needs the post-solve lambda_{s,i}
+                    _, gp_i = cb_im.vjp(t + sc.ct[i] * h, Y[i], w_im, want_u=False)
+                ops.multi_axpy(mu_im, gp_i, cb_im.sizes, h)
+        lam_n = torch.empty_like(lam)
+        ops.lincomb(lam_n, lam, 1.0, ls, [1.0] * s)
+        return lam_n
+
+    def _theta_adjoint(self, cb, imp, t, h, Y, lam, mu):
+        ops = self.ops
+        theta = 0.5 if self.kind == "cn" else 1.0
+        u0, u1 = Y
+        shift = 1.0 / (h * theta)
+        rhs = torch.empty_like(lam)
+        ops.lincomb(rhs, lam, shift, [], [])
+        ls = imp.solve_transpose(t + h, u1, shift, rhs)
+        _, gp1 = cb.vjp(t + h, u1, ls, want_u=False)
+        ops.multi_axpy(mu, gp1, cb.sizes, h * theta)
+        if theta < 1.0:
+            vu0, gp0 = cb.vjp(t, u0, ls)
+            ops.multi_axpy(mu, gp0, cb.sizes, h * (1.0 - theta))
+            lam_n = torch.empty_like(lam)
+            ops.lincomb(lam_n, ls, 1.0, [vu0], [h * (1.0 - theta)])
+            return lam_n
+        return ls

@@ -1,0 +1,50 @@
+"""TEST DOUBLE (lives in tests/, never shipped): a torch-CPU stand-in for pnode_b200.device.DeviceOps so that the HOST
+logic of the engine (stage loops, step controller, adjoint recurrences, option handling) can be exercised by the
+`-m "not gpu"` suite.  The product only ever constructs the CUDA DeviceOps."""
+import torch
+
+
+class FakeOps:
+    def __init__(self, device=None, dtype=None):
+        self.launches = 0
+
+    def lincomb(self, out, base, base_coef, vecs, coefs):
+        acc = torch.zeros_like(out) if base is None else base_coef * base
+        for v, c in zip(vecs, coefs):
+            acc = acc + c * v.reshape(-1)
+        out.copy_(acc)
+        self.launches += 1
+        return out
+
+    def complete(self, unew, u, ks, bw, ew=None, atol=0.0, rtol=0.0):
+        acc = u.clone()
+        for k, b in zip(ks, bw):
+            acc = acc + b * k
+        unew.copy_(acc)
+        self.launches += 1
+        if ew is None:
+            return None
+        err = torch.zeros_like(u)
+        for k, e in zip(ks, ew):
+            err = err + e * k
+        x = (acc + err).double()
+        a = acc.double()
+        tol = atol + rtol * torch.maximum(a.abs(), x.abs())
+        return (((a - x) / tol) ** 2).sum().reshape(1)
+
+    def multi_axpy(self, mu, grads, sizes, coef):
+        off = 0
+        for g, n in zip(grads, sizes):
+            if g is not None:
+                mu[off:off + n] += coef * g.reshape(-1)
+            off += n
+        self.launches += 1
+
+
+def patch_cpu(monkeypatch):
+    """Route ODEPetsc onto FakeOps and lift the CUDA-only gate -- for host-logic tests only."""
+    import pnode_b200.petsc_adjoint as pa
+
+    monkeypatch.setattr(pa, "DeviceOps", FakeOps)
+    monkeypatch.setattr(pa, "_check_device", lambda t, what: None)
+    return pa

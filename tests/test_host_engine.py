@@ -1,0 +1,164 @@
+"""HOST logic of the product (ODEPetsc option handling, stage loops, step controller, adjoint recurrences) against the
+oracle, with the device kernels replaced by the torch-CPU test double of tests/_fake_ops.py.  The GPU parity tests
+(test_gpu_*.py) run the same comparisons through the real C-ABI kernels."""
+import copy
+
+import pytest
+import torch
+
+from oracle import OracleODEPetsc
+from pnode_b200.options import Options
+from _fake_ops import patch_cpu
+from _problems import (PETSC_ARGS, ROBER_STEPS, ROBER_T, Rober, RoberEX, RoberIM, SpiralFunc, TimeMLP, rel_err,
+                       rober_truth, spiral_inputs)
+
+
+def _both(monkeypatch, argv, setup_kw, funcs, u0, t, gout, step):
+    pa = patch_cpu(monkeypatch)
+    Options.insert_args(argv)
+    res = []
+    for make in (lambda: OracleODEPetsc(argv), lambda: pa.ODEPetsc()):
+        fs = [copy.deepcopy(f) for f in funcs]
+        kw = dict(setup_kw)
+        if len(fs) == 2:
+            kw["func2"] = fs[1]
+        ode = make()
+        ode.setupTS(u0, fs[0], step_size=step, enable_adjoint=True, **kw)
+        y0 = u0.clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t)
+        (out * gout).sum().backward()
+        grads = [p.grad.clone() for f in fs for p in f.parameters()]
+        res.append((out.detach(), y0.grad.clone(), grads, ode))
+    return res
+
+
+def _assert_close(a, b, tol):
+    assert rel_err(a[0], b[0]) < tol
+    assert rel_err(a[1], b[1]) < tol
+    assert len(a[2]) == len(b[2])
+    for x, y in zip(a[2], b[2]):
+        assert rel_err(x, y) < tol
+
+
+@pytest.mark.parametrize("method", ["euler", "rk2", "bosh3", "rk4", "dopri5", "midpoint"])
+def test_fixed_step_rk(monkeypatch, method):
+    u0, t, gout = spiral_inputs(20)
+    o, p = _both(monkeypatch, ["-ts_adapt_type", "none"], dict(method=method), [SpiralFunc(bias_std=0.1)], u0, t, gout, 0.025)
+    _assert_close(p, o, 1e-13)
+    assert [a[:3] for a in p[3]._loop.attempts] == [a[:3] for a in o[3].ts.log]
+
+
+def test_adaptive_dopri5_identical_step_sequence(monkeypatch):
+    func = TimeMLP(d=6, hidden=16)
+    g = torch.Generator().manual_seed(5)
+    u0 = torch.randn(50, 6, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.4, 1.0], dtype=torch.float64)
+    gout = torch.randn(3, 50, 6, generator=g, dtype=torch.float64)
+    o, p = _both(monkeypatch, ["-ts_rtol", "1e-6", "-ts_atol", "1e-6"], dict(method="dopri5"), [func], u0, t, gout, 0.3)
+    log_o, log_p = o[3].ts.log, p[3]._loop.attempts
+    assert len(log_o) == len(log_p) and len(log_o) > 4
+    assert any(not a[2] for a in log_o), "the case must contain at least one rejected attempt"
+    for a, b in zip(log_o, log_p):
+        assert a[2] == b[2]
+        assert a[0] == pytest.approx(b[0], rel=1e-12, abs=1e-15) and a[1] == pytest.approx(b[1], rel=1e-12)
+        assert a[3] == pytest.approx(b[3], rel=1e-9)
+    _assert_close(p, o, 1e-12)
+
+
+def test_adaptive_bosh3_and_step_restore_after_span_point(monkeypatch):
+    func = TimeMLP(d=4, hidden=8)
+    g = torch.Generator().manual_seed(6)
+    u0 = torch.randn(10, 4, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.25, 0.5, 0.75], dtype=torch.float64)
+    gout = torch.randn(4, 10, 4, generator=g, dtype=torch.float64)
+    o, p = _both(monkeypatch, [], dict(method="bosh3"), [func], u0, t, gout, 0.1)
+    assert [(a[2]) for a in o[3].ts.log] == [(a[2]) for a in p[3]._loop.attempts]
+    _assert_close(p, o, 1e-12)
+    # fixed step that does not divide the output spacing: 0.1, then 0.15 left < 2h => halved to 0.075 + 0.075
+    # (MATCHSTEP), then the un-shortened 0.1 is restored after the span point
+    o, p = _both(monkeypatch, ["-ts_adapt_type", "none"], dict(method="rk4"), [func], u0, t, gout, 0.1)
+    hs = [a[1] for a in p[3]._loop.attempts]
+    assert hs[:4] == pytest.approx([0.1, 0.075, 0.075, 0.1])
+    assert [a[:2] for a in o[3].ts.log] == pytest.approx([a[:2] for a in p[3]._loop.attempts])
+    _assert_close(p, o, 1e-13)
+
+
+def test_rober_goldens_through_product_host_logic(monkeypatch):
+    true_y = rober_truth()
+    cases = [(dict(method="cn", implicit_form=True), [Rober()], 1.8492e-6),
+             (dict(method="imex", implicit_form=True, imex_form=True), [RoberIM(), RoberEX()], 3.1138e-6),
+             (dict(method="rk3"), [Rober()], 1.8495e-6)]
+    for kw, funcs, golden in cases:
+        gout = torch.sign(torch.ones_like(true_y))
+        o, p = _both(monkeypatch, PETSC_ARGS, kw, funcs, true_y[0], ROBER_T, gout, ROBER_STEPS)
+        loss = torch.mean(torch.abs(p[0] - true_y)).item()
+        assert loss == pytest.approx(golden, rel=2e-4)
+        _assert_close(p, o, 1e-9)
+        Options.clear_all()
+
+
+@pytest.mark.parametrize("name", ["l2", "3", "4", "5", "ars122"])
+def test_imex_batched_linear_solver(monkeypatch, name):
+    from test_oracle_adjoint import LinearIM
+
+    N, B = 8, 6
+    g = torch.Generator().manual_seed(7)
+    u0 = torch.randn(B, N, generator=g, dtype=torch.float64) * 0.5
+    t = torch.tensor([0.0, 0.2, 0.4], dtype=torch.float64)
+    gout = torch.randn(3, B, N, generator=g, dtype=torch.float64)
+    argv = ["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_arkimex_type", name]
+    o, p = _both(monkeypatch, argv, dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch"),
+                 [LinearIM(N), TimeMLP(d=N, hidden=12)], u0, t, gout, 0.1)
+    _assert_close(p, o, 1e-11)
+
+
+def test_options_override_method_and_resetup_semantics(monkeypatch):
+    pa = patch_cpu(monkeypatch)
+    u0, t, gout = spiral_inputs(5)
+    f = SpiralFunc()
+    Options.insert_args(["-ts_adapt_type", "none", "-ts_type", "rk", "-ts_rk_type", "4"])
+    ode = pa.ODEPetsc()
+    ode.setupTS(u0, f, step_size=0.025, method="euler")  # command line wins (petsc_adjoint.py:775)
+    assert ode._scheme.name == "4"
+    Options.clear_all()
+    Options.insert_args(["-ts_adapt_type", "none"])
+    ode = pa.ODEPetsc()
+    ode.setupTS(u0, f, step_size=0.025, method="rk4")
+    assert ode._scheme.name == "4"
+    ode.setupTS(u0, f, step_size=0.0125, method="euler", enable_adjoint=False)  # same meta: method NOT re-applied (C.3)
+    assert ode._scheme.name == "4" and ode.step_size == 0.0125 and not ode.enable_adjoint
+    ode.setupTS(u0[:3], f, step_size=0.025, method="euler")  # shape changed: method applied
+    assert ode._scheme.name == "1fe"
+    ode.setupTS(u0, f, method="no_such_method")  # silently the TS default (C.1)
+    assert ode._scheme.name == "3bs"
+    with pytest.raises(ValueError):
+        ode.setupTS(u0, f, imex_form=True)
+    ode2 = pa.ODEPetsc()
+    ode2.setupTS(u0, lambda t, y: y, method="rk4")
+    with pytest.raises(ValueError):
+        ode2.odeint_adjoint(u0, t)  # func must be an nn.Module (petsc_adjoint.py:896-897)
+
+
+def test_missed_output_point_raises(monkeypatch):
+    pa = patch_cpu(monkeypatch)
+    Options.insert_args(["-ts_adapt_type", "none"])
+    u0, _, _ = spiral_inputs(3)
+    ode = pa.ODEPetsc()
+    # per-step list that walks past the second output time without landing near it
+    ode.setupTS(u0, SpiralFunc(), step_size=[0.1, 0.1, 0.1], method="euler")
+    t = torch.tensor([0.0, 0.1, 0.25 + 1e-4, 0.3], dtype=torch.float64)
+    # the list entry set in PostStep overrides the MATCHSTEP clamp (petsc_adjoint.py:523-525), the run steps over
+    # t=0.2501 and the reference's sanity check fires (petsc_adjoint.py:867-868)
+    with pytest.raises(Exception, match="fails to step on all the specified points"):
+        ode.odeint(u0, t)
+
+
+def test_single_time_returns_leading_axis_one(monkeypatch):
+    pa = patch_cpu(monkeypatch)
+    Options.insert_args(["-ts_adapt_type", "none"])
+    u0, _, _ = spiral_inputs(4)
+    ode = pa.ODEPetsc()
+    ode.setupTS(u0, SpiralFunc(), step_size=0.05, method="rk4", enable_adjoint=False)
+    out = ode.odeint(u0, torch.tensor([0.2], dtype=torch.float64))
+    assert out.shape == (1, 4, 1, 2)
+    assert len(ode._loop.attempts) == 4 and ode._loop.attempts[0][0] == 0.0
