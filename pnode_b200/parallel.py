@@ -1,0 +1,53 @@
+"""Batch-sharded data parallelism (one process per GPU, torch.distributed over NCCL / NVLink).
+
+The reference is single-process (`ODEPetsc.comm = PETSc.COMM_SELF`, pnode/petsc_adjoint.py:367); trajectories are
+independent, so the forward and adjoint sweeps shard by batch with NO data-path collective.  Only two exchanges exist
+(SURVEY.md section 8e):
+  1. mu (parameter gradient): one all-reduce(sum) of [np] scalars per backward, because the loss sums over the global batch;
+  2. adaptive runs: one scalar all-reduce(sum) of the weighted squared error per step attempt, BEFORE accept/reject, so
+     that every rank takes the identical decision and the identical next step (the reference's single shared step size;
+     the WRMS norm is over the whole, i.e. global, state vector).
+Usage:  ode = ODEPetsc(); ode.comm = BatchComm()   # after torch.distributed.init_process_group(...)
+"""
+import torch
+import torch.distributed as dist
+
+
+class BatchComm:
+    def __init__(self, group=None):
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("BatchComm needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.collectives = 0
+        self._count_cache = {}
+
+    def allreduce_sum(self, tensor):
+        if self.world > 1:
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+            self.collectives += 1
+        return tensor
+
+    def allreduce_scalar(self, tensor):
+        return self.allreduce_sum(tensor)
+
+    def global_count(self, n_local):
+        """Global state length N of the WRMS norm (ranks may hold ragged shards)."""
+        if self.world == 1:
+            return n_local
+        if n_local not in self._count_cache:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else "cpu"
+            c = torch.tensor([n_local], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.group)
+            self._count_cache[n_local] = int(c.item())
+        return self._count_cache[n_local]
+
+
+def shard_batch(tensor, rank, world, dim=0):
+    """Contiguous batch slice of `tensor` owned by `rank` (ragged when world does not divide the batch)."""
+    n = tensor.shape[dim]
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    length = base + (1 if rank < rem else 0)
+    return tensor.narrow(dim, start, length)

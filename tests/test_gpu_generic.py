@@ -1,0 +1,90 @@
+"""GPU parity of the generic path (torch evaluates f / VJPs on the GPU, csrc/vecops.cu does the TS arithmetic) against
+the oracle: the reference's own ROBER known answers, adaptive dopri5 step sequences, IMEX with the batched solver."""
+import copy
+
+import pytest
+import torch
+
+from oracle import OracleODEPetsc
+from pnode_b200.options import Options
+from _problems import (PETSC_ARGS, ROBER_STEPS, ROBER_T, Rober, RoberEX, RoberIM, TimeMLP, rel_err, rober_truth)
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(make_ode, funcs, kw, u0, t, gout, step, dev):
+    fs = [copy.deepcopy(f).to(dev) for f in funcs]
+    kw = dict(kw)
+    if len(fs) == 2:
+        kw["func2"] = fs[1]
+    ode = make_ode()
+    ode.setupTS(u0.to(dev), fs[0], step_size=step, enable_adjoint=True, **kw)
+    y0 = u0.to(dev).clone().requires_grad_(True)
+    out = ode.odeint_adjoint(y0, t.to(dev))
+    (out * gout.to(dev)).sum().backward()
+    return out.detach(), y0.grad, [p.grad for f in fs for p in f.parameters()], ode
+
+
+def _pair(argv, funcs, kw, u0, t, gout, step):
+    from pnode import petsc_adjoint
+
+    Options.clear_all()
+    Options.insert_args(argv)
+    o = _run(lambda: OracleODEPetsc(argv), funcs, kw, u0, t, gout, step, "cpu")
+    p = _run(lambda: petsc_adjoint.ODEPetsc(), funcs, kw, u0, t, gout, step, "cuda")
+    return o, p
+
+
+def _compare(p, o, tol):
+    assert rel_err(p[0], o[0]) < tol
+    assert rel_err(p[1], o[1]) < tol
+    assert len(p[2]) == len(o[2])
+    for a, b in zip(p[2], o[2]):
+        assert rel_err(a, b) < tol
+
+
+def test_reference_rober_known_answers_on_gpu():
+    """The reference's three tests (tests/test_pnode.py:133-201), run through the drop-in on the GPU."""
+    true_y = rober_truth()
+    gout = torch.ones_like(true_y)
+    cases = [(dict(method="cn", implicit_form=True), [Rober()], 1.85e-6, 3.36e-6, 1e-6),
+             (dict(method="imex", implicit_form=True, imex_form=True), [RoberIM(), RoberEX()], 3.11e-6, 5.65e-6, 3e-6),
+             (dict(method="rk3"), [Rober()], 1.85e-6, 3.21e-6, 1e-6)]
+    for kw, funcs, g_loss, g_std, tol in cases:
+        o, p = _pair(PETSC_ARGS, funcs, kw, true_y[0], ROBER_T, gout, ROBER_STEPS)
+        err = torch.abs(p[0].cpu() - true_y)
+        assert err.mean().item() == pytest.approx(g_loss, abs=tol)
+        assert err.std().item() == pytest.approx(g_std, abs=tol)
+        _compare(p, o, 1e-8)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_adaptive_dopri5_identical_accepted_steps(dtype, tol):
+    func = TimeMLP(d=6, hidden=16, dtype=dtype)
+    g = torch.Generator().manual_seed(5)
+    u0 = torch.randn(1000, 6, generator=g, dtype=torch.float64).to(dtype)
+    t = torch.tensor([0.0, 0.4, 1.0], dtype=torch.float64)
+    gout = torch.randn(3, 1000, 6, generator=g, dtype=torch.float64).to(dtype)
+    o, p = _pair(["-ts_rtol", "1e-5", "-ts_atol", "1e-5"], [func], dict(method="dopri5"), u0, t, gout, 0.3)
+    lo, lp = o[3].ts.log, p[3]._loop.attempts
+    assert [a[2] for a in lo] == [a[2] for a in lp]  # same accept / reject pattern
+    assert any(not a[2] for a in lo)
+    htol = 1e-9 if dtype == torch.float64 else 1e-3
+    for a, b in zip(lo, lp):
+        assert a[1] == pytest.approx(b[1], rel=htol)
+    _compare(p, o, tol)
+
+
+@pytest.mark.parametrize("name", ["3", "l2", "4"])
+def test_imex_torch_solver_on_gpu(name):
+    from test_oracle_adjoint import LinearIM
+
+    N, B = 16, 32
+    g = torch.Generator().manual_seed(7)
+    u0 = torch.randn(B, N, generator=g, dtype=torch.float64) * 0.5
+    t = torch.tensor([0.0, 0.2, 0.4], dtype=torch.float64)
+    gout = torch.randn(3, B, N, generator=g, dtype=torch.float64)
+    argv = ["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_arkimex_type", name]
+    o, p = _pair(argv, [LinearIM(N), TimeMLP(d=N, hidden=24)],
+                 dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch"), u0, t, gout, 0.1)
+    _compare(p, o, 1e-10)

@@ -1,0 +1,116 @@
+"""GPU parity of the generic-path vector kernels (through the C ABI) against the oracle arithmetic on the same inputs."""
+import math
+
+import pytest
+import torch
+
+from oracle import wrms_norm
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops(dtype):
+    from pnode_b200.device import DeviceOps
+
+    return DeviceOps(torch.device("cuda:0"), dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n", [0, 1, 3, 40, 1023, 4096 + 5, 2 * 1024 * 1024 + 1])
+def test_lincomb(dtype, n):
+    g = torch.Generator().manual_seed(n + 1)
+    ops = _ops(dtype)
+    for nterms in (0, 1, 6, 16, 19):
+        vecs = [torch.randn(n, generator=g, dtype=torch.float64) for _ in range(nterms)]
+        coefs = [float(c) for c in torch.randn(nterms, generator=g, dtype=torch.float64)]
+        base = torch.randn(n, generator=g, dtype=torch.float64)
+        ref = 0.75 * base.to(dtype).double()
+        for v, c in zip(vecs, coefs):
+            ref = ref + float(torch.tensor(c, dtype=dtype)) * v.to(dtype).double()
+        out = torch.empty(n, dtype=dtype, device="cuda")
+        ops.lincomb(out, base.to(dtype).cuda(), 0.75, [v.to(dtype).cuda() for v in vecs], coefs)
+        tol = 1e-14 if dtype == torch.float64 else 2e-6
+        assert torch.allclose(out.cpu().double(), ref, rtol=tol, atol=tol * 10)
+        out2 = torch.empty(n, dtype=dtype, device="cuda")
+        ops.lincomb(out2, None, 0.0, [v.to(dtype).cuda() for v in vecs], coefs)
+        assert torch.allclose(out2.cpu().double(), ref - 0.75 * base.to(dtype).double(), rtol=tol, atol=tol * 10)
+
+
+def test_lincomb_unaligned_views_and_aliasing():
+    ops = _ops(torch.float64)
+    big = torch.randn(4099, dtype=torch.float64, device="cuda")
+    a, b = big[1:2050], big[2050:4099]  # 8-byte but not 16-byte aligned
+    ref = a.cpu() + 2.0 * b.cpu()
+    ops.lincomb(a, a, 1.0, [b], [2.0])  # in place
+    assert torch.allclose(a.cpu(), ref, rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n", [7, 7000, 3 * 1024 * 1024 + 3])
+def test_complete_with_weighted_norm(dtype, n):
+    g = torch.Generator().manual_seed(n)
+    ops = _ops(dtype)
+    u = torch.randn(n, generator=g, dtype=torch.float64).to(dtype)
+    ks = [torch.randn(n, generator=g, dtype=torch.float64).to(dtype) for _ in range(7)]
+    bw = [0.05 * (j + 1) for j in range(7)]
+    ew = [1e-4 * (-1) ** j * (j + 1) for j in range(7)]
+    unew_ref = u.double()
+    err = torch.zeros(n, dtype=torch.float64)
+    for k, b, e in zip(ks, bw, ew):
+        unew_ref = unew_ref + float(torch.tensor(b, dtype=dtype)) * k.double()
+        err = err + float(torch.tensor(e, dtype=dtype)) * k.double()
+    unew = torch.empty(n, dtype=dtype, device="cuda")
+    for rep in range(3):  # the work buffer (ticket) must be restored by the kernel
+        sumsq = ops.complete(unew, u.cuda(), [k.cuda() for k in ks], bw, ew, 1e-4, 1e-3)
+        got = math.sqrt(float(sumsq.item()) / n)
+    tol = 1e-13 if dtype == torch.float64 else 3e-6
+    assert torch.allclose(unew.cpu().double(), unew_ref, rtol=tol, atol=tol)
+    ref = wrms_norm(unew_ref, unew_ref + err, 1e-4, 1e-3)
+    assert got == pytest.approx(ref, rel=1e-9 if dtype == torch.float64 else 2e-3)
+    # plain completion
+    ops.complete(unew, u.cuda(), [k.cuda() for k in ks], bw)
+    assert torch.allclose(unew.cpu().double(), unew_ref, rtol=tol, atol=tol)
+    # bit-reproducible reduction
+    s1 = ops.complete(unew, u.cuda(), [k.cuda() for k in ks], bw, ew, 1e-4, 1e-3).clone()
+    s2 = ops.complete(unew, u.cuda(), [k.cuda() for k in ks], bw, ew, 1e-4, 1e-3).clone()
+    assert torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_multi_axpy(dtype):
+    g = torch.Generator().manual_seed(11)
+    ops = _ops(dtype)
+    sizes = [100, 50, 0, 1, 7, 3200 * 33] + [5] * 40
+    grads = [None if i == 4 else torch.randn(s, generator=g, dtype=torch.float64).to(dtype) for i, s in enumerate(sizes)]
+    mu0 = torch.randn(sum(sizes), generator=g, dtype=torch.float64).to(dtype)
+    ref = mu0.double().clone()
+    off = 0
+    for gr, s in zip(grads, sizes):
+        if gr is not None:
+            ref[off:off + s] += float(torch.tensor(0.3, dtype=dtype)) * gr.double()
+        off += s
+    mu = mu0.cuda()
+    ops.multi_axpy(mu, [None if x is None else x.cuda() for x in grads], sizes, 0.3)
+    tol = 1e-14 if dtype == torch.float64 else 2e-6
+    assert torch.allclose(mu.cpu().double(), ref, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 4e-16), (torch.float32, 3e-7)])
+def test_kernel_tanh_accuracy(dtype, tol):
+    import ctypes as C
+
+    from pnode_b200 import _lib
+
+    lib = _lib.load()
+    x = torch.cat((torch.linspace(-25, 25, 200001, dtype=torch.float64), torch.logspace(-300, 1, 4001, dtype=torch.float64),
+                   -torch.logspace(-30, 1, 4001, dtype=torch.float64), torch.tensor([0.0, 1e3, -1e3, 19.9, 20.1])))
+    xd = x.to(dtype).cuda()
+    out = torch.empty_like(xd)
+    _lib.check(lib.pnode_tanh_probe(xd.data_ptr(), out.data_ptr(), xd.numel(), 0 if dtype == torch.float32 else 1,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    ref = torch.tanh(xd.double().cpu())
+    err = (out.cpu().double() - ref).abs()
+    assert float(err.max()) < tol  # absolute error
+    if dtype == torch.float64:  # and a few ulp relative, also near zero (no cancellation)
+        rel = err / ref.abs().clamp_min(1e-300)
+        assert float(rel[ref != 0].max()) < 1e-15
