@@ -15,7 +15,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -138,28 +137,31 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
-        self._thr = None
-
-    def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for ln in out.strip().splitlines():
-                    self.samples.append([x.strip() for x in ln.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self._proc = None
 
     def __enter__(self):
-        self._thr = threading.Thread(target=self._loop, daemon=True)
-        self._thr.start()
+        # one long-lived sampler process (100 ms period) for the whole timed region -- B200_PROFILING.md "clocks line"
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
+        time.sleep(0.25)
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._thr.join(timeout=6)
+        if self._proc is None:
+            return
+        time.sleep(0.15)
+        self._proc.terminate()
+        try:
+            out, _ = self._proc.communicate(timeout=5)
+        except Exception:
+            self._proc.kill()
+            out = ""
+        for ln in (out or "").strip().splitlines():
+            self.samples.append([x.strip() for x in ln.split(",")])
 
     def summary(self):
         sm, mx, reasons = [], [], set()

@@ -212,6 +212,10 @@ class OracleTS:
         adaptive = self.adaptive()
         k_fsal = None
         tend_all = span[-1] if span is not None else max_time
+        # TSSolve, before the first step: with MATCHSTEP the initial step may not overshoot the first target
+        first = span[1] if span is not None and len(span) > 1 else max_time
+        if h >= first - t or _close(h, first - t, TSPAN_ABSTOL):
+            h = first - t
         while t < tend_all and not _close(t, tend_all, TSPAN_ABSTOL):
             prev_accepted = True
             rejections = 0

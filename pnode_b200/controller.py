@@ -70,6 +70,10 @@ class TimeLoop:
         self._rejections = 0
         self._dt_span_cached = 0.0
         self.last_out_slot = -1
+        # [PETSc] TSSolve, before the first step: MATCHSTEP keeps the initial step from overshooting the first target
+        first = self.span[1] if self.span is not None else self.t_end
+        if self.h >= first - self.t or abs(self.h - (first - self.t)) <= SPAN_ABSTOL:
+            self.h = first - self.t
         self.last_h = self.h
         self.attempts = []  # (t, h, accepted, enorm)
 

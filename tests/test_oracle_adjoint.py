@@ -69,7 +69,7 @@ class LinearIM(nn.Module):
 
     def matrix(self):
         N = self.N
-        eye = torch.eye(N, dtype=torch.float64)
+        eye = torch.eye(N, dtype=torch.float64, device=self.w.device)
         return self.w[0] * torch.roll(eye, -1, 1) + self.w[1] * eye + self.w[2] * torch.roll(eye, 1, 1)
 
     def forward(self, t, y):
