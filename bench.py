@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--ntraj", type=int, default=NTRAJ, help="trajectories per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 15, help="trajectories of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="trajectories of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -351,9 +351,9 @@ def run_native(args):
                     "each in fp64), which is what saturates the pipe"}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rate, dt = cpu_port_rate(args.cpu_sample, dtype)
+            rate, dt = cpu_port_rate(args.cpu_sample, dtype, reps=3)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d of %d trajectories, one fwd+adjoint pass (%.1f s), oracle = "
+                                    "sample": "%d of %d trajectories, 1 warm-up + 3 timed fwd+adjoint passes (%.1f s each), oracle = "
                                               "reference-structured CPU restatement (PETSc unavailable)" %
                                               (args.cpu_sample, ntraj, dt)}
         print(json.dumps(line), flush=True)

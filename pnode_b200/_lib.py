@@ -6,7 +6,7 @@ import os
 from .errors import Error
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpnode_b200.so")
+LIB_PATH = os.environ.get("PNODE_B200_LIB") or os.path.join(_HERE, "csrc", "libpnode_b200.so")  # env: tuning builds only
 
 F32, F64 = 0, 1
 MAX_TERMS, MAX_STAGES, MAX_SRCS = 16, 7, 32

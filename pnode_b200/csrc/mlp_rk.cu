@@ -7,71 +7,158 @@
 // does every step and stage of the forward sweep and ONE launch does the whole discrete adjoint.
 //
 // B200 mapping
-//  * forward: one trajectory per thread, weights (252 scalars) broadcast from shared memory, the s stage slopes in
-//    registers, stage values Y_i streamed to HBM as [step][stage][dim][traj] (coalesced, 8 scalars per
-//    trajectory-step for RK4) -- the "stage checkpoints in HBM" that replace -ts_trajectory_type memory.
-//  * adjoint: one trajectory per thread for the lambda recurrence and the VJP w.r.t. the state; the parameter gradient
-//    (a [batch x 5] x [batch x H] outer-product sum) is reduced without atomics or shuffles: each warp parks tanh(z_j)
-//    and s_j of its 32 trajectories in a warp-private shared-memory tile, then re-reads the tile TRANSPOSED (lane = hidden
-//    unit j) so that every lane accumulates "its" five parameter gradients over the 32 trajectories in registers.  Only
-//    __syncwarp() separates the two phases, warps never wait for each other, and the per-lane accumulators live across
-//    all stages, steps and tiles of the persistent kernel.  Per-block partials are combined in a fixed order by the last
-//    block (bit-reproducible mu).
-//  * the kernels are bound by the FP64 / FP32+MUFU instruction issue rate of tanh (arithmetic intensity ~80 flop/B,
-//    SURVEY.md section 8d), not by HBM: grids are persistent, sized SMs x resident CTAs.
+//  * forward: TPT trajectories per thread, weights (252 scalars, packed per hidden unit) broadcast from shared memory,
+//    the s stage slopes in registers, stage values Y_i streamed to HBM as [step][stage][dim][traj] (coalesced; 8 scalars
+//    per trajectory-step for RK4) -- the "stage checkpoints in HBM" that replace -ts_trajectory_type memory.
+//  * adjoint: lambda recurrence and state VJP with TPT trajectories per thread; the parameter gradient (a
+//    [batch x 5] x [batch x H] outer-product sum) is reduced without atomics or shuffles: each warp parks tanh(z_j) and s_j
+//    of its 32*TPT trajectories in a warp-private shared-memory tile, then re-reads the tile TRANSPOSED (lane = hidden
+//    unit j, 16-byte loads along the trajectory axis) so that every lane accumulates "its" five parameter gradients in
+//    registers.  Only __syncwarp() separates the phases, warps never wait for each other, the per-lane accumulators
+//    (double) live across all stages, steps and tiles of the persistent kernel.  Per-block partials are combined in a
+//    fixed order by the last block (bit-reproducible mu).
+//  * both kernels are bound by instruction issue of tanh (fp64: FP64 pipe; fp32: MUFU/issue), not by HBM (arithmetic
+//    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 64-entry 2^(j/64) table in
+//    SMEM + degree-6 polynomial + cubic reciprocal refinement = 17 FP64 ops; fp32: one MUFU.EX2 per unit and ONE shared
+//    MUFU.RCP per four units (product trick).  Grids are persistent: SMs x resident CTAs.
 #include "common.cuh"
 
 namespace pnode {
 
 // ---------------------------------------------------------------------------------------------------------------------
-// tanh, accurate to a few ulp in fp64 and ~1.5e-7 absolute in fp32, branch-free
+// tanh
 
-__device__ __forceinline__ float tanh_acc(float x) {
-    // 1 - 2/(1 + e^{2x}):  one MUFU.EX2 + one MUFU.RCP
-    float e, r;
-    float a = x * 2.8853900817779268f;  // 2*log2(e)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
-    float d = 1.0f + e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-    return fmaf(-2.0f, r, 1.0f);
+constexpr int EXP_TAB = 64;  // 2^(j/64), j = 0..63
+
+// fp64: tanh(x) = em1 / (em1 + 2), em1 = e^{2x} - 1 without cancellation.
+//   2x = k ln2/64 + r, |r| <= ln2/128;  e^{2x} = 2^(k>>6) * T[k&63] * (1 + P(r)),  P(r) = e^r - 1 (degree 6, trunc. 5e-18 rel.)
+//   em1 = (s - 1) + s P with s = T 2^(k>>6): exact for k == 0, so small |x| keeps full relative accuracy.
+__device__ __forceinline__ double tanh_acc(double x, const double *__restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52
+    double kf = fma(x, 184.6649652337873, MAGIC);     // 128 / ln2
+    const int k = __double2loint(kf);
+    kf -= MAGIC;
+    double rh = fma(kf, -0.00541521234663378, x);     // ln2/128 hi (0x1.62e42fee00000p-8: 21 trailing zero bits)
+    rh = fma(kf, -1.4907929134926466e-12, rh);        // ln2/128 lo ;  r = 2 rh
+    // P(r), r = 2 rh:  r + r^2/2 + ... + r^6/720 = rh (2 + rh (2 + rh (4/3 + rh (2/3 + rh (4/15 + rh 4/45)))))
+    double p = fma(rh, 0.08888888888888889, 0.26666666666666666);
+    p = fma(p, rh, 0.6666666666666666);
+    p = fma(p, rh, 1.3333333333333333);
+    p = fma(p, rh, 2.0);
+    p = fma(p, rh, 2.0);
+    p *= rh;
+    const double T = tab[k & (EXP_TAB - 1)];
+    const double s = __hiloint2double(__double2hiint(T) + ((k >> 6) << 20), __double2loint(T));
+    const double em1 = fma(s, p, s - 1.0);
+    const double d = em1 + 2.0;
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    const double e0 = fma(-d, r0, 1.0);
+    const double rc = fma(r0, fma(e0, e0, e0), r0);   // cubic refinement: error e0^3
+    double t = em1 * rc;
+    // |x| >= 20 (or non-finite intermediate): tanh rounds to +-1
+    const int hx = __double2hiint(x);
+    const bool big = (hx & 0x7fffffff) >= 0x40340000;
+    const int thi = big ? ((hx & 0x80000000) | 0x3ff00000) : __double2hiint(t);
+    const int tlo = big ? 0 : __double2loint(t);
+    return __hiloint2double(thi, tlo);
 }
 
-__device__ __forceinline__ double tanh_acc(double x) {
-    // tanh|x| = em1 / (em1 + 2),  em1 = e^{2|x|} - 1 evaluated without cancellation
-    double ax = fmin(fabs(x), 20.0);  // tanh(20) rounds to 1
-    double y = ax + ax;
-    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
-    double nf = fma(y, 1.4426950408889634, MAGIC);
-    int n = __double2loint(nf);
-    nf -= MAGIC;
-    double r = fma(nf, -6.93147180369123816490e-01, y);
-    r = fma(nf, -1.90821492927058770002e-10, r);
-    // q(r) = (e^r - 1)/r, |r| <= ln2/2, Taylor through r^12 (truncation 4e-18)
-    double q = 1.6059043836821613e-10;   // 1/13!
-    q = fma(q, r, 2.08767569878681e-09);   // 1/12!
-    q = fma(q, r, 2.505210838544172e-08);  // 1/11!
-    q = fma(q, r, 2.755731922398589e-07);  // 1/10!
-    q = fma(q, r, 2.7557319223985893e-06); // 1/9!
-    q = fma(q, r, 2.48015873015873e-05);   // 1/8!
-    q = fma(q, r, 1.984126984126984e-04);  // 1/7!
-    q = fma(q, r, 1.388888888888889e-03);  // 1/6!
-    q = fma(q, r, 8.333333333333333e-03);  // 1/5!
-    q = fma(q, r, 4.1666666666666664e-02); // 1/4!
-    q = fma(q, r, 1.6666666666666666e-01); // 1/3!
-    q = fma(q, r, 0.5);
-    q = fma(q, r, 1.0);
-    double rq = r * q;  // e^r - 1
-    double p = 1.0 + rq;
-    double e = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));  // p * 2^n, 0 <= n <= 58
-    double em1 = (n == 0) ? rq : e - 1.0;
-    double d = em1 + 2.0;
-    double rc;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));
-    rc = fma(fma(-d, rc, 1.0), rc, rc);
-    rc = fma(fma(-d, rc, 1.0), rc, rc);
-    double t = em1 * rc;
-    t = fma(fma(-d, t, em1), rc, t);
-    return copysign(t, x);
+__device__ __forceinline__ float ex2_approx(float a) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    return e;
+}
+__device__ __forceinline__ float rcp_approx(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+}
+
+// fp32: tanh(z) = 1 - 2/(1 + 2^(2 log2e z)); the argument is clamped to +-30 (tanh == +-1 in fp32 beyond) so that products
+// of up to four denominators stay finite.
+__device__ __forceinline__ float tanh_den(float z) {
+    float a = fminf(fmaxf(z * 2.8853900817779268f, -30.0f), 30.0f);
+    return 1.0f + ex2_approx(a);
+}
+__device__ __forceinline__ float tanh_acc(float z, const float *) { return fmaf(-2.0f, rcp_approx(tanh_den(z)), 1.0f); }
+
+// G tanh's at once.  fp32: one reciprocal for the whole group; fp64: independent.
+template <int G>
+__device__ __forceinline__ void tanh_group(const float (&z)[G], float (&a)[G], const float *) {
+    float d[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) d[g] = tanh_den(z[g]);
+    if (G == 4) {
+        const float p01 = d[0] * d[1], p23 = d[2] * d[3];
+        const float r = rcp_approx(p01 * p23);
+        const float r01 = r * p23, r23 = r * p01;
+        a[0] = fmaf(-2.0f, r01 * d[1], 1.0f);
+        a[1] = fmaf(-2.0f, r01 * d[0], 1.0f);
+        a[2 % G] = fmaf(-2.0f, r23 * d[3 % G], 1.0f);
+        a[3 % G] = fmaf(-2.0f, r23 * d[2 % G], 1.0f);
+    } else if (G == 2) {
+        const float r = rcp_approx(d[0] * d[1 % G]);
+        a[0] = fmaf(-2.0f, r * d[1 % G], 1.0f);
+        a[1 % G] = fmaf(-2.0f, r * d[0], 1.0f);
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) a[g] = fmaf(-2.0f, rcp_approx(d[g]), 1.0f);
+    }
+}
+// fp64 group: the same arithmetic as tanh_acc(double), written step-by-step ACROSS the group so that the G dependent
+// chains are interleaved in program order (ptxas keeps them interleaved; per-element inlining left Horner chains
+// back-to-back and the warps stalled on the FP64 pipe latency -- profiles/r1 "stall_wait").
+template <int G>
+__device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G], const double *__restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;
+    double kf[G], rh[G], p[G], s[G], em1[G], d[G], r0[G], e0[G];
+    int k[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) kf[g] = fma(z[g], 184.6649652337873, MAGIC);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        k[g] = __double2loint(kf[g]);
+        kf[g] -= MAGIC;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const double T = tab[k[g] & (EXP_TAB - 1)];
+        s[g] = __hiloint2double(__double2hiint(T) + ((k[g] >> 6) << 20), __double2loint(T));
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], -0.00541521234663378, z[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], -1.4907929134926466e-12, rh[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(rh[g], 0.08888888888888889, 0.26666666666666666);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 0.6666666666666666);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 1.3333333333333333);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 2.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 2.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] *= rh[g];
+#pragma unroll
+    for (int g = 0; g < G; ++g) em1[g] = fma(s[g], p[g], s[g] - 1.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) d[g] = em1[g] + 2.0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0[g]) : "d"(d[g]));
+#pragma unroll
+    for (int g = 0; g < G; ++g) e0[g] = fma(-d[g], r0[g], 1.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) r0[g] = fma(r0[g], fma(e0[g], e0[g], e0[g]), r0[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const double t = em1[g] * r0[g];
+        const int hx = __double2hiint(z[g]);
+        const bool big = (hx & 0x7fffffff) >= 0x40340000;
+        a[g] = __hiloint2double(big ? ((hx & 0x80000000) | 0x3ff00000) : __double2hiint(t), big ? 0 : __double2loint(t));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -90,8 +177,70 @@ struct alignas(2 * sizeof(T)) Unit {
     T pad[(2 * D + 1) % 2];
 };
 
+// tuning knobs (overridable with -D for tools/tune_spiral.py)
+#ifndef PNODE_F32_TPT
+#define PNODE_F32_TPT 2
+#endif
+#ifndef PNODE_F32_GROUP
+#define PNODE_F32_GROUP 4
+#endif
+#ifndef PNODE_F32_ADJ_GROUP
+#define PNODE_F32_ADJ_GROUP PNODE_F32_GROUP
+#endif
+#ifndef PNODE_F64_ADJ_GROUP
+#define PNODE_F64_ADJ_GROUP PNODE_F64_GROUP
+#endif
+#ifndef PNODE_F32_CHUNKS
+#define PNODE_F32_CHUNKS 2
+#endif
+#ifndef PNODE_F32_FWD_CTAS
+#define PNODE_F32_FWD_CTAS 8
+#endif
+#ifndef PNODE_F32_ADJ_CTAS
+#define PNODE_F32_ADJ_CTAS 3
+#endif
+#ifndef PNODE_F64_TPT
+#define PNODE_F64_TPT 1
+#endif
+#ifndef PNODE_F64_GROUP
+#define PNODE_F64_GROUP 5
+#endif
+#ifndef PNODE_F64_CHUNKS
+#define PNODE_F64_CHUNKS 2
+#endif
+#ifndef PNODE_F64_FWD_CTAS
+#define PNODE_F64_FWD_CTAS 5
+#endif
+#ifndef PNODE_F64_ADJ_CTAS
+#define PNODE_F64_ADJ_CTAS 3
+#endif
+#ifndef PNODE_ADJ_ROLL
+#define PNODE_ADJ_ROLL 1
+#endif
+
+template <typename T>
+struct Cfg;
+template <>
+struct Cfg<float> {
+    static constexpr int TPT = PNODE_F32_TPT;            // trajectories per thread
+    static constexpr int GROUP = PNODE_F32_GROUP;        // hidden units sharing one reciprocal
+    static constexpr int ADJ_GROUP = PNODE_F32_ADJ_GROUP;
+    static constexpr int ADJ_CHUNKS = PNODE_F32_CHUNKS;  // hidden units in chunks of <= 32 (lane = unit in phase 2)
+    static constexpr int FWD_MIN_CTAS = PNODE_F32_FWD_CTAS;
+    static constexpr int ADJ_MIN_CTAS = PNODE_F32_ADJ_CTAS;
+};
+template <>
+struct Cfg<double> {
+    static constexpr int TPT = PNODE_F64_TPT;
+    static constexpr int GROUP = PNODE_F64_GROUP;
+    static constexpr int ADJ_GROUP = PNODE_F64_ADJ_GROUP;
+    static constexpr int ADJ_CHUNKS = PNODE_F64_CHUNKS;
+    static constexpr int FWD_MIN_CTAS = PNODE_F64_FWD_CTAS;
+    static constexpr int ADJ_MIN_CTAS = PNODE_F64_ADJ_CTAS;
+};
+
 template <typename T, int D, int H>
-__device__ __forceinline__ void load_weights(Unit<T, D> *sW, T *sB2, const MlpPtrs<T> &w) {
+__device__ __forceinline__ void load_weights(Unit<T, D> *sW, T *sB2, T *sTab, const MlpPtrs<T> &w) {
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         Unit<T, D> u;
 #pragma unroll
@@ -103,6 +252,8 @@ __device__ __forceinline__ void load_weights(Unit<T, D> *sW, T *sB2, const MlpPt
         sW[j] = u;
     }
     if (threadIdx.x < D) sB2[threadIdx.x] = w.b2[threadIdx.x];
+    if (sizeof(T) == 8)
+        for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) sTab[j] = (T)exp2((double)j / EXP_TAB);
 }
 
 template <typename T, int D, int PHI>
@@ -111,23 +262,50 @@ __device__ __forceinline__ void apply_phi(const T (&y)[D], T (&x)[D]) {
     for (int d = 0; d < D; ++d) x[d] = (PHI == 1) ? y[d] * y[d] * y[d] : y[d];
 }
 
-template <typename T, int D, int H, int PHI>
-__device__ __forceinline__ void mlp_eval(const Unit<T, D> *__restrict__ sW, const T *__restrict__ sB2,
-                                         const T (&y)[D], T (&out)[D]) {
-    T x[D];
-    apply_phi<T, D, PHI>(y, x);
+// out[q] = f(y[q]) for the thread's TPT trajectories; hidden units in groups of G (weights loaded once per group).
+template <typename T, int D, int H, int PHI, int TPT, int G>
+__device__ __forceinline__ void mlp_eval_units(const Unit<T, D> *__restrict__ sW, const T *__restrict__ sTab, int j0,
+                                               const T (&x)[TPT][D], T (&out)[TPT][D]) {
+    Unit<T, D> u[G];
 #pragma unroll
-    for (int d = 0; d < D; ++d) out[d] = sB2[d];
-#pragma unroll 5
-    for (int j = 0; j < H; ++j) {
-        const Unit<T, D> u = sW[j];
-        T z = u.b1;
+    for (int g = 0; g < G; ++g) u[g] = sW[j0 + g];
 #pragma unroll
-        for (int d = 0; d < D; ++d) z = fma(u.w1[d], x[d], z);
-        const T a = tanh_acc(z);
+    for (int q = 0; q < TPT; ++q) {
+        T z[G], a[G];
 #pragma unroll
-        for (int d = 0; d < D; ++d) out[d] = fma(u.w2[d], a, out[d]);
+        for (int g = 0; g < G; ++g) {
+            z[g] = u[g].b1;
+#pragma unroll
+            for (int d = 0; d < D; ++d) z[g] = fma(u[g].w1[d], x[q][d], z[g]);
+        }
+        tanh_group<G>(z, a, sTab);
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int d = 0; d < D; ++d) out[q][d] = fma(u[g].w2[d], a[g], out[q][d]);
     }
+}
+
+template <typename T, int D, int H, int PHI, int TPT>
+__device__ __forceinline__ void mlp_eval(const Unit<T, D> *__restrict__ sW, const T *__restrict__ sB2,
+                                         const T *__restrict__ sTab, const T (&y)[TPT][D], T (&out)[TPT][D]) {
+    constexpr int G = Cfg<T>::GROUP;
+    T x[TPT][D];
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+        apply_phi<T, D, PHI>(y[q], x[q]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) out[q][d] = sB2[d];
+    }
+    constexpr int NG = H / G;
+#pragma unroll 1
+    for (int gi = 0; gi < NG; ++gi) mlp_eval_units<T, D, H, PHI, TPT, G>(sW, sTab, gi * G, x, out);
+    constexpr int R = H - NG * G;
+    if (R >= 2) mlp_eval_units<T, D, H, PHI, TPT, (R >= 2 ? 2 : 1)>(sW, sTab, NG * G, x, out);
+    if (R == 3) mlp_eval_units<T, D, H, PHI, TPT, 1>(sW, sTab, NG * G + 2, x, out);
+    if (R == 1) mlp_eval_units<T, D, H, PHI, TPT, 1>(sW, sTab, NG * G, x, out);
+    static_assert(R < 4 || G > 4, "remainder handling assumes GROUP <= 4 or H % GROUP == 0");
+    static_assert(G <= 4 || H % G == 0, "GROUP > 4 needs H % GROUP == 0");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -136,54 +314,80 @@ __device__ __forceinline__ void mlp_eval(const Unit<T, D> *__restrict__ sW, cons
 constexpr int FWD_THREADS = 128;
 
 template <typename T, int D, int H, int S, int PHI>
-__global__ void __launch_bounds__(FWD_THREADS)
+__global__ void __launch_bounds__(FWD_THREADS, Cfg<T>::FWD_MIN_CTAS)
 mlp_rk_fwd_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u0, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, T *__restrict__ sol, T *__restrict__ ckpt) {
+    constexpr int TPT = Cfg<T>::TPT;
     __shared__ Unit<T, D> sW[H];
     __shared__ T sB2[D];
-    load_weights<T, D, H>(sW, sB2, w);
+    __shared__ T sTab[EXP_TAB];
+    load_weights<T, D, H>(sW, sB2, sTab, w);
     __syncthreads();
 
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; traj < ntraj; traj += stride) {
-        T y[D];
+    const int64_t tile = (int64_t)FWD_THREADS * TPT;
+    const int64_t ntiles = (ntraj + tile - 1) / tile;
+    for (int64_t tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
+        int64_t traj[TPT];
+        bool valid[TPT];
+        T y[TPT][D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = u0[traj * D + d];
-        T K[S][D];
+        for (int q = 0; q < TPT; ++q) {
+            traj[q] = tidx * tile + q * FWD_THREADS + threadIdx.x;
+            valid[q] = traj[q] < ntraj;
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[q][d] = valid[q] ? u0[traj[q] * D + d] : T(0);
+        }
+        T K[S][TPT][D];
         for (int n = 0; n < nsteps; ++n) {
             const double h = sched[n].h;
             const int out_slot = sched[n].out_slot;
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                T Y[D];
+                T Y[TPT][D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) Y[d] = y[d];
+                for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) Y[q][d] = y[q][d];
 #pragma unroll
                 for (int j = 0; j < i; ++j) {
                     const T ha = (T)(h * tab.a[i][j]);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) Y[d] = fma(ha, K[j][d], Y[d]);
+                    for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) Y[q][d] = fma(ha, K[j][q][d], Y[q][d]);
                 }
                 if (ckpt != nullptr) {
 #pragma unroll
-                    for (int d = 0; d < D; ++d) ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj] = Y[d];
+                    for (int q = 0; q < TPT; ++q)
+                        if (valid[q]) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj[q]] = Y[q][d];
+                        }
                 }
                 if (i == 0 && tab.fsal && n > 0) {
 #pragma unroll
-                    for (int d = 0; d < D; ++d) K[0][d] = K[S - 1][d];
+                    for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) K[0][q][d] = K[S - 1][q][d];
                 } else {
-                    mlp_eval<T, D, H, PHI>(sW, sB2, Y, K[i]);
+                    mlp_eval<T, D, H, PHI, TPT>(sW, sB2, sTab, Y, K[i]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < S; ++j) {
                 const T hb = (T)(h * tab.b[j]);
 #pragma unroll
-                for (int d = 0; d < D; ++d) y[d] = fma(hb, K[j][d], y[d]);
+                for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) y[q][d] = fma(hb, K[j][q][d], y[q][d]);
             }
             if (out_slot >= 0) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) sol[((int64_t)out_slot * ntraj + traj) * D + d] = y[d];
+                for (int q = 0; q < TPT; ++q)
+                    if (valid[q]) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) sol[((int64_t)out_slot * ntraj + traj[q]) * D + d] = y[q][d];
+                    }
             }
         }
     }
@@ -196,12 +400,19 @@ constexpr int ADJ_WARPS = 4;
 constexpr int ADJ_THREADS = ADJ_WARPS * 32;
 constexpr int ADJ_MAX_BLOCKS = 148 * 8;
 
-template <int D, int H>
+template <typename T, int D, int H>
 struct AdjShape {
-    static constexpr int NCHUNK = (H + 31) / 32;
-    static constexpr int JH = (H + NCHUNK - 1) / NCHUNK;  // hidden units per chunk (<= 32)
-    static constexpr int PITCH = 33;                      // odd pitch: transposed re-read is bank-conflict free
+    static constexpr int TPT = Cfg<T>::TPT;
+    static constexpr int NCHUNK = Cfg<T>::ADJ_CHUNKS;
+    static constexpr int G = Cfg<T>::ADJ_GROUP;
+    // hidden units per chunk: <= 32 (lane = unit in phase 2), a multiple of the tanh group width
+    static constexpr int JH = ((H + NCHUNK - 1) / NCHUNK + G - 1) / G * G;
+    static constexpr int NK = 32 * TPT;                       // trajectories per warp tile
+    static constexpr int VEC = 16 / sizeof(T);                // scalars per 16-byte shared load
+    static constexpr int PITCH = NK + VEC;                    // rows 16B-aligned; (PITCH/VEC) odd => conflict-free
     static constexpr int NP = 2 * H * D + H + D;
+    static_assert(JH <= 32, "chunk too wide");
+    static_assert(((PITCH / VEC) & 1) == 1, "pitch must be an odd number of 16-byte words");
 };
 
 struct AdjWork {
@@ -211,28 +422,47 @@ struct AdjWork {
 };
 
 template <typename T, int D, int H>
-struct WarpTile {
-    T A[AdjShape<D, H>::JH * AdjShape<D, H>::PITCH];  // tanh(z_j) per (unit, trajectory)
-    T Sg[AdjShape<D, H>::JH * AdjShape<D, H>::PITCH];  // s_j = g_j (1 - a_j^2)
-    alignas(16) T VX[32 * 2 * D];                      // per trajectory: v[0..D), x[0..D)
+struct alignas(16) WarpTile {
+    T A[AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];   // tanh(z_j)           per (unit, trajectory)
+    T Sg[AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];  // s_j = g_j(1-a_j^2)   per (unit, trajectory)
+    T V[D][AdjShape<T, D, H>::NK];                           // stage cotangent v, per trajectory
+    T X[D][AdjShape<T, D, H>::NK];                           // phi(Y_i)
 };
 
+template <typename T>
+struct VecT;
+template <>
+struct VecT<float> {
+    typedef float4 type;
+};
+template <>
+struct VecT<double> {
+    typedef double2 type;
+};
+template <typename T>
+__device__ __forceinline__ void lds16(const T *p, T (&r)[16 / sizeof(T)]) {
+    typename VecT<T>::type v = *reinterpret_cast<const typename VecT<T>::type *>(p);
+    memcpy(r, &v, 16);
+}
+
 template <typename T, int D, int H, int S, int PHI>
-__global__ void __launch_bounds__(ADJ_THREADS)
+__global__ void __launch_bounds__(ADJ_THREADS, Cfg<T>::ADJ_MIN_CTAS)
 mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
                   T *__restrict__ mu_out, AdjWork *__restrict__ work) {
-    typedef AdjShape<D, H> Sh;
-    constexpr int NCHUNK = Sh::NCHUNK, JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP;
+    typedef AdjShape<T, D, H> Sh;
+    constexpr int TPT = Sh::TPT, NCHUNK = Sh::NCHUNK, JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP, NK = Sh::NK;
+    constexpr int VEC = Sh::VEC, G = Cfg<T>::ADJ_GROUP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Unit<T, D> *sW = reinterpret_cast<Unit<T, D> *>(smem_raw);
     T *sB2 = reinterpret_cast<T *>(sW + H);
+    T *sTab = sB2 + D;
     WarpTile<T, D, H> *tiles = reinterpret_cast<WarpTile<T, D, H> *>(
-        smem_raw + ((sizeof(Unit<T, D>) * H + sizeof(T) * D + 15) / 16) * 16);
+        smem_raw + ((sizeof(Unit<T, D>) * H + sizeof(T) * (D + EXP_TAB) + 15) / 16) * 16);
     __shared__ bool is_last;
 
-    load_weights<T, D, H>(sW, sB2, w);
+    load_weights<T, D, H>(sW, sB2, sTab, w);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,105 +479,148 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
 #pragma unroll
     for (int d = 0; d < D; ++d) accB2[d] = 0.0;
 
-    const int64_t ntiles = (ntraj + ADJ_THREADS - 1) / ADJ_THREADS;
+    const int64_t tile_traj = (int64_t)ADJ_THREADS * TPT;
+    const int64_t ntiles = (ntraj + tile_traj - 1) / tile_traj;
     for (int64_t tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
-        const int64_t traj = tidx * ADJ_THREADS + threadIdx.x;
-        const bool valid = traj < ntraj;
-        T lam[D];
+        // trajectory q of this thread sits at tile column k = q*32 + lane of the warp's tile
+        int64_t traj[TPT];
+        bool valid[TPT];
+        T lam[TPT][D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) lam[d] = valid ? gout[((int64_t)last_slot * ntraj + traj) * D + d] : T(0);
+        for (int q = 0; q < TPT; ++q) {
+            traj[q] = tidx * tile_traj + (int64_t)warp * NK + q * 32 + lane;
+            valid[q] = traj[q] < ntraj;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                lam[q][d] = valid[q] ? gout[((int64_t)last_slot * ntraj + traj[q]) * D + d] : T(0);
+        }
+
+        // stage values are fetched one stage ahead of their use (hides the HBM latency of the checkpoint stream)
+        const int s_top = (tab.fsal ? S - 2 : S - 1);
+        T Ynext[TPT][D];
+        auto fetch_Y = [&](int nn, int ii) {
+#pragma unroll
+            for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    Ynext[q][d] = (valid[q] && nn >= 0) ? ckpt[(((int64_t)nn * S + ii) * D + d) * ntraj + traj[q]] : T(0);
+        };
+        fetch_Y(nsteps - 1, s_top);
 
         for (int n = nsteps - 1; n >= 0; --n) {
             const double h = sched[n].h;
             const int in_slot = sched[n].in_slot;
-            T ls[S][D];
+            T ls[S][TPT][D];
+            // the stage loop is deliberately NOT unrolled (ls becomes a small local array, touched a few times per stage):
+            // the loop body stays resident in the instruction cache; the chunk loop IS unrolled so that the
+            // parameter-gradient accumulators stay in registers
+#if PNODE_ADJ_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int i = S - 1; i >= 0; --i) {
                 if (tab.fsal && i == S - 1) {
 #pragma unroll
-                    for (int d = 0; d < D; ++d) ls[i][d] = T(0);
+                    for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) ls[i][q][d] = T(0);
                     continue;
                 }
-                // cotangent of the stage slope, pre-multiplied by the step coefficient: v = c * w
-                T v[D];
+                // cotangent of the stage slope, pre-multiplied by the step coefficient: v = c * w   
+                T v[TPT][D];
                 const double bi = tab.b[i];
-                if (bi != 0.0) {
+                const bool has_b = bi != 0.0;
+                const T cstep = (T)(has_b ? h * bi : h);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) v[d] = lam[d];
+                for (int q = 0; q < TPT; ++q) {
 #pragma unroll
-                    for (int j = i + 1; j < S; ++j) {
-                        const T r = (T)(tab.a[j][i] / bi);
+                    for (int d = 0; d < D; ++d) v[q][d] = has_b ? lam[q][d] : T(0);
+                }
+                for (int j = i + 1; j < S; ++j) {
+                    const T r = (T)(has_b ? tab.a[j][i] / bi : tab.a[j][i]);
 #pragma unroll
-                        for (int d = 0; d < D; ++d) v[d] = fma(r, ls[j][d], v[d]);
+                    for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) v[q][d] = fma(r, ls[j][q][d], v[q][d]);
+                }
+                T Y[TPT][D], x[TPT][D], dx[TPT][D];
+#pragma unroll
+                for (int q = 0; q < TPT; ++q) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        Y[q][d] = Ynext[q][d];
+                        v[q][d] = valid[q] ? v[q][d] * cstep : T(0);
+                        dx[q][d] = T(0);
                     }
-                    const T c = (T)(h * bi);
+                    apply_phi<T, D, PHI>(Y[q], x[q]);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) v[d] *= c;
-                } else {
-#pragma unroll
-                    for (int d = 0; d < D; ++d) v[d] = T(0);
-#pragma unroll
-                    for (int j = i + 1; j < S; ++j) {
-                        const T r = (T)tab.a[j][i];
-#pragma unroll
-                        for (int d = 0; d < D; ++d) v[d] = fma(r, ls[j][d], v[d]);
+                    for (int d = 0; d < D; ++d) {
+                        tile.V[d][q * 32 + lane] = v[q][d];
+                        tile.X[d][q * 32 + lane] = x[q][d];
+                        accB2[d] += (double)v[q][d];
                     }
-                    const T c = (T)h;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) v[d] *= c;
                 }
-                T Y[D], x[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    Y[d] = valid ? ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj] : T(0);
-                    if (!valid) v[d] = T(0);
-                }
-                apply_phi<T, D, PHI>(Y, x);
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    tile.VX[lane * 2 * D + d] = v[d];
-                    tile.VX[lane * 2 * D + D + d] = x[d];
-                    accB2[d] += (double)v[d];
-                }
-                T dx[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) dx[d] = T(0);
+                if (i > 0) fetch_Y(n, i - 1); else fetch_Y(n - 1, s_top);
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int j0 = c * JH;
                     const int jn = (H - j0 < JH) ? (H - j0) : JH;
-                    // phase 1 (lane = trajectory): VJP through every hidden unit of the chunk
-#pragma unroll 5
-                    for (int jj = 0; jj < jn; ++jj) {
-                        const Unit<T, D> u = sW[j0 + jj];
-                        T z = u.b1;
+                    // ---- phase 1 (lane = trajectory): VJP through every hidden unit of the chunk ---------------------
+#pragma unroll 1
+                    for (int jb = 0; jb < jn; jb += G) {
+                        Unit<T, D> u[G];
 #pragma unroll
-                        for (int d = 0; d < D; ++d) z = fma(u.w1[d], x[d], z);
-                        const T a = tanh_acc(z);
-                        T g = T(0);
+                        for (int g = 0; g < G; ++g) u[g] = sW[j0 + ((jb + g < jn) ? jb + g : jn - 1)];
 #pragma unroll
-                        for (int d = 0; d < D; ++d) g = fma(u.w2[d], v[d], g);
-                        const T s = g * fma(-a, a, T(1));
+                        for (int q = 0; q < TPT; ++q) {
+                            T z[G], a[G];
 #pragma unroll
-                        for (int d = 0; d < D; ++d) dx[d] = fma(s, u.w1[d], dx[d]);
-                        tile.A[jj * PITCH + lane] = a;
-                        tile.Sg[jj * PITCH + lane] = s;
+                            for (int g = 0; g < G; ++g) {
+                                z[g] = u[g].b1;
+#pragma unroll
+                                for (int d = 0; d < D; ++d) z[g] = fma(u[g].w1[d], x[q][d], z[g]);
+                            }
+                            tanh_group<G>(z, a, sTab);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                if (jb + g < jn) {
+                                    T gg = T(0);
+#pragma unroll
+                                    for (int d = 0; d < D; ++d) gg = fma(u[g].w2[d], v[q][d], gg);
+                                    const T s = gg * fma(-a[g], a[g], T(1));
+#pragma unroll
+                                    for (int d = 0; d < D; ++d) dx[q][d] = fma(s, u[g].w1[d], dx[q][d]);
+                                    tile.A[(jb + g) * PITCH + q * 32 + lane] = a[g];
+                                    tile.Sg[(jb + g) * PITCH + q * 32 + lane] = s;
+                                }
+                            }
+                        }
                     }
                     __syncwarp();
-                    // phase 2 (lane = hidden unit): reduce the outer products over the warp's 32 trajectories
+                    // ---- phase 2 (lane = hidden unit): outer products summed over the warp's trajectories -------------
                     if (lane < jn) {
                         T pW2[D], pW1[D], pB1 = T(0);
 #pragma unroll
                         for (int d = 0; d < D; ++d) pW2[d] = pW1[d] = T(0);
-#pragma unroll 8
-                        for (int k = 0; k < 32; ++k) {
-                            const T a = tile.A[lane * PITCH + k];
-                            const T s = tile.Sg[lane * PITCH + k];
-                            pB1 += s;
+#pragma unroll 4
+                        for (int k = 0; k < NK; k += VEC) {
+                            T a[VEC], s[VEC], vv[D][VEC], xx[D][VEC];
+                            lds16(&tile.A[lane * PITCH + k], a);
+                            lds16(&tile.Sg[lane * PITCH + k], s);
 #pragma unroll
                             for (int d = 0; d < D; ++d) {
-                                pW2[d] = fma(tile.VX[k * 2 * D + d], a, pW2[d]);
-                                pW1[d] = fma(s, tile.VX[k * 2 * D + D + d], pW1[d]);
+                                lds16(&tile.V[d][k], vv[d]);
+                                lds16(&tile.X[d][k], xx[d]);
+                            }
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) {
+                                pB1 += s[e];
+#pragma unroll
+                                for (int d = 0; d < D; ++d) {
+                                    pW2[d] = fma(vv[d][e], a[e], pW2[d]);
+                                    pW1[d] = fma(s[e], xx[d][e], pW1[d]);
+                                }
                             }
                         }
                         accB1[c] += (double)pB1;
@@ -360,22 +633,29 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     __syncwarp();
                 }
 #pragma unroll
-                for (int d = 0; d < D; ++d)
-                    ls[i][d] = (PHI == 1) ? dx[d] * (T(3) * Y[d] * Y[d]) : dx[d];
+                for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        ls[i][q][d] = (PHI == 1) ? dx[q][d] * (T(3) * Y[q][d] * Y[q][d]) : dx[q][d];
             }
 #pragma unroll
-            for (int i = 0; i < S; ++i)
+            for (int q = 0; q < TPT; ++q) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) lam[d] += ls[i][d];
-            if (in_slot >= 0 && valid) {
+                for (int i = 0; i < S; ++i)
 #pragma unroll
-                for (int d = 0; d < D; ++d) lam[d] += gout[((int64_t)in_slot * ntraj + traj) * D + d];
+                    for (int d = 0; d < D; ++d) lam[q][d] += ls[i][q][d];
+                if (in_slot >= 0 && valid[q]) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) lam[q][d] += gout[((int64_t)in_slot * ntraj + traj[q]) * D + d];
+                }
             }
         }
-        if (valid) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) lambda_out[traj * D + d] = lam[d];
-        }
+        for (int q = 0; q < TPT; ++q)
+            if (valid[q]) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) lambda_out[traj[q] * D + d] = lam[q][d];
+            }
     }
 
     // ---- block-level combine of the per-lane accumulators (fixed order), then grid-level by the last block ----------
@@ -427,7 +707,7 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
 
 template <typename T, int D, int H>
 static size_t adj_smem_bytes() {
-    return ((sizeof(Unit<T, D>) * H + sizeof(T) * D + 15) / 16) * 16 + sizeof(WarpTile<T, D, H>) * ADJ_WARPS;
+    return ((sizeof(Unit<T, D>) * H + sizeof(T) * (D + EXP_TAB) + 15) / 16) * 16 + sizeof(WarpTile<T, D, H>) * ADJ_WARPS;
 }
 
 template <typename T, int D, int H, int S, int PHI>
@@ -441,7 +721,8 @@ static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, cons
         PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, FWD_THREADS, 0));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    int64_t want = (ntraj + FWD_THREADS - 1) / FWD_THREADS;
+    const int64_t tile = (int64_t)FWD_THREADS * Cfg<T>::TPT;
+    int64_t want = (ntraj + tile - 1) / tile;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
@@ -465,7 +746,8 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
         PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, ADJ_THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    int64_t want = (ntraj + ADJ_THREADS - 1) / ADJ_THREADS;
+    const int64_t tile = (int64_t)ADJ_THREADS * Cfg<T>::TPT;
+    int64_t want = (ntraj + tile - 1) / tile;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (cap > ADJ_MAX_BLOCKS) cap = ADJ_MAX_BLOCKS;
     int grid = (int)(want < cap ? want : cap);
@@ -519,8 +801,12 @@ static int dispatch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, in
 
 template <typename T>
 __global__ void tanh_probe_kernel(const T *in, T *out, int64_t n) {
+    __shared__ T sTab[EXP_TAB];
+    if (sizeof(T) == 8)
+        for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) sTab[j] = (T)exp2((double)j / EXP_TAB);
+    __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = tanh_acc(in[i]);
+        out[i] = tanh_acc(in[i], sTab);
 }
 
 }  // namespace pnode
