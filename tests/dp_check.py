@@ -1,0 +1,78 @@
+"""Run under torchrun (N ranks, one per GPU): the batch-sharded fused spiral path vs a single-rank run of the full batch.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/dp_check.py
+Also exercised by tests/test_gpu_dp.py when >= 2 GPUs are visible."""
+import copy
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def main():
+    from _problems import SpiralFunc, TimeMLP, rel_err, spiral_inputs
+    from pnode import petsc_adjoint
+    from pnode_b200.options import Options
+    from pnode_b200.parallel import BatchComm, shard_batch
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = BatchComm()
+
+    def run(func, u, go, t, method, step, comm_, argv):
+        Options.clear_all()
+        Options.insert_args(argv)
+        f = copy.deepcopy(func).to(dev)
+        ode = petsc_adjoint.ODEPetsc()
+        ode.comm = comm_
+        ode.setupTS(u.to(dev), f, step_size=step, method=method, enable_adjoint=True)
+        y0 = u.to(dev).clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t.to(dev))
+        (out * go.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        return out.detach().cpu(), y0.grad.cpu(), [p.grad.cpu() for p in f.parameters()], ode
+
+    # 1. fused spiral, fixed step (mu all-reduce only)
+    B = 4099
+    u0, t, gout = spiral_inputs(B)
+    func = SpiralFunc()
+    full = run(func, u0, gout, t, "rk4", 0.025, None, ["-ts_adapt_type", "none"])
+    mine = run(func, shard_batch(u0, rank, world).contiguous(), shard_batch(gout, rank, world, dim=1).contiguous(), t,
+               "rk4", 0.025, comm, ["-ts_adapt_type", "none"])
+    assert mine[3].path == "fused-mlp-rk"
+    assert rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)) < 1e-13
+    assert rel_err(mine[1], shard_batch(full[1], rank, world)) < 1e-12
+    for a, b in zip(mine[2], full[2]):
+        assert rel_err(a, b) < 1e-11, rel_err(a, b)
+
+    # 2. generic adaptive dopri5: one scalar all-reduce per attempt => same step sequence as the single-rank run
+    g = torch.Generator().manual_seed(5)
+    u1 = torch.randn(1000, 6, generator=g, dtype=torch.float64)
+    go1 = torch.randn(3, 1000, 6, generator=g, dtype=torch.float64)
+    t1 = torch.tensor([0.0, 0.4, 1.0], dtype=torch.float64)
+    f1 = TimeMLP(d=6, hidden=16)
+    argv = ["-ts_rtol", "1e-6", "-ts_atol", "1e-6"]
+    full = run(f1, u1, go1, t1, "dopri5", 0.3, None, argv)
+    mine = run(f1, shard_batch(u1, rank, world).contiguous(), shard_batch(go1, rank, world, dim=1).contiguous(), t1,
+               "dopri5", 0.3, comm, argv)
+    la, lb = full[3]._loop.attempts, mine[3]._loop.attempts
+    assert [a[2] for a in la] == [b[2] for b in lb] and any(not a[2] for a in la)
+    for a, b in zip(la, lb):
+        assert abs(a[1] - b[1]) <= 1e-10 * abs(a[1])
+    assert rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)) < 1e-10
+    for a, b in zip(mine[2], full[2]):
+        assert rel_err(a, b) < 1e-10
+    dist.barrier()
+    if rank == 0:
+        print("dp_check ok: world=%d collectives=%d" % (world, comm.collectives))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
