@@ -1,0 +1,107 @@
+"""BASELINE configs 3-5 through the drop-in on the GPU (generic path: torch evaluates the RHS / VJP, csrc/vecops.cu does
+the TS arithmetic) against the oracle on the same seeded inputs, at sizes the CPU oracle finishes in seconds."""
+import copy
+
+import pytest
+import torch
+
+from oracle import OracleODEPetsc
+from pnode_b200.options import Options
+from _problems import rel_err
+from _workloads import CNFFunc, KSExplicit, KSImplicit, OdeConvBlock, ks_dx
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(argv, funcs, kw, u0, t, gout, step):
+    from pnode import petsc_adjoint
+
+    res = []
+    for dev, make in (("cpu", lambda: OracleODEPetsc(argv)), ("cuda", lambda: petsc_adjoint.ODEPetsc())):
+        Options.clear_all()
+        Options.insert_args(argv)
+        fs = [copy.deepcopy(f).to(dev) for f in funcs]
+        k = dict(kw)
+        if len(fs) == 2:
+            k["func2"] = fs[1]
+        ode = make()
+        ode.setupTS(u0.to(dev), fs[0], step_size=step, enable_adjoint=True, **k)
+        y0 = u0.to(dev).clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t.to(dev))
+        (out * gout.to(dev)).sum().backward()
+        grads = [p.grad for f in fs for p in f.parameters() if p.requires_grad]
+        res.append((out.detach(), y0.grad, grads, ode, fs))
+    return res
+
+
+def _compare(p, o, tol, per_param=True):
+    assert rel_err(p[0], o[0]) < tol, ("trajectory", rel_err(p[0], o[0]))
+    assert rel_err(p[1], o[1]) < tol, ("lambda", rel_err(p[1], o[1]))
+    assert len(p[2]) == len(o[2]) and len(p[2]) > 0
+    flat = lambda gs: torch.cat([g.detach().double().cpu().reshape(-1) for g in gs])
+    assert rel_err(flat(p[2]), flat(o[2])) < tol, ("mu (whole vector)", rel_err(flat(p[2]), flat(o[2])))
+    if per_param:
+        for a, b in zip(p[2], o[2]):
+            assert rel_err(a, b) < tol, ("mu", rel_err(a, b))
+
+
+@pytest.mark.parametrize("dtype,tol,ts_tol", [(torch.float64, 1e-9, "1e-6"), (torch.float32, 2e-4, "1e-4")])
+def test_config3_ffjord_cnf_dopri5_adaptive(dtype, tol, ts_tol):
+    """POWER-shaped 6-D CNF, hidden 60, B=1000, t=[0,1], dopri5 adaptive from h=0.05, Hutchinson VJP (second order)."""
+    B, D = 1000, 6
+    func = CNFFunc(B, D, (60,), dtype=dtype)
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(B, D, generator=g, dtype=torch.float64)
+    u0 = torch.cat((z.view(-1), torch.zeros(B, dtype=torch.float64))).to(dtype)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    gout = torch.randn(2, B * (D + 1), generator=g, dtype=torch.float64).to(dtype)
+    o, p = _pair(["-ts_rtol", ts_tol, "-ts_atol", ts_tol], [func], dict(method="dopri5"), u0, t, gout, 0.05)
+    lo, lp = o[3].ts.log, p[3]._loop.attempts
+    assert [a[2] for a in lo] == [a[2] for a in lp] and len(lo) >= 3
+    for a, b in zip(lo, lp):
+        assert a[1] == pytest.approx(b[1], rel=1e-8 if dtype == torch.float64 else 2e-2)
+    assert p[3].np == 984  # np = 984 for the FFJORD defaults
+    _compare(p, o, tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)])
+def test_config4_cifar_ode_block_rk4(dtype, tol):
+    """SqueezeNext ODE block (conv + BatchNorm in train mode), RK4, t=[1.0] single point, Nt=2 => h=0.5."""
+    C, HW, B = 32, 8, 16
+    func = OdeConvBlock(C, dtype=dtype)
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(B, C, HW, HW, generator=g, dtype=torch.float64).to(dtype)
+    gout = torch.randn(1, B, C, HW, HW, generator=g, dtype=torch.float64).to(dtype)
+    t = torch.tensor([1.0], dtype=torch.float64)
+    # parity needs IEEE fp32 convolutions: cuDNN's default TF32 path alone moves lambda by 2e-2 (measured, tools/diag_cifar.py)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        o, p = _pair(["-ts_adapt_type", "none"], [func], dict(method="rk4"), u0, t, gout, 0.5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert p[0].shape == (1, B, C, HW, HW)
+    # conv biases feeding a BatchNorm have an exactly-zero gradient (pure rounding noise on both sides): compare mu as a
+    # whole vector, not parameter by parameter
+    _compare(p, o, tol, per_param=False)
+    # BatchNorm running statistics are mutated once per RHS evaluation, adjoint re-evaluations included
+    assert p[4][0].nfe == o[4][0].nfe == 16
+    assert rel_err(p[4][0].bn1.running_mean, o[4][0].bn1.running_mean) < tol * 10
+
+
+@pytest.mark.parametrize("name", ["3", "l2"])
+def test_config5_sinode_ks_imex(name):
+    """KS: fixed stiff linear operator (implicit) + MLP (explicit), ARKIMEX, linear_solver='torch', -snes_type ksponly,
+    h = 0.2, one step per call (examples-sinode/KS/runs64_a100.sh:23), fp64."""
+    N, B = 64, 16
+    f_im = KSImplicit(ks_dx(N))
+    f_ex = KSExplicit(N)
+    g = torch.Generator().manual_seed(4)
+    u0 = 0.5 * torch.randn(B, N, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.2], dtype=torch.float64)
+    gout = torch.randn(2, B, N, generator=g, dtype=torch.float64)
+    argv = ["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_arkimex_type", name]
+    o, p = _pair(argv, [f_im, f_ex], dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch",
+                                          fixed_jacobian_across_solves=True), u0, t, gout, 0.2)
+    assert p[3].npIM == 0 and p[3].npEX == 146464  # npEX = 146,464 at N = 64
+    _compare(p, o, 1e-9)
