@@ -83,6 +83,9 @@ typedef struct pnode_rk_tableau {
     double a[PNODE_MAX_STAGES][PNODE_MAX_STAGES];     /* strictly lower triangular */
     double b[PNODE_MAX_STAGES];
     double c[PNODE_MAX_STAGES];
+    double be[PNODE_MAX_STAGES];                      /* embedded (order p-1) weights, used when has_be != 0 */
+    int32_t has_be;
+    int32_t order;                                    /* order p of the scheme ([PETSc] TSAdapt candidate order) */
 } pnode_rk_tableau;
 
 typedef struct pnode_mlp_desc {
@@ -131,6 +134,52 @@ int pnode_mlp_rk_forward(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab,
  */
 int64_t pnode_mlp_rk_adjoint_work_bytes(const pnode_mlp_desc *mlp);
 int pnode_mlp_rk_adjoint(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                         void *d_lambda, void *d_mu, void *d_work, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Fused path for FFJORD continuous-normalising-flow right-hand sides (ffjord-pnode/lib/layers/odefunc.py:322-385 with
+ * an ODEnet of two ConcatSquashLinear layers + softplus, diffeq_layers/basic.py:76-86):
+ *     a    = (W1 z + b1) * sigmoid(hgw1 t + hgb1) + hb1 t            hidden pre-activation   [H]
+ *     dz   = (W2 softplus(a) + b2) * sigmoid(hgw2 t + hgb2) + hb2 t                          [D]
+ *     dlogp = - e^T (d dz / d z) e           Hutchinson estimator, e fixed per solve (odefunc.py:53-57, 359-364)
+ * evaluated ANALYTICALLY per trajectory (no autograd graph, no second-order autograd in the adjoint).  State layout is the
+ * reference's flattened cat(z.view(-1), logp.view(-1)) (cnf.py:74, 140-142): z block [ntraj, D] then logp block [ntraj].
+ * Parameter / mu order = func.parameters(): per layer _layer.weight, _layer.bias, _hyper_bias.weight,
+ * _hyper_gate.weight, _hyper_gate.bias.
+ * -------------------------------------------------------------------------------------------------------------- */
+
+typedef struct pnode_cnf_desc {
+    int32_t dim;     /* D (6 for POWER) */
+    int32_t hidden;  /* H (60) */
+    int32_t dtype;
+    int32_t t_via_f32; /* 1: the module rounds t through float32 (odefunc.py:356 `torch.tensor(t).type_as(y)`) */
+    const void *d_w1, *d_b1, *d_hb1, *d_hgw1, *d_hgb1; /* [H,D], [H], [H], [H], [H] */
+    const void *d_w2, *d_b2, *d_hb2, *d_hgw2, *d_hgb2; /* [D,H], [D], [D], [D], [D] */
+    const void *d_e;                                   /* [ntraj, D] Hutchinson probe */
+} pnode_cnf_desc;
+
+int pnode_cnf_rk_supported(int dim, int hidden, int dtype, int stages);
+
+/* ONE step attempt of an explicit RK scheme from (t, u) with size h: all stages, completion, and -- when d_sumsq is not
+ * NULL and the tableau has embedded weights -- the weighted squared error sum of [PETSc] TSErrorWeightedNorm2 over the
+ * local shard (deterministic reduction, see pnode_rk_complete_wrms).  Accept/reject stays with the caller, who first
+ * all-reduces *d_sumsq across ranks.  Replaces one pass of [PETSc] TSStep_RK + TSEvaluateStep_RK + the reference's
+ * evalRHSFunction callbacks (petsc_adjoint.py:393-412).
+ *   d_u, d_unew   [ntraj*(D+1)]      current state / candidate u_{n+1}
+ *   d_kfsal_in    [ntraj*(D+1)] or NULL: slope f(t,u) carried over from the previous ACCEPTED step (FSAL tableaux)
+ *   d_kfsal_out   [ntraj*(D+1)] or NULL: receives the last stage slope
+ *   d_ckpt        [s_eff, D, ntraj] or NULL: z-part of the stage values Y_i (s_eff = s-1 for FSAL tableaux)
+ */
+int pnode_cnf_rk_attempt(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, const void *d_u,
+                         const void *d_kfsal_in, int64_t ntraj, double t, double h, void *d_unew, void *d_kfsal_out,
+                         void *d_ckpt, double atol, double rtol, double *d_sumsq, void *d_work, void *stream);
+
+/* Whole discrete-adjoint sweep over the accepted steps (same conventions as pnode_mlp_rk_adjoint); the per-stage VJP
+ * (RHSJacShell.multTranspose, petsc_adjoint.py:52-82, which needs second-order autograd in the reference) is evaluated
+ * analytically.  d_ckpt is [nsteps, s_eff, D, ntraj]; d_gout / d_lambda use the flattened state layout. */
+int64_t pnode_cnf_rk_adjoint_work_bytes(const pnode_cnf_desc *cnf);
+int pnode_cnf_rk_adjoint(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj,
                          const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
                          void *d_lambda, void *d_mu, void *d_work, void *stream);
 

@@ -14,12 +14,19 @@ MAX_TERMS, MAX_STAGES, MAX_SRCS = 16, 7, 32
 
 class RKTableau(C.Structure):
     _fields_ = [("s", C.c_int32), ("fsal", C.c_int32), ("a", (C.c_double * MAX_STAGES) * MAX_STAGES),
-                ("b", C.c_double * MAX_STAGES), ("c", C.c_double * MAX_STAGES)]
+                ("b", C.c_double * MAX_STAGES), ("c", C.c_double * MAX_STAGES), ("be", C.c_double * MAX_STAGES),
+                ("has_be", C.c_int32), ("order", C.c_int32)]
 
 
 class MlpDesc(C.Structure):
     _fields_ = [("dim", C.c_int32), ("hidden", C.c_int32), ("phi", C.c_int32), ("dtype", C.c_int32),
                 ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p)]
+
+
+class CnfDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32), ("t_via_f32", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("d_w1", "d_b1", "d_hb1", "d_hgw1", "d_hgb1", "d_w2", "d_b2", "d_hb2", "d_hgw2",
+                                          "d_hgb2", "d_e")]
 
 
 class Step(C.Structure):
@@ -40,6 +47,12 @@ _SIGNATURES = {
     "pnode_mlp_rk_forward": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _vp, _i64, _vp, _i, _vp, _vp, _vp]),
     "pnode_mlp_rk_adjoint_work_bytes": (_i64, [C.POINTER(MlpDesc)]),
     "pnode_mlp_rk_adjoint": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
+                                       _vp, _vp]),
+    "pnode_cnf_rk_supported": (C.c_int, [_i, _i, _i, _i]),
+    "pnode_cnf_rk_attempt": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _d, _d, _vp, _vp, _vp, _d,
+                                       _d, _vp, _vp, _vp]),
+    "pnode_cnf_rk_adjoint_work_bytes": (_i64, [C.POINTER(CnfDesc)]),
+    "pnode_cnf_rk_adjoint": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),
     "pnode_peak_fma": (C.c_int, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float)]),
     "pnode_tanh_probe": (C.c_int, [_vp, _vp, _i64, _i, _vp]),

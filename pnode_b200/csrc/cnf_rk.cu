@@ -1,0 +1,692 @@
+// Fused FFJORD continuous-normalising-flow sweeps (BASELINE config 3).
+//
+// Reference path replaced: per stage, PETSc calls evalRHSFunction (pnode/petsc_adjoint.py:393-412) -> FlattenFunc ->
+// ODEfunc.forward (ffjord-pnode/lib/layers/odefunc.py:345-385), which runs the ConcatSquash MLP AND a torch.autograd.grad
+// with create_graph=True for the Hutchinson trace (odefunc.py:53-57); per adjoint stage RHSJacShell.multTranspose
+// (petsc_adjoint.py:52-82) re-evaluates all of that and differentiates THROUGH the inner autograd.grad (second order).
+// Here both are closed-form per trajectory:
+//     p_j = W1[j,:] z + b1_j      a_j = p_j g1_j(t) + c1_j(t)      s_j = softplus(a_j)      sg_j = sigmoid(a_j)
+//     dz_k = (W2[k,:] s + b2_k) g2_k(t) + c2_k(t)
+//     e^T J e = sum_j g1_j sg_j w_j q_j,   w_j = sum_k W2[k,j] g2_k e_k,   q_j = W1[j,:] e        (J = d dz / d z)
+// with g = sigmoid(hgw t + hgb), c = hb t the ConcatSquash gates (diffeq_layers/basic.py:76-86).  Only sg_j depends on z
+// inside the trace, which makes the VJP of the trace (the "second-order" part) one extra multiply-add per hidden unit.
+//
+// B200 mapping: CUDA-core kernels (D = 6, H = 60: GEMMs of K = 6 are not tensor-core shaped), one trajectory per thread,
+// weights packed per hidden unit in SMEM and broadcast, gates of every stage time precomputed once per launch.
+//  * cnf_rk_attempt_kernel: ONE launch = all stages of one step attempt + completion + embedded error + deterministic
+//    weighted-squared-error reduction (device scalar; the caller all-reduces it across GPUs before accept/reject).
+//  * cnf_rk_adj_kernel: ONE launch = the whole discrete-adjoint sweep.  Parameter gradients (984 scalars) are reduced with
+//    the same warp-private transposed SMEM tile as csrc/mlp_rk.cu (lane = hidden unit in the reduce phase), layer-2 gate /
+//    bias gradients in per-thread registers; per-block partials are combined in fixed order by the last block.
+#include "common.cuh"
+
+namespace pnode {
+
+template <typename T>
+struct CnfPtrs {
+    const T *w1, *b1, *hb1, *hgw1, *hgb1, *w2, *b2, *hb2, *hgw2, *hgb2, *e;
+    int t_f32;
+};
+
+template <typename T, int D>
+struct alignas(16) UnitC {
+    T w1[D];  // W1[j][:]
+    T w2[D];  // W2[:][j]
+    T b1;
+    T pad[3];
+};
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ double sigmoid_acc(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// softplus (torch.nn.Softplus: beta 1, threshold 20) and its derivative, from one exponential
+__device__ __forceinline__ void softplus_sigmoid(float a, float &s, float &sg) {
+    const float E = __expf(-fabsf(a));
+    const float r = __fdividef(1.0f, 1.0f + E);
+    sg = a >= 0.0f ? r : E * r;
+    s = a > 20.0f ? a : fmaxf(a, 0.0f) + log1pf(E);
+}
+__device__ __forceinline__ void softplus_sigmoid(double a, double &s, double &sg) {
+    const double E = exp(-fabs(a));
+    const double r = 1.0 / (1.0 + E);
+    sg = a >= 0.0 ? r : E * r;
+    s = a > 20.0 ? a : fmax(a, 0.0) + log1p(E);
+}
+
+// shared-memory image of the model for one launch
+template <typename T, int D, int H, int S>
+struct CnfShared {
+    UnitC<T, D> unit[H];
+    T g1[S][H], c1[S][H];   // layer-1 gate / bias at every stage time
+    T g2[S][D], c2[S][D];
+    T b2[D];
+    T tstage[S];
+};
+
+// Stage time as the module sees it.  FFJORD's ODEfunc does `t = torch.tensor(t).type_as(y)` (odefunc.py:356):
+// torch.tensor(python float) is float32, so even a float64 run sees t rounded through fp32 (t_f32 != 0 reproduces that).
+template <typename T>
+__device__ __forceinline__ T stage_time(double t, int t_f32) {
+    return t_f32 ? (T)(float)t : (T)t;
+}
+
+template <typename T, int D, int H, int S>
+__device__ __forceinline__ void cnf_setup(CnfShared<T, D, H, S> &sm, const CnfPtrs<T> &w, const pnode_rk_tableau &tab,
+                                          double t, double h) {
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        UnitC<T, D> u;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            u.w1[k] = w.w1[j * D + k];
+            u.w2[k] = w.w2[k * H + j];
+        }
+        u.b1 = w.b1[j];
+        u.pad[0] = u.pad[1] = u.pad[2] = T(0);
+        sm.unit[j] = u;
+        const T gw = w.hgw1[j], gb = w.hgb1[j], hb = w.hb1[j];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            const T tt = stage_time<T>(t + tab.c[i] * h, w.t_f32);
+            sm.g1[i][j] = sigmoid_acc(fma(gw, tt, gb));
+            sm.c1[i][j] = hb * tt;
+        }
+    }
+    if (threadIdx.x < D) {
+        const int k = threadIdx.x;
+        sm.b2[k] = w.b2[k];
+        const T gw = w.hgw2[k], gb = w.hgb2[k], hb = w.hb2[k];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            const T tt = stage_time<T>(t + tab.c[i] * h, w.t_f32);
+            sm.g2[i][k] = sigmoid_acc(fma(gw, tt, gb));
+            sm.c2[i][k] = hb * tt;
+        }
+    }
+    if (threadIdx.x < S) sm.tstage[threadIdx.x] = stage_time<T>(t + tab.c[threadIdx.x] * h, w.t_f32);
+}
+
+// f(t_i, (z, .)) for one trajectory: out[0..D) = dz, out[D] = -e^T J e
+template <typename T, int D, int H, int S>
+__device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i, const T (&z)[D], const T (&e)[D],
+                                         T (&out)[D + 1]) {
+    T ge[D], r[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        ge[k] = sm.g2[i][k] * e[k];
+        r[k] = sm.b2[k];
+    }
+    T div = T(0);
+#pragma unroll 2
+    for (int j = 0; j < H; ++j) {
+        const UnitC<T, D> u = sm.unit[j];
+        T p = u.b1, q = T(0), w = T(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            p = fma(u.w1[k], z[k], p);
+            q = fma(u.w1[k], e[k], q);
+            w = fma(u.w2[k], ge[k], w);
+        }
+        const T g1 = sm.g1[i][j];
+        const T a = fma(p, g1, sm.c1[i][j]);
+        T s, sg;
+        softplus_sigmoid(a, s, sg);
+#pragma unroll
+        for (int k = 0; k < D; ++k) r[k] = fma(u.w2[k], s, r[k]);
+        div = fma(g1 * sg, w * q, div);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) out[k] = fma(r[k], sm.g2[i][k], sm.c2[i][k]);
+    out[D] = -div;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// one step attempt
+
+constexpr int CNF_THREADS = 128;
+constexpr int CNF_MAX_BLOCKS = 148 * 8;
+
+struct CnfWrmsWork {
+    unsigned int ticket;
+    unsigned int pad[15];
+    double partial[CNF_MAX_BLOCKS];
+};
+
+template <typename T, int D, int H, int S>
+__global__ void __launch_bounds__(CNF_THREADS)
+cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u,
+                      const T *__restrict__ kfsal_in, const int64_t ntraj, const double t, const double h,
+                      T *__restrict__ unew, T *__restrict__ kfsal_out, T *__restrict__ ckpt, const double atol,
+                      const double rtol, double *__restrict__ sumsq, CnfWrmsWork *__restrict__ work) {
+    __shared__ CnfShared<T, D, H, S> sm;
+    cnf_setup<T, D, H, S>(sm, w, tab, t, h);
+    __syncthreads();
+    constexpr int N = D + 1;
+    const int s_eff = tab.fsal ? S - 1 : S;
+    double local = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; traj < ntraj; traj += stride) {
+        T y[N], e[D], K[S][N];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            y[k] = u[traj * D + k];
+            e[k] = w.e[traj * D + k];
+        }
+        y[D] = u[ntraj * D + traj];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            T Y[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) Y[k] = y[k];
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                const T ha = (T)(h * tab.a[i][j]);
+#pragma unroll
+                for (int k = 0; k < N; ++k) Y[k] = fma(ha, K[j][k], Y[k]);
+            }
+            if (ckpt != nullptr && i < s_eff) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) ckpt[((int64_t)i * D + k) * ntraj + traj] = Y[k];
+            }
+            if (i == 0 && kfsal_in != nullptr) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) K[0][k] = kfsal_in[traj * D + k];
+                K[0][D] = kfsal_in[ntraj * D + traj];
+            } else {
+                T z[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) z[k] = Y[k];
+                cnf_eval<T, D, H, S>(sm, i, z, e, K[i]);
+            }
+        }
+        T yn[N], err[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            yn[k] = y[k];
+            err[k] = T(0);
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const T hb = (T)(h * tab.b[j]);
+            const T he = (T)(h * (tab.be[j] - tab.b[j]));
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                yn[k] = fma(hb, K[j][k], yn[k]);
+                err[k] = fma(he, K[j][k], err[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) unew[traj * D + k] = yn[k];
+        unew[ntraj * D + traj] = yn[D];
+        if (kfsal_out != nullptr) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) kfsal_out[traj * D + k] = K[S - 1][k];
+            kfsal_out[ntraj * D + traj] = K[S - 1][D];
+        }
+        if (sumsq != nullptr) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double un = (double)yn[k], x = (double)(yn[k] + err[k]);
+                const double tol = atol + rtol * fmax(fabs(un), fabs(x));
+                const double rr = (un - x) / tol;
+                local = fma(rr, rr, local);
+            }
+        }
+    }
+    if (sumsq == nullptr) return;
+    __shared__ double wsum[CNF_THREADS / 32];
+    __shared__ bool is_last;
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int wi = 0; wi < CNF_THREADS / 32; ++wi) s += wsum[wi];
+        work->partial[blockIdx.x] = s;
+        __threadfence();
+        is_last = (atomicAdd(&work->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += ((volatile double *)work->partial)[b];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) {
+            *sumsq = s;
+            work->ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// adjoint sweep
+
+constexpr int CNF_ADJ_WARPS = 4;
+constexpr int CNF_ADJ_THREADS = CNF_ADJ_WARPS * 32;
+constexpr int CNF_NCHUNK = 3;
+
+template <typename T, int D, int H>
+struct CnfAdjShape {
+    static constexpr int JH = (H + CNF_NCHUNK - 1) / CNF_NCHUNK;  // 20 hidden units per chunk (lane = unit in phase 2)
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr int PITCH = 32 + VEC;
+    static constexpr int NP = 2 * H * D + 4 * H + 4 * D;
+    static_assert(JH <= 32, "chunk too wide");
+};
+
+struct CnfAdjWork {
+    unsigned int ticket;
+    unsigned int pad[15];
+    double partial[1];  // [blocks][NP]
+};
+
+// warp-private tile: five per-(unit, trajectory) arrays + the per-trajectory vectors phase 2 needs
+template <typename T, int D, int H>
+struct alignas(16) CnfTile {
+    T dl[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // delta_j  = dL/da_j
+    T bp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // beta'_j  = -v_l sg_j w_j
+    T th[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // theta_j  = dL/dg1_j
+    T sp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // s_j      = softplus(a_j)
+    T eg[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // -v_l sg_j q_j g1_j
+    T Z[D][32], E[D][32], VZ[D][32];
+};
+
+template <typename T>
+struct CnfVec;
+template <>
+struct CnfVec<float> {
+    typedef float4 type;
+};
+template <>
+struct CnfVec<double> {
+    typedef double2 type;
+};
+template <typename T>
+__device__ __forceinline__ void cnf_lds16(const T *p, T (&r)[16 / sizeof(T)]) {
+    typename CnfVec<T>::type v = *reinterpret_cast<const typename CnfVec<T>::type *>(p);
+    memcpy(r, &v, 16);
+}
+
+template <typename T, int D, int H, int S>
+__global__ void __launch_bounds__(CNF_ADJ_THREADS)
+cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
+                  const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
+                  const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
+                  T *__restrict__ mu_out, CnfAdjWork *__restrict__ work) {
+    typedef CnfAdjShape<T, D, H> Sh;
+    constexpr int JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP, VEC = Sh::VEC, NCH = CNF_NCHUNK;
+    constexpr int NST = D + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CnfShared<T, D, H, S> &sm = *reinterpret_cast<CnfShared<T, D, H, S> *>(smem_raw);
+    CnfTile<T, D, H> *tiles =
+        reinterpret_cast<CnfTile<T, D, H> *>(smem_raw + ((sizeof(CnfShared<T, D, H, S>) + 15) / 16) * 16);
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CnfTile<T, D, H> &tile = tiles[warp];
+    const int s_eff = tab.fsal ? S - 1 : S;
+    const int64_t state_n = ntraj * NST;
+
+    // per-lane accumulators, lane = hidden unit of chunk c (kept in a small local array: touched once per stage-chunk)
+    double aW1[NCH][D], aW2[NCH][D], aB1[NCH], aHB1[NCH], aHGW1[NCH], aHGB1[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        aB1[c] = aHB1[c] = aHGW1[c] = aHGB1[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) aW1[c][k] = aW2[c][k] = 0.0;
+    }
+    // per-thread accumulators of the layer-2 bias / gate gradients (reduced over the warp at the end)
+    T aB2[D], aHB2[D], aHGW2[D], aHGB2[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) aB2[k] = aHB2[k] = aHGW2[k] = aHGB2[k] = T(0);
+
+    const int64_t ntiles = (ntraj + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
+    for (int64_t tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
+        const int64_t traj = tidx * CNF_ADJ_THREADS + threadIdx.x;
+        const bool valid = traj < ntraj;
+        T lam[NST], e[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            lam[k] = valid ? gout[(int64_t)last_slot * state_n + traj * D + k] : T(0);
+            e[k] = valid ? w.e[traj * D + k] : T(0);
+        }
+        lam[D] = valid ? gout[(int64_t)last_slot * state_n + ntraj * D + traj] : T(0);
+
+        for (int n = nsteps - 1; n >= 0; --n) {
+            const double h = sched[n].h;
+            const double t = sched[n].t;
+            const int in_slot = sched[n].in_slot;
+            __syncthreads();  // every warp is done with the previous step's gates
+            cnf_setup<T, D, H, S>(sm, w, tab, t, h);
+            __syncthreads();
+            T ls[S][D];
+#pragma unroll 1
+            for (int i = S - 1; i >= 0; --i) {
+                if (tab.fsal && i == S - 1) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) ls[i][k] = T(0);
+                    continue;
+                }
+                // cotangents of the stage slope, pre-multiplied by the step coefficient
+                const double bi = tab.b[i];
+                const bool has_b = bi != 0.0;
+                const T cstep = (T)(has_b ? h * bi : h);
+                T vz[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) vz[k] = has_b ? lam[k] : T(0);
+                for (int j = i + 1; j < S; ++j) {
+                    const T rr = (T)(has_b ? tab.a[j][i] / bi : tab.a[j][i]);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) vz[k] = fma(rr, ls[j][k], vz[k]);
+                }
+                // the logp row of the Jacobian is zero: its stage adjoints vanish, only lambda_logp itself feeds v_l
+                const T mvl = valid ? -(has_b ? lam[D] * cstep : T(0)) : T(0);  // = -v_l
+                T z[D], vg[D], ge[D], r[D], rho[D], dzk[D];
+                const T tt = sm.tstage[i];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    z[k] = valid ? ckpt[(((int64_t)n * s_eff + i) * D + k) * ntraj + traj] : T(0);
+                    vz[k] = valid ? vz[k] * cstep : T(0);
+                    vg[k] = vz[k] * sm.g2[i][k];
+                    ge[k] = sm.g2[i][k] * e[k];
+                    r[k] = sm.b2[k];
+                    rho[k] = T(0);
+                    dzk[k] = T(0);
+                    tile.Z[k][lane] = z[k];
+                    tile.E[k][lane] = e[k];
+                    tile.VZ[k][lane] = vz[k];
+                }
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const int j0 = c * JH;
+                    const int jn = (H - j0 < JH) ? (H - j0) : JH;
+                    // ---- phase 1 (lane = trajectory) ------------------------------------------------------------------
+#pragma unroll 2
+                    for (int jj = 0; jj < jn; ++jj) {
+                        const int j = j0 + jj;
+                        const UnitC<T, D> u = sm.unit[j];
+                        T p = u.b1, q = T(0), ww = T(0), m = T(0);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            p = fma(u.w1[k], z[k], p);
+                            q = fma(u.w1[k], e[k], q);
+                            ww = fma(u.w2[k], ge[k], ww);
+                            m = fma(u.w2[k], vg[k], m);
+                        }
+                        const T g1 = sm.g1[i][j];
+                        const T a = fma(p, g1, sm.c1[i][j]);
+                        T s, sg;
+                        softplus_sigmoid(a, s, sg);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) r[k] = fma(u.w2[k], s, r[k]);
+                        const T bq = mvl * sg;     // -v_l sg
+                        const T betap = bq * ww;   // d(-v_l div)/d(g1 q) per unit
+                        const T epsp = bq * q;
+                        const T delta = fma(betap * g1 * q, T(1) - sg, m * sg);  // dL/da_j
+                        const T theta = fma(delta, p, betap * q);                // dL/dg1_j
+                        const T dg = delta * g1;
+                        const T egv = epsp * g1;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            dzk[k] = fma(u.w1[k], dg, dzk[k]);
+                            rho[k] = fma(u.w2[k], egv, rho[k]);
+                        }
+                        tile.dl[jj * PITCH + lane] = delta;
+                        tile.bp[jj * PITCH + lane] = betap;
+                        tile.th[jj * PITCH + lane] = theta;
+                        tile.sp[jj * PITCH + lane] = s;
+                        tile.eg[jj * PITCH + lane] = egv;
+                    }
+                    __syncwarp();
+                    // ---- phase 2 (lane = hidden unit): sums over the warp's 32 trajectories ---------------------------
+                    if (lane < jn) {
+                        T sW1[D], sW2[D], sD = T(0), sTh = T(0);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) sW1[k] = sW2[k] = T(0);
+#pragma unroll 2
+                        for (int kk = 0; kk < 32; kk += VEC) {
+                            T dl[VEC], bp[VEC], th[VEC], sp[VEC], eg[VEC];
+                            cnf_lds16(&tile.dl[lane * PITCH + kk], dl);
+                            cnf_lds16(&tile.bp[lane * PITCH + kk], bp);
+                            cnf_lds16(&tile.th[lane * PITCH + kk], th);
+                            cnf_lds16(&tile.sp[lane * PITCH + kk], sp);
+                            cnf_lds16(&tile.eg[lane * PITCH + kk], eg);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                sD += dl[v];
+                                sTh += th[v];
+                            }
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                T zz[VEC], ee[VEC], vv[VEC];
+                                cnf_lds16(&tile.Z[k][kk], zz);
+                                cnf_lds16(&tile.E[k][kk], ee);
+                                cnf_lds16(&tile.VZ[k][kk], vv);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    sW1[k] = fma(dl[v], zz[v], sW1[k]);
+                                    sW1[k] = fma(bp[v], ee[v], sW1[k]);
+                                    sW2[k] = fma(vv[v], sp[v], sW2[k]);
+                                    sW2[k] = fma(eg[v], ee[v], sW2[k]);
+                                }
+                            }
+                        }
+                        const double g1 = (double)sm.g1[i][j0 + lane];
+                        const double gd = g1 * (1.0 - g1);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            aW1[c][k] += g1 * (double)sW1[k];
+                            aW2[c][k] += (double)sm.g2[i][k] * (double)sW2[k];
+                        }
+                        aB1[c] += g1 * (double)sD;
+                        aHB1[c] += (double)tt * (double)sD;
+                        aHGB1[c] += gd * (double)sTh;
+                        aHGW1[c] += (double)tt * gd * (double)sTh;
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    ls[i][k] = dzk[k];
+                    const T g2 = sm.g2[i][k];
+                    const T Gk = fma(vz[k], r[k], e[k] * rho[k]) * (g2 * (T(1) - g2));  // dL/d(gate-2 pre-activation)
+                    aB2[k] += vg[k];
+                    aHB2[k] = fma(vz[k], tt, aHB2[k]);
+                    aHGB2[k] += Gk;
+                    aHGW2[k] = fma(Gk, tt, aHGW2[k]);
+                }
+            }
+            for (int i = 0; i < S; ++i)
+#pragma unroll
+                for (int k = 0; k < D; ++k) lam[k] += ls[i][k];
+            if (in_slot >= 0 && valid) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) lam[k] += gout[(int64_t)in_slot * state_n + traj * D + k];
+                lam[D] += gout[(int64_t)in_slot * state_n + ntraj * D + traj];
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) lambda_out[traj * D + k] = lam[k];
+            lambda_out[ntraj * D + traj] = lam[D];
+        }
+    }
+
+    // ---- combine: per-lane / per-thread accumulators -> block partial (fixed order) -> last block sums the grid ---------
+    __syncthreads();
+    double *blk = reinterpret_cast<double *>(tiles);  // [CNF_ADJ_WARPS][NP]
+    static_assert(sizeof(CnfTile<T, D, H>) * CNF_ADJ_WARPS >= sizeof(double) * CNF_ADJ_WARPS * NP, "tile storage too small");
+    constexpr int O_B1 = H * D, O_HB1 = O_B1 + H, O_HGW1 = O_HB1 + H, O_HGB1 = O_HGW1 + H, O_W2 = O_HGB1 + H,
+                  O_B2 = O_W2 + D * H, O_HB2 = O_B2 + D, O_HGW2 = O_HB2 + D, O_HGB2 = O_HGW2 + D;
+    for (int c = 0; c < NCH; ++c) {
+        const int j = c * JH + lane;
+        if (lane < JH && j < H) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                blk[warp * NP + j * D + k] = aW1[c][k];
+                blk[warp * NP + O_W2 + k * H + j] = aW2[c][k];
+            }
+            blk[warp * NP + O_B1 + j] = aB1[c];
+            blk[warp * NP + O_HB1 + j] = aHB1[c];
+            blk[warp * NP + O_HGW1 + j] = aHGW1[c];
+            blk[warp * NP + O_HGB1 + j] = aHGB1[c];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const double b2 = warp_sum((double)aB2[k]), hb2 = warp_sum((double)aHB2[k]);
+        const double hgw2 = warp_sum((double)aHGW2[k]), hgb2 = warp_sum((double)aHGB2[k]);
+        if (lane == 0) {
+            blk[warp * NP + O_B2 + k] = b2;
+            blk[warp * NP + O_HB2 + k] = hb2;
+            blk[warp * NP + O_HGW2 + k] = hgw2;
+            blk[warp * NP + O_HGB2 + k] = hgb2;
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < CNF_ADJ_WARPS; ++wi) s += blk[wi * NP + p];
+        work->partial[(int64_t)blockIdx.x * NP + p] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&work->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+            double s = 0.0;
+            for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double *)work->partial)[(int64_t)b * NP + p];
+            mu_out[p] = (T)s;
+        }
+        if (threadIdx.x == 0) work->ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host dispatch
+
+static bool cnf_shape_ok(int dim, int hidden, int stages) {
+    return dim == 6 && hidden == 60 && (stages == 4 || stages == 7 || stages == 1 || stages == 2 || stages == 3);
+}
+
+template <typename T>
+static CnfPtrs<T> cnf_ptrs(const pnode_cnf_desc *c) {
+    auto p = [](const void *x) { return static_cast<const T *>(x); };
+    return CnfPtrs<T>{p(c->d_w1), p(c->d_b1), p(c->d_hb1), p(c->d_hgw1), p(c->d_hgb1), p(c->d_w2),
+                      p(c->d_b2), p(c->d_hb2), p(c->d_hgw2), p(c->d_hgb2), p(c->d_e), c->t_via_f32};
+}
+
+template <typename T, int S>
+static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, const void *d_u, const void *d_kin,
+                              int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
+                              double rtol, double *d_sumsq, void *d_work, cudaStream_t st) {
+    auto kern = cnf_rk_attempt_kernel<T, 6, 60, S>;
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, CNF_THREADS, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int64_t want = (ntraj + CNF_THREADS - 1) / CNF_THREADS;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (cap > CNF_MAX_BLOCKS) cap = CNF_MAX_BLOCKS;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, CNF_THREADS, 0, st>>>(cnf_ptrs<T>(c), *tab, static_cast<const T *>(d_u), static_cast<const T *>(d_kin),
+                                       ntraj, t, h, static_cast<T *>(d_unew), static_cast<T *>(d_kout),
+                                       static_cast<T *>(d_ckpt), atol, rtol, d_sumsq,
+                                       static_cast<CnfWrmsWork *>(d_work));
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int S>
+static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
+                              const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
+                              const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, cudaStream_t st) {
+    auto kern = cnf_rk_adj_kernel<T, 6, 60, S>;
+    const size_t smem = ((sizeof(CnfShared<T, 6, 60, S>) + 15) / 16) * 16 + sizeof(CnfTile<T, 6, 60>) * CNF_ADJ_WARPS;
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        PNODE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, CNF_ADJ_THREADS, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int64_t want = (ntraj + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (cap > CNF_MAX_BLOCKS) cap = CNF_MAX_BLOCKS;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, CNF_ADJ_THREADS, smem, st>>>(cnf_ptrs<T>(c), *tab, ntraj, d_sched, nsteps, last_slot,
+                                              static_cast<const T *>(d_gout), static_cast<const T *>(d_ckpt),
+                                              static_cast<T *>(d_lambda), static_cast<T *>(d_mu),
+                                              static_cast<CnfAdjWork *>(d_work));
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pnode
+
+using namespace pnode;
+
+#define PNODE_CNF_STAGES(X) X(1) X(2) X(3) X(4) X(7)
+
+extern "C" {
+
+int pnode_cnf_rk_supported(int dim, int hidden, int dtype, int stages) {
+    return (dtype == PNODE_F32 || dtype == PNODE_F64) && cnf_shape_ok(dim, hidden, stages) ? 1 : 0;
+}
+
+int pnode_cnf_rk_attempt(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, const void *d_u,
+                         const void *d_kfsal_in, int64_t ntraj, double t, double h, void *d_unew, void *d_kfsal_out,
+                         void *d_ckpt, double atol, double rtol, double *d_sumsq, void *d_work, void *stream) {
+    PNODE_REQUIRE(cnf && tab && d_u && d_unew, "pnode_cnf_rk_attempt: null argument");
+    PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_attempt: unsupported shape D=%d H=%d s=%d",
+                  cnf->dim, cnf->hidden, tab->s);
+    PNODE_REQUIRE(d_sumsq == nullptr || (tab->has_be && d_work != nullptr),
+                  "pnode_cnf_rk_attempt: error norm needs an embedded tableau and a work buffer");
+    if (ntraj == 0) {
+        if (d_sumsq) PNODE_CUDA_OK(cudaMemsetAsync(d_sumsq, 0, sizeof(double), static_cast<cudaStream_t>(stream)));
+        return 0;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(SS)                                                                                                       \
+    if (tab->s == SS) {                                                                                             \
+        if (cnf->dtype == PNODE_F32)                                                                                \
+            return launch_cnf_attempt<float, SS>(cnf, tab, d_u, d_kfsal_in, ntraj, t, h, d_unew, d_kfsal_out, d_ckpt, \
+                                                 atol, rtol, d_sumsq, d_work, st);                                  \
+        return launch_cnf_attempt<double, SS>(cnf, tab, d_u, d_kfsal_in, ntraj, t, h, d_unew, d_kfsal_out, d_ckpt,   \
+                                              atol, rtol, d_sumsq, d_work, st);                                     \
+    }
+    PNODE_CNF_STAGES(X)
+#undef X
+    PNODE_REQUIRE(false, "pnode_cnf_rk_attempt: no kernel for %d stages", tab->s);
+}
+
+int64_t pnode_cnf_rk_adjoint_work_bytes(const pnode_cnf_desc *cnf) {
+    int64_t np = 2 * (int64_t)cnf->hidden * cnf->dim + 4 * cnf->hidden + 4 * cnf->dim;
+    return 64 + (int64_t)CNF_MAX_BLOCKS * np * (int64_t)sizeof(double);
+}
+
+int pnode_cnf_rk_adjoint(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                         void *d_lambda, void *d_mu, void *d_work, void *stream) {
+    PNODE_REQUIRE(cnf && tab && d_sched && d_work && d_ckpt, "pnode_cnf_rk_adjoint: null argument");
+    PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_adjoint: unsupported shape D=%d H=%d s=%d",
+                  cnf->dim, cnf->hidden, tab->s);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(SS)                                                                                                       \
+    if (tab->s == SS) {                                                                                             \
+        if (cnf->dtype == PNODE_F32)                                                                                \
+            return launch_cnf_adjoint<float, SS>(cnf, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,        \
+                                                 d_lambda, d_mu, d_work, st);                                       \
+        return launch_cnf_adjoint<double, SS>(cnf, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, \
+                                              d_mu, d_work, st);                                                    \
+    }
+    PNODE_CNF_STAGES(X)
+#undef X
+    PNODE_REQUIRE(false, "pnode_cnf_rk_adjoint: no kernel for %d stages", tab->s);
+}
+
+}  // extern "C"

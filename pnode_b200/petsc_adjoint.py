@@ -22,8 +22,17 @@ from .controller import TimeLoop
 from .device import DeviceOps
 from .engine import Callbacks, GenericTS, ImplicitSolver
 from .errors import Error
-from .fused import FusedMlpRK, recognise_mlp
+from .fused import FusedCnfRK, FusedMlpRK, recognise_cnf, recognise_mlp
 from .options import Options
+
+
+def single_time_adjoint_steps(loop):
+    """petsc_adjoint.py:873-875: for a one-element `t` the reference runs round(|t / ts.getTimeStep()|) adjoint steps,
+    where getTimeStep() is the step PETSc proposed AFTER the last step.  Exact for fixed steps that divide t; for adaptive
+    runs it is the reference's (questionable) behaviour, reproduced here and capped by the steps actually taken."""
+    h = loop.h
+    n = int(round(abs(loop.t_end / h))) if h != 0 else 0
+    return min(n, loop.steps)
 
 
 def _check_device(tensor, what):
@@ -59,6 +68,7 @@ class ODEPetsc(object):
         self._engine = None
         self._fused = None
         self._fused_spec = None
+        self._fused_kind = None
         self._fused_checked_for = None
         self._cb_ex = self._cb_im = self._imp = None
         self._loop = None
@@ -156,22 +166,33 @@ class ODEPetsc(object):
         return self._scheme.bembed is not None
 
     def _fused_runner(self):
-        """Pick the fused sweep when func is a recognised MLP and the run is fixed-step explicit RK."""
-        if not self._allow_fused or self._active_kind != "rk" or self._adaptive():
+        """Pick a fused sweep when func is recognised: tiny-state MLP (fixed-step explicit RK) or FFJORD CNF (explicit RK,
+        fixed or adaptive).  Returns (kind, runner) or None."""
+        if not self._allow_fused or self._active_kind != "rk":
             return None
         key = (id(self.funcEX), self.tensor_size, self.tensor_dtype, self.device)
         if self._fused_checked_for != key:
             self._fused_checked_for = key
-            self._fused_spec = recognise_mlp(self.funcEX, torch.empty(self.tensor_size, dtype=self.tensor_dtype,
-                                                                      device=self.device))
+            meta = torch.empty(self.tensor_size, dtype=self.tensor_dtype, device=self.device)
+            self._fused_spec = recognise_mlp(self.funcEX, meta)
+            self._fused_kind = "mlp"
+            if self._fused_spec is None:
+                self._fused_spec = recognise_cnf(self.funcEX, meta)
+                self._fused_kind = "cnf"
             self._fused = None
         if self._fused_spec is None:
             return None
-        if not FusedMlpRK.supported(self._fused_spec, self._scheme, self.tensor_dtype):
-            return None
-        if self._fused is None or self._fused.scheme is not self._scheme:
-            self._fused = FusedMlpRK(self._fused_spec, self._scheme, self.tensor_dtype, self.device)
-        return self._fused
+        if self._fused_kind == "mlp":
+            if self._adaptive() or not FusedMlpRK.supported(self._fused_spec, self._scheme, self.tensor_dtype):
+                return None
+            if self._fused is None or self._fused.scheme is not self._scheme:
+                self._fused = FusedMlpRK(self._fused_spec, self._scheme, self.tensor_dtype, self.device)
+        else:
+            if not FusedCnfRK.supported(self._fused_spec, self._scheme, self.tensor_dtype):
+                return None
+            if self._fused is None or self._fused.scheme is not self._scheme:
+                self._fused = FusedCnfRK(self._fused_spec, self._scheme, self.tensor_dtype, self.device)
+        return self._fused_kind, self._fused
 
     # ------------------------------------------------------------------------------------------------------------
     def _times(self, t):
@@ -189,13 +210,27 @@ class ODEPetsc(object):
         if not u_flat.is_contiguous():
             u_flat = u_flat.contiguous()
         T = len(times)
-        fused = self._fused_runner()
-        if fused is not None:
+        sel = self._fused_runner()
+        if sel is not None and sel[0] == "mlp":
+            fused = sel[1]
             self.path = "fused-mlp-rk"
             sol, ckpt, sched = fused.forward(u_flat, times, self.step_size, self.enable_adjoint)
             self._loop = sched[2]
             state = ("fused", fused, ckpt, sched)
             return sol.view((T,) + tuple(self.tensor_size)), state
+        if sel is not None and sel[0] == "cnf":
+            fused = sel[1]
+            self.path = "fused-cnf-rk"
+            loop = TimeLoop(times, self.step_size, self._adaptive(), self._scheme.order,
+                            self.tensor_dtype == torch.float64, self._max_reject)
+            uf, sols, st = fused.forward(u_flat, loop, self._atol, self._rtol, self.enable_adjoint, comm=self.comm)
+            self._loop = loop
+            if T == 1:
+                out = uf.view((1,) + tuple(self.tensor_size))
+            else:
+                out = torch.stack([sols[k].view(self.tensor_size) for k in range(T)], dim=0)
+            st["loop"] = loop
+            return out, ("fused-cnf", fused, st, T == 1)
         self.path = "generic"
         self._imp.reset()
         loop = TimeLoop(times, self.step_size, self._adaptive(), self._scheme.order if self._scheme else 1,
@@ -234,7 +269,7 @@ class ODEPetsc(object):
         np_im = self.npIM if self.imex else 0
         eng = self._engine
         if T == 1:
-            nsteps = int(round(abs(loop.t_end / loop.last_h))) if loop.last_h != 0 else 0  # petsc_adjoint.py:875
+            nsteps = single_time_adjoint_steps(loop)
             nsteps = min(nsteps, len(eng.traj))
             lam = eng.adjoint_steps(self._cb_ex, self._cb_im, self._imp, nsteps, lam, mu, np_im)
         for i in range(T - 1, 0, -1):
@@ -270,6 +305,10 @@ class _OdeintAdjoint(torch.autograd.Function):
                 _, fused, ckpt, sched = ctx.state
                 ntraj = ode.n // fused.spec.dim
                 lam, mu = fused.adjoint(grad.view(T, -1), ckpt, sched, ntraj)
+            elif ctx.state[0] == "fused-cnf":
+                _, fused, st, single = ctx.state
+                nadj = single_time_adjoint_steps(st["loop"]) if single else None
+                lam, mu = fused.adjoint(grad.view(T, -1), st, single, nadj)
             else:
                 lam, mu = ode._adjoint_generic(ctx.state[1], ctx.state[2], grad, T)
             if ode.comm is not None:

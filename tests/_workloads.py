@@ -26,44 +26,92 @@ class ConcatSquashLinear(nn.Module):
         return self._layer(x) * torch.sigmoid(self._hyper_gate(t.view(1, 1))) + self._hyper_bias(t.view(1, 1))
 
 
-class CNFNet(nn.Module):
-    def __init__(self, dim, hidden_dims):
+class ODEnet(nn.Module):
+    """lib/layers/odefunc.py:97-204 restricted to linear ConcatSquash layers + softplus (train_tabular.py defaults);
+    same attribute names as the reference (`layers`, `activation_fns`)."""
+
+    def __init__(self, hidden_dims, dim):
         super().__init__()
         dims = [dim] + list(hidden_dims) + [dim]
         self.layers = nn.ModuleList([ConcatSquashLinear(a, b) for a, b in zip(dims[:-1], dims[1:])])
+        self.activation_fns = nn.ModuleList([nn.Softplus() for _ in hidden_dims])
 
     def forward(self, t, y):
         dx = y
         for i, layer in enumerate(self.layers):
             dx = layer(t, dx)
             if i < len(self.layers) - 1:
-                dx = F.softplus(dx)
+                dx = self.activation_fns[i](dx)
         return dx
 
 
-class CNFFunc(nn.Module):
-    """FlattenFunc(ODEfunc(ODEnet)) for states (z [B,D], logp [B,1]); `e` is the Hutchinson probe fixed per solve."""
+def divergence_approx(f, y, e=None):
+    e_dzdx = torch.autograd.grad(f, y, e, create_graph=True)[0]
+    return (e_dzdx * e).view(y.shape[0], -1).sum(dim=1)
 
-    def __init__(self, batch, dim=6, hidden_dims=(60,), dtype=torch.float32, seed=0):
+
+class ODEfunc(nn.Module):
+    """lib/layers/odefunc.py:322-385: dy = diffeq(t, y), dlogp = -Hutchinson trace with noise fixed per solve."""
+
+    def __init__(self, diffeq):
         super().__init__()
-        torch.manual_seed(seed)
-        self.net = CNFNet(dim, hidden_dims).to(dtype)
-        self.batch, self.dim = batch, dim
-        g = torch.Generator().manual_seed(seed + 1)
-        self.register_buffer("e", torch.randn(batch, dim, generator=g, dtype=torch.float64).to(dtype))
-        self.nfe = 0
+        self.diffeq = diffeq
+        self.residual = False
+        self.rademacher = False
+        self.divergence_fn = divergence_approx
+        self.register_buffer("_num_evals", torch.tensor(0.0))
+        self._e = None
+
+    def before_odeint(self, e=None):
+        self._e = e
+        self._num_evals.fill_(0)
+
+    def forward(self, t, states):
+        y = states[0]
+        self._num_evals += 1
+        t = torch.tensor(t).type_as(y)
+        if self._e is None:
+            self._e = torch.randn_like(y)
+        with torch.set_grad_enabled(True):
+            y.requires_grad_(True)
+            dy = self.diffeq(t, y)
+            divergence = self.divergence_fn(dy, y, e=self._e).view(y.shape[0], 1)
+        return (dy, -divergence)
+
+
+class FlattenFunc(nn.Module):
+    """lib/layers/cnf.py:123-150: the state handed to ODEPetsc is cat(z.view(-1), logp.view(-1))."""
+
+    def __init__(self, base_func, y0):
+        super().__init__()
+        self.base_func = base_func
+        self.y0 = y0
 
     def forward(self, t, y):
-        self.nfe += 1
-        B, D = self.batch, self.dim
-        z = y[: B * D].view(B, D)
-        tt = torch.tensor(t).type_as(z)
-        with torch.set_grad_enabled(True):
-            z.requires_grad_(True)
-            dz = self.net(tt, z)
-            e_dzdx = torch.autograd.grad(dz, z, self.e, create_graph=True)[0]
-            div = (e_dzdx * self.e).view(B, -1).sum(dim=1)
-        return torch.cat((dz.reshape(-1), -div.reshape(-1)))
+        parts, idx = [], 0
+        for x0 in self.y0:
+            parts.append(y[idx: idx + x0.numel()].view(*x0.shape))
+            idx += x0.numel()
+        out = self.base_func(t, tuple(parts))
+        return torch.cat([o.contiguous().view(-1) for o in out])
+
+
+def CNFFunc(batch, dim=6, hidden_dims=(60,), dtype=torch.float32, seed=0, device="cpu"):
+    """FlattenFunc(ODEfunc(ODEnet)) with the Hutchinson probe already fixed (seeded) -- what cnf.py:72-80 builds."""
+    torch.manual_seed(seed)
+    odefunc = ODEfunc(ODEnet(hidden_dims, dim).to(dtype))
+    g = torch.Generator().manual_seed(seed + 1)
+    odefunc._e = torch.randn(batch, dim, generator=g, dtype=torch.float64).to(dtype)
+    y0 = (torch.zeros(batch, dim, dtype=dtype), torch.zeros(batch, 1, dtype=dtype))
+    return FlattenFunc(odefunc, y0)
+
+
+def cnf_to(func, device):
+    """Move a CNFFunc (module + the probe/y0 tensors that are plain attributes, as in the reference) to a device."""
+    func = func.to(device)
+    func.base_func._e = func.base_func._e.to(device)
+    func.y0 = tuple(x.to(device) for x in func.y0)
+    return func
 
 
 class OdeConvBlock(nn.Module):

@@ -37,7 +37,8 @@ def test_loads_and_reports_version():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Step) == 24
-    assert ctypes.sizeof(_lib.RKTableau) == 8 + 8 * (49 + 7 + 7)
+    assert ctypes.sizeof(_lib.RKTableau) == 8 + 8 * (49 + 7 + 7 + 7) + 8
+    assert ctypes.sizeof(_lib.CnfDesc) == 16 + 11 * 8
     assert ctypes.sizeof(_lib.MlpDesc) == 16 + 4 * 8
 
 

@@ -1,0 +1,137 @@
+"""GPU parity of the fused FFJORD CNF sweeps (csrc/cnf_rk.cu through ODEPetsc -> ctypes -> C ABI) against the oracle,
+which evaluates the same model the way the reference does (autograd Hutchinson trace, second-order autograd VJP)."""
+import copy
+
+import pytest
+import torch
+
+from oracle import OracleODEPetsc
+from pnode_b200.options import Options
+from _problems import rel_err
+from _workloads import CNFFunc, cnf_to
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, D, T, dtype, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, D, generator=g, dtype=torch.float64)
+    u0 = torch.cat((z.view(-1), torch.zeros(B, dtype=torch.float64))).to(dtype)
+    gout = torch.randn(T, B * (D + 1), generator=g, dtype=torch.float64).to(dtype)
+    return u0, gout
+
+
+def _run(make, dev, argv, func, u0, t, gout, method, step):
+    Options.clear_all()
+    Options.insert_args(argv)
+    f = cnf_to(copy.deepcopy(func), dev)
+    ode = make()
+    ode.setupTS(u0.to(dev), f, step_size=step, method=method, enable_adjoint=True)
+    y0 = u0.to(dev).clone().requires_grad_(True)
+    out = ode.odeint_adjoint(y0, t.to(dev))
+    (out * gout.to(dev)).sum().backward()
+    return out.detach(), y0.grad, [p.grad for p in f.parameters()], ode
+
+
+def _pair(argv, func, u0, t, gout, method, step, fused=True):
+    from pnode import petsc_adjoint
+
+    o = _run(lambda: OracleODEPetsc(argv), "cpu", argv, func, u0, t, gout, method, step)
+    p = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + ([] if fused else ["-pnode_fused", "0"]), func, u0, t, gout,
+             method, step)
+    return o, p
+
+
+def _compare(p, o, tol):
+    assert rel_err(p[0], o[0]) < tol, ("trajectory", rel_err(p[0], o[0]))
+    assert rel_err(p[1], o[1]) < tol, ("lambda", rel_err(p[1], o[1]))
+    assert len(p[2]) == len(o[2]) == 10
+    for i, (a, b) in enumerate(zip(p[2], o[2])):
+        assert rel_err(a, b) < tol, ("mu[%d]" % i, rel_err(a, b))
+
+
+@pytest.mark.parametrize("dtype,tol,ts_tol", [(torch.float64, 1e-10, "1e-6"), (torch.float32, 1e-4, "1e-4")])
+@pytest.mark.parametrize("B", [1000, 77])
+def test_config3_adaptive_dopri5_fused(dtype, tol, ts_tol, B):
+    func = CNFFunc(B, 6, (60,), dtype=dtype)
+    u0, gout = _inputs(B, 6, 2, dtype)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    o, p = _pair(["-ts_rtol", ts_tol, "-ts_atol", ts_tol], func, u0, t, gout, "dopri5", 0.05)
+    assert p[3].path == "fused-cnf-rk"
+    lo, lp = o[3].ts.log, p[3]._loop.attempts
+    assert [a[2] for a in lo] == [a[2] for a in lp], "accept/reject pattern"
+    for a, b in zip(lo, lp):
+        assert a[1] == pytest.approx(b[1], rel=1e-8 if dtype == torch.float64 else 2e-2)
+    _compare(p, o, tol)
+
+
+def test_rejections_and_multiple_output_times_fp64():
+    B = 200
+    func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=3)
+    with torch.no_grad():  # make the dynamics stiffer so that the first big step is rejected
+        for prm in func.parameters():
+            prm.mul_(4.0)
+    u0, gout = _inputs(B, 6, 4, torch.float64)
+    t = torch.tensor([0.0, 0.3, 0.35, 1.0], dtype=torch.float64)
+    o, p = _pair(["-ts_rtol", "1e-7", "-ts_atol", "1e-7"], func, u0, t, gout, "dopri5", 0.5)
+    assert p[3].path == "fused-cnf-rk"
+    assert any(not a[2] for a in o[3].ts.log), "case must contain a rejected attempt"
+    assert [a[2] for a in o[3].ts.log] == [a[2] for a in p[3]._loop.attempts]
+    _compare(p, o, 2e-9)  # weights x4: the flow amplifies rounding differences ~20x more than the default model
+
+
+@pytest.mark.parametrize("method,argv", [("rk4", ["-ts_adapt_type", "none"]), ("dopri5", ["-ts_adapt_type", "none"]),
+                                         ("bosh3", []), ("euler", [])])
+def test_other_schemes_fused_fp64(method, argv):
+    B = 64
+    func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=5)
+    u0, gout = _inputs(B, 6, 3, torch.float64)
+    t = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64)
+    o, p = _pair(argv, func, u0, t, gout, method, 0.25)
+    assert p[3].path == "fused-cnf-rk"
+    _compare(p, o, 1e-10)
+
+
+def test_many_steps_grow_the_checkpoint_buffer():
+    B = 40
+    func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=9)
+    u0, gout = _inputs(B, 6, 2, torch.float64)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    o, p = _pair(["-ts_adapt_type", "none"], func, u0, t, gout, "rk4", 0.02)  # 50 steps > 16 > 32 slots
+    assert p[3].path == "fused-cnf-rk" and p[3]._loop.steps == 50
+    _compare(p, o, 1e-10)
+
+
+def test_fused_equals_generic_and_single_time_point():
+    B = 500
+    func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=7)
+    u0, gout = _inputs(B, 6, 1, torch.float64)
+    t = torch.tensor([0.8], dtype=torch.float64)
+    argv = ["-ts_rtol", "1e-6", "-ts_atol", "1e-6"]
+    o, p = _pair(argv, func, u0, t, gout, "dopri5", 0.1)
+    assert p[0].shape == (1, B * 7)
+    _compare(p, o, 1e-10)
+    _, g = _pair(argv, func, u0, t, gout, "dopri5", 0.1, fused=False)
+    assert g[3].path == "generic" and p[3].path == "fused-cnf-rk"
+    _compare(p, g, 1e-10)
+
+
+def test_probe_is_sampled_like_the_reference_when_absent():
+    """odefunc.py:359-364: `_e` is drawn inside the first RHS evaluation of a solve; the fused path draws it instead."""
+    from pnode import petsc_adjoint
+
+    B = 32
+    func = cnf_to(CNFFunc(B, 6, (60,), dtype=torch.float32), "cuda")
+    func.base_func.before_odeint()  # e <- None
+    Options.insert_args(["-ts_adapt_type", "none"])
+    u0, _ = _inputs(B, 6, 2, torch.float32)
+    ode = petsc_adjoint.ODEPetsc()
+    ode.setupTS(u0.cuda(), func, step_size=0.25, method="rk4")
+    out = ode.odeint_adjoint(u0.cuda(), torch.tensor([0.0, 1.0]).cuda())
+    assert ode.path == "fused-cnf-rk" and func.base_func._e is not None and func.base_func._e.shape == (B, 6)
+    # the same probe through the un-fused module gives the same answer
+    Options.insert_args(["-pnode_fused", "0"])
+    ode2 = petsc_adjoint.ODEPetsc()
+    ode2.setupTS(u0.cuda(), func, step_size=0.25, method="rk4")
+    out2 = ode2.odeint_adjoint(u0.cuda(), torch.tensor([0.0, 1.0]).cuda())
+    assert ode2.path == "generic" and rel_err(out, out2) < 1e-5

@@ -8,7 +8,7 @@ import torch
 from oracle import OracleODEPetsc
 from pnode_b200.options import Options
 from _problems import rel_err
-from _workloads import CNFFunc, KSExplicit, KSImplicit, OdeConvBlock, ks_dx
+from _workloads import CNFFunc, KSExplicit, KSImplicit, OdeConvBlock, cnf_to, ks_dx
 
 pytestmark = pytest.mark.gpu
 
@@ -20,7 +20,7 @@ def _pair(argv, funcs, kw, u0, t, gout, step):
     for dev, make in (("cpu", lambda: OracleODEPetsc(argv)), ("cuda", lambda: petsc_adjoint.ODEPetsc())):
         Options.clear_all()
         Options.insert_args(argv)
-        fs = [copy.deepcopy(f).to(dev) for f in funcs]
+        fs = [cnf_to(copy.deepcopy(f), dev) if hasattr(f, "base_func") else copy.deepcopy(f).to(dev) for f in funcs]
         k = dict(kw)
         if len(fs) == 2:
             k["func2"] = fs[1]
