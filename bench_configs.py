@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""Secondary measurement harness: every BASELINE.json config (1-5) through the drop-in on ONE B200, next to the oracle on the
+host cores.  bench.py stays the contract (config 2); this script produces the per-config table of DESIGN.md section 6 /
+profiles/r1_configs.jsonl.   python bench_configs.py [--configs 1,3,4,5] [--iters 10] [--cpu]
+
+Per config one JSON line: trajectory-steps/s = batch * accepted steps / time(odeint_adjoint + backward), CUDA events, median of
+`iters` after 3 warm-ups; which engine ran (fused / generic); algorithmic flops per trajectory-step from SURVEY.md section 8d
+and the fraction of the measured peak of the pipe that bounds it.
+"""
+import argparse
+import copy
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+
+def _time_gpu(step, iters):
+    for _ in range(3):
+        step()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def _time_cpu(step, reps=2):
+    step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    return 1e3 * (time.perf_counter() - t0) / reps
+
+
+def _make_step(ode_factory, funcs, u0, t, target, setup_kw, step_size, dev, each_call_setup=False):
+    fs = funcs
+    kw = dict(setup_kw)
+    if len(fs) == 2:
+        kw["func2"] = fs[1]
+    ode = ode_factory()
+    ode.setupTS(u0, fs[0], step_size=step_size, enable_adjoint=True, **kw)
+
+    def step():
+        for f in fs:
+            f.zero_grad(set_to_none=True)
+        if each_call_setup:  # FFJORD / CIFAR drivers call setupTS every forward (cnf.py:73, train-Cifar10.py:124)
+            ode.setupTS(u0, fs[0], step_size=step_size, enable_adjoint=True, **kw)
+        pred = ode.odeint_adjoint(u0, t)
+        loss = torch.mean(torch.abs(pred - target))
+        loss.backward()
+        return ode
+
+    return step, ode
+
+
+def run_config(name, build, args, peaks):
+    from oracle import OracleODEPetsc
+    from pnode import petsc_adjoint
+    from pnode_b200.options import Options
+
+    spec = build()
+    out = {"config": name, "dtype": spec["dtype"], "workload": spec["desc"]}
+    Options.clear_all()
+    Options.insert_args(spec["argv"])
+    dev = torch.device("cuda:0")
+    to_dev = spec.get("to_dev", lambda f, d: f.to(d))
+    funcs = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
+    u0, t, target = spec["u0"].to(dev), spec["t"].to(dev), spec["target"].to(dev)
+    step, ode = _make_step(lambda: petsc_adjoint.ODEPetsc(), funcs, u0, t, target, spec["kw"], spec["step"], dev,
+                           spec.get("each_call_setup", False))
+    ms = _time_gpu(step, args.iters)
+    loop = ode._loop
+    accepted = loop.steps
+    attempts = len(loop.attempts)
+    units = spec["batch"] * accepted
+    out.update({"path": ode.path, "ms_per_pass": ms, "accepted_steps": accepted, "attempts": attempts,
+                "traj_steps_per_s": units / (ms * 1e-3)})
+    flops = spec["flops_per_unit"] * units + spec.get("flops_per_rejected", 0) * spec["batch"] * (attempts - accepted)
+    tfl = flops / (ms * 1e-3) / 1e12
+    out["algorithmic_tflops"] = tfl
+    out["roofline"] = {"pipe": spec["pipe"], "peak_tflops": peaks[spec["pipe"]], "frac": tfl / peaks[spec["pipe"]],
+                       "hbm_gbs": spec["bytes_per_unit"] * units / (ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
+    if spec.get("also_generic") and ode.path != "generic":
+        Options.insert_args(["-pnode_fused", "0"])
+        funcs_g = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
+        step_g, ode_g = _make_step(lambda: petsc_adjoint.ODEPetsc(), funcs_g, u0, t, target, spec["kw"], spec["step"], dev,
+                                   spec.get("each_call_setup", False))
+        ms_g = _time_gpu(step_g, max(3, args.iters // 2))
+        out["generic_path_ms_per_pass"] = ms_g
+        out["fused_speedup_vs_generic_path"] = ms_g / ms
+        Options.clear_all()
+        Options.insert_args(spec["argv"])
+    if args.cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cs = spec["cpu_sample"]()
+        funcs_c = [copy.deepcopy(f) for f in cs["funcs"]]
+        step_c, ode_c = _make_step(lambda: OracleODEPetsc(spec["argv"]), funcs_c, cs["u0"], cs["t"], cs["target"], cs["kw"],
+                                   spec["step"], "cpu", spec.get("each_call_setup", False))
+        ms_c = _time_cpu(step_c)
+        acc_c = len([a for a in ode_c.ts.log if a[2]])
+        out["cpu_baseline"] = {"traj_steps_per_s": cs["batch"] * acc_c / (ms_c * 1e-3), "cores": os.cpu_count(),
+                               "kind": "port", "sample": cs["desc"], "ms_per_pass": ms_c}
+        out["speedup_vs_cpu_port"] = out["traj_steps_per_s"] / out["cpu_baseline"]["traj_steps_per_s"]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+def cfg1():
+    from _problems import SpiralFunc, spiral_inputs
+
+    u0, t, target = spiral_inputs(20)
+    return dict(desc="cfg1 ode_demo_petsc spiral: batch 20, batch_time 10, RK4 h=0.025, fp64", dtype="f64",
+                argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"], funcs=[SpiralFunc()], u0=u0, t=t,
+                target=target, kw=dict(method="rk4"), step=0.025, batch=20, flops_per_unit=6400, bytes_per_unit=160,
+                pipe="fp64_fma", also_generic=True,
+                cpu_sample=lambda: dict(funcs=[SpiralFunc()], u0=u0, t=t, target=target, kw=dict(method="rk4"), batch=20,
+                                        desc="full size"))
+
+
+def _cnf(B, dtype):
+    from _workloads import CNFFunc, cnf_to
+
+    def build():
+        td = torch.float32 if dtype == "f32" else torch.float64
+        g = torch.Generator().manual_seed(2)
+        mk = lambda b: dict(
+            func=CNFFunc(b, 6, (60,), dtype=td),
+            u0=torch.cat((torch.randn(b, 6, generator=g, dtype=torch.float64).view(-1),
+                          torch.zeros(b, dtype=torch.float64))).to(td),
+            target=torch.randn(2, b * 7, generator=g, dtype=torch.float64).to(td))
+        full = mk(B)
+        t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+        bs = min(B, 1 << 14)
+
+        def cpu_sample():
+            s = mk(bs)
+            return dict(funcs=[s["func"]], u0=s["u0"], t=t, target=s["target"], kw=dict(method="dopri5"), batch=bs,
+                        desc="%d of %d samples" % (bs, B))
+
+        return dict(desc="cfg3 FFJORD tabular CNF, POWER-shaped D=6 H=60, B=%d, dopri5 adaptive rtol=atol=1e-4, h0=0.05, "
+                         "t=[0,1], Hutchinson trace, %s" % (B, dtype), dtype=dtype, argv=["-ts_trajectory_type", "memory"],
+                    funcs=[full["func"]], u0=full["u0"], t=t, target=full["target"], kw=dict(method="dopri5"), step=0.05,
+                    batch=B, flops_per_unit=69120, flops_per_rejected=17280, bytes_per_unit=112 * (4 if dtype == "f32" else 8),
+                    pipe="fp32_fma" if dtype == "f32" else "fp64_fma", also_generic=B <= (1 << 16), each_call_setup=True,
+                    to_dev=cnf_to, cpu_sample=cpu_sample)
+
+    return build
+
+
+def cfg4():
+    from _workloads import OdeConvBlock
+
+    C, HW, B = 32, 32, 256
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(B, C, HW, HW, generator=g)
+    target = torch.randn(1, B, C, HW, HW, generator=g)
+    t = torch.tensor([1.0], dtype=torch.float64)
+    bs = 32
+    return dict(desc="cfg4 CIFAR SqueezeNext ODE block 1: u [256,32,32,32] fp32, RK4, t=[1.0], Nt=1 (h=1), conv+BN(train)",
+                dtype="f32", argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"], funcs=[OdeConvBlock(C)],
+                u0=u0, t=t, target=target, kw=dict(method="rk4"), step=1.0, batch=B, flops_per_unit=75.5e6,
+                bytes_per_unit=96 * C * HW * HW * 4, pipe="bf16_tensor", each_call_setup=True,
+                cpu_sample=lambda: dict(funcs=[OdeConvBlock(C)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
+                                        kw=dict(method="rk4"), batch=bs, desc="%d of %d samples" % (bs, B)))
+
+
+def cfg5(N=1024, B=256, dtype="f64"):
+    from _workloads import KSExplicit, KSImplicit, ks_dx
+
+    def build():
+        td = torch.float64 if dtype == "f64" else torch.float32
+        g = torch.Generator().manual_seed(4)
+        u0 = (0.5 * torch.randn(B, N, generator=g, dtype=torch.float64)).to(td)
+        target = torch.randn(2, B, N, generator=g, dtype=torch.float64).to(td)
+        t = torch.tensor([0.0, 0.2], dtype=torch.float64)
+        H = N * 25 // 8
+        kw = dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch", fixed_jacobian_across_solves=True)
+        f_ex = 2 * (2 * N * H + 3 * H * H)
+        bs = 32
+        return dict(desc="cfg5 SINODE KS: N=%d, MLP hidden %d, batch %d, ARKIMEX-3 h=0.2 one step, torch LU-type solver, "
+                         "-snes_type ksponly, %s" % (N, H, B, dtype), dtype=dtype,
+                    argv=["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_trajectory_type", "memory"],
+                    funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)], u0=u0, t=t, target=target, kw=kw,
+                    step=0.2, batch=B, flops_per_unit=16 * f_ex + 6 * 2 * N * N, bytes_per_unit=12 * 37.3e6 * 8 / B,
+                    pipe="fp64_fma" if dtype == "f64" else "fp32_fma",
+                    cpu_sample=lambda: dict(funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)],
+                                            u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
+                                            kw=dict(kw, batch_size=bs), batch=bs, desc="%d of %d samples" % (bs, B)))
+
+    return build
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,3,3L,4,5")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.jsonl"))
+    args = ap.parse_args()
+    import ctypes as C
+
+    from pnode_b200 import _lib
+
+    lib = _lib.load()
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    pk = {"hbm_gbs": peaks["hbm_gbs"], "bf16_tensor": peaks["bf16_tflops"]}
+    for code, key in ((_lib.F32, "fp32_fma"), (_lib.F64, "fp64_fma")):
+        fl, ms = C.c_double(), C.c_float()
+        _lib.check(lib.pnode_peak_fma(code, 20000, C.byref(fl), C.byref(ms)))
+        pk[key] = fl.value / (ms.value * 1e-3) / 1e12
+    table = {"1": ("cfg1", cfg1), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
+             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4), "5": ("cfg5", cfg5()),
+             "5S": ("cfg5-f32", cfg5(dtype="f32"))}
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "a") as fo:
+        for c in args.configs.split(","):
+            name, build = table[c]
+            try:
+                res = run_config(name, build, args, pk)
+            except Exception as e:  # keep going: one failing config must not hide the others
+                res = {"config": name, "error": repr(e)[:300]}
+            res["peaks"] = pk
+            line = json.dumps(res)
+            print(line, flush=True)
+            fo.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()

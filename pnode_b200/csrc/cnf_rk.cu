@@ -40,11 +40,16 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + ex
 __device__ __forceinline__ double sigmoid_acc(double x) { return 1.0 / (1.0 + exp(-x)); }
 
 // softplus (torch.nn.Softplus: beta 1, threshold 20) and its derivative, from one exponential
+// fp32: three MUFU ops (ex2, rcp, lg2); absolute error ~1e-7, far inside the 1e-4 parity bar of the fp32 path
 __device__ __forceinline__ void softplus_sigmoid(float a, float &s, float &sg) {
-    const float E = __expf(-fabsf(a));
-    const float r = __fdividef(1.0f, 1.0f + E);
+    float E, r, l;
+    const float x = -1.4426950408889634f * fabsf(a);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(x));
+    const float d = 1.0f + E;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(d));
     sg = a >= 0.0f ? r : E * r;
-    s = a > 20.0f ? a : fmaxf(a, 0.0f) + log1pf(E);
+    s = a > 20.0f ? a : fmaf(l, 0.6931471805599453f, fmaxf(a, 0.0f));
 }
 __device__ __forceinline__ void softplus_sigmoid(double a, double &s, double &sg) {
     const double E = exp(-fabs(a));
@@ -152,7 +157,7 @@ struct CnfWrmsWork {
 };
 
 template <typename T, int D, int H, int S>
-__global__ void __launch_bounds__(CNF_THREADS)
+__global__ void __launch_bounds__(CNF_THREADS, sizeof(T) == 4 ? 4 : 2)
 cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u,
                       const T *__restrict__ kfsal_in, const int64_t ntraj, const double t, const double h,
                       T *__restrict__ unew, T *__restrict__ kfsal_out, T *__restrict__ ckpt, const double atol,
@@ -172,12 +177,13 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
             e[k] = w.e[traj * D + k];
         }
         y[D] = u[ntraj * D + traj];
-#pragma unroll
+        // the stage loop is NOT unrolled: the slopes K live in a small local array (touched ~50 times per stage, against
+        // ~3000 instructions of right-hand side), which keeps the kernel at ~1/7 of the unrolled code size and registers
+#pragma unroll 1
         for (int i = 0; i < S; ++i) {
             T Y[N];
 #pragma unroll
             for (int k = 0; k < N; ++k) Y[k] = y[k];
-#pragma unroll
             for (int j = 0; j < i; ++j) {
                 const T ha = (T)(h * tab.a[i][j]);
 #pragma unroll
@@ -204,7 +210,6 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
             yn[k] = y[k];
             err[k] = T(0);
         }
-#pragma unroll
         for (int j = 0; j < S; ++j) {
             const T hb = (T)(h * tab.b[j]);
             const T he = (T)(h * (tab.be[j] - tab.b[j]));
@@ -263,11 +268,11 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
 
 constexpr int CNF_ADJ_WARPS = 4;
 constexpr int CNF_ADJ_THREADS = CNF_ADJ_WARPS * 32;
-constexpr int CNF_NCHUNK = 3;
+constexpr int CNF_NCHUNK = 2;
 
 template <typename T, int D, int H>
 struct CnfAdjShape {
-    static constexpr int JH = (H + CNF_NCHUNK - 1) / CNF_NCHUNK;  // 20 hidden units per chunk (lane = unit in phase 2)
+    static constexpr int JH = (H + CNF_NCHUNK - 1) / CNF_NCHUNK;  // 30 hidden units per chunk (lane = unit in phase 2)
     static constexpr int VEC = 16 / sizeof(T);
     static constexpr int PITCH = 32 + VEC;
     static constexpr int NP = 2 * H * D + 4 * H + 4 * D;

@@ -87,7 +87,12 @@ class ImplicitSolver:
         if self._J0 is None:
             N = y.numel() // self.batch
             y0 = y.view(self.cb.tensor_size)[0:1].detach().clone()
-            J = torch.autograd.functional.jacobian(lambda v: self.cb.func(t, v), y0)
+            # vmap'd reverse mode like the reference (torch.func.jacrev, petsc_adjoint.py:475-480): one batched backward
+            # instead of N sequential ones
+            try:
+                J = torch.func.jacrev(lambda v: self.cb.func(t, v))(y0)
+            except Exception:
+                J = torch.autograd.functional.jacobian(lambda v: self.cb.func(t, v), y0)
             self._J0 = J.reshape(N, N)
         return self._J0
 
