@@ -18,8 +18,8 @@
 //    (double) live across all stages, steps and tiles of the persistent kernel.  Per-block partials are combined in a
 //    fixed order by the last block (bit-reproducible mu).
 //  * both kernels are bound by instruction issue of tanh (fp64: FP64 pipe; fp32: MUFU/issue), not by HBM (arithmetic
-//    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 64-entry 2^(j/64) table in
-//    SMEM + degree-6 polynomial + cubic reciprocal refinement = 17 FP64 ops; fp32: one MUFU.EX2 per unit and ONE shared
+//    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 256-entry 2^(j/256) table in
+//    SMEM + degree-4 polynomial + cubic reciprocal refinement = 15 FP64 ops; fp32: one MUFU.EX2 per unit and ONE shared
 //    MUFU.RCP per four units (product trick).  Grids are persistent: SMs x resident CTAs.
 #include "common.cuh"
 
@@ -28,40 +28,43 @@ namespace pnode {
 // ---------------------------------------------------------------------------------------------------------------------
 // tanh
 
-constexpr int EXP_TAB = 64;  // 2^(j/64), j = 0..63
+constexpr int EXP_TAB = 256;  // 2^(j/256), j = 0..255  (2 KB of shared memory per CTA)
+constexpr int EXP_TAB_LOG2 = 8;
+
+// |x| clamped to 24 on the high word (tanh(24) rounds to 1; keeps k = rint(x 512/ln2) small; NaN also saturates -- the
+// state that produced it stays NaN through the AXPYs, so divergence is still visible to the caller)
+__device__ __forceinline__ double clamp24(double x) {
+    const int hx = __double2hiint(x);
+    const int ha = min(hx & 0x7fffffff, 0x40380000);
+    return __hiloint2double(ha | (hx & 0x80000000), __double2loint(x));
+}
 
 // fp64: tanh(x) = em1 / (em1 + 2), em1 = e^{2x} - 1 without cancellation.
-//   2x = k ln2/64 + r, |r| <= ln2/128;  e^{2x} = 2^(k>>6) * T[k&63] * (1 + P(r)),  P(r) = e^r - 1 (degree 6, trunc. 5e-18 rel.)
-//   em1 = (s - 1) + s P with s = T 2^(k>>6): exact for k == 0, so small |x| keeps full relative accuracy.
-__device__ __forceinline__ double tanh_acc(double x, const double *__restrict__ tab) {
+//   2x = k ln2/256 + r, |r| <= ln2/512;  e^{2x} = 2^(k>>8) * T[k&255] * (1 + P(r)),  P(r) = e^r - 1 (degree 4: truncation
+//   r^5/120 < 4e-17 absolute, < 3e-14 relative to tanh near 0)
+//   em1 = (s - 1) + s P with s = T 2^(k>>8): exact for k == 0, so small |x| keeps its relative accuracy.
+__device__ __forceinline__ double tanh_acc(double xin, const double *__restrict__ tab) {
     const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52
-    double kf = fma(x, 184.6649652337873, MAGIC);     // 128 / ln2
+    const double x = clamp24(xin);
+    double kf = fma(x, 738.6598609351493, MAGIC);     // 512 / ln2
     const int k = __double2loint(kf);
     kf -= MAGIC;
-    double rh = fma(kf, -0.00541521234663378, x);     // ln2/128 hi (0x1.62e42fee00000p-8: 21 trailing zero bits)
-    rh = fma(kf, -1.4907929134926466e-12, rh);        // ln2/128 lo ;  r = 2 rh
-    // P(r), r = 2 rh:  r + r^2/2 + ... + r^6/720 = rh (2 + rh (2 + rh (4/3 + rh (2/3 + rh (4/15 + rh 4/45)))))
-    double p = fma(rh, 0.08888888888888889, 0.26666666666666666);
-    p = fma(p, rh, 0.6666666666666666);
-    p = fma(p, rh, 1.3333333333333333);
+    double rh = fma(kf, -0.001353803086658445, x);    // ln2/512 hi (0x1.62e42fee00000p-10: 21 trailing zero bits)
+    rh = fma(kf, -3.7269822837316166e-13, rh);        // ln2/512 lo ;  r = 2 rh
+    // P(r), r = 2 rh:  r + r^2/2 + r^3/6 + r^4/24 = rh (2 + rh (2 + rh (4/3 + rh 2/3)))
+    double p = fma(rh, 0.6666666666666666, 1.3333333333333333);
     p = fma(p, rh, 2.0);
     p = fma(p, rh, 2.0);
     p *= rh;
     const double T = tab[k & (EXP_TAB - 1)];
-    const double s = __hiloint2double(__double2hiint(T) + ((k >> 6) << 20), __double2loint(T));
+    const double s = __hiloint2double(__double2hiint(T) + ((k >> EXP_TAB_LOG2) << 20), __double2loint(T));
     const double em1 = fma(s, p, s - 1.0);
     const double d = em1 + 2.0;
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
     const double e0 = fma(-d, r0, 1.0);
     const double rc = fma(r0, fma(e0, e0, e0), r0);   // cubic refinement: error e0^3
-    double t = em1 * rc;
-    // |x| >= 20 (or non-finite intermediate): tanh rounds to +-1
-    const int hx = __double2hiint(x);
-    const bool big = (hx & 0x7fffffff) >= 0x40340000;
-    const int thi = big ? ((hx & 0x80000000) | 0x3ff00000) : __double2hiint(t);
-    const int tlo = big ? 0 : __double2loint(t);
-    return __hiloint2double(thi, tlo);
+    return em1 * rc;
 }
 
 __device__ __forceinline__ float ex2_approx(float a) {
@@ -112,10 +115,12 @@ __device__ __forceinline__ void tanh_group(const float (&z)[G], float (&a)[G], c
 template <int G>
 __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G], const double *__restrict__ tab) {
     const double MAGIC = 6755399441055744.0;
-    double kf[G], rh[G], p[G], s[G], em1[G], d[G], r0[G], e0[G];
+    double x[G], kf[G], rh[G], p[G], s[G], em1[G], d[G], r0[G], e0[G];
     int k[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) kf[g] = fma(z[g], 184.6649652337873, MAGIC);
+    for (int g = 0; g < G; ++g) x[g] = clamp24(z[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) kf[g] = fma(x[g], 738.6598609351493, MAGIC);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         k[g] = __double2loint(kf[g]);
@@ -124,18 +129,14 @@ __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G],
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const double T = tab[k[g] & (EXP_TAB - 1)];
-        s[g] = __hiloint2double(__double2hiint(T) + ((k[g] >> 6) << 20), __double2loint(T));
+        s[g] = __hiloint2double(__double2hiint(T) + ((k[g] >> EXP_TAB_LOG2) << 20), __double2loint(T));
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], -0.00541521234663378, z[g]);
+    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], -0.001353803086658445, x[g]);
 #pragma unroll
-    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], -1.4907929134926466e-12, rh[g]);
+    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], -3.7269822837316166e-13, rh[g]);
 #pragma unroll
-    for (int g = 0; g < G; ++g) p[g] = fma(rh[g], 0.08888888888888889, 0.26666666666666666);
-#pragma unroll
-    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 0.6666666666666666);
-#pragma unroll
-    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 1.3333333333333333);
+    for (int g = 0; g < G; ++g) p[g] = fma(rh[g], 0.6666666666666666, 1.3333333333333333);
 #pragma unroll
     for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 2.0);
 #pragma unroll
@@ -153,12 +154,7 @@ __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G],
 #pragma unroll
     for (int g = 0; g < G; ++g) r0[g] = fma(r0[g], fma(e0[g], e0[g], e0[g]), r0[g]);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const double t = em1[g] * r0[g];
-        const int hx = __double2hiint(z[g]);
-        const bool big = (hx & 0x7fffffff) >= 0x40340000;
-        a[g] = __hiloint2double(big ? ((hx & 0x80000000) | 0x3ff00000) : __double2hiint(t), big ? 0 : __double2loint(t));
-    }
+    for (int g = 0; g < G; ++g) a[g] = em1[g] * r0[g];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -103,7 +103,7 @@ def test_kernel_tanh_accuracy(dtype, tol):
 
     lib = _lib.load()
     x = torch.cat((torch.linspace(-25, 25, 200001, dtype=torch.float64), torch.logspace(-300, 1, 4001, dtype=torch.float64),
-                   -torch.logspace(-30, 1, 4001, dtype=torch.float64), torch.tensor([0.0, 1e3, -1e3, 19.9, 20.1])))
+                   -torch.logspace(-30, 1, 4001, dtype=torch.float64), torch.tensor([0.0, 1e3, -1e3, 19.9, 20.1, 23.9, 24.1, -24.1, 1e300, -1e300, float('inf'), -float('inf')])))
     xd = x.to(dtype).cuda()
     out = torch.empty_like(xd)
     _lib.check(lib.pnode_tanh_probe(xd.data_ptr(), out.data_ptr(), xd.numel(), 0 if dtype == torch.float32 else 1,
@@ -113,4 +113,4 @@ def test_kernel_tanh_accuracy(dtype, tol):
     assert float(err.max()) < tol  # absolute error
     if dtype == torch.float64:  # relative accuracy is kept near zero too (em1 is formed without cancellation)
         rel = err / ref.abs().clamp_min(1e-300)
-        assert float(rel[ref != 0].max()) < 5e-14
+        assert float(rel[ref != 0].max()) < 2e-13
