@@ -162,6 +162,7 @@ __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G],
 template <typename T>
 struct MlpPtrs {
     const T *w1, *b1, *w2, *b2;
+    int slot;  // __constant__ weight slot of this launch
 };
 
 // per-hidden-unit weights packed for vector LDS: w1[j][0..D), b1[j], w2[0..D)[j]
@@ -235,8 +236,57 @@ struct Cfg<double> {
     static constexpr int ADJ_MIN_CTAS = PNODE_F64_ADJ_CTAS;
 };
 
+// EXPERIMENT (off by default, -DPNODE_CONST_WEIGHTS=1): weights in __constant__ memory, fed to FFMA/DFMA through the
+// uniform datapath (LDCU -> UR operands) instead of shared-memory broadcasts.  Measured on B200 at 2^20 trajectories: fp32
+// forward 1.07 -> 1.03 ms, adjoint 2.60 -> 2.75 ms; fp64 forward 2.99 -> 11.4 ms (252 doubles + kernel parameters overflow
+// the per-SM immediate-constant cache and every hidden unit misses), adjoint 5.62 -> 5.79 ms.  Shared memory stays.
+// Layout per slot = the flat parameter order W1[H][D] | b1[H] | W2[D][H] | b2[D]; slots are used round-robin so that sweeps
+// enqueued on different streams would not overwrite each other's weights.
+#ifndef PNODE_CONST_WEIGHTS
+#define PNODE_CONST_WEIGHTS 0
+#endif
+constexpr int W_SLOTS = 4;
+constexpr int W_MAXP = 2 * 50 * 2 + 50 + 2;
+__constant__ float cWf[W_SLOTS][W_MAXP];
+__constant__ double cWd[W_SLOTS][W_MAXP];
+template <typename T>
+__device__ __forceinline__ T cwget(int slot, int idx);
+template <>
+__device__ __forceinline__ float cwget<float>(int slot, int idx) {
+    return cWf[slot][idx];
+}
+template <>
+__device__ __forceinline__ double cwget<double>(int slot, int idx) {
+    return cWd[slot][idx];
+}
+
+template <typename T, int D, int H>
+__device__ __forceinline__ Unit<T, D> get_unit(const Unit<T, D> *__restrict__ sW, int slot, int j) {
+#if PNODE_CONST_WEIGHTS
+    Unit<T, D> u;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        u.w1[d] = cwget<T>(slot, j * D + d);
+        u.w2[d] = cwget<T>(slot, H * D + H + d * H + j);
+    }
+    u.b1 = cwget<T>(slot, H * D + j);
+    return u;
+#else
+    return sW[j];
+#endif
+}
+template <typename T, int D, int H>
+__device__ __forceinline__ T get_b2(const T *__restrict__ sB2, int slot, int d) {
+#if PNODE_CONST_WEIGHTS
+    return cwget<T>(slot, H * D + H + D * H + d);
+#else
+    return sB2[d];
+#endif
+}
+
 template <typename T, int D, int H>
 __device__ __forceinline__ void load_weights(Unit<T, D> *sW, T *sB2, T *sTab, const MlpPtrs<T> &w) {
+#if !PNODE_CONST_WEIGHTS
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         Unit<T, D> u;
 #pragma unroll
@@ -248,6 +298,7 @@ __device__ __forceinline__ void load_weights(Unit<T, D> *sW, T *sB2, T *sTab, co
         sW[j] = u;
     }
     if (threadIdx.x < D) sB2[threadIdx.x] = w.b2[threadIdx.x];
+#endif
     if (sizeof(T) == 8)
         for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) sTab[j] = (T)exp2((double)j / EXP_TAB);
 }
@@ -260,11 +311,11 @@ __device__ __forceinline__ void apply_phi(const T (&y)[D], T (&x)[D]) {
 
 // out[q] = f(y[q]) for the thread's TPT trajectories; hidden units in groups of G (weights loaded once per group).
 template <typename T, int D, int H, int PHI, int TPT, int G>
-__device__ __forceinline__ void mlp_eval_units(const Unit<T, D> *__restrict__ sW, const T *__restrict__ sTab, int j0,
-                                               const T (&x)[TPT][D], T (&out)[TPT][D]) {
+__device__ __forceinline__ void mlp_eval_units(const Unit<T, D> *__restrict__ sW, const T *__restrict__ sTab, int slot,
+                                               int j0, const T (&x)[TPT][D], T (&out)[TPT][D]) {
     Unit<T, D> u[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) u[g] = sW[j0 + g];
+    for (int g = 0; g < G; ++g) u[g] = get_unit<T, D, H>(sW, slot, j0 + g);
 #pragma unroll
     for (int q = 0; q < TPT; ++q) {
         T z[G], a[G];
@@ -284,22 +335,23 @@ __device__ __forceinline__ void mlp_eval_units(const Unit<T, D> *__restrict__ sW
 
 template <typename T, int D, int H, int PHI, int TPT>
 __device__ __forceinline__ void mlp_eval(const Unit<T, D> *__restrict__ sW, const T *__restrict__ sB2,
-                                         const T *__restrict__ sTab, const T (&y)[TPT][D], T (&out)[TPT][D]) {
+                                         const T *__restrict__ sTab, int slot, const T (&y)[TPT][D],
+                                         T (&out)[TPT][D]) {
     constexpr int G = Cfg<T>::GROUP;
     T x[TPT][D];
 #pragma unroll
     for (int q = 0; q < TPT; ++q) {
         apply_phi<T, D, PHI>(y[q], x[q]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) out[q][d] = sB2[d];
+        for (int d = 0; d < D; ++d) out[q][d] = get_b2<T, D, H>(sB2, slot, d);
     }
     constexpr int NG = H / G;
 #pragma unroll 1
-    for (int gi = 0; gi < NG; ++gi) mlp_eval_units<T, D, H, PHI, TPT, G>(sW, sTab, gi * G, x, out);
+    for (int gi = 0; gi < NG; ++gi) mlp_eval_units<T, D, H, PHI, TPT, G>(sW, sTab, slot, gi * G, x, out);
     constexpr int R = H - NG * G;
-    if (R >= 2) mlp_eval_units<T, D, H, PHI, TPT, (R >= 2 ? 2 : 1)>(sW, sTab, NG * G, x, out);
-    if (R == 3) mlp_eval_units<T, D, H, PHI, TPT, 1>(sW, sTab, NG * G + 2, x, out);
-    if (R == 1) mlp_eval_units<T, D, H, PHI, TPT, 1>(sW, sTab, NG * G, x, out);
+    if (R >= 2) mlp_eval_units<T, D, H, PHI, TPT, (R >= 2 ? 2 : 1)>(sW, sTab, slot, NG * G, x, out);
+    if (R == 3) mlp_eval_units<T, D, H, PHI, TPT, 1>(sW, sTab, slot, NG * G + 2, x, out);
+    if (R == 1) mlp_eval_units<T, D, H, PHI, TPT, 1>(sW, sTab, slot, NG * G, x, out);
     static_assert(R < 4 || G > 4, "remainder handling assumes GROUP <= 4 or H % GROUP == 0");
     static_assert(G <= 4 || H % G == 0, "GROUP > 4 needs H % GROUP == 0");
 }
@@ -366,7 +418,7 @@ mlp_rk_fwd_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const T *__res
 #pragma unroll
                         for (int d = 0; d < D; ++d) K[0][q][d] = K[S - 1][q][d];
                 } else {
-                    mlp_eval<T, D, H, PHI, TPT>(sW, sB2, sTab, Y, K[i]);
+                    mlp_eval<T, D, H, PHI, TPT>(sW, sB2, sTab, w.slot, Y, K[i]);
                 }
             }
 #pragma unroll
@@ -567,7 +619,8 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     for (int jb = 0; jb < jn; jb += G) {
                         Unit<T, D> u[G];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) u[g] = sW[j0 + ((jb + g < jn) ? jb + g : jn - 1)];
+                        for (int g = 0; g < G; ++g)
+                            u[g] = get_unit<T, D, H>(sW, w.slot, j0 + ((jb + g < jn) ? jb + g : jn - 1));
 #pragma unroll
                         for (int q = 0; q < TPT; ++q) {
                             T z[G], a[G];
@@ -706,11 +759,35 @@ static size_t adj_smem_bytes() {
     return ((sizeof(Unit<T, D>) * H + sizeof(T) * (D + EXP_TAB) + 15) / 16) * 16 + sizeof(WarpTile<T, D, H>) * ADJ_WARPS;
 }
 
+static int g_slot_counter = 0;
+
+template <typename T>
+static int upload_weights(const pnode_mlp_desc *m, int *slot_out, cudaStream_t st) {
+    const int slot = (g_slot_counter++) % W_SLOTS;
+    *slot_out = slot;
+#if PNODE_CONST_WEIGHTS
+    const int D = m->dim, H = m->hidden;
+    const size_t base = (size_t)slot * W_MAXP * sizeof(T);
+    const void *sym = sizeof(T) == 4 ? (const void *)cWf : (const void *)cWd;
+    const void *src[4] = {m->d_w1, m->d_b1, m->d_w2, m->d_b2};
+    const size_t cnt[4] = {(size_t)H * D, (size_t)H, (size_t)D * H, (size_t)D};
+    size_t off = 0;
+    for (int i = 0; i < 4; ++i) {
+        PNODE_CUDA_OK(cudaMemcpyToSymbolAsync(sym, src[i], cnt[i] * sizeof(T), base + off * sizeof(T),
+                                              cudaMemcpyDeviceToDevice, st));
+        off += cnt[i];
+    }
+#endif
+    return 0;
+}
+
 template <typename T, int D, int H, int S, int PHI>
 static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
                       const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, cudaStream_t st) {
+    int slot = 0;
+    if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
-                 static_cast<const T *>(m->d_b2)};
+                 static_cast<const T *>(m->d_b2), slot};
     auto kern = mlp_rk_fwd_kernel<T, D, H, S, PHI>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
@@ -732,8 +809,10 @@ template <typename T, int D, int H, int S, int PHI>
 static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_step *d_sched,
                       int nsteps, int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu,
                       void *d_work, cudaStream_t st) {
+    int slot = 0;
+    if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
-                 static_cast<const T *>(m->d_b2)};
+                 static_cast<const T *>(m->d_b2), slot};
     auto kern = mlp_rk_adj_kernel<T, D, H, S, PHI>;
     const size_t smem = adj_smem_bytes<T, D, H>();
     static int ctas_per_sm = 0;
