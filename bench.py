@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--ntraj", type=int, default=NTRAJ, help="trajectories per GPU")
     ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="trajectories of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N>1: all-reduce mu with NCCL instead of inside the adjoint kernel")
     return ap.parse_args()
 
 
@@ -223,6 +224,8 @@ def run_native(args):
         from pnode_b200.parallel import BatchComm
 
         ode.comm = BatchComm()
+        if not args.no_peer:
+            ode.comm.enable_peer_reduce()
     ode.setupTS(u0_dev, func, step_size=H, method="rk4", enable_adjoint=True)
 
     def step_resident():
@@ -314,7 +317,10 @@ def run_native(args):
         "config": {"workload": "spiral MLP 2-50-2 on y**3 (BASELINE configs[1]), 2^20 trajectories per GPU, RK4 fixed "
                                "step, 10 output times = 9 steps of h=0.025, odeint_adjoint + loss.backward()",
                    "ntraj_per_gpu": ntraj, "global_ntraj": world * ntraj, "method": "rk4", "steps_per_pass": NSTEPS,
-                   "parallelism": "batch-sharded dp%d, NCCL all-reduce of mu only" % world,
+                   "parallelism": "batch-sharded dp%d; only exchange = all-reduce of mu (252 scalars), %s" % (
+                       world, "single rank" if world == 1 else (
+                           "NCCL" if (ode.comm is None or ode.comm.peer is None) else
+                           "fused into the adjoint kernel over NVLink peer memory")),
                    "l2": "per-pass working set (stage checkpoints %.0f MB + grad_output %.0f MB) exceeds the 126 MB L2; "
                          "no explicit flush" % (ntraj * NSTEPS * STAGES * DIM * w / 1e6, ntraj * T_OUT * DIM * w / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -184,6 +184,27 @@ int pnode_cnf_rk_adjoint(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab,
                          void *d_lambda, void *d_mu, void *d_work, void *stream);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * Data-parallel variants of the adjoint sweeps: the all-reduce of mu over the GPUs of one NVLink/NVSwitch domain is fused
+ * into the tail of the sweep kernel (one-shot all-reduce over peer-mapped symmetric memory: peer stores + system-scope
+ * release/acquire flags; no NCCL call, no extra launch).  The reference has no counterpart (single process,
+ * petsc_adjoint.py:367); it replaces the `all_reduce(mu)` a data-parallel training loop would issue after
+ * OdeintAdjointMethod.backward (petsc_adjoint.py:916-947).
+ * d_peer_bufs: DEVICE array [world] with the peer-mapped base address of every rank's symmetric buffer of
+ * pnode_peer_buffer_bytes(world) bytes (zero-initialised once); epoch: strictly increasing (>= 1) across calls and equal on
+ * all ranks.  world == 1 or d_peer_bufs == NULL: identical to the non-DP entry points.
+ * -------------------------------------------------------------------------------------------------------------- */
+#define PNODE_PEER_NP_MAX 1024
+int64_t pnode_peer_buffer_bytes(int world);
+int pnode_mlp_rk_adjoint_dp(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                            void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                            uint64_t epoch, void *stream);
+int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                            void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                            uint64_t epoch, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): peak FMA issue rate of the CUDA-core pipe in the given dtype, used as the
  * compute-roofline denominator for the MLP kernels (MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).
  * Launches a register-resident FMA chain on every SM; *flops = 2 * FMAs executed.  Synchronous.

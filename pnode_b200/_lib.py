@@ -54,6 +54,11 @@ _SIGNATURES = {
     "pnode_cnf_rk_adjoint_work_bytes": (_i64, [C.POINTER(CnfDesc)]),
     "pnode_cnf_rk_adjoint": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),
+    "pnode_peer_buffer_bytes": (_i64, [_i]),
+    "pnode_mlp_rk_adjoint_dp": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
+                                          _vp, _vp, _i, _i, C.c_uint64, _vp]),
+    "pnode_cnf_rk_adjoint_dp": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
+                                          _vp, _vp, _i, _i, C.c_uint64, _vp]),
     "pnode_peak_fma": (C.c_int, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float)]),
     "pnode_tanh_probe": (C.c_int, [_vp, _vp, _i64, _i, _vp]),
 }

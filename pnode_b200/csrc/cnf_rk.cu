@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(CNF_ADJ_THREADS)
 cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
-                  T *__restrict__ mu_out, CnfAdjWork *__restrict__ work) {
+                  T *__restrict__ mu_out, CnfAdjWork *__restrict__ work, const PeerComm pc) {
     typedef CnfAdjShape<T, D, H> Sh;
     constexpr int JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP, VEC = Sh::VEC, NCH = CNF_NCHUNK;
     constexpr int NST = D + 1;
@@ -560,12 +560,20 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     __syncthreads();
     if (is_last) {
         __threadfence();
+        const bool dp = pc.peer_bufs != nullptr && pc.world > 1;
         for (int p = threadIdx.x; p < NP; p += blockDim.x) {
             double s = 0.0;
             for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double *)work->partial)[(int64_t)b * NP + p];
-            mu_out[p] = (T)s;
+            if (dp)
+                blk[p] = s;
+            else
+                mu_out[p] = (T)s;
         }
         if (threadIdx.x == 0) work->ticket = 0u;
+        if (dp) {
+            __syncthreads();
+            peer_allreduce_and_store<T>(blk, NP, pc, mu_out);
+        }
     }
 }
 
@@ -609,7 +617,8 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
 template <typename T, int S>
 static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
                               const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
-                              const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, cudaStream_t st) {
+                              const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, const PeerComm &pc,
+                              cudaStream_t st) {
     auto kern = cnf_rk_adj_kernel<T, 6, 60, S>;
     const size_t smem = ((sizeof(CnfShared<T, 6, 60, S>) + 15) / 16) * 16 + sizeof(CnfTile<T, 6, 60>) * CNF_ADJ_WARPS;
     static int ctas_per_sm = 0;
@@ -626,7 +635,7 @@ static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *t
     kern<<<grid, CNF_ADJ_THREADS, smem, st>>>(cnf_ptrs<T>(c), *tab, ntraj, d_sched, nsteps, last_slot,
                                               static_cast<const T *>(d_gout), static_cast<const T *>(d_ckpt),
                                               static_cast<T *>(d_lambda), static_cast<T *>(d_mu),
-                                              static_cast<CnfAdjWork *>(d_work));
+                                              static_cast<CnfAdjWork *>(d_work), pc);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -674,24 +683,35 @@ int64_t pnode_cnf_rk_adjoint_work_bytes(const pnode_cnf_desc *cnf) {
     return 64 + (int64_t)CNF_MAX_BLOCKS * np * (int64_t)sizeof(double);
 }
 
-int pnode_cnf_rk_adjoint(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj,
-                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
-                         void *d_lambda, void *d_mu, void *d_work, void *stream) {
+int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                            void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                            uint64_t epoch, void *stream) {
     PNODE_REQUIRE(cnf && tab && d_sched && d_work && d_ckpt, "pnode_cnf_rk_adjoint: null argument");
     PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_adjoint: unsupported shape D=%d H=%d s=%d",
                   cnf->dim, cnf->hidden, tab->s);
+    PNODE_REQUIRE(world <= 1 || d_peer_bufs == nullptr || (epoch >= 1 && rank >= 0 && rank < world && world <= 64),
+                  "pnode_cnf_rk_adjoint_dp: bad rank/world/epoch");
+    PeerComm pc{reinterpret_cast<const unsigned long long *>(d_peer_bufs), rank, world, (unsigned long long)epoch};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define X(SS)                                                                                                       \
     if (tab->s == SS) {                                                                                             \
         if (cnf->dtype == PNODE_F32)                                                                                \
             return launch_cnf_adjoint<float, SS>(cnf, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,        \
-                                                 d_lambda, d_mu, d_work, st);                                       \
+                                                 d_lambda, d_mu, d_work, pc, st);                                   \
         return launch_cnf_adjoint<double, SS>(cnf, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, \
-                                              d_mu, d_work, st);                                                    \
+                                              d_mu, d_work, pc, st);                                                \
     }
     PNODE_CNF_STAGES(X)
 #undef X
     PNODE_REQUIRE(false, "pnode_cnf_rk_adjoint: no kernel for %d stages", tab->s);
+}
+
+int pnode_cnf_rk_adjoint(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                         void *d_lambda, void *d_mu, void *d_work, void *stream) {
+    return pnode_cnf_rk_adjoint_dp(cnf, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
+                                   nullptr, 0, 1, 0, stream);
 }
 
 }  // extern "C"

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(ADJ_THREADS, Cfg<T>::ADJ_MIN_CTAS)
 mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
-                  T *__restrict__ mu_out, AdjWork *__restrict__ work) {
+                  T *__restrict__ mu_out, AdjWork *__restrict__ work, const PeerComm pc) {
     typedef AdjShape<T, D, H> Sh;
     constexpr int TPT = Sh::TPT, NCHUNK = Sh::NCHUNK, JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP, NK = Sh::NK;
     constexpr int VEC = Sh::VEC, G = Cfg<T>::ADJ_GROUP;
@@ -742,12 +742,20 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     __syncthreads();
     if (is_last) {
         __threadfence();
+        const bool dp = pc.peer_bufs != nullptr && pc.world > 1;
         for (int p = threadIdx.x; p < NP; p += blockDim.x) {
             double s = 0.0;
             for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double *)work->partial)[(int64_t)b * NP + p];
-            mu_out[p] = (T)s;
+            if (dp)
+                blk[p] = s;  // this GPU's mu; the cross-GPU sum follows in the same kernel
+            else
+                mu_out[p] = (T)s;
         }
         if (threadIdx.x == 0) work->ticket = 0u;
+        if (dp) {
+            __syncthreads();
+            peer_allreduce_and_store<T>(blk, NP, pc, mu_out);
+        }
     }
 }
 
@@ -808,7 +816,7 @@ static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, cons
 template <typename T, int D, int H, int S, int PHI>
 static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_step *d_sched,
                       int nsteps, int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu,
-                      void *d_work, cudaStream_t st) {
+                      void *d_work, const PeerComm &pc, cudaStream_t st) {
     int slot = 0;
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
@@ -829,7 +837,7 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
     if (grid < 1) grid = 1;
     kern<<<grid, ADJ_THREADS, smem, st>>>(w, *tab, ntraj, d_sched, nsteps, last_slot, static_cast<const T *>(d_gout),
                                           static_cast<const T *>(d_ckpt), static_cast<T *>(d_lambda),
-                                          static_cast<T *>(d_mu), static_cast<AdjWork *>(d_work));
+                                          static_cast<T *>(d_mu), static_cast<AdjWork *>(d_work), pc);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -860,14 +868,14 @@ static int dispatch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, co
 template <typename T>
 static int dispatch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_step *d_sched,
                         int nsteps, int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu,
-                        void *d_work, cudaStream_t st) {
+                        void *d_work, const PeerComm &pc, cudaStream_t st) {
 #define X(SS)                                                                                                     \
     if (tab->s == SS) {                                                                                           \
         if (m->phi == 1)                                                                                          \
             return launch_adj<T, 2, 50, SS, 1>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,         \
-                                               d_lambda, d_mu, d_work, st);                                       \
+                                               d_lambda, d_mu, d_work, pc, st);                                   \
         return launch_adj<T, 2, 50, SS, 0>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda,   \
-                                           d_mu, d_work, st);                                                     \
+                                           d_mu, d_work, pc, st);                                                 \
     }
     PNODE_FOR_STAGES(X)
 #undef X
@@ -913,22 +921,37 @@ int64_t pnode_mlp_rk_adjoint_work_bytes(const pnode_mlp_desc *mlp) {
     return 64 + (int64_t)ADJ_MAX_BLOCKS * np * (int64_t)sizeof(double);
 }
 
-int pnode_mlp_rk_adjoint(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
-                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
-                         void *d_lambda, void *d_mu, void *d_work, void *stream) {
+int pnode_mlp_rk_adjoint_dp(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                            void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                            uint64_t epoch, void *stream) {
     PNODE_REQUIRE(mlp && tab && d_sched && d_work, "pnode_mlp_rk_adjoint: null argument");
     PNODE_REQUIRE(shape_ok(mlp->dim, mlp->hidden, mlp->phi, tab->s),
                   "pnode_mlp_rk_adjoint: unsupported shape dim=%d hidden=%d phi=%d stages=%d", mlp->dim, mlp->hidden,
                   mlp->phi, tab->s);
     PNODE_REQUIRE(d_ckpt != nullptr || nsteps == 0, "pnode_mlp_rk_adjoint: stage checkpoints missing");
+    PNODE_REQUIRE(world <= 1 || d_peer_bufs == nullptr || (epoch >= 1 && rank >= 0 && rank < world && world <= 64),
+                  "pnode_mlp_rk_adjoint_dp: bad rank/world/epoch");
+    PeerComm pc{reinterpret_cast<const unsigned long long *>(d_peer_bufs), rank, world, (unsigned long long)epoch};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mlp->dtype == PNODE_F32)
         return dispatch_adj<float>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
-                                   st);
+                                   pc, st);
     if (mlp->dtype == PNODE_F64)
         return dispatch_adj<double>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu,
-                                    d_work, st);
+                                    d_work, pc, st);
     PNODE_REQUIRE(false, "pnode_mlp_rk_adjoint: unsupported dtype %d", mlp->dtype);
+}
+
+int pnode_mlp_rk_adjoint(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                         void *d_lambda, void *d_mu, void *d_work, void *stream) {
+    return pnode_mlp_rk_adjoint_dp(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
+                                   nullptr, 0, 1, 0, stream);
+}
+
+int64_t pnode_peer_buffer_bytes(int world) {
+    return (int64_t)2 * world * PNODE_PEER_NP_MAX * (int64_t)sizeof(double) + (int64_t)2 * world * 8;
 }
 
 int pnode_tanh_probe(const void *d_in, void *d_out, int64_t n, int dtype, void *stream) {

@@ -159,8 +159,9 @@ class FusedMlpRK:
         self.launches += 1
         return sol, ckpt, (sched, nsteps, loop)
 
-    def adjoint(self, gout, ckpt, sched_entry, ntraj):
-        """gout: contiguous [T, ntraj*dim].  Returns (lambda [ntraj*dim], mu [np])."""
+    def adjoint(self, gout, ckpt, sched_entry, ntraj, comm=None):
+        """gout: contiguous [T, ntraj*dim].  Returns (lambda [ntraj*dim], mu [np], reduced) -- `reduced` tells the caller
+        that mu is already summed over the ranks of `comm` (in-kernel peer-memory all-reduce)."""
         sp = self.spec
         sched, nsteps, _ = sched_entry
         T = gout.shape[0]
@@ -174,12 +175,19 @@ class FusedMlpRK:
         if nsteps == 0:
             lam.copy_(gout[-1])
             mu.zero_()
-            return lam, mu
-        _lib.check(self.lib.pnode_mlp_rk_adjoint(C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps,
-                                                 T - 1, gout.data_ptr(), ckpt.data_ptr(), lam.data_ptr(),
-                                                 mu.data_ptr(), self._work.data_ptr(), _stream()))
+            return lam, mu, False
+        peer = getattr(comm, "peer", None) if comm is not None else None
+        if peer is not None:
+            _lib.check(self.lib.pnode_mlp_rk_adjoint_dp(C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps,
+                                                        T - 1, gout.data_ptr(), ckpt.data_ptr(), lam.data_ptr(),
+                                                        mu.data_ptr(), self._work.data_ptr(), peer["ptrs_dev"], comm.rank,
+                                                        comm.world, comm.next_epoch(), _stream()))
+        else:
+            _lib.check(self.lib.pnode_mlp_rk_adjoint(C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps,
+                                                     T - 1, gout.data_ptr(), ckpt.data_ptr(), lam.data_ptr(),
+                                                     mu.data_ptr(), self._work.data_ptr(), _stream()))
         self.launches += 1
-        return lam, mu
+        return lam, mu, peer is not None
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -385,9 +393,9 @@ class FusedCnfRK:
             self._ckpt = None  # ownership moves to the autograd node; the next solve allocates afresh
         return u, sols, state
 
-    def adjoint(self, gout, state, single, nadj=None):
+    def adjoint(self, gout, state, single, nadj=None, comm=None):
         """gout contiguous [T, B*(D+1)].  `nadj`: run only the last nadj steps (the reference's one-element-t rule).
-        Returns (lambda, mu)."""
+        Returns (lambda, mu, reduced)."""
         sp = self.spec
         steps, ntraj = state["steps"], state["ntraj"]
         first = 0 if nadj is None else max(len(steps) - nadj, 0)
@@ -400,7 +408,7 @@ class FusedCnfRK:
         if nsteps == 0:
             lam.copy_(gout[-1])
             mu.zero_()
-            return lam, mu
+            return lam, mu, False
         arr = np.zeros(nsteps, dtype=_STEP_DTYPE)
         for i, (t, h, slot) in enumerate(steps):
             arr[i]["t"], arr[i]["h"] = t, h
@@ -412,9 +420,13 @@ class FusedCnfRK:
         if self._adj_work is None:
             self._adj_work = torch.zeros(int(self.lib.pnode_cnf_rk_adjoint_work_bytes(C.byref(desc))), dtype=torch.uint8,
                                          device=self.device)
-        _lib.check(self.lib.pnode_cnf_rk_adjoint(C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps, T - 1,
-                                                 gout.data_ptr(), state["ckpt"].data_ptr() + first * per_step_bytes,
-                                                 lam.data_ptr(), mu.data_ptr(),
-                                                 self._adj_work.data_ptr(), _stream()))
+        peer = getattr(comm, "peer", None) if comm is not None else None
+        args = (C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps, T - 1, gout.data_ptr(),
+                state["ckpt"].data_ptr() + first * per_step_bytes, lam.data_ptr(), mu.data_ptr(), self._adj_work.data_ptr())
+        if peer is not None:
+            _lib.check(self.lib.pnode_cnf_rk_adjoint_dp(*args, peer["ptrs_dev"], comm.rank, comm.world, comm.next_epoch(),
+                                                        _stream()))
+        else:
+            _lib.check(self.lib.pnode_cnf_rk_adjoint(*args, _stream()))
         self.launches += 1
-        return lam, mu
+        return lam, mu, peer is not None

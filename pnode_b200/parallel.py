@@ -22,6 +22,31 @@ class BatchComm:
         self.world = dist.get_world_size(group)
         self.collectives = 0
         self._count_cache = {}
+        self.peer = None  # set by enable_peer_reduce()
+
+    def enable_peer_reduce(self):
+        """Fuse the mu all-reduce into the tail of the fused adjoint kernels: allocate one symmetric-memory buffer per rank
+        (torch symmetric memory = CUDA VMM allocations mapped into every peer over NVLink), exchange the mappings once,
+        and hand the peer address table to the kernels (include/pnode_b200.h, *_adjoint_dp).  Returns True when active."""
+        if self.world == 1 or self.peer is not None:
+            return self.peer is not None
+        from . import _lib
+        import torch.distributed._symmetric_memory as symm_mem
+
+        nbytes = int(_lib.load().pnode_peer_buffer_bytes(self.world))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        buf.zero_()
+        handle = symm_mem.rendezvous(buf, dist.group.WORLD if self.group is None else self.group)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.peer = {"buf": buf, "handle": handle, "ptrs_dev": int(handle.buffer_ptrs_dev), "epoch": 0}
+        return True
+
+    def next_epoch(self):
+        self.peer["epoch"] += 1
+        self.collectives += 1
+        return self.peer["epoch"]
 
     def allreduce_sum(self, tensor):
         if self.world > 1:

@@ -304,15 +304,16 @@ class _OdeintAdjoint(torch.autograd.Function):
             if ctx.state[0] == "fused":
                 _, fused, ckpt, sched = ctx.state
                 ntraj = ode.n // fused.spec.dim
-                lam, mu = fused.adjoint(grad.view(T, -1), ckpt, sched, ntraj)
+                lam, mu, reduced = fused.adjoint(grad.view(T, -1), ckpt, sched, ntraj, comm=ode.comm)
             elif ctx.state[0] == "fused-cnf":
                 _, fused, st, single = ctx.state
                 nadj = single_time_adjoint_steps(st["loop"]) if single else None
-                lam, mu = fused.adjoint(grad.view(T, -1), st, single, nadj)
+                lam, mu, reduced = fused.adjoint(grad.view(T, -1), st, single, nadj, comm=ode.comm)
             else:
                 lam, mu = ode._adjoint_generic(ctx.state[1], ctx.state[2], grad, T)
-            if ode.comm is not None:
-                ode.comm.allreduce_sum(mu)  # the loss sums over the global batch
+                reduced = False
+            if ode.comm is not None and not reduced:
+                ode.comm.allreduce_sum(mu)  # the loss sums over the global batch (NCCL; the fused sweeps do it in-kernel)
             outs = []
             off = 0
             plist = list(ode._cb_im.params) + (list(ode._cb_ex.params) if ode._cb_ex is not ode._cb_im else [])

@@ -24,6 +24,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     comm = BatchComm()
+    if "--peer" in sys.argv:
+        assert comm.enable_peer_reduce(), "peer-memory all-reduce could not be enabled"
 
     def run(func, u, go, t, method, step, comm_, argv):
         Options.clear_all()
@@ -68,9 +70,19 @@ def main():
     assert rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)) < 1e-10
     for a, b in zip(mine[2], full[2]):
         assert rel_err(a, b) < 1e-10
+    if comm.peer is not None:
+        # the in-kernel all-reduce must be bit-identical on every rank and repeatable (epochs / double buffering)
+        for rep in range(5):
+            again = run(func, shard_batch(u0, rank, world).contiguous(), shard_batch(gout, rank, world, dim=1).contiguous(),
+                        t, "rk4", 0.025, comm, ["-ts_adapt_type", "none"])
+            flat = torch.cat([g.reshape(-1) for g in again[2]]).cuda()
+            ref = flat.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(flat, ref), "mu differs across ranks"
+        assert comm.peer["epoch"] >= 6
     dist.barrier()
     if rank == 0:
-        print("dp_check ok: world=%d collectives=%d" % (world, comm.collectives))
+        print("dp_check ok: world=%d collectives=%d peer=%s" % (world, comm.collectives, comm.peer is not None))
     dist.destroy_process_group()
 
 

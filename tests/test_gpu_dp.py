@@ -11,10 +11,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_batch_sharded_nccl_matches_single_gpu():
+@pytest.mark.parametrize("peer", [False, True])
+def test_batch_sharded_matches_single_gpu(peer):
+    """peer=False: mu via NCCL all-reduce; peer=True: all-reduce fused into the adjoint kernel over NVLink peer memory."""
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "dp_check.py")]
+           "127.0.0.1", "--master-port", "29611" if not peer else "29613", os.path.join(HERE, "dp_check.py")] + \
+          (["--peer"] if peer else [])
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "dp_check ok" in p.stdout
