@@ -152,19 +152,28 @@ class ImplicitSolver:
 class GenericTS:
     """Host-driven stage loop over device kernels.  `ops` is a pnode_b200.device.DeviceOps."""
 
-    def __init__(self, ops, scheme, kind, atol, rtol, comm=None):
+    def __init__(self, ops, scheme, kind, atol, rtol, comm=None, solution_only=False, max_cps=None):
         self.ops = ops
         self.scheme = scheme
         self.kind = kind
         self.atol = atol
         self.rtol = rtol
         self.comm = comm  # optional data-parallel communicator (pnode_b200.parallel.BatchComm)
+        # [PETSc] TSTrajectory memory (SURVEY.md A.7): `-ts_trajectory_solution_only 1` keeps u_n only and recomputes the
+        # stages in the adjoint; `-ts_trajectory_max_cps_ram N` keeps at most N solution checkpoints in HBM and recomputes the
+        # steps in between from the nearest one (uniform stride; PETSc uses a binomial schedule -- the arithmetic, hence the
+        # result, is the same, only the amount of recomputation differs).
+        self.solution_only = solution_only or (max_cps is not None)
+        self.max_cps = max_cps
         self.traj = []
+        self.recomputed_steps = 0
 
     # -- forward ----------------------------------------------------------------------------------------------------
     def solve(self, cb_ex, cb_im, imp, u0, loop: TimeLoop, save_trajectory):
         ops = self.ops
         self.traj = []
+        self._stride = 1
+        self.recomputed_steps = 0
         u = u0.reshape(-1).clone()
         n_local = u.numel()
         n_global = n_local if self.comm is None else self.comm.global_count(n_local)
@@ -187,7 +196,7 @@ class GenericTS:
                 k_fsal = None
                 continue
             if save_trajectory:
-                self.traj.append((t, h, stages))
+                self._record(t, h, u, stages)
             if self.kind == "rk" and self.scheme.fsal:
                 k_fsal = stages[1][-1]
             u = unew
@@ -195,6 +204,42 @@ class GenericTS:
                 sols[loop.last_out_slot] = u
         loop.check_complete()
         return u, sols
+
+    def _record(self, t, h, u, stages):
+        if not self.solution_only:
+            self.traj.append((t, h, stages, None))
+            return
+        self.traj.append((t, h, None, u))
+        if self.max_cps is not None:
+            # thin the stored solutions so that at most max_cps remain: double the stride whenever the budget is exceeded
+            held = [i for i, e in enumerate(self.traj) if e[3] is not None]
+            while len(held) > max(self.max_cps, 1):
+                self._stride *= 2
+                for i in held:
+                    if i % self._stride != 0:
+                        tt, hh, _, _ = self.traj[i]
+                        self.traj[i] = (tt, hh, None, None)
+                held = [i for i, e in enumerate(self.traj) if e[3] is not None]
+
+    def _restore(self, cb_ex, cb_im, imp, idx):
+        """Make step `idx` of the trajectory hold its stage values again, recomputing forward from the nearest stored
+        solution at or before it (same kernels, same arithmetic => identical stages)."""
+        j = idx
+        while self.traj[j][3] is None:
+            j -= 1
+        u = self.traj[j][3]
+        for i in range(j, idx + 1):
+            t, h, stages, u_keep = self.traj[i]
+            if self.kind == "rk":
+                unew, st, _ = self._rk_attempt(cb_ex, t, h, u, None, False)
+            elif self.kind == "arkimex":
+                unew, st, _ = self._ark_attempt(cb_ex, cb_im, imp, t, h, u, False)
+            else:
+                unew, st, _ = self._theta_attempt(cb_im, imp, t, h, u)
+            self.recomputed_steps += 1
+            # keep the stages of every step of the segment: the adjoint consumes them next, in reverse order
+            self.traj[i] = (t, h, st, u_keep)
+            u = unew
 
     def _rk_attempt(self, cb, t, h, u, k_fsal, adaptive):
         sc, ops = self.scheme, self.ops
@@ -277,7 +322,9 @@ class GenericTS:
         for _ in range(nsteps):
             if not self.traj:
                 raise Error(-30, "adjoint requested more steps than the trajectory holds")
-            t, h, stages = self.traj.pop()
+            if self.traj[-1][2] is None:
+                self._restore(cb_ex, cb_im, imp, len(self.traj) - 1)
+            t, h, stages, _ = self.traj.pop()
             if self.kind == "rk":
                 lam = self._rk_adjoint(cb_ex, t, h, stages[0], lam, mu)
             elif self.kind == "arkimex":

@@ -158,7 +158,12 @@ class ODEPetsc(object):
         self._allow_fused = opt.getString("pnode_fused", "1") not in ("0", "false", "no")
         self._imp = ImplicitSolver(self._ops, self._cb_im, self.linear_solver, self.batch_size, self._ksponly,
                                    rtol=opt.getReal("snes_rtol", 1e-8), max_it=opt.getInt("snes_max_it", 50))
-        self._engine = GenericTS(self._ops, self._scheme, kind, self._atol, self._rtol, comm=self.comm)
+        sol_only = opt.getString("ts_trajectory_solution_only", "0") not in ("0", "false", "no")
+        max_cps = opt.getInt("ts_trajectory_max_cps_ram", None)
+        self._engine = GenericTS(self._ops, self._scheme, kind, self._atol, self._rtol, comm=self.comm,
+                                 solution_only=sol_only, max_cps=max_cps)
+        if sol_only or max_cps is not None:
+            self._allow_fused = False  # the fused sweeps always keep stage checkpoints in HBM
 
     def _adaptive(self):
         if self._adapt_none or self._active_kind in ("cn", "beuler"):

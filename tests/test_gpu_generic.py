@@ -89,3 +89,26 @@ def test_imex_torch_solver_on_gpu(name):
     o, p = _pair(argv, [LinearIM(N), TimeMLP(d=N, hidden=24)],
                  dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch"), u0, t, gout, 0.1)
     _compare(p, o, 1e-10)
+
+
+@pytest.mark.parametrize("extra", [["-ts_trajectory_solution_only", "1"], ["-ts_trajectory_max_cps_ram", "2"]])
+def test_bounded_checkpoint_storage_on_gpu(extra):
+    """-ts_trajectory_solution_only / -ts_trajectory_max_cps_ram: less HBM, recomputed stages, identical
+    results (same kernels, same arithmetic)."""
+    from pnode import petsc_adjoint
+
+    func = TimeMLP(d=6, hidden=16)
+    g = torch.Generator().manual_seed(8)
+    u0 = torch.randn(300, 6, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64)
+    gout = torch.randn(3, 300, 6, generator=g, dtype=torch.float64)
+
+    def run(argv):
+        Options.clear_all()
+        Options.insert_args(["-ts_adapt_type", "none"] + argv)
+        return _run(lambda: petsc_adjoint.ODEPetsc(), [func], dict(method="dopri5"), u0, t, gout, 0.05, "cuda")
+
+    full, lean = run([]), run(extra)
+    assert torch.equal(full[0], lean[0]) and torch.equal(full[1], lean[1])
+    assert all(torch.equal(a, b) for a, b in zip(full[2], lean[2]))
+    assert lean[3]._engine.recomputed_steps >= 20 and full[3]._engine.recomputed_steps == 0

@@ -162,3 +162,36 @@ def test_single_time_returns_leading_axis_one(monkeypatch):
     out = ode.odeint(u0, torch.tensor([0.2], dtype=torch.float64))
     assert out.shape == (1, 4, 1, 2)
     assert len(ode._loop.attempts) == 4 and ode._loop.attempts[0][0] == 0.0
+
+
+@pytest.mark.parametrize("extra,expect_recompute", [(["-ts_trajectory_solution_only", "1"], 12),
+                                                    (["-ts_trajectory_max_cps_ram", "3"], None),
+                                                    (["-ts_trajectory_max_cps_ram", "1"], None)])
+def test_bounded_checkpoint_storage_gives_identical_gradients(monkeypatch, extra, expect_recompute):
+    """-ts_trajectory_solution_only / -ts_trajectory_max_cps_ram trade HBM for recomputation; the
+    arithmetic is unchanged, so trajectories and gradients must be IDENTICAL to the store-everything run."""
+    pa = patch_cpu(monkeypatch)
+    func = TimeMLP(d=4, hidden=8)
+    g = torch.Generator().manual_seed(6)
+    u0 = torch.randn(10, 4, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.25, 0.5, 0.75], dtype=torch.float64)
+    gout = torch.randn(4, 10, 4, generator=g, dtype=torch.float64)
+
+    def run(argv):
+        Options.clear_all()
+        Options.insert_args(["-ts_adapt_type", "none"] + argv)
+        f = copy.deepcopy(func)
+        ode = pa.ODEPetsc()
+        ode.setupTS(u0, f, step_size=0.0625, method="rk4", enable_adjoint=True)
+        y0 = u0.clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t)
+        (out * gout).sum().backward()
+        return out.detach(), y0.grad, [p.grad for p in f.parameters()], ode
+
+    full = run([])
+    lean = run(extra)
+    assert torch.equal(full[0], lean[0]) and torch.equal(full[1], lean[1])
+    assert all(torch.equal(a, b) for a, b in zip(full[2], lean[2]))
+    assert lean[3]._engine.recomputed_steps >= 12 and full[3]._engine.recomputed_steps == 0
+    if expect_recompute is not None:
+        assert lean[3]._engine.recomputed_steps == expect_recompute
