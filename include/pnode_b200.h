@@ -70,6 +70,14 @@ int pnode_rk_complete_wrms(void *d_unew, const void *d_u, const void *const *k, 
 int pnode_multi_axpy(void *d_mu, const void *const *srcs, const int64_t *sizes, int nsrc, double coef, int dtype,
                      void *stream);
 
+/* d_out[j] = <vecs[j], w> for j < nvec (<= 16 per call) and d_out[nvec] = <w, w>, accumulated in double, fixed
+ * reduction order.  Replaces [PETSc] VecMDot + VecNorm inside KSPGMRES's classical Gram-Schmidt, which the reference
+ * reaches through SNES/KSP on IJacShell.mult / multTranspose (petsc_adjoint.py:98-177) when linear_solver="petsc".
+ * d_work: pnode_mdot_work_bytes() bytes, zero-initialised once.  `vecs` is a HOST array of device pointers. */
+int64_t pnode_mdot_work_bytes(void);
+int pnode_mdot(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t n, void *d_work, int dtype,
+               void *stream);
+
 /* ----------------------------------------------------------------------------------------------------------------
  * Fused path for tiny-state MLP right-hand sides  f(t,y) = W2 * tanh(W1 * phi(y) + b1) + b2,  phi = cube | identity
  * (the spiral model of examples-pnode/ode_demo_petsc.py:207-230: Linear(2,50)-Tanh-Linear(50,2) applied to y**3).

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "pnode_rk_complete_wrms": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_d), C.POINTER(_d), _i, _i64, _d, _d, _vp,
                                          _vp, _i, _vp]),
     "pnode_multi_axpy": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i, _d, _i, _vp]),
+    "pnode_mdot_work_bytes": (_i64, []),
+    "pnode_mdot": (C.c_int, [_vp, C.POINTER(_vp), _i, _vp, _i64, _vp, _i, _vp]),
     "pnode_mlp_rk_supported": (C.c_int, [_i, _i, _i, _i, _i]),
     "pnode_mlp_rk_forward": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _vp, _i64, _vp, _i, _vp, _vp, _vp]),
     "pnode_mlp_rk_adjoint_work_bytes": (_i64, [C.POINTER(MlpDesc)]),

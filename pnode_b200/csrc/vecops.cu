@@ -325,6 +325,79 @@ static int multi_axpy_impl(void *d_mu, const void *const *srcs, const int64_t *s
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// out[j] = <vecs[j], w>, j < nvec, and out[nvec] = <w, w>: the fused VecMDot + VecNorm of GMRES's classical Gram-Schmidt
+// (one pass over w and the basis instead of nvec+1 reductions), deterministic two-level reduction
+
+constexpr int MDOT_MAX = 16;
+constexpr int MDOT_MAX_BLOCKS = 148 * 4;
+struct MdotWork {
+    unsigned int ticket;
+    unsigned int pad[15];
+    double partial[MDOT_MAX_BLOCKS][MDOT_MAX + 1];
+};
+
+template <typename T>
+struct MdotTable {
+    const T *v[MDOT_MAX];
+    int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) mdot_kernel(double *__restrict__ out, const MdotTable<T> tb,
+                                                   const T *__restrict__ w, int64_t n, MdotWork *__restrict__ work) {
+    double acc[MDOT_MAX + 1];
+#pragma unroll
+    for (int j = 0; j <= MDOT_MAX; ++j) acc[j] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double wi = (double)w[i];
+        acc[MDOT_MAX] = fma(wi, wi, acc[MDOT_MAX]);
+#pragma unroll
+        for (int j = 0; j < MDOT_MAX; ++j)
+            if (j < tb.n) acc[j] = fma((double)tb.v[j][i], wi, acc[j]);
+    }
+    __shared__ double wsum[8][MDOT_MAX + 1];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int j = 0; j <= MDOT_MAX; ++j) {
+        const double s = warp_sum(acc[j]);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x <= MDOT_MAX) {
+        double s = 0.0;
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) s += wsum[wi][threadIdx.x];
+        work->partial[blockIdx.x][threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&work->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x <= MDOT_MAX) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double *)&work->partial[b][0])[threadIdx.x];
+        const int j = threadIdx.x;
+        if (j < tb.n) out[j] = s;
+        if (j == MDOT_MAX) out[tb.n] = s;
+        if (j == 0) work->ticket = 0u;
+    }
+}
+
+template <typename T>
+static int mdot_impl(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t n, void *d_work,
+                     cudaStream_t st) {
+    MdotTable<T> tb;
+    tb.n = nvec;
+    for (int j = 0; j < nvec; ++j) tb.v[j] = static_cast<const T *>(vecs[j]);
+    int grid = stream_grid(n, 256, 4);
+    if (grid > MDOT_MAX_BLOCKS) grid = MDOT_MAX_BLOCKS;
+    mdot_kernel<T><<<grid, 256, 0, st>>>(d_out, tb, static_cast<const T *>(d_w), n, static_cast<MdotWork *>(d_work));
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
 // peak FMA issue-rate probe
 
 template <typename T>
@@ -397,6 +470,18 @@ int pnode_multi_axpy(void *d_mu, const void *const *srcs, const int64_t *sizes, 
     if (dtype == PNODE_F32) return multi_axpy_impl<float>(d_mu, srcs, sizes, nsrc, coef, st);
     if (dtype == PNODE_F64) return multi_axpy_impl<double>(d_mu, srcs, sizes, nsrc, coef, st);
     PNODE_REQUIRE(false, "pnode_multi_axpy: unsupported dtype %d", dtype);
+}
+
+int64_t pnode_mdot_work_bytes(void) { return (int64_t)sizeof(MdotWork); }
+
+int pnode_mdot(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t n, void *d_work, int dtype,
+               void *stream) {
+    PNODE_REQUIRE(nvec >= 0 && nvec <= MDOT_MAX, "pnode_mdot: nvec=%d out of range (max %d per call)", nvec, MDOT_MAX);
+    PNODE_REQUIRE(d_out && d_w && d_work, "pnode_mdot: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PNODE_F32) return mdot_impl<float>(d_out, vecs, nvec, d_w, n, d_work, st);
+    if (dtype == PNODE_F64) return mdot_impl<double>(d_out, vecs, nvec, d_w, n, d_work, st);
+    PNODE_REQUIRE(false, "pnode_mdot: unsupported dtype %d", dtype);
 }
 
 int pnode_peak_fma(int dtype, int iters, double *flops, float *ms) {

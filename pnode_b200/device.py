@@ -38,6 +38,8 @@ class DeviceOps:
         self.code = dtype_code(dtype)
         self._wrms_work = None
         self._sumsq = None
+        self._mdot_work = None
+        self._mdot_out = None
         self.launches = 0
 
     # out = base_coef*base + sum_j coefs[j]*vecs[j]
@@ -95,3 +97,28 @@ class DeviceOps:
         sz = (C.c_int64 * ns)(*[int(s) for s in sizes])
         _lib.check(self.lib.pnode_multi_axpy(mu.data_ptr(), vp, sz, ns, float(coef), self.code, _stream()))
         self.launches += 1
+
+    # [<v_j, w> for j] + [<w, w>] as a HOST list of floats (one device->host read): GMRES Gram-Schmidt coefficients
+    def mdot(self, vecs, w):
+        if self._mdot_work is None:
+            self._mdot_work = torch.zeros(int(self.lib.pnode_mdot_work_bytes()), dtype=torch.uint8, device=self.device)
+            self._mdot_out = torch.zeros(64, dtype=torch.float64, device=self.device)
+        out, k = self._mdot_out, 0
+        n = w.numel()
+        if not vecs:
+            _lib.check(self.lib.pnode_mdot(out.data_ptr(), (C.c_void_p * 1)(), 0, w.data_ptr(), n,
+                                           self._mdot_work.data_ptr(), self.code, _stream()))
+            self.launches += 1
+            return [], float(out[0].item())
+        vals = []
+        while k < len(vecs):
+            chunk = vecs[k:k + 16]
+            vp = (C.c_void_p * len(chunk))(*[v.data_ptr() for v in chunk])
+            _lib.check(self.lib.pnode_mdot(out.data_ptr(), vp, len(chunk), w.data_ptr(), n, self._mdot_work.data_ptr(),
+                                           self.code, _stream()))
+            self.launches += 1
+            host = out[:len(chunk) + 1].tolist()
+            vals += host[:-1]
+            ww = host[-1]
+            k += 16
+        return vals, ww

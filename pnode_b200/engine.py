@@ -38,14 +38,30 @@ class Callbacks:
             out = out.to(u.dtype)
         return out if out.is_contiguous() else out.contiguous()
 
-    def vjp(self, t, u, w, want_u=True):
+    def jvp(self, t, u, v):
+        """RHSJacShell.mult / IJacShell._jvp (petsc_adjoint.py:19-49, 129-144): J v, by forward-mode AD."""
+        self.nfe += 1
+        f = lambda x: self.func(t, x.view(self.tensor_size)).reshape(-1)
+        try:
+            with torch.no_grad():
+                _, jv = torch.func.jvp(f, (u.detach().reshape(-1),), (v.detach().reshape(-1),))
+        except Exception:  # op without a forward-mode rule: the reference's double-backward trick
+            with torch.enable_grad():
+                x = u.detach().reshape(-1).requires_grad_(True)
+                out = f(x)
+                dummy = torch.zeros_like(out, requires_grad=True)
+                (g,) = torch.autograd.grad(out, x, dummy, create_graph=True)
+                (jv,) = torch.autograd.grad(g, dummy, v.detach().reshape(-1))
+        return jv.detach().contiguous()
+
+    def vjp(self, t, u, w, want_u=True, want_params=True):
         """RHSJacShell.multTranspose (petsc_adjoint.py:52-82): one autograd.grad gives J^T w and the per-parameter
         (df/dp)^T w (None for unused parameters, misc.py:9-14)."""
         self.nvjp += 1
         with torch.enable_grad():
             x = u.detach().view(self.tensor_size).requires_grad_(True)
             out = self.func(t, x)
-            inputs = ([x] if want_u else []) + self.params
+            inputs = ([x] if want_u else []) + (self.params if want_params else [])
             if not inputs:
                 return None, []
             g = torch.autograd.grad(out, inputs, w.view(out.shape).to(out.dtype), allow_unused=True)
@@ -57,18 +73,87 @@ class Callbacks:
         return vu, gp
 
 
+def gmres(ops, apply_op, b, rtol=1e-5, atol=1e-50, restart=30, max_it=10000):
+    """Restarted GMRES with classical Gram-Schmidt, zero initial guess, no preconditioner -- [PETSc] KSPGMRES as the reference
+    configures it by default for its matrix-free shells.  The Krylov basis lives in HBM; per inner iteration:
+    one operator application, one fused multi-dot (pnode_mdot: all Gram-Schmidt coefficients + ||w||^2 in one pass, one
+    8(k+2)-byte host read), one pnode_lincomb for the orthogonalisation, one multi-dot for the new norm.  The small
+    Hessenberg least-squares problem is solved on the host with Givens rotations.  Returns (x, iterations, residual)."""
+    x = torch.zeros_like(b)
+    _, bb = ops.mdot([], b)
+    bnorm = math.sqrt(bb)
+    if bnorm == 0.0:
+        return x, 0, 0.0
+    tol = max(rtol * bnorm, atol)
+    r, rnorm, its = b, bnorm, 0
+    while its < max_it:
+        V = [torch.empty_like(b)]
+        ops.lincomb(V[0], None, 0.0, [r], [1.0 / rnorm])
+        H = [[0.0] * restart for _ in range(restart + 1)]
+        cs, sn, g = [0.0] * restart, [0.0] * restart, [rnorm] + [0.0] * restart
+        k_used = 0
+        for k in range(restart):
+            w = apply_op(V[k])
+            h, _ = ops.mdot(V[:k + 1], w)
+            wn = torch.empty_like(w)
+            ops.lincomb(wn, w, 1.0, V[:k + 1], [-c for c in h])
+            _, nn = ops.mdot([], wn)
+            hk1 = math.sqrt(max(nn, 0.0))
+            col = list(h) + [hk1]
+            for i in range(k):  # apply the previous rotations to the new column
+                a, c = col[i], col[i + 1]
+                col[i], col[i + 1] = cs[i] * a + sn[i] * c, -sn[i] * a + cs[i] * c
+            den = math.hypot(col[k], col[k + 1])
+            cs[k], sn[k] = (col[k] / den, col[k + 1] / den) if den != 0.0 else (1.0, 0.0)
+            col[k], col[k + 1] = den, 0.0
+            g[k + 1] = -sn[k] * g[k]
+            g[k] = cs[k] * g[k]
+            for i in range(k + 1):
+                H[i][k] = col[i]
+            its += 1
+            k_used = k + 1
+            rnorm = abs(g[k + 1])
+            if rnorm <= tol or hk1 == 0.0 or its >= max_it:
+                break
+            V.append(torch.empty_like(b))
+            ops.lincomb(V[k + 1], None, 0.0, [wn], [1.0 / hk1])
+        y = [0.0] * k_used
+        for i in range(k_used - 1, -1, -1):
+            acc = g[i] - sum(H[i][j] * y[j] for j in range(i + 1, k_used))
+            y[i] = acc / H[i][i] if H[i][i] != 0.0 else 0.0
+        ops.lincomb(x, x, 1.0, V[:k_used], y)
+        if rnorm <= tol or its >= max_it:
+            break
+        ax = apply_op(x)  # restart: true residual
+        r = torch.empty_like(b)
+        ops.lincomb(r, b, 1.0, [ax], [-1.0])
+        _, rr = ops.mdot([], r)
+        rnorm = math.sqrt(rr)
+        if rnorm <= tol:
+            break
+    return x, its, rnorm
+
+
 class ImplicitSolver:
     """Solve shift*(Y - Z) - f_I(t, Y) = 0 for one implicit stage, and the transposed linearised system for the adjoint.
 
     linear_solver == "torch" (torch_linearsolve.PCShell): f_I is sample-independent; the dense [N,N] Jacobian of sample 0
         (petsc_adjoint.py:479) is inverted once per shift and applied to all samples as ONE GEMM  X <- R @ inv(A)^T
         ("factor once per step size, inverse-apply as tensor-core GEMM").
-    otherwise: dense Newton on the full state (small systems: ROBER-like), linear solves by LU.
+    otherwise ("petsc" / "hpddm"): Newton on the full state.  Small systems (n <= DENSE_SMALL, ROBER-like) assemble the
+        dense Jacobian and solve by LU; larger ones are matrix-free Newton-GMRES like the reference's IJacShell
+        (petsc_adjoint.py:98-196): J x by forward-mode AD (torch.func.jvp; the reference uses the double-backward trick),
+        J^T x by one reverse-mode pass, `gmres` above as the Krylov solver (-ksp_rtol, -ksp_max_it).
     """
 
     DENSE_LIMIT = 8192
+    DENSE_SMALL = 256
 
-    def __init__(self, ops, cb_im, linear_solver, batch_size, ksponly, rtol=1e-8, max_it=50):
+    def __init__(self, ops, cb_im, linear_solver, batch_size, ksponly, rtol=1e-8, max_it=50, ksp_rtol=1e-5,
+                 ksp_max_it=10000):
+        self.ksp_rtol = ksp_rtol
+        self.ksp_max_it = ksp_max_it
+        self.krylov_iterations = 0
         self.ops = ops
         self.cb = cb_im
         self.linear_solver = linear_solver
@@ -120,8 +205,27 @@ class ImplicitSolver:
             R = rhs.view(-1, N)
             # per sample x = A^{-1} r  <=>  X = R A^{-T};   transposed solve: X = R A^{-1}
             return (R @ (Ainv if transpose else Ainv.T)).reshape(-1)
+        if y.numel() > self.DENSE_SMALL:
+            return self._krylov(t, y, shift, rhs.reshape(-1), transpose)
         A = self._dense_matrix(t, y, shift)
         return torch.linalg.solve(A.T if transpose else A, rhs.reshape(-1))
+
+    def _krylov(self, t, y, shift, rhs, transpose):
+        cb, ops = self.cb, self.ops
+        y0 = y.detach()
+
+        def op(v):  # (shift I - J) v   or its transpose
+            if transpose:
+                jv, _ = cb.vjp(t, y0, v, want_params=False)
+            else:
+                jv = cb.jvp(t, y0, v)
+            out = torch.empty_like(v)
+            ops.lincomb(out, v, shift, [jv], [-1.0])
+            return out
+
+        x, its, _ = gmres(ops, op, rhs.contiguous(), rtol=self.ksp_rtol, max_it=self.ksp_max_it)
+        self.krylov_iterations += its
+        return x
 
     def solve(self, t, Z, shift, guess):
         y = guess

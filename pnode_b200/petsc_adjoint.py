@@ -157,7 +157,8 @@ class ODEPetsc(object):
         self._monitor = opt.hasName("ts_monitor")
         self._allow_fused = opt.getString("pnode_fused", "1") not in ("0", "false", "no")
         self._imp = ImplicitSolver(self._ops, self._cb_im, self.linear_solver, self.batch_size, self._ksponly,
-                                   rtol=opt.getReal("snes_rtol", 1e-8), max_it=opt.getInt("snes_max_it", 50))
+                                   rtol=opt.getReal("snes_rtol", 1e-8), max_it=opt.getInt("snes_max_it", 50),
+                                   ksp_rtol=opt.getReal("ksp_rtol", 1e-5), ksp_max_it=opt.getInt("ksp_max_it", 10000))
         sol_only = opt.getString("ts_trajectory_solution_only", "0") not in ("0", "false", "no")
         max_cps = opt.getInt("ts_trajectory_max_cps_ram", None)
         self._engine = GenericTS(self._ops, self._scheme, kind, self._atol, self._rtol, comm=self.comm,

@@ -41,6 +41,15 @@ class FakeOps:
         self.launches += 1
 
 
+def _mdot(self, vecs, w):
+    self.launches += 1
+    wd = w.reshape(-1).double()
+    return [float((v.reshape(-1).double() * wd).sum()) for v in vecs], float((wd * wd).sum())
+
+
+FakeOps.mdot = _mdot
+
+
 def patch_cpu(monkeypatch):
     """Route ODEPetsc onto FakeOps and lift the CUDA-only gate -- for host-logic tests only."""
     import pnode_b200.petsc_adjoint as pa

@@ -112,3 +112,18 @@ def test_bounded_checkpoint_storage_on_gpu(extra):
     assert torch.equal(full[0], lean[0]) and torch.equal(full[1], lean[1])
     assert all(torch.equal(a, b) for a, b in zip(full[2], lean[2]))
     assert lean[3]._engine.recomputed_steps >= 20 and full[3]._engine.recomputed_steps == 0
+
+
+@pytest.mark.parametrize("method", ["cn", "beuler"])
+def test_matrix_free_newton_gmres_on_gpu(method):
+    """Implicit theta methods with the reference's default linear_solver="petsc": matrix-free Newton-GMRES on the GPU
+    (pnode_mdot / pnode_lincomb Krylov kernels, torch forward/reverse-mode J products) vs the oracle's dense Newton."""
+    from _problems import SpiralFunc, spiral_inputs
+
+    func = SpiralFunc(bias_std=0.1)
+    u0, _, gout = spiral_inputs(300)
+    t = torch.tensor([0.0, 0.1, 0.2], dtype=torch.float64)
+    o, p = _pair(["-ts_adapt_type", "none", "-ksp_rtol", "1e-10", "-pnode_fused", "0"], [func],
+                 dict(method=method, implicit_form=True), u0, t, gout[:3], 0.1)
+    assert p[3]._imp.krylov_iterations > 0
+    _compare(p, o, 1e-7)

@@ -114,3 +114,21 @@ def test_kernel_tanh_accuracy(dtype, tol):
     if dtype == torch.float64:  # relative accuracy is kept near zero too (em1 is formed without cancellation)
         rel = err / ref.abs().clamp_min(1e-300)
         assert float(rel[ref != 0].max()) < 2e-13
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n", [5, 4097, 1 << 20])
+def test_mdot_matches_fp64_dots(dtype, n):
+    g = torch.Generator().manual_seed(n)
+    ops = _ops(dtype)
+    w = torch.randn(n, generator=g, dtype=torch.float64).to(dtype)
+    for nv in (0, 1, 7, 16, 31):
+        vs = [torch.randn(n, generator=g, dtype=torch.float64).to(dtype) for _ in range(nv)]
+        for rep in range(2):  # ticket restored between calls
+            vals, ww = ops.mdot([v.cuda() for v in vs], w.cuda())
+        ref = [float((v.double() * w.double()).sum()) for v in vs]
+        assert len(vals) == nv
+        scale = float(w.double().norm()) * (float(vs[0].double().norm()) if nv else 1.0)
+        for a, b in zip(vals, ref):
+            assert abs(a - b) <= 1e-12 * scale
+        assert ww == pytest.approx(float((w.double() ** 2).sum()), rel=1e-12)

@@ -195,3 +195,16 @@ def test_bounded_checkpoint_storage_gives_identical_gradients(monkeypatch, extra
     assert lean[3]._engine.recomputed_steps >= 12 and full[3]._engine.recomputed_steps == 0
     if expect_recompute is not None:
         assert lean[3]._engine.recomputed_steps == expect_recompute
+
+
+@pytest.mark.parametrize("method,ksp_rtol,tol", [("cn", "1e-10", 1e-7), ("beuler", "1e-10", 1e-7), ("cn", None, 1e-3)])
+def test_matrix_free_newton_gmres_matches_dense_oracle(monkeypatch, method, ksp_rtol, tol):
+    """implicit cn / beuler on a state too large for a dense Jacobian (n = 600): matrix-free Newton-GMRES
+    (the reference's IJacShell + KSPGMRES) against the oracle's dense Newton; parity only to the Krylov tolerance."""
+    func = SpiralFunc(bias_std=0.1)
+    u0, _, gout = spiral_inputs(300)
+    t = torch.tensor([0.0, 0.1, 0.2], dtype=torch.float64)
+    argv = ["-ts_adapt_type", "none"] + (["-ksp_rtol", ksp_rtol] if ksp_rtol else [])
+    o, p = _both(monkeypatch, argv, dict(method=method, implicit_form=True), [func], u0, t, gout[:3], 0.1)
+    assert p[3]._imp.krylov_iterations > 0
+    _assert_close(p, o, tol)
