@@ -29,6 +29,9 @@ H = 0.025
 NSTEPS = T_OUT - 1
 STAGES = 4
 DIM, HIDDEN = 2, 50
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE mlp_rk_adj_kernel launch on the default workload, from the
+# `ncu --set full` captures summarised in profiles/r1_ncu_full_spiral_f64_v3.txt / r1_ncu_full_spiral_f32_v2.txt
+NCU_ADJ_TRAFFIC = {("f64", 1 << 20): 772.183552e6 + 19.816192e6, ("f32", 1 << 20): 386.1e6 + 10.5e6}
 METRIC = "fwd+adjoint trajectory-steps/sec"
 UNIT = "trajectory-steps/s"
 
@@ -363,7 +366,9 @@ def run_native(args):
         fma_peak = fl.value / (pms.value * 1e-3) / 1e12
         ach = adj_bytes / (ta * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "mlp_rk_adj_kernel", "achieved": ach, "peak": peaks["hbm_gbs"],
-                            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                            "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                            "traffic": NCU_ADJ_TRAFFIC.get((args.dtype, ntraj)), "algorithmic_bytes": adj_bytes,
+                            "peak_source": peak_kind,
                             "ms_per_launch": ta,
                             "note": "arithmetic intensity ~60 flop/B: the kernel is bound by the %s FMA/transcendental "
                                     "issue rate, not HBM -- see roofline_compute" % args.dtype}
