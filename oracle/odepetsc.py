@@ -76,7 +76,8 @@ class _Callbacks:
     def _lin_solve(self, J, shift, rhs, transpose):
         o = self.o
         N = J.shape[0]
-        A = shift * torch.eye(N, dtype=J.dtype) - J
+        M = self.mass if self.mass is not None else torch.eye(N, dtype=J.dtype)
+        A = shift * M - J
         if transpose:
             A = A.T
         if o.linear_solver == "torch":
@@ -84,12 +85,21 @@ class _Callbacks:
             return torch.linalg.solve(A, R.T).T.reshape(rhs.shape)
         return torch.linalg.solve(A, rhs.reshape(-1)).reshape(rhs.shape)
 
-    def implicit_solve(self, t, Z, shift, guess):
+    @property
+    def mass(self):
+        return self.o.mass
+
+    def implicit_solve(self, t, Z, shift, guess, aff=None):
         o = self.o
         y = guess.clone()
         F0 = None
         for it in range(50):
-            F = shift * (y - Z) - self.f_im(t, y)
+            if self.mass is not None:
+                F = shift * (self.mass @ (y - Z).reshape(-1)).reshape(y.shape) - self.f_im(t, y)
+            else:
+                F = shift * (y - Z) - self.f_im(t, y)
+            if aff is not None:
+                F = F - aff
             fn = float(F.norm())
             if F0 is None:
                 F0 = fn
@@ -123,6 +133,7 @@ class OracleODEPetsc:
         self.imex = None
         self.linear_solver = None
         self.ksponly = self.options.get("snes_type") == "ksponly"
+        self.mass = None
         self._J0 = None
         self.cb = _Callbacks(self)
 
@@ -131,8 +142,7 @@ class OracleODEPetsc:
                 fixed_jacobian=False, matrixfree_jacobian=True, fixed_jacobian_across_solves=None):
         if imex_form and func2 is None:
             raise ValueError("func2 must be provided to enable imex_form=True")  # petsc_adjoint.py:585-586
-        if mass is not None:
-            raise NotImplementedError("oracle: mass matrix (DAE) path is out of scope (SURVEY.md section 8f.2)")
+        self.mass = None if mass is None else mass.reshape(u_tensor.numel(), u_tensor.numel()).to(u_tensor.dtype)
         self.imex = imex_form
         self.linear_solver = linear_solver
         if self.funcIM is not func or self.funcEX is not (func2 if imex_form else func):

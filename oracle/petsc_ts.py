@@ -333,12 +333,17 @@ class OracleTS:
 
     def _theta_attempt(self, ctx, t, u, h):
         theta = 0.5 if self.kind == "cn" else 1.0
+        shift = 1.0 / (h * theta)
+        if getattr(ctx, "mass", None) is not None:
+            # M (u1 - u)/h = (1-theta) f(t,u) + theta f(t+h,u1), M possibly singular (evalIFunction, petsc_adjoint.py:426-431)
+            aff = ((1.0 - theta) / theta) * ctx.f_im(t, u) if theta < 1.0 else None
+            u_new = ctx.implicit_solve(t + h, u, shift, u, aff=aff)
+            return u_new, {"Y": [u, u_new]}, None
         # endpoint form: u1 = u + h[(1-theta) f(t,u) + theta f(t+h,u1)]
         if theta < 1.0:
             Z = u + (h * (1.0 - theta)) * ctx.f_im(t, u)
         else:
             Z = u.clone()
-        shift = 1.0 / (h * theta)
         u_new = ctx.implicit_solve(t + h, Z, shift, u)
         return u_new, {"Y": [u, u_new]}, None
 
@@ -421,6 +426,17 @@ class OracleTS:
         t, h = cp["t"], cp["h"]
         u0, u1 = cp["stages"]["Y"]
         shift = 1.0 / (h * theta)
+        if getattr(ctx, "mass", None) is not None:
+            c = (1.0 - theta) / theta
+            w = ctx.implicit_solve_transpose(t + h, u1, shift, lam)
+            _, vp1 = ctx.vjp_im(t + h, u1, w)
+            mu = mu + ctx.pad_params(vp1, None)
+            lam_n = shift * (ctx.mass.T @ w.reshape(-1)).reshape(w.shape)
+            if theta < 1.0:
+                vu0, vp0 = ctx.vjp_im(t, u0, w)
+                lam_n = lam_n + c * vu0
+                mu = mu + c * ctx.pad_params(vp0, None)
+            return lam_n, mu
         ls = ctx.implicit_solve_transpose(t + h, u1, shift, shift * lam)
         _, vp1 = ctx.vjp_im(t + h, u1, ls)
         mu = mu + (h * theta) * ctx.pad_params(vp1, None)

@@ -163,10 +163,17 @@ class ImplicitSolver:
         self.max_it = max_it
         self.reset()
 
+    mass = None  # dense [n, n] mass matrix of M u' = f(t, u) (petsc_adjoint.py:426-431), theta methods only
+
     def reset(self):
         """Once per odeint: parameters may have changed (petsc_adjoint.py:792-799)."""
         self._J0 = None
         self._inv = {}
+
+    def _mass_times(self, v, transpose=False):
+        if self.mass is None:
+            return v
+        return torch.mv(self.mass.T if transpose else self.mass, v.reshape(-1))
 
     def _block_jacobian(self, t, y):
         if self._J0 is None:
@@ -196,6 +203,8 @@ class ImplicitSolver:
                              "linear_solver='torch' for batched sample-independent operators" % (self.DENSE_LIMIT, n))
         yy = y.detach().clone().view(self.cb.tensor_size)
         J = torch.autograd.functional.jacobian(lambda v: self.cb.func(t, v), yy).reshape(n, n)
+        if self.mass is not None:
+            return self.mass * shift - J
         return torch.eye(n, dtype=J.dtype, device=J.device).mul_(shift) - J
 
     def _apply(self, t, y, shift, rhs, transpose):
@@ -214,25 +223,35 @@ class ImplicitSolver:
         cb, ops = self.cb, self.ops
         y0 = y.detach()
 
-        def op(v):  # (shift I - J) v   or its transpose
+        def op(v):  # (shift M - J) v   or its transpose
             if transpose:
                 jv, _ = cb.vjp(t, y0, v, want_params=False)
             else:
                 jv = cb.jvp(t, y0, v)
             out = torch.empty_like(v)
-            ops.lincomb(out, v, shift, [jv], [-1.0])
+            ops.lincomb(out, self._mass_times(v, transpose), shift, [jv], [-1.0])
             return out
 
         x, its, _ = gmres(ops, op, rhs.contiguous(), rtol=self.ksp_rtol, max_it=self.ksp_max_it)
         self.krylov_iterations += its
         return x
 
-    def solve(self, t, Z, shift, guess):
+    def solve(self, t, Z, shift, guess, aff=None):
+        """Newton on  shift * M (Y - Z) - f(t, Y) - aff = 0   (M = I, aff = 0 unless a mass matrix is set)."""
         y = guess
         f0 = None
         for _ in range(self.max_it):
             F = torch.empty_like(Z)
-            self.ops.lincomb(F, None, 0.0, [y, Z, self.cb.f(t, y)], [shift, -shift, -1.0])
+            if self.mass is None and aff is None:
+                self.ops.lincomb(F, None, 0.0, [y, Z, self.cb.f(t, y)], [shift, -shift, -1.0])
+            else:
+                d0 = torch.empty_like(Z)
+                self.ops.lincomb(d0, None, 0.0, [y, Z], [1.0, -1.0])
+                terms, coefs = [self._mass_times(d0), self.cb.f(t, y)], [shift, -1.0]
+                if aff is not None:
+                    terms.append(aff)
+                    coefs.append(-1.0)
+                self.ops.lincomb(F, None, 0.0, terms, coefs)
             if not self.ksponly:
                 fn = float(torch.linalg.vector_norm(F))
                 if f0 is None:
@@ -412,13 +431,23 @@ class GenericTS:
         return unew, (Y,), sumsq
 
     def _theta_attempt(self, cb, imp, t, h, u):
+        """theta-method, endpoint form: M (X - u) / h = (1 - theta) f(t, u) + theta f(t + h, X)."""
         theta = 0.5 if self.kind == "cn" else 1.0
+        shift = 1.0 / (h * theta)
+        if imp.mass is not None:
+            # a (possibly singular) mass matrix cannot be folded into Z: keep the explicit half as an affine term
+            aff = None
+            if theta < 1.0:
+                aff = torch.empty_like(u)
+                self.ops.lincomb(aff, None, 0.0, [cb.f(t, u)], [(1.0 - theta) / theta])
+            unew = imp.solve(t + h, u, shift, u, aff=aff)
+            return unew, ([u, unew],), None
         if theta < 1.0:
             Z = torch.empty_like(u)
             self.ops.lincomb(Z, u, 1.0, [cb.f(t, u)], [h * (1.0 - theta)])
         else:
             Z = u
-        unew = imp.solve(t + h, Z, 1.0 / (h * theta), u)
+        unew = imp.solve(t + h, Z, shift, u)
         return unew, ([u, unew],), None
 
     # -- adjoint ----------------------------------------------------------------------------------------------------
@@ -501,15 +530,17 @@ class GenericTS:
         theta = 0.5 if self.kind == "cn" else 1.0
         u0, u1 = Y
         shift = 1.0 / (h * theta)
-        rhs = torch.empty_like(lam)
-        ops.lincomb(rhs, lam, shift, [], [])
-        ls = imp.solve_transpose(t + h, u1, shift, rhs)
-        _, gp1 = cb.vjp(t + h, u1, ls, want_u=False)
-        ops.multi_axpy(mu, gp1, cb.sizes, h * theta)
+        c = (1.0 - theta) / theta
+        # w = (shift M - J(u1))^-T lambda ;  lambda_n = shift M^T w + c J(u0)^T w ;  mu += Jp(u1)^T w + c Jp(u0)^T w
+        w = imp.solve_transpose(t + h, u1, shift, lam)
+        _, gp1 = cb.vjp(t + h, u1, w, want_u=False)
+        ops.multi_axpy(mu, gp1, cb.sizes, 1.0)
+        lam_n = torch.empty_like(lam)
+        mw = imp._mass_times(w, transpose=True)
         if theta < 1.0:
-            vu0, gp0 = cb.vjp(t, u0, ls)
-            ops.multi_axpy(mu, gp0, cb.sizes, h * (1.0 - theta))
-            lam_n = torch.empty_like(lam)
-            ops.lincomb(lam_n, ls, 1.0, [vu0], [h * (1.0 - theta)])
-            return lam_n
-        return ls
+            vu0, gp0 = cb.vjp(t, u0, w)
+            ops.multi_axpy(mu, gp0, cb.sizes, c)
+            ops.lincomb(lam_n, mw, shift, [vu0], [c])
+        else:
+            ops.lincomb(lam_n, mw, shift, [], [])
+        return lam_n

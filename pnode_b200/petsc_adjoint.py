@@ -81,8 +81,6 @@ class ODEPetsc(object):
         if imex_form and func2 is None:
             raise ValueError("func2 must be provided to enable imex_form=True")
         _check_device(u_tensor, "ODEPetsc.setupTS: the state tensor")
-        if mass is not None:
-            raise Error(-12, "mass-matrix (DAE) form is not implemented yet (SURVEY.md section 8f.2)")
         if fixed_jacobian_across_solves is not None:
             fixed_jacobian = bool(fixed_jacobian_across_solves)
         self.imex = imex_form
@@ -117,6 +115,9 @@ class ODEPetsc(object):
             else:
                 self.np = self.npIM = self.npEX = self._cb_ex.nparams
             self._fused_checked_for = None
+        if mass is not None:
+            mass = mass.to(device=u_tensor.device, dtype=u_tensor.dtype).reshape(u_tensor.numel(), u_tensor.numel())
+        self.mass = mass
         self.batch_size = batch_size
         self.step_size = step_size
         self.enable_adjoint = enable_adjoint
@@ -161,6 +162,10 @@ class ODEPetsc(object):
                                    ksp_rtol=opt.getReal("ksp_rtol", 1e-5), ksp_max_it=opt.getInt("ksp_max_it", 10000))
         sol_only = opt.getString("ts_trajectory_solution_only", "0") not in ("0", "false", "no")
         max_cps = opt.getInt("ts_trajectory_max_cps_ram", None)
+        if self.mass is not None and kind not in ("cn", "beuler"):
+            raise Error(-12, "mass= (M u' = f) is supported for the implicit theta methods cn / beuler only, as in the "
+                             "reference's DAE example (examples-pnode/pendulum_DAE.py)")
+        self._imp.mass = self.mass
         self._engine = GenericTS(self._ops, self._scheme, kind, self._atol, self._rtol, comm=self.comm,
                                  solution_only=sol_only, max_cps=max_cps)
         if sol_only or max_cps is not None:

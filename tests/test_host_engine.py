@@ -208,3 +208,40 @@ def test_matrix_free_newton_gmres_matches_dense_oracle(monkeypatch, method, ksp_
     o, p = _both(monkeypatch, argv, dict(method=method, implicit_form=True), [func], u0, t, gout[:3], 0.1)
     assert p[3]._imp.krylov_iterations > 0
     _assert_close(p, o, tol)
+
+
+class _Pendulum(torch.nn.Module):
+    """Index-1 pendulum DAE of examples-pnode/pendulum_DAE.py:108-117 with a trainable gravity constant."""
+
+    def __init__(self):
+        super().__init__()
+        self.g = torch.nn.Parameter(torch.tensor(9.81, dtype=torch.float64))
+
+    def forward(self, t, y):
+        g = self.g
+        return torch.stack((y[2], y[3], -y[0] * y[4], -y[1] * y[4] - g,
+                            y[4] * (y[0] ** 2 + y[1] ** 2) + g * y[1] - (y[2] ** 2 + y[3] ** 2)))
+
+
+@pytest.mark.parametrize("method", ["cn", "beuler"])
+def test_mass_matrix_dae_theta_methods(monkeypatch, method):
+    """mass= (M u' = f with singular M), evalIFunction petsc_adjoint.py:426-431, as used by pendulum_DAE.py:119-139."""
+    M = torch.eye(5, dtype=torch.float64)
+    M[-1, -1] = 0.0
+    u0 = torch.tensor([1.0, 0.0, 0.0, 1.0, 1.0 - 0.0], dtype=torch.float64)  # consistent: lambda = |v|^2 - g y = 1
+    t = torch.tensor([0.0, 0.02, 0.05], dtype=torch.float64)
+    gout = torch.tensor([[0.3, -0.2, 0.5, 0.1, 0.0], [1.0, 0.5, -0.3, 0.2, 0.1], [0.7, -1.0, 0.4, 0.3, -0.2]],
+                        dtype=torch.float64)
+    o, p = _both(monkeypatch, ["-ts_adapt_type", "none"], dict(method=method, implicit_form=True, mass=M), [_Pendulum()],
+                 u0, t, gout, 0.01)
+    _assert_close(p, o, 1e-9)
+    # the discrete adjoint of the DAE scheme is the derivative of the discrete map: finite-difference check on g
+    base = (p[0] * gout).sum().item()
+    import pnode_b200.petsc_adjoint as pa
+    f2 = _Pendulum()
+    with torch.no_grad():
+        f2.g.add_(1e-6)
+    ode = pa.ODEPetsc()
+    ode.setupTS(u0, f2, step_size=0.01, method=method, implicit_form=True, mass=M, enable_adjoint=False)
+    pert = (ode.odeint(u0, t) * gout).sum().item()
+    assert (pert - base) / 1e-6 == pytest.approx(p[2][0].item(), rel=1e-4)
