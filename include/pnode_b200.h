@@ -192,6 +192,25 @@ int pnode_cnf_rk_adjoint(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab,
                          void *d_lambda, void *d_mu, void *d_work, void *stream);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * Convolutional ODE block (BASELINE config 4: the SqueezeNext block of examples-pnode/models/sqnxt_PETSc.py:70-121, five
+ * times relu(bn(conv(x))) with nn.BatchNorm2d in TRAIN mode).  On the reference's path evalRHSFunction
+ * (petsc_adjoint.py:393-412) and RHSJacShell.multTranspose (52-82) spend most of their GPU time in cuDNN's one-CTA-per-
+ * channel batch-norm kernels; these entry points are the train-mode BatchNorm2d + ReLU forward / backward as
+ * many-CTA-per-channel HBM-streaming reductions (NCHW, contiguous, H*W a multiple of 16 bytes).
+ *   forward : y = relu(gamma (x - mean_c) / sqrt(var_c + eps) + beta); saves mean_c / inv-std_c; updates
+ *             running_mean / running_var like nn.BatchNorm2d (momentum, unbiased variance) when they are not NULL.
+ *   backward: dx, dgamma, dbeta from dy (gradient w.r.t. the ReLU output), the saved x, y, mean, inv-std.
+ * d_work: pnode_bn_work_bytes(C) bytes of scratch (per-CTA partial sums; reductions are formed in a fixed order).
+ * -------------------------------------------------------------------------------------------------------------- */
+int64_t pnode_bn_work_bytes(int channels);
+int pnode_bn_relu_forward(const void *d_x, void *d_y, const void *d_gamma, const void *d_beta, void *d_running_mean,
+                          void *d_running_var, void *d_save_mean, void *d_save_invstd, int N, int C, int HW, double eps,
+                          double momentum, void *d_work, int dtype, void *stream);
+int pnode_bn_relu_backward(const void *d_dy, const void *d_x, const void *d_y, const void *d_gamma,
+                           const void *d_save_mean, const void *d_save_invstd, void *d_dx, void *d_dgamma,
+                           void *d_dbeta, int N, int C, int HW, void *d_work, int dtype, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Data-parallel variants of the adjoint sweeps: the all-reduce of mu over the GPUs of one NVLink/NVSwitch domain is fused
  * into the tail of the sweep kernel (one-shot all-reduce over peer-mapped symmetric memory: peer stores + system-scope
  * release/acquire flags; no NCCL call, no extra launch).  The reference has no counterpart (single process,

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["vecops.cu", "mlp_rk.cu", "cnf_rk.cu"]
+SOURCES = ["vecops.cu", "mlp_rk.cu", "cnf_rk.cu", "bn_relu.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "pnode_b200.h")]
 LIB = os.path.join(CSRC, "libpnode_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-shared",

@@ -1,0 +1,156 @@
+"""Right-hand-side evaluator for convolutional ODE blocks of the SqueezeNext kind (BASELINE config 4,
+examples-pnode/models/sqnxt_PETSc.py:70-121): a chain of  relu(bn_k(conv_k(x)))  with nn.BatchNorm2d in train mode.
+
+It plugs into the generic time stepper in place of engine.Callbacks: `f(t, u)` (the reference's evalRHSFunction,
+pnode/petsc_adjoint.py:393-412) and `vjp(t, u, w)` (RHSJacShell.multTranspose, 52-82) are evaluated layer by layer WITHOUT an
+autograd graph.  Convolutions stay library calls (cuDNN / cuBLAS through ATen: plain library convs, they are ~15 % of the
+block's time); batch-norm + ReLU forward and backward -- 69 % of the time on the stock path, in cuDNN's one-CTA-per-channel
+kernels -- run in the many-CTA streaming kernels of csrc/bn_relu.cu.  Side effects of the module are reproduced: running_mean /
+running_var / num_batches_tracked advance once per evaluation, adjoint re-evaluations included.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .device import _stream, dtype_code
+from .engine import Callbacks
+
+
+def _layers(func):
+    out = []
+    k = 1
+    while hasattr(func, "conv%d" % k) and hasattr(func, "bn%d" % k):
+        out.append((getattr(func, "conv%d" % k), getattr(func, "bn%d" % k)))
+        k += 1
+    return out
+
+
+def recognise_convblock(func, u_meta):
+    """Structural match (conv1..convK / bn1..bnK and nothing else trainable, stride 1, groups 1, affine BN with running
+    statistics, train mode) + numerical probe of the fused evaluator against a deep copy of the module."""
+    if not isinstance(func, nn.Module) or not u_meta.is_cuda or u_meta.dim() != 4 or not func.training:
+        return None
+    layers = _layers(func)
+    if len(layers) < 1:
+        return None
+    want = []
+    for conv, bn in layers:
+        if not isinstance(conv, nn.Conv2d) or not isinstance(bn, nn.BatchNorm2d):
+            return None
+        if conv.groups != 1 or conv.dilation != (1, 1) or conv.stride != (1, 1) or conv.bias is None or \
+                conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+            return None
+        if not bn.affine or not bn.track_running_stats or bn.momentum is None:
+            return None
+        want += [conv.weight, conv.bias, bn.weight, bn.bias]
+    plist = [p for p in func.parameters() if p.requires_grad]
+    if len(plist) != len(want) or any(a is not b for a, b in zip(plist, want)):
+        return None
+    if any(p.dtype != u_meta.dtype or p.device != u_meta.device for p in want):
+        return None
+    hw = u_meta.shape[2] * u_meta.shape[3]
+    if (hw * u_meta.element_size()) % 16 != 0:
+        return None
+    import copy
+
+    probe = copy.deepcopy(func)
+    cb = ConvBlockCallbacks(copy.deepcopy(func), u_meta.shape, _probe=True)
+    tf32 = torch.backends.cudnn.allow_tf32
+    with torch.no_grad():
+        g = torch.Generator(device="cpu").manual_seed(99)
+        x = torch.randn(tuple(u_meta.shape), generator=g, dtype=torch.float64).to(u_meta)
+        try:
+            # the probe checks the LOGIC of the evaluator, so the library convolutions of both sides run in IEEE fp32 for
+            # its duration (two TF32 algorithm choices alone differ by ~3e-3 on this block)
+            torch.backends.cudnn.allow_tf32 = False
+            ref = probe(0.3, x)
+            got = cb.f(0.3, x.reshape(-1)).view_as(ref)
+        except Exception:
+            return None
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        tol = 1e-4 if u_meta.dtype == torch.float32 else 1e-9
+        if ref.shape != x.shape or not torch.allclose(got, ref, rtol=tol, atol=tol):
+            return None
+        rm_ok = torch.allclose(cb.layers[0][1].running_mean, probe.bn1.running_mean, rtol=tol, atol=tol)
+        if not rm_ok:
+            return None
+    return True
+
+
+class ConvBlockCallbacks(Callbacks):
+    def __init__(self, func, tensor_size, _probe=False):
+        super().__init__(func, tensor_size)
+        self.lib = _lib.load()
+        self.layers = _layers(func)
+        self.code = dtype_code(self.params[0].dtype)
+        cmax = max(bn.num_features for _, bn in self.layers)
+        dev = self.params[0].device
+        self._work = torch.empty(int(self.lib.pnode_bn_work_bytes(cmax)), dtype=torch.uint8, device=dev)
+        self.launches = 0
+
+    # -- one layer -----------------------------------------------------------------------------------------------
+    def _bn_relu_fwd(self, z, bn):
+        N, Cc, H, W = z.shape
+        y = torch.empty_like(z)
+        mean = torch.empty(Cc, dtype=z.dtype, device=z.device)
+        invstd = torch.empty(Cc, dtype=z.dtype, device=z.device)
+        _lib.check(self.lib.pnode_bn_relu_forward(z.data_ptr(), y.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                                  bn.running_mean.data_ptr(), bn.running_var.data_ptr(), mean.data_ptr(),
+                                                  invstd.data_ptr(), N, Cc, H * W, float(bn.eps), float(bn.momentum),
+                                                  self._work.data_ptr(), self.code, _stream()))
+        bn.num_batches_tracked += 1
+        self.launches += 2
+        return y, mean, invstd
+
+    def _forward(self, t, u, save):
+        x = u.view(self.tensor_size)
+        saved = []
+        for conv, bn in self.layers:
+            z = torch.nn.functional.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding)
+            if not z.is_contiguous():
+                z = z.contiguous()
+            y, mean, invstd = self._bn_relu_fwd(z, bn)
+            if save:
+                saved.append((x, z, y, mean, invstd))
+            x = y
+        return x, saved
+
+    # -- the two closures the engine needs ---------------------------------------------------------------------------
+    def f(self, t, u):
+        self.nfe += 1
+        if hasattr(self.func, "nfe"):
+            self.func.nfe += 1
+        with torch.no_grad():
+            out, _ = self._forward(t, u, save=False)
+        return out.reshape(-1)
+
+    def vjp(self, t, u, w, want_u=True, want_params=True):
+        self.nvjp += 1
+        if hasattr(self.func, "nfe"):
+            self.func.nfe += 1  # the reference's adjoint re-evaluates func once per stage (petsc_adjoint.py:68)
+        with torch.no_grad():
+            out, saved = self._forward(t, u, save=True)
+            dy = w.view(out.shape)
+            if not dy.is_contiguous():
+                dy = dy.contiguous()
+            grads = []
+            for (conv, bn), (x, z, y, mean, invstd) in zip(reversed(self.layers), reversed(saved)):
+                N, Cc, H, W = z.shape
+                dz = torch.empty_like(z)
+                dgamma = torch.empty(Cc, dtype=z.dtype, device=z.device)
+                dbeta = torch.empty(Cc, dtype=z.dtype, device=z.device)
+                _lib.check(self.lib.pnode_bn_relu_backward(dy.data_ptr(), z.data_ptr(), y.data_ptr(), bn.weight.data_ptr(),
+                                                           mean.data_ptr(), invstd.data_ptr(), dz.data_ptr(),
+                                                           dgamma.data_ptr(), dbeta.data_ptr(), N, Cc, H * W,
+                                                           self._work.data_ptr(), self.code, _stream()))
+                self.launches += 2
+                dx, dw, db = torch.ops.aten.convolution_backward(
+                    dz, x, conv.weight, [conv.out_channels], list(conv.stride), list(conv.padding), list(conv.dilation),
+                    False, [0, 0], 1, [True, True, True])
+                grads = [dw, db, dgamma, dbeta] + grads
+                dy = dx if dx.is_contiguous() else dx.contiguous()
+        vu = dy.reshape(-1) if want_u else None
+        return vu, (grads if want_params else [])

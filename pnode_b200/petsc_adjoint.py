@@ -20,6 +20,7 @@ import torch.nn as nn
 from . import tableaux
 from .controller import TimeLoop
 from .device import DeviceOps
+from .convblock import ConvBlockCallbacks, recognise_convblock
 from .engine import Callbacks, GenericTS, ImplicitSolver
 from .errors import Error
 from .fused import FusedCnfRK, FusedMlpRK, recognise_cnf, recognise_mlp
@@ -68,6 +69,8 @@ class ODEPetsc(object):
         self._engine = None
         self._fused = None
         self._fused_spec = None
+        self._convblock_cache = {}
+        self._rhs_kind = "torch"
         self._fused_kind = None
         self._fused_checked_for = None
         self._cb_ex = self._cb_im = self._imp = None
@@ -108,6 +111,14 @@ class ODEPetsc(object):
             self._ops = DeviceOps(self.device, self.tensor_dtype)
         if funcs_changed or meta_changed:
             self._cb_im = Callbacks(self.funcIM, self.tensor_size)
+            self._rhs_kind = "torch"
+            if not imex_form and Options().getString("pnode_fused", "1") not in ("0", "false", "no"):
+                # convolutional ODE block: same generic stage loop, hand-written BN+ReLU kernels inside f / vjp
+                key = (id(func), tuple(u_tensor.shape), u_tensor.dtype)
+                if key in self._convblock_cache or recognise_convblock(func, u_tensor):
+                    self._convblock_cache[key] = True
+                    self._cb_im = ConvBlockCallbacks(func, self.tensor_size)
+                    self._rhs_kind = "convblock"
             self._cb_ex = self._cb_im if self.funcEX is self.funcIM else Callbacks(self.funcEX, self.tensor_size)
             if imex_form:
                 self.npIM, self.npEX = self._cb_im.nparams, self._cb_ex.nparams
@@ -242,7 +253,7 @@ class ODEPetsc(object):
                 out = torch.stack([sols[k].view(self.tensor_size) for k in range(T)], dim=0)
             st["loop"] = loop
             return out, ("fused-cnf", fused, st, T == 1)
-        self.path = "generic"
+        self.path = "generic" if self._rhs_kind == "torch" else "generic+" + self._rhs_kind + "-rhs"
         self._imp.reset()
         loop = TimeLoop(times, self.step_size, self._adaptive(), self._scheme.order if self._scheme else 1,
                         self.tensor_dtype == torch.float64, self._max_reject)

@@ -81,6 +81,7 @@ def test_config4_cifar_ode_block_rk4(dtype, tol):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     assert p[0].shape == (1, B, C, HW, HW)
+    assert p[3].path == "generic+convblock-rhs"  # hand-written BN+ReLU kernels inside f / vjp (csrc/bn_relu.cu)
     # conv biases feeding a BatchNorm have an exactly-zero gradient (pure rounding noise on both sides): compare mu as a
     # whole vector, not parameter by parameter
     _compare(p, o, tol, per_param=False)
@@ -105,3 +106,73 @@ def test_config5_sinode_ks_imex(name):
                                           fixed_jacobian_across_solves=True), u0, t, gout, 0.2)
     assert p[3].npIM == 0 and p[3].npEX == 146464  # npEX = 146,464 at N = 64
     _compare(p, o, 1e-9)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", [(256, 16, 32, 32), (7, 32, 4, 4), (3, 5, 2, 2)])
+def test_bn_relu_kernels_match_torch(dtype, shape):
+    """csrc/bn_relu.cu against torch's train-mode batch_norm + relu and its autograd backward (same inputs, fp64 1e-11)."""
+    import ctypes as C
+
+    from pnode_b200 import _lib
+
+    lib = _lib.load()
+    N, Cc, H, W = shape
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(shape, generator=g, dtype=torch.float64).to(dtype).cuda()
+    dy = torch.randn(shape, generator=g, dtype=torch.float64).to(dtype).cuda()
+    gamma = (torch.rand(Cc, generator=g, dtype=torch.float64) + 0.5).to(dtype).cuda()
+    beta = torch.randn(Cc, generator=g, dtype=torch.float64).to(dtype).cuda()
+    rm0, rv0 = torch.zeros(Cc, dtype=dtype).cuda(), torch.ones(Cc, dtype=dtype).cuda()
+    # torch reference
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    yr = torch.relu(torch.nn.functional.batch_norm(xr, rm, rv, gr, br, True, 0.1, 1e-5))
+    yr.backward(dy)
+    # kernels
+    work = torch.empty(int(lib.pnode_bn_work_bytes(Cc)), dtype=torch.uint8, device="cuda")
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    mean, invstd = torch.empty(Cc, dtype=dtype).cuda(), torch.empty(Cc, dtype=dtype).cuda()
+    dg, db = torch.empty(Cc, dtype=dtype).cuda(), torch.empty(Cc, dtype=dtype).cuda()
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    code = 0 if dtype == torch.float32 else 1
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.pnode_bn_relu_forward(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(),
+                                         rv2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), N, Cc, H * W, 1e-5, 0.1,
+                                         work.data_ptr(), code, st))
+    _lib.check(lib.pnode_bn_relu_backward(dy.data_ptr(), x.data_ptr(), y.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                          invstd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), N, Cc, H * W,
+                                          work.data_ptr(), code, st))
+    tol = 1e-11 if dtype == torch.float64 else 2e-5
+    assert rel_err(y, yr) < tol and rel_err(dx, xr.grad) < tol * 10
+    assert rel_err(dg, gr.grad) < tol * 10 and rel_err(db, br.grad) < tol * 10
+    assert rel_err(rm2, rm) < tol * 10 and rel_err(rv2, rv) < tol * 10
+
+
+def test_config4_fused_rhs_equals_stock_module_path():
+    """The conv-block evaluator vs the same module driven through torch autograd (-pnode_fused 0), both on the GPU."""
+    from pnode import petsc_adjoint
+
+    C, HW, B = 32, 8, 16
+    func = OdeConvBlock(C, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(B, C, HW, HW, generator=g, dtype=torch.float64)
+    gout = torch.randn(2, B, C, HW, HW, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    res = []
+    for argv in (["-ts_adapt_type", "none"], ["-ts_adapt_type", "none", "-pnode_fused", "0"]):
+        Options.clear_all()
+        Options.insert_args(argv)
+        f = copy.deepcopy(func).cuda()
+        ode = petsc_adjoint.ODEPetsc()
+        ode.setupTS(u0.cuda(), f, step_size=0.25, method="rk4", enable_adjoint=True)
+        y0 = u0.cuda().clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t.cuda())
+        (out * gout.cuda()).sum().backward()
+        res.append((out.detach(), y0.grad, [p.grad for p in f.parameters()], ode, f))
+    a, b = res
+    assert a[3].path == "generic+convblock-rhs" and b[3].path == "generic"
+    _compare(a, b, 1e-9, per_param=False)
+    assert a[4].nfe == b[4].nfe == 32 and int(a[4].bn3.num_batches_tracked) == int(b[4].bn3.num_batches_tracked) == 32
+    assert rel_err(a[4].bn5.running_var, b[4].bn5.running_var) < 1e-9
