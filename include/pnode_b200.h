@@ -211,6 +211,47 @@ int pnode_bn_relu_backward(const void *d_dy, const void *d_x, const void *d_y, c
                            void *d_dbeta, int N, int C, int HW, void *d_work, int dtype, void *stream);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * Whole right-hand side of a convolutional ODE block and its vector-Jacobian products (csrc/conv_block.cu): a chain of
+ * relu(bn_k(conv_k(.))) with stride-1 "same" convolutions of kernel 1x1, (1,3) or (3,1) and train-mode BatchNorm2d
+ * (sqnxt_PETSc.py:70-121).  One kernel per layer: BatchNorm+ReLU of the previous layer applied on load, convolution,
+ * bias, batch statistics of the next BatchNorm in the epilogue; relu(bn(z)) is never written between layers.
+ *   pnode_convblock_forward  replaces evalRHSFunction for this module family (petsc_adjoint.py:393-412) and, with d_base,
+ *                            the [PETSc] VecMAXPY that follows it in TSStep_RK:   k = f(x);  out = base_coef*base + k_coef*k
+ *   pnode_convblock_vjp      replaces RHSJacShell.multTranspose (petsc_adjoint.py:52-82: forward re-evaluation + backward)
+ *                            and RHSJacPShell.multTranspose + [PETSc] VecAXPY on mu (341-363):
+ *                            vu = (df/dx)^T w;   grads = (df/dp)^T w   or   grads += coef * (df/dp)^T w  (accumulate != 0)
+ * Both advance running_mean / running_var / num_batches_tracked of every layer once, like the module's forward.
+ * Parameter order of d_grads = func.parameters(): per layer conv.weight [cout,cin,kh,kw], conv.bias, bn.weight, bn.bias.
+ * Tensors are NCHW contiguous, 16-byte aligned; W a power of two in 4..128; channel counts multiples of 4.
+ * d_work: pnode_convblock_work_bytes() bytes, zero-initialised once by the caller (holds z_k, the per-channel BatchNorm
+ * coefficients, per-CTA partial sums and a ticket counter the kernels restore).
+ * -------------------------------------------------------------------------------------------------------------- */
+#define PNODE_CONV_MAX_LAYERS 8
+typedef struct pnode_conv_layer {
+    int32_t cin, cout, kh, kw, ph, pw;
+    const void *d_weight, *d_bias;          /* conv */
+    const void *d_gamma, *d_beta;           /* BatchNorm affine */
+    void *d_running_mean, *d_running_var;   /* may be NULL */
+    void *d_num_batches_tracked;            /* int64 on the device, may be NULL */
+    double eps, momentum;
+} pnode_conv_layer;
+
+typedef struct pnode_convblock_desc {
+    int32_t nlayers, dtype;
+    int32_t N, H, W, reserved;
+    pnode_conv_layer layer[PNODE_CONV_MAX_LAYERS];
+} pnode_convblock_desc;
+
+int64_t pnode_convblock_work_bytes(const pnode_convblock_desc *desc);  /* -1: unsupported shape (pnode_last_error) */
+int64_t pnode_convblock_param_count(const pnode_convblock_desc *desc);
+/* d_out (may be NULL) = base_coef * d_base + k_coef * f(x)  (d_base NULL: d_out = f(x));  d_k (may be NULL) = f(x) */
+int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, void *d_out, const void *d_base,
+                            double base_coef, double k_coef, void *d_k, void *d_work, void *stream);
+/* d_vu (may be NULL: parameter gradients only); d_grads (may be NULL: state VJP only) [param_count] */
+int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads,
+                        double coef, int accumulate, void *d_work, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Data-parallel variants of the adjoint sweeps: the all-reduce of mu over the GPUs of one NVLink/NVSwitch domain is fused
  * into the tail of the sweep kernel (one-shot all-reduce over peer-mapped symmetric memory: peer stores + system-scope
  * release/acquire flags; no NCCL call, no extra launch).  The reference has no counterpart (single process,

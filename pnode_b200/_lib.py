@@ -29,6 +29,20 @@ class CnfDesc(C.Structure):
                                           "d_hgb2", "d_e")]
 
 
+CONV_MAX_LAYERS = 8
+
+
+class ConvLayer(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("cin", "cout", "kh", "kw", "ph", "pw")] + \
+               [(n, C.c_void_p) for n in ("d_weight", "d_bias", "d_gamma", "d_beta", "d_running_mean", "d_running_var",
+                                          "d_num_batches_tracked")] + [("eps", C.c_double), ("momentum", C.c_double)]
+
+
+class ConvBlockDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nlayers", "dtype", "N", "H", "W", "reserved")] + \
+               [("layer", ConvLayer * CONV_MAX_LAYERS)]
+
+
 class Step(C.Structure):
     _fields_ = [("t", C.c_double), ("h", C.c_double), ("out_slot", C.c_int32), ("in_slot", C.c_int32)]
 
@@ -59,6 +73,10 @@ _SIGNATURES = {
     "pnode_bn_work_bytes": (_i64, [_i]),
     "pnode_bn_relu_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp, _i, _vp]),
     "pnode_bn_relu_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "pnode_convblock_work_bytes": (_i64, [C.POINTER(ConvBlockDesc)]),
+    "pnode_convblock_param_count": (_i64, [C.POINTER(ConvBlockDesc)]),
+    "pnode_convblock_forward": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp]),
+    "pnode_convblock_vjp": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
     "pnode_peer_buffer_bytes": (_i64, [_i]),
     "pnode_mlp_rk_adjoint_dp": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _i, _i, C.c_uint64, _vp]),

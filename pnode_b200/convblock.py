@@ -2,11 +2,16 @@
 examples-pnode/models/sqnxt_PETSc.py:70-121): a chain of  relu(bn_k(conv_k(x)))  with nn.BatchNorm2d in train mode.
 
 It plugs into the generic time stepper in place of engine.Callbacks: `f(t, u)` (the reference's evalRHSFunction,
-pnode/petsc_adjoint.py:393-412) and `vjp(t, u, w)` (RHSJacShell.multTranspose, 52-82) are evaluated layer by layer WITHOUT an
-autograd graph.  Convolutions stay library calls (cuDNN / cuBLAS through ATen: plain library convs, they are ~15 % of the
-block's time); batch-norm + ReLU forward and backward -- 69 % of the time on the stock path, in cuDNN's one-CTA-per-channel
-kernels -- run in the many-CTA streaming kernels of csrc/bn_relu.cu.  Side effects of the module are reproduced: running_mean /
-running_var / num_batches_tracked advance once per evaluation, adjoint re-evaluations included.
+pnode/petsc_adjoint.py:393-412) and `vjp(t, u, w)` (RHSJacShell.multTranspose, 52-82) are evaluated WITHOUT an autograd graph.
+
+Two implementations, both on the GPU:
+  * native (`self.native`, the SqueezeNext shapes: 1x1 / (1,3) / (3,1) stride-1 same convolutions, W a power of two, channels
+    multiples of 4): the whole chain -- convolutions, BatchNorm statistics, BatchNorm+ReLU forward and backward, weight
+    gradients -- runs in the hand-written kernels of csrc/conv_block.cu through pnode_convblock_forward / pnode_convblock_vjp
+    (one C call per evaluation; no library convolution);
+  * otherwise: library convolutions (ATen) + the BatchNorm+ReLU kernels of csrc/bn_relu.cu, layer by layer.
+Side effects of the module are reproduced: running_mean / running_var / num_batches_tracked advance once per evaluation,
+adjoint re-evaluations included.
 """
 import ctypes as C
 
@@ -90,6 +95,76 @@ class ConvBlockCallbacks(Callbacks):
         dev = self.params[0].device
         self._work = torch.empty(int(self.lib.pnode_bn_work_bytes(cmax)), dtype=torch.uint8, device=dev)
         self.launches = 0
+        # native whole-chain kernels (csrc/conv_block.cu) when the shapes are the SqueezeNext ones
+        self.native = False
+        self._desc = None
+        self._cwork = None
+        from .options import Options
+
+        if len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4 and \
+                Options().getString("pnode_convblock_native", "1") not in ("0", "false", "no"):
+            desc = self._make_desc()
+            nbytes = int(self.lib.pnode_convblock_work_bytes(C.byref(desc)))
+            if nbytes >= 0 and int(self.lib.pnode_convblock_param_count(C.byref(desc))) == self.nparams:
+                self.native = True
+                self._desc = desc
+                self._cwork = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+
+    def _make_desc(self):
+        d = _lib.ConvBlockDesc()
+        d.nlayers = len(self.layers)
+        d.dtype = self.code
+        d.N, d.H, d.W = int(self.tensor_size[0]), int(self.tensor_size[2]), int(self.tensor_size[3])
+        for k, (conv, bn) in enumerate(self.layers):
+            l = d.layer[k]
+            l.cin, l.cout = conv.in_channels, conv.out_channels
+            l.kh, l.kw = conv.kernel_size
+            l.ph, l.pw = conv.padding
+            l.eps, l.momentum = float(bn.eps), float(bn.momentum)
+        self._refresh_pointers(d)
+        return d
+
+    def _refresh_pointers(self, d):
+        """Parameters are borrowed, never copied: re-read their addresses before every call."""
+        for k, (conv, bn) in enumerate(self.layers):
+            l = d.layer[k]
+            l.d_weight, l.d_bias = conv.weight.data_ptr(), conv.bias.data_ptr()
+            l.d_gamma, l.d_beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+            l.d_running_mean, l.d_running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            l.d_num_batches_tracked = bn.num_batches_tracked.data_ptr()
+
+    def _native_f(self, u, out=None, base=None, base_coef=0.0, k_coef=1.0, k=None):
+        self._refresh_pointers(self._desc)
+        if out is None and k is None:
+            out = torch.empty_like(u)
+        _lib.check(self.lib.pnode_convblock_forward(C.byref(self._desc), u.data_ptr(), None if out is None else out.data_ptr(),
+                                                    None if base is None else base.data_ptr(), float(base_coef), float(k_coef),
+                                                    None if k is None else k.data_ptr(), self._cwork.data_ptr(), _stream()))
+        self.launches += len(self.layers) + 1
+        return out
+
+    def _native_vjp(self, u, w, want_u, grads, coef, accumulate):
+        self._refresh_pointers(self._desc)
+        if not w.is_contiguous():
+            w = w.contiguous()
+        vu = torch.empty_like(u) if want_u else None
+        _lib.check(self.lib.pnode_convblock_vjp(C.byref(self._desc), u.data_ptr(), w.data_ptr(),
+                                                None if vu is None else vu.data_ptr(),
+                                                None if grads is None else grads.data_ptr(), float(coef), int(accumulate),
+                                                self._cwork.data_ptr(), _stream()))
+        L = len(self.layers)
+        self.launches += L + 1 + (L if grads is not None else 0) + (L if want_u else L - 1) + (1 if grads is not None else 0)
+        return vu
+
+    def vjp_accumulate(self, t, u, w, mu, coef):
+        """vjp + `mu += coef * (df/dp)^T w` in the same call (the engine uses it when present): J^T w is returned."""
+        if not self.native:
+            vu, gp = self.vjp(t, u, w)
+            return vu, gp
+        self.nvjp += 1
+        if hasattr(self.func, "nfe"):
+            self.func.nfe += 1
+        return self._native_vjp(u, w, True, mu, coef, True), None
 
     # -- one layer -----------------------------------------------------------------------------------------------
     def _bn_relu_fwd(self, z, bn):
@@ -123,6 +198,8 @@ class ConvBlockCallbacks(Callbacks):
         self.nfe += 1
         if hasattr(self.func, "nfe"):
             self.func.nfe += 1
+        if self.native:
+            return self._native_f(u)
         with torch.no_grad():
             out, _ = self._forward(t, u, save=False)
         return out.reshape(-1)
@@ -131,6 +208,10 @@ class ConvBlockCallbacks(Callbacks):
         self.nvjp += 1
         if hasattr(self.func, "nfe"):
             self.func.nfe += 1  # the reference's adjoint re-evaluates func once per stage (petsc_adjoint.py:68)
+        if self.native:
+            grads = torch.empty(self.nparams, dtype=u.dtype, device=u.device) if want_params else None
+            vu = self._native_vjp(u, w, want_u, grads, 1.0, False)
+            return vu, (list(torch.split(grads, self.sizes)) if want_params else [])
         with torch.no_grad():
             out, saved = self._forward(t, u, save=True)
             dy = w.view(out.shape)

@@ -482,8 +482,12 @@ class GenericTS:
             else:
                 ops.lincomb(w, None, 0.0, [vu[j] for j in later], [sc.A[j][i] * coef[j] for j in later])
                 coef[i] = h
-            vu[i], gp = cb.vjp(t + sc.c[i] * h, Y[i], w)
-            ops.multi_axpy(mu, gp, cb.sizes, coef[i])
+            if hasattr(cb, "vjp_accumulate"):  # RHS evaluator that adds coef * Jp^T w into mu itself
+                vu[i], gp = cb.vjp_accumulate(t + sc.c[i] * h, Y[i], w, mu, coef[i])
+            else:
+                vu[i], gp = cb.vjp(t + sc.c[i] * h, Y[i], w)
+            if gp is not None:
+                ops.multi_axpy(mu, gp, cb.sizes, coef[i])
         live = [i for i in range(s) if vu[i] is not None]
         lam_n = torch.empty_like(lam)
         ops.lincomb(lam_n, lam, 1.0, [vu[i] for i in live], [coef[i] for i in live])

@@ -1,0 +1,122 @@
+"""csrc/conv_block.cu through the C ABI (pnode_convblock_forward / pnode_convblock_vjp) against the stock torch module and its
+autograd backward on the same inputs: the whole SqueezeNext ODE-block right-hand side (convolutions + train-mode BatchNorm + ReLU),
+its state VJP, every parameter gradient, and the BatchNorm side effects.  fp64: 1e-10; fp32: 1e-4 (IEEE fp32 library reference)."""
+import copy
+import ctypes as C
+
+import pytest
+import torch
+
+from _problems import rel_err
+from _workloads import OdeConvBlock
+
+pytestmark = pytest.mark.gpu
+
+
+def _callbacks(func, shape):
+    from pnode_b200.convblock import ConvBlockCallbacks
+
+    cb = ConvBlockCallbacks(func, torch.Size(shape))
+    assert cb.native, "the conv-block kernels must accept this shape"
+    return cb
+
+
+def _reference(func, x, w):
+    f = copy.deepcopy(func)
+    xr = x.clone().requires_grad_(True)
+    out = f(0.0, xr)
+    out.backward(w)
+    return out.detach(), xr.grad, [p.grad for p in f.parameters()], f
+
+
+# (N, C, H, W): full tiles, partial tiles / partial warps, one-lane rows, the four CIFAR block aspect ratios (scaled down)
+SHAPES = [(16, 32, 8, 8), (3, 16, 6, 8), (2, 16, 4, 4), (5, 32, 16, 32), (4, 64, 16, 16), (8, 128, 8, 8), (16, 256, 4, 4),
+          (1, 16, 1, 4), (2, 32, 3, 64)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_rhs_and_vjp_match_torch(shape, dtype, tol):
+    N, Cc, H, W = shape
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        func = OdeConvBlock(Cc, dtype=dtype, seed=N).cuda()
+        with torch.no_grad():  # non-trivial affine parameters and biases
+            g = torch.Generator().manual_seed(7)
+            for m in func.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.weight.copy_((torch.rand(m.num_features, generator=g, dtype=torch.float64) + 0.5).to(dtype))
+                    m.bias.copy_((0.3 * torch.randn(m.num_features, generator=g, dtype=torch.float64)).to(dtype))
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(shape, generator=g, dtype=torch.float64).to(dtype).cuda()
+        w = torch.randn(shape, generator=g, dtype=torch.float64).to(dtype).cuda()
+        out_r, vu_r, gp_r, f_r = _reference(func, x, w)
+        mine = copy.deepcopy(func)
+        cb = _callbacks(mine, shape)
+        out = cb.f(0.0, x.reshape(-1)).view(shape)
+        vu, gp = cb.vjp(0.0, x.reshape(-1), w.reshape(-1))
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert rel_err(out, out_r) < tol, ("f", rel_err(out, out_r))
+    assert rel_err(vu.view(shape), vu_r) < tol * 10, ("J^T w", rel_err(vu.view(shape), vu_r))
+    flat = lambda gs: torch.cat([q.detach().double().reshape(-1) for q in gs])
+    assert rel_err(flat(gp), flat(gp_r)) < tol * 10, ("Jp^T w", rel_err(flat(gp), flat(gp_r)))
+    names = [n for n, _ in mine.named_parameters()]
+    for n, a, b in zip(names, gp, gp_r):
+        if n.endswith("conv1.bias") or ".bias" in n and "conv" in n:
+            continue  # a conv bias feeding a BatchNorm has an exactly-zero gradient: rounding noise on both sides
+        assert rel_err(a.view_as(b), b) < tol * 50, (n, rel_err(a.view_as(b), b))
+    # side effects: f advanced the statistics once, vjp (forward re-evaluation) once more; the reference module once
+    assert int(mine.bn3.num_batches_tracked) == 2 and int(f_r.bn3.num_batches_tracked) == 1
+    again = copy.deepcopy(func)
+    again(0.0, x), again(0.0, x)
+    for k in range(1, 6):
+        a, b = getattr(mine, "bn%d" % k), getattr(again, "bn%d" % k)
+        assert rel_err(a.running_mean, b.running_mean) < tol * 10 and rel_err(a.running_var, b.running_var) < tol * 10
+
+
+def test_fused_stage_combination_and_mu_accumulation():
+    """pnode_convblock_forward with d_base (Y = base_coef*base + k_coef*f(x), k = f(x)) and pnode_convblock_vjp accumulating
+    coef * Jp^T w into an existing mu: the two fusions the RK stage loop uses."""
+    shape = (4, 32, 8, 16)
+    dtype = torch.float64
+    func = OdeConvBlock(shape[1], dtype=dtype).cuda()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g, dtype=dtype).cuda()
+    base = torch.randn(shape, generator=g, dtype=dtype).cuda()
+    w = torch.randn(shape, generator=g, dtype=dtype).cuda()
+    out_r, vu_r, gp_r, _ = _reference(func, x, w)
+    cb = _callbacks(copy.deepcopy(func), shape)
+    y, k = torch.empty_like(x), torch.empty_like(x)
+    cb._native_f(x.reshape(-1), out=y, base=base, base_coef=1.0, k_coef=0.5, k=k)
+    assert rel_err(k, out_r) < 1e-10 and rel_err(y, base + 0.5 * out_r) < 1e-10
+    mu0 = torch.randn(cb.nparams, generator=g, dtype=dtype).cuda()
+    mu = mu0.clone()
+    vu, none = cb.vjp_accumulate(0.0, x.reshape(-1), w.reshape(-1), mu, 0.25)
+    assert none is None and rel_err(vu.view(shape), vu_r) < 1e-9
+    want = mu0 + 0.25 * torch.cat([q.reshape(-1) for q in gp_r])
+    assert rel_err(mu, want) < 1e-9
+    # bit-reproducible: the same call twice gives identical bits (fixed-order reductions everywhere)
+    mu2 = mu0.clone()
+    vu2, _ = cb.vjp_accumulate(0.0, x.reshape(-1), w.reshape(-1), mu2, 0.25)
+    assert torch.equal(vu, vu2) and torch.equal(mu, mu2)
+
+
+def test_unsupported_shapes_are_refused_by_the_abi_not_computed_wrongly():
+    from pnode_b200 import _lib
+
+    lib = _lib.load()
+    d = _lib.ConvBlockDesc()
+    d.nlayers, d.dtype, d.N, d.H, d.W = 1, 0, 2, 8, 12  # W not a power of two
+    l = d.layer[0]
+    l.cin = l.cout = 8
+    l.kh = l.kw = 1
+    l.d_weight = l.d_bias = l.d_gamma = l.d_beta = 16
+    assert lib.pnode_convblock_work_bytes(C.byref(d)) == -1
+    assert b"power of two" in lib.pnode_last_error()
+    d.W = 8
+    l.kh = l.kw = 3
+    l.ph = l.pw = 1
+    assert lib.pnode_convblock_work_bytes(C.byref(d)) == -1

@@ -81,7 +81,7 @@ def test_config4_cifar_ode_block_rk4(dtype, tol):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     assert p[0].shape == (1, B, C, HW, HW)
-    assert p[3].path == "generic+convblock-rhs"  # hand-written BN+ReLU kernels inside f / vjp (csrc/bn_relu.cu)
+    assert p[3].path == "generic+convblock-rhs" and p[3]._cb_im.native  # whole RHS / VJP in csrc/conv_block.cu
     # conv biases feeding a BatchNorm have an exactly-zero gradient (pure rounding noise on both sides): compare mu as a
     # whole vector, not parameter by parameter
     _compare(p, o, tol, per_param=False)
@@ -172,7 +172,7 @@ def test_config4_fused_rhs_equals_stock_module_path():
         (out * gout.cuda()).sum().backward()
         res.append((out.detach(), y0.grad, [p.grad for p in f.parameters()], ode, f))
     a, b = res
-    assert a[3].path == "generic+convblock-rhs" and b[3].path == "generic"
+    assert a[3].path == "generic+convblock-rhs" and a[3]._cb_im.native and b[3].path == "generic"
     _compare(a, b, 1e-9, per_param=False)
     assert a[4].nfe == b[4].nfe == 32 and int(a[4].bn3.num_batches_tracked) == int(b[4].bn3.num_batches_tracked) == 32
     assert rel_err(a[4].bn5.running_var, b[4].bn5.running_var) < 1e-9
