@@ -156,6 +156,21 @@ class ConvBlockCallbacks(Callbacks):
         self.launches += L + 1 + (L if grads is not None else 0) + (L if want_u else L - 1) + (1 if grads is not None else 0)
         return vu
 
+    def f_and_combine(self, t, u, base, coef):
+        """k = f(t, u) and y = base + coef * k in ONE output pass (the RK stage combination fused into the block's last
+        kernel): returns (k, y).  Used by engine.GenericTS._rk_attempt when the next stage depends on k alone."""
+        self.nfe += 1
+        if hasattr(self.func, "nfe"):
+            self.func.nfe += 1
+        if not self.native:
+            with torch.no_grad():
+                out, _ = self._forward(t, u, save=False)
+            k = out.reshape(-1)
+            return k, torch.add(base, k, alpha=float(coef))
+        k, y = torch.empty_like(u), torch.empty_like(u)
+        self._native_f(u, out=y, base=base, base_coef=1.0, k_coef=coef, k=k)
+        return k, y
+
     def vjp_accumulate(self, t, u, w, mu, coef):
         """vjp + `mu += coef * (df/dp)^T w` in the same call (the engine uses it when present): J^T w is returned."""
         if not self.native:

@@ -9,28 +9,35 @@
 // for MMA tiles, so these are CUDA-core FMA kernels whose job is to touch every activation once):
 //   * every layer is ONE kernel: it reads the raw output z_{k-1} of the previous convolution, applies that layer's
 //     BatchNorm scale/shift + ReLU in registers on load, convolves, adds the bias, writes z_k, and accumulates the
-//     per-channel sum / sum of squares of z_k for the NEXT BatchNorm in its epilogue.  The last CTA to finish (ticket
-//     counter) combines the per-CTA partial sums in a fixed order (deterministic), writes mean / inv-std / scale / shift and
-//     updates running_mean / running_var / num_batches_tracked like nn.BatchNorm2d.  relu(bn(z)) is never materialised
+//     per-channel sum / sum of squares of z_k for the NEXT BatchNorm in its epilogue.  relu(bn(z)) is never materialised
 //     between layers: per layer the HBM traffic is (C_in + C_out) scalars per pixel, the lower bound of section 8d.
+//   * batch statistics are accumulated EXACTLY: every CTA adds its partial sums into 128-bit fixed-point accumulators
+//     (two 64-bit integer atomics with carry; integer addition is associative, so the totals are bit-reproducible whatever
+//     the order the CTAs finish in).  There is no "last CTA" reduction tail and no separate finalise launch: the kernels
+//     that CONSUME a layer's statistics derive mean / inv-std / scale / shift from the accumulators in their prologue (one
+//     L2 round trip, overlapped with staging the weights), and CTA (0,0) of the first consumer updates running_mean /
+//     running_var / num_batches_tracked like nn.BatchNorm2d.  These grids are a single wave of latency-bound CTAs, so the
+//     number of dependent memory round trips per kernel is what is minimised.
 //   * thread = 4 consecutive pixels of one image row (one 16-byte access per channel) x RC output channels; weights of the
 //     CTA's channel tile sit in shared memory and are read as broadcast LDS.128; horizontal taps come from the neighbouring
-//     lanes by warp shuffle, vertical taps from the rows above / below (L1 hits).
+//     lanes by warp shuffle, vertical taps from the rows above / below (L1 hits); the loads of the next group of input
+//     channels are issued before the FMAs of the current one (register double buffer).
 //   * the backward of a layer is two kernels over the same inputs (g_k = dL/dy_k, z_k, z_{k-1}): a data-gradient kernel --
 //     the same convolution kernel with the BatchNorm+ReLU backward  dz = c0 [y>0] g + c1 (z - mean) + c2  applied on load,
 //     flipped taps / transposed weights, and the NEXT layer's backward reductions (sum [y>0] g, sum [y>0] g xhat) in its
 //     epilogue -- and a weight-gradient kernel (pixels are the reduction dimension: per-CTA register tiles of
 //     16 x 32 (c_out x c_in*tap) accumulated over a grid-stride loop of 128-pixel chunks staged in shared memory,
 //     per-CTA partials combined in a fixed order by one final kernel that can add  coef * gradient  straight into mu).
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace pnode {
 
-constexpr int CB_PGX = 64;    // pixel groups (4 pixels each) per CTA tile = blockDim.x
-constexpr int CB_MAXCG = 4;   // channel groups per CTA = blockDim.y (<= 256 threads)
-enum { COEF_SCALE = 0, COEF_SHIFT, COEF_MEAN, COEF_INVSTD, COEF_C0, COEF_C1, COEF_C2, COEF_DGAMMA, COEF_DBETA, COEF_N };
+constexpr int CB_PGX = 64;   // pixel groups (4 pixels each) per CTA tile = blockDim.x
+constexpr int CB_MAXCG = 4;  // channel groups per CTA = blockDim.y (<= 256 threads)
+constexpr int ACC_R = 4;     // replicas of every accumulator (spreads the atomics of concurrently finishing CTAs)
 enum { SRC_RAW = 0, SRC_ACT = 1, SRC_DZ = 2 };
 enum { EPI_NONE = 0, EPI_FWD = 1, EPI_DGRAD = 2 };
 #define FULL 0xffffffffu
@@ -66,92 +73,186 @@ __device__ __forceinline__ V4<T> zero4() {
     return r;
 }
 
+// ---- exact accumulators ---------------------------------------------------------------------------------------------------
+// value = hi * 16 + lo * 2^-60 as a 128-bit two's-complement integer {lo: u64, hi: s64}; |x| < 2^66, resolution 8.7e-19.
+// Adding is two integer atomics (the carry out of lo is known from the value the first atomic returns), so the total does
+// not depend on the order of the adds.  Non-finite contributions raise *flag and the readers return NaN.
+__device__ __forceinline__ void acc128_add(unsigned long long *p, double x, unsigned *flag) {
+    if (!(fabs(x) < 7.0e19)) {
+        atomicOr(flag, 1u);
+        return;
+    }
+    const double h = floor(x * 0.0625);
+    const double r = x - h * 16.0;  // exact, in [0, 16)
+    const unsigned long long lo = (unsigned long long)(r * 1152921504606846976.0);  // 2^60
+    long long hi = (long long)h;
+    const unsigned long long old = atomicAdd(p, lo);
+    if (old + lo < old) hi += 1;
+    if (hi != 0) atomicAdd(p + 1, (unsigned long long)hi);
+}
+
+// acc layout: [ACC_R][C][2 statistics][2 words]
+__device__ __forceinline__ double acc128_read(const unsigned long long *acc, int C, int ch, int stat) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < ACC_R; ++r) {
+        const unsigned long long *p = acc + (((int64_t)r * C + ch) * 2 + stat) * 2;
+        const unsigned long long lo = __ldcg(p);
+        const long long hi = (long long)__ldcg(p + 1);
+        t += (double)hi * 16.0 + (double)lo * 8.673617379884035e-19;  // 2^-60
+    }
+    return t;
+}
+
+// One BatchNorm layer as the kernels see it: where its statistics accumulate and its affine parameters / buffers.
+struct BnRef {
+    const unsigned long long *accF;  // sum z, sum z^2                       (forward)
+    const unsigned long long *accB;  // sum [y>0] g, sum [y>0] g xhat        (backward: dbeta, dgamma)
+    const void *gamma, *beta;
+    void *rmean, *rvar;
+    long long *nbt;
+    double eps, momentum;
+    int C;
+};
+
+struct FwdStats {
+    double mean, var, invstd, scale, shift;
+};
+template <typename T>
+__device__ __forceinline__ FwdStats bn_forward_stats(const BnRef &b, int ch, double M, const unsigned *flag) {
+    FwdStats f;
+    const double bad = __ldcg(flag) != 0u ? NAN : 0.0;
+    const double S = acc128_read(b.accF, b.C, ch, 0) + bad, Q = acc128_read(b.accF, b.C, ch, 1);
+    f.mean = S / M;
+    f.var = fmax(Q / M - f.mean * f.mean, 0.0);
+    f.invstd = 1.0 / sqrt(f.var + b.eps);
+    f.scale = (double)static_cast<const T *>(b.gamma)[ch] * f.invstd;
+    f.shift = (double)static_cast<const T *>(b.beta)[ch] - f.mean * f.scale;
+    return f;
+}
+
+// nn.BatchNorm2d's buffer update (momentum, unbiased variance), done once per evaluation by ONE CTA of the first consumer
+template <typename T>
+__device__ __forceinline__ void bn_update_running(const BnRef &b, double M, const unsigned *flag, int tid, int nthr) {
+    if (b.rmean != nullptr) {
+        T *rm = static_cast<T *>(b.rmean), *rv = static_cast<T *>(b.rvar);
+        for (int ch = tid; ch < b.C; ch += nthr) {
+            const FwdStats f = bn_forward_stats<T>(b, ch, M, flag);
+            const double unbiased = M > 1.0 ? f.var * M / (M - 1.0) : f.var;
+            rm[ch] = (T)((1.0 - b.momentum) * (double)rm[ch] + b.momentum * f.mean);
+            rv[ch] = (T)((1.0 - b.momentum) * (double)rv[ch] + b.momentum * unbiased);
+        }
+    }
+    if (tid == 0 && b.nbt != nullptr) *b.nbt += 1;
+}
+
+// per-channel coefficient tables in shared memory: [k][C], k-th coefficient of every channel
+enum { CF_SCALE = 0, CF_SHIFT = 1, CF_MEAN = 2, CF_C0 = 3, CF_C1 = 4, CF_C2 = 5, CF_INVSTD = 3 };
+template <int SRC>
+struct NCoef {
+    static constexpr int N = SRC == SRC_RAW ? 0 : (SRC == SRC_ACT ? 2 : 6);
+};
+
+// table of the INPUT-side coefficients of channels [c0, c0 + n): relu(bn(z)) = max(scale z + shift, 0) and, for SRC_DZ,
+// dz = c0 [scale z + shift > 0] g + c1 (z - mean) + c2
+template <typename T, int SRC>
+__device__ __forceinline__ void fill_input_coefs(T *tab, int stride, const BnRef &b, int c0, int n, double M, const unsigned *flag,
+                                                 int tid, int nthr) {
+    if constexpr (SRC != SRC_RAW) {
+        for (int i = tid; i < n; i += nthr) {
+            const int ch = c0 + i;
+            const FwdStats f = bn_forward_stats<T>(b, ch, M, flag);
+            tab[CF_SCALE * stride + i] = (T)f.scale;
+            tab[CF_SHIFT * stride + i] = (T)f.shift;
+            if constexpr (SRC == SRC_DZ) {
+                const double s1 = acc128_read(b.accB, b.C, ch, 0), s2 = acc128_read(b.accB, b.C, ch, 1);
+                tab[CF_MEAN * stride + i] = (T)f.mean;
+                tab[CF_C0 * stride + i] = (T)f.scale;
+                tab[CF_C1 * stride + i] = (T)(-f.scale * f.invstd * s2 / M);
+                tab[CF_C2 * stride + i] = (T)(-f.scale * s1 / M);
+            }
+        }
+    }
+}
+
+// table of the OUTPUT-side coefficients (data-gradient epilogue): scale, shift, mean, inv-std of the layer below
+template <typename T>
+__device__ __forceinline__ void fill_output_coefs(T *tab, int stride, const BnRef &b, int c0, int n, double M, const unsigned *flag,
+                                                  int tid, int nthr) {
+    for (int i = tid; i < n; i += nthr) {
+        const FwdStats f = bn_forward_stats<T>(b, c0 + i, M, flag);
+        tab[CF_SCALE * stride + i] = (T)f.scale;
+        tab[CF_SHIFT * stride + i] = (T)f.shift;
+        tab[CF_MEAN * stride + i] = (T)f.mean;
+        tab[CF_INVSTD * stride + i] = (T)f.invstd;
+    }
+}
+
 // ---- what a kernel reads: the raw tensor, relu(bn(z)) formed on load, or the BatchNorm+ReLU backward formed on load -------
-// Split into coefs(channel) / fetch(offset) / finish(coefs, data) so that a kernel can issue the loads of several channels
-// back to back (memory-level parallelism) before it starts consuming them.
+// Split into fetch(offset) / finish(channel, data) so that a kernel can issue the loads of several channels back to back
+// (memory-level parallelism) before it starts consuming them.  `tab` is the shared-memory coefficient table.
 template <typename T, int SRC>
 struct Source;
 
 template <typename T>
 struct Source<T, SRC_RAW> {
-    struct Coef {};
     struct Data {
         V4<T> a;
     };
     const T *p;
     __device__ __forceinline__ Source(const T *a, const T *, const T *, int) : p(a) {}
-    __device__ __forceinline__ Coef coefs(int) const { return Coef(); }
     __device__ __forceinline__ Data fetch(int64_t off) const {
         Data d;
         d.a = ld4(p + off);
         return d;
     }
-    __device__ __forceinline__ V4<T> finish(const Coef &, const Data &d) const { return d.a; }
+    __device__ __forceinline__ V4<T> finish(int, const Data &d) const { return d.a; }
 };
 
 template <typename T>
 struct Source<T, SRC_ACT> {
-    struct Coef {
-        T sc, sh;
-    };
     struct Data {
         V4<T> a;
     };
-    const T *p, *coef;
-    int cs;
-    __device__ __forceinline__ Source(const T *a, const T *, const T *c, int s) : p(a), coef(c), cs(s) {}
-    __device__ __forceinline__ Coef coefs(int ch) const {
-        Coef c;
-        c.sc = __ldg(coef + COEF_SCALE * cs + ch);
-        c.sh = __ldg(coef + COEF_SHIFT * cs + ch);
-        return c;
-    }
+    const T *p, *tab;
+    int stride;
+    __device__ __forceinline__ Source(const T *a, const T *, const T *t, int s) : p(a), tab(t), stride(s) {}
     __device__ __forceinline__ Data fetch(int64_t off) const {
         Data d;
         d.a = ld4(p + off);
         return d;
     }
-    __device__ __forceinline__ V4<T> finish(const Coef &c, const Data &d) const {
+    __device__ __forceinline__ V4<T> finish(int i, const Data &d) const {
+        const T sc = tab[CF_SCALE * stride + i], sh = tab[CF_SHIFT * stride + i];
         V4<T> v;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v.v[e] = fmax(fma(c.sc, d.a.v[e], c.sh), T(0));
+        for (int e = 0; e < 4; ++e) v.v[e] = fmax(fma(sc, d.a.v[e], sh), T(0));
         return v;
     }
 };
 
 template <typename T>
 struct Source<T, SRC_DZ> {
-    struct Coef {
-        T sc, sh, mean, c0, c1, c2;
-    };
     struct Data {
         V4<T> g, z;
     };
-    const T *g, *z, *coef;
-    int cs;
-    __device__ __forceinline__ Source(const T *a, const T *b, const T *c, int s) : g(a), z(b), coef(c), cs(s) {}
-    __device__ __forceinline__ Coef coefs(int ch) const {
-        Coef c;
-        c.sc = __ldg(coef + COEF_SCALE * cs + ch);
-        c.sh = __ldg(coef + COEF_SHIFT * cs + ch);
-        c.mean = __ldg(coef + COEF_MEAN * cs + ch);
-        c.c0 = __ldg(coef + COEF_C0 * cs + ch);
-        c.c1 = __ldg(coef + COEF_C1 * cs + ch);
-        c.c2 = __ldg(coef + COEF_C2 * cs + ch);
-        return c;
-    }
+    const T *g, *z, *tab;
+    int stride;
+    __device__ __forceinline__ Source(const T *a, const T *b, const T *t, int s) : g(a), z(b), tab(t), stride(s) {}
     __device__ __forceinline__ Data fetch(int64_t off) const {
         Data d;
         d.g = ld4(g + off);
         d.z = ld4(z + off);
         return d;
     }
-    __device__ __forceinline__ V4<T> finish(const Coef &c, const Data &d) const {
+    __device__ __forceinline__ V4<T> finish(int i, const Data &d) const {
+        const T sc = tab[CF_SCALE * stride + i], sh = tab[CF_SHIFT * stride + i], mean = tab[CF_MEAN * stride + i];
+        const T c0 = tab[CF_C0 * stride + i], c1 = tab[CF_C1 * stride + i], c2 = tab[CF_C2 * stride + i];
         V4<T> r;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const T base = fma(c.c1, d.z.v[e] - c.mean, c.c2);
-            r.v[e] = fma(c.sc, d.z.v[e], c.sh) > T(0) ? fma(c.c0, d.g.v[e], base) : base;
+            const T base = fma(c1, d.z.v[e] - mean, c2);
+            r.v[e] = fma(sc, d.z.v[e], sh) > T(0) ? fma(c0, d.g.v[e], base) : base;
         }
         return r;
     }
@@ -175,13 +276,12 @@ __device__ __forceinline__ void fetch_offsets(const S &src, int64_t off, int h, 
 }
 
 template <typename T, int KIND, typename S>
-__device__ __forceinline__ void finish_offsets(const S &src, const typename S::Coef &cf,
-                                               const typename S::Data (&d)[KIND == 2 ? 3 : 1], int h, int w0, int H, int W,
-                                               V4<T> (&o)[KIND == 0 ? 1 : 3]) {
+__device__ __forceinline__ void finish_offsets(const S &src, int i, const typename S::Data (&d)[KIND == 2 ? 3 : 1], int h, int w0,
+                                               int H, int W, V4<T> (&o)[KIND == 0 ? 1 : 3]) {
     if constexpr (KIND == 0) {
-        o[0] = src.finish(cf, d[0]);
+        o[0] = src.finish(i, d[0]);
     } else if constexpr (KIND == 1) {
-        const V4<T> c = src.finish(cf, d[0]);
+        const V4<T> c = src.finish(i, d[0]);
         T l = __shfl_up_sync(FULL, c.v[3], 1), r = __shfl_down_sync(FULL, c.v[0], 1);
         if (w0 == 0) l = T(0);
         if (w0 + 4 == W) r = T(0);
@@ -189,16 +289,16 @@ __device__ __forceinline__ void finish_offsets(const S &src, const typename S::C
         o[1] = c;
         o[2].v[0] = c.v[1], o[2].v[1] = c.v[2], o[2].v[2] = c.v[3], o[2].v[3] = r;
     } else {
-        o[0] = h > 0 ? src.finish(cf, d[0]) : zero4<T>();
-        o[1] = src.finish(cf, d[1]);
-        o[2] = h < H - 1 ? src.finish(cf, d[2]) : zero4<T>();
+        o[0] = h > 0 ? src.finish(i, d[0]) : zero4<T>();
+        o[1] = src.finish(i, d[1]);
+        o[2] = h < H - 1 ? src.finish(i, d[2]) : zero4<T>();
     }
 }
 
-// channels whose loads are in flight together, per thread (registers: UN * NF * (1 or 2) * 4 scalars)
+// input channels per register buffer (two buffers are live: the group being consumed and the group in flight)
 template <int KIND, int SRC>
 struct Unroll {
-    static constexpr int N = KIND == 2 ? (SRC == SRC_DZ ? 2 : 4) : 4;
+    static constexpr int N = KIND == 2 ? (SRC == SRC_DZ ? 1 : 2) : (SRC == SRC_DZ ? 2 : 4);
 };
 
 struct PixelCoord {
@@ -218,27 +318,23 @@ __device__ __forceinline__ PixelCoord pixel_coord(int64_t pg, int64_t npg, int H
 
 template <typename T>
 struct ConvArgs {
-    const T *in, *in2;      // forward: z_{k-1} (or x), unused;  data gradient: g_k, z_k
-    const T *coef_in;       // per-channel coefficients of the BatchNorm on the INPUT side (forward: layer k-1; dgrad: layer k)
-    const T *w, *bias;      // conv weight [Cout][Cin][taps]; bias [Cout] (forward only)
-    T *out;                 // forward: z_k;  data gradient: g_{k-1} (or the VJP w.r.t. the block input)
-    const T *zprev;         // EPI_DGRAD: z_{k-1} at the output pixels
-    T *coef_out;            // coefficients finalised by the last CTA (forward: layer k; dgrad: layer k-1)
-    double *partial;        // [gridDim.x][CB][2]
-    unsigned *counter;
-    const T *gamma, *beta;  // forward finalise
-    T *rmean, *rvar;
-    long long *nbt;
-    double eps, momentum;
-    int CA, CB;             // reduction channels, output channels
-    int H, W, HW, cs;
-    int64_t npg;            // pixel groups = N*H*W/4
+    const T *in, *in2;   // forward: z_{k-1} (or x), unused;  data gradient: g_k, z_k
+    const T *w, *bias;   // conv weight [Cout][Cin][taps]; bias [Cout] (forward only)
+    T *out;              // forward: z_k;  data gradient: g_{k-1} (or the VJP w.r.t. the block input)
+    const T *zprev;      // EPI_DGRAD: z_{k-1} at the output pixels
+    BnRef bin, bout;     // BatchNorm on the input side (forward: layer k-1; dgrad: layer k) / output side (dgrad: layer k-1)
+    unsigned long long *acc_out;  // accumulators this kernel adds into (forward: accF of layer k; dgrad: accB of layer k-1)
+    unsigned *flag;
+    int upd_in, upd_out;  // CTA (0,0) performs the running-statistics update of bin / bout
+    int CA, CB;           // reduction channels, output channels
+    int H, W, HW;
+    int64_t npg;          // pixel groups = N*H*W/4
     int tiles;
-    double M;               // N*H*W
+    double M;             // N*H*W
 };
 
 // 2*RC per-thread values summed over the 32 lanes with a transposing butterfly (2*RC + log-ish shuffles instead of 5 per
-// value): on return v[0] of lane l holds the warp total of value index idx(l) = bits 4..(5-log2(NV)) of l, mirrored.
+// value): on return lane l holds the warp total of value index idx(l) (the top log2(NV) bits of l, MSB first).
 template <typename T, int NV>
 __device__ __forceinline__ T warp_multi_sum(T (&v)[NV], int lane, int &idx) {
     idx = 0;
@@ -259,88 +355,32 @@ __device__ __forceinline__ T warp_multi_sum(T (&v)[NV], int lane, int &idx) {
     return t;
 }
 
-// Per-CTA partial sums -> global; the last CTA combines them (fixed order) and finalises the per-channel coefficients.
-template <typename T, int RC, int EPI>
+// CTA-level sums of the per-thread statistics, added into the exact accumulators (no tail, no ordering)
+template <typename T, int RC>
 __device__ __forceinline__ void stats_epilogue(const ConvArgs<T> &a, T (&s)[RC], T (&q)[RC], int cb0) {
     __shared__ double red[2][CB_MAXCG][2 * RC];
-    __shared__ double tot[2 * 512];
-    __shared__ int is_last;
     const int lane = threadIdx.x & 31, wx = threadIdx.x >> 5;
-    const int tid = threadIdx.y * CB_PGX + threadIdx.x, nthr = CB_PGX * blockDim.y;
     T v[2 * RC];
 #pragma unroll
     for (int r = 0; r < RC; ++r) v[r] = s[r], v[RC + r] = q[r];
     int idx;
     const T t = warp_multi_sum<T, 2 * RC>(v, lane, idx);
-    // lanes sharing idx hold the same total; one of them publishes it
-    constexpr int REP = 32 / (2 * RC);
+    constexpr int REP = 32 / (2 * RC);  // lanes sharing idx hold the same total; one of them publishes it
     if ((lane & (REP - 1)) == 0) red[wx][threadIdx.y][idx] = (double)t;
     __syncthreads();
     if (threadIdx.x < 2 * RC) {
         const int which = threadIdx.x / RC, r = threadIdx.x % RC;
         const int ch = cb0 + threadIdx.y * RC + r;
-        a.partial[((int64_t)blockIdx.x * a.CB + ch) * 2 + which] = red[0][threadIdx.y][threadIdx.x] + red[1][threadIdx.y][threadIdx.x];
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned ticket = atomicAdd(a.counter, 1u);
-        is_last = ticket == gridDim.x * gridDim.y - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    const int warp = tid >> 5, nwarp = nthr >> 5;
-    for (int base = 0; base < a.CB; base += 512) {  // tot[] holds up to 512 channels at a time
-        const int nch = min(512, a.CB - base);
-        for (int pair = warp; pair < 2 * nch; pair += nwarp) {
-            const int ch = base + (pair >> 1), which = pair & 1;
-            double acc = 0.0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) acc += __ldcg(a.partial + ((int64_t)b * a.CB + ch) * 2 + which);
-            acc = warp_sum(acc);
-            if (lane == 0) tot[pair] = acc;
-        }
-        __syncthreads();
-        for (int c = tid; c < nch; c += nthr) {
-            const int ch = base + c;
-            const double S = tot[2 * c], Q = tot[2 * c + 1];
-            T *co = a.coef_out;
-            if (EPI == EPI_FWD) {
-                const double mean = S / a.M;
-                const double var = fmax(Q / a.M - mean * mean, 0.0);
-                const double invstd = 1.0 / sqrt(var + a.eps);
-                const double scale = (double)a.gamma[ch] * invstd;
-                co[COEF_SCALE * a.cs + ch] = (T)scale;
-                co[COEF_SHIFT * a.cs + ch] = (T)((double)a.beta[ch] - mean * scale);
-                co[COEF_MEAN * a.cs + ch] = (T)mean;
-                co[COEF_INVSTD * a.cs + ch] = (T)invstd;
-                if (a.rmean != nullptr) {
-                    const double unbiased = a.M > 1.0 ? var * a.M / (a.M - 1.0) : var;
-                    a.rmean[ch] = (T)((1.0 - a.momentum) * (double)a.rmean[ch] + a.momentum * mean);
-                    a.rvar[ch] = (T)((1.0 - a.momentum) * (double)a.rvar[ch] + a.momentum * unbiased);
-                }
-            } else {
-                // S = sum [y>0] g = dbeta, Q = sum [y>0] g xhat = dgamma;  dz = c0 [y>0] g + c1 (z - mean) + c2
-                const double c0 = (double)co[COEF_SCALE * a.cs + ch], invstd = (double)co[COEF_INVSTD * a.cs + ch];
-                co[COEF_C0 * a.cs + ch] = (T)c0;
-                co[COEF_C1 * a.cs + ch] = (T)(-c0 * invstd * Q / a.M);
-                co[COEF_C2 * a.cs + ch] = (T)(-c0 * S / a.M);
-                co[COEF_DGAMMA * a.cs + ch] = (T)Q;
-                co[COEF_DBETA * a.cs + ch] = (T)S;
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        if (EPI == EPI_FWD && a.nbt != nullptr) *a.nbt += 1;
-        *a.counter = 0u;
+        const int rep = blockIdx.x % ACC_R;
+        acc128_add(a.acc_out + (((int64_t)rep * a.CB + ch) * 2 + which) * 2,
+                   red[0][threadIdx.y][threadIdx.x] + red[1][threadIdx.y][threadIdx.x], a.flag);
     }
 }
 
 // sum / sum-of-squares (forward) or the two BatchNorm-backward sums (dgrad) of one thread's RC x 4 outputs
 template <typename T, int RC, int EPI>
-__device__ __forceinline__ void stats_accumulate(const ConvArgs<T> &a, const T (&acc)[RC][4], int64_t off_out, int ch0,
-                                                 T (&s)[RC], T (&q)[RC]) {
+__device__ __forceinline__ void stats_accumulate(const ConvArgs<T> &a, const T (&acc)[RC][4], int64_t off_out, const T *tout,
+                                                 int tstride, int i0, T (&s)[RC], T (&q)[RC]) {
     if constexpr (EPI == EPI_FWD) {
 #pragma unroll
         for (int r = 0; r < RC; ++r)
@@ -350,34 +390,25 @@ __device__ __forceinline__ void stats_accumulate(const ConvArgs<T> &a, const T (
                 q[r] = fma(acc[r][j], acc[r][j], q[r]);
             }
     } else {
-        const T *co = a.coef_out;
         V4<T> z[RC];
-        T sc[RC], sh[RC], mean[RC], invstd[RC];
+#pragma unroll
+        for (int r = 0; r < RC; ++r) z[r] = ld4(a.zprev + off_out + (int64_t)r * a.HW);
 #pragma unroll
         for (int r = 0; r < RC; ++r) {
-            z[r] = ld4(a.zprev + off_out + (int64_t)r * a.HW);
-            sc[r] = __ldg(co + COEF_SCALE * a.cs + ch0 + r), sh[r] = __ldg(co + COEF_SHIFT * a.cs + ch0 + r);
-            mean[r] = __ldg(co + COEF_MEAN * a.cs + ch0 + r), invstd[r] = __ldg(co + COEF_INVSTD * a.cs + ch0 + r);
-        }
-#pragma unroll
-        for (int r = 0; r < RC; ++r)
+            const T sc = tout[CF_SCALE * tstride + i0 + r], sh = tout[CF_SHIFT * tstride + i0 + r];
+            const T mean = tout[CF_MEAN * tstride + i0 + r], invstd = tout[CF_INVSTD * tstride + i0 + r];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const T gm = fma(sc[r], z[r].v[j], sh[r]) > T(0) ? acc[r][j] : T(0);
+                const T gm = fma(sc, z[r].v[j], sh) > T(0) ? acc[r][j] : T(0);
                 s[r] += gm;
-                q[r] = fma(gm, (z[r].v[j] - mean[r]) * invstd[r], q[r]);
+                q[r] = fma(gm, (z[r].v[j] - mean) * invstd, q[r]);
             }
+        }
     }
 }
 
 template <typename T>
-__device__ __forceinline__ V4<T> lds4(const T *p);
-template <>
-__device__ __forceinline__ V4<float> lds4<float>(const float *p) {
-    return ld4(p);
-}
-template <>
-__device__ __forceinline__ V4<double> lds4<double>(const double *p) {
+__device__ __forceinline__ V4<T> lds4(const T *p) {
     return ld4(p);
 }
 
@@ -386,9 +417,13 @@ template <typename T, int KIND, int SRC, int EPI, int RC>
 __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T> a) {
     constexpr int TAPS = KIND == 0 ? 1 : 3;
     constexpr bool FWD = SRC != SRC_DZ;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *ws = reinterpret_cast<T *>(smem_raw);  // [CA * TAPS][CT]
+    constexpr int UN = Unroll<KIND, SRC>::N, NF = KIND == 2 ? 3 : 1;
+    typedef Source<T, SRC> S;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int CT = blockDim.y * RC;
+    T *ws = reinterpret_cast<T *>(smem_raw);  // [CA * TAPS][CT]
+    T *tin = ws + a.CA * TAPS * CT;           // [NCoef][CA]
+    T *tout = tin + NCoef<SRC>::N * a.CA;     // [4][CT]   (EPI_DGRAD)
     const int cb0 = blockIdx.y * CT;
     const int tid = threadIdx.y * CB_PGX + threadIdx.x, nthr = CB_PGX * blockDim.y;
     for (int i = tid; i < a.CA * TAPS * CT; i += nthr) {
@@ -396,8 +431,14 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T
         // forward: W[co = b][ci = ach][tap = o];  data gradient: W[co = ach][ci = b][tap = TAPS-1-o]
         ws[i] = FWD ? a.w[((int64_t)b * a.CA + ach) * TAPS + o] : a.w[((int64_t)ach * a.CB + b) * TAPS + (TAPS - 1 - o)];
     }
+    fill_input_coefs<T, SRC>(tin, a.CA, a.bin, 0, a.CA, a.M, a.flag, tid, nthr);
+    if constexpr (EPI == EPI_DGRAD) fill_output_coefs<T>(tout, CT, a.bout, cb0, CT, a.M, a.flag, tid, nthr);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (a.upd_in) bn_update_running<T>(a.bin, a.M, a.flag, tid, nthr);
+        if (a.upd_out) bn_update_running<T>(a.bout, a.M, a.flag, tid, nthr);
+    }
     __syncthreads();
-    Source<T, SRC> src(a.in, a.in2, a.coef_in, a.cs);
+    S src(a.in, a.in2, tin, a.CA);
     const int ch0 = cb0 + threadIdx.y * RC;
     T bias[RC], s[RC], q[RC];
 #pragma unroll
@@ -413,19 +454,20 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T
         for (int r = 0; r < RC; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[r][j] = bias[r];
-        constexpr int UN = Unroll<KIND, SRC>::N, NF = KIND == 2 ? 3 : 1;
-        for (int cb = 0; cb < a.CA; cb += UN) {  // host guarantees CA % 4 == 0
-            typename Source<T, SRC>::Coef cf[UN];
-            typename Source<T, SRC>::Data dd[UN][NF];
+        typename S::Data cur[UN][NF], nxt[UN][NF];
 #pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                cf[u] = src.coefs(cb + u);
-                fetch_offsets<T, KIND>(src, off_in + (int64_t)(cb + u) * a.HW, pc.h, a.H, a.W, dd[u]);
+        for (int u = 0; u < UN; ++u) fetch_offsets<T, KIND>(src, off_in + (int64_t)u * a.HW, pc.h, a.H, a.W, cur[u]);
+        for (int cb = 0; cb < a.CA; cb += UN) {  // host guarantees CA % 4 == 0
+            const bool more = cb + UN < a.CA;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+                    fetch_offsets<T, KIND>(src, off_in + (int64_t)(cb + UN + u) * a.HW, pc.h, a.H, a.W, nxt[u]);
             }
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
                 V4<T> o[TAPS];
-                finish_offsets<T, KIND>(src, cf[u], dd[u], pc.h, pc.w0, a.H, a.W, o);
+                finish_offsets<T, KIND>(src, cb + u, cur[u], pc.h, pc.w0, a.H, a.W, o);
 #pragma unroll
                 for (int oi = 0; oi < TAPS; ++oi) {
                     const T *wr = ws + ((cb + u) * TAPS + oi) * CT + threadIdx.y * RC;
@@ -439,6 +481,12 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T
                     }
                 }
             }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) cur[u][f] = nxt[u][f];
+            }
         }
         if (pc.active) {
             const int64_t off_out = ((int64_t)pc.n * a.CB + ch0) * a.HW + pc.rem;
@@ -449,17 +497,222 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T
                 for (int j = 0; j < 4; ++j) v.v[j] = acc[r][j];
                 st4(a.out + off_out + (int64_t)r * a.HW, v);
             }
-            if (EPI != EPI_NONE) stats_accumulate<T, RC, EPI>(a, acc, off_out, ch0, s, q);
+            if constexpr (EPI != EPI_NONE) stats_accumulate<T, RC, EPI>(a, acc, off_out, tout, CT, threadIdx.y * RC, s, q);
         }
     }
-    if (EPI != EPI_NONE) stats_epilogue<T, RC, EPI>(a, s, q, cb0);
+    if constexpr (EPI != EPI_NONE) stats_epilogue<T, RC>(a, s, q, cb0);
+}
+
+// ---- pipelined variant: TMA bulk copies (cp.async.bulk, no tensor map: a tile of one channel of one image is contiguous in
+// NCHW) feed a ring of shared-memory stages through mbarriers; one producer warp, eight consumer warps --------------------
+// CTA tile = TP = 1024 / CG consecutive pixels (whole images when HW <= TP, else a row range of one image) x CT = CG * RC
+// output channels; a stage holds KC input channels of the tile, raw (the BatchNorm+ReLU / backward transform is applied when
+// a consumer reads its 4 pixels out of shared memory, so each activation is transformed once per channel group).  The copies
+// of up to S stages are in flight while the consumers run FMAs, across tile boundaries too: the grid is persistent.
+constexpr int CP_CONSUMERS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (long long spin = 0; spin < (1ll << 26); ++spin) {  // bounded: a protocol bug must not hang the GPU
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int SRC>
+struct PipeKC {
+    static constexpr int N = SRC == SRC_DZ ? 2 : 4;  // input channels per stage (SRC_DZ stages two tensors)
+};
+
+template <typename T, int KIND, int SRC, int EPI, int RC>
+__global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs<T> a, const int CG, const int S) {
+    constexpr int TAPS = KIND == 0 ? 1 : 3;
+    constexpr bool FWD = SRC != SRC_DZ;
+    constexpr int KC = PipeKC<SRC>::N, NT = SRC == SRC_DZ ? 2 : 1, NF = KIND == 2 ? 3 : 1;
+    typedef Source<T, SRC> SS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int CT = CG * RC, PGT = CP_CONSUMERS / CG, TP = 4 * PGT;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw), *empty = full + 8;
+    T *ws = reinterpret_cast<T *>(smem_raw + 128);  // [CA * TAPS][CT]
+    T *tin = ws + a.CA * TAPS * CT;                 // [NCoef][CA]
+    T *tout = tin + NCoef<SRC>::N * a.CA;           // [4][CT]
+    const size_t head = (128 + ((size_t)a.CA * TAPS * CT + (size_t)NCoef<SRC>::N * a.CA + 4 * CT) * sizeof(T) + 127) & ~(size_t)127;
+    T *stages = reinterpret_cast<T *>(smem_raw + head);  // [S][NT][KC][TP]
+    const int stage_elems = NT * KC * TP;
+    const int cb0 = blockIdx.y * CT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunk = a.CA / KC;
+    const int ipt = TP >= a.HW ? TP / a.HW : 0;  // images per tile (0: the tile is a row range of one image)
+    const int64_t total_px = a.npg * 4;
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, CP_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == CP_CONSUMERS / 32) {
+        // ---- producer warp: every lane issues a share of the stage's bulk copies; lane 0 arms the barrier -------------------
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+            const int64_t px0 = (int64_t)tile * TP;
+            int imgs, n0, rem0;
+            uint32_t bytes_each;
+            if (ipt > 0) {
+                n0 = tile * ipt, rem0 = 0;
+                const int64_t left = (total_px - px0) / a.HW;
+                imgs = (int)(left < ipt ? left : ipt);
+                bytes_each = (uint32_t)(a.HW * sizeof(T));
+            } else {
+                n0 = (int)(px0 / a.HW), rem0 = (int)(px0 - (int64_t)n0 * a.HW);
+                imgs = 1;
+                bytes_each = (uint32_t)(TP * sizeof(T));
+            }
+            const int ncopy = NT * KC * imgs;
+            for (int chunk = 0; chunk < nchunk; ++chunk) {
+                mbar_wait(empty + slot, phase ^ 1u);
+                T *st = stages + (size_t)slot * stage_elems;
+                if (lane == 0) mbar_expect_tx(full + slot, bytes_each * (uint32_t)ncopy);
+                __syncwarp();
+                for (int i = lane; i < ncopy; i += 32) {
+                    const int m = i % imgs, tc = i / imgs, c = tc % KC, t = tc / KC;
+                    const T *base = (t == 0) ? a.in : a.in2;
+                    const T *src = base + ((int64_t)(n0 + m) * a.CA + chunk * KC + c) * a.HW + rem0;
+                    bulk_g2s(st + (t * KC + c) * TP + m * a.HW, src, bytes_each, full + slot);
+                }
+                if (++slot == S) slot = 0, phase ^= 1u;
+            }
+        }
+        return;
+    }
+    // ---- consumers ------------------------------------------------------------------------------------------------------------
+    const int x = tid % PGT, cg = tid / PGT;
+    for (int i = tid; i < a.CA * TAPS * CT; i += CP_CONSUMERS) {
+        const int bl = i % CT, ao = i / CT, o = ao % TAPS, ach = ao / TAPS, b = cb0 + bl;
+        ws[i] = FWD ? a.w[((int64_t)b * a.CA + ach) * TAPS + o] : a.w[((int64_t)ach * a.CB + b) * TAPS + (TAPS - 1 - o)];
+    }
+    fill_input_coefs<T, SRC>(tin, a.CA, a.bin, 0, a.CA, a.M, a.flag, tid, CP_CONSUMERS);
+    if constexpr (EPI == EPI_DGRAD) fill_output_coefs<T>(tout, CT, a.bout, cb0, CT, a.M, a.flag, tid, CP_CONSUMERS);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (a.upd_in) bn_update_running<T>(a.bin, a.M, a.flag, tid, CP_CONSUMERS);
+        if (a.upd_out) bn_update_running<T>(a.bout, a.M, a.flag, tid, CP_CONSUMERS);
+    }
+    consumer_sync();
+    const int ch0 = cb0 + cg * RC;
+    T bias[RC], s[RC], q[RC];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+        bias[r] = (FWD && a.bias != nullptr) ? a.bias[ch0 + r] : T(0);
+        s[r] = q[r] = T(0);
+    }
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+        const PixelCoord pc = pixel_coord((int64_t)tile * PGT + x, a.npg, a.HW, a.W);
+        const int xo = pc.active ? 4 * x : 0;  // lanes past the end of the tensor read the tile's first pixels (never stored)
+        T acc[RC][4];
+#pragma unroll
+        for (int r = 0; r < RC; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][j] = bias[r];
+        for (int chunk = 0; chunk < nchunk; ++chunk) {
+            mbar_wait(full + slot, phase);
+            const T *st = stages + (size_t)slot * stage_elems;
+            SS src(st, st + KC * TP, tin, a.CA);
+            typename SS::Data dd[KC][NF];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) fetch_offsets<T, KIND>(src, (int64_t)c * TP + xo, pc.h, a.H, a.W, dd[c]);
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const int ch = chunk * KC + c;
+                V4<T> o[TAPS];
+                finish_offsets<T, KIND>(src, ch, dd[c], pc.h, pc.w0, a.H, a.W, o);
+#pragma unroll
+                for (int oi = 0; oi < TAPS; ++oi) {
+                    const T *wr = ws + (ch * TAPS + oi) * CT + cg * RC;
+#pragma unroll
+                    for (int r4 = 0; r4 < RC; r4 += 4) {
+                        const V4<T> wv = lds4<T>(wr + r4);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[r4 + r][j] = fma(wv.v[r], o[oi].v[j], acc[r4 + r][j]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+            if (++slot == S) slot = 0, phase ^= 1u;
+        }
+        if (pc.active) {
+            const int64_t off_out = ((int64_t)pc.n * a.CB + ch0) * a.HW + pc.rem;
+#pragma unroll
+            for (int r = 0; r < RC; ++r) {
+                V4<T> v;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v.v[j] = acc[r][j];
+                st4(a.out + off_out + (int64_t)r * a.HW, v);
+            }
+            if constexpr (EPI != EPI_NONE) stats_accumulate<T, RC, EPI>(a, acc, off_out, tout, CT, cg * RC, s, q);
+        }
+    }
+    if constexpr (EPI != EPI_NONE) {
+        // CTA-level sums -> exact accumulators (same scheme as stats_epilogue, 8 consumer warps)
+        __shared__ double red[CP_CONSUMERS / 32][2 * RC];
+        T v[2 * RC];
+#pragma unroll
+        for (int r = 0; r < RC; ++r) v[r] = s[r], v[RC + r] = q[r];
+        int idx;
+        const T t = warp_multi_sum<T, 2 * RC>(v, lane, idx);
+        constexpr int REP = 32 / (2 * RC);
+        if ((lane & (REP - 1)) == 0) red[warp][idx] = (double)t;
+        consumer_sync();
+        if (tid < 2 * CT) {
+            const int g = tid / (2 * RC), i = tid % (2 * RC), which = i / RC, r = i % RC;
+            const int wpg = PGT / 32;  // warps per channel group
+            double tot = 0.0;
+            for (int w = 0; w < wpg; ++w) tot += red[g * wpg + w][i];
+            const int ch = cb0 + g * RC + r;
+            const int rep = blockIdx.x % ACC_R;
+            acc128_add(a.acc_out + (((int64_t)rep * a.CB + ch) * 2 + which) * 2, tot, a.flag);
+        }
+    }
 }
 
 // BatchNorm-backward sums of the TOP layer (g = the cotangent handed to the VJP, z = z_L): same epilogue, no convolution.
 template <typename T, int RC>
 __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) top_stats_kernel(const ConvArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *tout = reinterpret_cast<T *>(smem_raw);  // [4][CT]
     const int CT = blockDim.y * RC;
     const int cb0 = blockIdx.y * CT, ch0 = cb0 + threadIdx.y * RC;
+    const int tid = threadIdx.y * CB_PGX + threadIdx.x, nthr = CB_PGX * blockDim.y;
+    fill_output_coefs<T>(tout, CT, a.bout, cb0, CT, a.M, a.flag, tid, nthr);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && a.upd_out) bn_update_running<T>(a.bout, a.M, a.flag, tid, nthr);
+    __syncthreads();
     T s[RC], q[RC];
 #pragma unroll
     for (int r = 0; r < RC; ++r) s[r] = q[r] = T(0);
@@ -475,30 +728,36 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) top_stats_kernel(const ConvA
         for (int r = 0; r < RC; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[r][j] = g[r].v[j];
-        stats_accumulate<T, RC, EPI_DGRAD>(a, acc, off_out, ch0, s, q);
+        stats_accumulate<T, RC, EPI_DGRAD>(a, acc, off_out, tout, CT, threadIdx.y * RC, s, q);
     }
-    stats_epilogue<T, RC, EPI_DGRAD>(a, s, q, cb0);
+    stats_epilogue<T, RC>(a, s, q, cb0);
 }
 
 // out = base_coef * base + coef * relu(scale_c * z + shift_c)      (base may be NULL: plain activation of the last layer;
 // with base it is the RK stage combination Y_{i+1} = u + h a_{i+1,i} k_i fused into the block's output pass)
 template <typename T>
-__global__ void __launch_bounds__(256) act_out_kernel(const T *__restrict__ z, const T *__restrict__ coef, int cs, int C,
-                                                      int HW, int64_t nvec, T *__restrict__ out, const T *__restrict__ base,
-                                                      T base_coef, T kcoef, T *__restrict__ kout) {
+__global__ void __launch_bounds__(256) act_out_kernel(const T *__restrict__ z, const BnRef b, double M, const unsigned *flag,
+                                                      int upd, int HW, int64_t nvec, T *__restrict__ out,
+                                                      const T *__restrict__ base, T base_coef, T kcoef, T *__restrict__ kout) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *tab = reinterpret_cast<T *>(smem_raw);  // [2][C]
+    const int C = b.C;
+    fill_input_coefs<T, SRC_ACT>(tab, C, b, 0, C, M, flag, threadIdx.x, blockDim.x);
+    if (blockIdx.x == 0 && upd) bn_update_running<T>(b, M, flag, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         const int64_t e0 = i * 4;
         const int c = (int)((e0 / HW) % C);
-        const T sc = __ldg(coef + COEF_SCALE * cs + c), sh = __ldg(coef + COEF_SHIFT * cs + c);
+        const T sc = tab[CF_SCALE * C + c], sh = tab[CF_SHIFT * C + c];
         V4<T> v = ld4(z + e0);
 #pragma unroll
         for (int e = 0; e < 4; ++e) v.v[e] = fmax(fma(sc, v.v[e], sh), T(0));
         if (kout != nullptr) st4(kout + e0, v);
         if (base != nullptr) {
-            const V4<T> b = ld4(base + e0);
+            const V4<T> bb = ld4(base + e0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v.v[e] = fma(kcoef, v.v[e], base_coef * b.v[e]);
+            for (int e = 0; e < 4; ++e) v.v[e] = fma(kcoef, v.v[e], base_coef * bb.v[e]);
         }
         if (out != nullptr) st4(out + e0, v);
     }
@@ -509,29 +768,39 @@ constexpr int WG_CO = 16, WG_CIT = 32, WG_PX = 128, WG_LD = 132, WG_THREADS = 25
 
 template <typename T>
 struct WgradArgs {
-    const T *g, *z, *coef_k;   // dz_k formed on load from g_k, z_k and layer k's coefficients
-    const T *yin, *coef_in;    // y_{k-1}: raw block input (k = 1) or relu(bn(z_{k-1}))
-    T *partial;                // [gridDim.x][gridDim.y][WG_TILE]
-    int Cin, Cout, H, W, HW, cs, tiles_cit;
+    const T *g, *z;   // dz_k formed on load from g_k, z_k and layer k's statistics
+    const T *yin;     // y_{k-1}: raw block input (k = 1) or relu(bn(z_{k-1}))
+    BnRef bk, bin;    // layer k (forward + backward sums), layer k-1 (forward sums)
+    const unsigned *flag;
+    T *partial;       // [gridDim.x][gridDim.y][WG_TILE]
+    int Cin, Cout, H, W, HW, tiles_cit;
     int64_t npg;
     int nchunks;
+    double M;
 };
 
 template <typename T, int KIND, int YSRC>
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<T> a) {
     constexpr int TAPS = KIND == 0 ? 1 : 3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NY = TAPS == 1 ? WG_CIT / 8 : 2, NF = KIND == 2 ? 3 : 1;
+    typedef Source<T, SRC_DZ> SD;
+    typedef Source<T, YSRC> SY;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *s_dz = reinterpret_cast<T *>(smem_raw);  // [WG_CO][WG_LD]
     T *s_y = s_dz + WG_CO * WG_LD;              // [WG_CIT][WG_LD]
+    T *tdz = s_y + WG_CIT * WG_LD;              // [6][WG_CO]
+    T *ty = tdz + 6 * WG_CO;                    // [2][WG_CIT]
     const int tile = blockIdx.y, tco = tile / a.tiles_cit, tcit = tile % a.tiles_cit;
     const int co0 = tco * WG_CO, cit0 = tcit * WG_CIT;
     const int ci_lo = cit0 / TAPS, ci_hi = min(a.Cin, (cit0 + WG_CIT - 1) / TAPS + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cgp = lane & 3, cg8 = lane >> 2;
     for (int i = threadIdx.x; i < (WG_CO + WG_CIT) * WG_LD; i += WG_THREADS) s_dz[i] = T(0);
+    fill_input_coefs<T, SRC_DZ>(tdz, WG_CO, a.bk, co0, min(WG_CO, a.Cout - co0), a.M, a.flag, threadIdx.x, WG_THREADS);
+    fill_input_coefs<T, YSRC>(ty, WG_CIT, a.bin, ci_lo, ci_hi - ci_lo, a.M, a.flag, threadIdx.x, WG_THREADS);
     __syncthreads();
-    Source<T, SRC_DZ> dsrc(a.g, a.z, a.coef_k, a.cs);
-    Source<T, YSRC> ysrc(a.yin, nullptr, a.coef_in, a.cs);
+    SD dsrc(a.g, a.z, tdz, WG_CO);
+    SY ysrc(a.yin, nullptr, ty, WG_CIT);
     T acc[4][4], accb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -539,36 +808,34 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
     }
+    // this warp's rows of a chunk: 2 dz rows (channels co0 + warp + 8 i) and NY source channels (ci_lo + warp + 8 u), clamped
+    int rdz[2], rci[NY];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) rdz[i] = min(warp + 8 * i, a.Cout - co0 - 1);
+#pragma unroll
+    for (int u = 0; u < NY; ++u) rci[u] = min(warp + 8 * u, ci_hi - ci_lo - 1);
+    typename SD::Data ddz[2];
+    typename SY::Data dy[NY][NF];
+    PixelCoord pc = pixel_coord((int64_t)blockIdx.x * 32 + lane, a.npg, a.HW, a.W);
+    auto fetch = [&](const PixelCoord &c) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) ddz[i] = dsrc.fetch(((int64_t)c.n * a.Cout + co0 + rdz[i]) * a.HW + c.rem);
+#pragma unroll
+        for (int u = 0; u < NY; ++u)
+            fetch_offsets<T, KIND>(ysrc, ((int64_t)c.n * a.Cin + ci_lo + rci[u]) * a.HW + c.rem, c.h, a.H, a.W, dy[u]);
+    };
+    if ((int)blockIdx.x < a.nchunks) fetch(pc);
     for (int chunk = blockIdx.x; chunk < a.nchunks; chunk += gridDim.x) {
-        const PixelCoord pc = pixel_coord((int64_t)chunk * 32 + lane, a.npg, a.HW, a.W);
-        // issue every load of this warp's rows (2 dz rows, up to NY source channels) before consuming any of them
-        constexpr int NY = TAPS == 1 ? WG_CIT / 8 : 2, NF = KIND == 2 ? 3 : 1;
-        typename Source<T, SRC_DZ>::Coef cdz[2];
-        typename Source<T, SRC_DZ>::Data ddz[2];
-        typename Source<T, YSRC>::Coef cy[NY];
-        typename Source<T, YSRC>::Data dy[NY][NF];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int co = min(co0 + warp + 8 * i, a.Cout - 1);
-            cdz[i] = dsrc.coefs(co);
-            ddz[i] = dsrc.fetch(((int64_t)pc.n * a.Cout + co) * a.HW + pc.rem);
-        }
-#pragma unroll
-        for (int u = 0; u < NY; ++u) {
-            const int ci = min(ci_lo + warp + 8 * u, ci_hi - 1);
-            cy[u] = ysrc.coefs(ci);
-            fetch_offsets<T, KIND>(ysrc, ((int64_t)pc.n * a.Cin + ci) * a.HW + pc.rem, pc.h, a.H, a.W, dy[u]);
-        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int r = warp + 8 * i;
-            if (co0 + r < a.Cout) st4(s_dz + r * WG_LD + lane * 4, pc.active ? dsrc.finish(cdz[i], ddz[i]) : zero4<T>());
+            if (co0 + r < a.Cout) st4(s_dz + r * WG_LD + lane * 4, pc.active ? dsrc.finish(rdz[i], ddz[i]) : zero4<T>());
         }
 #pragma unroll
         for (int u = 0; u < NY; ++u) {
             const int ci = ci_lo + warp + 8 * u;  // warp-uniform
             V4<T> o[TAPS];
-            finish_offsets<T, KIND>(ysrc, cy[u], dy[u], pc.h, pc.w0, a.H, a.W, o);
+            finish_offsets<T, KIND>(ysrc, rci[u], dy[u], pc.h, pc.w0, a.H, a.W, o);
             if (ci < ci_hi) {
 #pragma unroll
                 for (int oi = 0; oi < TAPS; ++oi) {
@@ -578,6 +845,12 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
             }
         }
         __syncthreads();
+        // the next chunk's loads fly while this one is consumed
+        const int next = chunk + gridDim.x;
+        if (next < a.nchunks) {
+            pc = pixel_coord((int64_t)next * 32 + lane, a.npg, a.HW, a.W);
+            fetch(pc);
+        }
 #pragma unroll
         for (int pp = 0; pp < WG_PX / 8; pp += 4) {
             const int p = warp * (WG_PX / 8) + pp;
@@ -617,15 +890,17 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
 
 template <typename T>
 struct GradLayer {
-    const T *partial, *coef;
+    const T *partial;
+    const unsigned long long *accB;
     int PX, ntiles, tiles_cit, Cin, Cout, taps;
     int64_t base;  // offset of this layer's first parameter (conv.weight, conv.bias, bn.weight, bn.bias follow each other)
 };
 template <typename T>
 struct GradArgs {
     GradLayer<T> L[PNODE_CONV_MAX_LAYERS];
-    int nl, cs, accumulate;
+    int nl, accumulate;
     int64_t np;
+    const unsigned *flag;
     T *out;
     double coef;
 };
@@ -636,6 +911,7 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
     const int sub = threadIdx.x % G;
     const int64_t stride = (int64_t)gridDim.x * (blockDim.x / G);
     const int64_t rounds = (a.np + stride - 1) / stride;
+    const double bad = __ldcg(a.flag) != 0u ? NAN : 0.0;
     for (int64_t rd = 0; rd < rounds; ++rd) {
         const int64_t i = rd * stride + (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
         const bool live = i < a.np;
@@ -659,8 +935,9 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
                 }
                 for (int b = sub; b < l.PX; b += G) val += (double)__ldcg(l.partial + ((int64_t)b * l.ntiles + tile) * WG_TILE + idx);
             } else if (sub == 0) {
-                loc -= nw + l.Cout;
-                val = loc < l.Cout ? (double)l.coef[COEF_DGAMMA * a.cs + loc] : (double)l.coef[COEF_DBETA * a.cs + (loc - l.Cout)];
+                loc -= nw + l.Cout;  // bn.weight gradient = sum [y>0] g xhat, bn.bias gradient = sum [y>0] g
+                val = loc < l.Cout ? acc128_read(l.accB, l.Cout, (int)loc, 1) : acc128_read(l.accB, l.Cout, (int)(loc - l.Cout), 0);
+                val += bad;
             }
         }
 #pragma unroll
@@ -671,11 +948,11 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
 struct CbPlan {
-    int L, Cmax, cs;
+    int L, Cmax;
     int64_t M, npg;
     size_t esz;
-    size_t off_z[PNODE_CONV_MAX_LAYERS], off_g[2], off_coef[PNODE_CONV_MAX_LAYERS], off_stat, off_wpart[PNODE_CONV_MAX_LAYERS];
-    size_t off_counter, total;
+    size_t off_z[PNODE_CONV_MAX_LAYERS], off_g[2], off_accF[PNODE_CONV_MAX_LAYERS], off_accB[PNODE_CONV_MAX_LAYERS];
+    size_t off_flag, off_acc0, acc_bytes, off_wpart[PNODE_CONV_MAX_LAYERS], total;
     int kind[PNODE_CONV_MAX_LAYERS], taps[PNODE_CONV_MAX_LAYERS];
     int wg_px[PNODE_CONV_MAX_LAYERS], wg_tiles_cit[PNODE_CONV_MAX_LAYERS], wg_ntiles[PNODE_CONV_MAX_LAYERS];
     int64_t pbase[PNODE_CONV_MAX_LAYERS + 1];
@@ -688,23 +965,30 @@ struct ConvGrid {
     size_t smem;
 };
 
-// thread = 4 pixels x rc output channels; rc = 4 when 8 channels per thread would leave the SMs short of resident warps
-static ConvGrid conv_grid(int CA, int CB, int taps, int64_t npg, size_t esz) {
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// thread = 4 pixels x rc output channels, CTA = 64 pixel groups x cg channel groups, grid.y = further channel tiles
+static ConvGrid conv_grid(int CA, int CB, int taps, int ncoef_in, bool dgrad_epi, int64_t npg, size_t esz) {
     ConvGrid g;
     const int sm = sm_count();
-    g.rc = (CB % 8 == 0 && (int64_t)(CB / 8) * npg >= (int64_t)sm * 1024) ? 8 : 4;
-    static const int force_rc = getenv("PNODE_CONV_RC") ? atoi(getenv("PNODE_CONV_RC")) : 0;  // tuning knob
-    if (force_rc == 4 || (force_rc == 8 && CB % 8 == 0)) g.rc = force_rc;
+    static const int want_rc = env_int("PNODE_CONV_RC", 8);  // tuning knobs
+    static const int occ = env_int("PNODE_CONV_OCC", 1024);
+    g.rc = want_rc;
+    if (g.rc == 16 && (CB % 16 != 0 || esz == 8)) g.rc = 8;
+    if (g.rc == 8 && CB % 8 != 0) g.rc = 4;
+    if (g.rc != 4 && g.rc != 8 && g.rc != 16) g.rc = 4;
     int groups = CB / g.rc;
     g.cg = groups < CB_MAXCG ? groups : CB_MAXCG;
     while (groups % g.cg != 0) --g.cg;
     g.gy = groups / g.cg;
     const int tiles = (int)((npg + CB_PGX - 1) / CB_PGX);
-    static const int occ = getenv("PNODE_CONV_OCC") ? atoi(getenv("PNODE_CONV_OCC")) : 1024;  // tuning knob
     int cap = sm * (occ / (CB_PGX * g.cg)) / g.gy;
     if (cap < 1) cap = 1;
     g.gx = tiles < cap ? tiles : cap;
-    g.smem = (size_t)CA * taps * g.cg * g.rc * esz;
+    g.smem = ((size_t)CA * taps * g.cg * g.rc + (size_t)ncoef_in * CA + (dgrad_epi ? 4 * g.cg * g.rc : 0)) * esz;
     return g;
 }
 
@@ -737,7 +1021,7 @@ static int cb_plan(const pnode_convblock_desc *d, CbPlan &p) {
         if (l.cout > p.Cmax) p.Cmax = l.cout;
         p.pbase[k + 1] = p.pbase[k] + (int64_t)l.cout * l.cin * p.taps[k] + 3 * (int64_t)l.cout;
     }
-    p.cs = p.Cmax;
+    PNODE_REQUIRE(p.Cmax <= 2048, "convblock: at most 2048 channels (got %d)", p.Cmax);
     size_t off = 0;
     for (int k = 0; k < p.L; ++k) {
         p.off_z[k] = off;
@@ -747,54 +1031,128 @@ static int cb_plan(const pnode_convblock_desc *d, CbPlan &p) {
         p.off_g[i] = off;
         off = align_up(off + (size_t)p.M * p.Cmax * p.esz);
     }
+    // accumulators + flag: one contiguous region, zeroed by ONE memset at the start of every evaluation
+    p.off_acc0 = off;
+    p.off_flag = off;
+    off += 256;
     for (int k = 0; k < p.L; ++k) {
-        p.off_coef[k] = off;
-        off = align_up(off + (size_t)COEF_N * p.cs * p.esz);
+        const size_t one = (size_t)ACC_R * d->layer[k].cout * 2 * 2 * sizeof(unsigned long long);
+        p.off_accF[k] = off;
+        off += one;
+        p.off_accB[k] = off;
+        off += one;
     }
-    size_t stat = 0;
+    p.acc_bytes = off - p.off_acc0;
+    off = align_up(off);
     const int sm = sm_count();
     for (int k = 0; k < p.L; ++k) {
         const pnode_conv_layer &l = d->layer[k];
-        const ConvGrid f = conv_grid(l.cin, l.cout, p.taps[k], p.npg, p.esz);
-        const ConvGrid b = conv_grid(l.cout, l.cin, p.taps[k], p.npg, p.esz);
-        const ConvGrid t = conv_grid(0, l.cout, 1, p.npg, p.esz);
-        size_t need = (size_t)f.gx * l.cout;
-        if ((size_t)b.gx * l.cin > need) need = (size_t)b.gx * l.cin;
-        if ((size_t)t.gx * l.cout > need) need = (size_t)t.gx * l.cout;
-        if (need > stat) stat = need;
+        const ConvGrid f = conv_grid(l.cin, l.cout, p.taps[k], 2, false, p.npg, p.esz);
+        const ConvGrid b = conv_grid(l.cout, l.cin, p.taps[k], 6, true, p.npg, p.esz);
         PNODE_REQUIRE(f.smem <= 200 * 1024 && b.smem <= 200 * 1024, "convblock: layer %d weights do not fit in shared memory", k);
         p.wg_tiles_cit[k] = (l.cin * p.taps[k] + WG_CIT - 1) / WG_CIT;
         p.wg_ntiles[k] = ((l.cout + WG_CO - 1) / WG_CO) * p.wg_tiles_cit[k];
         const int nchunks = (int)((p.npg + 31) / 32);
-        int px = sm * 4 / p.wg_ntiles[k];
+        static const int wg_occ = env_int("PNODE_WGRAD_OCC", 4);
+        int px = sm * wg_occ / p.wg_ntiles[k];
         if (px < 1) px = 1;
         if (px > nchunks) px = nchunks;
         p.wg_px[k] = px;
     }
-    p.off_stat = off;
-    off = align_up(off + stat * 2 * sizeof(double));
     for (int k = 0; k < p.L; ++k) {
         p.off_wpart[k] = off;
         off = align_up(off + (size_t)p.wg_px[k] * p.wg_ntiles[k] * WG_TILE * p.esz);
     }
-    p.off_counter = off;
-    off = align_up(off + 256);
     p.total = off;
     return 0;
 }
 
+struct PipeGrid {
+    bool ok;
+    int rc, cg, gy, gx, S, tiles;
+    size_t smem;
+};
+
+// geometry of the pipelined kernel, or ok = false when the shape needs the direct kernel (halo rows, odd channel counts)
+static PipeGrid pipe_grid(int kind, int src, int CA, int CB, int taps, int64_t npg, int HW, size_t esz) {
+    PipeGrid g = {};
+    static const int enabled = env_int("PNODE_CONV_PIPE", 1);
+    static const int want_rc = env_int("PNODE_PIPE_RC", 16);
+    static const int want_s = env_int("PNODE_PIPE_STAGES", 4);
+    static const int ctas_per_sm = env_int("PNODE_PIPE_CTAS", 2);
+    if (!enabled) return g;
+    const int rcmax = esz == 8 ? 8 : (want_rc >= 16 ? 16 : 8);
+    g.rc = 0;
+    for (int rc = rcmax; rc >= (esz == 8 ? 4 : 8); rc >>= 1)
+        if (CB % rc == 0) {
+            g.rc = rc;
+            break;
+        }
+    if (g.rc == 0) return g;
+    const int groups = CB / g.rc;
+    g.cg = groups % 2 == 0 ? 2 : 1;
+    g.gy = groups / g.cg;
+    const int PGT = CP_CONSUMERS / g.cg, TP = 4 * PGT;
+    if (!((TP % HW == 0) || (HW % TP == 0 && kind != 2))) return g;
+    const int KC = src == SRC_DZ ? 2 : 4, NT = src == SRC_DZ ? 2 : 1;
+    if (CA % KC != 0) return g;
+    const int ncoef = src == SRC_RAW ? 0 : (src == SRC_ACT ? 2 : 6);
+    const int CT = g.cg * g.rc;
+    const size_t head = (128 + ((size_t)CA * taps * CT + (size_t)ncoef * CA + 4 * CT) * esz + 127) & ~(size_t)127;
+    const size_t stage = (size_t)NT * KC * TP * esz;
+    g.S = want_s < 2 ? 2 : (want_s > 8 ? 8 : want_s);
+    static const int smem_cap = env_int("PNODE_PIPE_SMEM_KB", 110);
+    while (g.S > 2 && head + g.S * stage > (size_t)smem_cap * 1024) --g.S;
+    g.smem = head + g.S * stage;
+    if (g.smem > 200 * 1024) return g;
+    g.tiles = (int)((npg + PGT - 1) / PGT);
+    int cap = sm_count() * ctas_per_sm / g.gy;
+    if (cap < 1) cap = 1;
+    g.gx = g.tiles < cap ? g.tiles : cap;
+    g.ok = true;
+    return g;
+}
+
 template <typename T, int KIND, int SRC, int EPI>
-static int launch_conv_rc(const ConvArgs<T> &a, const ConvGrid &g, cudaStream_t st) {
-    dim3 grid(g.gx, g.gy), block(CB_PGX, g.cg);
-    if (g.rc == 8) {
-        if (g.smem > 32 * 1024)
-            PNODE_CUDA_OK(cudaFuncSetAttribute(conv_kernel<T, KIND, SRC, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        conv_kernel<T, KIND, SRC, EPI, 8><<<grid, block, g.smem, st>>>(a);
-    } else {
-        if (g.smem > 32 * 1024)
-            PNODE_CUDA_OK(cudaFuncSetAttribute(conv_kernel<T, KIND, SRC, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        conv_kernel<T, KIND, SRC, EPI, 4><<<grid, block, g.smem, st>>>(a);
+static int launch_conv_rc(const ConvArgs<T> &a_in, const ConvGrid &g, cudaStream_t st) {
+    const PipeGrid pg = pipe_grid(KIND, SRC, a_in.CA, a_in.CB, KIND == 0 ? 1 : 3, a_in.npg, a_in.HW, sizeof(T));
+    if (pg.ok) {
+        ConvArgs<T> a = a_in;
+        a.tiles = pg.tiles;
+        dim3 grid(pg.gx, pg.gy);
+#define PNODE_PIPE_LAUNCH(RC)                                                                                                    \
+    do {                                                                                                                         \
+        PNODE_CUDA_OK(cudaFuncSetAttribute(convp_kernel<T, KIND, SRC, EPI, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           (int)pg.smem));                                                                      \
+        convp_kernel<T, KIND, SRC, EPI, RC><<<grid, CP_CONSUMERS + 32, pg.smem, st>>>(a, pg.cg, pg.S);                          \
+    } while (0)
+        if (pg.rc == 16) {
+            if constexpr (sizeof(T) == 4) PNODE_PIPE_LAUNCH(16);
+        } else if (pg.rc == 8) {
+            PNODE_PIPE_LAUNCH(8);
+        } else {
+            if constexpr (sizeof(T) == 8) PNODE_PIPE_LAUNCH(4);
+        }
+#undef PNODE_PIPE_LAUNCH
+        return 0;
     }
+    const ConvArgs<T> &a = a_in;
+    dim3 grid(g.gx, g.gy), block(CB_PGX, g.cg);
+#define PNODE_CONV_LAUNCH(RC)                                                                                                   \
+    do {                                                                                                                        \
+        if (g.smem > 32 * 1024)                                                                                                 \
+            PNODE_CUDA_OK(cudaFuncSetAttribute(conv_kernel<T, KIND, SRC, EPI, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)g.smem));                                                                  \
+        conv_kernel<T, KIND, SRC, EPI, RC><<<grid, block, g.smem, st>>>(a);                                                     \
+    } while (0)
+    if (g.rc == 16) {
+        if constexpr (sizeof(T) == 4) PNODE_CONV_LAUNCH(16);
+    } else if (g.rc == 8) {
+        PNODE_CONV_LAUNCH(8);
+    } else {
+        PNODE_CONV_LAUNCH(4);
+    }
+#undef PNODE_CONV_LAUNCH
     return 0;
 }
 
@@ -807,11 +1165,11 @@ static int launch_conv(int kind, const ConvArgs<T> &a, const ConvGrid &g, cudaSt
 
 template <typename T, int YSRC>
 static int launch_wgrad(int kind, const WgradArgs<T> &a, int px, int ntiles, cudaStream_t st) {
-    const size_t smem = (size_t)(WG_CO + WG_CIT) * WG_LD * sizeof(T);
+    const size_t smem = ((size_t)(WG_CO + WG_CIT) * WG_LD + 6 * WG_CO + 2 * WG_CIT) * sizeof(T);
     dim3 grid(px, ntiles);
 #define PNODE_WG(K)                                                                                                        \
     do {                                                                                                                   \
-        if (smem > 48 * 1024)                                                                                              \
+        if (smem > 32 * 1024)                                                                                              \
             PNODE_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<T, K, YSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                (int)smem));                                                               \
         conv_wgrad_kernel<T, K, YSRC><<<grid, WG_THREADS, smem, st>>>(a);                                                  \
@@ -830,40 +1188,50 @@ struct Bufs {
     Bufs(void *work, const CbPlan &pl) : w(static_cast<unsigned char *>(work)), p(pl) {}
     T *z(int k) const { return reinterpret_cast<T *>(w + p.off_z[k]); }
     T *g(int i) const { return reinterpret_cast<T *>(w + p.off_g[i]); }
-    T *coef(int k) const { return reinterpret_cast<T *>(w + p.off_coef[k]); }
-    double *stat() const { return reinterpret_cast<double *>(w + p.off_stat); }
+    unsigned long long *accF(int k) const { return reinterpret_cast<unsigned long long *>(w + p.off_accF[k]); }
+    unsigned long long *accB(int k) const { return reinterpret_cast<unsigned long long *>(w + p.off_accB[k]); }
+    unsigned *flag() const { return reinterpret_cast<unsigned *>(w + p.off_flag); }
     T *wpart(int k) const { return reinterpret_cast<T *>(w + p.off_wpart[k]); }
-    unsigned *counter() const { return reinterpret_cast<unsigned *>(w + p.off_counter); }
 };
 
 template <typename T>
+static BnRef bn_ref(const pnode_convblock_desc *d, const Bufs<T> &b, int k) {
+    const pnode_conv_layer &l = d->layer[k];
+    BnRef r;
+    r.accF = b.accF(k), r.accB = b.accB(k);
+    r.gamma = l.d_gamma, r.beta = l.d_beta;
+    r.rmean = l.d_running_mean, r.rvar = l.d_running_var;
+    r.nbt = static_cast<long long *>(l.d_num_batches_tracked);
+    r.eps = l.eps, r.momentum = l.momentum;
+    r.C = l.cout;
+    return r;
+}
+
+template <typename T>
 static void fill_common(ConvArgs<T> &a, const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b) {
-    a.H = d->H, a.W = d->W, a.HW = d->H * d->W, a.cs = p.cs;
+    a.H = d->H, a.W = d->W, a.HW = d->H * d->W;
     a.npg = p.npg;
     a.tiles = (int)((p.npg + CB_PGX - 1) / CB_PGX);
     a.M = (double)p.M;
-    a.partial = b.stat();
-    a.counter = b.counter();
+    a.flag = b.flag();
 }
 
-// z_1 .. z_L of the chain (and the BatchNorm coefficients / running statistics of every layer)
+// z_1 .. z_L of the chain, the exact batch statistics of every layer, and the running-statistics updates of layers 1..L-1
+// (layer L's update belongs to whoever consumes z_L next: act_out_kernel or top_stats_kernel)
 template <typename T>
 static int forward_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b, const T *x, cudaStream_t st) {
+    PNODE_CUDA_OK(cudaMemsetAsync(b.w + p.off_acc0, 0, p.acc_bytes, st));
     for (int k = 0; k < p.L; ++k) {
         const pnode_conv_layer &l = d->layer[k];
         ConvArgs<T> a = {};
         fill_common(a, d, p, b);
         a.in = k == 0 ? x : b.z(k - 1);
-        a.coef_in = k == 0 ? nullptr : b.coef(k - 1);
+        if (k > 0) a.bin = bn_ref(d, b, k - 1), a.upd_in = 1;
         a.w = static_cast<const T *>(l.d_weight), a.bias = static_cast<const T *>(l.d_bias);
         a.out = b.z(k);
-        a.coef_out = b.coef(k);
-        a.gamma = static_cast<const T *>(l.d_gamma), a.beta = static_cast<const T *>(l.d_beta);
-        a.rmean = static_cast<T *>(l.d_running_mean), a.rvar = static_cast<T *>(l.d_running_var);
-        a.nbt = static_cast<long long *>(l.d_num_batches_tracked);
-        a.eps = l.eps, a.momentum = l.momentum;
+        a.acc_out = b.accF(k);
         a.CA = l.cin, a.CB = l.cout;
-        const ConvGrid g = conv_grid(l.cin, l.cout, p.taps[k], p.npg, p.esz);
+        const ConvGrid g = conv_grid(l.cin, l.cout, p.taps[k], k == 0 ? 0 : 2, false, p.npg, p.esz);
         int rc = k == 0 ? launch_conv<T, SRC_RAW, EPI_FWD>(p.kind[k], a, g, st) : launch_conv<T, SRC_ACT, EPI_FWD>(p.kind[k], a, g, st);
         if (rc) return rc;
     }
@@ -879,8 +1247,8 @@ static int act_out(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T>
     int64_t blocks = (nvec + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    act_out_kernel<T><<<(int)blocks, 256, 0, st>>>(b.z(p.L - 1), b.coef(p.L - 1), p.cs, C, d->H * d->W, nvec, out, base,
-                                                    (T)base_coef, (T)kcoef, kout);
+    act_out_kernel<T><<<(int)blocks, 256, 2 * C * sizeof(T), st>>>(b.z(p.L - 1), bn_ref(d, b, p.L - 1), (double)p.M, b.flag(), 1,
+                                                                    d->H * d->W, nvec, out, base, (T)base_coef, (T)kcoef, kout);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -893,25 +1261,36 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
         const pnode_conv_layer &l = d->layer[L - 1];
         ConvArgs<T> a = {};
         fill_common(a, d, p, b);
-        a.in = w, a.zprev = b.z(L - 1), a.coef_out = b.coef(L - 1);
+        a.in = w, a.zprev = b.z(L - 1);
+        a.bout = bn_ref(d, b, L - 1), a.upd_out = 1;
+        a.acc_out = b.accB(L - 1);
         a.CA = 0, a.CB = l.cout;
-        const ConvGrid g = conv_grid(0, l.cout, 1, p.npg, p.esz);
+        const ConvGrid g = conv_grid(0, l.cout, 1, 0, true, p.npg, p.esz);
         dim3 grid(g.gx, g.gy), block(CB_PGX, g.cg);
-        if (g.rc == 8) top_stats_kernel<T, 8><<<grid, block, 0, st>>>(a);
-        else top_stats_kernel<T, 4><<<grid, block, 0, st>>>(a);
+        const size_t smem = (size_t)4 * g.cg * g.rc * sizeof(T);
+        if (g.rc == 16) {
+            if constexpr (sizeof(T) == 4) top_stats_kernel<T, 16><<<grid, block, smem, st>>>(a);
+        } else if (g.rc == 8) {
+            top_stats_kernel<T, 8><<<grid, block, smem, st>>>(a);
+        } else {
+            top_stats_kernel<T, 4><<<grid, block, smem, st>>>(a);
+        }
     }
     const T *gk = w;
     for (int k = L - 1; k >= 0; --k) {
         const pnode_conv_layer &l = d->layer[k];
         if (gout != nullptr) {
             WgradArgs<T> wa = {};
-            wa.g = gk, wa.z = b.z(k), wa.coef_k = b.coef(k);
-            wa.yin = k == 0 ? x : b.z(k - 1), wa.coef_in = k == 0 ? nullptr : b.coef(k - 1);
+            wa.g = gk, wa.z = b.z(k), wa.bk = bn_ref(d, b, k);
+            wa.yin = k == 0 ? x : b.z(k - 1);
+            if (k > 0) wa.bin = bn_ref(d, b, k - 1);
+            wa.flag = b.flag();
             wa.partial = b.wpart(k);
-            wa.Cin = l.cin, wa.Cout = l.cout, wa.H = d->H, wa.W = d->W, wa.HW = d->H * d->W, wa.cs = p.cs;
+            wa.Cin = l.cin, wa.Cout = l.cout, wa.H = d->H, wa.W = d->W, wa.HW = d->H * d->W;
             wa.tiles_cit = p.wg_tiles_cit[k];
             wa.npg = p.npg;
             wa.nchunks = (int)((p.npg + 31) / 32);
+            wa.M = (double)p.M;
             int rc = k == 0 ? launch_wgrad<T, SRC_RAW>(p.kind[k], wa, p.wg_px[k], p.wg_ntiles[k], st)
                             : launch_wgrad<T, SRC_ACT>(p.kind[k], wa, p.wg_px[k], p.wg_ntiles[k], st);
             if (rc) return rc;
@@ -919,17 +1298,18 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
         if (k == 0 && vu == nullptr) break;
         ConvArgs<T> a = {};
         fill_common(a, d, p, b);
-        a.in = gk, a.in2 = b.z(k), a.coef_in = b.coef(k);
+        a.in = gk, a.in2 = b.z(k), a.bin = bn_ref(d, b, k);
         a.w = static_cast<const T *>(l.d_weight);
         a.CA = l.cout, a.CB = l.cin;
-        const ConvGrid g = conv_grid(l.cout, l.cin, p.taps[k], p.npg, p.esz);
+        const ConvGrid g = conv_grid(l.cout, l.cin, p.taps[k], 6, k > 0, p.npg, p.esz);
         int rc;
         if (k == 0) {
             a.out = vu;
             rc = launch_conv<T, SRC_DZ, EPI_NONE>(p.kind[k], a, g, st);
         } else {
             a.out = b.g(k & 1);
-            a.zprev = b.z(k - 1), a.coef_out = b.coef(k - 1);
+            a.zprev = b.z(k - 1), a.bout = bn_ref(d, b, k - 1);
+            a.acc_out = b.accB(k - 1);
             rc = launch_conv<T, SRC_DZ, EPI_DGRAD>(p.kind[k], a, g, st);
             gk = a.out;
         }
@@ -937,15 +1317,15 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
     }
     if (gout != nullptr) {
         GradArgs<T> ga = {};
-        ga.nl = L, ga.cs = p.cs, ga.accumulate = accumulate, ga.np = p.pbase[L], ga.out = gout, ga.coef = coef;
+        ga.nl = L, ga.accumulate = accumulate, ga.np = p.pbase[L], ga.out = gout, ga.coef = coef, ga.flag = b.flag();
+        int pxmax = 1;
         for (int k = 0; k < L; ++k) {
-            ga.L[k].partial = b.wpart(k), ga.L[k].coef = b.coef(k);
+            ga.L[k].partial = b.wpart(k), ga.L[k].accB = b.accB(k);
             ga.L[k].PX = p.wg_px[k], ga.L[k].ntiles = p.wg_ntiles[k], ga.L[k].tiles_cit = p.wg_tiles_cit[k];
             ga.L[k].Cin = d->layer[k].cin, ga.L[k].Cout = d->layer[k].cout, ga.L[k].taps = p.taps[k];
             ga.L[k].base = p.pbase[k];
+            pxmax = p.wg_px[k] > pxmax ? p.wg_px[k] : pxmax;
         }
-        int pxmax = 1;
-        for (int k = 0; k < L; ++k) pxmax = p.wg_px[k] > pxmax ? p.wg_px[k] : pxmax;
         const int G = pxmax > 8 ? 32 : 4;
         int64_t blocks = (ga.np * G + 255) / 256;
         const int64_t cap = (int64_t)sm_count() * 8;

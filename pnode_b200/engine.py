@@ -368,16 +368,25 @@ class GenericTS:
         sc, ops = self.scheme, self.ops
         s = sc.s
         Y, K = [], []
+        y_next = None  # Y_{i+1} already formed by a right-hand-side evaluator that fuses the stage combination into its output pass
         for i in range(s):
             if i == 0:
                 y = u
+            elif y_next is not None:
+                y = y_next
             else:
                 idx = [j for j in range(i) if sc.A[i][j] != 0.0]
                 y = torch.empty_like(u)
                 ops.lincomb(y, u, 1.0, [K[j] for j in idx], [h * sc.A[i][j] for j in idx])
             Y.append(y)
+            y_next = None
             if i == 0 and k_fsal is not None:
                 K.append(k_fsal)
+            elif (hasattr(cb, "f_and_combine") and i + 1 < s
+                  and [j for j in range(i + 1) if sc.A[i + 1][j] != 0.0] == [i]):
+                # Y_{i+1} = u + h a_{i+1,i} k_i depends on k_i alone (euler / midpoint / rk4): one pass writes k_i and Y_{i+1}
+                k, y_next = cb.f_and_combine(t + sc.c[i] * h, y, u, h * sc.A[i + 1][i])
+                K.append(k)
             else:
                 K.append(cb.f(t + sc.c[i] * h, y))
         idx = [j for j in range(s) if sc.b[j] != 0.0 or (adaptive and sc.bembed[j] != 0.0)]
