@@ -223,8 +223,11 @@ int pnode_bn_relu_backward(const void *d_dy, const void *d_x, const void *d_y, c
  * Both advance running_mean / running_var / num_batches_tracked of every layer once, like the module's forward.
  * Parameter order of d_grads = func.parameters(): per layer conv.weight [cout,cin,kh,kw], conv.bias, bn.weight, bn.bias.
  * Tensors are NCHW contiguous, 16-byte aligned; W a power of two in 4..128; channel counts multiples of 4.
- * d_work: pnode_convblock_work_bytes() bytes, zero-initialised once by the caller (holds z_k, the per-channel BatchNorm
- * coefficients, per-CTA partial sums and a ticket counter the kernels restore).
+ * Memory: d_act (pnode_convblock_act_bytes) receives the raw layer outputs z_1..z_L and the exact batch statistics of ONE
+ * evaluation -- the forward's by-product; kept by the caller, it lets the adjoint skip the forward re-evaluation of that stage
+ * (act_valid != 0: same x, same parameters; the BatchNorm buffers still advance once, as the module's re-evaluation would).
+ * d_work (pnode_convblock_work_bytes) is scratch shared by all calls.  Neither needs initialising.
+ * Batch statistics are accumulated exactly (128-bit fixed point, integer atomics): results are bit-reproducible.
  * -------------------------------------------------------------------------------------------------------------- */
 #define PNODE_CONV_MAX_LAYERS 8
 typedef struct pnode_conv_layer {
@@ -242,14 +245,15 @@ typedef struct pnode_convblock_desc {
     pnode_conv_layer layer[PNODE_CONV_MAX_LAYERS];
 } pnode_convblock_desc;
 
-int64_t pnode_convblock_work_bytes(const pnode_convblock_desc *desc);  /* -1: unsupported shape (pnode_last_error) */
+int64_t pnode_convblock_act_bytes(const pnode_convblock_desc *desc);   /* -1: unsupported shape (pnode_last_error) */
+int64_t pnode_convblock_work_bytes(const pnode_convblock_desc *desc);
 int64_t pnode_convblock_param_count(const pnode_convblock_desc *desc);
 /* d_out (may be NULL) = base_coef * d_base + k_coef * f(x)  (d_base NULL: d_out = f(x));  d_k (may be NULL) = f(x) */
 int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, void *d_out, const void *d_base,
-                            double base_coef, double k_coef, void *d_k, void *d_work, void *stream);
+                            double base_coef, double k_coef, void *d_k, void *d_act, void *stream);
 /* d_vu (may be NULL: parameter gradients only); d_grads (may be NULL: state VJP only) [param_count] */
 int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads,
-                        double coef, int accumulate, void *d_work, void *stream);
+                        double coef, int accumulate, void *d_act, int act_valid, void *d_work, void *stream);
 
 /* ----------------------------------------------------------------------------------------------------------------
  * Data-parallel variants of the adjoint sweeps: the all-reduce of mu over the GPUs of one NVLink/NVSwitch domain is fused

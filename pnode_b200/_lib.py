@@ -73,10 +73,11 @@ _SIGNATURES = {
     "pnode_bn_work_bytes": (_i64, [_i]),
     "pnode_bn_relu_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp, _i, _vp]),
     "pnode_bn_relu_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "pnode_convblock_act_bytes": (_i64, [C.POINTER(ConvBlockDesc)]),
     "pnode_convblock_work_bytes": (_i64, [C.POINTER(ConvBlockDesc)]),
     "pnode_convblock_param_count": (_i64, [C.POINTER(ConvBlockDesc)]),
     "pnode_convblock_forward": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp]),
-    "pnode_convblock_vjp": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
+    "pnode_convblock_vjp": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _d, _i, _vp, _i, _vp, _vp]),
     "pnode_peer_buffer_bytes": (_i64, [_i]),
     "pnode_mlp_rk_adjoint_dp": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _i, _i, C.c_uint64, _vp]),

@@ -104,11 +104,20 @@ class ConvBlockCallbacks(Callbacks):
         if len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4 and \
                 Options().getString("pnode_convblock_native", "1") not in ("0", "false", "no"):
             desc = self._make_desc()
-            nbytes = int(self.lib.pnode_convblock_work_bytes(C.byref(desc)))
-            if nbytes >= 0 and int(self.lib.pnode_convblock_param_count(C.byref(desc))) == self.nparams:
+            nact = int(self.lib.pnode_convblock_act_bytes(C.byref(desc)))
+            if nact >= 0 and int(self.lib.pnode_convblock_param_count(C.byref(desc))) == self.nparams:
                 self.native = True
                 self._desc = desc
-                self._cwork = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+                self._act_bytes = nact
+                self._cwork = torch.empty(int(self.lib.pnode_convblock_work_bytes(C.byref(desc))), dtype=torch.uint8, device=dev)
+                self._act0 = torch.empty(nact, dtype=torch.uint8, device=dev)  # activation set of evaluations that are not kept
+                # Forward evaluations keep their activation set (z_1..z_L + batch statistics: the forward's by-product) so
+                # that the adjoint stage at the same point skips the module's forward re-evaluation; bounded by a byte budget.
+                self._saved = {}
+                self._saved_bytes = 0
+                self._save_budget = int(float(Options().getString("pnode_convblock_save_mb", "8192")) * (1 << 20))
+                self.reused_activations = 0
+                self._keep = True
 
     def _make_desc(self):
         d = _lib.ConvBlockDesc()
@@ -125,7 +134,8 @@ class ConvBlockCallbacks(Callbacks):
         return d
 
     def _refresh_pointers(self, d):
-        """Parameters are borrowed, never copied: re-read their addresses before every call."""
+        """Parameters are borrowed, never copied: their addresses are re-read at the start of every
+        solve / adjoint sweep (begin()), not cached across optimiser steps."""
         for k, (conv, bn) in enumerate(self.layers):
             l = d.layer[k]
             l.d_weight, l.d_bias = conv.weight.data_ptr(), conv.bias.data_ptr()
@@ -133,27 +143,54 @@ class ConvBlockCallbacks(Callbacks):
             l.d_running_mean, l.d_running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             l.d_num_batches_tracked = bn.num_batches_tracked.data_ptr()
 
-    def _native_f(self, u, out=None, base=None, base_coef=0.0, k_coef=1.0, k=None):
+    def _param_versions(self):
+        return tuple(p._version for p in self.params)
+
+    def begin(self, forward, keep=True):
+        """Called by the time stepper at the start of a forward solve (forward=True; keep = an adjoint sweep will follow) and
+        of an adjoint sweep."""
+        if not self.native:
+            return
         self._refresh_pointers(self._desc)
+        if forward:
+            self._saved.clear()
+            self._saved_bytes = 0
+            self._keep = bool(keep)
+
+    def _act_for(self, u):
+        """Activation buffer for a forward evaluation at u: a kept one while the budget lasts, else the shared one."""
+        if not self._keep or self._saved_bytes + self._act_bytes > self._save_budget:
+            return self._act0
+        act = torch.empty(self._act_bytes, dtype=torch.uint8, device=u.device)
+        self._saved[u.data_ptr()] = (u, u._version, self._param_versions(), act)  # holding u keeps its address unique
+        self._saved_bytes += self._act_bytes
+        return act
+
+    def _native_f(self, u, out=None, base=None, base_coef=0.0, k_coef=1.0, k=None, keep=True):
         if out is None and k is None:
             out = torch.empty_like(u)
+        act = self._act_for(u) if keep else self._act0
         _lib.check(self.lib.pnode_convblock_forward(C.byref(self._desc), u.data_ptr(), None if out is None else out.data_ptr(),
                                                     None if base is None else base.data_ptr(), float(base_coef), float(k_coef),
-                                                    None if k is None else k.data_ptr(), self._cwork.data_ptr(), _stream()))
+                                                    None if k is None else k.data_ptr(), act.data_ptr(), _stream()))
         self.launches += len(self.layers) + 1
         return out
 
     def _native_vjp(self, u, w, want_u, grads, coef, accumulate):
-        self._refresh_pointers(self._desc)
         if not w.is_contiguous():
             w = w.contiguous()
         vu = torch.empty_like(u) if want_u else None
+        ent = self._saved.get(u.data_ptr())
+        valid = ent is not None and ent[1] == u._version and ent[2] == self._param_versions() and ent[0].numel() == u.numel()
+        act = ent[3] if valid else self._act0
         _lib.check(self.lib.pnode_convblock_vjp(C.byref(self._desc), u.data_ptr(), w.data_ptr(),
                                                 None if vu is None else vu.data_ptr(),
                                                 None if grads is None else grads.data_ptr(), float(coef), int(accumulate),
-                                                self._cwork.data_ptr(), _stream()))
+                                                act.data_ptr(), int(valid), self._cwork.data_ptr(), _stream()))
         L = len(self.layers)
-        self.launches += L + 1 + (L if grads is not None else 0) + (L if want_u else L - 1) + (1 if grads is not None else 0)
+        self.reused_activations += int(valid)
+        self.launches += (0 if valid else L) + 1 + (L if grads is not None else 0) + (L if want_u else L - 1) + \
+            (1 if grads is not None else 0)
         return vu
 
     def f_and_combine(self, t, u, base, coef):

@@ -31,6 +31,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <map>
+
 #include "common.cuh"
 
 namespace pnode {
@@ -46,6 +48,11 @@ template <typename T>
 struct V4 {
     T v[4];
 };
+
+// Programmatic dependent launch: every kernel of this file lets its successor start early (its prologue -- barrier init, weight
+// staging -- overlaps this kernel's tail) and waits for its predecessor's memory before touching anything that depends on it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ V4<float> ld4(const float *p) {
     const float4 t = *reinterpret_cast<const float4 *>(p);
@@ -426,11 +433,13 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T
     T *tout = tin + NCoef<SRC>::N * a.CA;     // [4][CT]   (EPI_DGRAD)
     const int cb0 = blockIdx.y * CT;
     const int tid = threadIdx.y * CB_PGX + threadIdx.x, nthr = CB_PGX * blockDim.y;
+    pdl_launch_dependents();
     for (int i = tid; i < a.CA * TAPS * CT; i += nthr) {
         const int bl = i % CT, ao = i / CT, o = ao % TAPS, ach = ao / TAPS, b = cb0 + bl;
         // forward: W[co = b][ci = ach][tap = o];  data gradient: W[co = ach][ci = b][tap = TAPS-1-o]
         ws[i] = FWD ? a.w[((int64_t)b * a.CA + ach) * TAPS + o] : a.w[((int64_t)ach * a.CB + b) * TAPS + (TAPS - 1 - o)];
     }
+    pdl_wait();
     fill_input_coefs<T, SRC>(tin, a.CA, a.bin, 0, a.CA, a.M, a.flag, tid, nthr);
     if constexpr (EPI == EPI_DGRAD) fill_output_coefs<T>(tout, CT, a.bout, cb0, CT, a.M, a.flag, tid, nthr);
     if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -572,8 +581,10 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_launch_dependents();
     __syncthreads();
     if (warp == CP_CONSUMERS / 32) {
+        pdl_wait();
         // ---- producer warp: every lane issues a share of the stage's bulk copies; lane 0 arms the barrier -------------------
         int slot = 0;
         uint32_t phase = 0;
@@ -614,6 +625,7 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
         const int bl = i % CT, ao = i / CT, o = ao % TAPS, ach = ao / TAPS, b = cb0 + bl;
         ws[i] = FWD ? a.w[((int64_t)b * a.CA + ach) * TAPS + o] : a.w[((int64_t)ach * a.CB + b) * TAPS + (TAPS - 1 - o)];
     }
+    pdl_wait();
     fill_input_coefs<T, SRC>(tin, a.CA, a.bin, 0, a.CA, a.M, a.flag, tid, CP_CONSUMERS);
     if constexpr (EPI == EPI_DGRAD) fill_output_coefs<T>(tout, CT, a.bout, cb0, CT, a.M, a.flag, tid, CP_CONSUMERS);
     if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -710,6 +722,8 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) top_stats_kernel(const ConvA
     const int CT = blockDim.y * RC;
     const int cb0 = blockIdx.y * CT, ch0 = cb0 + threadIdx.y * RC;
     const int tid = threadIdx.y * CB_PGX + threadIdx.x, nthr = CB_PGX * blockDim.y;
+    pdl_launch_dependents();
+    pdl_wait();
     fill_output_coefs<T>(tout, CT, a.bout, cb0, CT, a.M, a.flag, tid, nthr);
     if (blockIdx.x == 0 && blockIdx.y == 0 && a.upd_out) bn_update_running<T>(a.bout, a.M, a.flag, tid, nthr);
     __syncthreads();
@@ -742,6 +756,8 @@ __global__ void __launch_bounds__(256) act_out_kernel(const T *__restrict__ z, c
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *tab = reinterpret_cast<T *>(smem_raw);  // [2][C]
     const int C = b.C;
+    pdl_launch_dependents();
+    pdl_wait();
     fill_input_coefs<T, SRC_ACT>(tab, C, b, 0, C, M, flag, threadIdx.x, blockDim.x);
     if (blockIdx.x == 0 && upd) bn_update_running<T>(b, M, flag, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -764,7 +780,13 @@ __global__ void __launch_bounds__(256) act_out_kernel(const T *__restrict__ z, c
 }
 
 // ---- weight gradient ------------------------------------------------------------------------------------------------------
-constexpr int WG_CO = 16, WG_CIT = 32, WG_PX = 128, WG_LD = 132, WG_THREADS = 256, WG_TILE = WG_CO * WG_CIT + WG_CO;
+// dW[co][ci][tap] = sum_pixels dz[co][p] * y[ci][p + tap - 1]: pixels are the reduction dimension.  A CTA owns one
+// (4 TM) x (8 TN) tile of the (c_out) x (c_in * taps) gradient and a grid-stride share of the 128-pixel chunks; a chunk's dz
+// rows and (tap-shifted) y rows are formed on load, staged pixel-major in shared memory, and every warp accumulates the tile
+// over its own 16 pixels of the chunk (lane = 4 c_out groups x 8 c_in*tap groups, TM x TN register tile, LDS.128 along the
+// pixels).  (TM, TN) is picked per layer so that the tile fits the layer's channel counts (block 1: 16x32, 8x16, 16x24,
+// 16x48, 32x16).  The gradient of a convolution bias that feeds a BatchNorm is exactly zero (sum_p dz = 0) and is not computed.
+constexpr int WG_PX = 128, WG_LD = 132, WG_THREADS = 256;
 
 template <typename T>
 struct WgradArgs {
@@ -772,17 +794,20 @@ struct WgradArgs {
     const T *yin;     // y_{k-1}: raw block input (k = 1) or relu(bn(z_{k-1}))
     BnRef bk, bin;    // layer k (forward + backward sums), layer k-1 (forward sums)
     const unsigned *flag;
-    T *partial;       // [gridDim.x][gridDim.y][WG_TILE]
+    T *partial;       // [gridDim.x][gridDim.y][WG_CO * WG_CIT]
     int Cin, Cout, H, W, HW, tiles_cit;
     int64_t npg;
     int nchunks;
     double M;
 };
 
-template <typename T, int KIND, int YSRC>
+template <typename T, int KIND, int YSRC, int TM, int TN>
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<T> a) {
     constexpr int TAPS = KIND == 0 ? 1 : 3;
-    constexpr int NY = TAPS == 1 ? WG_CIT / 8 : 2, NF = KIND == 2 ? 3 : 1;
+    constexpr int WG_CO = 4 * TM, WG_CIT = 8 * TN, WG_TILE = WG_CO * WG_CIT;
+    constexpr int NDZ = (WG_CO + 7) / 8;                                          // dz rows per warp
+    constexpr int NY = TAPS == 1 ? (WG_CIT + 7) / 8 : (WG_CIT / 3 + 2 + 7) / 8;   // source channels per warp
+    constexpr int NF = KIND == 2 ? 3 : 1;
     typedef Source<T, SRC_DZ> SD;
     typedef Source<T, YSRC> SY;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -795,31 +820,31 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
     const int ci_lo = cit0 / TAPS, ci_hi = min(a.Cin, (cit0 + WG_CIT - 1) / TAPS + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cgp = lane & 3, cg8 = lane >> 2;
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < (WG_CO + WG_CIT) * WG_LD; i += WG_THREADS) s_dz[i] = T(0);
+    pdl_wait();
     fill_input_coefs<T, SRC_DZ>(tdz, WG_CO, a.bk, co0, min(WG_CO, a.Cout - co0), a.M, a.flag, threadIdx.x, WG_THREADS);
     fill_input_coefs<T, YSRC>(ty, WG_CIT, a.bin, ci_lo, ci_hi - ci_lo, a.M, a.flag, threadIdx.x, WG_THREADS);
     __syncthreads();
     SD dsrc(a.g, a.z, tdz, WG_CO);
     SY ysrc(a.yin, nullptr, ty, WG_CIT);
-    T acc[4][4], accb[4];
+    T acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        accb[i] = T(0);
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-    }
-    // this warp's rows of a chunk: 2 dz rows (channels co0 + warp + 8 i) and NY source channels (ci_lo + warp + 8 u), clamped
-    int rdz[2], rci[NY];
+        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+    // this warp's rows of a chunk: NDZ dz rows (channels co0 + warp + 8 i) and NY source channels (ci_lo + warp + 8 u), clamped
+    int rdz[NDZ], rci[NY];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) rdz[i] = min(warp + 8 * i, a.Cout - co0 - 1);
+    for (int i = 0; i < NDZ; ++i) rdz[i] = min(warp + 8 * i, min(WG_CO, a.Cout - co0) - 1);
 #pragma unroll
     for (int u = 0; u < NY; ++u) rci[u] = min(warp + 8 * u, ci_hi - ci_lo - 1);
-    typename SD::Data ddz[2];
+    typename SD::Data ddz[NDZ];
     typename SY::Data dy[NY][NF];
     PixelCoord pc = pixel_coord((int64_t)blockIdx.x * 32 + lane, a.npg, a.HW, a.W);
     auto fetch = [&](const PixelCoord &c) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) ddz[i] = dsrc.fetch(((int64_t)c.n * a.Cout + co0 + rdz[i]) * a.HW + c.rem);
+        for (int i = 0; i < NDZ; ++i) ddz[i] = dsrc.fetch(((int64_t)c.n * a.Cout + co0 + rdz[i]) * a.HW + c.rem);
 #pragma unroll
         for (int u = 0; u < NY; ++u)
             fetch_offsets<T, KIND>(ysrc, ((int64_t)c.n * a.Cin + ci_lo + rci[u]) * a.HW + c.rem, c.h, a.H, a.W, dy[u]);
@@ -827,9 +852,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
     if ((int)blockIdx.x < a.nchunks) fetch(pc);
     for (int chunk = blockIdx.x; chunk < a.nchunks; chunk += gridDim.x) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NDZ; ++i) {
             const int r = warp + 8 * i;
-            if (co0 + r < a.Cout) st4(s_dz + r * WG_LD + lane * 4, pc.active ? dsrc.finish(rdz[i], ddz[i]) : zero4<T>());
+            if (r < WG_CO && co0 + r < a.Cout)
+                st4(s_dz + r * WG_LD + lane * 4, pc.active ? dsrc.finish(rdz[i], ddz[i]) : zero4<T>());
         }
 #pragma unroll
         for (int u = 0; u < NY; ++u) {
@@ -854,31 +880,26 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
 #pragma unroll
         for (int pp = 0; pp < WG_PX / 8; pp += 4) {
             const int p = warp * (WG_PX / 8) + pp;
-            V4<T> av[4], bv[4];
+            V4<T> av[TM], bv[TN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = lds4<T>(s_dz + (cgp + 4 * i) * WG_LD + p);
+            for (int i = 0; i < TM; ++i) av[i] = lds4<T>(s_dz + (cgp + 4 * i) * WG_LD + p);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = lds4<T>(s_y + (cg8 + 8 * j) * WG_LD + p);
+            for (int j = 0; j < TN; ++j) bv[j] = lds4<T>(s_y + (cg8 + 8 * j) * WG_LD + p);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) accb[i] += av[i].v[e];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < TN; ++j)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[i][j] = fma(av[i].v[e], bv[j].v[e], acc[i][j]);
-            }
         }
         __syncthreads();
     }
     // combine the 8 warps (each saw different pixels) in a fixed order, one partial tile per CTA
     T *red = s_dz;  // 8 * WG_TILE scalars <= (WG_CO + WG_CIT) * WG_LD
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) red[warp * WG_TILE + (cgp + 4 * i) * WG_CIT + cg8 + 8 * j] = acc[i][j];
-        if (cg8 == 0) red[warp * WG_TILE + WG_CO * WG_CIT + cgp + 4 * i] = accb[i];
-    }
+        for (int j = 0; j < TN; ++j) red[warp * WG_TILE + (cgp + 4 * i) * WG_CIT + cg8 + 8 * j] = acc[i][j];
     __syncthreads();
     for (int idx = threadIdx.x; idx < WG_TILE; idx += WG_THREADS) {
         T t = T(0);
@@ -892,7 +913,7 @@ template <typename T>
 struct GradLayer {
     const T *partial;
     const unsigned long long *accB;
-    int PX, ntiles, tiles_cit, Cin, Cout, taps;
+    int PX, ntiles, tiles_cit, Cin, Cout, taps, wg_co, wg_cit;
     int64_t base;  // offset of this layer's first parameter (conv.weight, conv.bias, bn.weight, bn.bias follow each other)
 };
 template <typename T>
@@ -911,6 +932,8 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
     const int sub = threadIdx.x % G;
     const int64_t stride = (int64_t)gridDim.x * (blockDim.x / G);
     const int64_t rounds = (a.np + stride - 1) / stride;
+    pdl_launch_dependents();
+    pdl_wait();
     const double bad = __ldcg(a.flag) != 0u ? NAN : 0.0;
     for (int64_t rd = 0; rd < rounds; ++rd) {
         const int64_t i = rd * stride + (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
@@ -922,18 +945,14 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
             const GradLayer<T> &l = a.L[k];
             int64_t loc = i - l.base;
             const int64_t nw = (int64_t)l.Cout * l.Cin * l.taps;
-            if (loc < nw + l.Cout) {
-                int tile, idx;
-                if (loc < nw) {
-                    const int co = (int)(loc / (l.Cin * l.taps)), cit = (int)(loc % (l.Cin * l.taps));
-                    tile = (co / WG_CO) * l.tiles_cit + cit / WG_CIT;
-                    idx = (co % WG_CO) * WG_CIT + cit % WG_CIT;
-                } else {
-                    const int co = (int)(loc - nw);
-                    tile = (co / WG_CO) * l.tiles_cit;
-                    idx = WG_CO * WG_CIT + co % WG_CO;
-                }
-                for (int b = sub; b < l.PX; b += G) val += (double)__ldcg(l.partial + ((int64_t)b * l.ntiles + tile) * WG_TILE + idx);
+            if (loc < nw) {
+                const int co = (int)(loc / (l.Cin * l.taps)), cit = (int)(loc % (l.Cin * l.taps));
+                const int tile = (co / l.wg_co) * l.tiles_cit + cit / l.wg_cit;
+                const int idx = (co % l.wg_co) * l.wg_cit + cit % l.wg_cit;
+                const int64_t tsz = (int64_t)l.wg_co * l.wg_cit;
+                for (int b = sub; b < l.PX; b += G) val += (double)__ldcg(l.partial + ((int64_t)b * l.ntiles + tile) * tsz + idx);
+            } else if (loc < nw + l.Cout) {
+                val = 0.0;  // conv bias under a BatchNorm: sum_p dz = 0 exactly
             } else if (sub == 0) {
                 loc -= nw + l.Cout;  // bn.weight gradient = sum [y>0] g xhat, bn.bias gradient = sum [y>0] g
                 val = loc < l.Cout ? acc128_read(l.accB, l.Cout, (int)loc, 1) : acc128_read(l.accB, l.Cout, (int)(loc - l.Cout), 0);
@@ -951,10 +970,11 @@ struct CbPlan {
     int L, Cmax;
     int64_t M, npg;
     size_t esz;
-    size_t off_z[PNODE_CONV_MAX_LAYERS], off_g[2], off_accF[PNODE_CONV_MAX_LAYERS], off_accB[PNODE_CONV_MAX_LAYERS];
-    size_t off_flag, off_acc0, acc_bytes, off_wpart[PNODE_CONV_MAX_LAYERS], total;
+    size_t off_z[PNODE_CONV_MAX_LAYERS], off_g[PNODE_CONV_MAX_LAYERS], off_accF[PNODE_CONV_MAX_LAYERS], off_accB[PNODE_CONV_MAX_LAYERS];
+    size_t off_flag, off_acc0, acc_bytes, accB_bytes, off_wpart[PNODE_CONV_MAX_LAYERS], act_total, total;
     int kind[PNODE_CONV_MAX_LAYERS], taps[PNODE_CONV_MAX_LAYERS];
     int wg_px[PNODE_CONV_MAX_LAYERS], wg_tiles_cit[PNODE_CONV_MAX_LAYERS], wg_ntiles[PNODE_CONV_MAX_LAYERS];
+    int wg_tm[PNODE_CONV_MAX_LAYERS], wg_tn[PNODE_CONV_MAX_LAYERS];
     int64_t pbase[PNODE_CONV_MAX_LAYERS + 1];
 };
 
@@ -968,6 +988,29 @@ struct ConvGrid {
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
+}
+
+// One launcher for every kernel of this file: opt-in dynamic shared memory is raised once per kernel (not per launch), and the
+// launch carries the programmatic-stream-serialization attribute so that consecutive kernels overlap prologue and tail.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const int pdl = env_int("PNODE_CONV_PDL", 1);
+    static std::map<const void *, size_t> raised;
+    if (smem > 48 * 1024 - 4096) {
+        size_t &have = raised[reinterpret_cast<const void *>(kernel)];
+        if (have < smem) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            have = smem;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // thread = 4 pixels x rc output channels, CTA = 64 pixel groups x cg channel groups, grid.y = further channel tiles
@@ -1022,36 +1065,52 @@ static int cb_plan(const pnode_convblock_desc *d, CbPlan &p) {
         p.pbase[k + 1] = p.pbase[k] + (int64_t)l.cout * l.cin * p.taps[k] + 3 * (int64_t)l.cout;
     }
     PNODE_REQUIRE(p.Cmax <= 2048, "convblock: at most 2048 channels (got %d)", p.Cmax);
+    // activation region (one per saved evaluation): z_1..z_L, then the flag + forward accumulators (zeroed by one memset)
     size_t off = 0;
     for (int k = 0; k < p.L; ++k) {
         p.off_z[k] = off;
         off = align_up(off + (size_t)p.M * d->layer[k].cout * p.esz);
     }
-    for (int i = 0; i < 2; ++i) {
-        p.off_g[i] = off;
-        off = align_up(off + (size_t)p.M * p.Cmax * p.esz);
-    }
-    // accumulators + flag: one contiguous region, zeroed by ONE memset at the start of every evaluation
     p.off_acc0 = off;
     p.off_flag = off;
     off += 256;
     for (int k = 0; k < p.L; ++k) {
-        const size_t one = (size_t)ACC_R * d->layer[k].cout * 2 * 2 * sizeof(unsigned long long);
         p.off_accF[k] = off;
-        off += one;
-        p.off_accB[k] = off;
-        off += one;
+        off += (size_t)ACC_R * d->layer[k].cout * 2 * 2 * sizeof(unsigned long long);
     }
     p.acc_bytes = off - p.off_acc0;
+    p.act_total = align_up(off);
+    // scratch region: backward accumulators (zeroed by one memset), g_k = dL/dy_k of every layer, weight-gradient partials
+    off = 0;
+    for (int k = 0; k < p.L; ++k) {
+        p.off_accB[k] = off;
+        off += (size_t)ACC_R * d->layer[k].cout * 2 * 2 * sizeof(unsigned long long);
+    }
+    p.accB_bytes = off;
     off = align_up(off);
+    for (int k = 0; k < p.L; ++k) {
+        p.off_g[k] = off;
+        off = align_up(off + (size_t)p.M * d->layer[k].cout * p.esz);
+    }
     const int sm = sm_count();
     for (int k = 0; k < p.L; ++k) {
         const pnode_conv_layer &l = d->layer[k];
         const ConvGrid f = conv_grid(l.cin, l.cout, p.taps[k], 2, false, p.npg, p.esz);
         const ConvGrid b = conv_grid(l.cout, l.cin, p.taps[k], 6, true, p.npg, p.esz);
         PNODE_REQUIRE(f.smem <= 200 * 1024 && b.smem <= 200 * 1024, "convblock: layer %d weights do not fit in shared memory", k);
-        p.wg_tiles_cit[k] = (l.cin * p.taps[k] + WG_CIT - 1) / WG_CIT;
-        p.wg_ntiles[k] = ((l.cout + WG_CO - 1) / WG_CO) * p.wg_tiles_cit[k];
+        {  // gradient tile (4 TM) x (8 TN): least padding, then largest
+            static const int cand[5][2] = {{4, 4}, {4, 6}, {8, 2}, {4, 3}, {2, 2}};
+            const int rows = l.cout, cols = l.cin * p.taps[k];
+            int64_t best = -1;
+            for (int c = 0; c < 5; ++c) {
+                const int co = 4 * cand[c][0], ci = 8 * cand[c][1];
+                const int64_t area = (int64_t)((rows + co - 1) / co) * ((cols + ci - 1) / ci) * co * ci;
+                if (best < 0 || area < best) best = area, p.wg_tm[k] = cand[c][0], p.wg_tn[k] = cand[c][1];
+            }
+        }
+        const int wg_co = 4 * p.wg_tm[k], wg_cit = 8 * p.wg_tn[k];
+        p.wg_tiles_cit[k] = (l.cin * p.taps[k] + wg_cit - 1) / wg_cit;
+        p.wg_ntiles[k] = ((l.cout + wg_co - 1) / wg_co) * p.wg_tiles_cit[k];
         const int nchunks = (int)((p.npg + 31) / 32);
         static const int wg_occ = env_int("PNODE_WGRAD_OCC", 4);
         int px = sm * wg_occ / p.wg_ntiles[k];
@@ -1061,7 +1120,7 @@ static int cb_plan(const pnode_convblock_desc *d, CbPlan &p) {
     }
     for (int k = 0; k < p.L; ++k) {
         p.off_wpart[k] = off;
-        off = align_up(off + (size_t)p.wg_px[k] * p.wg_ntiles[k] * WG_TILE * p.esz);
+        off = align_up(off + (size_t)p.wg_px[k] * p.wg_ntiles[k] * (16 * p.wg_tm[k] * 2 * p.wg_tn[k]) * p.esz);
     }
     p.total = off;
     return 0;
@@ -1120,12 +1179,8 @@ static int launch_conv_rc(const ConvArgs<T> &a_in, const ConvGrid &g, cudaStream
         ConvArgs<T> a = a_in;
         a.tiles = pg.tiles;
         dim3 grid(pg.gx, pg.gy);
-#define PNODE_PIPE_LAUNCH(RC)                                                                                                    \
-    do {                                                                                                                         \
-        PNODE_CUDA_OK(cudaFuncSetAttribute(convp_kernel<T, KIND, SRC, EPI, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                           (int)pg.smem));                                                                      \
-        convp_kernel<T, KIND, SRC, EPI, RC><<<grid, CP_CONSUMERS + 32, pg.smem, st>>>(a, pg.cg, pg.S);                          \
-    } while (0)
+#define PNODE_PIPE_LAUNCH(RC) \
+    PNODE_CUDA_OK(launch_k(convp_kernel<T, KIND, SRC, EPI, RC>, grid, dim3(CP_CONSUMERS + 32), pg.smem, st, a, pg.cg, pg.S))
         if (pg.rc == 16) {
             if constexpr (sizeof(T) == 4) PNODE_PIPE_LAUNCH(16);
         } else if (pg.rc == 8) {
@@ -1138,13 +1193,7 @@ static int launch_conv_rc(const ConvArgs<T> &a_in, const ConvGrid &g, cudaStream
     }
     const ConvArgs<T> &a = a_in;
     dim3 grid(g.gx, g.gy), block(CB_PGX, g.cg);
-#define PNODE_CONV_LAUNCH(RC)                                                                                                   \
-    do {                                                                                                                        \
-        if (g.smem > 32 * 1024)                                                                                                 \
-            PNODE_CUDA_OK(cudaFuncSetAttribute(conv_kernel<T, KIND, SRC, EPI, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)g.smem));                                                                  \
-        conv_kernel<T, KIND, SRC, EPI, RC><<<grid, block, g.smem, st>>>(a);                                                     \
-    } while (0)
+#define PNODE_CONV_LAUNCH(RC) PNODE_CUDA_OK(launch_k(conv_kernel<T, KIND, SRC, EPI, RC>, grid, block, g.smem, st, a))
     if (g.rc == 16) {
         if constexpr (sizeof(T) == 4) PNODE_CONV_LAUNCH(16);
     } else if (g.rc == 8) {
@@ -1163,34 +1212,39 @@ static int launch_conv(int kind, const ConvArgs<T> &a, const ConvGrid &g, cudaSt
     return launch_conv_rc<T, 2, SRC, EPI>(a, g, st);
 }
 
-template <typename T, int YSRC>
-static int launch_wgrad(int kind, const WgradArgs<T> &a, int px, int ntiles, cudaStream_t st) {
-    const size_t smem = ((size_t)(WG_CO + WG_CIT) * WG_LD + 6 * WG_CO + 2 * WG_CIT) * sizeof(T);
-    dim3 grid(px, ntiles);
-#define PNODE_WG(K)                                                                                                        \
-    do {                                                                                                                   \
-        if (smem > 32 * 1024)                                                                                              \
-            PNODE_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<T, K, YSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)smem));                                                               \
-        conv_wgrad_kernel<T, K, YSRC><<<grid, WG_THREADS, smem, st>>>(a);                                                  \
-    } while (0)
-    if (kind == 0) PNODE_WG(0);
-    else if (kind == 1) PNODE_WG(1);
-    else PNODE_WG(2);
-#undef PNODE_WG
+template <typename T, int KIND, int YSRC, int TM, int TN>
+static int launch_wgrad_tile(const WgradArgs<T> &a, int px, int ntiles, cudaStream_t st) {
+    const size_t smem = ((size_t)(4 * TM + 8 * TN) * WG_LD + 6 * 4 * TM + 2 * 8 * TN) * sizeof(T);
+    PNODE_CUDA_OK(launch_k(conv_wgrad_kernel<T, KIND, YSRC, TM, TN>, dim3(px, ntiles), dim3(WG_THREADS), smem, st, a));
     return 0;
+}
+
+template <typename T, int KIND, int YSRC>
+static int launch_wgrad_kind(int tm, int tn, const WgradArgs<T> &a, int px, int ntiles, cudaStream_t st) {
+    if (tm == 4 && tn == 4) return launch_wgrad_tile<T, KIND, YSRC, 4, 4>(a, px, ntiles, st);
+    if (tm == 4 && tn == 6) return launch_wgrad_tile<T, KIND, YSRC, 4, 6>(a, px, ntiles, st);
+    if (tm == 8 && tn == 2) return launch_wgrad_tile<T, KIND, YSRC, 8, 2>(a, px, ntiles, st);
+    if (tm == 4 && tn == 3) return launch_wgrad_tile<T, KIND, YSRC, 4, 3>(a, px, ntiles, st);
+    return launch_wgrad_tile<T, KIND, YSRC, 2, 2>(a, px, ntiles, st);
+}
+
+template <typename T, int YSRC>
+static int launch_wgrad(int kind, int tm, int tn, const WgradArgs<T> &a, int px, int ntiles, cudaStream_t st) {
+    if (kind == 0) return launch_wgrad_kind<T, 0, YSRC>(tm, tn, a, px, ntiles, st);
+    if (kind == 1) return launch_wgrad_kind<T, 1, YSRC>(tm, tn, a, px, ntiles, st);
+    return launch_wgrad_kind<T, 2, YSRC>(tm, tn, a, px, ntiles, st);
 }
 
 template <typename T>
 struct Bufs {
-    unsigned char *w;
+    unsigned char *a, *w;  // activation region, scratch region
     const CbPlan &p;
-    Bufs(void *work, const CbPlan &pl) : w(static_cast<unsigned char *>(work)), p(pl) {}
-    T *z(int k) const { return reinterpret_cast<T *>(w + p.off_z[k]); }
-    T *g(int i) const { return reinterpret_cast<T *>(w + p.off_g[i]); }
-    unsigned long long *accF(int k) const { return reinterpret_cast<unsigned long long *>(w + p.off_accF[k]); }
-    unsigned long long *accB(int k) const { return reinterpret_cast<unsigned long long *>(w + p.off_accB[k]); }
-    unsigned *flag() const { return reinterpret_cast<unsigned *>(w + p.off_flag); }
+    Bufs(void *act, void *work, const CbPlan &pl) : a(static_cast<unsigned char *>(act)), w(static_cast<unsigned char *>(work)), p(pl) {}
+    T *z(int k) const { return reinterpret_cast<T *>(a + p.off_z[k]); }
+    unsigned long long *accF(int k) const { return reinterpret_cast<unsigned long long *>(a + p.off_accF[k]); }
+    unsigned *flag() const { return reinterpret_cast<unsigned *>(a + p.off_flag); }
+    T *g(int k) const { return reinterpret_cast<T *>(w + p.off_g[k]); }
+    unsigned long long *accB(int k) const { return w ? reinterpret_cast<unsigned long long *>(w + p.off_accB[k]) : nullptr; }
     T *wpart(int k) const { return reinterpret_cast<T *>(w + p.off_wpart[k]); }
 };
 
@@ -1220,7 +1274,7 @@ static void fill_common(ConvArgs<T> &a, const pnode_convblock_desc *d, const CbP
 // (layer L's update belongs to whoever consumes z_L next: act_out_kernel or top_stats_kernel)
 template <typename T>
 static int forward_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b, const T *x, cudaStream_t st) {
-    PNODE_CUDA_OK(cudaMemsetAsync(b.w + p.off_acc0, 0, p.acc_bytes, st));
+    PNODE_CUDA_OK(cudaMemsetAsync(b.a + p.off_acc0, 0, p.acc_bytes, st));
     for (int k = 0; k < p.L; ++k) {
         const pnode_conv_layer &l = d->layer[k];
         ConvArgs<T> a = {};
@@ -1247,16 +1301,17 @@ static int act_out(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T>
     int64_t blocks = (nvec + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    act_out_kernel<T><<<(int)blocks, 256, 2 * C * sizeof(T), st>>>(b.z(p.L - 1), bn_ref(d, b, p.L - 1), (double)p.M, b.flag(), 1,
-                                                                    d->H * d->W, nvec, out, base, (T)base_coef, (T)kcoef, kout);
-    PNODE_CUDA_OK(cudaGetLastError());
+    PNODE_CUDA_OK(launch_k(act_out_kernel<T>, dim3((unsigned)blocks), dim3(256), 2 * C * sizeof(T), st, (const T *)b.z(p.L - 1),
+                           bn_ref(d, b, p.L - 1), (double)p.M, (const unsigned *)b.flag(), 1, d->H * d->W, nvec, out, base,
+                           (T)base_coef, (T)kcoef, kout));
     return 0;
 }
 
 template <typename T>
 static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b, const T *x, const T *w, T *vu, T *gout,
-                     double coef, int accumulate, cudaStream_t st) {
+                     double coef, int accumulate, int replay_running, cudaStream_t st) {
     const int L = p.L;
+    PNODE_CUDA_OK(cudaMemsetAsync(b.w + p.off_accB[0], 0, p.accB_bytes, st));
     {  // BatchNorm-backward sums of the top layer
         const pnode_conv_layer &l = d->layer[L - 1];
         ConvArgs<T> a = {};
@@ -1269,11 +1324,11 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
         dim3 grid(g.gx, g.gy), block(CB_PGX, g.cg);
         const size_t smem = (size_t)4 * g.cg * g.rc * sizeof(T);
         if (g.rc == 16) {
-            if constexpr (sizeof(T) == 4) top_stats_kernel<T, 16><<<grid, block, smem, st>>>(a);
+            if constexpr (sizeof(T) == 4) PNODE_CUDA_OK(launch_k(top_stats_kernel<T, 16>, grid, block, smem, st, a));
         } else if (g.rc == 8) {
-            top_stats_kernel<T, 8><<<grid, block, smem, st>>>(a);
+            PNODE_CUDA_OK(launch_k(top_stats_kernel<T, 8>, grid, block, smem, st, a));
         } else {
-            top_stats_kernel<T, 4><<<grid, block, smem, st>>>(a);
+            PNODE_CUDA_OK(launch_k(top_stats_kernel<T, 4>, grid, block, smem, st, a));
         }
     }
     const T *gk = w;
@@ -1291,8 +1346,8 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             wa.npg = p.npg;
             wa.nchunks = (int)((p.npg + 31) / 32);
             wa.M = (double)p.M;
-            int rc = k == 0 ? launch_wgrad<T, SRC_RAW>(p.kind[k], wa, p.wg_px[k], p.wg_ntiles[k], st)
-                            : launch_wgrad<T, SRC_ACT>(p.kind[k], wa, p.wg_px[k], p.wg_ntiles[k], st);
+            int rc = k == 0 ? launch_wgrad<T, SRC_RAW>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], st)
+                            : launch_wgrad<T, SRC_ACT>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], st);
             if (rc) return rc;
         }
         if (k == 0 && vu == nullptr) break;
@@ -1307,8 +1362,9 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             a.out = vu;
             rc = launch_conv<T, SRC_DZ, EPI_NONE>(p.kind[k], a, g, st);
         } else {
-            a.out = b.g(k & 1);
+            a.out = b.g(k - 1);
             a.zprev = b.z(k - 1), a.bout = bn_ref(d, b, k - 1);
+            a.upd_out = replay_running;  // saved activations: the module's forward re-evaluation still advances the buffers
             a.acc_out = b.accB(k - 1);
             rc = launch_conv<T, SRC_DZ, EPI_DGRAD>(p.kind[k], a, g, st);
             gk = a.out;
@@ -1324,14 +1380,15 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             ga.L[k].PX = p.wg_px[k], ga.L[k].ntiles = p.wg_ntiles[k], ga.L[k].tiles_cit = p.wg_tiles_cit[k];
             ga.L[k].Cin = d->layer[k].cin, ga.L[k].Cout = d->layer[k].cout, ga.L[k].taps = p.taps[k];
             ga.L[k].base = p.pbase[k];
+            ga.L[k].wg_co = 4 * p.wg_tm[k], ga.L[k].wg_cit = 8 * p.wg_tn[k];
             pxmax = p.wg_px[k] > pxmax ? p.wg_px[k] : pxmax;
         }
         const int G = pxmax > 8 ? 32 : 4;
         int64_t blocks = (ga.np * G + 255) / 256;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
-        if (G == 32) grads_finalize_kernel<T, 32><<<(int)blocks, 256, 0, st>>>(ga);
-        else grads_finalize_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(ga);
+        if (G == 32) PNODE_CUDA_OK(launch_k(grads_finalize_kernel<T, 32>, dim3((unsigned)blocks), dim3(256), 0, st, ga));
+        else PNODE_CUDA_OK(launch_k(grads_finalize_kernel<T, 4>, dim3((unsigned)blocks), dim3(256), 0, st, ga));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1344,6 +1401,12 @@ static bool cb_aligned(const void *p) { return p == nullptr || (reinterpret_cast
 using namespace pnode;
 
 extern "C" {
+
+int64_t pnode_convblock_act_bytes(const pnode_convblock_desc *desc) {
+    CbPlan p;
+    if (cb_plan(desc, p) != 0) return -1;
+    return (int64_t)p.act_total;
+}
 
 int64_t pnode_convblock_work_bytes(const pnode_convblock_desc *desc) {
     CbPlan p;
@@ -1358,23 +1421,23 @@ int64_t pnode_convblock_param_count(const pnode_convblock_desc *desc) {
 }
 
 int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, void *d_out, const void *d_base,
-                            double base_coef, double k_coef, void *d_k, void *d_work, void *stream) {
+                            double base_coef, double k_coef, void *d_k, void *d_act, void *stream) {
     CbPlan p;
     int rc = cb_plan(desc, p);
     if (rc) return rc;
-    PNODE_REQUIRE(d_x && d_work && (d_out || d_k), "pnode_convblock_forward: null argument");
-    PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_out) && cb_aligned(d_base) && cb_aligned(d_k) && cb_aligned(d_work),
+    PNODE_REQUIRE(d_x && d_act && (d_out || d_k), "pnode_convblock_forward: null argument");
+    PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_out) && cb_aligned(d_base) && cb_aligned(d_k) && cb_aligned(d_act),
                   "pnode_convblock_forward: tensors must be 16-byte aligned");
     PNODE_REQUIRE(desc->layer[p.L - 1].cout == desc->layer[0].cin, "pnode_convblock_forward: an ODE right-hand side maps C -> C");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (desc->dtype == PNODE_F32) {
-        Bufs<float> b(d_work, p);
+        Bufs<float> b(d_act, nullptr, p);
         rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), st);
         if (rc) return rc;
         return act_out<float>(desc, p, b, static_cast<float *>(d_out), static_cast<const float *>(d_base), base_coef, k_coef,
                               static_cast<float *>(d_k), st);
     }
-    Bufs<double> b(d_work, p);
+    Bufs<double> b(d_act, nullptr, p);
     rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), st);
     if (rc) return rc;
     return act_out<double>(desc, p, b, static_cast<double *>(d_out), static_cast<const double *>(d_base), base_coef, k_coef,
@@ -1382,26 +1445,30 @@ int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, v
 }
 
 int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads,
-                        double coef, int accumulate, void *d_work, void *stream) {
+                        double coef, int accumulate, void *d_act, int act_valid, void *d_work, void *stream) {
     CbPlan p;
     int rc = cb_plan(desc, p);
     if (rc) return rc;
-    PNODE_REQUIRE(d_x && d_w && d_work && (d_vu || d_grads), "pnode_convblock_vjp: null argument");
-    PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_w) && cb_aligned(d_vu) && cb_aligned(d_work),
+    PNODE_REQUIRE(d_x && d_w && d_act && d_work && (d_vu || d_grads), "pnode_convblock_vjp: null argument");
+    PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_w) && cb_aligned(d_vu) && cb_aligned(d_act) && cb_aligned(d_work),
                   "pnode_convblock_vjp: tensors must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (desc->dtype == PNODE_F32) {
-        Bufs<float> b(d_work, p);
-        rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), st);
-        if (rc) return rc;
+        Bufs<float> b(d_act, d_work, p);
+        if (!act_valid) {
+            rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), st);
+            if (rc) return rc;
+        }
         return vjp_chain<float>(desc, p, b, static_cast<const float *>(d_x), static_cast<const float *>(d_w),
-                                static_cast<float *>(d_vu), static_cast<float *>(d_grads), coef, accumulate, st);
+                                static_cast<float *>(d_vu), static_cast<float *>(d_grads), coef, accumulate, act_valid != 0, st);
     }
-    Bufs<double> b(d_work, p);
-    rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), st);
-    if (rc) return rc;
+    Bufs<double> b(d_act, d_work, p);
+    if (!act_valid) {
+        rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), st);
+        if (rc) return rc;
+    }
     return vjp_chain<double>(desc, p, b, static_cast<const double *>(d_x), static_cast<const double *>(d_w),
-                             static_cast<double *>(d_vu), static_cast<double *>(d_grads), coef, accumulate, st);
+                             static_cast<double *>(d_vu), static_cast<double *>(d_grads), coef, accumulate, act_valid != 0, st);
 }
 
 }  // extern "C"

@@ -297,6 +297,9 @@ class GenericTS:
         self.traj = []
         self._stride = 1
         self.recomputed_steps = 0
+        for cb in (cb_ex, cb_im):
+            if cb is not None and hasattr(cb, "begin"):
+                cb.begin(True, keep=save_trajectory)
         u = u0.reshape(-1).clone()
         n_local = u.numel()
         n_global = n_local if self.comm is None else self.comm.global_count(n_local)
@@ -461,6 +464,9 @@ class GenericTS:
 
     # -- adjoint ----------------------------------------------------------------------------------------------------
     def adjoint_steps(self, cb_ex, cb_im, imp, nsteps, lam, mu, np_im):
+        for cb in (cb_ex, cb_im):
+            if cb is not None and hasattr(cb, "begin"):
+                cb.begin(False)
         for _ in range(nsteps):
             if not self.traj:
                 raise Error(-30, "adjoint requested more steps than the trajectory holds")

@@ -55,7 +55,12 @@ def test_rhs_and_vjp_match_torch(shape, dtype, tol):
         mine = copy.deepcopy(func)
         cb = _callbacks(mine, shape)
         out = cb.f(0.0, x.reshape(-1)).view(shape)
-        vu, gp = cb.vjp(0.0, x.reshape(-1), w.reshape(-1))
+        vu, gp = cb.vjp(0.0, x.reshape(-1), w.reshape(-1))  # reuses the activation set the forward evaluation kept
+        assert cb.reused_activations == 1
+        cb.begin(True)  # forget it: the same VJP now re-evaluates the forward inside the call, bit-identically
+        vu2, gp2 = cb.vjp(0.0, x.reshape(-1), w.reshape(-1))
+        assert cb.reused_activations == 1
+        assert torch.equal(vu, vu2) and all(torch.equal(a, b) for a, b in zip(gp, gp2))
         torch.cuda.synchronize()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -68,10 +73,10 @@ def test_rhs_and_vjp_match_torch(shape, dtype, tol):
         if n.endswith("conv1.bias") or ".bias" in n and "conv" in n:
             continue  # a conv bias feeding a BatchNorm has an exactly-zero gradient: rounding noise on both sides
         assert rel_err(a.view_as(b), b) < tol * 50, (n, rel_err(a.view_as(b), b))
-    # side effects: f advanced the statistics once, vjp (forward re-evaluation) once more; the reference module once
-    assert int(mine.bn3.num_batches_tracked) == 2 and int(f_r.bn3.num_batches_tracked) == 1
+    # side effects: f advanced the statistics once, each vjp (forward re-evaluation, replayed or real) once more
+    assert int(mine.bn3.num_batches_tracked) == 3 and int(f_r.bn3.num_batches_tracked) == 1
     again = copy.deepcopy(func)
-    again(0.0, x), again(0.0, x)
+    again(0.0, x), again(0.0, x), again(0.0, x)
     for k in range(1, 6):
         a, b = getattr(mine, "bn%d" % k), getattr(again, "bn%d" % k)
         assert rel_err(a.running_mean, b.running_mean) < tol * 10 and rel_err(a.running_var, b.running_var) < tol * 10
