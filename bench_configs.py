@@ -86,13 +86,17 @@ def run_config(name, build, args, peaks):
     accepted = loop.steps
     attempts = len(loop.attempts)
     units = spec["batch"] * accepted
+    cb = getattr(ode, "_cb_im", None)
+    if getattr(cb, "native", None) is not None:
+        out["rhs_evaluator"] = "csrc/conv_block.cu" if cb.native else "library convolutions + csrc/bn_relu.cu"
     out.update({"path": ode.path, "ms_per_pass": ms, "accepted_steps": accepted, "attempts": attempts,
                 "traj_steps_per_s": units / (ms * 1e-3)})
     flops = spec["flops_per_unit"] * units + spec.get("flops_per_rejected", 0) * spec["batch"] * (attempts - accepted)
     tfl = flops / (ms * 1e-3) / 1e12
     out["algorithmic_tflops"] = tfl
+    hbm = spec["bytes_per_unit"] * units / (ms * 1e-3) / 1e9
     out["roofline"] = {"pipe": spec["pipe"], "peak_tflops": peaks[spec["pipe"]], "frac": tfl / peaks[spec["pipe"]],
-                       "hbm_gbs": spec["bytes_per_unit"] * units / (ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
+                       "hbm_gbs": hbm, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": hbm / peaks["hbm_gbs"]}
     if spec.get("also_generic") and ode.path != "generic":
         Options.insert_args(["-pnode_fused", "0"])
         funcs_g = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
@@ -162,21 +166,26 @@ def _cnf(B, dtype):
     return build
 
 
-def cfg4():
-    from _workloads import OdeConvBlock
+def cfg4(C=32, HW=32):
+    def build():
+        from _workloads import OdeConvBlock
 
-    C, HW, B = 32, 32, 256
-    g = torch.Generator().manual_seed(3)
-    u0 = torch.randn(B, C, HW, HW, generator=g)
-    target = torch.randn(1, B, C, HW, HW, generator=g)
-    t = torch.tensor([1.0], dtype=torch.float64)
-    bs = 32
-    return dict(desc="cfg4 CIFAR SqueezeNext ODE block 1: u [256,32,32,32] fp32, RK4, t=[1.0], Nt=1 (h=1), conv+BN(train)",
-                dtype="f32", argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"], funcs=[OdeConvBlock(C)],
-                u0=u0, t=t, target=target, kw=dict(method="rk4"), step=1.0, batch=B, flops_per_unit=75.5e6,
-                bytes_per_unit=96 * C * HW * HW * 4, pipe="bf16_tensor", each_call_setup=True,
-                cpu_sample=lambda: dict(funcs=[OdeConvBlock(C)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
-                                        kw=dict(method="rk4"), batch=bs, desc="%d of %d samples" % (bs, B)))
+        B = 256
+        g = torch.Generator().manual_seed(3)
+        u0 = torch.randn(B, C, HW, HW, generator=g)
+        target = torch.randn(1, B, C, HW, HW, generator=g)
+        t = torch.tensor([1.0], dtype=torch.float64)
+        bs = 32
+        # 75.5 Mflop and 96 C HW w bytes per trajectory-step (every layer reads its input and writes its output
+        # once per RHS evaluation, adjoint = 3 evaluations' worth, stage checkpoints): block 1-2 are HBM-bound on CUDA cores
+        return dict(desc="cfg4 CIFAR SqueezeNext ODE block: u [256,%d,%d,%d] fp32, RK4, t=[1.0], Nt=1 (h=1), conv+BN(train)"
+                         % (C, HW, HW), dtype="f32", argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"],
+                    funcs=[OdeConvBlock(C)], u0=u0, t=t, target=target, kw=dict(method="rk4"), step=1.0, batch=B,
+                    flops_per_unit=75.5e6, bytes_per_unit=96 * C * HW * HW * 4, pipe="fp32_fma", each_call_setup=True,
+                    cpu_sample=lambda: dict(funcs=[OdeConvBlock(C)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
+                                            kw=dict(method="rk4"), batch=bs, desc="%d of %d samples" % (bs, B)))
+
+    return build
 
 
 def cfg5(N=1024, B=256, dtype="f64"):
@@ -225,7 +234,8 @@ def main():
         _lib.check(lib.pnode_peak_fma(code, 20000, C.byref(fl), C.byref(ms)))
         pk[key] = fl.value / (ms.value * 1e-3) / 1e12
     table = {"1": ("cfg1", cfg1), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
-             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4), "5": ("cfg5", cfg5()),
+             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
+             "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)), "5": ("cfg5", cfg5()),
              "5S": ("cfg5-f32", cfg5(dtype="f32"))}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "a") as fo:

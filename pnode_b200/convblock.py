@@ -86,6 +86,8 @@ def recognise_convblock(func, u_meta):
 
 
 class ConvBlockCallbacks(Callbacks):
+    NATIVE_MIN_PIXELS = 8192
+
     def __init__(self, func, tensor_size, _probe=False):
         super().__init__(func, tensor_size)
         self.lib = _lib.load()
@@ -101,11 +103,16 @@ class ConvBlockCallbacks(Callbacks):
         self._cwork = None
         from .options import Options
 
-        if len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4 and \
-                Options().getString("pnode_convblock_native", "1") not in ("0", "false", "no"):
+        mode = Options().getString("pnode_convblock_native", "auto")  # auto | 1 (whenever the shape is supported) | 0
+        if len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4 and mode not in ("0", "false", "no"):
             desc = self._make_desc()
             nact = int(self.lib.pnode_convblock_act_bytes(C.byref(desc)))
-            if nact >= 0 and int(self.lib.pnode_convblock_param_count(C.byref(desc))) == self.nparams:
+            # The native kernels give one thread 4 pixels x 16 output channels: they need pixels to fill the machine.  The
+            # last CIFAR block ([256,256,4,4]: 4096 pixels, 256 channels) is a small GEMM per layer -- measured 2.3x slower
+            # than the library GEMM convolutions there (tools/time_convblock.py), 1.7x-4.2x faster on the other three.
+            pixels = int(tensor_size[0]) * int(tensor_size[2]) * int(tensor_size[3])
+            enough = pixels >= self.NATIVE_MIN_PIXELS or mode in ("1", "true", "yes", "force")
+            if nact >= 0 and enough and int(self.lib.pnode_convblock_param_count(C.byref(desc))) == self.nparams:
                 self.native = True
                 self._desc = desc
                 self._act_bytes = nact

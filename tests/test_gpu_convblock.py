@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 
 def _callbacks(func, shape):
     from pnode_b200.convblock import ConvBlockCallbacks
+    from pnode_b200.options import Options
 
+    Options.insert_args(["-pnode_convblock_native", "1"])  # also below the pixel count where "auto" prefers library GEMMs
     cb = ConvBlockCallbacks(func, torch.Size(shape))
     assert cb.native, "the conv-block kernels must accept this shape"
     return cb

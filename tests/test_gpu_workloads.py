@@ -77,7 +77,7 @@ def test_config4_cifar_ode_block_rk4(dtype, tol):
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        o, p = _pair(["-ts_adapt_type", "none"], [func], dict(method="rk4"), u0, t, gout, 0.5)
+        o, p = _pair(["-ts_adapt_type", "none", "-pnode_convblock_native", "1"], [func], dict(method="rk4"), u0, t, gout, 0.5)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     assert p[0].shape == (1, B, C, HW, HW)
@@ -150,6 +150,36 @@ def test_bn_relu_kernels_match_torch(dtype, shape):
     assert rel_err(rm2, rm) < tol * 10 and rel_err(rv2, rv) < tol * 10
 
 
+def test_config4_evaluator_choice_and_library_path():
+    """auto: the hand-written conv kernels when there are pixels enough to fill the GPU, else library GEMM convolutions + the
+    BatchNorm+ReLU kernels of csrc/bn_relu.cu; both evaluators give the same trajectory and gradients."""
+    from pnode import petsc_adjoint
+    from pnode_b200.convblock import ConvBlockCallbacks
+
+    big = ConvBlockCallbacks(OdeConvBlock(32).cuda(), torch.Size((16, 32, 32, 32)))
+    small = ConvBlockCallbacks(OdeConvBlock(256).cuda(), torch.Size((256, 256, 4, 4)))
+    assert big.native and not small.native
+    C, HW, B = 16, 8, 8
+    func = OdeConvBlock(C, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(B, C, HW, HW, generator=g, dtype=torch.float64)
+    gout = torch.randn(1, B, C, HW, HW, generator=g, dtype=torch.float64)
+    res = []
+    for mode in ("1", "0"):
+        Options.clear_all()
+        Options.insert_args(["-ts_adapt_type", "none", "-pnode_convblock_native", mode])
+        f = copy.deepcopy(func).cuda()
+        ode = petsc_adjoint.ODEPetsc()
+        ode.setupTS(u0.cuda(), f, step_size=0.5, method="rk4", enable_adjoint=True)
+        y0 = u0.cuda().clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, torch.tensor([1.0], dtype=torch.float64).cuda())
+        (out * gout.cuda()).sum().backward()
+        res.append((out.detach(), y0.grad, [p.grad for p in f.parameters()], ode, f))
+    assert res[0][3]._cb_im.native and not res[1][3]._cb_im.native and res[1][3].path == "generic+convblock-rhs"
+    assert res[0][3]._cb_im.reused_activations == 8  # 2 steps x 4 stages: no forward re-evaluation in the adjoint
+    _compare(res[0], res[1], 1e-9, per_param=False)
+
+
 def test_config4_fused_rhs_equals_stock_module_path():
     """The conv-block evaluator vs the same module driven through torch autograd (-pnode_fused 0), both on the GPU."""
     from pnode import petsc_adjoint
@@ -161,7 +191,7 @@ def test_config4_fused_rhs_equals_stock_module_path():
     gout = torch.randn(2, B, C, HW, HW, generator=g, dtype=torch.float64)
     t = torch.tensor([0.0, 1.0], dtype=torch.float64)
     res = []
-    for argv in (["-ts_adapt_type", "none"], ["-ts_adapt_type", "none", "-pnode_fused", "0"]):
+    for argv in (["-ts_adapt_type", "none", "-pnode_convblock_native", "1"], ["-ts_adapt_type", "none", "-pnode_fused", "0"]):
         Options.clear_all()
         Options.insert_args(argv)
         f = copy.deepcopy(func).cuda()

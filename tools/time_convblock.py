@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--shapes", default="32x32,64x16,128x8,256x4")
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--native", type=int, default=1, help="0: library convolutions + csrc/bn_relu.cu (the non-native evaluator)")
     args = ap.parse_args()
     dt = torch.float32 if args.dtype == "f32" else torch.float64
     w = 4 if args.dtype == "f32" else 8
@@ -33,18 +34,29 @@ def main():
     for sh in args.shapes.split(","):
         Cc, H = (int(v) for v in sh.split("x"))
         func = OdeConvBlock(Cc, dtype=dt).cuda()
+        from pnode_b200.options import Options
+        Options.insert_args(["-pnode_convblock_native", str(args.native)])
         cb = ConvBlockCallbacks(func, torch.Size((args.batch, Cc, H, H)))
-        assert cb.native
+        assert cb.native == bool(args.native)
         x = torch.randn(args.batch * Cc * H * H, dtype=dt, device="cuda")
         g = torch.randn_like(x)
         mu = torch.zeros(cb.nparams, dtype=dt, device="cuda")
+        if not args.native:
+            from pnode_b200.device import DeviceOps
+            ops = DeviceOps(x.device, dt)
+
+            def vjp_acc():
+                vu, gp = cb.vjp(0.0, x, g)
+                ops.multi_axpy(mu, gp, cb.sizes, 1.0)
+        else:
+            vjp_acc = lambda: cb.vjp_accumulate(0.0, x, g, mu, 1.0)
         if args.once:
             cb.f(0.0, x)
-            cb.vjp_accumulate(0.0, x, g, mu, 1.0)
+            vjp_acc()
             torch.cuda.synchronize()
             continue
         res = {"shape": [args.batch, Cc, H, H], "dtype": args.dtype}
-        for name, call, mult in (("f", lambda: cb.f(0.0, x), 1.0), ("vjp", lambda: cb.vjp_accumulate(0.0, x, g, mu, 1.0), 3.0)):
+        for name, call, mult in (("f", lambda: cb.f(0.0, x), 1.0), ("vjp", vjp_acc, 3.0)):
             for _ in range(3):
                 call()
             torch.cuda.synchronize()
