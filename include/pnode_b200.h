@@ -243,6 +243,18 @@ typedef struct pnode_convblock_desc {
     int32_t nlayers, dtype;
     int32_t N, H, W, reserved;
     pnode_conv_layer layer[PNODE_CONV_MAX_LAYERS];
+    /* Batch-sharded runs (one process per GPU; all zero / NULL otherwise).  BatchNorm statistics must be those of the GLOBAL
+     * batch: the last CTA of every statistics-producing kernel exchanges this rank's exact totals with the other ranks through
+     * the symmetric-memory inbox of pnode_peer_buffer_bytes() (same buffer, flags and epoch counter as *_adjoint_dp below:
+     * peer stores over NVLink + system-scope release/acquire flags, no NCCL call, no extra launch) and the integer sums make
+     * every rank's statistics bit-identical to a single-GPU run of the whole batch.  A forward call consumes nlayers
+     * consecutive epochs starting at `epoch`; a vjp call nlayers (+ nlayers more when it re-evaluates the forward).
+     * The BatchNorm affine gradients written by pnode_convblock_vjp are global: rank 0 alone contributes them to d_grads, so
+     * that the caller's all-reduce(sum) of mu over ranks counts them once. */
+    const uint64_t *d_peer_bufs;   /* DEVICE array [world] of peer-mapped inbox base addresses */
+    int32_t rank, world;
+    uint64_t epoch;                /* first collective number of this call (>= 1, strictly increasing, equal on all ranks) */
+    int64_t global_pixels;         /* N*H*W summed over ranks */
 } pnode_convblock_desc;
 
 int64_t pnode_convblock_act_bytes(const pnode_convblock_desc *desc);   /* -1: unsupported shape (pnode_last_error) */

@@ -40,7 +40,8 @@ class ConvLayer(C.Structure):
 
 class ConvBlockDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("nlayers", "dtype", "N", "H", "W", "reserved")] + \
-               [("layer", ConvLayer * CONV_MAX_LAYERS)]
+               [("layer", ConvLayer * CONV_MAX_LAYERS), ("d_peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
+                ("epoch", C.c_uint64), ("global_pixels", C.c_int64)]
 
 
 class Step(C.Structure):

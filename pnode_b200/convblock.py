@@ -21,6 +21,7 @@ import torch.nn as nn
 from . import _lib
 from .device import _stream, dtype_code
 from .engine import Callbacks
+from .errors import Error
 
 
 def _layers(func):
@@ -125,6 +126,7 @@ class ConvBlockCallbacks(Callbacks):
                 self._save_budget = int(float(Options().getString("pnode_convblock_save_mb", "8192")) * (1 << 20))
                 self.reused_activations = 0
                 self._keep = True
+                self._comm = None
 
     def _make_desc(self):
         d = _lib.ConvBlockDesc()
@@ -153,12 +155,25 @@ class ConvBlockCallbacks(Callbacks):
     def _param_versions(self):
         return tuple(p._version for p in self.params)
 
-    def begin(self, forward, keep=True):
+    def begin(self, forward, keep=True, comm=None):
         """Called by the time stepper at the start of a forward solve (forward=True; keep = an adjoint sweep will follow) and
-        of an adjoint sweep."""
+        of an adjoint sweep.  comm: the run's BatchComm (batch sharded over GPUs) or None."""
         if not self.native:
+            if comm is not None and comm.world > 1:
+                raise Error(-40, "batch-sharded conv ODE blocks need the native evaluator (global BatchNorm statistics are "
+                                 "exchanged inside csrc/conv_block.cu); this shape runs on library convolutions")
             return
         self._refresh_pointers(self._desc)
+        self._comm = comm if (comm is not None and comm.world > 1) else None
+        d = self._desc
+        if self._comm is not None:
+            if not self._comm.enable_peer_reduce():
+                raise Error(-41, "batch-sharded conv ODE blocks need NVLink peer (symmetric) memory for the BatchNorm statistics")
+            d.d_peer_bufs = self._comm.peer["ptrs_dev"]
+            d.rank, d.world = self._comm.rank, self._comm.world
+            d.global_pixels = self._comm.global_count(int(d.N) * int(d.H) * int(d.W))
+        else:
+            d.d_peer_bufs, d.rank, d.world, d.global_pixels, d.epoch = None, 0, 1, 0, 0
         if forward:
             self._saved.clear()
             self._saved_bytes = 0
@@ -177,6 +192,8 @@ class ConvBlockCallbacks(Callbacks):
         if out is None and k is None:
             out = torch.empty_like(u)
         act = self._act_for(u) if keep else self._act0
+        if self._comm is not None:
+            self._desc.epoch = self._comm.reserve_epochs(len(self.layers))
         _lib.check(self.lib.pnode_convblock_forward(C.byref(self._desc), u.data_ptr(), None if out is None else out.data_ptr(),
                                                     None if base is None else base.data_ptr(), float(base_coef), float(k_coef),
                                                     None if k is None else k.data_ptr(), act.data_ptr(), _stream()))
@@ -190,6 +207,8 @@ class ConvBlockCallbacks(Callbacks):
         ent = self._saved.get(u.data_ptr())
         valid = ent is not None and ent[1] == u._version and ent[2] == self._param_versions() and ent[0].numel() == u.numel()
         act = ent[3] if valid else self._act0
+        if self._comm is not None:
+            self._desc.epoch = self._comm.reserve_epochs(len(self.layers) * (1 if valid else 2))
         _lib.check(self.lib.pnode_convblock_vjp(C.byref(self._desc), u.data_ptr(), w.data_ptr(),
                                                 None if vu is None else vu.data_ptr(),
                                                 None if grads is None else grads.data_ptr(), float(coef), int(accumulate),

@@ -332,6 +332,10 @@ struct ConvArgs {
     BnRef bin, bout;     // BatchNorm on the input side (forward: layer k-1; dgrad: layer k) / output side (dgrad: layer k-1)
     unsigned long long *acc_out;  // accumulators this kernel adds into (forward: accF of layer k; dgrad: accB of layer k-1)
     unsigned *flag;
+    unsigned *ticket;                      // data-parallel runs: CTA completion counter of the kernel (self-resetting)
+    const unsigned long long *peer_bufs;   // DEVICE array [world]: peer-mapped base of every rank's symmetric inbox, or NULL
+    unsigned long long epoch;              // collective number of this kernel's statistics exchange (consecutive, all ranks)
+    int rank, world;
     int upd_in, upd_out;  // CTA (0,0) performs the running-statistics update of bin / bout
     int CA, CB;           // reduction channels, output channels
     int H, W, HW;
@@ -362,6 +366,75 @@ __device__ __forceinline__ T warp_multi_sum(T (&v)[NV], int lane, int &idx) {
     return t;
 }
 
+template <bool NAMED>
+__device__ __forceinline__ void cta_sync() {
+    if constexpr (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+
+// Batch-sharded runs (one process per GPU): the batch statistics must be those of the GLOBAL batch.  Compute and collective in
+// one kernel: the last CTA of this rank (ticket) folds the accumulator replicas into exact 128-bit totals, stores them into
+// every rank's symmetric-memory inbox over NVLink (plain st.global on peer-mapped addresses), raises a system-scope release
+// flag, waits for the other ranks' flags, sums the inbox -- integer sums: every rank gets the same bits whatever the order --
+// and writes the global totals back as THE accumulator, so every consumer (next kernel, saved activation sets, the adjoint)
+// is unchanged.  Same inbox / flag / epoch protocol as common.cuh:peer_allreduce_and_store (two sets alternate by epoch).
+template <typename T, bool NAMED>
+__device__ __forceinline__ void stats_exchange(const ConvArgs<T> &a, int tid, int nthr) {
+    if (a.world <= 1 || a.peer_bufs == nullptr) return;
+    __shared__ int is_last;
+    __threadfence();
+    cta_sync<NAMED>();
+    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    cta_sync<NAMED>();
+    if (!is_last) return;
+    __threadfence();
+    const int nval = 2 * a.CB, set = (int)(a.epoch & 1ull);
+    for (int v = tid; v < nval; v += nthr) {
+        unsigned long long lo = 0;
+        long long hi = 0;
+        for (int r = 0; r < ACC_R; ++r) {
+            const unsigned long long *p = a.acc_out + ((int64_t)r * nval + v) * 2;
+            const unsigned long long l = __ldcg(p);
+            lo += l;
+            hi += (long long)__ldcg(p + 1) + (lo < l ? 1 : 0);
+        }
+        for (int r = 0; r < a.world; ++r) {
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(peer_slot(a.peer_bufs[r], set, a.world, a.rank));
+            dst[2 * v] = lo;
+            dst[2 * v + 1] = (unsigned long long)hi;
+        }
+    }
+    __threadfence_system();
+    cta_sync<NAMED>();
+    if (tid < a.world) {
+        unsigned long long *f = peer_flag(a.peer_bufs[tid], set, a.world, a.rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
+        unsigned long long *w = peer_flag(a.peer_bufs[a.rank], set, a.world, tid), v = 0;
+        for (long long spin = 0; spin < (1ll << 27); ++spin) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (v >= a.epoch) break;
+            __nanosleep(64);
+        }
+        if (v < a.epoch) atomicOr(a.flag, 2u);  // a peer never arrived: poison the statistics instead of hanging
+    }
+    cta_sync<NAMED>();
+    const unsigned long long mine = a.peer_bufs[a.rank];
+    for (int v = tid; v < nval; v += nthr) {
+        unsigned long long lo = 0;
+        long long hi = 0;
+        for (int r = 0; r < a.world; ++r) {
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(peer_slot(mine, set, a.world, r));
+            const unsigned long long l = __ldcg(src + 2 * v);
+            lo += l;
+            hi += (long long)__ldcg(src + 2 * v + 1) + (lo < l ? 1 : 0);
+        }
+        a.acc_out[2 * v] = lo;
+        a.acc_out[2 * v + 1] = (unsigned long long)hi;
+        for (int r = 1; r < ACC_R; ++r) a.acc_out[((int64_t)r * nval + v) * 2] = 0ull, a.acc_out[((int64_t)r * nval + v) * 2 + 1] = 0ull;
+    }
+    if (tid == 0) *a.ticket = 0u;
+}
+
 // CTA-level sums of the per-thread statistics, added into the exact accumulators (no tail, no ordering)
 template <typename T, int RC>
 __device__ __forceinline__ void stats_epilogue(const ConvArgs<T> &a, T (&s)[RC], T (&q)[RC], int cb0) {
@@ -382,6 +455,7 @@ __device__ __forceinline__ void stats_epilogue(const ConvArgs<T> &a, T (&s)[RC],
         acc128_add(a.acc_out + (((int64_t)rep * a.CB + ch) * 2 + which) * 2,
                    red[0][threadIdx.y][threadIdx.x] + red[1][threadIdx.y][threadIdx.x], a.flag);
     }
+    stats_exchange<T, false>(a, threadIdx.y * CB_PGX + threadIdx.x, CB_PGX * blockDim.y);
 }
 
 // sum / sum-of-squares (forward) or the two BatchNorm-backward sums (dgrad) of one thread's RC x 4 outputs
@@ -711,6 +785,7 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
             const int rep = blockIdx.x % ACC_R;
             acc128_add(a.acc_out + (((int64_t)rep * a.CB + ch) * 2 + which) * 2, tot, a.flag);
         }
+        stats_exchange<T, true>(a, tid, CP_CONSUMERS);
     }
 }
 
@@ -919,7 +994,7 @@ struct GradLayer {
 template <typename T>
 struct GradArgs {
     GradLayer<T> L[PNODE_CONV_MAX_LAYERS];
-    int nl, accumulate;
+    int nl, accumulate, bn_grads;  // bn_grads = 0: the (global) BatchNorm gradients are contributed by rank 0 only
     int64_t np;
     const unsigned *flag;
     T *out;
@@ -956,7 +1031,7 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
             } else if (sub == 0) {
                 loc -= nw + l.Cout;  // bn.weight gradient = sum [y>0] g xhat, bn.bias gradient = sum [y>0] g
                 val = loc < l.Cout ? acc128_read(l.accB, l.Cout, (int)loc, 1) : acc128_read(l.accB, l.Cout, (int)(loc - l.Cout), 0);
-                val += bad;
+                val = a.bn_grads ? val + bad : 0.0;
             }
         }
 #pragma unroll
@@ -968,7 +1043,7 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
 // ---- host side ------------------------------------------------------------------------------------------------------------
 struct CbPlan {
     int L, Cmax;
-    int64_t M, npg;
+    int64_t M, Mglobal, npg;
     size_t esz;
     size_t off_z[PNODE_CONV_MAX_LAYERS], off_g[PNODE_CONV_MAX_LAYERS], off_accF[PNODE_CONV_MAX_LAYERS], off_accB[PNODE_CONV_MAX_LAYERS];
     size_t off_flag, off_acc0, acc_bytes, accB_bytes, off_wpart[PNODE_CONV_MAX_LAYERS], act_total, total;
@@ -1045,6 +1120,7 @@ static int cb_plan(const pnode_convblock_desc *d, CbPlan &p) {
     p.L = d->nlayers;
     p.esz = d->dtype == PNODE_F32 ? 4 : 8;
     p.M = (int64_t)d->N * d->H * d->W;
+    p.Mglobal = d->world > 1 && d->global_pixels > 0 ? d->global_pixels : p.M;
     p.npg = p.M / 4;
     p.Cmax = 0;
     p.pbase[0] = 0;
@@ -1065,6 +1141,8 @@ static int cb_plan(const pnode_convblock_desc *d, CbPlan &p) {
         p.pbase[k + 1] = p.pbase[k] + (int64_t)l.cout * l.cin * p.taps[k] + 3 * (int64_t)l.cout;
     }
     PNODE_REQUIRE(p.Cmax <= 2048, "convblock: at most 2048 channels (got %d)", p.Cmax);
+    PNODE_REQUIRE(d->world <= 1 || d->d_peer_bufs == nullptr || 4 * p.Cmax <= PNODE_PEER_NP_MAX,
+                  "convblock: the in-kernel statistics exchange takes at most %d channels (got %d)", PNODE_PEER_NP_MAX / 4, p.Cmax);
     // activation region (one per saved evaluation): z_1..z_L, then the flag + forward accumulators (zeroed by one memset)
     size_t off = 0;
     for (int k = 0; k < p.L; ++k) {
@@ -1266,14 +1344,18 @@ static void fill_common(ConvArgs<T> &a, const pnode_convblock_desc *d, const CbP
     a.H = d->H, a.W = d->W, a.HW = d->H * d->W;
     a.npg = p.npg;
     a.tiles = (int)((p.npg + CB_PGX - 1) / CB_PGX);
-    a.M = (double)p.M;
+    a.M = (double)p.Mglobal;
     a.flag = b.flag();
+    a.ticket = b.flag() + 16;
+    a.peer_bufs = d->world > 1 ? reinterpret_cast<const unsigned long long *>(d->d_peer_bufs) : nullptr;
+    a.rank = d->rank, a.world = d->world;
 }
 
 // z_1 .. z_L of the chain, the exact batch statistics of every layer, and the running-statistics updates of layers 1..L-1
 // (layer L's update belongs to whoever consumes z_L next: act_out_kernel or top_stats_kernel)
 template <typename T>
-static int forward_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b, const T *x, cudaStream_t st) {
+static int forward_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b, const T *x, unsigned long long &epoch,
+                         cudaStream_t st) {
     PNODE_CUDA_OK(cudaMemsetAsync(b.a + p.off_acc0, 0, p.acc_bytes, st));
     for (int k = 0; k < p.L; ++k) {
         const pnode_conv_layer &l = d->layer[k];
@@ -1284,6 +1366,7 @@ static int forward_chain(const pnode_convblock_desc *d, const CbPlan &p, const B
         a.w = static_cast<const T *>(l.d_weight), a.bias = static_cast<const T *>(l.d_bias);
         a.out = b.z(k);
         a.acc_out = b.accF(k);
+        a.epoch = epoch++;
         a.CA = l.cin, a.CB = l.cout;
         const ConvGrid g = conv_grid(l.cin, l.cout, p.taps[k], k == 0 ? 0 : 2, false, p.npg, p.esz);
         int rc = k == 0 ? launch_conv<T, SRC_RAW, EPI_FWD>(p.kind[k], a, g, st) : launch_conv<T, SRC_ACT, EPI_FWD>(p.kind[k], a, g, st);
@@ -1302,14 +1385,14 @@ static int act_out(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T>
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     PNODE_CUDA_OK(launch_k(act_out_kernel<T>, dim3((unsigned)blocks), dim3(256), 2 * C * sizeof(T), st, (const T *)b.z(p.L - 1),
-                           bn_ref(d, b, p.L - 1), (double)p.M, (const unsigned *)b.flag(), 1, d->H * d->W, nvec, out, base,
+                           bn_ref(d, b, p.L - 1), (double)p.Mglobal, (const unsigned *)b.flag(), 1, d->H * d->W, nvec, out, base,
                            (T)base_coef, (T)kcoef, kout));
     return 0;
 }
 
 template <typename T>
 static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<T> &b, const T *x, const T *w, T *vu, T *gout,
-                     double coef, int accumulate, int replay_running, cudaStream_t st) {
+                     double coef, int accumulate, int replay_running, unsigned long long &epoch, cudaStream_t st) {
     const int L = p.L;
     PNODE_CUDA_OK(cudaMemsetAsync(b.w + p.off_accB[0], 0, p.accB_bytes, st));
     {  // BatchNorm-backward sums of the top layer
@@ -1319,6 +1402,7 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
         a.in = w, a.zprev = b.z(L - 1);
         a.bout = bn_ref(d, b, L - 1), a.upd_out = 1;
         a.acc_out = b.accB(L - 1);
+        a.epoch = epoch++;
         a.CA = 0, a.CB = l.cout;
         const ConvGrid g = conv_grid(0, l.cout, 1, 0, true, p.npg, p.esz);
         dim3 grid(g.gx, g.gy), block(CB_PGX, g.cg);
@@ -1345,7 +1429,7 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             wa.tiles_cit = p.wg_tiles_cit[k];
             wa.npg = p.npg;
             wa.nchunks = (int)((p.npg + 31) / 32);
-            wa.M = (double)p.M;
+            wa.M = (double)p.Mglobal;
             int rc = k == 0 ? launch_wgrad<T, SRC_RAW>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], st)
                             : launch_wgrad<T, SRC_ACT>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], st);
             if (rc) return rc;
@@ -1366,6 +1450,7 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             a.zprev = b.z(k - 1), a.bout = bn_ref(d, b, k - 1);
             a.upd_out = replay_running;  // saved activations: the module's forward re-evaluation still advances the buffers
             a.acc_out = b.accB(k - 1);
+            a.epoch = epoch++;
             rc = launch_conv<T, SRC_DZ, EPI_DGRAD>(p.kind[k], a, g, st);
             gk = a.out;
         }
@@ -1374,6 +1459,7 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
     if (gout != nullptr) {
         GradArgs<T> ga = {};
         ga.nl = L, ga.accumulate = accumulate, ga.np = p.pbase[L], ga.out = gout, ga.coef = coef, ga.flag = b.flag();
+        ga.bn_grads = d->world <= 1 || d->d_peer_bufs == nullptr || d->rank == 0;
         int pxmax = 1;
         for (int k = 0; k < L; ++k) {
             ga.L[k].partial = b.wpart(k), ga.L[k].accB = b.accB(k);
@@ -1430,15 +1516,16 @@ int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, v
                   "pnode_convblock_forward: tensors must be 16-byte aligned");
     PNODE_REQUIRE(desc->layer[p.L - 1].cout == desc->layer[0].cin, "pnode_convblock_forward: an ODE right-hand side maps C -> C");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long epoch = desc->epoch;
     if (desc->dtype == PNODE_F32) {
         Bufs<float> b(d_act, nullptr, p);
-        rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), st);
+        rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), epoch, st);
         if (rc) return rc;
         return act_out<float>(desc, p, b, static_cast<float *>(d_out), static_cast<const float *>(d_base), base_coef, k_coef,
                               static_cast<float *>(d_k), st);
     }
     Bufs<double> b(d_act, nullptr, p);
-    rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), st);
+    rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), epoch, st);
     if (rc) return rc;
     return act_out<double>(desc, p, b, static_cast<double *>(d_out), static_cast<const double *>(d_base), base_coef, k_coef,
                            static_cast<double *>(d_k), st);
@@ -1453,22 +1540,25 @@ int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const
     PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_w) && cb_aligned(d_vu) && cb_aligned(d_act) && cb_aligned(d_work),
                   "pnode_convblock_vjp: tensors must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long epoch = desc->epoch;
     if (desc->dtype == PNODE_F32) {
         Bufs<float> b(d_act, d_work, p);
         if (!act_valid) {
-            rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), st);
+            rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), epoch, st);
             if (rc) return rc;
         }
         return vjp_chain<float>(desc, p, b, static_cast<const float *>(d_x), static_cast<const float *>(d_w),
-                                static_cast<float *>(d_vu), static_cast<float *>(d_grads), coef, accumulate, act_valid != 0, st);
+                                static_cast<float *>(d_vu), static_cast<float *>(d_grads), coef, accumulate, act_valid != 0, epoch,
+                                st);
     }
     Bufs<double> b(d_act, d_work, p);
     if (!act_valid) {
-        rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), st);
+        rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), epoch, st);
         if (rc) return rc;
     }
     return vjp_chain<double>(desc, p, b, static_cast<const double *>(d_x), static_cast<const double *>(d_w),
-                             static_cast<double *>(d_vu), static_cast<double *>(d_grads), coef, accumulate, act_valid != 0, st);
+                             static_cast<double *>(d_vu), static_cast<double *>(d_grads), coef, accumulate, act_valid != 0, epoch,
+                             st);
 }
 
 }  // extern "C"

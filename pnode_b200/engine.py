@@ -299,7 +299,7 @@ class GenericTS:
         self.recomputed_steps = 0
         for cb in (cb_ex, cb_im):
             if cb is not None and hasattr(cb, "begin"):
-                cb.begin(True, keep=save_trajectory)
+                cb.begin(True, keep=save_trajectory, comm=self.comm)
         u = u0.reshape(-1).clone()
         n_local = u.numel()
         n_global = n_local if self.comm is None else self.comm.global_count(n_local)
@@ -466,7 +466,7 @@ class GenericTS:
     def adjoint_steps(self, cb_ex, cb_im, imp, nsteps, lam, mu, np_im):
         for cb in (cb_ex, cb_im):
             if cb is not None and hasattr(cb, "begin"):
-                cb.begin(False)
+                cb.begin(False, comm=self.comm)
         for _ in range(nsteps):
             if not self.traj:
                 raise Error(-30, "adjoint requested more steps than the trajectory holds")

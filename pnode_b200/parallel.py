@@ -48,6 +48,14 @@ class BatchComm:
         self.collectives += 1
         return self.peer["epoch"]
 
+    def reserve_epochs(self, n):
+        """First of n consecutive collective numbers for kernels that exchange through the symmetric inbox themselves (the
+        conv block's statistics exchange, csrc/conv_block.cu); every rank reserves the same numbers in the same order."""
+        first = self.peer["epoch"] + 1
+        self.peer["epoch"] += n
+        self.collectives += n
+        return first
+
     def allreduce_sum(self, tensor):
         if self.world > 1:
             dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)

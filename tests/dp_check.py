@@ -70,6 +70,39 @@ def main():
     assert rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)) < 1e-10
     for a, b in zip(mine[2], full[2]):
         assert rel_err(a, b) < 1e-10
+    # 3. conv ODE block (BASELINE config 4), batch sharded: train-mode BatchNorm needs the statistics of the GLOBAL batch.  The
+    #    kernels exchange exact integer totals over NVLink peer memory in their tail: every rank holds bit-identical statistics,
+    #    and the sharded run reproduces the single-GPU run of the whole batch to rounding (the per-CTA partial sums group the
+    #    pixels differently when the batch is split, nothing else differs).
+    if "--peer" in sys.argv:
+        from _workloads import OdeConvBlock
+
+        for dtype, shape, tol in ((torch.float64, (4 * world, 16, 8, 8), 1e-12), (torch.float32, (16 * world, 32, 16, 16), 2e-5)):
+            g = torch.Generator().manual_seed(9)
+            u2 = torch.randn(shape, generator=g, dtype=torch.float64).to(dtype)
+            go2 = torch.randn((1,) + shape, generator=g, dtype=torch.float64).to(dtype)
+            t2 = torch.tensor([1.0], dtype=torch.float64)
+            f2 = OdeConvBlock(shape[1], dtype=dtype)
+            argv = ["-ts_adapt_type", "none", "-pnode_convblock_native", "1"]
+            full = run(f2, u2, go2, t2, "rk4", 0.5, None, argv)
+            mine = run(f2, shard_batch(u2, rank, world).contiguous(), shard_batch(go2, rank, world, dim=1).contiguous(), t2,
+                       "rk4", 0.5, comm, argv)
+            assert mine[3]._cb_im.native and mine[3]._cb_im._comm is comm
+            flat = lambda gs: torch.cat([q.double().reshape(-1) for q in gs])
+            errs = (rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)), rel_err(mine[1], shard_batch(full[1], rank, world)),
+                    rel_err(flat(mine[2]), flat(full[2])))
+            fa, fb = mine[3].funcIM, full[3].funcIM
+            errs += (rel_err(fa.bn3.running_var.cpu(), fb.bn3.running_var.cpu()), rel_err(fa.bn5.running_mean.cpu(), fb.bn5.running_mean.cpu()))
+            if rank == 0:
+                print("conv block sharded vs full batch (%s): trajectory %.2e lambda %.2e mu %.2e running stats %.2e %.2e" %
+                      ((str(dtype),) + errs), flush=True)
+            assert max(errs) < tol, errs
+            assert int(fa.bn3.num_batches_tracked) == int(fb.bn3.num_batches_tracked)
+            # every rank holds the SAME statistics bit for bit (exact integer exchange): compare the BatchNorm buffers across ranks
+            rv = fa.bn4.running_var.detach().clone()
+            ref = rv.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(rv, ref), "BatchNorm statistics differ across ranks"
     if comm.peer is not None:
         # the in-kernel all-reduce must be bit-identical on every rank and repeatable (epochs / double buffering)
         for rep in range(5):
