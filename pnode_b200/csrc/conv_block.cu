@@ -1313,6 +1313,28 @@ static int launch_wgrad(int kind, int tm, int tn, const WgradArgs<T> &a, int px,
     return launch_wgrad_kind<T, 2, YSRC>(tm, tn, a, px, ntiles, st);
 }
 
+// The weight-gradient kernel of a layer and its data-gradient kernel read the same inputs and do not depend on each other:
+// the weight gradients run on a side stream (fork after the kernel that completed the layer's backward sums, join before the
+// final gradient kernel), so the two latency-bound kernels share the SMs instead of queueing.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[PNODE_CONV_MAX_LAYERS + 1] = {}, join = nullptr;
+    bool ok = false;
+};
+static SideStream &side_stream() {
+    static SideStream s;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        static const int enabled = env_int("PNODE_WGRAD_STREAM", 1);
+        bool ok = enabled && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; ok && i <= PNODE_CONV_MAX_LAYERS; ++i) ok = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+        s.ok = ok;
+    }
+    return s;
+}
+
 template <typename T>
 struct Bufs {
     unsigned char *a, *w;  // activation region, scratch region
@@ -1416,8 +1438,16 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
         }
     }
     const T *gk = w;
+    SideStream &side = side_stream();
+    const bool fork = side.ok && gout != nullptr;
     for (int k = L - 1; k >= 0; --k) {
         const pnode_conv_layer &l = d->layer[k];
+        cudaStream_t wst = st;
+        if (fork) {  // everything wgrad_k needs (g_k, the backward sums of layer k) is complete at this point of the main stream
+            PNODE_CUDA_OK(cudaEventRecord(side.fork[k], st));
+            PNODE_CUDA_OK(cudaStreamWaitEvent(side.stream, side.fork[k], 0));
+            wst = side.stream;
+        }
         if (gout != nullptr) {
             WgradArgs<T> wa = {};
             wa.g = gk, wa.z = b.z(k), wa.bk = bn_ref(d, b, k);
@@ -1430,8 +1460,8 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             wa.npg = p.npg;
             wa.nchunks = (int)((p.npg + 31) / 32);
             wa.M = (double)p.Mglobal;
-            int rc = k == 0 ? launch_wgrad<T, SRC_RAW>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], st)
-                            : launch_wgrad<T, SRC_ACT>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], st);
+            int rc = k == 0 ? launch_wgrad<T, SRC_RAW>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], wst)
+                            : launch_wgrad<T, SRC_ACT>(p.kind[k], p.wg_tm[k], p.wg_tn[k], wa, p.wg_px[k], p.wg_ntiles[k], wst);
             if (rc) return rc;
         }
         if (k == 0 && vu == nullptr) break;
@@ -1455,6 +1485,10 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
             gk = a.out;
         }
         if (rc) return rc;
+    }
+    if (fork) {
+        PNODE_CUDA_OK(cudaEventRecord(side.join, side.stream));
+        PNODE_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
     }
     if (gout != nullptr) {
         GradArgs<T> ga = {};
