@@ -272,7 +272,7 @@ class ConvBlockCallbacks(Callbacks):
         return x, saved
 
     # -- the two closures the engine needs ---------------------------------------------------------------------------
-    def f(self, t, u):
+    def f(self, t, u, keep=True):
         self.nfe += 1
         if hasattr(self.func, "nfe"):
             self.func.nfe += 1

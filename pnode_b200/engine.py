@@ -17,7 +17,14 @@ from .errors import Error
 
 
 class Callbacks:
-    """The two closures the engine needs from the user's modules: f(t,u) and vjp(t,u,w) -> (J^T w, Jp^T w)."""
+    """The two closures the engine needs from the user's modules: f(t,u) and vjp(t,u,w) -> (J^T w, Jp^T w).
+
+    Stage evaluations of a solve that an adjoint sweep will follow keep their autograd graph (keep=True), keyed by the stage
+    tensor: the adjoint stage at the same point then differentiates the kept graph instead of re-evaluating the module -- the
+    reference re-evaluates (petsc_adjoint.py:64-70) because PETSc's trajectory only stores vectors; the arithmetic is the same,
+    one forward evaluation per adjoint stage is saved (a third of the adjoint's cost).  It is switched off for modules whose
+    forward has side effects the re-evaluation would repeat (train-mode BatchNorm statistics, active Dropout), by
+    `-pnode_reuse_graph 0`, and beyond a memory budget (`-pnode_reuse_graph_mb`, default 8192)."""
 
     def __init__(self, func, tensor_size):
         self.func = func
@@ -27,10 +34,60 @@ class Callbacks:
         self.nparams = sum(self.sizes)
         self.nfe = 0
         self.nvjp = 0
+        self._graphs = {}
+        self._graph_bytes = 0
+        self._marks = []
+        self.reused_graphs = 0
+        from .options import Options
 
-    def f(self, t, u):
+        self._graph_budget = int(float(Options().getString("pnode_reuse_graph_mb", "8192")) * (1 << 20))
+        self._reuse = Options().getString("pnode_reuse_graph", "1") not in ("0", "false", "no") and self._side_effect_free()
+
+    def _side_effect_free(self):
+        if not isinstance(self.func, torch.nn.Module):
+            return False
+        for m in self.func.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.training and m.track_running_stats:
+                return False
+            if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout1d, torch.nn.Dropout2d, torch.nn.Dropout3d,
+                              torch.nn.AlphaDropout)) and m.training and m.p > 0:
+                return False
+        return True
+
+    def begin(self, forward, keep=True, comm=None):
+        """Start of a forward solve (kept graphs of the previous one are dropped) / of an adjoint sweep."""
+        if forward:
+            self._graphs.clear()
+            self._graph_bytes = 0
+            self._marks = []
+
+    def mark(self):
+        """Remember the kept graphs so far: a rejected step attempt rolls back to here."""
+        self._marks = list(self._graphs.keys())
+
+    def rollback(self):
+        for k in [k for k in self._graphs if k not in self._marks]:
+            self._graph_bytes -= self._graphs.pop(k)[5]
+
+    def _pversions(self):
+        return tuple(p._version for p in self.params)
+
+    def f(self, t, u, keep=False):
         """evalRHSFunction (petsc_adjoint.py:393-405): t is handed over as a python float."""
         self.nfe += 1
+        if keep and self._reuse and u.is_cuda and self._graph_bytes < self._graph_budget:
+            before = torch.cuda.memory_allocated(u.device)
+            with torch.enable_grad():
+                x = u.detach().view(self.tensor_size).requires_grad_(True)
+                out = self.func(t, x)
+            if isinstance(out, torch.Tensor) and out.requires_grad:
+                nbytes = max(torch.cuda.memory_allocated(u.device) - before, 0)
+                self._graphs[u.data_ptr()] = (u, u._version, self._pversions(), x, out, nbytes, float(t))
+                self._graph_bytes += nbytes
+            flat = out.detach().reshape(-1)
+            if flat.dtype != u.dtype:
+                flat = flat.to(u.dtype)
+            return flat if flat.is_contiguous() else flat.contiguous()
         with torch.no_grad():
             out = self.func(t, u.view(self.tensor_size))
         out = out.detach().reshape(-1)
@@ -58,13 +115,26 @@ class Callbacks:
         """RHSJacShell.multTranspose (petsc_adjoint.py:52-82): one autograd.grad gives J^T w and the per-parameter
         (df/dp)^T w (None for unused parameters, misc.py:9-14)."""
         self.nvjp += 1
-        with torch.enable_grad():
-            x = u.detach().view(self.tensor_size).requires_grad_(True)
-            out = self.func(t, x)
+        ent = self._graphs.get(u.data_ptr())
+        if ent is not None and ent[1] == u._version and ent[2] == self._pversions() and ent[6] == float(t) and \
+                ent[0].numel() == u.numel():
+            # the graph of the forward evaluation at this very stage is still alive: differentiate it (no re-evaluation)
+            x, out = ent[3], ent[4]
+            self.reused_graphs += 1
+            if isinstance(getattr(self.func, "nfe", None), int):
+                self.func.nfe += 1  # observable count of the reference, whose adjoint calls func once per stage
             inputs = ([x] if want_u else []) + (self.params if want_params else [])
             if not inputs:
                 return None, []
-            g = torch.autograd.grad(out, inputs, w.view(out.shape).to(out.dtype), allow_unused=True)
+            g = torch.autograd.grad(out, inputs, w.view(out.shape).to(out.dtype), allow_unused=True, retain_graph=True)
+        else:
+            with torch.enable_grad():
+                x = u.detach().view(self.tensor_size).requires_grad_(True)
+                out = self.func(t, x)
+                inputs = ([x] if want_u else []) + (self.params if want_params else [])
+                if not inputs:
+                    return None, []
+                g = torch.autograd.grad(out, inputs, w.view(out.shape).to(out.dtype), allow_unused=True)
         if want_u:
             vu, gp = g[0], list(g[1:])
             vu = torch.zeros_like(u) if vu is None else vu.reshape(-1).contiguous()
@@ -165,8 +235,29 @@ class ImplicitSolver:
 
     mass = None  # dense [n, n] mass matrix of M u' = f(t, u) (petsc_adjoint.py:426-431), theta methods only
 
+    # fixed_jacobian=True ("the Jacobian is constant across ODE solves", petsc_adjoint.py:582): the block Jacobian and its
+    # inverses survive from one odeint to the next -- and across setupTS calls, through `cache`, a dict the ODEPetsc object owns
+    # -- as long as no parameter or buffer of the implicit function has been modified.  The reference documents the flag but
+    # rebuilds anyway (its reset condition at 792-795 is always true); honouring it removes an O(N^3) factorisation per solve.
+    fixed_jacobian = False
+    cache = None
+
+    def _signature(self):
+        f = self.cb.func
+        if not isinstance(f, torch.nn.Module):
+            return None
+        return tuple((id(q), q._version) for q in list(f.parameters()) + list(f.buffers())) + (self.batch, self.linear_solver)
+
     def reset(self):
         """Once per odeint: parameters may have changed (petsc_adjoint.py:792-799)."""
+        if self.fixed_jacobian and self.cache is not None:
+            sig = self._signature()
+            if sig is not None and self.cache.get("sig") == sig and self.cache.get("func") is self.cb.func:
+                self._J0, self._inv = self.cache["J0"], self.cache["inv"]
+                return
+            self._J0, self._inv = None, {}
+            self.cache.update(sig=sig, func=self.cb.func, J0=None, inv=self._inv)
+            return
         self._J0 = None
         self._inv = {}
 
@@ -186,6 +277,8 @@ class ImplicitSolver:
             except Exception:
                 J = torch.autograd.functional.jacobian(lambda v: self.cb.func(t, v), y0)
             self._J0 = J.reshape(N, N)
+            if self.fixed_jacobian and self.cache is not None:
+                self.cache["J0"] = self._J0
         return self._J0
 
     def _block_inverse(self, t, y, shift):
@@ -290,6 +383,7 @@ class GenericTS:
         self.max_cps = max_cps
         self.traj = []
         self.recomputed_steps = 0
+        self._keep = False  # stage evaluations keep what the adjoint stage at the same point can reuse
 
     # -- forward ----------------------------------------------------------------------------------------------------
     def solve(self, cb_ex, cb_im, imp, u0, loop: TimeLoop, save_trajectory):
@@ -300,6 +394,7 @@ class GenericTS:
         for cb in (cb_ex, cb_im):
             if cb is not None and hasattr(cb, "begin"):
                 cb.begin(True, keep=save_trajectory, comm=self.comm)
+        self._keep = bool(save_trajectory)
         u = u0.reshape(-1).clone()
         n_local = u.numel()
         n_global = n_local if self.comm is None else self.comm.global_count(n_local)
@@ -320,7 +415,13 @@ class GenericTS:
                 enorm = math.sqrt(float(sumsq.item()) / n_global)
             if not loop.report(enorm):
                 k_fsal = None
+                for cb in (cb_ex, cb_im):
+                    if cb is not None and hasattr(cb, "rollback"):
+                        cb.rollback()  # graphs / activation sets of the rejected attempt
                 continue
+            for cb in (cb_ex, cb_im):
+                if cb is not None and hasattr(cb, "mark"):
+                    cb.mark()
             if save_trajectory:
                 self._record(t, h, u, stages)
             if self.kind == "rk" and self.scheme.fsal:
@@ -391,7 +492,7 @@ class GenericTS:
                 k, y_next = cb.f_and_combine(t + sc.c[i] * h, y, u, h * sc.A[i + 1][i])
                 K.append(k)
             else:
-                K.append(cb.f(t + sc.c[i] * h, y))
+                K.append(cb.f(t + sc.c[i] * h, y, keep=self._keep))
         idx = [j for j in range(s) if sc.b[j] != 0.0 or (adaptive and sc.bembed[j] != 0.0)]
         unew = torch.empty_like(u)
         ew = [h * (sc.bembed[j] - sc.b[j]) for j in idx] if adaptive else None
@@ -418,7 +519,7 @@ class GenericTS:
                 Z = u
             if sc.At[i][i] == 0.0:
                 y = Z
-                ki = cb_im.f(t + sc.ct[i] * h, y)
+                ki = cb_im.f(t + sc.ct[i] * h, y, keep=self._keep)
             else:
                 shift = 1.0 / (h * sc.At[i][i])
                 y = imp.solve(t + sc.ct[i] * h, Z, shift, Y[i - 1] if i > 0 else u)
@@ -426,7 +527,7 @@ class GenericTS:
                 ops.lincomb(ki, None, 0.0, [y, Z], [shift, -shift])  # K^I_i = shift (Y_i - Z), not re-evaluated
             Y.append(y)
             KI.append(ki)
-            KE.append(cb_ex.f(t + sc.c[i] * h, y))
+            KE.append(cb_ex.f(t + sc.c[i] * h, y, keep=self._keep))
         vecs, bw, ew = [], [], []
         for j in range(s):
             be = sc.bembed[j] if (adaptive and sc.bembed is not None) else sc.b[j]

@@ -171,6 +171,10 @@ class ODEPetsc(object):
         self._imp = ImplicitSolver(self._ops, self._cb_im, self.linear_solver, self.batch_size, self._ksponly,
                                    rtol=opt.getReal("snes_rtol", 1e-8), max_it=opt.getInt("snes_max_it", 50),
                                    ksp_rtol=opt.getReal("ksp_rtol", 1e-5), ksp_max_it=opt.getInt("ksp_max_it", 10000))
+        self._imp.fixed_jacobian = bool(self.fixed_jacobian)
+        if not hasattr(self, "_imp_cache"):
+            self._imp_cache = {}
+        self._imp.cache = self._imp_cache
         sol_only = opt.getString("ts_trajectory_solution_only", "0") not in ("0", "false", "no")
         max_cps = opt.getInt("ts_trajectory_max_cps_ram", None)
         if self.mass is not None and kind not in ("cn", "beuler"):

@@ -108,6 +108,49 @@ def test_config5_sinode_ks_imex(name):
     _compare(p, o, 1e-9)
 
 
+def test_config5_fixed_jacobian_is_kept_across_solves_and_stage_graphs_are_reused():
+    """fixed_jacobian(_across_solves)=True: the (shift I - J)^-1 factorisation survives from one odeint to the next until a
+    parameter / buffer of the implicit function changes; the adjoint differentiates the stage graphs the forward kept."""
+    from pnode import petsc_adjoint
+
+    N, B = 64, 8
+    f_im, f_ex = KSImplicit(ks_dx(N)).cuda(), KSExplicit(N).cuda()
+    g = torch.Generator().manual_seed(4)
+    u0 = (0.5 * torch.randn(B, N, generator=g, dtype=torch.float64)).cuda()
+    t = torch.tensor([0.0, 0.2], dtype=torch.float64).cuda()
+    gout = torch.randn(2, B, N, generator=g, dtype=torch.float64).cuda()
+    Options.insert_args(["-ts_adapt_type", "none", "-snes_type", "ksponly"])
+
+    def solve(ode):
+        f_ex.zero_grad(set_to_none=True)
+        y0 = u0.clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t)
+        (out * gout).sum().backward()
+        return out.detach().clone(), y0.grad.clone(), [p.grad.clone() for p in f_ex.parameters()]
+
+    ode = petsc_adjoint.ODEPetsc()
+    ode.setupTS(u0, f_im, step_size=0.2, method="imex", imex_form=True, func2=f_ex, batch_size=B, linear_solver="torch",
+                fixed_jacobian_across_solves=True)
+    a = solve(ode)
+    inv1 = dict(ode._imp._inv)
+    assert len(inv1) >= 1 and ode._cb_ex.reused_graphs >= 4  # ARK3: four explicit stage evaluations reused by the adjoint
+    b = solve(ode)
+    assert all(ode._imp._inv[k] is v for k, v in inv1.items()), "the factorisation was rebuilt although nothing changed"
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and all(torch.equal(x, y) for x, y in zip(a[2], b[2]))
+    with torch.no_grad():
+        f_im.A.weight.mul_(1.0)  # in-place touch: version counter moves, the Jacobian must be rebuilt
+    solve(ode)
+    assert all(ode._imp._inv[k] is not v for k, v in inv1.items())
+    # without the promise the factorisation is rebuilt at every solve, as in the reference
+    ode2 = petsc_adjoint.ODEPetsc()
+    ode2.setupTS(u0, f_im, step_size=0.2, method="imex", imex_form=True, func2=f_ex, batch_size=B, linear_solver="torch")
+    c = solve(ode2)
+    inv2 = dict(ode2._imp._inv)
+    solve(ode2)
+    assert all(ode2._imp._inv[k] is not v for k, v in inv2.items())
+    assert rel_err(c[0], a[0]) < 1e-12 and rel_err(c[1], a[1]) < 1e-12
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("shape", [(256, 16, 32, 32), (7, 32, 4, 4), (3, 5, 2, 2)])
 def test_bn_relu_kernels_match_torch(dtype, shape):
