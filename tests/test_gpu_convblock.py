@@ -111,6 +111,55 @@ def test_fused_stage_combination_and_mu_accumulation():
     assert torch.equal(vu, vu2) and torch.equal(mu, mu2)
 
 
+def test_full_size_properties_of_config4():
+    """BASELINE config 4 at its full size ([256,32,32,32], where the CPU oracle takes minutes): size-independent properties.
+    (1) batch-permutation equivariance: BatchNorm statistics are sums over the batch, everything else is per sample;
+    (2) the VJP is linear in the cotangent and `mu += coef * Jp^T w` accumulates;
+    (3) adjoint dot-product test in fp64: <w, (f(x + e v) - f(x - e v)) / 2e> == <J^T w, v> (central differences of the forward
+        kernels against the hand-written backward kernels);
+    (4) the stock torch module and its autograd backward at the full size, fp64, every parameter gradient."""
+    shape = (256, 32, 32, 32)
+    g = torch.Generator().manual_seed(21)
+    func = OdeConvBlock(32, dtype=torch.float32).cuda()
+    cb = _callbacks(func, shape)
+    x = torch.randn(shape, generator=g).cuda().reshape(-1)
+    w1 = torch.randn(shape, generator=g).cuda().reshape(-1)
+    w2 = torch.randn(shape, generator=g).cuda().reshape(-1)
+    perm = torch.randperm(shape[0], generator=g).cuda()
+    fx = cb.f(0.0, x).view(shape)
+    fp = cb.f(0.0, x.view(shape)[perm].contiguous().reshape(-1)).view(shape)
+    assert rel_err(fp, fx[perm]) < 2e-6
+    va, ga = cb.vjp(0.0, x, w1)
+    vb, gb = cb.vjp(0.0, x, w2)
+    vc, gc = cb.vjp(0.0, x, (2.0 * w1 - 0.5 * w2))
+    flat = lambda gs: torch.cat([q.reshape(-1) for q in gs])
+    assert rel_err(vc, 2.0 * va - 0.5 * vb) < 1e-5 and rel_err(flat(gc), 2.0 * flat(ga) - 0.5 * flat(gb)) < 1e-4
+    mu = torch.ones(cb.nparams, device="cuda")
+    cb.vjp_accumulate(0.0, x, w1, mu, 0.5)
+    assert rel_err(mu, 1.0 + 0.5 * flat(ga)) < 1e-6
+    # (3) fp64
+    func64 = OdeConvBlock(32, dtype=torch.float64).cuda()
+    cb64 = _callbacks(func64, shape)
+    x64, w64 = x.double(), w1.double()
+    v64 = torch.randn(shape, generator=g, dtype=torch.float64).cuda().reshape(-1)
+    eps = 1e-8  # millions of ReLU kinks: central differences only settle below ~1e-7 (tools/diag_fd.py, same for the torch module)
+    jtw, gp = cb64.vjp(0.0, x64, w64)
+    fd = (cb64.f(0.0, x64 + eps * v64) - cb64.f(0.0, x64 - eps * v64)) / (2 * eps)
+    lhs, rhs = float(torch.dot(w64, fd)), float(torch.dot(jtw, v64))
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+    # (4) and, since the stock module runs at this size on the GPU in seconds, the direct comparison in fp64
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out_r, vu_r, gp_r, _ = _reference(func64, x64.view(shape), w64.view(shape))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert rel_err(cb64.f(0.0, x64).view(shape), out_r) < 1e-12 and rel_err(jtw.view(shape), vu_r) < 1e-12
+    for (n, _), a, b in zip(func64.named_parameters(), gp, gp_r):
+        if not (n.startswith("conv") and n.endswith("bias")):
+            assert rel_err(a.view_as(b), b) < 1e-11, (n, rel_err(a.view_as(b), b))
+
+
 def test_unsupported_shapes_are_refused_by_the_abi_not_computed_wrongly():
     from pnode_b200 import _lib
 
