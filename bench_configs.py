@@ -166,7 +166,7 @@ def _cnf(B, dtype):
     return build
 
 
-def cfg4(C=32, HW=32):
+def cfg4(C=32, HW=32, Nt=1):
     def build():
         from _workloads import OdeConvBlock
 
@@ -178,9 +178,9 @@ def cfg4(C=32, HW=32):
         bs = 32
         # 75.5 Mflop and 96 C HW w bytes per trajectory-step (every layer reads its input and writes its output
         # once per RHS evaluation, adjoint = 3 evaluations' worth, stage checkpoints): block 1-2 are HBM-bound on CUDA cores
-        return dict(desc="cfg4 CIFAR SqueezeNext ODE block: u [256,%d,%d,%d] fp32, RK4, t=[1.0], Nt=1 (h=1), conv+BN(train)"
-                         % (C, HW, HW), dtype="f32", argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"],
-                    funcs=[OdeConvBlock(C)], u0=u0, t=t, target=target, kw=dict(method="rk4"), step=1.0, batch=B,
+        return dict(desc="cfg4 CIFAR SqueezeNext ODE block: u [256,%d,%d,%d] fp32, RK4, t=[1.0], Nt=%d (h=%g), conv+BN(train)"
+                         % (C, HW, HW, Nt, 1.0 / Nt), dtype="f32", argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"],
+                    funcs=[OdeConvBlock(C)], u0=u0, t=t, target=target, kw=dict(method="rk4"), step=1.0 / Nt, batch=B,
                     flops_per_unit=75.5e6, bytes_per_unit=96 * C * HW * HW * 4, pipe="fp32_fma", each_call_setup=True,
                     cpu_sample=lambda: dict(funcs=[OdeConvBlock(C)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
                                             kw=dict(method="rk4"), batch=bs, desc="%d of %d samples" % (bs, B)))
@@ -235,7 +235,7 @@ def main():
         pk[key] = fl.value / (ms.value * 1e-3) / 1e12
     table = {"1": ("cfg1", cfg1), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
              "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
-             "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)), "5": ("cfg5", cfg5()),
+             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)), "5": ("cfg5", cfg5()),
              "5S": ("cfg5-f32", cfg5(dtype="f32"))}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "a") as fo:
