@@ -295,6 +295,11 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
  * -------------------------------------------------------------------------------------------------------------- */
 int pnode_peak_fma(int dtype, int iters, double *flops, float *ms);
 
+/* *d_out = sum of d_values[0..n) formed with the conv block's exact 128-bit fixed-point accumulator (integer atomics, one add per
+ * thread, arbitrary order): unit-test hook for its exactness and order independence.  NaN if any value is not finite.
+ * d_work: 256 bytes of scratch. */
+int pnode_acc128_probe(const double *d_values, int64_t n, double *d_out, void *d_work, void *stream);
+
 /* out[i] = tanh(in[i]) evaluated with the kernels' own tanh (unit-test hook for its accuracy). */
 int pnode_tanh_probe(const void *d_in, void *d_out, int64_t n, int dtype, void *stream);
 

@@ -86,6 +86,7 @@ _SIGNATURES = {
                                           _vp, _vp, _i, _i, C.c_uint64, _vp]),
     "pnode_peak_fma": (C.c_int, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float)]),
     "pnode_tanh_probe": (C.c_int, [_vp, _vp, _i64, _i, _vp]),
+    "pnode_acc128_probe": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -100,15 +100,22 @@ __device__ __forceinline__ void acc128_add(unsigned long long *p, double x, unsi
 
 // acc layout: [ACC_R][C][2 statistics][2 words]
 __device__ __forceinline__ double acc128_read(const unsigned long long *acc, int C, int ch, int stat) {
-    double t = 0.0;
+    unsigned long long lo = 0;  // the replicas are added as 128-bit integers (exact); one conversion at the end
+    long long hi = 0;
 #pragma unroll
     for (int r = 0; r < ACC_R; ++r) {
         const unsigned long long *p = acc + (((int64_t)r * C + ch) * 2 + stat) * 2;
-        const unsigned long long lo = __ldcg(p);
-        const long long hi = (long long)__ldcg(p + 1);
-        t += (double)hi * 16.0 + (double)lo * 8.673617379884035e-19;  // 2^-60
+        const unsigned long long l = __ldcg(p);
+        lo += l;
+        hi += (long long)__ldcg(p + 1) + (lo < l ? 1 : 0);
     }
-    return t;
+    const bool neg = hi < 0;  // convert the magnitude: a small negative total is hi = -1, lo = 2^64 - small
+    if (neg) {
+        lo = ~lo + 1ull;
+        hi = ~hi + (lo == 0ull ? 1 : 0);
+    }
+    const double v = (double)hi * 16.0 + (double)lo * 8.673617379884035e-19;  // 2^-60
+    return neg ? -v : v;
 }
 
 // One BatchNorm layer as the kernels see it: where its statistics accumulate and its affine parameters / buffers.
@@ -1040,6 +1047,15 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
     }
 }
 
+// unit-test hook: every thread adds one value into ONE accumulator (all replicas used), then the total is read back
+__global__ void acc128_probe_kernel(const double *__restrict__ v, int64_t n, unsigned long long *acc, unsigned *flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc128_add(acc + ((int64_t)(blockIdx.x % ACC_R) * 2) * 2, v[i], flag);
+}
+__global__ void acc128_read_kernel(const unsigned long long *acc, const unsigned *flag, double *out) {
+    out[0] = *flag != 0u ? NAN : acc128_read(acc, 1, 0, 0);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------
 struct CbPlan {
     int L, Cmax;
@@ -1521,6 +1537,18 @@ static bool cb_aligned(const void *p) { return p == nullptr || (reinterpret_cast
 using namespace pnode;
 
 extern "C" {
+
+int pnode_acc128_probe(const double *d_values, int64_t n, double *d_out, void *d_work, void *stream) {
+    PNODE_REQUIRE(d_values && d_out && d_work && n >= 0, "pnode_acc128_probe: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *acc = static_cast<unsigned long long *>(d_work);
+    unsigned *flag = reinterpret_cast<unsigned *>(acc + ACC_R * 2 * 2);
+    PNODE_CUDA_OK(cudaMemsetAsync(d_work, 0, 256, st));
+    if (n > 0) acc128_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_values, n, acc, flag);
+    acc128_read_kernel<<<1, 1, 0, st>>>(acc, flag, d_out);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int64_t pnode_convblock_act_bytes(const pnode_convblock_desc *desc) {
     CbPlan p;

@@ -176,3 +176,39 @@ def test_unsupported_shapes_are_refused_by_the_abi_not_computed_wrongly():
     l.kh = l.kw = 3
     l.ph = l.pw = 1
     assert lib.pnode_convblock_work_bytes(C.byref(d)) == -1
+
+
+def test_exact_accumulator_is_exact_and_order_independent():
+    """The 128-bit fixed-point accumulator behind the BatchNorm statistics: a million adds in whatever order the hardware
+    schedules them give the exact sum (math.fsum) to a few ulp of the final conversion, bit-identically on every repetition -- also when the terms
+    cancel catastrophically; non-finite terms poison the result instead of disappearing."""
+    import math
+
+    from pnode_b200 import _lib
+
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    work = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    g = torch.Generator().manual_seed(0)
+    n = 1 << 20
+    cases = [torch.randn(n, generator=g, dtype=torch.float64) * 1e3,
+             torch.cat((torch.full((n // 2,), 1e15, dtype=torch.float64), torch.full((n // 2,), -1e15, dtype=torch.float64),
+                        torch.tensor([2.0 ** -40, -3.5, 7.25], dtype=torch.float64))),
+             torch.rand(n, generator=g, dtype=torch.float64) * 2.0 ** -30 - 2.0 ** -31]
+    for v in cases:
+        want = math.fsum(math.floor(x * 2.0 ** 60) * 2.0 ** -60 for x in v.tolist()) if float(v.abs().max()) < 1.0 else None
+        vd = v.cuda()
+        got = []
+        for _ in range(3):
+            _lib.check(lib.pnode_acc128_probe(vd.data_ptr(), vd.numel(), out.data_ptr(), work.data_ptr(), st))
+            got.append(float(out.item()))
+        assert got[0] == got[1] == got[2]
+        exact = math.fsum(v.tolist())
+        if want is not None:  # terms finer than the 2^-60 resolution are truncated toward -inf, deterministically; the read-back
+            assert abs(got[0] - want) <= 8 * math.ulp(want), (got[0], want)  # rounds each of the 4 replicas to double once
+        else:
+            assert abs(got[0] - exact) <= v.numel() * 2.0 ** -60 + 4 * math.ulp(exact), (got[0], exact)
+    bad = torch.tensor([1.0, float("inf"), 2.0], dtype=torch.float64).cuda()
+    _lib.check(lib.pnode_acc128_probe(bad.data_ptr(), 3, out.data_ptr(), work.data_ptr(), st))
+    assert math.isnan(float(out.item()))
