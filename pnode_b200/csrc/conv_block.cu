@@ -89,10 +89,15 @@ __device__ __forceinline__ void acc128_add(unsigned long long *p, double x, unsi
         atomicOr(flag, 1u);
         return;
     }
-    const double h = floor(x * 0.0625);
-    const double r = x - h * 16.0;  // exact, in [0, 16)
-    const unsigned long long lo = (unsigned long long)(r * 1152921504606846976.0);  // 2^60
+    const double m = fabs(x);
+    const double h = floor(m * 0.0625);
+    const double r = m - h * 16.0;  // exact (the low bits of m), in [0, 16)
+    unsigned long long lo = (unsigned long long)(r * 1152921504606846976.0);  // 2^60; bits below 2^-60 are dropped
     long long hi = (long long)h;
+    if (x < 0.0) {  // 128-bit two's-complement negation of the magnitude
+        lo = ~lo + 1ull;
+        hi = ~hi + (lo == 0ull ? 1 : 0);
+    }
     const unsigned long long old = atomicAdd(p, lo);
     if (old + lo < old) hi += 1;
     if (hi != 0) atomicAdd(p + 1, (unsigned long long)hi);
@@ -715,12 +720,7 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
     }
     consumer_sync();
     const int ch0 = cb0 + cg * RC;
-    T bias[RC], s[RC], q[RC];
-#pragma unroll
-    for (int r = 0; r < RC; ++r) {
-        bias[r] = (FWD && a.bias != nullptr) ? a.bias[ch0 + r] : T(0);
-        s[r] = q[r] = T(0);
-    }
+    __shared__ double red[CP_CONSUMERS / 32][2 * RC];
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
@@ -728,9 +728,11 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
         const int xo = pc.active ? 4 * x : 0;  // lanes past the end of the tensor read the tile's first pixels (never stored)
         T acc[RC][4];
 #pragma unroll
-        for (int r = 0; r < RC; ++r)
+        for (int r = 0; r < RC; ++r) {
+            const T b = (FWD && a.bias != nullptr) ? __ldg(a.bias + ch0 + r) : T(0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[r][j] = bias[r];
+            for (int j = 0; j < 4; ++j) acc[r][j] = b;
+        }
         for (int chunk = 0; chunk < nchunk; ++chunk) {
             mbar_wait(full + slot, phase);
             const T *st = stages + (size_t)slot * stage_elems;
@@ -760,6 +762,11 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
             if (lane == 0) mbar_arrive(empty + slot);
             if (++slot == S) slot = 0, phase ^= 1u;
         }
+        // per-TILE statistics (not carried across tiles in registers: the main loop keeps its registers, and a tile's partial
+        // sums do not depend on how tiles are spread over CTAs)
+        T s[RC], q[RC];
+#pragma unroll
+        for (int r = 0; r < RC; ++r) s[r] = q[r] = T(0);
         if (pc.active) {
             const int64_t off_out = ((int64_t)pc.n * a.CB + ch0) * a.HW + pc.rem;
 #pragma unroll
@@ -771,29 +778,28 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
             }
             if constexpr (EPI != EPI_NONE) stats_accumulate<T, RC, EPI>(a, acc, off_out, tout, CT, cg * RC, s, q);
         }
-    }
-    if constexpr (EPI != EPI_NONE) {
-        // CTA-level sums -> exact accumulators (same scheme as stats_epilogue, 8 consumer warps)
-        __shared__ double red[CP_CONSUMERS / 32][2 * RC];
-        T v[2 * RC];
+        if constexpr (EPI != EPI_NONE) {
+            T v[2 * RC];
 #pragma unroll
-        for (int r = 0; r < RC; ++r) v[r] = s[r], v[RC + r] = q[r];
-        int idx;
-        const T t = warp_multi_sum<T, 2 * RC>(v, lane, idx);
-        constexpr int REP = 32 / (2 * RC);
-        if ((lane & (REP - 1)) == 0) red[warp][idx] = (double)t;
-        consumer_sync();
-        if (tid < 2 * CT) {
-            const int g = tid / (2 * RC), i = tid % (2 * RC), which = i / RC, r = i % RC;
-            const int wpg = PGT / 32;  // warps per channel group
-            double tot = 0.0;
-            for (int w = 0; w < wpg; ++w) tot += red[g * wpg + w][i];
-            const int ch = cb0 + g * RC + r;
-            const int rep = blockIdx.x % ACC_R;
-            acc128_add(a.acc_out + (((int64_t)rep * a.CB + ch) * 2 + which) * 2, tot, a.flag);
+            for (int r = 0; r < RC; ++r) v[r] = s[r], v[RC + r] = q[r];
+            int idx;
+            const T t = warp_multi_sum<T, 2 * RC>(v, lane, idx);
+            constexpr int REP = 32 / (2 * RC);
+            if ((lane & (REP - 1)) == 0) red[warp][idx] = (double)t;
+            consumer_sync();
+            if (tid < 2 * CT) {
+                const int g = tid / (2 * RC), i = tid % (2 * RC), which = i / RC, r = i % RC;
+                const int wpg = PGT / 32;  // warps per channel group
+                double tot = 0.0;
+                for (int w = 0; w < wpg; ++w) tot += red[g * wpg + w][i];
+                const int ch = cb0 + g * RC + r;
+                const int rep = tile % ACC_R;
+                acc128_add(a.acc_out + (((int64_t)rep * a.CB + ch) * 2 + which) * 2, tot, a.flag);
+            }
+            consumer_sync();
         }
-        stats_exchange<T, true>(a, tid, CP_CONSUMERS);
     }
+    if constexpr (EPI != EPI_NONE) stats_exchange<T, true>(a, tid, CP_CONSUMERS);
 }
 
 // BatchNorm-backward sums of the TOP layer (g = the cotangent handed to the VJP, z = z_L): same epilogue, no convolution.

@@ -197,7 +197,7 @@ def test_exact_accumulator_is_exact_and_order_independent():
                         torch.tensor([2.0 ** -40, -3.5, 7.25], dtype=torch.float64))),
              torch.rand(n, generator=g, dtype=torch.float64) * 2.0 ** -30 - 2.0 ** -31]
     for v in cases:
-        want = math.fsum(math.floor(x * 2.0 ** 60) * 2.0 ** -60 for x in v.tolist()) if float(v.abs().max()) < 1.0 else None
+        want = math.fsum(math.trunc(x * 2.0 ** 60) * 2.0 ** -60 for x in v.tolist()) if float(v.abs().max()) < 1.0 else None
         vd = v.cuda()
         got = []
         for _ in range(3):
@@ -205,7 +205,7 @@ def test_exact_accumulator_is_exact_and_order_independent():
             got.append(float(out.item()))
         assert got[0] == got[1] == got[2]
         exact = math.fsum(v.tolist())
-        if want is not None:  # terms finer than the 2^-60 resolution are truncated toward -inf, deterministically; the read-back
+        if want is not None:  # terms finer than the 2^-60 resolution are truncated toward zero, deterministically; the read-back
             assert abs(got[0] - want) <= 8 * math.ulp(want), (got[0], want)  # rounds each of the 4 replicas to double once
         else:
             assert abs(got[0] - exact) <= v.numel() * 2.0 ** -60 + 4 * math.ulp(exact), (got[0], exact)
