@@ -28,6 +28,12 @@
 //     epilogue -- and a weight-gradient kernel (pixels are the reduction dimension: per-CTA register tiles of
 //     16 x 32 (c_out x c_in*tap) accumulated over a grid-stride loop of 128-pixel chunks staged in shared memory,
 //     per-CTA partials combined in a fixed order by one final kernel that can add  coef * gradient  straight into mu).
+//
+// Measured dead ends (kept out of the code): a 64-register weight-gradient kernel so that it co-resides with the data-gradient
+// CTA (spills: 296 vs 287 us per adjoint stage); folding the producer warp into consumer warp 0 to fit two pipelined CTAs per SM
+// at 128 registers (warp 0 stalls on the slowest warp every chunk: 147 vs 107 us per evaluation on block 2).
+// Tuning knobs (environment, read once; the defaults are the measured best): PNODE_CONV_PIPE (0: direct-load kernels only),
+// PNODE_PIPE_RC / _STAGES / _CTAS / _SMEM_KB, PNODE_CONV_RC / _OCC (direct kernel), PNODE_WGRAD_OCC / _STREAM, PNODE_CONV_PDL.
 #include <math.h>
 #include <stdlib.h>
 
