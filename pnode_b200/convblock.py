@@ -179,6 +179,18 @@ class ConvBlockCallbacks(Callbacks):
             self._saved_bytes = 0
             self._keep = bool(keep)
 
+    def mark(self):
+        super().mark()
+        self._saved_mark = set(self._saved.keys()) if self.native else set()
+
+    def rollback(self):
+        """A rejected adaptive attempt: forget the activation sets its stage evaluations kept."""
+        super().rollback()
+        if self.native:
+            for k in [k for k in self._saved if k not in getattr(self, "_saved_mark", set())]:
+                del self._saved[k]
+                self._saved_bytes -= self._act_bytes
+
     def _act_for(self, u):
         """Activation buffer for a forward evaluation at u: a kept one while the budget lasts, else the shared one."""
         if not self._keep or self._saved_bytes + self._act_bytes > self._save_budget:

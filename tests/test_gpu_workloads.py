@@ -223,6 +223,36 @@ def test_config4_evaluator_choice_and_library_path():
     _compare(res[0], res[1], 1e-9, per_param=False)
 
 
+def test_config4_adaptive_dopri5_with_rejections_matches_stock_module_path():
+    """The conv-block evaluator under the adaptive controller (dopri5, tight tolerance, a too-large first step so that attempts
+    are rejected): same accept/reject sequence, trajectory and gradients as the stock module through autograd; activation sets
+    of rejected attempts are dropped."""
+    from pnode import petsc_adjoint
+
+    C, HW, B = 16, 8, 8
+    func = OdeConvBlock(C, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(B, C, HW, HW, generator=g, dtype=torch.float64)
+    gout = torch.randn(2, B, C, HW, HW, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    res = []
+    for extra in (["-pnode_convblock_native", "1"], ["-pnode_fused", "0"]):
+        Options.clear_all()
+        Options.insert_args(["-ts_rtol", "1e-7", "-ts_atol", "1e-7"] + extra)
+        f = copy.deepcopy(func).cuda()
+        ode = petsc_adjoint.ODEPetsc()
+        ode.setupTS(u0.cuda(), f, step_size=1.0, method="dopri5", enable_adjoint=True)
+        y0 = u0.cuda().clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t.cuda())
+        (out * gout.cuda()).sum().backward()
+        res.append((out.detach(), y0.grad, [p.grad for p in f.parameters()], ode, f))
+    a, b = res
+    la, lb = a[3]._loop.attempts, b[3]._loop.attempts
+    assert [x[2] for x in la] == [x[2] for x in lb] and any(not x[2] for x in la) and a[3]._loop.steps >= 2
+    assert a[3]._cb_im.native and len(a[3]._cb_im._saved) <= 6 * a[3]._loop.steps + 1
+    _compare(a, b, 1e-8, per_param=False)
+
+
 def test_config4_fused_rhs_equals_stock_module_path():
     """The conv-block evaluator vs the same module driven through torch autograd (-pnode_fused 0), both on the GPU."""
     from pnode import petsc_adjoint
