@@ -591,11 +591,15 @@ class GenericTS:
             if sc.fsal and i == s - 1:
                 continue
             later = [j for j in range(i + 1, s) if sc.A[j][i] != 0.0 and vu[j] is not None]
-            w = torch.empty_like(lam)
-            if sc.b[i] != 0.0:
+            if sc.b[i] != 0.0 and not later:
+                w = lam  # last stage: w = lambda itself (the VJP only reads it): no copy
+                coef[i] = h * sc.b[i]
+            elif sc.b[i] != 0.0:
+                w = torch.empty_like(lam)
                 ops.lincomb(w, lam, 1.0, [vu[j] for j in later], [sc.A[j][i] / sc.b[i] * coef[j] for j in later])
                 coef[i] = h * sc.b[i]
             else:
+                w = torch.empty_like(lam)
                 ops.lincomb(w, None, 0.0, [vu[j] for j in later], [sc.A[j][i] * coef[j] for j in later])
                 coef[i] = h
             if hasattr(cb, "vjp_accumulate"):  # RHS evaluator that adds coef * Jp^T w into mu itself
