@@ -75,13 +75,14 @@ class Callbacks:
     def f(self, t, u, keep=False):
         """evalRHSFunction (petsc_adjoint.py:393-405): t is handed over as a python float."""
         self.nfe += 1
-        if keep and self._reuse and u.is_cuda and self._graph_bytes < self._graph_budget:
-            before = torch.cuda.memory_allocated(u.device)
+        if keep and self._reuse and self._graph_bytes < self._graph_budget:
+            before = torch.cuda.memory_allocated(u.device) if u.is_cuda else 0
             with torch.enable_grad():
                 x = u.detach().view(self.tensor_size).requires_grad_(True)
                 out = self.func(t, x)
             if isinstance(out, torch.Tensor) and out.requires_grad:
-                nbytes = max(torch.cuda.memory_allocated(u.device) - before, 0)
+                # what the kept graph holds: measured on the device; on the host-logic test double a nominal estimate
+                nbytes = max(torch.cuda.memory_allocated(u.device) - before, 0) if u.is_cuda else 4 * out.numel() * out.element_size()
                 self._graphs[u.data_ptr()] = (u, u._version, self._pversions(), x, out, nbytes, float(t))
                 self._graph_bytes += nbytes
             flat = out.detach().reshape(-1)

@@ -245,3 +245,115 @@ def test_mass_matrix_dae_theta_methods(monkeypatch, method):
     ode.setupTS(u0, f2, step_size=0.01, method=method, implicit_form=True, mass=M, enable_adjoint=False)
     pert = (ode.odeint(u0, t) * gout).sum().item()
     assert (pert - base) / 1e-6 == pytest.approx(p[2][0].item(), rel=1e-4)
+
+
+def _run_product(monkeypatch, argv, setup_kw, funcs, u0, t, gout, step, twice=False):
+    pa = patch_cpu(monkeypatch)
+    Options.clear_all()
+    Options.insert_args(argv)
+    fs = [copy.deepcopy(f) for f in funcs]
+    kw = dict(setup_kw)
+    if len(fs) == 2:
+        kw["func2"] = fs[1]
+    ode = pa.ODEPetsc()
+    ode.setupTS(u0, fs[0], step_size=step, enable_adjoint=True, **kw)
+    outs = []
+    for _ in range(2 if twice else 1):
+        for f in fs:
+            f.zero_grad(set_to_none=True)
+        y0 = u0.clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t)
+        (out * gout).sum().backward()
+        outs.append((out.detach().clone(), y0.grad.clone(), [p.grad.clone() for f in fs for p in f.parameters()], ode, fs))
+    return outs
+
+
+def test_adjoint_reuses_the_forward_stage_graphs(monkeypatch):
+    """Stage evaluations keep their autograd graph; the adjoint stage at the same point differentiates it instead of
+    re-evaluating the module: same bits as the re-evaluating path (-pnode_reuse_graph 0), func.nfe still counts the reference's
+    calls, graphs of rejected adaptive attempts are dropped, and a touched parameter invalidates what was kept."""
+    func = TimeMLP(d=6, hidden=16)
+    g = torch.Generator().manual_seed(5)
+    u0 = torch.randn(50, 6, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.4, 1.0], dtype=torch.float64)
+    gout = torch.randn(3, 50, 6, generator=g, dtype=torch.float64)
+    argv = ["-ts_rtol", "1e-6", "-ts_atol", "1e-6"]
+    (a,) = _run_product(monkeypatch, argv, dict(method="dopri5"), [func], u0, t, gout, 0.3)
+    (b,) = _run_product(monkeypatch, argv + ["-pnode_reuse_graph", "0"], dict(method="dopri5"), [func], u0, t, gout, 0.3)
+    cb_a, cb_b = a[3]._cb_ex, b[3]._cb_ex
+    loop = a[3]._loop
+    assert any(not x[2] for x in loop.attempts), "needs a rejected attempt"
+    # dopri5: 6 adjoint stages per accepted step; the first stage of a step that inherited its slope from the previous step (FSAL)
+    # was never evaluated at that step's own state tensor, so its adjoint stage re-evaluates
+    carried = sum(1 for k in range(1, len(loop.attempts)) if loop.attempts[k][2] and loop.attempts[k - 1][2])
+    assert cb_a.reused_graphs == 6 * loop.steps - carried and cb_b.reused_graphs == 0
+    assert len(cb_a._graphs) <= 7 * loop.steps  # nothing kept from the rejected attempts
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and all(torch.equal(x, y) for x, y in zip(a[2], b[2]))
+    assert cb_a.nvjp == cb_b.nvjp and cb_b.nfe == cb_a.nfe  # the engine's own counters do not depend on the reuse
+    # a parameter modified between the forward and the backward invalidates the kept graphs (version counters)
+    pa = patch_cpu(monkeypatch)
+    Options.clear_all()
+    Options.insert_args(["-ts_adapt_type", "none"])
+    f = copy.deepcopy(func)
+    ode = pa.ODEPetsc()
+    ode.setupTS(u0, f, step_size=0.2, method="rk4", enable_adjoint=True)
+    y0 = u0.clone().requires_grad_(True)
+    out = ode.odeint_adjoint(y0, t)
+    with torch.no_grad():
+        next(f.parameters()).mul_(1.0)
+    (out * gout).sum().backward()
+    assert ode._cb_ex.reused_graphs == 0
+
+
+def test_module_with_forward_side_effects_is_re_evaluated(monkeypatch):
+    class Noisy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4, 4).double()
+            self.bn = torch.nn.BatchNorm1d(4).double()
+
+        def forward(self, t, y):
+            return self.bn(self.lin(y))
+
+    g = torch.Generator().manual_seed(1)
+    u0 = torch.randn(8, 4, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.2], dtype=torch.float64)
+    gout = torch.randn(2, 8, 4, generator=g, dtype=torch.float64)
+    (a,) = _run_product(monkeypatch, ["-ts_adapt_type", "none"], dict(method="rk4"), [Noisy()], u0, t, gout, 0.1)
+    assert a[3]._cb_ex.reused_graphs == 0
+    assert int(a[4][0].bn.num_batches_tracked) == 16  # 2 steps x 4 stages, forward + the adjoint's re-evaluation
+
+
+def test_fixed_jacobian_keeps_the_factorisation_across_solves(monkeypatch):
+    """fixed_jacobian=True (documented: constant across ODE solves): the block inverse survives odeint calls and setupTS calls
+    until a parameter of the implicit function is touched; without the flag it is rebuilt per solve like the reference."""
+    class Lin(torch.nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            gg = torch.Generator().manual_seed(2)
+            self.A = torch.nn.Parameter(-torch.eye(n, dtype=torch.float64) + 0.1 * torch.randn(n, n, generator=gg, dtype=torch.float64))
+
+        def forward(self, t, y):
+            return y @ self.A.T
+
+    n, B = 5, 6
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.randn(B, n, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 0.2], dtype=torch.float64)
+    gout = torch.randn(2, B, n, generator=g, dtype=torch.float64)
+    f_im, f_ex = Lin(n), TimeMLP(d=n, hidden=8)
+    argv = ["-ts_adapt_type", "none", "-snes_type", "ksponly"]
+    kw = dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch")
+    a1, a2 = _run_product(monkeypatch, argv, dict(kw, fixed_jacobian=True), [f_im, f_ex], u0, t, gout, 0.1, twice=True)
+    ode = a2[3]
+    inv = dict(ode._imp._inv)
+    assert len(inv) >= 1 and all(torch.equal(x, y) for x, y in zip(a1[2], a2[2])) and torch.equal(a1[0], a2[0])
+    ode.setupTS(u0, a2[4][0], step_size=0.1, enable_adjoint=True, func2=a2[4][1], **dict(kw, fixed_jacobian=True))
+    ode.odeint_adjoint(u0.clone().requires_grad_(True), t)
+    assert all(ode._imp._inv[k] is v for k, v in inv.items()), "rebuilt although nothing changed"
+    with torch.no_grad():
+        a2[4][0].A.mul_(1.0)
+    ode.odeint_adjoint(u0.clone().requires_grad_(True), t)
+    assert all(ode._imp._inv[k] is not v for k, v in inv.items()), "kept although a parameter was touched"
+    b1, b2 = _run_product(monkeypatch, argv, kw, [f_im, f_ex], u0, t, gout, 0.1, twice=True)
+    assert torch.equal(b1[0], a1[0]) and all(torch.equal(x, y) for x, y in zip(b1[2], a1[2]))
