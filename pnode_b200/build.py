@@ -10,7 +10,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["vecops.cu", "mlp_rk.cu", "cnf_rk.cu", "bn_relu.cu", "conv_block.cu"]
+# (source, object, extra flags): conv_block.cu is the long pole, so its fp32 and fp64 instantiations compile as two objects
+UNITS = [("vecops.cu", "vecops.o", []), ("mlp_rk.cu", "mlp_rk.o", []), ("cnf_rk.cu", "cnf_rk.o", []),
+         ("bn_relu.cu", "bn_relu.o", []), ("conv_block.cu", "conv_block_f32.o", ["-DPNODE_CB_PART=1"]),
+         ("conv_block.cu", "conv_block_f64.o", ["-DPNODE_CB_PART=2"])]
+SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "pnode_b200.h")]
 LIB = os.path.join(CSRC, "libpnode_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
@@ -20,9 +24,10 @@ def _mtime(path):
     return os.path.getmtime(path) if os.path.exists(path) else 0.0
 
 
-def _compile(nvcc, src, verbose):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+def _compile(nvcc, unit, verbose):
+    src, objname, extra = unit
+    obj = os.path.join(OBJ, objname)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
@@ -36,11 +41,11 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdr_t = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
     objs, todo = [], []
-    for src in SOURCES:
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    for unit in UNITS:
+        obj = os.path.join(OBJ, unit[1])
         objs.append(obj)
-        if force or _mtime(obj) < max(_mtime(os.path.join(CSRC, src)), hdr_t):
-            todo.append(src)
+        if force or _mtime(obj) < max(_mtime(os.path.join(CSRC, unit[0])), hdr_t):
+            todo.append(unit)
     if todo:
         with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
             list(ex.map(lambda s: _compile(nvcc, s, verbose), todo))

@@ -39,6 +39,12 @@
 
 #include <map>
 
+// The file is compiled twice, in parallel (pnode_b200/build.py): PNODE_CB_PART 1 = the fp32 instantiations + the C entry points,
+// 2 = the fp64 instantiations.  0 (default, e.g. a plain `nvcc -c`) = everything in one object.
+#ifndef PNODE_CB_PART
+#define PNODE_CB_PART 0
+#endif
+
 #include "common.cuh"
 
 namespace pnode {
@@ -1059,6 +1065,7 @@ __global__ void __launch_bounds__(256) grads_finalize_kernel(const GradArgs<T> a
     }
 }
 
+#if PNODE_CB_PART != 2
 // unit-test hook: every thread adds one value into ONE accumulator (all replicas used), then the total is read back
 __global__ void acc128_probe_kernel(const double *__restrict__ v, int64_t n, unsigned long long *acc, unsigned *flag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1067,6 +1074,7 @@ __global__ void acc128_probe_kernel(const double *__restrict__ v, int64_t n, uns
 __global__ void acc128_read_kernel(const unsigned long long *acc, const unsigned *flag, double *out) {
     out[0] = *flag != 0u ? NAN : acc128_read(acc, 1, 0, 0);
 }
+#endif
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
 struct CbPlan {
@@ -1544,8 +1552,56 @@ static int vjp_chain(const pnode_convblock_desc *d, const CbPlan &p, const Bufs<
 
 static bool cb_aligned(const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// one non-template entry per scalar type, so that the two types can live in two objects
+template <typename T>
+static int run_forward(const pnode_convblock_desc *desc, const CbPlan &p, const void *d_x, void *d_out, const void *d_base,
+                       double base_coef, double k_coef, void *d_k, void *d_act, cudaStream_t st) {
+    unsigned long long epoch = desc->epoch;
+    Bufs<T> b(d_act, nullptr, p);
+    int rc = forward_chain<T>(desc, p, b, static_cast<const T *>(d_x), epoch, st);
+    if (rc) return rc;
+    return act_out<T>(desc, p, b, static_cast<T *>(d_out), static_cast<const T *>(d_base), base_coef, k_coef, static_cast<T *>(d_k), st);
+}
+
+template <typename T>
+static int run_vjp(const pnode_convblock_desc *desc, const CbPlan &p, const void *d_x, const void *d_w, void *d_vu, void *d_grads,
+                   double coef, int accumulate, void *d_act, int act_valid, void *d_work, cudaStream_t st) {
+    unsigned long long epoch = desc->epoch;
+    Bufs<T> b(d_act, d_work, p);
+    if (!act_valid) {
+        int rc = forward_chain<T>(desc, p, b, static_cast<const T *>(d_x), epoch, st);
+        if (rc) return rc;
+    }
+    return vjp_chain<T>(desc, p, b, static_cast<const T *>(d_x), static_cast<const T *>(d_w), static_cast<T *>(d_vu),
+                        static_cast<T *>(d_grads), coef, accumulate, act_valid != 0, epoch, st);
+}
+
+int convblock_forward_f64(const pnode_convblock_desc *desc, const void *d_x, void *d_out, const void *d_base, double base_coef,
+                          double k_coef, void *d_k, void *d_act, void *stream);
+int convblock_vjp_f64(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads, double coef,
+                      int accumulate, void *d_act, int act_valid, void *d_work, void *stream);
+
+#if PNODE_CB_PART != 1
+int convblock_forward_f64(const pnode_convblock_desc *desc, const void *d_x, void *d_out, const void *d_base, double base_coef,
+                          double k_coef, void *d_k, void *d_act, void *stream) {
+    CbPlan p;
+    int rc = cb_plan(desc, p);
+    if (rc) return rc;
+    return run_forward<double>(desc, p, d_x, d_out, d_base, base_coef, k_coef, d_k, d_act, static_cast<cudaStream_t>(stream));
+}
+int convblock_vjp_f64(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads, double coef,
+                      int accumulate, void *d_act, int act_valid, void *d_work, void *stream) {
+    CbPlan p;
+    int rc = cb_plan(desc, p);
+    if (rc) return rc;
+    return run_vjp<double>(desc, p, d_x, d_w, d_vu, d_grads, coef, accumulate, d_act, act_valid, d_work,
+                           static_cast<cudaStream_t>(stream));
+}
+#endif
+
 }  // namespace pnode
 
+#if PNODE_CB_PART != 2
 using namespace pnode;
 
 extern "C" {
@@ -1589,20 +1645,9 @@ int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, v
     PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_out) && cb_aligned(d_base) && cb_aligned(d_k) && cb_aligned(d_act),
                   "pnode_convblock_forward: tensors must be 16-byte aligned");
     PNODE_REQUIRE(desc->layer[p.L - 1].cout == desc->layer[0].cin, "pnode_convblock_forward: an ODE right-hand side maps C -> C");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned long long epoch = desc->epoch;
-    if (desc->dtype == PNODE_F32) {
-        Bufs<float> b(d_act, nullptr, p);
-        rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), epoch, st);
-        if (rc) return rc;
-        return act_out<float>(desc, p, b, static_cast<float *>(d_out), static_cast<const float *>(d_base), base_coef, k_coef,
-                              static_cast<float *>(d_k), st);
-    }
-    Bufs<double> b(d_act, nullptr, p);
-    rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), epoch, st);
-    if (rc) return rc;
-    return act_out<double>(desc, p, b, static_cast<double *>(d_out), static_cast<const double *>(d_base), base_coef, k_coef,
-                           static_cast<double *>(d_k), st);
+    if (desc->dtype == PNODE_F32)
+        return run_forward<float>(desc, p, d_x, d_out, d_base, base_coef, k_coef, d_k, d_act, static_cast<cudaStream_t>(stream));
+    return convblock_forward_f64(desc, d_x, d_out, d_base, base_coef, k_coef, d_k, d_act, stream);
 }
 
 int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads,
@@ -1613,26 +1658,11 @@ int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const
     PNODE_REQUIRE(d_x && d_w && d_act && d_work && (d_vu || d_grads), "pnode_convblock_vjp: null argument");
     PNODE_REQUIRE(cb_aligned(d_x) && cb_aligned(d_w) && cb_aligned(d_vu) && cb_aligned(d_act) && cb_aligned(d_work),
                   "pnode_convblock_vjp: tensors must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned long long epoch = desc->epoch;
-    if (desc->dtype == PNODE_F32) {
-        Bufs<float> b(d_act, d_work, p);
-        if (!act_valid) {
-            rc = forward_chain<float>(desc, p, b, static_cast<const float *>(d_x), epoch, st);
-            if (rc) return rc;
-        }
-        return vjp_chain<float>(desc, p, b, static_cast<const float *>(d_x), static_cast<const float *>(d_w),
-                                static_cast<float *>(d_vu), static_cast<float *>(d_grads), coef, accumulate, act_valid != 0, epoch,
-                                st);
-    }
-    Bufs<double> b(d_act, d_work, p);
-    if (!act_valid) {
-        rc = forward_chain<double>(desc, p, b, static_cast<const double *>(d_x), epoch, st);
-        if (rc) return rc;
-    }
-    return vjp_chain<double>(desc, p, b, static_cast<const double *>(d_x), static_cast<const double *>(d_w),
-                             static_cast<double *>(d_vu), static_cast<double *>(d_grads), coef, accumulate, act_valid != 0, epoch,
-                             st);
+    if (desc->dtype == PNODE_F32)
+        return run_vjp<float>(desc, p, d_x, d_w, d_vu, d_grads, coef, accumulate, d_act, act_valid, d_work,
+                              static_cast<cudaStream_t>(stream));
+    return convblock_vjp_f64(desc, d_x, d_w, d_vu, d_grads, coef, accumulate, d_act, act_valid, d_work, stream);
 }
 
 }  // extern "C"
+#endif
