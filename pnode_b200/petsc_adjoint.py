@@ -222,7 +222,15 @@ class ODEPetsc(object):
 
     # ------------------------------------------------------------------------------------------------------------
     def _times(self, t):
-        return [float(x) for x in t.detach().cpu().to(dtype=torch.float64).reshape(-1)]
+        """Output times on the host (petsc_adjoint.py:811 `t.cpu()`).  A device->host read costs a stream sync, so the list is
+        kept while the caller hands in the SAME tensor object, unmodified (identity + version counter: holding the object keeps
+        its address from being recycled)."""
+        c = getattr(self, "_times_cache", None)
+        if c is not None and c[0] is t and c[1] == t._version:
+            return list(c[2])
+        times = [float(x) for x in t.detach().cpu().to(dtype=torch.float64).reshape(-1)]
+        self._times_cache = (t, t._version, tuple(times))
+        return times
 
     def _odeint_impl(self, u0, t):
         if self.tensor_size is None:
