@@ -64,3 +64,39 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_convblock_plan_runs_without_a_gpu():
+    """Host half of csrc/conv_block.cu (shape validation, buffer sizing, parameter layout) -- no kernel is launched."""
+    import ctypes as C
+
+    import torch
+
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _workloads import OdeConvBlock
+
+    lib = _lib.load()
+    for (N, Cc, H, W), dtype in (((256, 32, 32, 32), torch.float32), ((4, 16, 8, 8), torch.float64), ((256, 256, 4, 4), torch.float32)):
+        func = OdeConvBlock(Cc, dtype=dtype)
+        d = _lib.ConvBlockDesc()
+        d.nlayers, d.dtype, d.N, d.H, d.W = 5, (0 if dtype == torch.float32 else 1), N, H, W
+        for k in range(5):
+            conv, bn = getattr(func, "conv%d" % (k + 1)), getattr(func, "bn%d" % (k + 1))
+            l = d.layer[k]
+            l.cin, l.cout = conv.in_channels, conv.out_channels
+            l.kh, l.kw = conv.kernel_size
+            l.ph, l.pw = conv.padding
+            l.d_weight = l.d_bias = l.d_gamma = l.d_beta = 16  # non-null placeholders: the plan never dereferences them
+            l.eps, l.momentum = bn.eps, bn.momentum
+        assert lib.pnode_convblock_param_count(C.byref(d)) == sum(p.numel() for p in func.parameters())
+        esz = 4 if dtype == torch.float32 else 8
+        zbytes = sum(getattr(func, "conv%d" % (k + 1)).out_channels for k in range(5)) * N * H * W * esz
+        act, work = lib.pnode_convblock_act_bytes(C.byref(d)), lib.pnode_convblock_work_bytes(C.byref(d))
+        assert zbytes <= act <= zbytes + (1 << 20) and work >= zbytes  # z_1..z_L + statistics; g_k of every layer + partials
+    d.W = 12
+    assert lib.pnode_convblock_act_bytes(C.byref(d)) == -1 and b"power of two" in lib.pnode_last_error()
+    d.W = 4
+    d.layer[2].cin = 6
+    assert lib.pnode_convblock_act_bytes(C.byref(d)) == -1 and b"multiples of 4" in lib.pnode_last_error()
+    assert C.sizeof(_lib.ConvLayer) == 24 + 7 * 8 + 16 and C.sizeof(_lib.ConvBlockDesc) == 24 + 8 * C.sizeof(_lib.ConvLayer) + 32
