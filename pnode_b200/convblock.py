@@ -179,6 +179,12 @@ class ConvBlockCallbacks(Callbacks):
             self._saved_bytes = 0
             self._keep = bool(keep)
 
+    def release(self):
+        super().release()
+        if self.native:
+            self._saved.clear()
+            self._saved_bytes = 0
+
     def mark(self):
         super().mark()
         self._saved_mark = set(self._saved.keys()) if self.native else set()

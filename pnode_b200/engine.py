@@ -61,6 +61,13 @@ class Callbacks:
             self._graph_bytes = 0
             self._marks = []
 
+    def release(self):
+        """End of the adjoint sweep: nothing kept by the forward is needed any more (frees the graphs' activations now instead
+        of at the next forward solve)."""
+        self._graphs.clear()
+        self._graph_bytes = 0
+        self._marks = []
+
     def mark(self):
         """Remember the kept graphs so far: a rejected step attempt rolls back to here."""
         self._marks = list(self._graphs.keys())

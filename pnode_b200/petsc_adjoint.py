@@ -309,6 +309,10 @@ class ODEPetsc(object):
         for i in range(T - 1, 0, -1):
             lam = eng.adjoint_steps(self._cb_ex, self._cb_im, self._imp, loop.cur_sol_steps[i], lam, mu, np_im)
             self._ops.lincomb(lam, lam, 1.0, [grad[i - 1].reshape(-1)], [1.0])  # forcing (petsc_adjoint.py:938)
+        if not eng.traj:  # the whole trajectory has been consumed: drop what the forward kept for this sweep
+            for cb in (self._cb_ex, self._cb_im):
+                if cb is not None and hasattr(cb, "release"):
+                    cb.release()
         return lam, mu
 
 
