@@ -148,8 +148,11 @@ class KSImplicit(nn.Module):
     def __init__(self, dx, dtype=torch.float64):
         super().__init__()
         self.A = nn.Conv1d(1, 1, kernel_size=5, padding="same", padding_mode="circular", bias=False)
+        # the reference builds the stencil with torch.tensor(<python floats>) -- float32 -- and only then calls .double()
+        # (imex.py:20-36, KS.py:470): in a double-precision run the coefficients are the float32-ROUNDED values (pinned by
+        # tests/golden/ks_ref_fp64.pt)
         K = torch.tensor([[[-1.0 / dx ** 4, 4.0 / dx ** 4 - 1.0 / dx ** 2, -6.0 / dx ** 4 + 2.0 / dx ** 2,
-                            4.0 / dx ** 4 - 1.0 / dx ** 2, -1.0 / dx ** 4]]], dtype=dtype)
+                            4.0 / dx ** 4 - 1.0 / dx ** 2, -1.0 / dx ** 4]]], dtype=torch.float32).to(dtype)
         self.A.weight = nn.Parameter(K, requires_grad=False)
         self.nfe = 0
 
