@@ -289,6 +289,37 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
                             uint64_t epoch, void *stream);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * Tensor-core matrix products on SLICED operands (csrc/umma_gemm.cu): TMA-fed tcgen05.mma, accumulators in tensor
+ * memory.  They replace the library GEMMs the reference reaches through ATen for wide right-hand sides: the Linear
+ * layers of examples-sinode/KS/models/imex.py:40-70 (forward in evalRHSFunction, pnode/petsc_adjoint.py:393-412; the
+ * two backward products per layer inside RHSJacShell.multTranspose's autograd.grad, 52-82) and the batched solve
+ * X = R A^-1 of pnode/torch_linearsolve.py:25-35 (inverse-apply as one product).
+ *
+ * A sliced operand holds a row-major matrix [rows][k] as S slice matrices [S][rows][pitch] (pitch = k elements rounded
+ * up to 128 bytes) such that products of slices are exact on the tensor cores:
+ *   PNODE_SLICED_I8   fp64 source: x[r][c] = 2^exp[r] * sum_s q_s[r][c] * 2^-(6+7s), q_s int8, S = PNODE_I8_SLICES
+ *                     (Ozaki splitting: int8 x int8 -> int32 products are exact; 48 bits of every entry relative to
+ *                     its row maximum are kept)
+ *   PNODE_SLICED_TF32 fp32 source: x = hi + lo with hi = tf32(x), S = 2 (3xTF32: hi.hi + hi.lo + lo.hi)
+ * pnode_slice_rows slices x itself (operand row = row of x); pnode_slice_cols slices x^T (operand row = column of x,
+ * reduction over the rows of x) and can add coef * (column sums of x) into d_colsum (bias gradients).
+ * pnode_sliced_gemm:  C[m][n] (op)= mask( relu( alpha * sum_k A[m][k] B[n][k] + bias[n] ) ),  C row-major with leading
+ * dimension ldc, fp64 for I8 operands / fp32 for TF32; `accumulate` adds into C; mask (same type and layout as C,
+ * leading dimension ldmask) keeps the result where mask > 0 (ReLU backward).  d_a_exp / d_b_exp: the row exponents
+ * written by the slicing kernels (ignored for TF32).
+ * -------------------------------------------------------------------------------------------------------------- */
+#define PNODE_SLICED_I8 0
+#define PNODE_SLICED_TF32 1
+#define PNODE_I8_SLICES 7
+int64_t pnode_sliced_bytes(int kind, int rows, int k);
+int pnode_slice_rows(int kind, const void *d_x, int64_t ldx, int rows, int k, void *d_slices, int32_t *d_exp, void *stream);
+int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols, void *d_slices, int32_t *d_exp,
+                     void *d_colsum, double coef, void *stream);
+int pnode_sliced_gemm(int kind, const void *d_a, const int32_t *d_a_exp, const void *d_b, const int32_t *d_b_exp, int M,
+                      int N, int K, void *d_c, int64_t ldc, double alpha, const void *d_bias, int relu, const void *d_mask,
+                      int64_t ldmask, int accumulate, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): peak FMA issue rate of the CUDA-core pipe in the given dtype, used as the
  * compute-roofline denominator for the MLP kernels (MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).
  * Launches a register-resident FMA chain on every SM; *flops = 2 * FMAs executed.  Synchronous.

@@ -84,6 +84,10 @@ _SIGNATURES = {
                                           _vp, _vp, _i, _i, C.c_uint64, _vp]),
     "pnode_cnf_rk_adjoint_dp": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _i, _i, C.c_uint64, _vp]),
+    "pnode_sliced_bytes": (_i64, [_i, _i, _i]),
+    "pnode_slice_rows": (C.c_int, [_i, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "pnode_slice_cols": (C.c_int, [_i, _vp, _i64, _i, _i, _vp, _vp, _vp, _d, _vp]),
+    "pnode_sliced_gemm": (C.c_int, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _d, _vp, _i, _vp, _i64, _i, _vp]),
     "pnode_peak_fma": (C.c_int, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float)]),
     "pnode_tanh_probe": (C.c_int, [_vp, _vp, _i64, _i, _vp]),
     "pnode_acc128_probe": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),

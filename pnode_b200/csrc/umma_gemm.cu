@@ -1,0 +1,556 @@
+// Tensor-core matrix products for the wide right-hand sides (SINODE MLP, implicit-stage inverse apply, GEMM-sized conv
+// layers): TMA-fed tcgen05.mma with the accumulators in tensor memory, hand-written for sm_100a.
+//
+// The state is fp64 (reference: PETSc scalar type, tests/test_pnode.py:127-130) or fp32, and results must match the
+// reference to 1e-10 / 1e-4.  The 5th-generation tensor cores have no fp64 mode and TF32 alone is 1e-3, so every
+// operand is a SLICED matrix and a product is a short sum of exact slice products:
+//
+//   kind i8   (fp64):  x[r][k] = 2^e[r] * sum_s q_s[r][k] 2^-(6+7s),  q_s int8 in [-64, 64], S = 7 slices (48 bits).
+//              A.B^T = 2^(ea+eb) * sum_{d<S} 2^-(12+7d) * sum_{i+j=d} (q^A_i . q^B_j)      [Ozaki splitting]
+//              every slice product is an EXACT int32 dot product (tcgen05.mma kind::i8), one TMEM accumulator per
+//              diagonal d; the fp64 combination happens once, in the epilogue.  Dropped terms are < 2^-47 of
+//              (row max)(column max) per term.
+//   kind tf32 (fp32):  x = hi + lo, hi = tf32(x), lo = x - hi;  A.B^T = hi.hi + hi.lo + lo.hi  (3xTF32, fp32 accumulate
+//              in TMEM), relative error ~2^-21 per product.
+//
+// One CTA computes a 128 x BN tile of C: warp 4 (one lane) issues the TMA loads of ALL slices of the current K block
+// into a ring of shared-memory stages (3-d tensor maps {K, rows, slice}, hardware swizzle, zero fill outside the
+// matrix), warp 5 (one lane) issues the tcgen05.mma of every slice pair i+j<S against those tiles -- each slice tile is
+// read from shared memory S times but fetched from L2 once -- and warps 0-3 drain the accumulators with tcgen05.ld,
+// combine / scale / add bias / ReLU / mask / accumulate and store.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pnode {
+namespace umma {
+
+constexpr int KIND_I8 = PNODE_SLICED_I8, KIND_TF32 = PNODE_SLICED_TF32;
+
+template <int KIND>
+struct Cfg;
+template <>
+struct Cfg<KIND_I8> {
+    static constexpr int S = PNODE_I8_SLICES, BN = 64, KB = 64, STAGES = 2, NACC = PNODE_I8_SLICES, ELEM = 1;
+    using Out = double;
+};
+template <>
+struct Cfg<KIND_TF32> {
+    static constexpr int S = 2, BN = 64, KB = 128, STAGES = 4, NACC = 1, ELEM = 4;
+    using Out = float;
+};
+
+struct Epilogue {
+    void *C;
+    long long ldc;
+    const int *ea, *eb;  // row exponents of A / of B (i8 only)
+    double alpha;
+    const void *bias;    // [N] added after alpha (NULL: none)
+    const void *mask;    // [M][ldmask]: result kept where mask > 0, else 0 (ReLU backward); NULL: none
+    long long ldmask;
+    int relu, accumulate;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps after ~2 s instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (KIND == KIND_I8) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(
+                         tmem_d),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                     : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major tile whose rows are KB bytes (= the swizzle span) and dense:
+// 8-row groups are 8*KB bytes apart (SBO); LBO is unused for swizzled K-major operands; version 1 = sm_100.
+template <int KB>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * KB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(KB == 128 ? 2 : (KB == 64 ? 4 : 6)) << 61;
+    return d;
+}
+
+// Instruction descriptor (dense, K-major A and B, M = 128, N = BN).
+template <int KIND, int BN>
+__device__ __forceinline__ constexpr uint32_t instr_desc() {
+    uint32_t fmt = KIND == KIND_I8 ? ((2u << 4) | (1u << 7) | (1u << 10))    // D = S32, A = B = signed 8 bit
+                                   : ((1u << 4) | (2u << 7) | (2u << 10));   // D = F32, A = B = TF32
+    return fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ double pow2(int e) {  // 2^e, |e| < 1000
+    return __longlong_as_double((long long)(1023 + e) << 52);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(192, 1)
+    umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                     int K, Epilogue ep) {
+    using C = Cfg<KIND>;
+    using Out = typename C::Out;
+    constexpr int S = C::S, BN = C::BN, KB = C::KB, STAGES = C::STAGES;
+    constexpr int A_TILE = 128 * KB, B_TILE = BN * KB, STAGE_BYTES = S * (A_TILE + B_TILE);
+    constexpr int TMEM_COLS = (C::NACC * BN <= 32) ? 32 : (C::NACC * BN <= 64) ? 64 : (C::NACC * BN <= 128) ? 128
+                              : (C::NACC * BN <= 256) ? 256 : 512;
+    static_assert(C::NACC * BN <= 512, "accumulators exceed tensor memory");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *accfull = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
+    const int num_kb = (K * C::ELEM + KB - 1) / KB;
+
+    if (threadIdx.x == 128) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (threadIdx.x == 128) {
+        // ---- TMA producer: all slices of K block kb into stage kb % STAGES ----
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int st = kb % STAGES, it = kb / STAGES;
+            if (kb >= STAGES) mbar_wait(&empty[st], (it - 1) & 1);
+            uint8_t *sa = smem + st * STAGE_BYTES, *sb = sa + S * A_TILE;
+            mbar_expect_tx(&full[st], STAGE_BYTES);
+            const int k0 = kb * (KB / C::ELEM);
+#pragma unroll
+            for (int s = 0; s < S; ++s) tma_load_3d(sa + s * A_TILE, &map_a, &full[st], k0, m0, s);
+#pragma unroll
+            for (int s = 0; s < S; ++s) tma_load_3d(sb + s * B_TILE, &map_b, &full[st], k0, n0, s);
+        }
+    } else if (threadIdx.x == 160) {
+        // ---- MMA issuer: every slice pair i + j < S of this K block ----
+        constexpr uint32_t idesc = instr_desc<KIND, BN>();
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int st = kb % STAGES, it = kb / STAGES;
+            mbar_wait(&full[st], it & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + st * STAGE_BYTES), sb = sa + S * A_TILE;
+#pragma unroll
+            for (int k = 0; k < KB / 32; ++k) {
+#pragma unroll
+                for (int d = 0; d < S; ++d) {
+#pragma unroll
+                    for (int i = 0; i <= d; ++i) {
+                        const int j = d - i;
+                        const uint64_t ad = smem_desc<KB>(sa + i * A_TILE) + (uint64_t)(k * 2);
+                        const uint64_t bd = smem_desc<KB>(sb + j * B_TILE) + (uint64_t)(k * 2);
+                        const int acc = (KIND == KIND_I8) ? d : 0;
+                        const bool first = (kb == 0) && (k == 0) && (i == 0) && (KIND == KIND_I8 || d == 0);
+                        tc_mma<KIND>(tmem_base + acc * BN, ad, bd, idesc, first ? 0u : 1u);
+                    }
+                }
+            }
+            tc_commit(&empty[st]);  // frees the stage when these MMAs have read it
+        }
+        tc_commit(accfull);
+    } else if (warp < 4) {
+        // ---- epilogue: thread = one row of the tile (TMEM lane), 8 columns at a time ----
+        mbar_wait(accfull, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        double srow = 1.0;
+        if constexpr (KIND == KIND_I8) srow = (m < M) ? pow2(ep.ea[m]) : 0.0;
+        Out *crow = reinterpret_cast<Out *>(ep.C) + (long long)m * ep.ldc;
+        const Out *mrow = ep.mask ? reinterpret_cast<const Out *>(ep.mask) + (long long)m * ep.ldmask : nullptr;
+        for (int c0 = 0; c0 < BN; c0 += 8) {
+            double v[8];
+            if constexpr (KIND == KIND_I8) {
+                uint32_t r[S][8];
+#pragma unroll
+                for (int d = 0; d < S; ++d) tc_ld8(trow + d * BN + c0, r[d]);
+                tc_wait_ld();
+                constexpr int NH = S < 4 ? S : 4;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    long long hi = 0, lo = 0;
+#pragma unroll
+                    for (int d = 0; d < NH; ++d) hi = hi * 128 + (long long)(int)r[d][q];
+#pragma unroll
+                    for (int d = NH; d < S; ++d) lo = lo * 128 + (long long)(int)r[d][q];
+                    double x = (double)hi * pow2(-(12 + 7 * (NH - 1)));
+                    if (S > NH) x = fma((double)lo, pow2(-(12 + 7 * (S - 1))), x);
+                    v[q] = x;
+                }
+            } else {
+                uint32_t r[8];
+                tc_ld8(trow + c0, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (double)__uint_as_float(r[q]);
+            }
+            if (m < M) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = n0 + c0 + q;
+                    if (n < N) {
+                        double x = v[q];
+                        if constexpr (KIND == KIND_I8) x = x * srow * pow2(ep.eb[n]);
+                        x *= ep.alpha;
+                        if (ep.bias) x += (double)reinterpret_cast<const Out *>(ep.bias)[n];
+                        if (ep.relu) x = x > 0.0 ? x : 0.0;
+                        if (mrow) x = ((double)mrow[n] > 0.0) ? x : 0.0;
+                        if (ep.accumulate) x += (double)crow[n];
+                        crow[n] = (Out)x;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- operand slicing ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int exponent_above(double amax) {  // smallest e with amax < 2^e (0 for amax == 0)
+    if (!(amax > 0.0)) return 0;
+    int e = (int)((__double_as_longlong(amax) >> 52) & 0x7ff) - 1022;
+    return e < -960 ? -960 : (e > 960 ? 960 : e);
+}
+
+template <typename T>
+__device__ __forceinline__ T block_max(T v, T *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmax(r, sh[w]);
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ float tf32_round(float x) {  // round to nearest even on the 10-bit mantissa
+    uint32_t u = __float_as_uint(x);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0xfffu + ((u >> 13) & 1u);
+    return __uint_as_float(u & 0xffffe000u);
+}
+
+// Row slicing: operand row r = x[r][0..k).  One block per row.  out: [S][rows][pitch bytes].
+template <int KIND>
+__global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int k, uint8_t *out, long long pitch,
+                                  int *exps) {
+    using C = Cfg<KIND>;
+    const int r = blockIdx.x;
+    const long long slice_stride = (long long)rows * pitch;
+    if constexpr (KIND == KIND_I8) {
+        __shared__ double sh[8];
+        const double *x = reinterpret_cast<const double *>(xin) + (long long)r * ldx;
+        double amax = 0.0;
+        for (int c = threadIdx.x; c < k; c += blockDim.x) amax = fmax(amax, fabs(x[c]));
+        amax = block_max(amax, sh);
+        const int e = exponent_above(amax);
+        if (threadIdx.x == 0) exps[r] = e;
+        const double sc = pow2(6 - e);
+        int8_t *o = reinterpret_cast<int8_t *>(out) + (long long)r * pitch;
+        for (int c = threadIdx.x * 4; c < k; c += blockDim.x * 4) {
+            double res[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res[q] = (c + q < k) ? x[c + q] * sc : 0.0;
+#pragma unroll
+            for (int s = 0; s < C::S; ++s) {
+                uint32_t pack = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double qd = rint(res[q]);
+                    res[q] = (res[q] - qd) * 128.0;
+                    pack |= ((uint32_t)(int)qd & 0xffu) << (8 * q);
+                }
+                *reinterpret_cast<uint32_t *>(o + s * slice_stride + c) = pack;  // pitch is a multiple of 128: in bounds
+            }
+        }
+    } else {
+        const float *x = reinterpret_cast<const float *>(xin) + (long long)r * ldx;
+        float *o = reinterpret_cast<float *>(out + (long long)r * pitch);
+        float *o1 = reinterpret_cast<float *>(out + slice_stride + (long long)r * pitch);
+        for (int c = threadIdx.x; c < k; c += blockDim.x) {
+            const float v = x[c], hi = tf32_round(v);
+            o[c] = hi;
+            o1[c] = v - hi;
+        }
+    }
+}
+
+// Column slicing: operand row c = x[0..rows)[c] (the operand is x^T, reduction over the rows of x).
+// Block = 256 threads = 32 columns x 8 row groups.  out: [S][cols][pitch bytes].  Optionally colsum[c] += coef*sum_r x[r][c].
+template <int KIND>
+__global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int cols, uint8_t *out, long long pitch,
+                                  int *exps, void *colsum, double coef) {
+    using C = Cfg<KIND>;
+    const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const long long slice_stride = (long long)cols * pitch;
+    const int rows_per = (((rows + 7) / 8) + 3) / 4 * 4;  // multiple of 4: packed 4-byte stores along the row index
+    const int rbeg = rg * rows_per, rend = min(rows, rbeg + rows_per);
+    __shared__ double sh_max[8][33], sh_sum[8][33];
+    if constexpr (KIND == KIND_I8) {
+        const double *x = reinterpret_cast<const double *>(xin);
+        double amax = 0.0, sum = 0.0;
+        if (c < cols)
+            for (int r = rbeg; r < rend; ++r) {
+                const double v = x[(long long)r * ldx + c];
+                amax = fmax(amax, fabs(v));
+                sum += v;
+            }
+        sh_max[rg][cl] = amax;
+        sh_sum[rg][cl] = sum;
+        __syncthreads();
+        amax = 0.0;
+        sum = 0.0;
+        for (int g = 0; g < 8; ++g) {
+            amax = fmax(amax, sh_max[g][cl]);
+            sum += sh_sum[g][cl];
+        }
+        if (c >= cols) return;
+        const int e = exponent_above(amax);
+        if (rg == 0) {
+            exps[c] = e;
+            if (colsum) reinterpret_cast<double *>(colsum)[c] += coef * sum;
+        }
+        const double sc = pow2(6 - e);
+        int8_t *o = reinterpret_cast<int8_t *>(out) + (long long)c * pitch;
+        for (int r = rbeg; r < rend; r += 4) {
+            double res[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res[q] = (r + q < rend) ? x[(long long)(r + q) * ldx + c] * sc : 0.0;
+#pragma unroll
+            for (int s = 0; s < C::S; ++s) {
+                uint32_t pack = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double qd = rint(res[q]);
+                    res[q] = (res[q] - qd) * 128.0;
+                    pack |= ((uint32_t)(int)qd & 0xffu) << (8 * q);
+                }
+                *reinterpret_cast<uint32_t *>(o + s * slice_stride + r) = pack;  // r % 4 == 0, pitch % 128 == 0: in bounds
+            }
+        }
+    } else {
+        const float *x = reinterpret_cast<const float *>(xin);
+        double sum = 0.0;
+        if (c < cols) {
+            float *o = reinterpret_cast<float *>(out + (long long)c * pitch);
+            float *o1 = reinterpret_cast<float *>(out + slice_stride + (long long)c * pitch);
+            for (int r = rbeg; r < rend; ++r) {
+                const float v = x[(long long)r * ldx + c], hi = tf32_round(v);
+                o[r] = hi;
+                o1[r] = v - hi;
+                sum += (double)v;
+            }
+        }
+        sh_sum[rg][cl] = sum;
+        __syncthreads();
+        if (rg == 0 && c < cols && colsum) {
+            sum = 0.0;
+            for (int g = 0; g < 8; ++g) sum += sh_sum[g][cl];
+            reinterpret_cast<float *>(colsum)[c] += (float)(coef * sum);
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static inline long long pitch_bytes(int kind, int k) {
+    const long long b = (long long)k * (kind == KIND_I8 ? 1 : 4);
+    return (b + 127) / 128 * 128;
+}
+
+template <int KIND>
+static int make_map(CUtensorMap *map, const void *base, int rows, int k, int box_rows) {
+    using C = Cfg<KIND>;
+    EncodeTiledFn fn = encode_fn();
+    PNODE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const long long pitch = pitch_bytes(KIND, k);
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)C::S};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)(C::KB / C::ELEM), (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, KIND == KIND_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    C::KB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PNODE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d k=%d", (int)r, rows, k);
+    return 0;
+}
+
+template <int KIND>
+static int launch_gemm(const void *a, const void *b, int M, int N, int K, const Epilogue &ep, cudaStream_t stream) {
+    using C = Cfg<KIND>;
+    constexpr int STAGE_BYTES = C::S * (128 + C::BN) * C::KB;
+    constexpr int SMEM = C::STAGES * STAGE_BYTES + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        PNODE_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    CUtensorMap ma, mb;
+    if (int rc = make_map<KIND>(&ma, a, M, K, 128)) return rc;
+    if (int rc = make_map<KIND>(&mb, b, N, K, C::BN)) return rc;
+    dim3 grid((N + C::BN - 1) / C::BN, (M + 127) / 128);
+    umma_gemm_kernel<KIND><<<grid, 192, SMEM, stream>>>(ma, mb, M, N, K, ep);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gemm(int kind, const void *a, const int *ea, const void *b, const int *eb, int M, int N, int K, void *c,
+         long long ldc, double alpha, const void *bias, int relu, const void *mask, long long ldmask, int accumulate,
+         cudaStream_t stream) {
+    PNODE_REQUIRE(M > 0 && N > 0 && K > 0 && K <= 65536, "umma gemm: bad shape %d x %d x %d", M, N, K);
+    Epilogue ep{c, ldc, ea, eb, alpha, bias, mask, ldmask, relu, accumulate};
+    if (kind == KIND_I8) return launch_gemm<KIND_I8>(a, b, M, N, K, ep, stream);
+    if (kind == KIND_TF32) return launch_gemm<KIND_TF32>(a, b, M, N, K, ep, stream);
+    PNODE_REQUIRE(false, "umma gemm: unknown operand kind %d", kind);
+}
+
+int slice_rows(int kind, const void *x, long long ldx, int rows, int k, void *out, int *exps, cudaStream_t stream) {
+    const long long pitch = pitch_bytes(kind, k);
+    if (kind == KIND_I8)
+        slice_rows_kernel<KIND_I8><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
+    else
+        slice_rows_kernel<KIND_TF32><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void *out, int *exps, void *colsum, double coef,
+               cudaStream_t stream) {
+    const long long pitch = pitch_bytes(kind, rows);
+    const int grid = (cols + 31) / 32;
+    if (kind == KIND_I8)
+        slice_cols_kernel<KIND_I8><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps, colsum, coef);
+    else
+        slice_cols_kernel<KIND_TF32><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps, colsum, coef);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace umma
+}  // namespace pnode
+
+using namespace pnode;
+
+extern "C" {
+
+int64_t pnode_sliced_bytes(int kind, int rows, int k) {
+    if (kind != PNODE_SLICED_I8 && kind != PNODE_SLICED_TF32) return -1;
+    const int S = kind == PNODE_SLICED_I8 ? PNODE_I8_SLICES : 2;
+    return (int64_t)S * rows * umma::pitch_bytes(kind, k);
+}
+
+int pnode_slice_rows(int kind, const void *d_x, int64_t ldx, int rows, int k, void *d_slices, int32_t *d_exp, void *stream) {
+    PNODE_REQUIRE(kind == PNODE_SLICED_I8 || kind == PNODE_SLICED_TF32, "pnode_slice_rows: unknown kind %d", kind);
+    PNODE_REQUIRE(rows > 0 && k > 0, "pnode_slice_rows: empty operand");
+    return umma::slice_rows(kind, d_x, ldx, rows, k, d_slices, d_exp, (cudaStream_t)stream);
+}
+
+int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols, void *d_slices, int32_t *d_exp,
+                     void *d_colsum, double coef, void *stream) {
+    PNODE_REQUIRE(kind == PNODE_SLICED_I8 || kind == PNODE_SLICED_TF32, "pnode_slice_cols: unknown kind %d", kind);
+    PNODE_REQUIRE(rows > 0 && cols > 0, "pnode_slice_cols: empty operand");
+    return umma::slice_cols(kind, d_x, ldx, rows, cols, d_slices, d_exp, d_colsum, coef, (cudaStream_t)stream);
+}
+
+int pnode_sliced_gemm(int kind, const void *d_a, const int32_t *d_a_exp, const void *d_b, const int32_t *d_b_exp, int M,
+                      int N, int K, void *d_c, int64_t ldc, double alpha, const void *d_bias, int relu, const void *d_mask,
+                      int64_t ldmask, int accumulate, void *stream) {
+    return umma::gemm(kind, d_a, d_a_exp, d_b, d_b_exp, M, N, K, d_c, ldc, alpha, d_bias, relu, d_mask, ldmask, accumulate,
+                      (cudaStream_t)stream);
+}
+
+}  // extern "C"
