@@ -25,11 +25,26 @@ class _Callbacks:
     def __init__(self, ode):
         self.o = ode
 
+    # Without imex_form the reference registers ONE function: as the IFunction when implicit_form=True, else as the
+    # RHSFunction (petsc_adjoint.py:666-730).  An ARKIMEX scheme then integrates an empty other half ([PETSc]: a missing
+    # RHSFunction contributes 0, a missing IFunction is F = udot).
+    def _no_ex(self):
+        o = self.o
+        return o.ts.kind == "arkimex" and not o.imex and bool(getattr(o, "implicit_form", False))
+
+    def _no_im(self):
+        o = self.o
+        return o.ts.kind == "arkimex" and not o.imex and not bool(getattr(o, "implicit_form", False))
+
     def f_ex(self, t, u):
+        if self._no_ex():
+            return torch.zeros_like(u)
         with torch.no_grad():
             return self.o.funcEX(t, u.view(self.o.tensor_size)).reshape(u.shape).clone()  # petsc_adjoint.py:405
 
     def f_im(self, t, u):
+        if self._no_im():
+            return torch.zeros_like(u)
         with torch.no_grad():
             return self.o.funcIM(t, u.view(self.o.tensor_size)).reshape(u.shape).clone()  # petsc_adjoint.py:427
 
@@ -44,15 +59,21 @@ class _Callbacks:
         return vu.reshape(u.shape), _cat(vp, u)
 
     def vjp_ex(self, t, u, w):
+        if self._no_ex():
+            return torch.zeros_like(u), None
         return self._vjp(self.o.funcEX, t, u, w)
 
     def vjp_im(self, t, u, w):
+        if self._no_im():
+            return torch.zeros_like(u), None
         return self._vjp(self.o.funcIM, t, u, w)
 
     def pad_params(self, vp_im, vp_ex):
         """mu layout = [mu_IM (npIM), mu_EX (npEX)] for IMEX (petsc_adjoint.py:322-330, 351-359)."""
         o = self.o
         if not o.imex:
+            if vp_im is None and vp_ex is None:
+                return torch.zeros(o.np, dtype=o.tensor_dtype)
             return vp_im if vp_im is not None else vp_ex
         z = lambda n: torch.zeros(n, dtype=o.tensor_dtype)
         return torch.cat((vp_im if vp_im is not None else z(o.npIM), vp_ex if vp_ex is not None else z(o.npEX)))
@@ -60,6 +81,13 @@ class _Callbacks:
     # -- implicit stage: solve shift*(Y - Z) - f_I(t, Y) = 0 ------------------------------------------------------
     def _jac(self, t, y):
         o = self.o
+        if self._no_im():
+            n = y.numel() // (o.batch_size if o.linear_solver == "torch" and hasattr(o, "batch_size") else 1)
+            if o.linear_solver == "torch":
+                n = y.view(o.tensor_size)[0:1].numel()
+            else:
+                n = y.numel()
+            return torch.zeros(n, n, dtype=y.dtype)
         if o.linear_solver == "torch":
             # dense Jacobian of sample 0 only (petsc_adjoint.py:479), applied per sample (torch_linearsolve.py:25-29)
             if o._J0 is None:

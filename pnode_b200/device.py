@@ -90,17 +90,21 @@ class DeviceOps:
         ns = len(grads)
         if ns == 0:
             return
-        ptrs = []
+        ptrs, keep = [], []  # `keep` holds contiguous copies until the launch below has been issued
         for g in grads:
             if g is None:
                 ptrs.append(None)
             else:
+                if g.dtype != mu.dtype or g.device != mu.device:
+                    raise Error(-18, "parameter gradient is %s on %s, mu is %s on %s" % (g.dtype, g.device, mu.dtype, mu.device))
                 if not g.is_contiguous():
                     g = g.contiguous()
+                keep.append(g)
                 ptrs.append(g.data_ptr())
         vp = (C.c_void_p * ns)(*ptrs)
         sz = (C.c_int64 * ns)(*[int(s) for s in sizes])
         _lib.check(self.lib.pnode_multi_axpy(mu.data_ptr(), vp, sz, ns, float(coef), self.code, _stream()))
+        del keep
         self.launches += 1
 
     # [<v_j, w> for j] + [<w, w>] as a HOST list of floats (one device->host read): GMRES Gram-Schmidt coefficients

@@ -293,7 +293,18 @@ class ImplicitSolver:
         key = float(shift)
         if key not in self._inv:
             J = self._block_jacobian(t, y)
-            A = torch.eye(J.shape[0], dtype=J.dtype, device=J.device).mul_(shift) - J
+            N = J.shape[0]
+            if self.mass is not None:
+                # reference petsc_adjoint.py:491-507 forms shift * mass - J; per-sample blocks need a block-diagonal mass
+                # matrix with identical blocks
+                M = self.mass
+                Mb = M[:N, :N]
+                if not torch.equal(M, torch.block_diag(*([Mb] * (M.shape[0] // N)))):
+                    raise Error(-21, "linear_solver='torch' with mass= needs a block-diagonal mass matrix with identical "
+                                     "[n/batch, n/batch] blocks")
+                A = Mb * shift - J
+            else:
+                A = torch.eye(N, dtype=J.dtype, device=J.device).mul_(shift) - J
             self._inv[key] = torch.linalg.inv(A)
         return self._inv[key]
 
@@ -514,10 +525,10 @@ class GenericTS:
         for i in range(s):
             vecs, coefs = [], []
             for j in range(i):
-                if sc.At[i][j] != 0.0:
+                if sc.At[i][j] != 0.0 and KI[j] is not None:
                     vecs.append(KI[j])
                     coefs.append(h * sc.At[i][j])
-                if sc.A[i][j] != 0.0:
+                if sc.A[i][j] != 0.0 and KE[j] is not None:
                     vecs.append(KE[j])
                     coefs.append(h * sc.A[i][j])
             if vecs:
@@ -525,7 +536,11 @@ class GenericTS:
                 ops.lincomb(Z, u, 1.0, vecs, coefs)
             else:
                 Z = u
-            if sc.At[i][i] == 0.0:
+            if cb_im is None:
+                # only an RHSFunction is registered (reference petsc_adjoint.py:716-730): F = udot, the stage equation
+                # shift (Y - Z) = 0 gives Y = Z and K^I = 0
+                y, ki = Z, None
+            elif sc.At[i][i] == 0.0:
                 y = Z
                 ki = cb_im.f(t + sc.ct[i] * h, y, keep=self._keep)
             else:
@@ -535,15 +550,15 @@ class GenericTS:
                 ops.lincomb(ki, None, 0.0, [y, Z], [shift, -shift])  # K^I_i = shift (Y_i - Z), not re-evaluated
             Y.append(y)
             KI.append(ki)
-            KE.append(cb_ex.f(t + sc.c[i] * h, y, keep=self._keep))
+            KE.append(None if cb_ex is None else cb_ex.f(t + sc.c[i] * h, y, keep=self._keep))
         vecs, bw, ew = [], [], []
         for j in range(s):
             be = sc.bembed[j] if (adaptive and sc.bembed is not None) else sc.b[j]
-            if sc.bt[j] != 0.0 or be != sc.bt[j]:
+            if (sc.bt[j] != 0.0 or be != sc.bt[j]) and KI[j] is not None:
                 vecs.append(KI[j])
                 bw.append(h * sc.bt[j])
                 ew.append(h * (be - sc.bt[j]))
-            if sc.b[j] != 0.0 or be != sc.b[j]:
+            if (sc.b[j] != 0.0 or be != sc.b[j]) and KE[j] is not None:
                 vecs.append(KE[j])
                 bw.append(h * sc.b[j])
                 ew.append(h * (be - sc.b[j]))
@@ -634,20 +649,31 @@ class GenericTS:
             ep = torch.empty_like(lam)
             ops.lincomb(om, lam, sc.bt[i], [ls[j] for j in later_t], [sc.At[j][i] for j in later_t])
             ops.lincomb(ep, lam, sc.b[i], [ls[j] for j in later_e], [sc.A[j][i] for j in later_e])
-            vu_e, gp_e = cb_ex.vjp(t + sc.c[i] * h, Y[i], ep)
-            ops.multi_axpy(mu_ex, gp_e, cb_ex.sizes, h)
-            vu_i, gp_i0 = cb_im.vjp(t + sc.ct[i] * h, Y[i], om)
+            parts = []
+            if cb_ex is not None:
+                if hasattr(cb_ex, "vjp_accumulate"):  # evaluator that adds h * Jp^T eps into mu itself
+                    vu_e, gp_e = cb_ex.vjp_accumulate(t + sc.c[i] * h, Y[i], ep, mu_ex, h)
+                else:
+                    vu_e, gp_e = cb_ex.vjp(t + sc.c[i] * h, Y[i], ep)
+                if gp_e is not None:
+                    ops.multi_axpy(mu_ex, gp_e, cb_ex.sizes, h)
+                parts.append(vu_e)
+            gp_i0 = None
+            if cb_im is not None:
+                vu_i, gp_i0 = cb_im.vjp(t + sc.ct[i] * h, Y[i], om, want_params=cb_im.nparams > 0)
+                parts.append(vu_i)
             r = torch.empty_like(lam)
-            if sc.At[i][i] == 0.0:
-                ops.lincomb(r, None, 0.0, [vu_i, vu_e], [h, h])
+            if cb_im is None or sc.At[i][i] == 0.0:
+                # no implicit function registered: the stage equation is shift (Y - Z) = 0, whose transposed solve is h r
+                ops.lincomb(r, None, 0.0, parts, [h] * len(parts))
                 ls[i] = r
                 w_im = om
             else:
-                ops.lincomb(r, None, 0.0, [vu_i, vu_e], [1.0 / sc.At[i][i], 1.0 / sc.At[i][i]])
+                ops.lincomb(r, None, 0.0, parts, [1.0 / sc.At[i][i]] * len(parts))
                 ls[i] = imp.solve_transpose(t + sc.ct[i] * h, Y[i], 1.0 / (h * sc.At[i][i]), r)
                 w_im = torch.empty_like(lam)
                 ops.lincomb(w_im, om, 1.0, [ls[i]], [sc.At[i][i]])
-            if cb_im.nparams > 0:
+            if cb_im is not None and cb_im.nparams > 0:
                 if w_im is om:
                     gp_i = gp_i0
                 else:  # the j = i term needs the post-solve lambda_{s,i}

@@ -36,6 +36,14 @@ def single_time_adjoint_steps(loop):
     return min(n, loop.steps)
 
 
+def _on_device(device):
+    """Kernels are launched on the raw stream of the CURRENT device: make the state's device current for the call."""
+    import contextlib
+    if device is not None and device.type == "cuda":
+        return torch.cuda.device(device)
+    return contextlib.nullcontext()
+
+
 def _check_device(tensor, what):
     """The single gate of the product path: CUDA tensors only."""
     if not tensor.is_cuda:
@@ -98,6 +106,11 @@ class ODEPetsc(object):
         funcs_changed = self.funcIM is not func or self.funcEX is not func_ex
         meta_changed = (u_tensor.size() != self.tensor_size or u_tensor.dtype != self.tensor_dtype
                         or u_tensor.device != self.device)
+        # train()/eval() switches change what the modules compute (BatchNorm statistics, Dropout): the evaluators chosen below
+        # -- and Callbacks' decision to keep stage graphs -- are re-derived whenever any sub-module's mode flips
+        mode_sig = tuple(m.training for f in (func, func_ex) if isinstance(f, nn.Module) for m in f.modules())
+        mode_changed = mode_sig != getattr(self, "_mode_sig", None)
+        self._mode_sig = mode_sig
         if funcs_changed:
             self.funcIM, self.funcEX = func, func_ex
         if meta_changed:
@@ -109,12 +122,12 @@ class ODEPetsc(object):
             self._kind, self._scheme_name = tableaux.METHODS.get(method, tableaux.TS_DEFAULT)
             self.implicit_form = implicit_form
             self._ops = DeviceOps(self.device, self.tensor_dtype)
-        if funcs_changed or meta_changed:
+        if funcs_changed or meta_changed or mode_changed:
             self._cb_im = Callbacks(self.funcIM, self.tensor_size)
             self._rhs_kind = "torch"
             if not imex_form and Options().getString("pnode_fused", "1") not in ("0", "false", "no"):
                 # convolutional ODE block: same generic stage loop, hand-written BN+ReLU kernels inside f / vjp
-                key = (id(func), tuple(u_tensor.shape), u_tensor.dtype)
+                key = (id(func), tuple(u_tensor.shape), u_tensor.dtype, mode_sig)
                 if key in self._convblock_cache or recognise_convblock(func, u_tensor):
                     self._convblock_cache[key] = True
                     self._cb_im = ConvBlockCallbacks(func, self.tensor_size)
@@ -186,6 +199,18 @@ class ODEPetsc(object):
         if sol_only or max_cps is not None:
             self._allow_fused = False  # the fused sweeps always keep stage checkpoints in HBM
 
+    def _active_callbacks(self):
+        """(explicit, implicit) right-hand sides the active scheme integrates.  Without imex_form the reference registers ONE
+        function: as the IFunction when implicit_form=True, else as the RHSFunction (petsc_adjoint.py:666-730) -- an ARKIMEX
+        scheme then sees an empty other half (treating the single function as both halves would integrate u' = 2 f)."""
+        cb_ex, cb_im = self._cb_ex, self._cb_im
+        if self._active_kind == "arkimex" and not self.imex:
+            if getattr(self, "implicit_form", False):
+                cb_ex = None
+            else:
+                cb_im = None
+        return cb_ex, cb_im
+
     def _adaptive(self):
         if self._adapt_none or self._active_kind in ("cn", "beuler"):
             return False
@@ -233,6 +258,10 @@ class ODEPetsc(object):
         return times
 
     def _odeint_impl(self, u0, t):
+        with _on_device(self.device):
+            return self._odeint_body(u0, t)
+
+    def _odeint_body(self, u0, t):
         if self.tensor_size is None:
             raise Error(-15, "setupTS must be called before odeint")
         _check_device(u0, "ODEPetsc.odeint: u0")
@@ -269,7 +298,8 @@ class ODEPetsc(object):
         self._imp.reset()
         loop = TimeLoop(times, self.step_size, self._adaptive(), self._scheme.order if self._scheme else 1,
                         self.tensor_dtype == torch.float64, self._max_reject)
-        uf, sols = self._engine.solve(self._cb_ex, self._cb_im, self._imp, u_flat, loop, self.enable_adjoint)
+        cb_ex, cb_im = self._active_callbacks()
+        uf, sols = self._engine.solve(cb_ex, cb_im, self._imp, u_flat, loop, self.enable_adjoint)
         self._loop = loop
         if self._monitor:
             for k, (tt, hh, ok, en) in enumerate(loop.attempts):
@@ -300,14 +330,15 @@ class ODEPetsc(object):
         self._engine.traj = traj
         lam = grad[-1].reshape(-1).clone()
         mu = torch.zeros(self.np, dtype=self.tensor_dtype, device=self.device)
-        np_im = self.npIM if self.imex else 0
+        cb_ex, cb_im = self._active_callbacks()
+        np_im = self.npIM if self.imex else (self.np if cb_ex is None else 0)
         eng = self._engine
         if T == 1:
             nsteps = single_time_adjoint_steps(loop)
             nsteps = min(nsteps, len(eng.traj))
-            lam = eng.adjoint_steps(self._cb_ex, self._cb_im, self._imp, nsteps, lam, mu, np_im)
+            lam = eng.adjoint_steps(cb_ex, cb_im, self._imp, nsteps, lam, mu, np_im)
         for i in range(T - 1, 0, -1):
-            lam = eng.adjoint_steps(self._cb_ex, self._cb_im, self._imp, loop.cur_sol_steps[i], lam, mu, np_im)
+            lam = eng.adjoint_steps(cb_ex, cb_im, self._imp, loop.cur_sol_steps[i], lam, mu, np_im)
             self._ops.lincomb(lam, lam, 1.0, [grad[i - 1].reshape(-1)], [1.0])  # forcing (petsc_adjoint.py:938)
         if not eng.traj:  # the whole trajectory has been consumed: drop what the forward kept for this sweep
             for cb in (self._cb_ex, self._cb_im):
@@ -337,7 +368,7 @@ class _OdeintAdjoint(torch.autograd.Function):
         if not ode.enable_adjoint:
             raise Error(-17, "backward through odeint_adjoint needs setupTS(enable_adjoint=True)")
         T = ctx.T
-        with torch.no_grad():
+        with torch.no_grad(), _on_device(ode.device):
             grad = grad_output if grad_output.is_contiguous() else grad_output.contiguous()
             if ctx.state[0] == "fused":
                 _, fused, ckpt, sched = ctx.state

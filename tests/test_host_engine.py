@@ -357,3 +357,33 @@ def test_fixed_jacobian_keeps_the_factorisation_across_solves(monkeypatch):
     assert all(ode._imp._inv[k] is not v for k, v in inv.items()), "kept although a parameter was touched"
     b1, b2 = _run_product(monkeypatch, argv, kw, [f_im, f_ex], u0, t, gout, 0.1, twice=True)
     assert torch.equal(b1[0], a1[0]) and all(torch.equal(x, y) for x, y in zip(b1[2], a1[2]))
+
+
+class _Decay(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.k = torch.nn.Parameter(torch.tensor([1.0], dtype=torch.float64))
+
+    def forward(self, t, u):
+        return -self.k * u
+
+
+@pytest.mark.parametrize("implicit_form", [False, True])
+@pytest.mark.parametrize("how", ["method", "option"])
+def test_arkimex_with_a_single_function_integrates_it_once(monkeypatch, implicit_form, how):
+    """Oracle-independent: u' = -k u, u(0) = 1 must give exp(-t) (an ARKIMEX scheme handed ONE function -- method='imex'
+    without imex_form, or -ts_type arkimex on an ordinary model -- registers it as the RHSFunction, or as the IFunction when
+    implicit_form=True, reference petsc_adjoint.py:666-730; treating it as both halves integrates u' = 2 f -> exp(-2t))."""
+    import math
+
+    argv = ["-ts_adapt_type", "none"] + (["-ts_type", "arkimex"] if how == "option" else [])
+    u0 = torch.ones(3, dtype=torch.float64)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    kw = dict(method="imex" if how == "method" else "rk4", implicit_form=implicit_form)
+    gout = torch.stack([torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)])
+    o, p = _both(monkeypatch, argv, kw, [_Decay()], u0, t, gout, 0.05)
+    for res in (o, p):
+        assert abs(res[0][-1][0].item() - math.exp(-1.0)) < 5e-6
+        assert abs(res[1][0].item() - math.exp(-1.0)) < 5e-6          # d u(1) / d u0
+        assert abs(res[2][0].item() + 3 * math.exp(-1.0)) < 5e-5      # d sum u(1) / d k = -t exp(-k t) per component
+    _assert_close(p, o, 1e-12)
