@@ -82,6 +82,20 @@ RK["5f"] = RKTableau(
 )
 
 
+# Bogacki-Shampine 5(4), 8 stages, FSAL (Bogacki & Shampine 1996; [PETSc] TSRK5BS)
+RK["5bs"] = RKTableau(
+    "5bs", 5,
+    [[], [Fr(1, 6)], [Fr(2, 27), Fr(4, 27)], [Fr(183, 1372), Fr(-162, 343), Fr(1053, 1372)],
+     [Fr(68, 297), Fr(-4, 11), Fr(42, 143), Fr(1960, 3861)],
+     [Fr(597, 22528), Fr(81, 352), Fr(63099, 585728), Fr(58653, 366080), Fr(4617, 20480)],
+     [Fr(174197, 959244), Fr(-30942, 79937), Fr(8152137, 19744439), Fr(666106, 1039181), Fr(-29421, 29068),
+      Fr(482048, 414219)],
+     [Fr(587, 8064), 0, Fr(4440339, 15491840), Fr(24353, 124800), Fr(387, 44800), Fr(2152, 5985), Fr(7267, 94080)]],
+    [Fr(587, 8064), 0, Fr(4440339, 15491840), Fr(24353, 124800), Fr(387, 44800), Fr(2152, 5985), Fr(7267, 94080), 0],
+    [Fr(2479, 34992), 0, Fr(123, 416), Fr(612941, 3411720), Fr(43, 1440), Fr(2272, 6561), Fr(79937, 1113912),
+     Fr(3293, 556956)], fsal=True)
+
+
 class ARKTableau:
     """Additive (implicit At / explicit A) tableau.  PETSc's TSARKIMEX keeps bt == b and ct == c for all schemes below."""
 
@@ -106,6 +120,35 @@ class ARKTableau:
 
 
 ARK = {}
+# [PETSc] TSARKIMEX1BEE (backward Euler as two half steps, one full step embedded; registered order 2), 2C / 2D / 2E (Giraldo et
+# al. 2013 family: gamma = 1 - 1/sqrt 2), PRSSP2 (Pareschi-Russo SSP2(3,3,2)), BPR3 (Boscarino-Pareschi-Russo BPR(3,5,3)),
+# ARS443 (Ascher-Ruuth-Spiteri 1997).  Restated from the published schemes; additive order conditions incl. coupling are
+# checked in tests/test_tableaux.py.
+ARK["1bee"] = ARKTableau("1bee", 2, [[1, 0, 0], [0, Fr(1, 2), 0], [0, Fr(1, 2), Fr(1, 2)]], [[0, 0, 0], [0, 0, 0], [0, Fr(1, 2), 0]],
+                         [0, Fr(1, 2), Fr(1, 2)], [1, 0, 0])
+_r2 = sqrt(2.0)
+_u2, _h2 = 1.0 - 1.0 / _r2, 1.0 / (2.0 * _r2)
+_at2 = [[0.0, 0.0, 0.0], [_u2, _u2, 0.0], [_h2, _h2, _u2]]
+_be2 = [(4.0 - _r2) / 8.0, (4.0 - _r2) / 8.0, _h2]
+ARK["2c"] = ARKTableau("2c", 2, _at2, [[0.0, 0.0, 0.0], [2.0 - _r2, 0.0, 0.0], [0.5, 0.5, 0.0]], [_h2, _h2, _u2], _be2)
+ARK["2d"] = ARKTableau("2d", 2, _at2, [[0.0, 0.0, 0.0], [2.0 - _r2, 0.0, 0.0], [0.75, 0.25, 0.0]], [_h2, _h2, _u2], _be2)
+ARK["2e"] = ARKTableau("2e", 2, _at2, [[0.0, 0.0, 0.0], [2.0 - _r2, 0.0, 0.0],
+                                       [(3.0 - 2.0 * _r2) / 6.0, (3.0 + 2.0 * _r2) / 6.0, 0.0]], [_h2, _h2, _u2], _be2)
+ARK["prssp2"] = ARKTableau("prssp2", 2, [[Fr(1, 4), 0, 0], [0, Fr(1, 4), 0], [Fr(1, 3), Fr(1, 3), Fr(1, 3)]],
+                           [[0, 0, 0], [Fr(1, 2), 0, 0], [Fr(1, 2), Fr(1, 2), 0]], [Fr(1, 3), Fr(1, 3), Fr(1, 3)])
+ARK["bpr3"] = ARKTableau(
+    "bpr3", 3,
+    [[0] * 5, [Fr(1, 2), Fr(1, 2), 0, 0, 0], [Fr(5, 18), Fr(-1, 9), Fr(1, 2), 0, 0], [Fr(1, 2), 0, 0, Fr(1, 2), 0],
+     [Fr(1, 4), 0, Fr(3, 4), Fr(-1, 2), Fr(1, 2)]],
+    [[0] * 5, [1, 0, 0, 0, 0], [Fr(4, 9), Fr(2, 9), 0, 0, 0], [Fr(1, 4), 0, Fr(3, 4), 0, 0], [Fr(1, 4), 0, Fr(3, 4), 0, 0]],
+    [Fr(1, 4), 0, Fr(3, 4), Fr(-1, 2), Fr(1, 2)])
+ARK["ars443"] = ARKTableau(
+    "ars443", 3,
+    [[0] * 5, [0, Fr(1, 2), 0, 0, 0], [0, Fr(1, 6), Fr(1, 2), 0, 0], [0, Fr(-1, 2), Fr(1, 2), Fr(1, 2), 0],
+     [0, Fr(3, 2), Fr(-3, 2), Fr(1, 2), Fr(1, 2)]],
+    [[0] * 5, [Fr(1, 2), 0, 0, 0, 0], [Fr(11, 18), Fr(1, 18), 0, 0, 0], [Fr(5, 6), Fr(-5, 6), Fr(1, 2), 0, 0],
+     [Fr(1, 4), Fr(7, 4), Fr(3, 4), Fr(-7, 4), 0]],
+    [0, Fr(3, 2), Fr(-3, 2), Fr(1, 2), Fr(1, 2)], [Fr(1, 4), Fr(7, 4), Fr(3, 4), Fr(-7, 4), 0])
 ARK["ars122"] = ARKTableau("ars122", 2, [[0, 0], [0, Fr(1, 2)]], [[0, 0], [Fr(1, 2), 0]], [0, 1], [Fr(1, 2), Fr(1, 2)])
 ARK["a2"] = ARKTableau("a2", 2, [[0, 0], [Fr(1, 2), Fr(1, 2)]], [[0, 0], [1, 0]], [Fr(1, 2), Fr(1, 2)], [0, 1])
 _g = 1.0 - 1.0 / sqrt(2.0)

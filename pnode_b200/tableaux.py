@@ -55,6 +55,15 @@ RK = {
         ["", "1/4", "3/32 9/32", "1932/2197 -7200/2197 7296/2197", "439/216 -8 3680/513 -845/4104",
          "-8/27 2 -3544/2565 1859/4104 -11/40"],
         "16/135 0 6656/12825 28561/56430 -9/50 2/55", "25/216 0 1408/2565 2197/4104 -1/5 0"),
+    # Bogacki-Shampine 5(4), 8 stages, FSAL ([PETSc] TSRK5BS); order conditions checked exactly in tests/test_tableaux.py
+    "5bs": Scheme(
+        "5bs", "rk", 5,
+        ["", "1/6", "2/27 4/27", "183/1372 -162/343 1053/1372", "68/297 -4/11 42/143 1960/3861",
+         "597/22528 81/352 63099/585728 58653/366080 4617/20480",
+         "174197/959244 -30942/79937 8152137/19744439 666106/1039181 -29421/29068 482048/414219",
+         "587/8064 0 4440339/15491840 24353/124800 387/44800 2152/5985 7267/94080"],
+        "587/8064 0 4440339/15491840 24353/124800 387/44800 2152/5985 7267/94080 0",
+        "2479/34992 0 123/416 612941/3411720 43/1440 2272/6561 79937/1113912 3293/556956", fsal=True),
     "5dp": Scheme(
         "5dp", "rk", 5,
         ["", "1/5", "3/40 9/40", "44/45 -56/15 32/9", "19372/6561 -25360/2187 64448/6561 -212/729",
@@ -71,7 +80,31 @@ _ARK4_B = "82889/524892 0 15625/83664 69875/102672 -2260/8211 1/4"
 _ARK5_B = ("-872700587467/9133579230613 0 0 22348218063261/9555858737531 -1143369518992/8141816002931 "
            "-39379526789629/19018526304540 32727382324388/42900044865799 41/200")
 
+_R2 = sqrt(2.0)
+_U2 = "~" + repr(1.0 - 1.0 / _R2)          # 1 - 1/sqrt(2)
+_H2 = "~" + repr(1.0 / (2.0 * _R2))        # 1/(2 sqrt(2))
+_AT2 = ["0", _U2 + " " + _U2, _H2 + " " + _H2 + " " + _U2]   # implicit part shared by 2c / 2d / 2e
+_B2 = _H2 + " " + _H2 + " " + _U2
+_BE2 = "~%r ~%r %s" % ((4.0 - _R2) / 8.0, (4.0 - _R2) / 8.0, _H2)
+_A21 = "~" + repr(2.0 - _R2)
+
 ARK = {
+    # [PETSc] TSARKIMEX1BEE: backward Euler (two half steps) with one full step as the embedded solution; registered order 2
+    "1bee": Scheme("1bee", "arkimex", 2, A=["0", "0", "0 1/2"], At=["1", "0 1/2", "0 1/2 1/2"], b="0 1/2 1/2", bembed="1 0 0"),
+    # [PETSc] TSARKIMEX2C / 2D / 2E: one explicit + two L-stable implicit stages (gamma = 1 - 1/sqrt 2), three explicit parts
+    "2c": Scheme("2c", "arkimex", 2, A=["0", _A21, "1/2 1/2"], At=_AT2, b=_B2, bembed=_BE2),
+    "2d": Scheme("2d", "arkimex", 2, A=["0", _A21, "3/4 1/4"], At=_AT2, b=_B2, bembed=_BE2),
+    "2e": Scheme("2e", "arkimex", 2, A=["0", _A21, "~%r ~%r" % ((3.0 - 2.0 * _R2) / 6.0, (3.0 + 2.0 * _R2) / 6.0)], At=_AT2,
+                 b=_B2, bembed=_BE2),
+    # Pareschi-Russo SSP2(3,3,2)
+    "prssp2": Scheme("prssp2", "arkimex", 2, A=["0", "1/2", "1/2 1/2"], At=["1/4", "0 1/4", "1/3 1/3 1/3"], b="1/3 1/3 1/3"),
+    # Boscarino-Pareschi-Russo BPR(3,5,3)
+    "bpr3": Scheme("bpr3", "arkimex", 3, A=["0", "1", "4/9 2/9", "1/4 0 3/4", "1/4 0 3/4"],
+                   At=["0", "1/2 1/2", "5/18 -1/9 1/2", "1/2 0 0 1/2", "1/4 0 3/4 -1/2 1/2"], b="1/4 0 3/4 -1/2 1/2"),
+    # Ascher-Ruuth-Spiteri (4,4,3); the explicit weights serve as the embedded solution
+    "ars443": Scheme("ars443", "arkimex", 3, A=["0", "1/2", "11/18 1/18", "5/6 -5/6 1/2", "1/4 7/4 3/4 -7/4"],
+                     At=["0", "0 1/2", "0 1/6 1/2", "0 -1/2 1/2 1/2", "0 3/2 -3/2 1/2 1/2"], b="0 3/2 -3/2 1/2 1/2",
+                     bembed="1/4 7/4 3/4 -7/4 0"),
     "ars122": Scheme("ars122", "arkimex", 2, A=["0", "1/2"], At=["0", "0 1/2"], b="0 1", bembed="1/2 1/2"),
     "a2": Scheme("a2", "arkimex", 2, A=["0", "1"], At=["0", "1/2 1/2"], b="1/2 1/2", bembed="0 1"),
     "l2": Scheme("l2", "arkimex", 2, A=["0", "1"], At=["~" + _G2, "~" + _G2b + " ~" + _G2], b="1/2 1/2", bembed="0 1"),

@@ -40,6 +40,22 @@ def _assert_close(a, b, tol):
         assert rel_err(x, y) < tol
 
 
+@pytest.mark.parametrize("scheme", ["5bs", "5f", "3", "2a"])
+def test_fixed_step_rk_types_from_the_option(monkeypatch, scheme):
+    u0, t, gout = spiral_inputs(20)
+    o, p = _both(monkeypatch, ["-ts_adapt_type", "none", "-ts_rk_type", scheme], dict(method="rk4"),
+                 [SpiralFunc(bias_std=0.1)], u0, t, gout, 0.025)
+    _assert_close(p, o, 1e-13)
+
+
+def test_adaptive_bogacki_shampine_54(monkeypatch):
+    u0, t, gout = spiral_inputs(20)
+    o, p = _both(monkeypatch, ["-ts_rk_type", "5bs", "-ts_rtol", "1e-7", "-ts_atol", "1e-7"], dict(method="rk4"),
+                 [SpiralFunc(bias_std=0.1)], u0, t, gout, 0.025)
+    _assert_close(p, o, 1e-12)
+    assert [a[2] for a in p[3]._loop.attempts] == [a[2] for a in o[3].ts.log]
+
+
 @pytest.mark.parametrize("method", ["euler", "rk2", "bosh3", "rk4", "dopri5", "midpoint"])
 def test_fixed_step_rk(monkeypatch, method):
     u0, t, gout = spiral_inputs(20)
@@ -97,7 +113,7 @@ def test_rober_goldens_through_product_host_logic(monkeypatch):
         Options.clear_all()
 
 
-@pytest.mark.parametrize("name", ["l2", "3", "4", "5", "ars122"])
+@pytest.mark.parametrize("name", ["l2", "3", "4", "5", "ars122", "a2", "1bee", "2c", "2d", "2e", "prssp2", "bpr3", "ars443"])
 def test_imex_batched_linear_solver(monkeypatch, name):
     from test_oracle_adjoint import LinearIM
 

@@ -42,6 +42,25 @@ def test_rk_adjoint_matches_autograd(method, scheme):
         assert rel_err(g, p.grad) < 1e-12
 
 
+@pytest.mark.parametrize("scheme", ["5bs", "5f", "3", "2a"])
+def test_rk_adjoint_of_option_selected_schemes_matches_autograd(scheme):
+    """Schemes only reachable through -ts_rk_type (petsc_adjoint.py:775), incl. the 8-stage FSAL Bogacki-Shampine 5(4)."""
+    func = SpiralFunc(bias_std=0.1)
+    u0, t, gout = spiral_inputs(20)
+    out, lam, mu, ode = _oracle_grads(dict(method="rk4"), [func], u0, t, gout, argv=ARGS + ["-ts_rk_type", scheme])
+    A, b, _, c = otab.RK[scheme].floats()
+    sched = [(tt, hh, k + 1) for k, (tt, hh, ok, _) in enumerate(ode.ts.log)]
+    func.zero_grad()
+    y0 = u0.clone().requires_grad_(True)
+    outs, _ = rk_unrolled(lambda tt, y: func(tt, y), y0, sched, A, b, c)
+    ref = torch.stack([outs[k] for k in range(len(t))])
+    (ref * gout).sum().backward()
+    assert rel_err(out, ref) < 1e-14
+    assert rel_err(lam, y0.grad) < 1e-12
+    for g, p in zip(mu, func.parameters()):
+        assert rel_err(g, p.grad) < 1e-12
+
+
 def test_rk_adjoint_single_time_point():
     func = SpiralFunc(bias_std=0.1)
     u0, _, gout = spiral_inputs(7)
@@ -76,7 +95,7 @@ class LinearIM(nn.Module):
         return y @ self.matrix().T
 
 
-@pytest.mark.parametrize("name", ["l2", "ars122", "a2", "3", "4", "5"])
+@pytest.mark.parametrize("name", ["l2", "ars122", "a2", "3", "4", "5", "1bee", "2c", "2d", "2e", "prssp2", "bpr3", "ars443"])
 def test_arkimex_adjoint_matches_autograd(name):
     N, B = 8, 5
     f_im = LinearIM(N)
