@@ -206,7 +206,7 @@ def cfg5(N=1024, B=256, dtype="f64"):
                     argv=["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_trajectory_type", "memory"],
                     funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)], u0=u0, t=t, target=target, kw=kw,
                     step=0.2, batch=B, flops_per_unit=16 * f_ex + 6 * 2 * N * N, bytes_per_unit=12 * 37.3e6 * 8 / B,
-                    pipe="fp64_fma" if dtype == "f64" else "fp32_fma",
+                    pipe="fp64_fma" if dtype == "f64" else "fp32_fma", also_generic=True,
                     cpu_sample=lambda: dict(funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)],
                                             u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
                                             kw=dict(kw, batch_size=bs), batch=bs, desc="%d of %d samples" % (bs, B)))

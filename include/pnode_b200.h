@@ -303,7 +303,7 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
  *   PNODE_SLICED_TF32 fp32 source: x = hi + lo with hi = tf32(x), S = 2 (3xTF32: hi.hi + hi.lo + lo.hi)
  * pnode_slice_rows slices x itself (operand row = row of x); pnode_slice_cols slices x^T (operand row = column of x,
  * reduction over the rows of x) and can add coef * (column sums of x) into d_colsum (bias gradients).
- * pnode_sliced_gemm:  C[m][n] (op)= mask( relu( alpha * sum_k A[m][k] B[n][k] + bias[n] ) ),  C row-major with leading
+ * pnode_sliced_gemm:  C[m][n] (op)= mask( relu( alpha * ( sum_k A[m][k] B[n][k] + bias[n] ) ) ),  C row-major with leading
  * dimension ldc, fp64 for I8 operands / fp32 for TF32; `accumulate` adds into C; mask (same type and layout as C,
  * leading dimension ldmask) keeps the result where mask > 0 (ReLU backward).  d_a_exp / d_b_exp: the row exponents
  * written by the slicing kernels (ignored for TF32).
@@ -318,6 +318,55 @@ int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols,
 int pnode_sliced_gemm(int kind, const void *d_a, const int32_t *d_a_exp, const void *d_b, const int32_t *d_b_exp, int M,
                       int N, int K, void *d_c, int64_t ldc, double alpha, const void *d_bias, int relu, const void *d_mask,
                       int64_t ldmask, int accumulate, void *stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Wide ReLU-MLP right-hand side f(t, u) = out_scale * net(u), net = Linear -> ReLU -> ... -> Linear (csrc/dense_mlp.cu):
+ * the explicit half of the SINODE pair (ODEFuncEX, examples-sinode/KS/models/imex.py:46-70: returns -F(y);
+ * examples-sinode/Burgers/Burgers.py:134-160: returns net(y)).  One call per right-hand-side evaluation
+ * (replaces evalRHSFunction -> func(t, u), pnode/petsc_adjoint.py:393-412) and one per adjoint stage (replaces
+ * RHSJacShell.multTranspose's forward re-evaluation + autograd.grad, 52-82, AND RHSJacPShell.multTranspose + the VecAXPY on
+ * mu, 341-363: the weight gradients are accumulated straight into mu by the product's epilogue).  Every product runs
+ * on the tensor cores through the sliced operands above (fp64: int8 slices; fp32: 3xTF32).
+ *   prepare : slice every weight matrix in both orientations (once per solve: parameters are borrowed, never cached
+ *             across optimiser steps)
+ *   forward : d_out[batch][dims[L]] = f(d_u[batch][dims[0]]); with d_act != NULL the evaluation keeps what the adjoint
+ *             stage at the same point needs (column-sliced layer inputs, post-ReLU activations) -- the stage checkpoint
+ *             of this right-hand side
+ *   vjp     : d_vu = J^T w (skipped if NULL);  if d_mu != NULL:  mu[mu_w_off[l] ...] += coef * dW_l,
+ *             mu[mu_b_off[l] ...] += coef * db_l  (offsets in elements, -1: that parameter takes no gradient)
+ * -------------------------------------------------------------------------------------------------------------- */
+#define PNODE_DMLP_MAX_LAYERS 8
+typedef struct pnode_dmlp_desc {
+    int32_t nlayers, dtype, batch, reserved;
+    int32_t dims[PNODE_DMLP_MAX_LAYERS + 1];        /* dims[0] = input width ... dims[nlayers] = output width */
+    const void *d_weight[PNODE_DMLP_MAX_LAYERS];    /* [dims[l+1]][dims[l]] row-major (torch nn.Linear.weight) */
+    const void *d_bias[PNODE_DMLP_MAX_LAYERS];      /* [dims[l+1]] or NULL */
+    int64_t mu_w_off[PNODE_DMLP_MAX_LAYERS];
+    int64_t mu_b_off[PNODE_DMLP_MAX_LAYERS];
+    double out_scale;
+} pnode_dmlp_desc;
+int64_t pnode_dmlp_weight_bytes(const pnode_dmlp_desc *desc);   /* -1: unsupported (pnode_last_error) */
+int64_t pnode_dmlp_act_bytes(const pnode_dmlp_desc *desc);
+int64_t pnode_dmlp_work_bytes(const pnode_dmlp_desc *desc);
+int pnode_dmlp_prepare(const pnode_dmlp_desc *desc, void *d_wslices, void *stream);
+int pnode_dmlp_forward(const pnode_dmlp_desc *desc, const void *d_wslices, const void *d_u, void *d_out, void *d_act,
+                       void *d_work, void *stream);
+int pnode_dmlp_vjp(const pnode_dmlp_desc *desc, const void *d_wslices, const void *d_act, const void *d_w, void *d_vu,
+                   void *d_mu, double coef, void *d_work, void *stream);
+
+/* Circulant linear operator J[i][j] = c[(i - j) mod n] applied to every row of d_x[rows][n] (the implicit half of the
+ * SINODE pair: a circular-padding Conv1d stencil, imex.py:6-44; replaces evalIFunction's func(t, u), petsc_adjoint.py:
+ * 414-431, and IJacShell's J^T x, 179-196).  `offsets` / `coefs` (HOST arrays, ntaps <= PNODE_CIRC_MAX_TAPS) list the
+ * non-zero entries c[offsets[d]] = coefs[d].  transpose != 0 applies J^T. */
+#define PNODE_CIRC_MAX_TAPS 16
+int pnode_circulant_apply(const void *d_x, void *d_out, int rows, int n, const int32_t *offsets, const double *coefs,
+                          int ntaps, int transpose, int dtype, void *stream);
+/* d_inverse[n][n] = (shift * I - J)^-1 for the circulant J with first column d_col (fp64, on the device), from its
+ * spectrum: lam_k = sum_j a_j exp(-2 pi i jk/n), inverse first column = (1/n) sum_k exp(2 pi i mk/n) / lam_k (compensated
+ * O(n^2) sums, exact argument reduction).  Replaces torch_linearsolve.PCShell.get_factor's LU (pnode/torch_linearsolve.py:
+ * 15-19); the solves of 25-35 become one sliced product with this matrix.  d_work: pnode_circulant_work_bytes(n). */
+int64_t pnode_circulant_work_bytes(int n);
+int pnode_circulant_inverse(const double *d_col, int n, double shift, void *d_inverse, int dtype, void *d_work, void *stream);
 
 /* ----------------------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): peak FMA issue rate of the CUDA-core pipe in the given dtype, used as the

@@ -30,6 +30,16 @@ class CnfDesc(C.Structure):
 
 
 CONV_MAX_LAYERS = 8
+DMLP_MAX_LAYERS = 8
+CIRC_MAX_TAPS = 16
+
+
+class DmlpDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nlayers", "dtype", "batch", "reserved")] + \
+               [("dims", C.c_int32 * (DMLP_MAX_LAYERS + 1)), ("d_weight", C.c_void_p * DMLP_MAX_LAYERS),
+                ("d_bias", C.c_void_p * DMLP_MAX_LAYERS), ("mu_w_off", C.c_int64 * DMLP_MAX_LAYERS),
+                ("mu_b_off", C.c_int64 * DMLP_MAX_LAYERS), ("out_scale", C.c_double)]
+
 
 
 class ConvLayer(C.Structure):
@@ -88,6 +98,15 @@ _SIGNATURES = {
     "pnode_slice_rows": (C.c_int, [_i, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "pnode_slice_cols": (C.c_int, [_i, _vp, _i64, _i, _i, _vp, _vp, _vp, _d, _vp]),
     "pnode_sliced_gemm": (C.c_int, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _d, _vp, _i, _vp, _i64, _i, _vp]),
+    "pnode_dmlp_weight_bytes": (_i64, [C.POINTER(DmlpDesc)]),
+    "pnode_dmlp_act_bytes": (_i64, [C.POINTER(DmlpDesc)]),
+    "pnode_dmlp_work_bytes": (_i64, [C.POINTER(DmlpDesc)]),
+    "pnode_dmlp_prepare": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp]),
+    "pnode_dmlp_forward": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnode_dmlp_vjp": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp]),
+    "pnode_circulant_apply": (C.c_int, [_vp, _vp, _i, _i, C.POINTER(C.c_int32), C.POINTER(_d), _i, _i, _i, _vp]),
+    "pnode_circulant_work_bytes": (_i64, [_i]),
+    "pnode_circulant_inverse": (C.c_int, [_vp, _i, _d, _vp, _i, _vp, _vp]),
     "pnode_peak_fma": (C.c_int, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float)]),
     "pnode_tanh_probe": (C.c_int, [_vp, _vp, _i64, _i, _vp]),
     "pnode_acc128_probe": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),

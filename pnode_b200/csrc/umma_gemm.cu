@@ -21,11 +21,10 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace pnode {
 namespace umma {
-
-constexpr int KIND_I8 = PNODE_SLICED_I8, KIND_TF32 = PNODE_SLICED_TF32;
 
 template <int KIND>
 struct Cfg;
@@ -45,7 +44,7 @@ struct Epilogue {
     long long ldc;
     const int *ea, *eb;  // row exponents of A / of B (i8 only)
     double alpha;
-    const void *bias;    // [N] added after alpha (NULL: none)
+    const void *bias;    // [N] added before alpha (NULL: none)
     const void *mask;    // [M][ldmask]: result kept where mask > 0, else 0 (ReLU backward); NULL: none
     long long ldmask;
     int relu, accumulate;
@@ -262,8 +261,8 @@ __global__ void __launch_bounds__(192, 1)
                     if (n < N) {
                         double x = v[q];
                         if constexpr (KIND == KIND_I8) x = x * srow * pow2(ep.eb[n]);
-                        x *= ep.alpha;
                         if (ep.bias) x += (double)reinterpret_cast<const Out *>(ep.bias)[n];
+                        x *= ep.alpha;
                         if (ep.relu) x = x > 0.0 ? x : 0.0;
                         if (mrow) x = ((double)mrow[n] > 0.0) ? x : 0.0;
                         if (ep.accumulate) x += (double)crow[n];
@@ -446,10 +445,6 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static inline long long pitch_bytes(int kind, int k) {
-    const long long b = (long long)k * (kind == KIND_I8 ? 1 : 4);
-    return (b + 127) / 128 * 128;
-}
 
 template <int KIND>
 static int make_map(CUtensorMap *map, const void *base, int rows, int k, int box_rows) {

@@ -21,6 +21,8 @@ from . import tableaux
 from .controller import TimeLoop
 from .device import DeviceOps
 from .convblock import ConvBlockCallbacks, recognise_convblock
+from .densemlp import (CirculantCallbacks, CirculantSolver, DenseMlpCallbacks, recognise_circulant,
+                       recognise_relu_mlp)
 from .engine import Callbacks, GenericTS, ImplicitSolver
 from .errors import Error
 from .fused import FusedCnfRK, FusedMlpRK, recognise_cnf, recognise_mlp
@@ -133,6 +135,20 @@ class ODEPetsc(object):
                     self._cb_im = ConvBlockCallbacks(func, self.tensor_size)
                     self._rhs_kind = "convblock"
             self._cb_ex = self._cb_im if self.funcEX is self.funcIM else Callbacks(self.funcEX, self.tensor_size)
+            if Options().getString("pnode_fused", "1") not in ("0", "false", "no") and self._rhs_kind == "torch":
+                # wide ReLU MLP (SINODE explicit half / plain MLP right-hand side): tensor-core evaluator
+                spec = recognise_relu_mlp(self.funcEX, u_tensor)
+                if spec is not None:
+                    cb = DenseMlpCallbacks(self.funcEX, self.tensor_size, spec[0], spec[1])
+                    if self._cb_ex is self._cb_im:
+                        self._cb_im = cb
+                    self._cb_ex = cb
+                    self._rhs_kind = "dense-mlp"
+                if imex_form:
+                    col = recognise_circulant(self.funcIM, u_tensor)
+                    if col is not None:
+                        self._cb_im = CirculantCallbacks(self.funcIM, self.tensor_size, col, u_tensor.dtype, u_tensor.device)
+                        self._rhs_kind = (self._rhs_kind + "+circulant") if self._rhs_kind != "torch" else "circulant"
             if imex_form:
                 self.npIM, self.npEX = self._cb_im.nparams, self._cb_ex.nparams
                 self.np = self.npIM + self.npEX
@@ -181,7 +197,10 @@ class ODEPetsc(object):
         self._ksponly = opt.getString("snes_type") == "ksponly"
         self._monitor = opt.hasName("ts_monitor")
         self._allow_fused = opt.getString("pnode_fused", "1") not in ("0", "false", "no")
-        self._imp = ImplicitSolver(self._ops, self._cb_im, self.linear_solver, self.batch_size, self._ksponly,
+        solver_cls = ImplicitSolver
+        if isinstance(self._cb_im, CirculantCallbacks) and self.linear_solver == "torch" and self.mass is None:
+            solver_cls = CirculantSolver
+        self._imp = solver_cls(self._ops, self._cb_im, self.linear_solver, self.batch_size, self._ksponly,
                                    rtol=opt.getReal("snes_rtol", 1e-8), max_it=opt.getInt("snes_max_it", 50),
                                    ksp_rtol=opt.getReal("ksp_rtol", 1e-5), ksp_max_it=opt.getInt("ksp_max_it", 10000))
         self._imp.fixed_jacobian = bool(self.fixed_jacobian)

@@ -64,7 +64,7 @@ def slice_cols(x, into=None, colsum=None, coef=0.0):
 
 
 def gemm(a, b, out=None, alpha=1.0, bias=None, relu=False, mask=None, accumulate=False):
-    """out[m][n] (+)= mask(relu(alpha * sum_k a[m][k] b[n][k] + bias[n]))."""
+    """out[m][n] (+)= mask(relu(alpha * (sum_k a[m][k] b[n][k] + bias[n])))."""
     if a.kind != b.kind or a.k != b.k:
         raise Error(-13, "sliced gemm: operand kinds / reduction lengths differ")
     dtype = torch.float64 if a.kind == I8 else torch.float32

@@ -105,7 +105,8 @@ def test_config5_sinode_ks_imex(name):
     o, p = _pair(argv, [f_im, f_ex], dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch",
                                           fixed_jacobian_across_solves=True), u0, t, gout, 0.2)
     assert p[3].npIM == 0 and p[3].npEX == 146464  # npEX = 146,464 at N = 64
-    _compare(p, o, 1e-9)
+    assert p[3].path == "generic+dense-mlp+circulant-rhs"  # tensor-core MLP + circulant implicit operator
+    _compare(p, o, 1e-10)
 
 
 def test_config5_fixed_jacobian_is_kept_across_solves_and_stage_graphs_are_reused():
@@ -119,7 +120,8 @@ def test_config5_fixed_jacobian_is_kept_across_solves_and_stage_graphs_are_reuse
     u0 = (0.5 * torch.randn(B, N, generator=g, dtype=torch.float64)).cuda()
     t = torch.tensor([0.0, 0.2], dtype=torch.float64).cuda()
     gout = torch.randn(2, B, N, generator=g, dtype=torch.float64).cuda()
-    Options.insert_args(["-ts_adapt_type", "none", "-snes_type", "ksponly"])
+    Options.clear_all()
+    Options.insert_args(["-ts_adapt_type", "none", "-snes_type", "ksponly", "-pnode_fused", "0"])  # the generic engine
 
     def solve(ode):
         f_ex.zero_grad(set_to_none=True)
