@@ -214,6 +214,13 @@ def cfg5(N=1024, B=256, dtype="f64"):
     return build
 
 
+def config_table():
+    return {"1": ("cfg1", cfg1), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
+            "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
+            "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)),
+            "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32"))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,3L,4,5")
@@ -233,10 +240,7 @@ def main():
         fl, ms = C.c_double(), C.c_float()
         _lib.check(lib.pnode_peak_fma(code, 20000, C.byref(fl), C.byref(ms)))
         pk[key] = fl.value / (ms.value * 1e-3) / 1e12
-    table = {"1": ("cfg1", cfg1), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
-             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
-             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)), "5": ("cfg5", cfg5()),
-             "5S": ("cfg5-f32", cfg5(dtype="f32"))}
+    table = config_table()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "a") as fo:
         for c in args.configs.split(","):

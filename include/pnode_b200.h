@@ -300,6 +300,9 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
  *   PNODE_SLICED_I8   fp64 source: x[r][c] = 2^exp[r] * sum_s q_s[r][c] * 2^-(6+7s), q_s int8, S = PNODE_I8_SLICES
  *                     (Ozaki splitting: int8 x int8 -> int32 products are exact; 48 bits of every entry relative to
  *                     its row maximum are kept)
+ *   PNODE_SLICED_I8X  the same with S = PNODE_I8X_SLICES (55 bits): the truncation error of a sliced product is relative to
+ *                     (row maximum)(column maximum), so products whose terms cancel by many orders of magnitude -- applying
+ *                     (shift I - J)^-1 of a stiff operator to a rough vector -- need the extra digit to stay at fp64 level
  *   PNODE_SLICED_TF32 fp32 source: x = hi + lo with hi = tf32(x), S = 2 (3xTF32: hi.hi + hi.lo + lo.hi)
  * pnode_slice_rows slices x itself (operand row = row of x); pnode_slice_cols slices x^T (operand row = column of x,
  * reduction over the rows of x) and can add coef * (column sums of x) into d_colsum (bias gradients).
@@ -310,7 +313,9 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
  * -------------------------------------------------------------------------------------------------------------- */
 #define PNODE_SLICED_I8 0
 #define PNODE_SLICED_TF32 1
+#define PNODE_SLICED_I8X 2   /* int8 slices with one more digit (55 bits): for products with heavy cancellation */
 #define PNODE_I8_SLICES 7
+#define PNODE_I8X_SLICES 8
 int64_t pnode_sliced_bytes(int kind, int rows, int k);
 int pnode_slice_rows(int kind, const void *d_x, int64_t ldx, int rows, int k, void *d_slices, int32_t *d_exp, void *stream);
 int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols, void *d_slices, int32_t *d_exp,

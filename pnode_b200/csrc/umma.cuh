@@ -5,11 +5,11 @@
 namespace pnode {
 namespace umma {
 
-constexpr int KIND_I8 = PNODE_SLICED_I8, KIND_TF32 = PNODE_SLICED_TF32;
+constexpr int KIND_I8 = PNODE_SLICED_I8, KIND_TF32 = PNODE_SLICED_TF32, KIND_I8X = PNODE_SLICED_I8X;
 
-inline int slices_of(int kind) { return kind == KIND_I8 ? PNODE_I8_SLICES : 2; }
+inline int slices_of(int kind) { return kind == KIND_I8 ? PNODE_I8_SLICES : (kind == KIND_I8X ? PNODE_I8X_SLICES : 2); }
 inline long long pitch_bytes(int kind, int k) {  // bytes of one operand row: k elements rounded up to 128 bytes
-    const long long b = (long long)k * (kind == KIND_I8 ? 1 : 4);
+    const long long b = (long long)k * (kind == KIND_TF32 ? 4 : 1);
     return (b + 127) / 128 * 128;
 }
 inline long long sliced_bytes(int kind, int rows, int k) { return (long long)slices_of(kind) * rows * pitch_bytes(kind, k); }

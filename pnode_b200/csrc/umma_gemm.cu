@@ -31,11 +31,19 @@ struct Cfg;
 template <>
 struct Cfg<KIND_I8> {
     static constexpr int S = PNODE_I8_SLICES, BN = 64, KB = 64, STAGES = 2, NACC = PNODE_I8_SLICES, ELEM = 1;
+    static constexpr bool INT = true;
+    using Out = double;
+};
+template <>
+struct Cfg<KIND_I8X> {  // one more slice (55 bits): products with heavy cancellation (stiff inverse apply)
+    static constexpr int S = PNODE_I8X_SLICES, BN = 64, KB = 64, STAGES = 2, NACC = PNODE_I8X_SLICES, ELEM = 1;
+    static constexpr bool INT = true;
     using Out = double;
 };
 template <>
 struct Cfg<KIND_TF32> {
     static constexpr int S = 2, BN = 64, KB = 128, STAGES = 4, NACC = 1, ELEM = 4;
+    static constexpr bool INT = false;
     using Out = float;
 };
 
@@ -91,7 +99,7 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
 }
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    if constexpr (KIND == KIND_I8) {
+    if constexpr (Cfg<KIND>::INT) {
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(
                          tmem_d),
                      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
@@ -125,7 +133,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
 // Instruction descriptor (dense, K-major A and B, M = 128, N = BN).
 template <int KIND, int BN>
 __device__ __forceinline__ constexpr uint32_t instr_desc() {
-    uint32_t fmt = KIND == KIND_I8 ? ((2u << 4) | (1u << 7) | (1u << 10))    // D = S32, A = B = signed 8 bit
+    uint32_t fmt = Cfg<KIND>::INT ? ((2u << 4) | (1u << 7) | (1u << 10))    // D = S32, A = B = signed 8 bit
                                    : ((1u << 4) | (2u << 7) | (2u << 10));   // D = F32, A = B = TF32
     return fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
@@ -209,8 +217,8 @@ __global__ void __launch_bounds__(192, 1)
                         const int j = d - i;
                         const uint64_t ad = smem_desc<KB>(sa + i * A_TILE) + (uint64_t)(k * 2);
                         const uint64_t bd = smem_desc<KB>(sb + j * B_TILE) + (uint64_t)(k * 2);
-                        const int acc = (KIND == KIND_I8) ? d : 0;
-                        const bool first = (kb == 0) && (k == 0) && (i == 0) && (KIND == KIND_I8 || d == 0);
+                        const int acc = C::INT ? d : 0;
+                        const bool first = (kb == 0) && (k == 0) && (i == 0) && (C::INT || d == 0);
                         tc_mma<KIND>(tmem_base + acc * BN, ad, bd, idesc, first ? 0u : 1u);
                     }
                 }
@@ -219,18 +227,21 @@ __global__ void __launch_bounds__(192, 1)
         }
         tc_commit(accfull);
     } else if (warp < 4) {
-        // ---- epilogue: thread = one row of the tile (TMEM lane), 8 columns at a time ----
+        // ---- epilogue.  Phase 1: thread = one row of the tile (TMEM lane): combine the diagonals, scale by the row
+        // exponent, park the row in shared memory (the pipeline stages are free once the last MMA has completed).
+        // Phase 2: the warp walks over its 32 rows with lanes along the columns: coalesced bias / mask / accumulate / store.
         mbar_wait(accfull, 0);
         tc_fence_after();
-        const int m = m0 + warp * 32 + lane;
+        constexpr int TP = BN + 1;  // row pitch of the parked tile (elements): conflict-free for both phases
+        static_assert(128 * TP * (int)sizeof(Out) <= STAGE_BYTES, "parked tile does not fit one pipeline stage");
+        Out *tile = reinterpret_cast<Out *>(smem) + (warp * 32) * TP;
+        const int mrow0 = m0 + warp * 32;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         double srow = 1.0;
-        if constexpr (KIND == KIND_I8) srow = (m < M) ? pow2(ep.ea[m]) : 0.0;
-        Out *crow = reinterpret_cast<Out *>(ep.C) + (long long)m * ep.ldc;
-        const Out *mrow = ep.mask ? reinterpret_cast<const Out *>(ep.mask) + (long long)m * ep.ldmask : nullptr;
+        if constexpr (C::INT) srow = (mrow0 + lane < M) ? pow2(ep.ea[mrow0 + lane]) : 0.0;
         for (int c0 = 0; c0 < BN; c0 += 8) {
             double v[8];
-            if constexpr (KIND == KIND_I8) {
+            if constexpr (C::INT) {
                 uint32_t r[S][8];
 #pragma unroll
                 for (int d = 0; d < S; ++d) tc_ld8(trow + d * BN + c0, r[d]);
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(192, 1)
                     for (int d = NH; d < S; ++d) lo = lo * 128 + (long long)(int)r[d][q];
                     double x = (double)hi * pow2(-(12 + 7 * (NH - 1)));
                     if (S > NH) x = fma((double)lo, pow2(-(12 + 7 * (S - 1))), x);
-                    v[q] = x;
+                    v[q] = x * srow;
                 }
             } else {
                 uint32_t r[8];
@@ -254,20 +265,34 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = (double)__uint_as_float(r[q]);
             }
-            if (m < M) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n = n0 + c0 + q;
-                    if (n < N) {
-                        double x = v[q];
-                        if constexpr (KIND == KIND_I8) x = x * srow * pow2(ep.eb[n]);
-                        if (ep.bias) x += (double)reinterpret_cast<const Out *>(ep.bias)[n];
-                        x *= ep.alpha;
-                        if (ep.relu) x = x > 0.0 ? x : 0.0;
-                        if (mrow) x = ((double)mrow[n] > 0.0) ? x : 0.0;
-                        if (ep.accumulate) x += (double)crow[n];
-                        crow[n] = (Out)x;
-                    }
+            for (int q = 0; q < 8; ++q) tile[lane * TP + c0 + q] = (Out)v[q];
+        }
+        __syncwarp();
+        constexpr int NH2 = BN / 32;
+        double scol[NH2], bcol[NH2];
+#pragma unroll
+        for (int h = 0; h < NH2; ++h) {
+            const int n = n0 + lane + 32 * h;
+            scol[h] = 1.0, bcol[h] = 0.0;
+            if (n < N) {
+                if constexpr (C::INT) scol[h] = pow2(ep.eb[n]);
+                if (ep.bias) bcol[h] = (double)reinterpret_cast<const Out *>(ep.bias)[n];
+            }
+        }
+        const int rows = min(32, M - mrow0);
+        for (int r = 0; r < rows; ++r) {
+            Out *crow = reinterpret_cast<Out *>(ep.C) + (long long)(mrow0 + r) * ep.ldc;
+            const Out *mrow = ep.mask ? reinterpret_cast<const Out *>(ep.mask) + (long long)(mrow0 + r) * ep.ldmask : nullptr;
+#pragma unroll
+            for (int h = 0; h < NH2; ++h) {
+                const int n = n0 + lane + 32 * h;
+                if (n < N) {
+                    double x = ((double)tile[r * TP + lane + 32 * h] * scol[h] + bcol[h]) * ep.alpha;
+                    if (ep.relu) x = x > 0.0 ? x : 0.0;
+                    if (mrow) x = ((double)mrow[n] > 0.0) ? x : 0.0;
+                    if (ep.accumulate) x += (double)crow[n];
+                    crow[n] = (Out)x;
                 }
             }
         }
@@ -281,11 +306,14 @@ __global__ void __launch_bounds__(192, 1)
 }
 
 // ---- operand slicing ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int exponent_above(double amax) {  // smallest e with amax < 2^e (0 for amax == 0)
-    if (!(amax > 0.0)) return 0;
+constexpr int EXP_SENTINEL = (int)0x80808080;  // cudaMemsetAsync(0x80) pattern: below every real exponent
+
+__device__ __forceinline__ int exponent_above(double amax) {  // smallest e with amax < 2^e (sentinel for amax == 0)
+    if (!(amax > 0.0)) return EXP_SENTINEL;
     int e = (int)((__double_as_longlong(amax) >> 52) & 0x7ff) - 1022;
     return e < -960 ? -960 : (e > 960 ? 960 : e);
 }
+__device__ __forceinline__ int exponent_or_zero(int e) { return e == EXP_SENTINEL ? 0 : e; }
 
 template <typename T>
 __device__ __forceinline__ T block_max(T v, T *sh) {
@@ -306,6 +334,22 @@ __device__ __forceinline__ float tf32_round(float x) {  // round to nearest even
     return __uint_as_float(u & 0xffffe000u);
 }
 
+// int8 digits of NV values already scaled to |v| < 64: digit s = rint(v), v <- 128 (v - digit); packed little-endian.
+template <int S, int NV>
+__device__ __forceinline__ void digits(double (&res)[NV], uint32_t (&pack)[S][NV / 4]) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int w = 0; w < NV / 4; ++w) pack[s][w] = 0;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const double qd = rint(res[q]);
+            res[q] = (res[q] - qd) * 128.0;
+            pack[s][q >> 2] |= ((uint32_t)(int)qd & 0xffu) << (8 * (q & 3));
+        }
+    }
+}
+
 // Row slicing: operand row r = x[r][0..k).  One block per row.  out: [S][rows][pitch bytes].
 template <int KIND>
 __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int k, uint8_t *out, long long pitch,
@@ -313,31 +357,25 @@ __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int 
     using C = Cfg<KIND>;
     const int r = blockIdx.x;
     const long long slice_stride = (long long)rows * pitch;
-    if constexpr (KIND == KIND_I8) {
+    if constexpr (C::INT) {
         __shared__ double sh[8];
         const double *x = reinterpret_cast<const double *>(xin) + (long long)r * ldx;
         double amax = 0.0;
         for (int c = threadIdx.x; c < k; c += blockDim.x) amax = fmax(amax, fabs(x[c]));
         amax = block_max(amax, sh);
-        const int e = exponent_above(amax);
+        const int e = exponent_or_zero(exponent_above(amax));
         if (threadIdx.x == 0) exps[r] = e;
         const double sc = pow2(6 - e);
-        int8_t *o = reinterpret_cast<int8_t *>(out) + (long long)r * pitch;
+        uint8_t *o = out + (long long)r * pitch;
         for (int c = threadIdx.x * 4; c < k; c += blockDim.x * 4) {
             double res[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) res[q] = (c + q < k) ? x[c + q] * sc : 0.0;
+            uint32_t pack[C::S][1];
+            digits<C::S, 4>(res, pack);
 #pragma unroll
-            for (int s = 0; s < C::S; ++s) {
-                uint32_t pack = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double qd = rint(res[q]);
-                    res[q] = (res[q] - qd) * 128.0;
-                    pack |= ((uint32_t)(int)qd & 0xffu) << (8 * q);
-                }
-                *reinterpret_cast<uint32_t *>(o + s * slice_stride + c) = pack;  // pitch is a multiple of 128: in bounds
-            }
+            for (int s = 0; s < C::S; ++s)
+                *reinterpret_cast<uint32_t *>(o + s * slice_stride + c) = pack[s][0];  // pitch % 128 == 0: in bounds
         }
     } else {
         const float *x = reinterpret_cast<const float *>(xin) + (long long)r * ldx;
@@ -351,81 +389,93 @@ __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int 
     }
 }
 
-// Column slicing: operand row c = x[0..rows)[c] (the operand is x^T, reduction over the rows of x).
-// Block = 256 threads = 32 columns x 8 row groups.  out: [S][cols][pitch bytes].  Optionally colsum[c] += coef*sum_r x[r][c].
-template <int KIND>
-__global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int cols, uint8_t *out, long long pitch,
-                                  int *exps, void *colsum, double coef) {
-    using C = Cfg<KIND>;
+// Column slicing (operand = x^T: operand row c = column c of x, reduction over the rows of x), three small kernels:
+//   col_exponent_kernel  per-column exponent: every block takes 32 columns x 256 rows, atomicMax on exps[c] (an integer
+//                        maximum: exact and order independent; exps is preset to the sentinel)
+//   slice_cols_kernel    32 columns x 128 rows per block: a thread turns 16 consecutive rows of its column into one
+//                        16-byte store per slice (fp32: two coalesced-by-row streams through a shared-memory transpose)
+//   col_sum_kernel       colsum[c] += coef * sum_r x[r][c] in a fixed order (bias gradients)
+__global__ void col_exponent_kernel(const double *x, long long ldx, int rows, int cols, int *exps) {
     const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
-    const long long slice_stride = (long long)cols * pitch;
-    const int rows_per = (((rows + 7) / 8) + 3) / 4 * 4;  // multiple of 4: packed 4-byte stores along the row index
-    const int rbeg = rg * rows_per, rend = min(rows, rbeg + rows_per);
-    __shared__ double sh_max[8][33], sh_sum[8][33];
-    if constexpr (KIND == KIND_I8) {
-        const double *x = reinterpret_cast<const double *>(xin);
-        double amax = 0.0, sum = 0.0;
-        if (c < cols)
-            for (int r = rbeg; r < rend; ++r) {
-                const double v = x[(long long)r * ldx + c];
-                amax = fmax(amax, fabs(v));
-                sum += v;
-            }
-        sh_max[rg][cl] = amax;
-        sh_sum[rg][cl] = sum;
-        __syncthreads();
-        amax = 0.0;
-        sum = 0.0;
-        for (int g = 0; g < 8; ++g) {
-            amax = fmax(amax, sh_max[g][cl]);
-            sum += sh_sum[g][cl];
-        }
-        if (c >= cols) return;
+    const int rbeg = blockIdx.y * 256 + rg * 32, rend = min(rows, rbeg + 32);
+    __shared__ double sh[8][33];
+    double amax = 0.0;
+    if (c < cols)
+        for (int r = rbeg; r < rend; ++r) amax = fmax(amax, fabs(x[(long long)r * ldx + c]));
+    sh[rg][cl] = amax;
+    __syncthreads();
+    if (rg == 0 && c < cols) {
+        for (int g = 1; g < 8; ++g) amax = fmax(amax, sh[g][cl]);
         const int e = exponent_above(amax);
-        if (rg == 0) {
-            exps[c] = e;
-            if (colsum) reinterpret_cast<double *>(colsum)[c] += coef * sum;
-        }
+        if (e != EXP_SENTINEL) atomicMax(exps + c, e);
+    }
+}
+
+template <int KIND>
+__global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int cols, uint8_t *out, long long pitch,
+                                  int *exps) {
+    using C = Cfg<KIND>;
+    const long long slice_stride = (long long)cols * pitch;
+    if constexpr (C::INT) {
+        const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+        const int c = blockIdx.x * 32 + cl;
+        const int r0 = blockIdx.y * 128 + rg * 16;
+        if (c >= cols || r0 >= rows) return;
+        const double *x = reinterpret_cast<const double *>(xin);
+        const int e = exponent_or_zero(exps[c]);  // blocks with blockIdx.y > 0 may read the sentinel or the 0 written below
+        if (blockIdx.y == 0 && rg == 0 && exps[c] == EXP_SENTINEL) exps[c] = 0;
         const double sc = pow2(6 - e);
-        int8_t *o = reinterpret_cast<int8_t *>(out) + (long long)c * pitch;
-        for (int r = rbeg; r < rend; r += 4) {
-            double res[4];
+        double res[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) res[q] = (r + q < rend) ? x[(long long)(r + q) * ldx + c] * sc : 0.0;
+        for (int q = 0; q < 16; ++q) res[q] = (r0 + q < rows) ? x[(long long)(r0 + q) * ldx + c] * sc : 0.0;
+        uint32_t pack[C::S][4];
+        digits<C::S, 16>(res, pack);
+        uint8_t *o = out + (long long)c * pitch + r0;  // r0 % 16 == 0, pitch % 128 == 0: aligned and in bounds
 #pragma unroll
-            for (int s = 0; s < C::S; ++s) {
-                uint32_t pack = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double qd = rint(res[q]);
-                    res[q] = (res[q] - qd) * 128.0;
-                    pack |= ((uint32_t)(int)qd & 0xffu) << (8 * q);
-                }
-                *reinterpret_cast<uint32_t *>(o + s * slice_stride + r) = pack;  // r % 4 == 0, pitch % 128 == 0: in bounds
-            }
-        }
+        for (int s = 0; s < C::S; ++s)
+            *reinterpret_cast<uint4 *>(o + s * slice_stride) = make_uint4(pack[s][0], pack[s][1], pack[s][2], pack[s][3]);
     } else {
+        // 32 x 32 transpose tiles: coalesced reads along the columns of x, coalesced writes along its rows
+        __shared__ float th[32][33], tl[32][33];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 x 32 threads
         const float *x = reinterpret_cast<const float *>(xin);
-        double sum = 0.0;
-        if (c < cols) {
-            float *o = reinterpret_cast<float *>(out + (long long)c * pitch);
-            float *o1 = reinterpret_cast<float *>(out + slice_stride + (long long)c * pitch);
-            for (int r = rbeg; r < rend; ++r) {
-                const float v = x[(long long)r * ldx + c], hi = tf32_round(v);
-                o[r] = hi;
-                o1[r] = v - hi;
-                sum += (double)v;
+        const int cbase = blockIdx.x * 32;
+        for (int rb = blockIdx.y * 128; rb < min(rows, blockIdx.y * 128 + 128); rb += 32) {
+            for (int i = ty; i < 32; i += 8) {
+                const int r = rb + i, c = cbase + tx;
+                const float v = (r < rows && c < cols) ? x[(long long)r * ldx + c] : 0.f;
+                const float hi = tf32_round(v);
+                th[i][tx] = hi;
+                tl[i][tx] = v - hi;
             }
-        }
-        sh_sum[rg][cl] = sum;
-        __syncthreads();
-        if (rg == 0 && c < cols && colsum) {
-            sum = 0.0;
-            for (int g = 0; g < 8; ++g) sum += sh_sum[g][cl];
-            reinterpret_cast<float *>(colsum)[c] += (float)(coef * sum);
+            __syncthreads();
+            for (int i = ty; i < 32; i += 8) {
+                const int c = cbase + i, r = rb + tx;
+                if (c < cols && r < rows) {
+                    reinterpret_cast<float *>(out + (long long)c * pitch)[r] = th[tx][i];
+                    reinterpret_cast<float *>(out + slice_stride + (long long)c * pitch)[r] = tl[tx][i];
+                }
+            }
+            __syncthreads();
         }
     }
+}
+
+template <typename T>
+__global__ void col_sum_kernel(const T *x, long long ldx, int rows, int cols, T *colsum, double coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = 0;
+    for (; r + 3 < rows; r += 4) {
+        a0 += (double)x[(long long)r * ldx + c];
+        a1 += (double)x[(long long)(r + 1) * ldx + c];
+        a2 += (double)x[(long long)(r + 2) * ldx + c];
+        a3 += (double)x[(long long)(r + 3) * ldx + c];
+    }
+    for (; r < rows; ++r) a0 += (double)x[(long long)r * ldx + c];
+    colsum[c] = (T)((double)colsum[c] + coef * ((a0 + a1) + (a2 + a3)));
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -456,7 +506,7 @@ static int make_map(CUtensorMap *map, const void *base, int rows, int k, int box
     cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)rows};
     cuuint32_t box[3] = {(cuuint32_t)(C::KB / C::ELEM), (cuuint32_t)box_rows, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = fn(map, KIND == KIND_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+    CUresult r = fn(map, C::INT ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                     const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     C::KB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -489,6 +539,7 @@ int gemm(int kind, const void *a, const int *ea, const void *b, const int *eb, i
     PNODE_REQUIRE(M > 0 && N > 0 && K > 0 && K <= 65536, "umma gemm: bad shape %d x %d x %d", M, N, K);
     Epilogue ep{c, ldc, ea, eb, alpha, bias, mask, ldmask, relu, accumulate};
     if (kind == KIND_I8) return launch_gemm<KIND_I8>(a, b, M, N, K, ep, stream);
+    if (kind == KIND_I8X) return launch_gemm<KIND_I8X>(a, b, M, N, K, ep, stream);
     if (kind == KIND_TF32) return launch_gemm<KIND_TF32>(a, b, M, N, K, ep, stream);
     PNODE_REQUIRE(false, "umma gemm: unknown operand kind %d", kind);
 }
@@ -497,6 +548,8 @@ int slice_rows(int kind, const void *x, long long ldx, int rows, int k, void *ou
     const long long pitch = pitch_bytes(kind, k);
     if (kind == KIND_I8)
         slice_rows_kernel<KIND_I8><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
+    else if (kind == KIND_I8X)
+        slice_rows_kernel<KIND_I8X><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
     else
         slice_rows_kernel<KIND_TF32><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
     PNODE_CUDA_OK(cudaGetLastError());
@@ -506,11 +559,23 @@ int slice_rows(int kind, const void *x, long long ldx, int rows, int k, void *ou
 int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void *out, int *exps, void *colsum, double coef,
                cudaStream_t stream) {
     const long long pitch = pitch_bytes(kind, rows);
-    const int grid = (cols + 31) / 32;
-    if (kind == KIND_I8)
-        slice_cols_kernel<KIND_I8><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps, colsum, coef);
-    else
-        slice_cols_kernel<KIND_TF32><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps, colsum, coef);
+    dim3 grid((cols + 31) / 32, (rows + 127) / 128);
+    if (kind == KIND_TF32) {
+        slice_cols_kernel<KIND_TF32><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
+        if (colsum)
+            col_sum_kernel<float><<<(cols + 127) / 128, 128, 0, stream>>>((const float *)x, ldx, rows, cols, (float *)colsum, coef);
+    } else {
+        PNODE_CUDA_OK(cudaMemsetAsync(exps, 0x80, sizeof(int) * (size_t)cols, stream));
+        col_exponent_kernel<<<dim3((cols + 31) / 32, (rows + 255) / 256), 256, 0, stream>>>((const double *)x, ldx, rows, cols,
+                                                                                             exps);
+        if (kind == KIND_I8)
+            slice_cols_kernel<KIND_I8><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
+        else
+            slice_cols_kernel<KIND_I8X><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
+        if (colsum)
+            col_sum_kernel<double><<<(cols + 127) / 128, 128, 0, stream>>>((const double *)x, ldx, rows, cols, (double *)colsum,
+                                                                           coef);
+    }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -522,21 +587,22 @@ using namespace pnode;
 
 extern "C" {
 
+static bool known_kind(int kind) { return kind == PNODE_SLICED_I8 || kind == PNODE_SLICED_TF32 || kind == PNODE_SLICED_I8X; }
+
 int64_t pnode_sliced_bytes(int kind, int rows, int k) {
-    if (kind != PNODE_SLICED_I8 && kind != PNODE_SLICED_TF32) return -1;
-    const int S = kind == PNODE_SLICED_I8 ? PNODE_I8_SLICES : 2;
-    return (int64_t)S * rows * umma::pitch_bytes(kind, k);
+    if (!known_kind(kind)) return -1;
+    return umma::sliced_bytes(kind, rows, k);
 }
 
 int pnode_slice_rows(int kind, const void *d_x, int64_t ldx, int rows, int k, void *d_slices, int32_t *d_exp, void *stream) {
-    PNODE_REQUIRE(kind == PNODE_SLICED_I8 || kind == PNODE_SLICED_TF32, "pnode_slice_rows: unknown kind %d", kind);
+    PNODE_REQUIRE(known_kind(kind), "pnode_slice_rows: unknown kind %d", kind);
     PNODE_REQUIRE(rows > 0 && k > 0, "pnode_slice_rows: empty operand");
     return umma::slice_rows(kind, d_x, ldx, rows, k, d_slices, d_exp, (cudaStream_t)stream);
 }
 
 int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols, void *d_slices, int32_t *d_exp,
                      void *d_colsum, double coef, void *stream) {
-    PNODE_REQUIRE(kind == PNODE_SLICED_I8 || kind == PNODE_SLICED_TF32, "pnode_slice_cols: unknown kind %d", kind);
+    PNODE_REQUIRE(known_kind(kind), "pnode_slice_cols: unknown kind %d", kind);
     PNODE_REQUIRE(rows > 0 && cols > 0, "pnode_slice_cols: empty operand");
     return umma::slice_cols(kind, d_x, ldx, rows, cols, d_slices, d_exp, d_colsum, coef, (cudaStream_t)stream);
 }

@@ -360,7 +360,10 @@ class CirculantSolver(ImplicitSolver):
             dense = torch.empty(n, n, dtype=cb.dtype, device=cb.device)
             _lib.check(self.lib.pnode_circulant_inverse(col.data_ptr(), n, key, dense.data_ptr(), cb.code,
                                                         self._cwork.data_ptr(), _stream()))
-            ent = (sliced.slice_rows(dense), sliced.slice_cols(dense))  # B operands of X = R A^-T and X = R A^-1
+            # B operands of X = R A^-T and X = R A^-1.  The right-hand sides of the stiff stages are rough (K^I_0 = J u_n is
+            # ~1e7 |u_n| for KS at N = 1024) and the inverse annihilates almost all of them: the product cancels by ~7 orders
+            # of magnitude, so these operands carry the extra digit (55 bits relative to the row maximum)
+            ent = (sliced.slice_rows(dense, extended=True), sliced.slice_cols(dense, extended=True))
             self._circ[key] = ent
         return ent
 
@@ -369,7 +372,7 @@ class CirculantSolver(ImplicitSolver):
         R = rhs.view(-1, n)
         inv = self._inverse(shift)[1 if transpose else 0]
         out = torch.empty_like(R)
-        sliced.gemm(sliced.slice_rows(R), inv, out=out, alpha=alpha)
+        sliced.gemm(sliced.slice_rows(R, extended=True), inv, out=out, alpha=alpha)
         return out.reshape(-1)
 
     def solve(self, t, Z, shift, guess, aff=None):

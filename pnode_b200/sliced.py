@@ -8,12 +8,13 @@ from . import _lib
 from .device import _stream
 from .errors import Error
 
-I8, TF32 = 0, 1
+I8, TF32, I8X = 0, 1, 2
 
 
-def kind_of(dtype):
+def kind_of(dtype, extended=False):
+    """extended: one more int8 digit (55 instead of 48 bits) for products whose terms cancel by orders of magnitude."""
     if dtype == torch.float64:
-        return I8
+        return I8X if extended else I8
     if dtype == torch.float32:
         return TF32
     raise Error(-10, "sliced operands exist for float64 (int8 slices) and float32 (TF32 pairs), not %s" % dtype)
@@ -36,10 +37,10 @@ def _check2d(x):
         raise Error(-11, "sliced operand source must be a 2-d CUDA tensor with unit inner stride")
 
 
-def slice_rows(x, into=None):
+def slice_rows(x, into=None, extended=False):
     """Operand = x ([rows][k], reduction over the columns of x)."""
     _check2d(x)
-    kind = kind_of(x.dtype)
+    kind = kind_of(x.dtype, extended)
     rows, k = x.shape
     s = into if into is not None else Sliced(kind, rows, k, x.device)
     if (s.kind, s.rows, s.k) != (kind, rows, k):
@@ -49,10 +50,10 @@ def slice_rows(x, into=None):
     return s
 
 
-def slice_cols(x, into=None, colsum=None, coef=0.0):
+def slice_cols(x, into=None, colsum=None, coef=0.0, extended=False):
     """Operand = x^T ([cols][rows], reduction over the rows of x); optionally colsum += coef * x.sum(0)."""
     _check2d(x)
-    kind = kind_of(x.dtype)
+    kind = kind_of(x.dtype, extended)
     rows, cols = x.shape
     s = into if into is not None else Sliced(kind, cols, rows, x.device)
     if (s.kind, s.rows, s.k) != (kind, cols, rows):
@@ -67,7 +68,7 @@ def gemm(a, b, out=None, alpha=1.0, bias=None, relu=False, mask=None, accumulate
     """out[m][n] (+)= mask(relu(alpha * (sum_k a[m][k] b[n][k] + bias[n])))."""
     if a.kind != b.kind or a.k != b.k:
         raise Error(-13, "sliced gemm: operand kinds / reduction lengths differ")
-    dtype = torch.float64 if a.kind == I8 else torch.float32
+    dtype = torch.float32 if a.kind == TF32 else torch.float64
     if out is None:
         out = torch.empty(a.rows, b.rows, dtype=dtype, device=a.buf.device)
     if out.dtype != dtype or out.stride(1) != 1 or out.shape != (a.rows, b.rows):

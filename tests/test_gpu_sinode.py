@@ -28,7 +28,7 @@ def _mlp_pair(n, hidden, dtype, batch, seed=0, out_scale=-1.0):
     return func, DenseMlpCallbacks(func, meta.shape, spec[0], spec[1])
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 1e-4)])  # BASELINE bar: 1e-10 / 1e-4
 @pytest.mark.parametrize("n,hidden,batch", [(64, 200, 16), (96, 130, 37), (1024, 3200, 256)])
 def test_dense_mlp_forward_and_vjp_match_autograd(dtype, tol, n, hidden, batch):
     func, cb = _mlp_pair(n, hidden, dtype, batch)
@@ -49,14 +49,14 @@ def test_dense_mlp_forward_and_vjp_match_autograd(dtype, tol, n, hidden, batch):
     assert rel_err(vu.view(batch, n), gr[0]) < tol
     off = 0
     for p, gp in zip(f64.parameters(), gr[1:]):
-        assert rel_err(mu[off:off + p.numel()].view_as(p), 0.37 * gp) < tol * 5, (tuple(p.shape), off)
+        assert rel_err(mu[off:off + p.numel()].view_as(p), 0.37 * gp) < tol, (tuple(p.shape), off)
         off += p.numel()
     # the generic-interface vjp (per-parameter tensors, no kept activation set) gives the same numbers
     cb.release()
     vu2, gps = cb.vjp(0.0, u.reshape(-1).clone(), w.reshape(-1))
     assert rel_err(vu2, vu) < 1e-13 if dtype == torch.float64 else 1e-6
     for gp2, gp in zip(gps, gr[1:]):
-        assert rel_err(gp2.view_as(gp), gp) < tol * 5
+        assert rel_err(gp2.view_as(gp), gp) < tol
 
 
 def test_recognisers_refuse_what_they_cannot_reproduce():
@@ -104,7 +104,9 @@ def test_circulant_operator_and_spectral_inverse(dtype, tol, n):
     A = shift * torch.eye(n, dtype=torch.float64, device="cuda") - J
     Y = imp.solve(0.0, y.reshape(-1), shift, y.reshape(-1)).view(B, n)
     ref = shift * torch.linalg.solve(A, y.double().T).T
-    stol = 1e-11 if dtype == torch.float64 else 2e-4      # fp32: the operator's entries (1/dx^4) carry 1e-7 themselves
+    # (shift I - J) has condition number 6e6 at n = 1024 (3e2 at 64): an LU solve is good to cond * eps ~ 1e-9, and so is
+    # the spectral inverse; fp32: the operator's entries (1/dx^4) carry 1e-7 themselves
+    stol = (1e-11 if n <= 64 else 5e-9) if dtype == torch.float64 else 2e-4
     assert rel_err(Y, ref) < stol
     Yt = imp.solve_transpose(0.0, None, shift, y.reshape(-1)).view(B, n)
     assert rel_err(Yt, torch.linalg.solve(A.T, y.double().T).T) < stol

@@ -22,7 +22,7 @@ def _ops():
 
 def _unpack_i8(s):
     """Host reconstruction of an int8-sliced operand: x = 2^e sum_s q_s 2^-(6+7s)."""
-    S = 7
+    S = 8 if s.kind == 2 else 7
     pitch = s.buf.numel() // (S * s.rows)
     q = s.buf.view(torch.int8).view(S, s.rows, pitch)[:, :, :s.k].to(torch.float64).cpu()
     e = s.exp.cpu().to(torch.float64)
@@ -73,6 +73,7 @@ def case_exact_int(M, N, K):
 
 def case_gemm(dtype, M, N, K, **kw):
     sl = _ops()
+    ext = bool(kw.pop("extended", False))
     g = torch.Generator().manual_seed(M + 7 * N + 13 * K)
     a = torch.randn(M, K, generator=g, dtype=torch.float64)
     b = torch.randn(N, K, generator=g, dtype=torch.float64) * 0.01
@@ -92,11 +93,11 @@ def case_gemm(dtype, M, N, K, **kw):
     if c0 is not None:
         ref = ref + c0.double()
     out = None if c0 is None else c0.clone().cuda()
-    c = sl.gemm(sl.slice_rows(a.cuda()), sl.slice_rows(b.cuda()), out=out, alpha=alpha,
+    c = sl.gemm(sl.slice_rows(a.cuda(), extended=ext), sl.slice_rows(b.cuda(), extended=ext), out=out, alpha=alpha,
                 bias=None if bias is None else bias.cuda(), relu=bool(kw.get("relu")),
                 mask=None if mask is None else mask.cuda(), accumulate=c0 is not None)
     scale = (a.double().abs() @ b.double().abs().T).max().item() * abs(alpha)
-    return (c.double().cpu() - ref).abs().max().item() / scale, (1e-13 if dtype == torch.float64 else 5e-6)
+    return (c.double().cpu() - ref).abs().max().item() / scale, ((1e-15 if ext else 1e-13) if dtype == torch.float64 else 5e-6)
 
 
 def case_cols(dtype, M, N, K):
@@ -130,6 +131,13 @@ def test_integer_products_are_exact(shape):
 @pytest.mark.parametrize("shape", SHAPES)
 def test_gemm_matches_fp64(dtype, shape):
     err, tol = case_gemm(dtype, *shape)
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("shape", [(128, 64, 64), (256, 1024, 1024), (100, 70, 200)])
+def test_extended_slices_reach_fp64_rounding(shape):
+    """Eight digits (55 bits relative to the row maximum): the product is as good as a correctly rounded fp64 GEMM."""
+    err, tol = case_gemm(torch.float64, *shape, extended=True)
     assert err <= tol, (err, tol)
 
 
@@ -169,6 +177,9 @@ if __name__ == "__main__":
             run("gemm %s %s" % (dt, shp), case_gemm, dt, *shp)
         run("cols %s" % dt, case_cols, dt, 320, 200, 256)
         run("epi %s" % dt, case_gemm, dt, 200, 130, 300, bias=True, relu=True, mask=True, accumulate=True, alpha=0.7)
+    if torch.float64 in dts:
+        for shp in [(128, 64, 64), (256, 1024, 1024), (100, 70, 200)]:
+            run("gemm extended %s" % (shp,), case_gemm, torch.float64, *shp, extended=True)
     # timing of the SINODE layer shape
     sl = _ops()
     for dt in dts:
