@@ -6,7 +6,10 @@ examples-pnode/ode_demo_petsc.py:207-230) scaled to 2^20 synthetic trajectories,
 h = 0.025, `odeint_adjoint` + `loss.backward()`.  A "step" of this bench is one such fwd+adjoint pass over the batch.
 A trajectory-step = one sample advanced one accepted step forward plus its adjoint step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--impl reference] [--no-configs]
+Besides the headline the line carries `parity` (a 32-trajectory slice against the CPU oracle; at N > 1 bit-equality of mu
+across ranks) and `configs`: every BASELINE.json shape through the drop-in (bench_configs.py) -- ms per pass, rate, roofline,
+bounded CPU baseline at N = 1; the sharding configs (3, 4, 5) weak-scaled at N > 1.
 N>1: launched by torchrun, one rank per GPU, weak scaling (2^20 trajectories per GPU), the only collective is the NCCL
 all-reduce of mu (252 scalars) inside backward.
 """
@@ -44,8 +47,12 @@ def parse():
     ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--ntraj", type=int, default=NTRAJ, help="trajectories per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="trajectories of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 19,
+                    help="trajectories of the bounded CPU-baseline sample inside the native arm's line (the --impl reference "
+                         "arm runs the full --ntraj batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (`configs` key of the JSON line)")
+    ap.add_argument("--config-iters", type=int, default=5)
     ap.add_argument("--no-peer", action="store_true", help="N>1: all-reduce mu with NCCL instead of inside the adjoint kernel")
     return ap.parse_args()
 
@@ -60,6 +67,23 @@ def make_problem(ntraj, dtype, seed=0):
     target = torch.randn(T_OUT, ntraj, 1, 2, generator=g, dtype=torch.float64).to(dtype)
     func = SpiralFunc(dtype=dtype)
     return func, u0, t, target
+
+
+def headline_config(world, ntraj, exchange):
+    """`config` of the JSON line: the SAME object for the native and the reference arm at equal --gpus / --ntraj."""
+    w = 8
+    return {"workload": "spiral MLP 2-50-2 on y**3 (BASELINE configs[1]), 2^20 trajectories per GPU, RK4 fixed "
+                        "step, 10 output times = 9 steps of h=0.025, odeint_adjoint + loss.backward()",
+            "ntraj_per_gpu": ntraj, "global_ntraj": world * ntraj, "method": "rk4", "steps_per_pass": NSTEPS,
+            "parallelism": "batch-sharded dp%d; only exchange = all-reduce of mu (252 scalars), %s" % (world, exchange),
+            "l2": "per-pass working set (stage checkpoints %.0f MB + grad_output %.0f MB in fp64) exceeds the 126 MB L2; "
+                  "no explicit flush" % (ntraj * NSTEPS * STAGES * DIM * w / 1e6, ntraj * T_OUT * DIM * w / 1e6)}
+
+
+def exchange_desc(world, peer):
+    if world == 1:
+        return "single rank"
+    return "fused into the adjoint kernel over NVLink peer memory" if peer else "NCCL"
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -95,7 +119,7 @@ def run_reference(args):
         return
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     cores = os.cpu_count() or 1
-    ntraj = args.cpu_sample
+    ntraj = args.ntraj  # the full per-GPU batch of the native arm: same config on both arms
     torch.set_num_threads(cores)
     from oracle import OracleODEPetsc
 
@@ -116,14 +140,15 @@ def run_reference(args):
         one()
     total = time.perf_counter() - t0
     value = ntraj * NSTEPS * args.steps / total
-    sample = "%d of %d trajectories per step (same model, schedule, dtype)" % (ntraj, args.ntraj)
+    sample = "all %d trajectories of one GPU's batch per step (same model, schedule, dtype), %d warm-up + %d timed passes" % (
+        ntraj, max(args.warmup, 1), args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "spiral MLP 2-50-2, RK4 fwd + discrete adjoint, 9 steps h=0.025, bounded sample "
-                               "of the 2^20-trajectory batch", "ntraj_per_step": ntraj,
-                   "note": "reference-structured CPU restatement (PETSc unavailable: not installed, unpinned, no network)"},
+        "config": headline_config(args.gpus, ntraj, exchange_desc(args.gpus, not args.no_peer)),
+        "note": "reference-structured CPU restatement on the host cores (PETSc unavailable: not installed, unpinned, no "
+                "network); at --gpus N > 1 rank 0 alone runs ONE GPU's batch",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -190,6 +215,70 @@ def measured_peaks():
         with open(p) as f:
             return json.load(f), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def parity_check(args, dtype, dev, func, u0_h, t_h, target_h, world):
+    """32 trajectories of this rank's batch: product on the GPU (single-rank solve, the fused sweeps) vs the CPU oracle."""
+    import copy
+
+    from oracle import OracleODEPetsc
+    from pnode import petsc_adjoint
+
+    n = 32
+    u0s, tgts = u0_h[:n].clone(), target_h[:, :n].clone()
+    res = []
+    for where in ("cpu", "cuda"):
+        f = copy.deepcopy(func).to("cpu" if where == "cpu" else dev)
+        ode = OracleODEPetsc(["-ts_adapt_type", "none"]) if where == "cpu" else petsc_adjoint.ODEPetsc()
+        d = "cpu" if where == "cpu" else dev
+        ode.setupTS(u0s.to(d), f, step_size=H, method="rk4", enable_adjoint=True)
+        y0 = u0s.to(d).clone().requires_grad_(True)
+        pred = ode.odeint_adjoint(y0, t_h.to(d))
+        torch.mean(torch.abs(pred - tgts.to(d))).backward()
+        res.append((pred.detach().cpu().double(), y0.grad.cpu().double(),
+                    torch.cat([p.grad.reshape(-1) for p in f.parameters()]).cpu().double()))
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    errs = [rel(a, b) for a, b in zip(res[1], res[0])]
+    tol = 1e-10 if dtype == torch.float64 else 1e-4
+    out = {"oracle_slice": {"trajectories": n, "rel_err_trajectory": errs[0], "rel_err_lambda": errs[1], "rel_err_mu": errs[2],
+                            "tolerance": tol, "ok": max(errs) < tol}}
+    assert out["oracle_slice"]["ok"], "parity check against the oracle failed: %r" % (out,)
+    return out
+
+
+def per_config_table(args, world, rank, comm):
+    """BASELINE.json "each named shape": one entry per config through the drop-in.  N = 1: every config with its bounded CPU
+    baseline (rank 0).  N > 1: the configs that shard (3, 4, 5) weak-scaled, every rank taking part, whole-job rates."""
+    import types
+
+    import bench_configs as bc
+
+    peaks, kind = measured_peaks()
+    pk = {"hbm_gbs": peaks["hbm_gbs"], "bf16_tensor": peaks["bf16_tflops"], "source": kind}
+    import ctypes as C
+
+    from pnode_b200 import _lib
+
+    lib = _lib.load()
+    for code, key in ((_lib.F32, "fp32_fma"), (_lib.F64, "fp64_fma")):
+        fl, ms = C.c_double(), C.c_float()
+        _lib.check(lib.pnode_peak_fma(code, 20000, C.byref(fl), C.byref(ms)))
+        pk[key] = fl.value / (ms.value * 1e-3) / 1e12
+    names = ["1", "2S", "3", "3L", "4", "4b", "4c", "4d", "5", "5S"] if world == 1 else ["3L", "4", "5"]
+    a = types.SimpleNamespace(iters=args.config_iters, cpu=(world == 1 and not args.no_cpu_baseline), no_generic=True)
+    bc.SEED_OFFSET = 100 * rank
+    table, out = bc.config_table(), {"peaks": pk}
+    for c in names:
+        name, build = table[c]
+        try:
+            r = bc.run_config(name, build, a, pk, world=world, comm=comm if world > 1 else None)
+        except Exception as e:  # one failing config must not take the headline down with it
+            r = {"error": repr(e)[:300]}
+        keep = {k: r[k] for k in ("workload", "dtype", "path", "n_gpus", "ms_per_pass", "traj_steps_per_s", "accepted_steps",
+                                  "attempts", "algorithmic_tflops", "roofline", "cpu_baseline", "speedup_vs_cpu_port",
+                                  "rhs_evaluator", "error") if k in r}
+        out[name] = keep
+    return out
 
 
 def run_native(args):
@@ -292,9 +381,19 @@ def run_native(args):
             ms = float(tmax.item())
         return ms
 
+    # ---- correctness bit carried by the line: (1) a 32-trajectory slice of this rank's batch through the product against the
+    # CPU oracle; (2) at N > 1, mu after the in-kernel / NCCL all-reduce is bit-identical on every rank
+    parity = parity_check(args, dtype, dev, func, u0_h, t_h, target_h, world)
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     assert ode.path == "fused-mlp-rk", "bench must run the fused CUDA sweep, got %r" % ode.path
+    if world > 1:
+        mu_now = torch.cat([p.grad.reshape(-1) for p in func.parameters()]).contiguous()
+        gathered = [torch.empty_like(mu_now) for _ in range(world)]
+        dist.all_gather(gathered, mu_now)
+        parity["mu_bit_equal_across_ranks"] = all(torch.equal(gathered[0], gk) for gk in gathered[1:])
+        assert parity["mu_bit_equal_across_ranks"], "mu differs between ranks after the all-reduce"
     fused = ode._fused
     l0 = fused.launches + ode._ops.launches
     with ClockSampler(local) as clk:
@@ -317,20 +416,15 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "spiral MLP 2-50-2 on y**3 (BASELINE configs[1]), 2^20 trajectories per GPU, RK4 fixed "
-                               "step, 10 output times = 9 steps of h=0.025, odeint_adjoint + loss.backward()",
-                   "ntraj_per_gpu": ntraj, "global_ntraj": world * ntraj, "method": "rk4", "steps_per_pass": NSTEPS,
-                   "parallelism": "batch-sharded dp%d; only exchange = all-reduce of mu (252 scalars), %s" % (
-                       world, "single rank" if world == 1 else (
-                           "NCCL" if (ode.comm is None or ode.comm.peer is None) else
-                           "fused into the adjoint kernel over NVLink peer memory")),
-                   "l2": "per-pass working set (stage checkpoints %.0f MB + grad_output %.0f MB) exceeds the 126 MB L2; "
-                         "no explicit flush" % (ntraj * NSTEPS * STAGES * DIM * w / 1e6, ntraj * T_OUT * DIM * w / 1e6)},
+        "config": headline_config(world, ntraj, exchange_desc(world, ode.comm is not None and ode.comm.peer is not None)),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
+        "parity": parity,
     }
+    if not args.no_configs:
+        line["configs"] = per_config_table(args, world, rank, ode.comm)
 
     if rank == 0:
         # ---- per-kernel timing of the two sweeps (CUDA events on the launching stream) + rooflines -----------------

@@ -21,18 +21,32 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 
-def _time_gpu(step, iters):
+SEED_OFFSET = 0  # bench.py --gpus N: rank r draws its own shard of synthetic inputs (models stay identical)
+
+
+def _time_gpu(step, iters, world=1):
+    """Median over `iters` passes of the CUDA-event time of one pass; at world > 1 every pass is bracketed by a barrier and
+    its time is the max over ranks."""
+    import torch.distributed as dist
+
     for _ in range(3):
         step()
     ts = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0.record()
         step()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+        ts.append(ms)
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -45,12 +59,14 @@ def _time_cpu(step, reps=2):
     return 1e3 * (time.perf_counter() - t0) / reps
 
 
-def _make_step(ode_factory, funcs, u0, t, target, setup_kw, step_size, dev, each_call_setup=False):
+def _make_step(ode_factory, funcs, u0, t, target, setup_kw, step_size, dev, each_call_setup=False, comm=None):
     fs = funcs
     kw = dict(setup_kw)
     if len(fs) == 2:
         kw["func2"] = fs[1]
     ode = ode_factory()
+    if comm is not None:
+        ode.comm = comm
     ode.setupTS(u0, fs[0], step_size=step_size, enable_adjoint=True, **kw)
 
     def step():
@@ -66,38 +82,41 @@ def _make_step(ode_factory, funcs, u0, t, target, setup_kw, step_size, dev, each
     return step, ode
 
 
-def run_config(name, build, args, peaks):
-    from oracle import OracleODEPetsc
+def run_config(name, build, args, peaks, world=1, comm=None):
+    """One config through the drop-in.  world > 1 (under torchrun, every rank calls this): the batch of `spec` is the PER-GPU
+    batch (weak scaling), `comm` the run's BatchComm; the reported rate is the whole job's."""
     from pnode import petsc_adjoint
     from pnode_b200.options import Options
 
     spec = build()
-    out = {"config": name, "dtype": spec["dtype"], "workload": spec["desc"]}
+    out = {"config": name, "dtype": spec["dtype"], "workload": spec["desc"], "n_gpus": world}
     Options.clear_all()
     Options.insert_args(spec["argv"])
-    dev = torch.device("cuda:0")
+    dev = torch.device("cuda", torch.cuda.current_device())
     to_dev = spec.get("to_dev", lambda f, d: f.to(d))
     funcs = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
     u0, t, target = spec["u0"].to(dev), spec["t"].to(dev), spec["target"].to(dev)
     step, ode = _make_step(lambda: petsc_adjoint.ODEPetsc(), funcs, u0, t, target, spec["kw"], spec["step"], dev,
-                           spec.get("each_call_setup", False))
-    ms = _time_gpu(step, args.iters)
+                           spec.get("each_call_setup", False), comm=comm)
+    if comm is not None and world > 1 and spec.get("peer_reduce"):
+        comm.enable_peer_reduce()
+    ms = _time_gpu(step, args.iters, world)
     loop = ode._loop
     accepted = loop.steps
     attempts = len(loop.attempts)
-    units = spec["batch"] * accepted
+    units = spec["batch"] * accepted * world
     cb = getattr(ode, "_cb_im", None)
     if getattr(cb, "native", None) is not None:
         out["rhs_evaluator"] = "csrc/conv_block.cu" if cb.native else "library convolutions + csrc/bn_relu.cu"
     out.update({"path": ode.path, "ms_per_pass": ms, "accepted_steps": accepted, "attempts": attempts,
                 "traj_steps_per_s": units / (ms * 1e-3)})
-    flops = spec["flops_per_unit"] * units + spec.get("flops_per_rejected", 0) * spec["batch"] * (attempts - accepted)
-    tfl = flops / (ms * 1e-3) / 1e12
+    flops = (spec["flops_per_unit"] * units + spec.get("flops_per_rejected", 0) * spec["batch"] * (attempts - accepted) * world) / world
+    tfl = flops / (ms * 1e-3) / 1e12  # per GPU
     out["algorithmic_tflops"] = tfl
-    hbm = spec["bytes_per_unit"] * units / (ms * 1e-3) / 1e9
+    hbm = spec["bytes_per_unit"] * units / world / (ms * 1e-3) / 1e9
     out["roofline"] = {"pipe": spec["pipe"], "peak_tflops": peaks[spec["pipe"]], "frac": tfl / peaks[spec["pipe"]],
                        "hbm_gbs": hbm, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": hbm / peaks["hbm_gbs"]}
-    if spec.get("also_generic") and ode.path != "generic":
+    if spec.get("also_generic") and ode.path != "generic" and world == 1 and not getattr(args, "no_generic", False):
         Options.insert_args(["-pnode_fused", "0"])
         funcs_g = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
         step_g, ode_g = _make_step(lambda: petsc_adjoint.ODEPetsc(), funcs_g, u0, t, target, spec["kw"], spec["step"], dev,
@@ -107,7 +126,9 @@ def run_config(name, build, args, peaks):
         out["fused_speedup_vs_generic_path"] = ms_g / ms
         Options.clear_all()
         Options.insert_args(spec["argv"])
-    if args.cpu:
+    if args.cpu and world == 1:
+        from oracle import OracleODEPetsc
+
         torch.set_num_threads(os.cpu_count() or 1)
         cs = spec["cpu_sample"]()
         funcs_c = [copy.deepcopy(f) for f in cs["funcs"]]
@@ -136,12 +157,34 @@ def cfg1():
                                         desc="full size"))
 
 
+def cfg2(dtype="f32", ntraj=1 << 20):
+    def build():
+        from _problems import SpiralFunc
+
+        td = torch.float32 if dtype == "f32" else torch.float64
+        T, H = 10, 0.025
+        g = torch.Generator().manual_seed(SEED_OFFSET)
+        u0 = ((torch.rand(ntraj, 1, 2, generator=g, dtype=torch.float64) * 2 - 1) * 2).to(td)
+        t = torch.arange(T, dtype=torch.float64) * H
+        target = torch.randn(T, ntraj, 1, 2, generator=g, dtype=torch.float64).to(td)
+        bs = 1 << 16
+        w = 4 if dtype == "f32" else 8
+        return dict(desc="cfg2 spiral MLP 2-50-2 on y**3, 2^%d trajectories, RK4 9 steps h=0.025, %s" % (ntraj.bit_length() - 1, dtype),
+                    dtype=dtype, argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"], funcs=[SpiralFunc(dtype=td)],
+                    u0=u0, t=t, target=target, kw=dict(method="rk4"), step=H, batch=ntraj, flops_per_unit=6400,
+                    bytes_per_unit=20 * w, pipe="fp32_fma" if dtype == "f32" else "fp64_fma", peer_reduce=True,
+                    cpu_sample=lambda: dict(funcs=[SpiralFunc(dtype=td)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
+                                            kw=dict(method="rk4"), batch=bs, desc="%d of %d trajectories" % (bs, ntraj)))
+
+    return build
+
+
 def _cnf(B, dtype):
     from _workloads import CNFFunc, cnf_to
 
     def build():
         td = torch.float32 if dtype == "f32" else torch.float64
-        g = torch.Generator().manual_seed(2)
+        g = torch.Generator().manual_seed(2 + SEED_OFFSET)
         mk = lambda b: dict(
             func=CNFFunc(b, 6, (60,), dtype=td),
             u0=torch.cat((torch.randn(b, 6, generator=g, dtype=torch.float64).view(-1),
@@ -161,7 +204,7 @@ def _cnf(B, dtype):
                     funcs=[full["func"]], u0=full["u0"], t=t, target=full["target"], kw=dict(method="dopri5"), step=0.05,
                     batch=B, flops_per_unit=69120, flops_per_rejected=17280, bytes_per_unit=112 * (4 if dtype == "f32" else 8),
                     pipe="fp32_fma" if dtype == "f32" else "fp64_fma", also_generic=B <= (1 << 16), each_call_setup=True,
-                    to_dev=cnf_to, cpu_sample=cpu_sample)
+                    to_dev=cnf_to, cpu_sample=cpu_sample, peer_reduce=True)
 
     return build
 
@@ -171,7 +214,7 @@ def cfg4(C=32, HW=32, Nt=1):
         from _workloads import OdeConvBlock
 
         B = 256
-        g = torch.Generator().manual_seed(3)
+        g = torch.Generator().manual_seed(3 + SEED_OFFSET)
         u0 = torch.randn(B, C, HW, HW, generator=g)
         target = torch.randn(1, B, C, HW, HW, generator=g)
         t = torch.tensor([1.0], dtype=torch.float64)
@@ -193,7 +236,7 @@ def cfg5(N=1024, B=256, dtype="f64"):
 
     def build():
         td = torch.float64 if dtype == "f64" else torch.float32
-        g = torch.Generator().manual_seed(4)
+        g = torch.Generator().manual_seed(4 + SEED_OFFSET)
         u0 = (0.5 * torch.randn(B, N, generator=g, dtype=torch.float64)).to(td)
         target = torch.randn(2, B, N, generator=g, dtype=torch.float64).to(td)
         t = torch.tensor([0.0, 0.2], dtype=torch.float64)
@@ -215,7 +258,7 @@ def cfg5(N=1024, B=256, dtype="f64"):
 
 
 def config_table():
-    return {"1": ("cfg1", cfg1), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
+    return {"1": ("cfg1", cfg1), "2S": ("cfg2-f32", cfg2("f32")), "2D": ("cfg2-f64", cfg2("f64")), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)),
             "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32"))}

@@ -143,8 +143,12 @@ __device__ __forceinline__ double pow2(int e) {  // 2^e, |e| < 1000
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
+constexpr int EPI_WARPS = 16;                    // 4 per TMEM lane quarter: the epilogue arithmetic is latency bound with one
+constexpr int GEMM_THREADS = 32 * (EPI_WARPS + 2);  // warp per scheduler; + one TMA-producer warp + one MMA-issuer warp
+constexpr int TMA_THREAD = 32 * EPI_WARPS, MMA_THREAD = 32 * (EPI_WARPS + 1);
+
 template <int KIND>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                      int K, Epilogue ep) {
     using C = Cfg<KIND>;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(192, 1)
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
     const int num_kb = (K * C::ELEM + KB - 1) / KB;
 
-    if (threadIdx.x == 128) {
+    if (threadIdx.x == TMA_THREAD) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int s = 0; s < STAGES; ++s) {
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(192, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (threadIdx.x == 128) {
+    if (threadIdx.x == TMA_THREAD) {
         // ---- TMA producer: all slices of K block kb into stage kb % STAGES ----
         for (int kb = 0; kb < num_kb; ++kb) {
             const int st = kb % STAGES, it = kb / STAGES;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll
             for (int s = 0; s < S; ++s) tma_load_3d(sb + s * B_TILE, &map_b, &full[st], k0, n0, s);
         }
-    } else if (threadIdx.x == 160) {
+    } else if (threadIdx.x == MMA_THREAD) {
         // ---- MMA issuer: every slice pair i + j < S of this K block ----
         constexpr uint32_t idesc = instr_desc<KIND, BN>();
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -226,25 +230,30 @@ __global__ void __launch_bounds__(192, 1)
             tc_commit(&empty[st]);  // frees the stage when these MMAs have read it
         }
         tc_commit(accfull);
-    } else if (warp < 4) {
-        // ---- epilogue.  Phase 1: thread = one row of the tile (TMEM lane): combine the diagonals, scale by the row
-        // exponent, park the row in shared memory (the pipeline stages are free once the last MMA has completed).
-        // Phase 2: the warp walks over its 32 rows with lanes along the columns: coalesced bias / mask / accumulate / store.
+    } else if (warp < EPI_WARPS) {
+        // ---- epilogue: warp = TMEM lane quarter (warp % 4: a warp may only touch its own 32 lanes) x column group
+        // (warp / 4).  Phase 1: thread = one row: combine the diagonals, scale by the row exponent, park the values in shared
+        // memory (the pipeline stages are free once the last MMA has completed).  Phase 2: lanes along the columns, CW
+        // columns of 32 / CW rows per step: coalesced bias / mask / accumulate / store, loads batched for latency.
         mbar_wait(accfull, 0);
         tc_fence_after();
+        constexpr int G = EPI_WARPS / 4, CW = BN / G;  // column groups, columns per group
+        static_assert(CW % 8 == 0 && CW <= 32 && 32 % CW == 0, "epilogue column split");
         constexpr int TP = BN + 1;  // row pitch of the parked tile (elements): conflict-free for both phases
         static_assert(128 * TP * (int)sizeof(Out) <= STAGE_BYTES, "parked tile does not fit one pipeline stage");
-        Out *tile = reinterpret_cast<Out *>(smem) + (warp * 32) * TP;
-        const int mrow0 = m0 + warp * 32;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int quarter = warp & 3, cg = warp >> 2;
+        Out *tile = reinterpret_cast<Out *>(smem) + (quarter * 32) * TP + cg * CW;
+        const int mrow0 = m0 + quarter * 32;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         double srow = 1.0;
         if constexpr (C::INT) srow = (mrow0 + lane < M) ? pow2(ep.ea[mrow0 + lane]) : 0.0;
-        for (int c0 = 0; c0 < BN; c0 += 8) {
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 8) {
             double v[8];
             if constexpr (C::INT) {
                 uint32_t r[S][8];
 #pragma unroll
-                for (int d = 0; d < S; ++d) tc_ld8(trow + d * BN + c0, r[d]);
+                for (int d = 0; d < S; ++d) tc_ld8(trow + d * BN + cg * CW + c0, r[d]);
                 tc_wait_ld();
                 constexpr int NH = S < 4 ? S : 4;
 #pragma unroll
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(192, 1)
                 }
             } else {
                 uint32_t r[8];
-                tc_ld8(trow + c0, r);
+                tc_ld8(trow + cg * CW + c0, r);
                 tc_wait_ld();
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = (double)__uint_as_float(r[q]);
@@ -269,30 +278,37 @@ __global__ void __launch_bounds__(192, 1)
             for (int q = 0; q < 8; ++q) tile[lane * TP + c0 + q] = (Out)v[q];
         }
         __syncwarp();
-        constexpr int NH2 = BN / 32;
-        double scol[NH2], bcol[NH2];
-#pragma unroll
-        for (int h = 0; h < NH2; ++h) {
-            const int n = n0 + lane + 32 * h;
-            scol[h] = 1.0, bcol[h] = 0.0;
-            if (n < N) {
-                if constexpr (C::INT) scol[h] = pow2(ep.eb[n]);
-                if (ep.bias) bcol[h] = (double)reinterpret_cast<const Out *>(ep.bias)[n];
-            }
+        constexpr int RPS = 32 / CW;                 // rows per step
+        const int col = lane % CW, rsub = lane / CW; // this lane's column within the group / row within the step
+        const int n = n0 + cg * CW + col;
+        const bool ncol = n < N;
+        double scol = 1.0, bcol = 0.0;
+        if (ncol) {
+            if constexpr (C::INT) scol = pow2(ep.eb[n]);
+            if (ep.bias) bcol = (double)reinterpret_cast<const Out *>(ep.bias)[n];
         }
         const int rows = min(32, M - mrow0);
-        for (int r = 0; r < rows; ++r) {
-            Out *crow = reinterpret_cast<Out *>(ep.C) + (long long)(mrow0 + r) * ep.ldc;
-            const Out *mrow = ep.mask ? reinterpret_cast<const Out *>(ep.mask) + (long long)(mrow0 + r) * ep.ldmask : nullptr;
+        constexpr int UN = 8;
+        for (int rb = 0; rb < rows; rb += RPS * UN) {
+            double acc[UN], msk[UN];
 #pragma unroll
-            for (int h = 0; h < NH2; ++h) {
-                const int n = n0 + lane + 32 * h;
-                if (n < N) {
-                    double x = ((double)tile[r * TP + lane + 32 * h] * scol[h] + bcol[h]) * ep.alpha;
+            for (int u = 0; u < UN; ++u) {           // all global loads of the batch first
+                const int r = rb + u * RPS + rsub;
+                acc[u] = 0.0, msk[u] = 1.0;
+                if (ncol && r < rows) {
+                    const long long m = mrow0 + r;
+                    if (ep.accumulate) acc[u] = (double)reinterpret_cast<const Out *>(ep.C)[m * ep.ldc + n];
+                    if (ep.mask) msk[u] = (double)reinterpret_cast<const Out *>(ep.mask)[m * ep.ldmask + n];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int r = rb + u * RPS + rsub;
+                if (ncol && r < rows) {
+                    double x = ((double)tile[r * TP + col] * scol + bcol) * ep.alpha;
                     if (ep.relu) x = x > 0.0 ? x : 0.0;
-                    if (mrow) x = ((double)mrow[n] > 0.0) ? x : 0.0;
-                    if (ep.accumulate) x += (double)crow[n];
-                    crow[n] = (Out)x;
+                    x = msk[u] > 0.0 ? x : 0.0;
+                    reinterpret_cast<Out *>(ep.C)[(long long)(mrow0 + r) * ep.ldc + n] = (Out)(x + acc[u]);
                 }
             }
         }
@@ -395,20 +411,27 @@ __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int 
 //   slice_cols_kernel    32 columns x 128 rows per block: a thread turns 16 consecutive rows of its column into one
 //                        16-byte store per slice (fp32: two coalesced-by-row streams through a shared-memory transpose)
 //   col_sum_kernel       colsum[c] += coef * sum_r x[r][c] in a fixed order (bias gradients)
-__global__ void col_exponent_kernel(const double *x, long long ldx, int rows, int cols, int *exps) {
+__global__ void col_exponent_kernel(const double *x, long long ldx, int rows, int cols, int *exps, double *colsum,
+                                    double coef) {
     const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     const int rbeg = blockIdx.y * 256 + rg * 32, rend = min(rows, rbeg + 32);
-    __shared__ double sh[8][33];
-    double amax = 0.0;
+    __shared__ double sh[8][33], ss[8][33];
+    double amax = 0.0, sum = 0.0;
     if (c < cols)
-        for (int r = rbeg; r < rend; ++r) amax = fmax(amax, fabs(x[(long long)r * ldx + c]));
+        for (int r = rbeg; r < rend; ++r) {
+            const double v = x[(long long)r * ldx + c];
+            amax = fmax(amax, fabs(v));
+            sum += v;
+        }
     sh[rg][cl] = amax;
+    ss[rg][cl] = sum;
     __syncthreads();
     if (rg == 0 && c < cols) {
-        for (int g = 1; g < 8; ++g) amax = fmax(amax, sh[g][cl]);
+        for (int g = 1; g < 8; ++g) amax = fmax(amax, sh[g][cl]), sum += ss[g][cl];
         const int e = exponent_above(amax);
         if (e != EXP_SENTINEL) atomicMax(exps + c, e);
+        if (colsum) colsum[c] += coef * sum;  // only passed when one block covers all rows (fixed summation order)
     }
 }
 
@@ -462,20 +485,28 @@ __global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int 
     }
 }
 
+// colsum[c] += coef * sum_r x[r][c], fixed order: 32 columns x 8 row classes (r mod 8) per block.
 template <typename T>
 __global__ void col_sum_kernel(const T *x, long long ldx, int rows, int cols, T *colsum, double coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int r = 0;
-    for (; r + 3 < rows; r += 4) {
-        a0 += (double)x[(long long)r * ldx + c];
-        a1 += (double)x[(long long)(r + 1) * ldx + c];
-        a2 += (double)x[(long long)(r + 2) * ldx + c];
-        a3 += (double)x[(long long)(r + 3) * ldx + c];
+    const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    __shared__ double ss[8][33];
+    double a0 = 0.0, a1 = 0.0;
+    if (c < cols) {
+        int r = rg;
+        for (; r + 8 < rows; r += 16) {
+            a0 += (double)x[(long long)r * ldx + c];
+            a1 += (double)x[(long long)(r + 8) * ldx + c];
+        }
+        if (r < rows) a0 += (double)x[(long long)r * ldx + c];
     }
-    for (; r < rows; ++r) a0 += (double)x[(long long)r * ldx + c];
-    colsum[c] = (T)((double)colsum[c] + coef * ((a0 + a1) + (a2 + a3)));
+    ss[rg][cl] = a0 + a1;
+    __syncthreads();
+    if (rg == 0 && c < cols) {
+        double sum = ss[0][cl];
+        for (int g = 1; g < 8; ++g) sum += ss[g][cl];
+        colsum[c] = (T)((double)colsum[c] + coef * sum);
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -528,7 +559,7 @@ static int launch_gemm(const void *a, const void *b, int M, int N, int K, const 
     if (int rc = make_map<KIND>(&ma, a, M, K, 128)) return rc;
     if (int rc = make_map<KIND>(&mb, b, N, K, C::BN)) return rc;
     dim3 grid((N + C::BN - 1) / C::BN, (M + 127) / 128);
-    umma_gemm_kernel<KIND><<<grid, 192, SMEM, stream>>>(ma, mb, M, N, K, ep);
+    umma_gemm_kernel<KIND><<<grid, GEMM_THREADS, SMEM, stream>>>(ma, mb, M, N, K, ep);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -563,18 +594,19 @@ int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void 
     if (kind == KIND_TF32) {
         slice_cols_kernel<KIND_TF32><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
         if (colsum)
-            col_sum_kernel<float><<<(cols + 127) / 128, 128, 0, stream>>>((const float *)x, ldx, rows, cols, (float *)colsum, coef);
+            col_sum_kernel<float><<<(cols + 31) / 32, 256, 0, stream>>>((const float *)x, ldx, rows, cols, (float *)colsum, coef);
     } else {
         PNODE_CUDA_OK(cudaMemsetAsync(exps, 0x80, sizeof(int) * (size_t)cols, stream));
-        col_exponent_kernel<<<dim3((cols + 31) / 32, (rows + 255) / 256), 256, 0, stream>>>((const double *)x, ldx, rows, cols,
-                                                                                             exps);
+        const bool one_chunk = rows <= 256;
+        col_exponent_kernel<<<dim3((cols + 31) / 32, (rows + 255) / 256), 256, 0, stream>>>(
+            (const double *)x, ldx, rows, cols, exps, one_chunk ? (double *)colsum : nullptr, coef);
         if (kind == KIND_I8)
             slice_cols_kernel<KIND_I8><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
         else
             slice_cols_kernel<KIND_I8X><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
-        if (colsum)
-            col_sum_kernel<double><<<(cols + 127) / 128, 128, 0, stream>>>((const double *)x, ldx, rows, cols, (double *)colsum,
-                                                                           coef);
+        if (colsum && !one_chunk)
+            col_sum_kernel<double><<<(cols + 31) / 32, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (double *)colsum,
+                                                                         coef);
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
