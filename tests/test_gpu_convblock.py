@@ -212,3 +212,42 @@ def test_exact_accumulator_is_exact_and_order_independent():
     bad = torch.tensor([1.0, float("inf"), 2.0], dtype=torch.float64).cuda()
     _lib.check(lib.pnode_acc128_probe(bad.data_ptr(), 3, out.data_ptr(), work.data_ptr(), st))
     assert math.isnan(float(out.item()))
+
+
+@pytest.mark.parametrize("name,dtype,tol", [("fp64", torch.float64, 1e-10), ("fp32", torch.float32, 1e-4)])
+def test_config4_full_size_against_the_committed_oracle_fixture(name, dtype, tol):
+    """BASELINE config 4 at FULL size ([256,32,32,32], RK4, t=[1.0], one step of h=1) through the drop-in against the CPU
+    oracle's results for the same seeded inputs (tests/golden/make_cfg4_full.py): sampled entries + norms of the final state
+    and of lambda, mu in full, BatchNorm running statistics, evaluation count."""
+    import os
+
+    from pnode import petsc_adjoint
+    from pnode_b200.options import Options
+
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg4_full_%s.pt" % name))
+    B, Cc, HW = fx["B"], fx["C"], fx["HW"]
+    g = torch.Generator().manual_seed(fx["seed"])
+    u0 = torch.randn(B, Cc, HW, HW, generator=g, dtype=torch.float64).to(dtype).cuda()
+    gout = torch.randn(1, B, Cc, HW, HW, generator=g, dtype=torch.float64).to(dtype).cuda()
+    t = torch.tensor([1.0], dtype=torch.float64).cuda()
+    Options.clear_all()
+    Options.insert_args(["-ts_adapt_type", "none"])
+    func = OdeConvBlock(Cc, dtype=dtype).cuda()
+    ode = petsc_adjoint.ODEPetsc()
+    ode.setupTS(u0, func, step_size=1.0, method="rk4")
+    y0 = u0.clone().requires_grad_(True)
+    out = ode.odeint_adjoint(y0, t)
+    (out * gout).sum().backward()
+    assert ode.path == "generic+convblock-rhs" and ode._cb_im.native
+    uf, lam = out[-1].detach().reshape(-1).cpu(), y0.grad.reshape(-1).cpu()
+    mu = torch.cat([p.grad.reshape(-1) for p in func.parameters()]).cpu()
+    idx = fx["index"]
+    errs = dict(u=float((uf[idx] - fx["u_sample"]).abs().max() / fx["u_absmax"]),
+                lam=float((lam[idx] - fx["lam_sample"]).abs().max() / fx["lam_absmax"]),
+                u_norm=abs(float(uf.double().norm()) - fx["u_norm"]) / fx["u_norm"],
+                lam_norm=abs(float(lam.double().norm()) - fx["lam_norm"]) / fx["lam_norm"],
+                mu=rel_err(mu, fx["mu"]),
+                bn1_mean=rel_err(func.bn1.running_mean.cpu(), fx["bn1_running_mean"]),
+                bn5_var=rel_err(func.bn5.running_var.cpu(), fx["bn5_running_var"]))
+    assert func.nfe == fx["nfe"]
+    assert max(errs.values()) < tol, errs

@@ -127,3 +127,42 @@ def test_matrix_free_newton_gmres_on_gpu(method):
                  dict(method=method, implicit_form=True), u0, t, gout[:3], 0.1)
     assert p[3]._imp.krylov_iterations > 0
     _compare(p, o, 1e-7)
+
+
+class _Pendulum(torch.nn.Module):
+    """Index-1 pendulum DAE of examples-pnode/pendulum_DAE.py:108-117 with a trainable gravity constant."""
+
+    def __init__(self):
+        super().__init__()
+        self.g = torch.nn.Parameter(torch.tensor(9.81, dtype=torch.float64))
+
+    def forward(self, t, y):
+        g = self.g
+        return torch.stack((y[2], y[3], -y[0] * y[4], -y[1] * y[4] - g,
+                            y[4] * (y[0] ** 2 + y[1] ** 2) + g * y[1] - (y[2] ** 2 + y[3] ** 2)))
+
+
+@pytest.mark.parametrize("method", ["cn", "beuler"])
+def test_mass_matrix_dae_on_gpu(method):
+    """mass= (M u' = f, singular M: the reference's evalIFunction, petsc_adjoint.py:426-431, as examples-pnode/
+    pendulum_DAE.py:119-139 uses it) through the drop-in on the GPU: trajectory, lambda and mu against the oracle, and mu
+    against a finite difference of the discrete map."""
+    from pnode import petsc_adjoint
+
+    M = torch.eye(5, dtype=torch.float64)
+    M[-1, -1] = 0.0
+    u0 = torch.tensor([1.0, 0.0, 0.0, 1.0, 1.0], dtype=torch.float64)  # consistent initial value: lambda = |v|^2 - g y
+    t = torch.tensor([0.0, 0.02, 0.05], dtype=torch.float64)
+    gout = torch.tensor([[0.3, -0.2, 0.5, 0.1, 0.0], [1.0, 0.5, -0.3, 0.2, 0.1], [0.7, -1.0, 0.4, 0.3, -0.2]],
+                        dtype=torch.float64)
+    kw = dict(method=method, implicit_form=True, mass=M)
+    o, p = _pair(["-ts_adapt_type", "none"], [_Pendulum()], kw, u0, t, gout, 0.01)
+    _compare(p, o, 1e-9)  # Newton iterations converge to the SNES tolerance on both sides: parity to solver tolerance
+    base = (p[0].cpu() * gout).sum().item()
+    f2 = _Pendulum().cuda()
+    with torch.no_grad():
+        f2.g.add_(1e-6)
+    ode = petsc_adjoint.ODEPetsc()
+    ode.setupTS(u0.cuda(), f2, step_size=0.01, enable_adjoint=False, **kw)
+    pert = (ode.odeint(u0.cuda(), t.cuda()).cpu() * gout).sum().item()
+    assert (pert - base) / 1e-6 == pytest.approx(p[2][0].item(), rel=1e-4)
