@@ -267,6 +267,24 @@ int pnode_convblock_forward(const pnode_convblock_desc *desc, const void *d_x, v
 int pnode_convblock_vjp(const pnode_convblock_desc *desc, const void *d_x, const void *d_w, void *d_vu, void *d_grads,
                         double coef, int accumulate, void *d_act, int act_valid, void *d_work, void *stream);
 
+/* The same right-hand side on the TENSOR CORES (csrc/conv_mma.cu) for GEMM-sized shapes (few pixels, many channels: the
+ * CIFAR blocks [256,128,8,8] and [256,256,4,4]; fp32): every convolution, data gradient and weight gradient is an
+ * implicit GEMM through the sliced products above (3xTF32), BatchNorm + ReLU folded into the operand gathers, batch
+ * statistics and ReLU masks in the products' epilogues.  Same descriptor, same contract and reference lines as
+ * pnode_convblock_forward / _vjp; additionally d_wbuf (pnode_convmma_weight_bytes) holds the weight operands written by
+ * pnode_convmma_prepare once per solve, and d_work is needed by the forward as well.  N*H*W <= 65536, channel counts
+ * multiples of 4 and >= 8, kernels 1x1 / (1,3) / (3,1) with "same" padding. */
+int64_t pnode_convmma_act_bytes(const pnode_convblock_desc *desc);     /* -1: unsupported shape (pnode_last_error) */
+int64_t pnode_convmma_work_bytes(const pnode_convblock_desc *desc);
+int64_t pnode_convmma_weight_bytes(const pnode_convblock_desc *desc);
+int64_t pnode_convmma_param_count(const pnode_convblock_desc *desc);
+int pnode_convmma_prepare(const pnode_convblock_desc *desc, void *d_wbuf, void *stream);
+int pnode_convmma_forward(const pnode_convblock_desc *desc, const void *d_wbuf, const void *d_x, void *d_out,
+                          const void *d_base, double base_coef, double k_coef, void *d_k, void *d_act, void *d_work,
+                          void *stream);
+int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, const void *d_x, const void *d_w, void *d_vu,
+                      void *d_grads, double coef, int accumulate, void *d_act, int act_valid, void *d_work, void *stream);
+
 /* ----------------------------------------------------------------------------------------------------------------
  * Data-parallel variants of the adjoint sweeps: the all-reduce of mu over the GPUs of one NVLink/NVSwitch domain is fused
  * into the tail of the sweep kernel (one-shot all-reduce over peer-mapped symmetric memory: peer stores + system-scope

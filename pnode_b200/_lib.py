@@ -89,6 +89,13 @@ _SIGNATURES = {
     "pnode_convblock_param_count": (_i64, [C.POINTER(ConvBlockDesc)]),
     "pnode_convblock_forward": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp]),
     "pnode_convblock_vjp": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _d, _i, _vp, _i, _vp, _vp]),
+    "pnode_convmma_act_bytes": (_i64, [C.POINTER(ConvBlockDesc)]),
+    "pnode_convmma_work_bytes": (_i64, [C.POINTER(ConvBlockDesc)]),
+    "pnode_convmma_weight_bytes": (_i64, [C.POINTER(ConvBlockDesc)]),
+    "pnode_convmma_param_count": (_i64, [C.POINTER(ConvBlockDesc)]),
+    "pnode_convmma_prepare": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp]),
+    "pnode_convmma_forward": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
+    "pnode_convmma_vjp": (C.c_int, [C.POINTER(ConvBlockDesc), _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _i, _vp, _vp]),
     "pnode_peer_buffer_bytes": (_i64, [_i]),
     "pnode_mlp_rk_adjoint_dp": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _i, _i, C.c_uint64, _vp]),

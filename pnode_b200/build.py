@@ -13,7 +13,7 @@ OBJ = os.path.join(CSRC, "_obj")
 # (source, object, extra flags): conv_block.cu is the long pole, so its fp32 and fp64 instantiations compile as two objects
 UNITS = [("vecops.cu", "vecops.o", []), ("mlp_rk.cu", "mlp_rk.o", []), ("cnf_rk.cu", "cnf_rk.o", []),
          ("bn_relu.cu", "bn_relu.o", []), ("umma_gemm.cu", "umma_gemm.o", []),
-         ("dense_mlp.cu", "dense_mlp.o", []), ("conv_block.cu", "conv_block_f32.o", ["-DPNODE_CB_PART=1"]),
+         ("dense_mlp.cu", "dense_mlp.o", []), ("conv_mma.cu", "conv_mma.o", []), ("conv_block.cu", "conv_block_f32.o", ["-DPNODE_CB_PART=1"]),
          ("conv_block.cu", "conv_block_f64.o", ["-DPNODE_CB_PART=2"])]
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["common.cuh", "umma.cuh", os.path.join("..", "..", "include", "pnode_b200.h")]

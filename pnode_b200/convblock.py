@@ -105,7 +105,35 @@ class ConvBlockCallbacks(Callbacks):
         from .options import Options
 
         mode = Options().getString("pnode_convblock_native", "auto")  # auto | 1 (whenever the shape is supported) | 0
-        if len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4 and mode not in ("0", "false", "no"):
+        # Tensor-core evaluator (csrc/conv_mma.cu, fp32 as 3xTF32) for GEMM-sized shapes: every layer at least 32 channels
+        # wide (the CIFAR blocks [256,128,8,8] and [256,256,4,4]).  -pnode_convblock_mma auto | 1 (whenever supported) | 0
+        self.mma = False
+        mma_mode = Options().getString("pnode_convblock_mma", "auto")
+        if (len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4 and self.params[0].dtype == torch.float32
+                and mma_mode not in ("0", "false", "no") and mode not in ("0", "false", "no")):
+            wide = min(min(c.in_channels, c.out_channels) for c, _ in self.layers) >= 32
+            if wide or mma_mode in ("1", "true", "yes", "force"):
+                desc = self._make_desc()
+                nact = int(self.lib.pnode_convmma_act_bytes(C.byref(desc)))
+                if nact >= 0 and int(self.lib.pnode_convmma_param_count(C.byref(desc))) == self.nparams:
+                    self.mma = True
+                    self.native = True
+                    self._desc = desc
+                    self._act_bytes = nact
+                    self._cwork = torch.empty(int(self.lib.pnode_convmma_work_bytes(C.byref(desc))), dtype=torch.uint8,
+                                              device=dev)
+                    self._wbuf = torch.empty(int(self.lib.pnode_convmma_weight_bytes(C.byref(desc))), dtype=torch.uint8,
+                                             device=dev)
+                    self._wbuf_for = None
+                    self._act0 = torch.empty(nact, dtype=torch.uint8, device=dev)
+                    self._saved = {}
+                    self._saved_bytes = 0
+                    self._save_budget = int(float(Options().getString("pnode_convblock_save_mb", "8192")) * (1 << 20))
+                    self.reused_activations = 0
+                    self._keep = True
+                    self._comm = None
+        if (not self.mma and len(self.layers) <= _lib.CONV_MAX_LAYERS and len(tensor_size) == 4
+                and mode not in ("0", "false", "no")):
             desc = self._make_desc()
             nact = int(self.lib.pnode_convblock_act_bytes(C.byref(desc)))
             # The native kernels give one thread 4 pixels x 16 output channels: they need pixels to fill the machine.  The
@@ -164,6 +192,8 @@ class ConvBlockCallbacks(Callbacks):
                                  "exchanged inside csrc/conv_block.cu); this shape runs on library convolutions")
             return
         self._refresh_pointers(self._desc)
+        if self.mma:
+            self._prepare_weights()
         self._comm = comm if (comm is not None and comm.world > 1) else None
         d = self._desc
         if self._comm is not None:
@@ -178,6 +208,16 @@ class ConvBlockCallbacks(Callbacks):
             self._saved.clear()
             self._saved_bytes = 0
             self._keep = bool(keep)
+
+    def _prepare_weights(self):
+        """Weight operands (hi/lo, forward and data-gradient layouts) of the tensor-core evaluator: rewritten when a
+        parameter has changed (parameters are borrowed, never cached across optimiser steps)."""
+        ver = tuple((conv.weight.data_ptr(), conv.weight._version) for conv, _ in self.layers)
+        if ver != self._wbuf_for:
+            self._refresh_pointers(self._desc)
+            _lib.check(self.lib.pnode_convmma_prepare(C.byref(self._desc), self._wbuf.data_ptr(), _stream()))
+            self._wbuf_for = ver
+            self.launches += len(self.layers)
 
     def release(self):
         super().release()
@@ -212,6 +252,15 @@ class ConvBlockCallbacks(Callbacks):
         act = self._act_for(u) if keep else self._act0
         if self._comm is not None:
             self._desc.epoch = self._comm.reserve_epochs(len(self.layers))
+        if self.mma:
+            self._prepare_weights()
+            _lib.check(self.lib.pnode_convmma_forward(C.byref(self._desc), self._wbuf.data_ptr(), u.data_ptr(),
+                                                      None if out is None else out.data_ptr(),
+                                                      None if base is None else base.data_ptr(), float(base_coef),
+                                                      float(k_coef), None if k is None else k.data_ptr(), act.data_ptr(),
+                                                      self._cwork.data_ptr(), _stream()))
+            self.launches += 3 * len(self.layers) + 2
+            return out
         _lib.check(self.lib.pnode_convblock_forward(C.byref(self._desc), u.data_ptr(), None if out is None else out.data_ptr(),
                                                     None if base is None else base.data_ptr(), float(base_coef), float(k_coef),
                                                     None if k is None else k.data_ptr(), act.data_ptr(), _stream()))
@@ -227,11 +276,20 @@ class ConvBlockCallbacks(Callbacks):
         act = ent[3] if valid else self._act0
         if self._comm is not None:
             self._desc.epoch = self._comm.reserve_epochs(len(self.layers) * (1 if valid else 2))
+        L = len(self.layers)
+        if self.mma:
+            self._prepare_weights()
+            _lib.check(self.lib.pnode_convmma_vjp(C.byref(self._desc), self._wbuf.data_ptr(), u.data_ptr(), w.data_ptr(),
+                                                  None if vu is None else vu.data_ptr(),
+                                                  None if grads is None else grads.data_ptr(), float(coef), int(accumulate),
+                                                  act.data_ptr(), int(valid), self._cwork.data_ptr(), _stream()))
+            self.reused_activations += int(valid)
+            self.launches += (L + 1 if valid else 3 * L + 1) + 1 + L + (4 * L if grads is not None else 0) + 2 * L + 1
+            return vu
         _lib.check(self.lib.pnode_convblock_vjp(C.byref(self._desc), u.data_ptr(), w.data_ptr(),
                                                 None if vu is None else vu.data_ptr(),
                                                 None if grads is None else grads.data_ptr(), float(coef), int(accumulate),
                                                 act.data_ptr(), int(valid), self._cwork.data_ptr(), _stream()))
-        L = len(self.layers)
         self.reused_activations += int(valid)
         self.launches += (0 if valid else L) + 1 + (L if grads is not None else 0) + (L if want_u else L - 1) + \
             (1 if grads is not None else 0)

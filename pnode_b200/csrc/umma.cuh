@@ -14,6 +14,30 @@ inline long long pitch_bytes(int kind, int k) {  // bytes of one operand row: k 
 }
 inline long long sliced_bytes(int kind, int rows, int k) { return (long long)slices_of(kind) * rows * pitch_bytes(kind, k); }
 
+// Epilogue of one product.  Zero-initialise, then set what is needed.
+struct Epilogue {
+    void *C;
+    long long ldc;
+    const int *ea, *eb;   // row exponents of A / of B (int8 kinds only)
+    double alpha;
+    const void *bias;     // [N] added before alpha (NULL: none)
+    const void *mask;     // [M][ldmask]: result kept where mask_a[n] * mask + mask_b[n] > 0 (NULL arrays: 1 / 0), else 0
+    long long ldmask;
+    int relu, accumulate;
+    const void *mask_a, *mask_b;
+    // column statistics of the stored tile, per CTA row block: stats[blockIdx.y][n][2] = {sum x, sum x * q},
+    // stat_mode 1: q = x (sum of squares);  2: q = q_a[n] * mask + q_b[n];  0: none
+    double *stats;
+    const void *q_a, *q_b;
+    int stat_mode;
+    // split-K: kb_per_split > 0 cuts the reduction into grid.z slices of that many K blocks (64 bytes of int8 / 32 floats);
+    // slice z writes C + z * split_stride (elements)
+    int kb_per_split;
+    long long split_stride;
+};
+int gemm_ex(int kind, const void *a, const void *b, int M, int N, int K, const Epilogue &ep, cudaStream_t stream);
+int split_k_blocks(int kind, int K, int splits);  // K blocks per slice for (about) `splits` slices
+
 // C[m][n] (+)= mask(relu(alpha * (sum_k A[m][k] B[n][k] + bias[n])))
 int gemm(int kind, const void *a, const int *ea, const void *b, const int *eb, int M, int N, int K, void *c, long long ldc,
          double alpha, const void *bias, int relu, const void *mask, long long ldmask, int accumulate, cudaStream_t stream);

@@ -47,16 +47,6 @@ struct Cfg<KIND_TF32> {
     using Out = float;
 };
 
-struct Epilogue {
-    void *C;
-    long long ldc;
-    const int *ea, *eb;  // row exponents of A / of B (i8 only)
-    double alpha;
-    const void *bias;    // [N] added before alpha (NULL: none)
-    const void *mask;    // [M][ldmask]: result kept where mask > 0, else 0 (ReLU backward); NULL: none
-    long long ldmask;
-    int relu, accumulate;
-};
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,7 +158,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BN;
-    const int num_kb = (K * C::ELEM + KB - 1) / KB;
+    // split-K: grid.z slices of kb_per_split K blocks each, every slice writes its own output (C + z * split_stride)
+    const int total_kb = (K * C::ELEM + KB - 1) / KB;
+    const int kb_begin = ep.kb_per_split > 0 ? (int)blockIdx.z * ep.kb_per_split : 0;
+    const int num_kb = ep.kb_per_split > 0 ? max(0, min(ep.kb_per_split, total_kb - kb_begin)) : total_kb;
 
     if (threadIdx.x == TMA_THREAD) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -198,7 +191,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (kb >= STAGES) mbar_wait(&empty[st], (it - 1) & 1);
             uint8_t *sa = smem + st * STAGE_BYTES, *sb = sa + S * A_TILE;
             mbar_expect_tx(&full[st], STAGE_BYTES);
-            const int k0 = kb * (KB / C::ELEM);
+            const int k0 = (kb_begin + kb) * (KB / C::ELEM);
 #pragma unroll
             for (int s = 0; s < S; ++s) tma_load_3d(sa + s * A_TILE, &map_a, &full[st], k0, m0, s);
 #pragma unroll
@@ -235,8 +228,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // (warp / 4).  Phase 1: thread = one row: combine the diagonals, scale by the row exponent, park the values in shared
         // memory (the pipeline stages are free once the last MMA has completed).  Phase 2: lanes along the columns, CW
         // columns of 32 / CW rows per step: coalesced bias / mask / accumulate / store, loads batched for latency.
-        mbar_wait(accfull, 0);
-        tc_fence_after();
+        if (num_kb > 0) {
+            mbar_wait(accfull, 0);
+            tc_fence_after();
+        }
         constexpr int G = EPI_WARPS / 4, CW = BN / G;  // column groups, columns per group
         static_assert(CW % 8 == 0 && CW <= 32 && 32 % CW == 0, "epilogue column split");
         constexpr int TP = BN + 1;  // row pitch of the parked tile (elements): conflict-free for both phases
@@ -255,6 +250,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                 for (int d = 0; d < S; ++d) tc_ld8(trow + d * BN + cg * CW + c0, r[d]);
                 tc_wait_ld();
+                if (num_kb == 0) {
+#pragma unroll
+                    for (int d = 0; d < S; ++d)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) r[d][q] = 0u;
+                }
                 constexpr int NH = S < 4 ? S : 4;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 tc_ld8(trow + cg * CW + c0, r);
                 tc_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (double)__uint_as_float(r[q]);
+                for (int q = 0; q < 8; ++q) v[q] = num_kb == 0 ? 0.0 : (double)__uint_as_float(r[q]);
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) tile[lane * TP + c0 + q] = (Out)v[q];
@@ -287,6 +288,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if constexpr (C::INT) scol = pow2(ep.eb[n]);
             if (ep.bias) bcol = (double)reinterpret_cast<const Out *>(ep.bias)[n];
         }
+        double ma = 1.0, mb = 0.0, qa = 0.0, qb = 0.0;  // mask kept where ma * mask + mb > 0;  q = qa * mask + qb
+        if (ncol) {
+            if (ep.mask_a) ma = (double)reinterpret_cast<const Out *>(ep.mask_a)[n];
+            if (ep.mask_b) mb = (double)reinterpret_cast<const Out *>(ep.mask_b)[n];
+            if (ep.stat_mode == 2) {
+                qa = (double)reinterpret_cast<const Out *>(ep.q_a)[n];
+                qb = (double)reinterpret_cast<const Out *>(ep.q_b)[n];
+            }
+        }
+        double st1 = 0.0, st2 = 0.0;  // column statistics of the stored values (this lane's rows)
+        Out *cbase = reinterpret_cast<Out *>(ep.C) + (ep.kb_per_split > 0 ? (long long)blockIdx.z * ep.split_stride : 0);
         const int rows = min(32, M - mrow0);
         constexpr int UN = 8;
         for (int rb = 0; rb < rows; rb += RPS * UN) {
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 acc[u] = 0.0, msk[u] = 1.0;
                 if (ncol && r < rows) {
                     const long long m = mrow0 + r;
-                    if (ep.accumulate) acc[u] = (double)reinterpret_cast<const Out *>(ep.C)[m * ep.ldc + n];
+                    if (ep.accumulate) acc[u] = (double)cbase[m * ep.ldc + n];
                     if (ep.mask) msk[u] = (double)reinterpret_cast<const Out *>(ep.mask)[m * ep.ldmask + n];
                 }
             }
@@ -307,9 +319,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (ncol && r < rows) {
                     double x = ((double)tile[r * TP + col] * scol + bcol) * ep.alpha;
                     if (ep.relu) x = x > 0.0 ? x : 0.0;
-                    x = msk[u] > 0.0 ? x : 0.0;
-                    reinterpret_cast<Out *>(ep.C)[(long long)(mrow0 + r) * ep.ldc + n] = (Out)(x + acc[u]);
+                    x = (ma * msk[u] + mb) > 0.0 ? x : 0.0;
+                    const Out stored = (Out)(x + acc[u]);
+                    cbase[(long long)(mrow0 + r) * ep.ldc + n] = stored;
+                    if (ep.stat_mode) {
+                        const double sv = (double)stored;
+                        st1 += sv;
+                        st2 += sv * (ep.stat_mode == 1 ? sv : qa * msk[u] + qb);
+                    }
                 }
+            }
+        }
+        if (ep.stat_mode) {
+            // per-column partial sums of this CTA's 128 rows, fixed order: lanes sharing a column, then the 4 lane quarters
+#pragma unroll
+            for (int o = CW; o < 32; o <<= 1) {
+                st1 += __shfl_xor_sync(0xffffffffu, st1, o);
+                st2 += __shfl_xor_sync(0xffffffffu, st2, o);
+            }
+            double *sstat = reinterpret_cast<double *>(smem + STAGE_BYTES);  // second pipeline stage: free as well
+            if (rsub == 0) {
+                sstat[(quarter * BN + cg * CW + col) * 2 + 0] = st1;
+                sstat[(quarter * BN + cg * CW + col) * 2 + 1] = st2;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            if ((int)threadIdx.x < BN && n0 + (int)threadIdx.x < N) {
+                double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    a1 += sstat[(qd * BN + threadIdx.x) * 2 + 0];
+                    a2 += sstat[(qd * BN + threadIdx.x) * 2 + 1];
+                }
+                double *dst = ep.stats + ((long long)blockIdx.y * N + n0 + threadIdx.x) * 2;
+                dst[0] = a1, dst[1] = a2;
             }
         }
     }
@@ -558,21 +600,38 @@ static int launch_gemm(const void *a, const void *b, int M, int N, int K, const 
     CUtensorMap ma, mb;
     if (int rc = make_map<KIND>(&ma, a, M, K, 128)) return rc;
     if (int rc = make_map<KIND>(&mb, b, N, K, C::BN)) return rc;
-    dim3 grid((N + C::BN - 1) / C::BN, (M + 127) / 128);
+    int splits = 1;
+    if (ep.kb_per_split > 0) {
+        const int total_kb = (K * C::ELEM + C::KB - 1) / C::KB;
+        splits = (total_kb + ep.kb_per_split - 1) / ep.kb_per_split;
+    }
+    dim3 grid((N + C::BN - 1) / C::BN, (M + 127) / 128, splits);
     umma_gemm_kernel<KIND><<<grid, GEMM_THREADS, SMEM, stream>>>(ma, mb, M, N, K, ep);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int gemm(int kind, const void *a, const int *ea, const void *b, const int *eb, int M, int N, int K, void *c,
-         long long ldc, double alpha, const void *bias, int relu, const void *mask, long long ldmask, int accumulate,
-         cudaStream_t stream) {
+int gemm_ex(int kind, const void *a, const void *b, int M, int N, int K, const Epilogue &ep, cudaStream_t stream) {
     PNODE_REQUIRE(M > 0 && N > 0 && K > 0 && K <= 65536, "umma gemm: bad shape %d x %d x %d", M, N, K);
-    Epilogue ep{c, ldc, ea, eb, alpha, bias, mask, ldmask, relu, accumulate};
     if (kind == KIND_I8) return launch_gemm<KIND_I8>(a, b, M, N, K, ep, stream);
     if (kind == KIND_I8X) return launch_gemm<KIND_I8X>(a, b, M, N, K, ep, stream);
     if (kind == KIND_TF32) return launch_gemm<KIND_TF32>(a, b, M, N, K, ep, stream);
     PNODE_REQUIRE(false, "umma gemm: unknown operand kind %d", kind);
+}
+
+int gemm(int kind, const void *a, const int *ea, const void *b, const int *eb, int M, int N, int K, void *c,
+         long long ldc, double alpha, const void *bias, int relu, const void *mask, long long ldmask, int accumulate,
+         cudaStream_t stream) {
+    Epilogue ep{};
+    ep.C = c, ep.ldc = ldc, ep.ea = ea, ep.eb = eb, ep.alpha = alpha, ep.bias = bias, ep.mask = mask, ep.ldmask = ldmask;
+    ep.relu = relu, ep.accumulate = accumulate;
+    return gemm_ex(kind, a, b, M, N, K, ep, stream);
+}
+
+int split_k_blocks(int kind, int K, int splits) {
+    const int kb = kind == KIND_TF32 ? 128 / 4 : 64;
+    const int total = (K + kb - 1) / kb;
+    return (total + splits - 1) / splits;
 }
 
 int slice_rows(int kind, const void *x, long long ldx, int rows, int k, void *out, int *exps, cudaStream_t stream) {
