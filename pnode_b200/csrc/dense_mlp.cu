@@ -27,7 +27,7 @@ struct Layout {
     long long wf[PNODE_DMLP_MAX_LAYERS], wf_exp[PNODE_DMLP_MAX_LAYERS], wb[PNODE_DMLP_MAX_LAYERS],
         wb_exp[PNODE_DMLP_MAX_LAYERS], w_total;
     long long act_xt[PNODE_DMLP_MAX_LAYERS], act_xt_exp[PNODE_DMLP_MAX_LAYERS], act_x[PNODE_DMLP_MAX_LAYERS], act_total;
-    long long xs, xs_exp, gs, gs_exp, gt, gt_exp, d0, d1, work_total;
+    long long xs, xs_exp, gs, gs_exp, gt, gt_exp, d0, d1, colpart, work_total;
 };
 
 static int make_layout(const pnode_dmlp_desc *d, Layout &lay) {
@@ -73,6 +73,7 @@ static int make_layout(const pnode_dmlp_desc *d, Layout &lay) {
     lay.gt_exp = off, off += align256(4ll * maxdim);
     lay.d0 = off, off += align256((long long)lay.batch * maxdim * lay.esz);
     lay.d1 = off, off += align256((long long)lay.batch * maxdim * lay.esz);
+    lay.colpart = off, off += align256((long long)((lay.batch + 31) / 32) * maxdim * 8);
     lay.work_total = off;
     return 0;
 }
@@ -183,10 +184,8 @@ int pnode_dmlp_prepare(const pnode_dmlp_desc *desc, void *d_wslices, void *strea
     for (int l = 0; l < lay.L; ++l) {
         const int in = lay.dims[l], out = lay.dims[l + 1];
         PNODE_REQUIRE(desc->d_weight[l] != nullptr, "pnode_dmlp_prepare: layer %d has no weight", l);
-        if (int rc = umma::slice_rows(lay.kind, desc->d_weight[l], in, out, in, W + lay.wf[l], (int *)(W + lay.wf_exp[l]), st))
-            return rc;
-        if (int rc = umma::slice_cols(lay.kind, desc->d_weight[l], in, out, in, W + lay.wb[l], (int *)(W + lay.wb_exp[l]),
-                                      nullptr, 0.0, st))
+        if (int rc = umma::slice_both(lay.kind, desc->d_weight[l], in, out, in, W + lay.wf[l], (int *)(W + lay.wf_exp[l]),
+                                      W + lay.wb[l], (int *)(W + lay.wb_exp[l]), nullptr, 0.0, nullptr, st))
             return rc;
     }
     return 0;
@@ -204,11 +203,12 @@ int pnode_dmlp_forward(const pnode_dmlp_desc *desc, const void *d_wslices, const
     for (int l = 0; l < lay.L; ++l) {
         const int in = lay.dims[l], out = lay.dims[l + 1];
         const bool last = l == lay.L - 1;
-        if (int rc = umma::slice_rows(lay.kind, X, in, lay.batch, in, work + lay.xs, (int *)(work + lay.xs_exp), st)) return rc;
-        if (act)
-            if (int rc = umma::slice_cols(lay.kind, X, in, lay.batch, in, act + lay.act_xt[l], (int *)(act + lay.act_xt_exp[l]),
-                                          nullptr, 0.0, st))
+        if (act) {
+            if (int rc = umma::slice_both(lay.kind, X, in, lay.batch, in, work + lay.xs, (int *)(work + lay.xs_exp),
+                                          act + lay.act_xt[l], (int *)(act + lay.act_xt_exp[l]), nullptr, 0.0, nullptr, st))
                 return rc;
+        } else if (int rc = umma::slice_rows(lay.kind, X, in, lay.batch, in, work + lay.xs, (int *)(work + lay.xs_exp), st))
+            return rc;
         void *Y = last ? d_out : (act ? (void *)(act + lay.act_x[l + 1]) : (void *)(work + ((l & 1) ? lay.d1 : lay.d0)));
         if (int rc = umma::gemm(lay.kind, work + lay.xs, (const int *)(work + lay.xs_exp), W + lay.wf[l],
                                 (const int *)(W + lay.wf_exp[l]), lay.batch, out, in, Y, out, last ? desc->out_scale : 1.0,
@@ -232,14 +232,22 @@ int pnode_dmlp_vjp(const pnode_dmlp_desc *desc, const void *d_wslices, const voi
     for (int l = lay.L - 1; l >= 0; --l) {
         const int in = lay.dims[l], out = lay.dims[l + 1];
         const bool need_dx = l > 0 || d_vu != nullptr;
-        if (need_dx)
+        const bool gw = mu && desc->mu_w_off[l] >= 0, gb = mu && desc->mu_b_off[l] >= 0;
+        if (need_dx && (gw || gb)) {
+            if (int rc = umma::slice_both(lay.kind, G, out, lay.batch, out, work + lay.gs, (int *)(work + lay.gs_exp),
+                                          work + lay.gt, (int *)(work + lay.gt_exp),
+                                          gb ? mu + desc->mu_b_off[l] * lay.esz : nullptr, coef * gscale,
+                                          (double *)(work + lay.colpart), st))
+                return rc;
+        } else if (need_dx) {
             if (int rc = umma::slice_rows(lay.kind, G, out, lay.batch, out, work + lay.gs, (int *)(work + lay.gs_exp), st))
                 return rc;
-        const bool gw = mu && desc->mu_w_off[l] >= 0, gb = mu && desc->mu_b_off[l] >= 0;
-        if (gw || gb) {
+        } else if (gw || gb) {
             if (int rc = umma::slice_cols(lay.kind, G, out, lay.batch, out, work + lay.gt, (int *)(work + lay.gt_exp),
                                           gb ? mu + desc->mu_b_off[l] * lay.esz : nullptr, coef * gscale, st))
                 return rc;
+        }
+        if (gw || gb) {
             if (gw)
                 if (int rc = umma::gemm(lay.kind, work + lay.gt, (const int *)(work + lay.gt_exp), act + lay.act_xt[l],
                                         (const int *)(act + lay.act_xt_exp[l]), out, in, lay.batch,

@@ -45,5 +45,10 @@ int slice_rows(int kind, const void *x, long long ldx, int rows, int k, void *ou
 int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void *out, int *exps, void *colsum, double coef,
                cudaStream_t stream);
 
+// Both slicings of one source in one pass: rows (operand = x) and columns (operand = x^T).  colpart: scratch of
+// ceil(rows / 32) * cols doubles, needed when colsum != NULL (colsum += coef * column sums, fixed summation order).
+int slice_both(int kind, const void *x, long long ldx, int rows, int cols, void *out_r, int *exp_r, void *out_c, int *exp_c,
+               void *colsum, double coef, double *colpart, cudaStream_t stream);
+
 }  // namespace umma
 }  // namespace pnode

@@ -551,6 +551,148 @@ __global__ void col_sum_kernel(const T *x, long long ldx, int rows, int cols, T 
     }
 }
 
+// ---- fused row + column slicing of one source (an activation is the A operand of the next product by rows and the
+// B operand of a weight-gradient product by columns): one read of the source per kernel, 32 x 64 tiles --------------------
+__global__ void fill_sentinel_kernel(int *a, int na, int *b, int nb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na) a[i] = EXP_SENTINEL;
+    if (i < nb) b[i] = EXP_SENTINEL;
+}
+
+__global__ void exp_both_kernel(const double *x, long long ldx, int rows, int cols, int *exp_r, int *exp_c, double *colpart) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
+    __shared__ double cm[8][64], cs[8][64];
+    double m0 = 0.0, m1 = 0.0, s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + warp * 4 + i;
+        double v0 = 0.0, v1 = 0.0;
+        if (r < rows) {
+            if (c0 + lane < cols) v0 = x[(long long)r * ldx + c0 + lane];
+            if (c0 + lane + 32 < cols) v1 = x[(long long)r * ldx + c0 + lane + 32];
+        }
+        double rm = fmax(fabs(v0), fabs(v1));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+        if (lane == 0 && r < rows) {
+            const int e = exponent_above(rm);
+            if (e != EXP_SENTINEL) atomicMax(exp_r + r, e);
+        }
+        m0 = fmax(m0, fabs(v0)), m1 = fmax(m1, fabs(v1));
+        s0 += v0, s1 += v1;
+    }
+    cm[warp][lane] = m0, cm[warp][lane + 32] = m1;
+    cs[warp][lane] = s0, cs[warp][lane + 32] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64 && c0 + (int)threadIdx.x < cols) {
+        double m = cm[0][threadIdx.x], sum = cs[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) m = fmax(m, cm[w][threadIdx.x]), sum += cs[w][threadIdx.x];
+        const int e = exponent_above(m);
+        if (e != EXP_SENTINEL) atomicMax(exp_c + c0 + threadIdx.x, e);
+        if (colpart) colpart[(long long)blockIdx.y * cols + c0 + threadIdx.x] = sum;
+    }
+}
+
+template <int KIND>
+__global__ void slice_both_kernel(const double *x, long long ldx, int rows, int cols, uint8_t *out_r, long long pitch_r,
+                                  uint8_t *out_c, long long pitch_c, int *exp_r, int *exp_c, double *colsum, double coef,
+                                  const double *colpart, int nrt) {
+    using C = Cfg<KIND>;
+    __shared__ double tile[32][65];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        tile[r][c] = (r0 + r < rows && c0 + c < cols) ? x[(long long)(r0 + r) * ldx + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    // by rows: (row, 4 consecutive columns) -> one 4-byte store per slice
+    for (int task = threadIdx.x; task < 512; task += 256) {
+        const int r = task >> 4, cg = (task & 15) * 4;
+        if (r0 + r < rows && c0 + cg < cols) {
+            const double sc = pow2(6 - exponent_or_zero(exp_r[r0 + r]));
+            double res[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res[q] = tile[r][cg + q] * sc;
+            uint32_t pack[C::S][1];
+            digits<C::S, 4>(res, pack);
+            uint8_t *o = out_r + (long long)(r0 + r) * pitch_r + c0 + cg;
+#pragma unroll
+            for (int s = 0; s < C::S; ++s) *reinterpret_cast<uint32_t *>(o + (long long)s * rows * pitch_r) = pack[s][0];
+        }
+    }
+    // by columns: (column, 16 consecutive rows) -> one 16-byte store per slice
+    if (threadIdx.x < 128) {
+        const int c = threadIdx.x & 63, rg = (threadIdx.x >> 6) * 16;
+        if (c0 + c < cols && r0 + rg < rows) {
+            const double sc = pow2(6 - exponent_or_zero(exp_c[c0 + c]));
+            double res[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) res[q] = tile[rg + q][c] * sc;
+            uint32_t pack[C::S][4];
+            digits<C::S, 16>(res, pack);
+            uint8_t *o = out_c + (long long)(c0 + c) * pitch_c + r0 + rg;
+#pragma unroll
+            for (int s = 0; s < C::S; ++s)
+                *reinterpret_cast<uint4 *>(o + (long long)s * cols * pitch_c) = make_uint4(pack[s][0], pack[s][1], pack[s][2], pack[s][3]);
+        }
+    }
+    // all-zero rows / columns keep the sentinel: publish exponent 0 for the products' epilogues (readers treat both alike)
+    if (blockIdx.x == 0 && threadIdx.x < 32 && r0 + (int)threadIdx.x < rows && exp_r[r0 + threadIdx.x] == EXP_SENTINEL)
+        exp_r[r0 + threadIdx.x] = 0;
+    if (blockIdx.y == 0 && threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int c = c0 + (int)threadIdx.x - 64;
+        if (c < cols) {
+            if (exp_c[c] == EXP_SENTINEL) exp_c[c] = 0;
+            if (colsum) {
+                double sum = 0.0;
+                for (int t = 0; t < nrt; ++t) sum += colpart[(long long)t * cols + c];  // fixed order over the row tiles
+                colsum[c] += coef * sum;
+            }
+        }
+    }
+}
+
+// fp32: hi / lo of every entry in both layouts; column sums of the tile's 32 rows into colpart.
+__global__ void slice_both_tf32_kernel(const float *x, long long ldx, int rows, int cols, float *out_r, long long pitch_r,
+                                       float *out_c, long long pitch_c, double *colpart) {
+    __shared__ float th[32][65], tl[32][65];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
+    const long long slice_r = (long long)rows * pitch_r, slice_c = (long long)cols * pitch_c;
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        const bool in = r0 + r < rows && c0 + c < cols;
+        const float v = in ? x[(long long)(r0 + r) * ldx + c0 + c] : 0.f;
+        const float hi = tf32_round(v), lo = v - hi;
+        th[r][c] = hi, tl[r][c] = lo;
+        if (in) {
+            float *o = out_r + (long long)(r0 + r) * pitch_r + c0 + c;
+            o[0] = hi, o[slice_r] = lo;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < 64; c += 8) {
+        if (c0 + c < cols && r0 + lane < rows) {
+            float *o = out_c + (long long)(c0 + c) * pitch_c + r0 + lane;
+            o[0] = th[lane][c], o[slice_c] = tl[lane][c];
+        }
+    }
+    if (colpart && threadIdx.x < 64 && c0 + (int)threadIdx.x < cols) {
+        double sum = 0.0;
+        for (int r = 0; r < 32; ++r) sum += (double)th[r][threadIdx.x] + (double)tl[r][threadIdx.x];
+        colpart[(long long)blockIdx.y * cols + c0 + threadIdx.x] = sum;
+    }
+}
+
+__global__ void colsum_finalize_f32_kernel(const double *colpart, int nrt, int cols, float *colsum, double coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double sum = 0.0;
+    for (int t = 0; t < nrt; ++t) sum += colpart[(long long)t * cols + c];
+    colsum[c] = (float)((double)colsum[c] + coef * sum);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -666,6 +808,34 @@ int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void 
         if (colsum && !one_chunk)
             col_sum_kernel<double><<<(cols + 31) / 32, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (double *)colsum,
                                                                          coef);
+    }
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int slice_both(int kind, const void *x, long long ldx, int rows, int cols, void *out_r, int *exp_r, void *out_c, int *exp_c,
+               void *colsum, double coef, double *colpart, cudaStream_t stream) {
+    PNODE_REQUIRE(colsum == nullptr || colpart != nullptr, "slice_both: column sums need the partial-sum scratch");
+    const long long pitch_r = pitch_bytes(kind, cols), pitch_c = pitch_bytes(kind, rows);
+    dim3 grid((cols + 63) / 64, (rows + 31) / 32);
+    const int nrt = (int)grid.y;
+    if (kind == KIND_TF32) {
+        slice_both_tf32_kernel<<<grid, 256, 0, stream>>>((const float *)x, ldx, rows, cols, (float *)out_r, pitch_r / 4,
+                                                         (float *)out_c, pitch_c / 4, colsum ? colpart : nullptr);
+        if (colsum)
+            colsum_finalize_f32_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(colpart, nrt, cols, (float *)colsum, coef);
+    } else {
+        const int n = rows > cols ? rows : cols;
+        fill_sentinel_kernel<<<(n + 255) / 256, 256, 0, stream>>>(exp_r, rows, exp_c, cols);
+        exp_both_kernel<<<grid, 256, 0, stream>>>((const double *)x, ldx, rows, cols, exp_r, exp_c, colsum ? colpart : nullptr);
+        if (kind == KIND_I8)
+            slice_both_kernel<KIND_I8><<<grid, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (uint8_t *)out_r, pitch_r,
+                                                                 (uint8_t *)out_c, pitch_c, exp_r, exp_c, (double *)colsum, coef,
+                                                                 colpart, nrt);
+        else
+            slice_both_kernel<KIND_I8X><<<grid, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (uint8_t *)out_r, pitch_r,
+                                                                  (uint8_t *)out_c, pitch_c, exp_r, exp_c, (double *)colsum,
+                                                                  coef, colpart, nrt);
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;

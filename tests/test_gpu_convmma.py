@@ -70,11 +70,15 @@ def test_rhs_vjp_and_parameter_gradients(shape):
     assert rel_err(vu.view(shape), vu_r) < tol, ("J^T w", rel_err(vu.view(shape), vu_r))
     flat = lambda gs: torch.cat([q.detach().double().reshape(-1) for q in gs])
     assert rel_err(flat(gp), flat(gp_r)) < tol, ("Jp^T w", rel_err(flat(gp), flat(gp_r)))
+    gscale = float(flat(gp_r).norm()) / len(gp_r) ** 0.5
     for (n, _), a, b in zip(mine.named_parameters(), gp, gp_r):
         if "conv" in n and n.endswith("bias"):
             assert float(a.abs().max()) == 0.0  # exactly zero: the bias cancels in the BatchNorm that follows
             continue
-        assert rel_err(a.view_as(b), b) < 3 * tol, (n, rel_err(a.view_as(b), b))
+        # a gradient that vanishes analytically (BatchNorm shifts when every unit is active) is rounding noise on both sides:
+        # errors are measured against the parameter's own gradient or 1e-3 of the typical gradient, whichever is larger
+        err = float((a.view_as(b).double() - b).norm()) / max(float(b.norm()), 1e-3 * gscale)
+        assert err < 3 * tol, (n, err)
     # BatchNorm side effects: f once + each vjp once (re-evaluated or replayed from the stored statistics)
     assert int(mine.bn3.num_batches_tracked) == 3
     again = copy.deepcopy(func)

@@ -21,10 +21,11 @@ def _mlp_pair(n, hidden, dtype, batch, seed=0, out_scale=-1.0, kink_free=False):
 
     func = KSExplicit(n, hidden=hidden, dtype=dtype, seed=seed)
     if kink_free:  # every hidden unit active: the fp32 / fp64 comparison at full size involves no ReLU branch decisions
-        with torch.no_grad():
+        with torch.no_grad():  # (weights / 5 keep the row sums of W, which multiply the common shift, well below 1)
             for m in list(func.F)[:-1]:
                 if isinstance(m, torch.nn.Linear):
-                    m.bias.fill_(2.0)
+                    m.weight.mul_(0.2)
+                    m.bias.fill_(1.0)
     func = func.cuda()
     if out_scale > 0:
         func.forward = lambda t, y, F=func.F: F(y)

@@ -201,9 +201,13 @@ def test_config4_evaluator_choice_and_library_path():
     from pnode import petsc_adjoint
     from pnode_b200.convblock import ConvBlockCallbacks
 
+    Options.clear_all()
     big = ConvBlockCallbacks(OdeConvBlock(32).cuda(), torch.Size((16, 32, 32, 32)))
-    small = ConvBlockCallbacks(OdeConvBlock(256).cuda(), torch.Size((256, 256, 4, 4)))
-    assert big.native and not small.native
+    wide = ConvBlockCallbacks(OdeConvBlock(256).cuda(), torch.Size((256, 256, 4, 4)))
+    wide64 = ConvBlockCallbacks(OdeConvBlock(256, dtype=torch.float64).cuda(), torch.Size((256, 256, 4, 4)))
+    # many pixels, few channels: the CUDA-core kernels; few pixels, many channels: fp32 on the tensor cores (conv_mma.cu),
+    # fp64 (no tensor-core evaluator, too few pixels for the CUDA-core one) on library convolutions + bn_relu.cu
+    assert big.native and not big.mma and wide.native and wide.mma and not wide64.native
     C, HW, B = 16, 8, 8
     func = OdeConvBlock(C, dtype=torch.float64)
     g = torch.Generator().manual_seed(3)
