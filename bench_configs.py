@@ -107,7 +107,8 @@ def run_config(name, build, args, peaks, world=1, comm=None):
     units = spec["batch"] * accepted * world
     cb = getattr(ode, "_cb_im", None)
     if getattr(cb, "native", None) is not None:
-        out["rhs_evaluator"] = "csrc/conv_block.cu" if cb.native else "library convolutions + csrc/bn_relu.cu"
+        out["rhs_evaluator"] = ("csrc/conv_mma.cu (tcgen05 implicit GEMM, 3xTF32)" if getattr(cb, "mma", False) else
+                                "csrc/conv_block.cu") if cb.native else "library convolutions + csrc/bn_relu.cu"
     out.update({"path": ode.path, "ms_per_pass": ms, "accepted_steps": accepted, "attempts": attempts,
                 "traj_steps_per_s": units / (ms * 1e-3)})
     flops = (spec["flops_per_unit"] * units + spec.get("flops_per_rejected", 0) * spec["batch"] * (attempts - accepted) * world) / world

@@ -107,7 +107,7 @@ static int make_plan(const pnode_convblock_desc *d, Plan &p) {
         part = max(part, (long long)wgrad_slices(p.g[k], p.P, nullptr) * p.g[k].cout * p.g[k].taps * p.g[k].cin * 4);
     p.part = off, off += al256(part);
     p.stats = off, off += al256((long long)p.mtiles * p.cmax * 16);
-    p.tot = off, off += al256(4ll * p.cmax * 8);
+    p.tot = off, off += al256((4ll + 32) * p.cmax * 8);
     p.bwdc = off, off += al256(3ll * p.cmax * 4);
     p.work_total = off;
     return 0;
@@ -306,6 +306,30 @@ __global__ void weight_operands_kernel(const float *w, int cin, int cout, int ta
     }
 }
 
+// Totals of the per-row-block partial sums, fixed order: RG threads per channel take contiguous ranges of the row blocks,
+// their sums are combined in range order.  tot[c] = sum of [.][c][0], tot[C + c] = sum of [.][c][1].  All threads of the block.
+template <int RG>
+__device__ void reduce_partials(const double *partials, int mtiles, int C, double *tot, double *scratch /* [2][RG][C] */) {
+    for (int i = threadIdx.x; i < C * RG; i += blockDim.x) {
+        const int c = i % C, g = i / C;
+        const int per = (mtiles + RG - 1) / RG, m0 = g * per, m1 = min(mtiles, m0 + per);
+        double s1 = 0.0, s2 = 0.0;
+        for (int m = m0; m < m1; ++m) {
+            s1 += partials[((long long)m * C + c) * 2];
+            s2 += partials[((long long)m * C + c) * 2 + 1];
+        }
+        scratch[(long long)g * C + c] = s1;
+        scratch[(long long)(RG + g) * C + c] = s2;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int g = 0; g < RG; ++g) s1 += scratch[(long long)g * C + c], s2 += scratch[(long long)(RG + g) * C + c];
+        tot[c] = s1, tot[C + c] = s2;
+    }
+    __syncthreads();
+}
+
 // ---- BatchNorm bookkeeping (one block; the cross-GPU exchange of common.cuh needs all threads of ONE block) ----------
 struct BnFwd {
     const double *partials;  // [mtiles][C][2]
@@ -318,20 +342,13 @@ struct BnFwd {
     double *mean, *invstd;   // activation set
     float *a, *b, *qa, *qb;
     double *tot, *tot_global;  // scratch [2C] each
+    double *scratch;           // [2][16][C]
     int update_running;
 };
 
 __global__ void bn_forward_finalize_kernel(BnFwd B, PeerComm pc) {
     const int C = B.C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int m = 0; m < B.mtiles; ++m) {
-            s1 += B.partials[((long long)m * C + c) * 2];
-            s2 += B.partials[((long long)m * C + c) * 2 + 1];
-        }
-        B.tot[c] = s1, B.tot[C + c] = s2;
-    }
-    __syncthreads();
+    reduce_partials<16>(B.partials, B.mtiles, C, B.tot, B.scratch);
     const double *tot = B.tot;
     if (pc.world > 1 && pc.peer_bufs) {
         peer_allreduce_and_store<double>(B.tot, 2 * C, pc, B.tot_global);
@@ -380,20 +397,12 @@ struct BnBwd {
     float *ggamma, *gbeta, *gbias;  // gradient slots (NULL: not wanted)
     double coef;
     int accumulate, contribute;    // contribute == 0: another rank reports the (global) affine gradients
-    double *tot, *tot_global;
+    double *tot, *tot_global, *scratch;
 };
 
 __global__ void bn_backward_finalize_kernel(BnBwd B, PeerComm pc) {
     const int C = B.C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int m = 0; m < B.mtiles; ++m) {
-            s1 += B.partials[((long long)m * C + c) * 2];
-            s2 += B.partials[((long long)m * C + c) * 2 + 1];
-        }
-        B.tot[c] = s1, B.tot[C + c] = s2;
-    }
-    __syncthreads();
+    reduce_partials<16>(B.partials, B.mtiles, C, B.tot, B.scratch);
     const double *tot = B.tot;
     if (pc.world > 1 && pc.peer_bufs) {
         peer_allreduce_and_store<double>(B.tot, 2 * C, pc, B.tot_global);
@@ -421,16 +430,25 @@ __global__ void bn_backward_finalize_kernel(BnBwd B, PeerComm pc) {
     }
 }
 
-// grads_w[co][ci][t] (+)= coef * sum_s part[s][co][t*cin + ci]   (fixed order over the split-K slices)
+// grads_w[co][ci][t] (+)= coef * sum_s part[s][co][t*cin + ci]: 8 lanes per entry take contiguous ranges of the split-K
+// slices, combined in lane order (fixed order => bit-reproducible)
 __global__ void wgrad_reduce_kernel(const float *part, int splits, int cout, int cin, int taps, float *gw, double coef,
                                     int accumulate) {
     const int kc = cin * taps, total = cout * kc;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int sub = threadIdx.x & 7;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    double s = 0.0;
+    if (idx < total) {
+        const int per = (splits + 7) / 8, k0 = sub * per, k1 = min(splits, k0 + per);
+        for (int k = k0; k < k1; ++k) s += (double)part[(long long)k * total + idx];
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) sum += __shfl_sync(0xffffffffu, s, (threadIdx.x & 24) + l);
+    if (idx < total && sub == 0) {
         const int co = idx / kc, r = idx % kc, t = r / cin, ci = r % cin;
-        double s = 0.0;
-        for (int k = 0; k < splits; ++k) s += (double)part[(long long)k * total + idx];
         float *dst = gw + ((long long)co * cin + ci) * taps + t;
-        *dst = accumulate ? (float)((double)*dst + coef * s) : (float)s;
+        *dst = accumulate ? (float)((double)*dst + coef * sum) : (float)sum;
     }
 }
 
@@ -508,7 +526,8 @@ static int forward_impl(const pnode_convblock_desc *d, const Plan &p, const uint
         B.eps = l.eps, B.momentum = l.momentum, B.mean = cur.mean, B.invstd = cur.invstd;
         B.a = cur.a, B.b = cur.b, B.qa = cur.qa, B.qb = cur.qb;
         B.tot = reinterpret_cast<double *>(work + p.tot), B.tot_global = B.tot + 2 * p.cmax, B.update_running = 1;
-        bn_forward_finalize_kernel<<<1, 256, 0, st>>>(B, peer_of(d, epoch + k));
+        B.scratch = B.tot + 4 * p.cmax;
+        bn_forward_finalize_kernel<<<1, 1024, 0, st>>>(B, peer_of(d, epoch + k));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -623,8 +642,8 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
         B.mean = b.mean, B.invstd = b.invstd, B.ca = ca, B.cb = cb, B.cc = cc;
         if (grads) B.ggamma = grads + p.goff_gamma[k], B.gbeta = grads + p.goff_beta[k], B.gbias = grads + p.goff_b[k];
         B.coef = coef, B.accumulate = accumulate, B.contribute = (p.world == 1 || p.rank == 0) ? 1 : 0;
-        B.tot = tot, B.tot_global = tot + 2 * p.cmax;
-        cmma::bn_backward_finalize_kernel<<<1, 256, 0, st>>>(B, cmma::peer_of(desc, epoch + (p.L - 1 - k)));
+        B.tot = tot, B.tot_global = tot + 2 * p.cmax, B.scratch = tot + 4 * p.cmax;
+        cmma::bn_backward_finalize_kernel<<<1, 1024, 0, st>>>(B, cmma::peer_of(desc, epoch + (p.L - 1 - k)));
         const int kc = g.taps * g.cin, kd = g.taps * g.cout;
         // dz_k = ca g_k + cb z_k + cc, formed inside the gathers
         cmma::Gather D = cmma::base_gather(p, g, g.cout, -1);
@@ -646,7 +665,7 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
             const int nsplit = cmma::wgrad_slices(g, p.P, &ep.kb_per_split);
             ep.split_stride = (long long)g.cout * kc;
             if (int rc = umma::gemm_ex(cmma::KIND, work + p.dzT, work + p.AT, g.cout, kc, (int)p.P, ep, st)) return rc;
-            cmma::wgrad_reduce_kernel<<<(g.cout * kc + 255) / 256, 256, 0, st>>>((const float *)(work + p.part), nsplit, g.cout,
+            cmma::wgrad_reduce_kernel<<<(g.cout * kc * 8 + 255) / 256, 256, 0, st>>>((const float *)(work + p.part), nsplit, g.cout,
                                                                                g.cin, g.taps, grads + p.goff_w[k], coef,
                                                                                accumulate);
         }

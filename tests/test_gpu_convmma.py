@@ -53,9 +53,10 @@ SHAPES = [(8, 128, 8, 8), (16, 256, 4, 4), (4, 64, 16, 16), (3, 32, 6, 8), (2, 3
           (256, 256, 4, 4)]
 
 
+@pytest.mark.parametrize("kink_free", [True, False])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_rhs_vjp_and_parameter_gradients(shape):
-    func, x, w, out_r, vu_r, gp_r, ref = _setup(shape, seed=shape[0], kink_free=shape[0] >= 256)
+def test_rhs_vjp_and_parameter_gradients(shape, kink_free):
+    func, x, w, out_r, vu_r, gp_r, ref = _setup(shape, seed=shape[0], kink_free=kink_free)
     mine = copy.deepcopy(func)
     cb = _callbacks(mine, shape)
     cb.begin(True)
@@ -67,6 +68,11 @@ def test_rhs_vjp_and_parameter_gradients(shape):
     assert torch.equal(vu, vu2) and all(torch.equal(a, b) for a, b in zip(gp, gp2))
     tol = 1e-4
     assert rel_err(out, out_r) < tol, ("f", rel_err(out, out_r))
+    if not kink_free:
+        # stock initialisation: with more than ~1e5 ReLU units per evaluation one of them is likely to sit within fp32 rounding
+        # of the kink (see _setup): the derivative bars then allow for that unit's branch
+        units = shape[0] * shape[2] * shape[3] * sum(c.out_channels for c in [mine.conv1, mine.conv2, mine.conv3, mine.conv4, mine.conv5])
+        tol = 1e-4 if units < 1e5 else 2e-2
     assert rel_err(vu.view(shape), vu_r) < tol, ("J^T w", rel_err(vu.view(shape), vu_r))
     flat = lambda gs: torch.cat([q.detach().double().reshape(-1) for q in gs])
     assert rel_err(flat(gp), flat(gp_r)) < tol, ("Jp^T w", rel_err(flat(gp), flat(gp_r)))
@@ -86,7 +92,7 @@ def test_rhs_vjp_and_parameter_gradients(shape):
     for k in range(1, 6):
         a, b = getattr(mine, "bn%d" % k), getattr(again, "bn%d" % k)
         # batch means are ~1e-2 of the activations' spread: their own relative error is that much larger than the data's
-        assert rel_err(a.running_mean, b.running_mean) < 10 * tol and rel_err(a.running_var, b.running_var) < tol
+        assert rel_err(a.running_mean, b.running_mean) < 1e-3 and rel_err(a.running_var, b.running_var) < 1e-3
 
 
 def test_stage_combination_and_mu_accumulation_are_fused():
