@@ -315,12 +315,14 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
  *
  * A sliced operand holds a row-major matrix [rows][k] as S slice matrices [S][rows][pitch] (pitch = k elements rounded
  * up to 128 bytes) such that products of slices are exact on the tensor cores:
- *   PNODE_SLICED_I8   fp64 source: x[r][c] = 2^exp[r] * sum_s q_s[r][c] * 2^-(6+7s), q_s int8, S = PNODE_I8_SLICES
- *                     (Ozaki splitting: int8 x int8 -> int32 products are exact; 48 bits of every entry relative to
- *                     its row maximum are kept)
- *   PNODE_SLICED_I8X  the same with S = PNODE_I8X_SLICES (55 bits): the truncation error of a sliced product is relative to
- *                     (row maximum)(column maximum), so products whose terms cancel by many orders of magnitude -- applying
- *                     (shift I - J)^-1 of a stiff operator to a rough vector -- need the extra digit to stay at fp64 level
+ *   PNODE_SLICED_I8   fp64 source: x[r][c] = 2^exp[r] * (q_0 2^-7 + sum_{s>=1} u_s 2^-(7+8s)), q_0 a signed and u_s unsigned
+ *                     bytes, S = PNODE_I8_SLICES = 6 (Ozaki splitting: 8-bit x 8-bit -> int32 products are exact on the
+ *                     tensor cores; 47 bits of every entry relative to its row maximum, rounded to nearest, are kept; a
+ *                     product needs the 21 slice pairs i + j < 6).  Reduction length <= PNODE_I8_MAX_K (int32 accumulators).
+ *   PNODE_SLICED_I8X  signed digits in [-64, 64], base 128, S = PNODE_I8X_SLICES = 8 (55 bits, 36 slice pairs, any reduction
+ *                     length <= 65536): the truncation error of a sliced product is relative to (row maximum)(column
+ *                     maximum), so products whose terms cancel by many orders of magnitude -- applying (shift I - J)^-1 of a
+ *                     stiff operator to a rough vector -- need the extra digits to stay at fp64 level
  *   PNODE_SLICED_TF32 fp32 source: x = hi + lo with hi = tf32(x), S = 2 (3xTF32: hi.hi + hi.lo + lo.hi)
  * pnode_slice_rows slices x itself (operand row = row of x); pnode_slice_cols slices x^T (operand row = column of x,
  * reduction over the rows of x) and can add coef * (column sums of x) into d_colsum (bias gradients).
@@ -332,8 +334,9 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
 #define PNODE_SLICED_I8 0
 #define PNODE_SLICED_TF32 1
 #define PNODE_SLICED_I8X 2   /* int8 slices with one more digit (55 bits): for products with heavy cancellation */
-#define PNODE_I8_SLICES 7
+#define PNODE_I8_SLICES 6
 #define PNODE_I8X_SLICES 8
+#define PNODE_I8_MAX_K 5461
 int64_t pnode_sliced_bytes(int kind, int rows, int k);
 int pnode_slice_rows(int kind, const void *d_x, int64_t ldx, int rows, int k, void *d_slices, int32_t *d_exp, void *stream);
 int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols, void *d_slices, int32_t *d_exp,

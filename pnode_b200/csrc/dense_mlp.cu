@@ -38,6 +38,11 @@ static int make_layout(const pnode_dmlp_desc *d, Layout &lay) {
     PNODE_REQUIRE(d->batch >= 1, "dense mlp: empty batch");
     lay.L = d->nlayers;
     lay.kind = d->dtype == PNODE_F64 ? umma::KIND_I8 : umma::KIND_TF32;
+    if (d->dtype == PNODE_F64) {  // the dense 8-bit digits bound the reduction length (int32 accumulators)
+        int longest = d->batch;
+        for (int l = 0; l <= d->nlayers; ++l) longest = d->dims[l] > longest ? d->dims[l] : longest;
+        if (longest > PNODE_I8_MAX_K) lay.kind = umma::KIND_I8X;
+    }
     lay.esz = d->dtype == PNODE_F64 ? 8 : 4;
     lay.batch = d->batch;
     int maxdim = 0;

@@ -29,21 +29,24 @@ namespace umma {
 template <int KIND>
 struct Cfg;
 template <>
-struct Cfg<KIND_I8> {
-    static constexpr int S = PNODE_I8_SLICES, BN = 64, KB = 64, STAGES = 2, NACC = PNODE_I8_SLICES, ELEM = 1;
-    static constexpr bool INT = true;
+struct Cfg<KIND_I8> {  // dense digits: slice 0 signed, slices 1.. unsigned bytes (base 256) -> 21 slice pairs for 47 bits
+    static constexpr int S = PNODE_I8_SLICES, BN = 64, KB = 64, STAGES = 3, NACC = PNODE_I8_SLICES, ELEM = 1;
+    static constexpr bool INT = true, DENSE = true;
+    static constexpr int BASE_BITS = 8, LEAD_BITS = 7;  // digit width; bits of the leading (signed) digit
     using Out = double;
 };
 template <>
 struct Cfg<KIND_I8X> {  // one more slice (55 bits): products with heavy cancellation (stiff inverse apply)
     static constexpr int S = PNODE_I8X_SLICES, BN = 64, KB = 64, STAGES = 2, NACC = PNODE_I8X_SLICES, ELEM = 1;
-    static constexpr bool INT = true;
+    static constexpr bool INT = true, DENSE = false;  // signed digits in [-64, 64] (base 128): any reduction length
+    static constexpr int BASE_BITS = 7, LEAD_BITS = 6;
     using Out = double;
 };
 template <>
 struct Cfg<KIND_TF32> {
     static constexpr int S = 2, BN = 64, KB = 128, STAGES = 4, NACC = 1, ELEM = 4;
-    static constexpr bool INT = false;
+    static constexpr bool INT = false, DENSE = false;
+    static constexpr int BASE_BITS = 0, LEAD_BITS = 0;
     using Out = float;
 };
 
@@ -120,11 +123,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return d;
 }
 
-// Instruction descriptor (dense, K-major A and B, M = 128, N = BN).
+// Instruction descriptor (dense, K-major A and B, M = 128, N = BN).  Integer kinds: per-operand signedness.
 template <int KIND, int BN>
-__device__ __forceinline__ constexpr uint32_t instr_desc() {
-    uint32_t fmt = Cfg<KIND>::INT ? ((2u << 4) | (1u << 7) | (1u << 10))    // D = S32, A = B = signed 8 bit
-                                   : ((1u << 4) | (2u << 7) | (2u << 10));   // D = F32, A = B = TF32
+__device__ __forceinline__ constexpr uint32_t instr_desc(bool a_signed = true, bool b_signed = true) {
+    uint32_t fmt = Cfg<KIND>::INT ? ((2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10))  // D = S32
+                                  : ((1u << 4) | (2u << 7) | (2u << 10));                                   // D = F32, TF32
     return fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
@@ -199,7 +202,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
     } else if (threadIdx.x == MMA_THREAD) {
         // ---- MMA issuer: every slice pair i + j < S of this K block ----
-        constexpr uint32_t idesc = instr_desc<KIND, BN>();
         for (int kb = 0; kb < num_kb; ++kb) {
             const int st = kb % STAGES, it = kb / STAGES;
             mbar_wait(&full[st], it & 1);
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         const uint64_t bd = smem_desc<KB>(sb + j * B_TILE) + (uint64_t)(k * 2);
                         const int acc = C::INT ? d : 0;
                         const bool first = (kb == 0) && (k == 0) && (i == 0) && (C::INT || d == 0);
+                        // dense digits: only the leading slice of each operand is signed
+                        const uint32_t idesc = instr_desc<KIND, BN>(!C::DENSE || i == 0, !C::DENSE || j == 0);
                         tc_mma<KIND>(tmem_base + acc * BN, ad, bd, idesc, first ? 0u : 1u);
                     }
                 }
@@ -256,16 +260,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                         for (int q = 0; q < 8; ++q) r[d][q] = 0u;
                 }
-                constexpr int NH = S < 4 ? S : 4;
+                // diagonal d carries weight 2^-(2 LEAD + BASE d): Horner in int64, in two halves that each stay below 2^53
+                constexpr int NH = C::DENSE ? (S < 3 ? S : 3) : (S < 4 ? S : 4);
+                constexpr long long RADIX = 1ll << C::BASE_BITS;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     long long hi = 0, lo = 0;
 #pragma unroll
-                    for (int d = 0; d < NH; ++d) hi = hi * 128 + (long long)(int)r[d][q];
+                    for (int d = 0; d < NH; ++d) hi = hi * RADIX + (long long)(int)r[d][q];
 #pragma unroll
-                    for (int d = NH; d < S; ++d) lo = lo * 128 + (long long)(int)r[d][q];
-                    double x = (double)hi * pow2(-(12 + 7 * (NH - 1)));
-                    if (S > NH) x = fma((double)lo, pow2(-(12 + 7 * (S - 1))), x);
+                    for (int d = NH; d < S; ++d) lo = lo * RADIX + (long long)(int)r[d][q];
+                    double x = (double)hi * pow2(-(2 * C::LEAD_BITS + C::BASE_BITS * (NH - 1)));
+                    if (S > NH) x = fma((double)lo, pow2(-(2 * C::LEAD_BITS + C::BASE_BITS * (S - 1))), x);
                     v[q] = x * srow;
                 }
             } else {
@@ -392,17 +398,30 @@ __device__ __forceinline__ float tf32_round(float x) {  // round to nearest even
     return __uint_as_float(u & 0xffffe000u);
 }
 
-// int8 digits of NV values already scaled to |v| < 64: digit s = rint(v), v <- 128 (v - digit); packed little-endian.
-template <int S, int NV>
-__device__ __forceinline__ void digits(double (&res)[NV], uint32_t (&pack)[S][NV / 4]) {
+// Digits of NV values already scaled by 2^(LEAD - e) (|v| < 2^LEAD), packed little-endian, one byte per digit.
+//   signed scheme (base 128): digit = rint(v), v <- 128 (v - digit): digits in [-64, 64], remainder dropped after S digits
+//   dense scheme  (base 256): v is first rounded to 40 fractional bits (unbiased), then digit 0 = floor(v) in [-128, 127]
+//                             and five exact unsigned bytes follow: nothing is truncated
+template <int KIND, int NV>
+__device__ __forceinline__ void digits(double (&res)[NV], uint32_t (&pack)[Cfg<KIND>::S][NV / 4]) {
+    using C = Cfg<KIND>;
+    if constexpr (C::DENSE) {
+        constexpr double FR = 1099511627776.0;  // 2^40 = 2^(8 (S - 1)) for S = 6
+        static_assert(C::S == 6, "dense digit scheme is laid out for 6 slices");
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
+        for (int q = 0; q < NV; ++q) {
+            double t = rint(res[q] * FR) * (1.0 / FR);
+            res[q] = t < 128.0 ? t : 128.0 - 1.0 / FR;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < C::S; ++s) {
 #pragma unroll
         for (int w = 0; w < NV / 4; ++w) pack[s][w] = 0;
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-            const double qd = rint(res[q]);
-            res[q] = (res[q] - qd) * 128.0;
+            const double qd = C::DENSE ? floor(res[q]) : rint(res[q]);
+            res[q] = (res[q] - qd) * (double)(1 << C::BASE_BITS);
             pack[s][q >> 2] |= ((uint32_t)(int)qd & 0xffu) << (8 * (q & 3));
         }
     }
@@ -423,14 +442,14 @@ __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int 
         amax = block_max(amax, sh);
         const int e = exponent_or_zero(exponent_above(amax));
         if (threadIdx.x == 0) exps[r] = e;
-        const double sc = pow2(6 - e);
+        const double sc = pow2(C::LEAD_BITS - e);
         uint8_t *o = out + (long long)r * pitch;
         for (int c = threadIdx.x * 4; c < k; c += blockDim.x * 4) {
             double res[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) res[q] = (c + q < k) ? x[c + q] * sc : 0.0;
             uint32_t pack[C::S][1];
-            digits<C::S, 4>(res, pack);
+            digits<KIND, 4>(res, pack);
 #pragma unroll
             for (int s = 0; s < C::S; ++s)
                 *reinterpret_cast<uint32_t *>(o + s * slice_stride + c) = pack[s][0];  // pitch % 128 == 0: in bounds
@@ -490,12 +509,12 @@ __global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int 
         const double *x = reinterpret_cast<const double *>(xin);
         const int e = exponent_or_zero(exps[c]);  // blocks with blockIdx.y > 0 may read the sentinel or the 0 written below
         if (blockIdx.y == 0 && rg == 0 && exps[c] == EXP_SENTINEL) exps[c] = 0;
-        const double sc = pow2(6 - e);
+        const double sc = pow2(C::LEAD_BITS - e);
         double res[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) res[q] = (r0 + q < rows) ? x[(long long)(r0 + q) * ldx + c] * sc : 0.0;
         uint32_t pack[C::S][4];
-        digits<C::S, 16>(res, pack);
+        digits<KIND, 16>(res, pack);
         uint8_t *o = out + (long long)c * pitch + r0;  // r0 % 16 == 0, pitch % 128 == 0: aligned and in bounds
 #pragma unroll
         for (int s = 0; s < C::S; ++s)
@@ -610,12 +629,12 @@ __global__ void slice_both_kernel(const double *x, long long ldx, int rows, int 
     for (int task = threadIdx.x; task < 512; task += 256) {
         const int r = task >> 4, cg = (task & 15) * 4;
         if (r0 + r < rows && c0 + cg < cols) {
-            const double sc = pow2(6 - exponent_or_zero(exp_r[r0 + r]));
+            const double sc = pow2(C::LEAD_BITS - exponent_or_zero(exp_r[r0 + r]));
             double res[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) res[q] = tile[r][cg + q] * sc;
             uint32_t pack[C::S][1];
-            digits<C::S, 4>(res, pack);
+            digits<KIND, 4>(res, pack);
             uint8_t *o = out_r + (long long)(r0 + r) * pitch_r + c0 + cg;
 #pragma unroll
             for (int s = 0; s < C::S; ++s) *reinterpret_cast<uint32_t *>(o + (long long)s * rows * pitch_r) = pack[s][0];
@@ -625,12 +644,12 @@ __global__ void slice_both_kernel(const double *x, long long ldx, int rows, int 
     if (threadIdx.x < 128) {
         const int c = threadIdx.x & 63, rg = (threadIdx.x >> 6) * 16;
         if (c0 + c < cols && r0 + rg < rows) {
-            const double sc = pow2(6 - exponent_or_zero(exp_c[c0 + c]));
+            const double sc = pow2(C::LEAD_BITS - exponent_or_zero(exp_c[c0 + c]));
             double res[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) res[q] = tile[rg + q][c] * sc;
             uint32_t pack[C::S][4];
-            digits<C::S, 16>(res, pack);
+            digits<KIND, 16>(res, pack);
             uint8_t *o = out_c + (long long)(c0 + c) * pitch_c + r0 + rg;
 #pragma unroll
             for (int s = 0; s < C::S; ++s)
@@ -755,6 +774,9 @@ static int launch_gemm(const void *a, const void *b, int M, int N, int K, const 
 
 int gemm_ex(int kind, const void *a, const void *b, int M, int N, int K, const Epilogue &ep, cudaStream_t stream) {
     PNODE_REQUIRE(M > 0 && N > 0 && K > 0 && K <= 65536, "umma gemm: bad shape %d x %d x %d", M, N, K);
+    // dense digits: a diagonal accumulates up to S products of 255 x 255 per reduction index in int32
+    PNODE_REQUIRE(kind != KIND_I8 || K <= PNODE_I8_MAX_K, "umma gemm: reduction length %d exceeds %d for PNODE_SLICED_I8 "
+                  "(use PNODE_SLICED_I8X)", K, PNODE_I8_MAX_K);
     if (kind == KIND_I8) return launch_gemm<KIND_I8>(a, b, M, N, K, ep, stream);
     if (kind == KIND_I8X) return launch_gemm<KIND_I8X>(a, b, M, N, K, ep, stream);
     if (kind == KIND_TF32) return launch_gemm<KIND_TF32>(a, b, M, N, K, ep, stream);

@@ -21,15 +21,24 @@ def _ops():
 
 
 def _unpack_i8(s):
-    """Host reconstruction of an int8-sliced operand: x = 2^e sum_s q_s 2^-(6+7s)."""
-    S = 8 if s.kind == 2 else 7
+    """Host reconstruction of an int8-sliced operand.  kind 0 (dense digits): x = 2^e (q_0 2^-7 + sum_{i>=1} u_i 2^-(7+8i)),
+    q_0 signed, u_i unsigned bytes; kind 2: x = 2^e sum_i q_i 2^-(6+7i), signed digits in [-64, 64]."""
+    S = 8 if s.kind == 2 else 6
     pitch = s.buf.numel() // (S * s.rows)
-    q = s.buf.view(torch.int8).view(S, s.rows, pitch)[:, :, :s.k].to(torch.float64).cpu()
+    raw = s.buf.view(S, s.rows, pitch)[:, :, :s.k].cpu()
     e = s.exp.cpu().to(torch.float64)
     x = torch.zeros(s.rows, s.k, dtype=torch.float64)
-    for i in range(S):
-        x += q[i] * 2.0 ** (-(6 + 7 * i))
-    return x * (2.0 ** e)[:, None], q, e
+    if s.kind == 2:
+        q = raw.view(torch.int8).to(torch.float64)
+        for i in range(S):
+            x += q[i] * 2.0 ** (-(6 + 7 * i))
+        ok = bool(q.abs().max() <= 64)
+    else:
+        x += raw[0].view(torch.int8).to(torch.float64) * 2.0 ** -7
+        for i in range(1, S):
+            x += raw[i].to(torch.float64) * 2.0 ** (-(7 + 8 * i))
+        ok = True
+    return x * (2.0 ** e)[:, None], ok, e
 
 
 def case_slices(dtype):
@@ -38,14 +47,16 @@ def case_slices(dtype):
     x = (torch.randn(50, 333, dtype=torch.float64) * torch.logspace(-6, 3, 50, dtype=torch.float64)[:, None]).to(dtype).cuda()
     x[7] = 0.0
     if dtype == torch.float64:
-        xr, q, e = _unpack_i8(sl.slice_rows(x))
-        amax = x.abs().amax(1).cpu()
-        ok = bool(q.abs().max() <= 64) and bool((amax < 2.0 ** e).all())
-        err_r = ((xr - x.cpu()).abs().amax(1) / (2.0 ** e)).max().item()
-        xc, q, e = _unpack_i8(sl.slice_cols(x))
-        ok = ok and bool(q.abs().max() <= 64)
-        err_c = ((xc - x.cpu().T).abs().amax(1) / (2.0 ** e)).max().item()
-        return max(err_r, err_c), 2.0 ** -48, ok
+        errs, ok = [], True
+        for ext in (False, True):
+            xr, okq, e = _unpack_i8(sl.slice_rows(x, extended=ext))
+            amax = x.abs().amax(1).cpu()
+            ok = ok and okq and bool((amax < 2.0 ** e).all())
+            errs.append(((xr - x.cpu()).abs().amax(1) / (2.0 ** e)).max().item())
+            xc, okq, e = _unpack_i8(sl.slice_cols(x, extended=ext))
+            ok = ok and okq
+            errs.append(((xc - x.cpu().T).abs().amax(1) / (2.0 ** e)).max().item())
+        return max(errs), 2.0 ** -48, ok
     s = sl.slice_rows(x)
     pitch = s.buf.numel() // (2 * s.rows)
     parts = s.buf.view(2, s.rows, pitch)[:, :, :s.k * 4].contiguous().view(torch.float32).view(2, s.rows, s.k)
