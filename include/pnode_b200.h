@@ -315,9 +315,9 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
  *
  * A sliced operand holds a row-major matrix [rows][k] as S slice matrices [S][rows][pitch] (pitch = k elements rounded
  * up to 128 bytes) such that products of slices are exact on the tensor cores:
- *   PNODE_SLICED_I8   fp64 source: x[r][c] = 2^exp[r] * (q_0 2^-7 + sum_{s>=1} u_s 2^-(7+8s)), q_0 a signed and u_s unsigned
- *                     bytes, S = PNODE_I8_SLICES = 6 (Ozaki splitting: 8-bit x 8-bit -> int32 products are exact on the
- *                     tensor cores; 47 bits of every entry relative to its row maximum, rounded to nearest, are kept; a
+ *   PNODE_SLICED_I8   fp64 source: x[r][c] = 2^exp[r] * sum_s q_s[r][c] 2^-(6+8s), q_s signed bytes (balanced base-256
+ *                     digits), S = PNODE_I8_SLICES = 6 (Ozaki splitting: int8 x int8 -> int32 products are exact on the
+ *                     tensor cores; 46 bits of every entry relative to its row maximum, rounded to nearest, are kept; a
  *                     product needs the 21 slice pairs i + j < 6).  Reduction length <= PNODE_I8_MAX_K (int32 accumulators).
  *   PNODE_SLICED_I8X  signed digits in [-64, 64], base 128, S = PNODE_I8X_SLICES = 8 (55 bits, 36 slice pairs, any reduction
  *                     length <= 65536): the truncation error of a sliced product is relative to (row maximum)(column
@@ -336,7 +336,7 @@ int pnode_cnf_rk_adjoint_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *t
 #define PNODE_SLICED_I8X 2   /* int8 slices with one more digit (55 bits): for products with heavy cancellation */
 #define PNODE_I8_SLICES 6
 #define PNODE_I8X_SLICES 8
-#define PNODE_I8_MAX_K 5461
+#define PNODE_I8_MAX_K 16384
 int64_t pnode_sliced_bytes(int kind, int rows, int k);
 int pnode_slice_rows(int kind, const void *d_x, int64_t ldx, int rows, int k, void *d_slices, int32_t *d_exp, void *stream);
 int pnode_slice_cols(int kind, const void *d_x, int64_t ldx, int rows, int cols, void *d_slices, int32_t *d_exp,

@@ -29,10 +29,10 @@ namespace umma {
 template <int KIND>
 struct Cfg;
 template <>
-struct Cfg<KIND_I8> {  // dense digits: slice 0 signed, slices 1.. unsigned bytes (base 256) -> 21 slice pairs for 47 bits
+struct Cfg<KIND_I8> {  // dense digits: base 256, balanced (all signed bytes) -> 21 slice pairs for 46 bits
     static constexpr int S = PNODE_I8_SLICES, BN = 64, KB = 64, STAGES = 3, NACC = PNODE_I8_SLICES, ELEM = 1;
     static constexpr bool INT = true, DENSE = true;
-    static constexpr int BASE_BITS = 8, LEAD_BITS = 7;  // digit width; bits of the leading (signed) digit
+    static constexpr int BASE_BITS = 8, LEAD_BITS = 6;  // digit width; magnitude bits of the leading digit
     using Out = double;
 };
 template <>
@@ -218,8 +218,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         const uint64_t bd = smem_desc<KB>(sb + j * B_TILE) + (uint64_t)(k * 2);
                         const int acc = C::INT ? d : 0;
                         const bool first = (kb == 0) && (k == 0) && (i == 0) && (C::INT || d == 0);
-                        // dense digits: only the leading slice of each operand is signed
-                        const uint32_t idesc = instr_desc<KIND, BN>(!C::DENSE || i == 0, !C::DENSE || j == 0);
+                        constexpr uint32_t idesc = instr_desc<KIND, BN>();
                         tc_mma<KIND>(tmem_base + acc * BN, ad, bd, idesc, first ? 0u : 1u);
                     }
                 }
@@ -398,32 +397,35 @@ __device__ __forceinline__ float tf32_round(float x) {  // round to nearest even
     return __uint_as_float(u & 0xffffe000u);
 }
 
-// Digits of NV values already scaled by 2^(LEAD - e) (|v| < 2^LEAD), packed little-endian, one byte per digit.
-//   signed scheme (base 128): digit = rint(v), v <- 128 (v - digit): digits in [-64, 64], remainder dropped after S digits
-//   dense scheme  (base 256): v is first rounded to 40 fractional bits (unbiased), then digit 0 = floor(v) in [-128, 127]
-//                             and five exact unsigned bytes follow: nothing is truncated
+// Digits of NV values already scaled by 2^(LEAD - e) (|v| < 2^LEAD), packed little-endian, one signed byte per digit:
+// digit_s = rint(v), v <- RADIX (v - digit_s); the remainder after S digits (at most half a unit of the last digit) is
+// dropped.  Base 128: digits in [-64, 64].  Base 256 (dense): rint gives [-128, 128]; a digit above 127 is lowered by 256
+// with a carry into the next more significant one (the leading digit has a bit to spare), so every digit is a signed byte
+// and the digits stay balanced -- products of dropped digit pairs have random signs, no bias.
 template <int KIND, int NV>
 __device__ __forceinline__ void digits(double (&res)[NV], uint32_t (&pack)[Cfg<KIND>::S][NV / 4]) {
     using C = Cfg<KIND>;
-    if constexpr (C::DENSE) {
-        constexpr double FR = 1099511627776.0;  // 2^40 = 2^(8 (S - 1)) for S = 6
-        static_assert(C::S == 6, "dense digit scheme is laid out for 6 slices");
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            double t = rint(res[q] * FR) * (1.0 / FR);
-            res[q] = t < 128.0 ? t : 128.0 - 1.0 / FR;
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < C::S; ++s) {
+    for (int s = 0; s < C::S; ++s)
 #pragma unroll
         for (int w = 0; w < NV / 4; ++w) pack[s][w] = 0;
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const double qd = C::DENSE ? floor(res[q]) : rint(res[q]);
-            res[q] = (res[q] - qd) * (double)(1 << C::BASE_BITS);
-            pack[s][q >> 2] |= ((uint32_t)(int)qd & 0xffu) << (8 * (q & 3));
+    for (int q = 0; q < NV; ++q) {
+        int d[C::S];
+        double r = res[q];
+#pragma unroll
+        for (int s = 0; s < C::S; ++s) {
+            const double qd = rint(r);
+            r = (r - qd) * (double)(1 << C::BASE_BITS);
+            d[s] = (int)qd;
         }
+        if constexpr (C::DENSE) {
+#pragma unroll
+            for (int s = C::S - 1; s >= 1; --s)
+                if (d[s] > 127) d[s] -= 256, d[s - 1] += 1;
+        }
+#pragma unroll
+        for (int s = 0; s < C::S; ++s) pack[s][q >> 2] |= ((uint32_t)d[s] & 0xffu) << (8 * (q & 3));
     }
 }
 

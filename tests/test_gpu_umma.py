@@ -21,23 +21,16 @@ def _ops():
 
 
 def _unpack_i8(s):
-    """Host reconstruction of an int8-sliced operand.  kind 0 (dense digits): x = 2^e (q_0 2^-7 + sum_{i>=1} u_i 2^-(7+8i)),
-    q_0 signed, u_i unsigned bytes; kind 2: x = 2^e sum_i q_i 2^-(6+7i), signed digits in [-64, 64]."""
-    S = 8 if s.kind == 2 else 6
+    """Host reconstruction of an int8-sliced operand: x = 2^e sum_i q_i 2^-(L + B i), signed bytes; kind 0: balanced base-256
+    digits (L = 6, B = 8, 6 slices), kind 2: base 128, digits in [-64, 64] (L = 6, B = 7, 8 slices)."""
+    S, B = (8, 7) if s.kind == 2 else (6, 8)
     pitch = s.buf.numel() // (S * s.rows)
-    raw = s.buf.view(S, s.rows, pitch)[:, :, :s.k].cpu()
+    q = s.buf.view(torch.int8).view(S, s.rows, pitch)[:, :, :s.k].to(torch.float64).cpu()
     e = s.exp.cpu().to(torch.float64)
     x = torch.zeros(s.rows, s.k, dtype=torch.float64)
-    if s.kind == 2:
-        q = raw.view(torch.int8).to(torch.float64)
-        for i in range(S):
-            x += q[i] * 2.0 ** (-(6 + 7 * i))
-        ok = bool(q.abs().max() <= 64)
-    else:
-        x += raw[0].view(torch.int8).to(torch.float64) * 2.0 ** -7
-        for i in range(1, S):
-            x += raw[i].to(torch.float64) * 2.0 ** (-(7 + 8 * i))
-        ok = True
+    for i in range(S):
+        x += q[i] * 2.0 ** (-(6 + B * i))
+    ok = bool(q.abs().max() <= 64) if s.kind == 2 else bool(q[0].abs().max() <= 65)
     return x * (2.0 ** e)[:, None], ok, e
 
 
@@ -56,7 +49,7 @@ def case_slices(dtype):
             xc, okq, e = _unpack_i8(sl.slice_cols(x, extended=ext))
             ok = ok and okq
             errs.append(((xc - x.cpu().T).abs().amax(1) / (2.0 ** e)).max().item())
-        return max(errs), 2.0 ** -48, ok
+        return max(errs), 2.0 ** -47, ok
     s = sl.slice_rows(x)
     pitch = s.buf.numel() // (2 * s.rows)
     parts = s.buf.view(2, s.rows, pitch)[:, :, :s.k * 4].contiguous().view(torch.float32).view(2, s.rows, s.k)
