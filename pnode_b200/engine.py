@@ -384,6 +384,43 @@ class ImplicitSolver:
         return self._apply(t, y, shift, rhs, transpose=True)
 
 
+def _beta(c, r):
+    """Binomial number beta(c, r) = C(c + r, c): the longest step sequence that c checkpoints (the one holding the start state
+    included) reverse with no step advanced more than r times (Griewank & Walther, "revolve"); 0 for negative arguments."""
+    if c < 0 or r < 0:
+        return 0
+    return math.comb(c + r, c)
+
+
+def revolve_split(n, free):
+    """Where to put the next checkpoint when n >= 2 steps starting at a stored state are to be reversed and `free` >= 1 more
+    checkpoint slots are available: advance m steps, store, reverse the n - m steps behind it, then the first m.  The choice of
+    Griewank & Walther (Algorithm 799) with c = free + 1 checkpoints: it minimises the number of recomputed steps."""
+    c = free + 1
+    r = 1
+    while _beta(c, r) < n:
+        r += 1
+    if n <= _beta(c, r - 1) + _beta(c - 2, r - 1):
+        m = _beta(c, r - 2)
+    elif n >= _beta(c, r) - _beta(c - 3, r):
+        m = _beta(c, r - 1)
+    else:
+        m = n - _beta(c - 1, r - 1) - _beta(c - 2, r - 1)
+    return max(1, min(m, n - 1))
+
+
+def revolve_forward_positions(n, c):
+    """Step indices whose START state the forward sweep of n steps keeps when c solution checkpoints fit (index 0 always)."""
+    pos, i0, nn, cc = [0], 0, n, c - 1  # cc: slots still free once the start state of the current segment is held
+    while cc > 0 and nn > 1:
+        m = revolve_split(nn, cc)
+        i0 += m
+        pos.append(i0)
+        nn -= m
+        cc -= 1
+    return pos
+
+
 class GenericTS:
     """Host-driven stage loop over device kernels.  `ops` is a pnode_b200.device.DeviceOps."""
 
@@ -395,9 +432,10 @@ class GenericTS:
         self.rtol = rtol
         self.comm = comm  # optional data-parallel communicator (pnode_b200.parallel.BatchComm)
         # [PETSc] TSTrajectory memory: `-ts_trajectory_solution_only 1` keeps u_n only and recomputes the
-        # stages in the adjoint; `-ts_trajectory_max_cps_ram N` keeps at most N solution checkpoints in HBM and recomputes the
-        # steps in between from the nearest one (uniform stride; PETSc uses a binomial schedule -- the arithmetic, hence the
-        # result, is the same, only the amount of recomputation differs).
+        # stages in the adjoint; `-ts_trajectory_max_cps_ram N` keeps at most N solution checkpoints in HBM at any time, placed
+        # by the binomial (revolve) schedule: fixed-step runs know their step count, so the forward sweep stores exactly the
+        # states of the offline schedule; adaptive runs thin a uniform grid on the fly (half of the slots) and the reverse sweep
+        # re-checkpoints inside each gap with the slots that have become free.  Same kernels, same arithmetic: identical results.
         self.solution_only = solution_only or (max_cps is not None)
         self.max_cps = max_cps
         self.traj = []
@@ -410,6 +448,15 @@ class GenericTS:
         self.traj = []
         self._stride = 1
         self.recomputed_steps = 0
+        self.peak_checkpoints = 0
+        self._keep_at = None
+        if save_trajectory and self.max_cps is not None and not loop.adaptive:
+            import copy as _copy
+            dry, n = _copy.deepcopy(loop), 0  # the step schedule of a fixed-step run is known before it starts
+            while not dry.done:
+                dry.report(None)
+                n += 1
+            self._keep_at = set(revolve_forward_positions(n, max(self.max_cps, 1)))
         for cb in (cb_ex, cb_im):
             if cb is not None and hasattr(cb, "begin"):
                 cb.begin(True, keep=save_trajectory, comm=self.comm)
@@ -451,41 +498,76 @@ class GenericTS:
         loop.check_complete()
         return u, sols
 
+    def _stored(self):
+        return sum(1 for e in self.traj if e[3] is not None)
+
     def _record(self, t, h, u, stages):
         if not self.solution_only:
             self.traj.append((t, h, stages, None))
             return
-        self.traj.append((t, h, None, u))
-        if self.max_cps is not None:
-            # thin the stored solutions so that at most max_cps remain: double the stride whenever the budget is exceeded
+        if self.max_cps is None:
+            self.traj.append((t, h, None, u))
+            return
+        idx = len(self.traj)
+        if self._keep_at is not None:  # offline binomial schedule
+            self.traj.append((t, h, None, u if idx in self._keep_at else None))
+        else:
+            # step count unknown (adaptive): uniform grid thinned by stride doubling within half of the slots; the other half
+            # is left to the reverse sweep's re-checkpointing
+            self.traj.append((t, h, None, u))
+            budget = max((max(self.max_cps, 1) + 1) // 2, 1)
             held = [i for i, e in enumerate(self.traj) if e[3] is not None]
-            while len(held) > max(self.max_cps, 1):
+            while len(held) > budget:
                 self._stride *= 2
                 for i in held:
                     if i % self._stride != 0:
                         tt, hh, _, _ = self.traj[i]
                         self.traj[i] = (tt, hh, None, None)
                 held = [i for i, e in enumerate(self.traj) if e[3] is not None]
+        self.peak_checkpoints = max(self.peak_checkpoints, self._stored())
+
+    def _advance(self, cb_ex, cb_im, imp, i, u):
+        t, h = self.traj[i][0], self.traj[i][1]
+        if self.kind == "rk":
+            unew, st, _ = self._rk_attempt(cb_ex, t, h, u, None, False)
+        elif self.kind == "arkimex":
+            unew, st, _ = self._ark_attempt(cb_ex, cb_im, imp, t, h, u, False)
+        else:
+            unew, st, _ = self._theta_attempt(cb_im, imp, t, h, u)
+        self.recomputed_steps += 1
+        return unew, st
 
     def _restore(self, cb_ex, cb_im, imp, idx):
-        """Make step `idx` of the trajectory hold its stage values again, recomputing forward from the nearest stored
-        solution at or before it (same kernels, same arithmetic => identical stages)."""
+        """Make step `idx` (the last one still in the trajectory) hold its stage values again: advance from the nearest stored
+        solution at or before it (same kernels, same arithmetic => identical stages).  With a checkpoint budget the advance
+        drops new checkpoints at the binomial split points while slots are free (revolve); a popped step frees its slot."""
         j = idx
         while self.traj[j][3] is None:
             j -= 1
         u = self.traj[j][3]
-        for i in range(j, idx + 1):
-            t, h, stages, u_keep = self.traj[i]
-            if self.kind == "rk":
-                unew, st, _ = self._rk_attempt(cb_ex, t, h, u, None, False)
-            elif self.kind == "arkimex":
-                unew, st, _ = self._ark_attempt(cb_ex, cb_im, imp, t, h, u, False)
-            else:
-                unew, st, _ = self._theta_attempt(cb_im, imp, t, h, u)
-            self.recomputed_steps += 1
-            # keep the stages of every step of the segment: the adjoint consumes them next, in reverse order
-            self.traj[i] = (t, h, st, u_keep)
-            u = unew
+        if self.max_cps is None:
+            # every start state is kept: one step to recompute
+            for i in range(j, idx + 1):
+                unew, st = self._advance(cb_ex, cb_im, imp, i, u)
+                t, h, _, u_keep = self.traj[i]
+                self.traj[i] = (t, h, st, u_keep)
+                u = unew
+            return
+        pos = j
+        while pos < idx:
+            free = max(self.max_cps, 1) - self._stored()
+            n = idx + 1 - pos
+            m = revolve_split(n, free) if free >= 1 else n - 1
+            for i in range(pos, pos + m):
+                u, _ = self._advance(cb_ex, cb_im, imp, i, u)
+            pos += m
+            if free >= 1 and pos < idx:
+                t, h, st, _ = self.traj[pos]
+                self.traj[pos] = (t, h, st, u)
+                self.peak_checkpoints = max(self.peak_checkpoints, self._stored())
+        _, st = self._advance(cb_ex, cb_im, imp, idx, u)
+        t, h, _, u_keep = self.traj[idx]
+        self.traj[idx] = (t, h, st, u_keep)
 
     def _rk_attempt(self, cb, t, h, u, k_fsal, adaptive):
         sc, ops = self.scheme, self.ops

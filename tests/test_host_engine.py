@@ -403,3 +403,75 @@ def test_arkimex_with_a_single_function_integrates_it_once(monkeypatch, implicit
         assert abs(res[1][0].item() - math.exp(-1.0)) < 5e-6          # d u(1) / d u0
         assert abs(res[2][0].item() + 3 * math.exp(-1.0)) < 5e-5      # d sum u(1) / d k = -t exp(-k t) per component
     _assert_close(p, o, 1e-12)
+
+
+@pytest.mark.parametrize("n,c", [(12, 3), (48, 4), (100, 2), (7, 7), (300, 5), (5, 1)])
+def test_revolve_schedule_is_binomial(n, c):
+    """The checkpoint placement of -ts_trajectory_max_cps_ram: simulate the forward placement + the reverse sweep's
+    re-checkpointing for n steps and c slots; never more than c states held, every step's stages produced exactly once in reverse
+    order, and no step advanced more often than the optimal repetition number r (beta(c, r) >= n > beta(c, r - 1)) + 2."""
+    import math
+
+    from pnode_b200.engine import revolve_forward_positions, revolve_split
+
+    stored = set(revolve_forward_positions(n, c))
+    assert 0 in stored and len(stored) <= c
+    advanced = [1] * n  # the forward sweep itself
+    peak = len(stored)
+    for idx in range(n - 1, -1, -1):
+        pos = max(j for j in stored if j <= idx)
+        while pos < idx:
+            free = c - len(stored)
+            m = revolve_split(idx + 1 - pos, free) if free >= 1 else idx - pos
+            for i in range(pos, pos + m):
+                advanced[i] += 1
+            pos += m
+            if free >= 1 and pos < idx:
+                stored.add(pos)
+                peak = max(peak, len(stored))
+        advanced[idx] += 1  # its stages
+        stored.discard(idx)
+    assert peak <= c
+    r = 1
+    while math.comb(c + r, c) < n:
+        r += 1
+    if c > 1:
+        # forward sweep + stage evaluation + at most r re-advances per step; total of the order of r sweeps, far below the
+        # quadratic cost of a single checkpoint
+        assert max(advanced) <= r + 2, (max(advanced), r)
+        assert sum(advanced) <= (r + 2) * n
+
+
+def test_checkpoint_budget_is_respected_and_results_identical(monkeypatch):
+    pa = patch_cpu(monkeypatch)
+    func = TimeMLP(d=4, hidden=8)
+    g = torch.Generator().manual_seed(6)
+    u0 = torch.randn(6, 4, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.0, 1.0, 2.0, 3.0], dtype=torch.float64)
+    gout = torch.randn(4, 6, 4, generator=g, dtype=torch.float64)
+
+    def run(argv, method="rk4"):
+        Options.clear_all()
+        Options.insert_args(argv)
+        f = copy.deepcopy(func)
+        ode = pa.ODEPetsc()
+        ode.setupTS(u0, f, step_size=0.0625, method=method, enable_adjoint=True)
+        y0 = u0.clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t)
+        (out * gout).sum().backward()
+        return out.detach(), y0.grad, [p.grad for p in f.parameters()], ode
+
+    full = run(["-ts_adapt_type", "none"])
+    for cps in (2, 4, 9):
+        lean = run(["-ts_adapt_type", "none", "-ts_trajectory_max_cps_ram", str(cps)])
+        eng = lean[3]._engine
+        assert torch.equal(full[0], lean[0]) and torch.equal(full[1], lean[1])
+        assert all(torch.equal(a, b) for a, b in zip(full[2], lean[2]))
+        assert eng.peak_checkpoints <= cps
+        # 48 steps: the binomial schedule needs about r sweeps (beta(4, 4) = 70 >= 48: r = 4), not 48^2 / 2 steps
+        assert 48 <= eng.recomputed_steps <= {2: 48 * 10, 4: 48 * 6, 9: 48 * 4}[cps]
+    # adaptive run (step count unknown in advance): budget still respected, results identical
+    fulla = run(["-ts_rtol", "1e-6", "-ts_atol", "1e-6"], method="dopri5")
+    leana = run(["-ts_rtol", "1e-6", "-ts_atol", "1e-6", "-ts_trajectory_max_cps_ram", "4"], method="dopri5")
+    assert torch.equal(fulla[0], leana[0]) and torch.equal(fulla[1], leana[1])
+    assert leana[3]._engine.peak_checkpoints <= 4
