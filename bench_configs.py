@@ -258,11 +258,41 @@ def cfg5(N=1024, B=256, dtype="f64"):
     return build
 
 
+def burgers(N=1024, B=200, dtype="f64"):
+    """the second SINODE driver (examples-sinode/Burgers/Burgers.py:134-195, 359-377): 3-tap stencil + MLP of
+    width 9N/8, batch 200, 10 output times, ARKIMEX; run_a100_512.sh uses -ts_arkimex_type 1bee and a fixed step."""
+    from _workloads import BurgersExplicit, BurgersImplicit
+
+    def build():
+        td = torch.float64 if dtype == "f64" else torch.float32
+        g = torch.Generator().manual_seed(5 + SEED_OFFSET)
+        x = torch.linspace(0, 1, N + 1, dtype=torch.float64)[:-1]
+        u0 = (torch.sin(2 * torch.pi * x)[None, :] * (0.5 + torch.rand(B, 1, generator=g, dtype=torch.float64))).to(td)
+        T, h = 10, 0.01
+        t = torch.arange(T, dtype=torch.float64) * h
+        target = torch.randn(T, B, N, generator=g, dtype=torch.float64).to(td)
+        H = N * 9 // 8
+        kw = dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch", fixed_jacobian_across_solves=True)
+        f_ex = 2 * (2 * N * H + 3 * H * H)
+        bs = 25
+        mk = lambda: [BurgersImplicit(N, dtype=td), BurgersExplicit(N, dtype=td)]
+        return dict(desc="Burgers SINODE: N=%d, MLP width %d, batch %d, ARKIMEX 1bee h=0.01, 10 output times, torch solver, "
+                         "-snes_type ksponly, %s" % (N, H, B, dtype), dtype=dtype,
+                    argv=["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_arkimex_type", "1bee", "-ts_trajectory_type",
+                          "memory"], funcs=mk(), u0=u0, t=t, target=target, kw=kw, step=h, batch=B,
+                    flops_per_unit=(3 + 3 * 3) * f_ex + 6 * 2 * N * N, bytes_per_unit=12 * 8 * (2 * N * H + 3 * H * H) / B,
+                    pipe="fp64_fma" if dtype == "f64" else "fp32_fma", also_generic=True,
+                    cpu_sample=lambda: dict(funcs=mk(), u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
+                                            kw=dict(kw, batch_size=bs), batch=bs, desc="%d of %d samples" % (bs, B)))
+
+    return build
+
+
 def config_table():
     return {"1": ("cfg1", cfg1), "2S": ("cfg2-f32", cfg2("f32")), "2D": ("cfg2-f64", cfg2("f64")), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)),
-            "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32"))}
+            "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32")), "B": ("burgers", burgers())}
 
 
 def main():

@@ -182,3 +182,41 @@ class KSExplicit(nn.Module):
 
 def ks_dx(n):
     return 22.0 / n
+
+
+class BurgersImplicit(nn.Module):
+    """Viscous term alpha u_xx on a periodic grid: the fixed 3-point stencil of examples-sinode/Burgers/Burgers.py:163-195
+    (built in float32 like the reference, then cast)."""
+
+    def __init__(self, n, alpha=8e-4, dtype=torch.float64):
+        super().__init__()
+        dx = 1.0 / n
+        self.A = nn.Conv1d(1, 1, kernel_size=3, padding="same", padding_mode="circular", bias=False)
+        K = torch.tensor([[[alpha / dx ** 2, -2.0 * alpha / dx ** 2, alpha / dx ** 2]]], dtype=torch.float32).to(dtype)
+        self.A.weight = nn.Parameter(K, requires_grad=False)
+        self.nfe = 0
+
+    def forward(self, t, y):
+        self.nfe += 1
+        return torch.squeeze(self.A(torch.unsqueeze(y, 1)), 1)
+
+
+class BurgersExplicit(nn.Module):
+    """Burgers.py:134-160: five Linear layers of width 9N/8 with ReLU, weights N(0, 0.1^2), zero biases, returning +net(y)."""
+
+    def __init__(self, n, dtype=torch.float64, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        h = n * 9 // 8
+        self.net = nn.Sequential(nn.Linear(n, h), nn.ReLU(), nn.Linear(h, h), nn.ReLU(), nn.Linear(h, h), nn.ReLU(),
+                                 nn.Linear(h, h), nn.ReLU(), nn.Linear(h, n))
+        for m in self.net.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, mean=0, std=0.1)
+                nn.init.constant_(m.bias, val=0)
+        self.to(dtype)
+        self.nfe = 0
+
+    def forward(self, t, y):
+        self.nfe += 1
+        return self.net(y)

@@ -178,3 +178,34 @@ def test_ks_full_size_against_the_committed_oracle_fixture():
     # constant in Y and move only through the transposed solves).  Bars: that floor x 5 for the trajectory, 1e-8 for lambda / mu.
     assert errs["traj"] < 1e-7 and errs["lam"] < 1e-8 and errs["mu_sample"] < 1e-8, errs
     assert errs["mu_sum"] < 1e-8 and errs["mu_norm"] < 1e-8, errs
+
+
+def test_burgers_pair_takes_the_same_evaluators_and_matches_the_oracle():
+    """the Burgers driver's shapes (Burgers.py:134-195: 3-tap periodic stencil, MLP of width 9N/8 returning
+    +net(y), several output times, ARKIMEX 1bee as in run_a100_512.sh) at N = 64, batch 10, against the oracle."""
+    from pnode import petsc_adjoint
+    from _workloads import BurgersExplicit, BurgersImplicit
+
+    N, B = 64, 10
+    g = torch.Generator().manual_seed(8)
+    x = torch.linspace(0, 1, N + 1, dtype=torch.float64)[:-1]
+    u0 = torch.sin(2 * torch.pi * x)[None, :] * (0.5 + torch.rand(B, 1, generator=g, dtype=torch.float64))
+    t = torch.arange(5, dtype=torch.float64) * 0.02
+    gout = torch.randn(5, B, N, generator=g, dtype=torch.float64)
+    argv = ["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_arkimex_type", "1bee"]
+    res = []
+    for dev in ("cpu", "cuda"):
+        Options.clear_all()
+        Options.insert_args(argv)
+        f_im, f_ex = BurgersImplicit(N).to(dev), BurgersExplicit(N).to(dev)
+        ode = OracleODEPetsc(argv) if dev == "cpu" else petsc_adjoint.ODEPetsc()
+        ode.setupTS(u0.to(dev), f_im, step_size=0.01, method="imex", imex_form=True, func2=f_ex, batch_size=B,
+                    linear_solver="torch")
+        y0 = u0.to(dev).clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t.to(dev))
+        (out * gout.to(dev)).sum().backward()
+        res.append((out.detach().cpu(), y0.grad.cpu(), torch.cat([p.grad.reshape(-1) for p in f_ex.parameters()]).cpu(), ode))
+    o, p = res
+    assert p[3].path == "generic+dense-mlp+circulant-rhs" and p[3]._cb_ex.out_scale == 1.0
+    errs = [rel_err(a, b) for a, b in zip(p[:3], o[:3])]
+    assert max(errs) < 1e-10, errs
