@@ -117,6 +117,16 @@ def run_config(name, build, args, peaks, world=1, comm=None):
     hbm = spec["bytes_per_unit"] * units / world / (ms * 1e-3) / 1e9
     out["roofline"] = {"pipe": spec["pipe"], "peak_tflops": peaks[spec["pipe"]], "frac": tfl / peaks[spec["pipe"]],
                        "hbm_gbs": hbm, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": hbm / peaks["hbm_gbs"]}
+    if spec.get("tensor_ops_per_unit") and "dense-mlp" in str(ode.path):
+        # tensor-pipe roofline of the sliced products: operations the tensor cores EXECUTE (21 int8 slice pairs per fp64 product,
+        # 3 TF32 products per fp32 product) against the dense peak of that input type -- the measured bf16 peak of this pool
+        # scaled by the nominal ratio of the type (int8 2x, tf32 0.5x; MEASURED_PEAKS.json has no int8 / tf32 entry)
+        tops = spec["tensor_ops_per_unit"] * units / world / (ms * 1e-3) / 1e12
+        ratio = 2.0 if spec["dtype"] == "f64" else 0.5
+        out["roofline"]["tensor"] = {"pipe": "int8 tcgen05 (Ozaki digits, 21 slice pairs)" if spec["dtype"] == "f64" else
+                                     "tf32 tcgen05 (3xTF32)", "executed_tops": tops,
+                                     "peak_tops": ratio * peaks["bf16_tensor"], "frac": tops / (ratio * peaks["bf16_tensor"]),
+                                     "peak_note": "%.1fx the measured bf16 peak (nominal type ratio)" % ratio}
     if spec.get("also_generic") and ode.path != "generic" and world == 1 and not getattr(args, "no_generic", False):
         Options.insert_args(["-pnode_fused", "0"])
         funcs_g = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
@@ -251,6 +261,8 @@ def cfg5(N=1024, B=256, dtype="f64"):
                     funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)], u0=u0, t=t, target=target, kw=kw,
                     step=0.2, batch=B, flops_per_unit=16 * f_ex + 6 * 2 * N * N, bytes_per_unit=12 * 37.3e6 * 8 / B,
                     pipe="fp64_fma" if dtype == "f64" else "fp32_fma", also_generic=True,
+                    # executed by the products: 4 forward + 8 backward layer sweeps of F_f / 2 MACs, (21 | 3) slice pairs, 2 ops
+                    tensor_ops_per_unit=12 * (f_ex / 2) * (21 if dtype == "f64" else 3) * 2,
                     cpu_sample=lambda: dict(funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)],
                                             u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
                                             kw=dict(kw, batch_size=bs), batch=bs, desc="%d of %d samples" % (bs, B)))
