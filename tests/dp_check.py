@@ -77,17 +77,20 @@ def main():
     if "--peer" in sys.argv:
         from _workloads import OdeConvBlock
 
-        for dtype, shape, tol in ((torch.float64, (4 * world, 16, 8, 8), 1e-12), (torch.float32, (16 * world, 32, 16, 16), 2e-5)):
+        # third case: the tensor-core evaluator (csrc/conv_mma.cu), statistics exchanged inside its finalize kernels
+        for dtype, shape, tol, extra in ((torch.float64, (4 * world, 16, 8, 8), 1e-12, []),
+                                         (torch.float32, (16 * world, 32, 16, 16), 2e-5, []),
+                                         (torch.float32, (8 * world, 128, 4, 4), 2e-5, ["-pnode_convblock_mma", "1"])):
             g = torch.Generator().manual_seed(9)
             u2 = torch.randn(shape, generator=g, dtype=torch.float64).to(dtype)
             go2 = torch.randn((1,) + shape, generator=g, dtype=torch.float64).to(dtype)
             t2 = torch.tensor([1.0], dtype=torch.float64)
             f2 = OdeConvBlock(shape[1], dtype=dtype)
-            argv = ["-ts_adapt_type", "none", "-pnode_convblock_native", "1"]
+            argv = ["-ts_adapt_type", "none", "-pnode_convblock_native", "1"] + extra
             full = run(f2, u2, go2, t2, "rk4", 0.5, None, argv)
             mine = run(f2, shard_batch(u2, rank, world).contiguous(), shard_batch(go2, rank, world, dim=1).contiguous(), t2,
                        "rk4", 0.5, comm, argv)
-            assert mine[3]._cb_im.native and mine[3]._cb_im._comm is comm
+            assert mine[3]._cb_im.native and mine[3]._cb_im._comm is comm and bool(mine[3]._cb_im.mma) == bool(extra)
             flat = lambda gs: torch.cat([q.double().reshape(-1) for q in gs])
             errs = (rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)), rel_err(mine[1], shard_batch(full[1], rank, world)),
                     rel_err(flat(mine[2]), flat(full[2])))
