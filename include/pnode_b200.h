@@ -183,6 +183,39 @@ int pnode_cnf_rk_attempt(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab,
                          const void *d_kfsal_in, int64_t ntraj, double t, double h, void *d_unew, void *d_kfsal_out,
                          void *d_ckpt, double atol, double rtol, double *d_sumsq, void *d_work, void *stream);
 
+/* The same attempt with the STEP CONTROLLER ON THE DEVICE: [PETSc] TSAdaptChoose_Basic (accept iff the weighted error norm
+ * <= 1, h_next = h clip(safety enorm^(-1/order), 0.1, 10), halved safety after a rejected attempt), the MATCHSTEP clamp onto the
+ * next output time and pnode's tspanPostStep bookkeeping (petsc_adjoint.py:518-532) are evaluated by the last block of the
+ * attempt kernel, which then publishes (t, h, buffers to use) for the next attempt in *d_ctl.  The host launches `nlaunch`
+ * attempts back to back with NO read in between (attempts launched after the end time has been reached return at once) and
+ * reads d_ctl once per batch.  State lives in ping-pong buffers: d_ubuf [2][ntraj*(D+1)] (ctl->cur selects the current state),
+ * d_kbuf [2][ntraj*(D+1)] (FSAL slope); stage checkpoints of accepted step n go to d_ckpt_base + n * ckpt_step_elems (the host
+ * guarantees room for ctl->steps + nlaunch steps; NULL: no checkpoints); states at the output times go to d_sol [nspan][ntraj*(D+1)]
+ * (NULL when nspan == 0).  Every attempt is logged (t, h, error norm, accepted) for the host's
+ * bookkeeping.  Single rank only (a batch-sharded run needs the cross-rank sum of the error norm before the decision). */
+#define PNODE_CTL_MAX_SPAN 16
+#define PNODE_CTL_MAX_LOG 1024
+typedef struct pnode_cnf_ctl {
+    double t, h, t_end;              /* next attempt starts at t with size h */
+    double dt_span_cached;           /* [PETSc] tspan: un-shortened step remembered across an output-time hit */
+    double span[PNODE_CTL_MAX_SPAN]; /* output times (nspan == 0: single end time, integrate [t, t_end]) */
+    double n_global;                 /* length of the state vector in the WRMS norm */
+    double delta;                    /* tspanPostStep hit tolerance: 1e-5 (fp64) / 1e-3 (fp32) */
+    int32_t nspan, order, max_reject;
+    int32_t done;                    /* 0 running, 1 end time reached, 2 too many rejections, 3 log full */
+    int32_t cur, kcur, have_k;       /* ping-pong indices of d_ubuf / d_kbuf; have_k: a carried-over FSAL slope exists */
+    int32_t steps, attempts, rejections, prev_ok;
+    int32_t ctr, cur_sol_index;      /* [PETSc] tspan->spanctr; pnode's cur_sol_index */
+    int32_t pending_slot;            /* output slot the state reached by the last accepted step belongs to (-1: none); the
+                                        NEXT attempt copies its input state there (the final state is read from d_ubuf) */
+    double sumsq;                    /* the last attempt's weighted error sum of squares */
+    double log_t[PNODE_CTL_MAX_LOG], log_h[PNODE_CTL_MAX_LOG], log_enorm[PNODE_CTL_MAX_LOG];
+    int32_t log_accepted[PNODE_CTL_MAX_LOG];
+} pnode_cnf_ctl;
+int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
+                              int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol,
+                              double rtol, pnode_cnf_ctl *d_ctl, void *d_work, int nlaunch, void *stream);
+
 /* Whole discrete-adjoint sweep over the accepted steps (same conventions as pnode_mlp_rk_adjoint); the per-stage VJP
  * (RHSJacShell.multTranspose, petsc_adjoint.py:52-82, which needs second-order autograd in the reference) is evaluated
  * analytically.  d_ckpt is [nsteps, s_eff, D, ntraj]; d_gout / d_lambda use the flattened state layout. */

@@ -29,6 +29,20 @@ class CnfDesc(C.Structure):
                                           "d_hgb2", "d_e")]
 
 
+CTL_MAX_SPAN = 16
+CTL_MAX_LOG = 1024
+
+
+class CnfCtl(C.Structure):
+    """include/pnode_b200.h: pnode_cnf_ctl (the device-resident step controller's state and attempt log)."""
+    _fields_ = [("t", C.c_double), ("h", C.c_double), ("t_end", C.c_double), ("dt_span_cached", C.c_double),
+                ("span", C.c_double * CTL_MAX_SPAN), ("n_global", C.c_double), ("delta", C.c_double)] + \
+               [(n, C.c_int32) for n in ("nspan", "order", "max_reject", "done", "cur", "kcur", "have_k", "steps",
+                                         "attempts", "rejections", "prev_ok", "ctr", "cur_sol_index", "pending_slot")] + \
+               [("sumsq", C.c_double), ("log_t", C.c_double * CTL_MAX_LOG), ("log_h", C.c_double * CTL_MAX_LOG),
+                ("log_enorm", C.c_double * CTL_MAX_LOG), ("log_accepted", C.c_int32 * CTL_MAX_LOG)]
+
+
 CONV_MAX_LAYERS = 8
 DMLP_MAX_LAYERS = 8
 CIRC_MAX_TAPS = 16
@@ -78,6 +92,8 @@ _SIGNATURES = {
     "pnode_cnf_rk_supported": (C.c_int, [_i, _i, _i, _i]),
     "pnode_cnf_rk_attempt": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _d, _d, _vp, _vp, _vp, _d,
                                        _d, _vp, _vp, _vp]),
+    "pnode_cnf_rk_attempts_ctl": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _vp, _i64, _vp, _d, _d,
+                                            _vp, _vp, _i, _vp]),
     "pnode_cnf_rk_adjoint_work_bytes": (_i64, [C.POINTER(CnfDesc)]),
     "pnode_cnf_rk_adjoint": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),

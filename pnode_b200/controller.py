@@ -150,6 +150,35 @@ class TimeLoop:
             self.ctr += 1
         return True
 
+    def follow(self, accept, enorm, t_next, h_next):
+        """Book-keeping of one attempt whose verdict the DEVICE controller took (csrc/cnf_rk.cu, namespace ctl): the
+        attempt started at (self.t, self.h); `accept` and the next attempt's (t_next, h_next) come from the device's log,
+        so the host never re-derives a step size the kernels did not use.  Mirrors report()."""
+        h = self.h
+        self.attempts.append((self.t, h, bool(accept), enorm))
+        if not accept:
+            self.h = h_next
+            self._prev_ok = False
+            self._rejections += 1
+            return False
+        t_new = t_next
+        self._prev_ok = True
+        self._rejections = 0
+        self.t = t_new
+        self.steps += 1
+        self.last_h = h
+        self.h = h_next
+        if self.span is not None and self.cur_sol_index < len(self.span):
+            self.cur_sol_steps[self.cur_sol_index] += 1
+            if abs(t_new - self.span[self.cur_sol_index]) < self.delta:
+                self.cur_sol_index += 1
+        self.last_out_slot = -1
+        if self.span is not None and self.ctr < len(self.span) and \
+                abs(t_new - self.span[self.ctr]) <= SPAN_RELTOL * h + SPAN_ABSTOL:
+            self.last_out_slot = self.ctr
+            self.ctr += 1
+        return True
+
     def check_complete(self):
         if self.span is not None and self.cur_sol_index != len(self.span):
             raise Exception("TSSolve fails to step on all the specified points")  # petsc_adjoint.py:867-868

@@ -19,6 +19,7 @@
 //    the same warp-private transposed SMEM tile as csrc/mlp_rk.cu (lane = hidden unit in the reduce phase), layer-2 gate /
 //    bias gradients in per-thread registers; per-block partials are combined in fixed order by the last block.
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace pnode {
 
@@ -49,7 +50,23 @@ __device__ __forceinline__ void softplus_sigmoid(float a, float &s, float &sg) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(d));
     sg = a >= 0.0f ? r : E * r;
-    s = a > 20.0f ? a : fmaf(l, 0.6931471805599453f, fmaxf(a, 0.0f));
+    // no threshold branch: for a > 20, E < 2^-28 so d rounds to 1, lg2(1) = +0 and s = a exactly, as torch's Softplus returns
+    s = fmaf(l, 0.6931471805599453f, fmaxf(a, 0.0f));
+}
+// two trajectories at once: the MUFU part is per half, the arithmetic around it packed
+__device__ __forceinline__ void softplus_sigmoid(F2 a, F2 &s, F2 &sg) {
+    float a0, a1, E0, E1, r0, r1, l0, l1, d0, d1;
+    unpk(a, a0, a1);
+    const float x0 = -1.4426950408889634f * fabsf(a0), x1 = -1.4426950408889634f * fabsf(a1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E0) : "f"(x0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E1) : "f"(x1));
+    unpk(pk(E0, E1) + 1.0f, d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(d0));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(d1));
+    sg = pk(a0 >= 0.0f ? r0 : E0 * r0, a1 >= 0.0f ? r1 : E1 * r1);
+    s = fma(pk(l0, l1), 0.6931471805599453f, pk(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f)));
 }
 __device__ __forceinline__ void softplus_sigmoid(double a, double &s, double &sg) {
     const double E = exp(-fabs(a));
@@ -66,6 +83,7 @@ struct CnfShared {
     T g2[S][D], c2[S][D];
     T b2[D];
     T tstage[S];
+    T ha[S][S], hb[S], he[S];  // h a_ij, h b_j, h (be_j - b_j): the stage / completion / error coefficients of this step
 };
 
 // Stage time as the module sees it.  FFJORD's ODEfunc does `t = torch.tensor(t).type_as(y)` (odefunc.py:356):
@@ -107,24 +125,32 @@ __device__ __forceinline__ void cnf_setup(CnfShared<T, D, H, S> &sm, const CnfPt
             sm.c2[i][k] = hb * tt;
         }
     }
-    if (threadIdx.x < S) sm.tstage[threadIdx.x] = stage_time<T>(t + tab.c[threadIdx.x] * h, w.t_f32);
+    if (threadIdx.x < S) {
+        const int i = threadIdx.x;
+        sm.tstage[i] = stage_time<T>(t + tab.c[i] * h, w.t_f32);
+        sm.hb[i] = (T)(h * tab.b[i]);
+        sm.he[i] = (T)(h * (tab.be[i] - tab.b[i]));
+#pragma unroll
+        for (int j = 0; j < S; ++j) sm.ha[i][j] = (T)(h * tab.a[i][j]);
+    }
 }
 
-// f(t_i, (z, .)) for one trajectory: out[0..D) = dz, out[D] = -e^T J e
-template <typename T, int D, int H, int S>
-__device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i, const T (&z)[D], const T (&e)[D],
-                                         T (&out)[D + 1]) {
-    T ge[D], r[D];
+// f(t_i, (z, .)): out[0..D) = dz, out[D] = -e^T J e -- for the Pack<T>::W trajectories a thread carries (fp64: one, plain
+// doubles; fp32: two, in the halves of packed registers, every operation an FFMA2 / FMUL2 / FADD2)
+template <typename T, int D, int H, int S, typename V>
+__device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i, const V (&z)[D], const V (&e)[D],
+                                         V (&out)[D + 1]) {
+    V ge[D], r[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         ge[k] = sm.g2[i][k] * e[k];
-        r[k] = sm.b2[k];
+        r[k] = Pack<T>::all(sm.b2[k]);
     }
-    T div = T(0);
+    V div = Pack<T>::all(T(0));
 #pragma unroll 2
     for (int j = 0; j < H; ++j) {
         const UnitC<T, D> u = sm.unit[j];
-        T p = u.b1, q = T(0), w = T(0);
+        V p = Pack<T>::all(u.b1), q = Pack<T>::all(T(0)), w = Pack<T>::all(T(0));
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             p = fma(u.w1[k], z[k], p);
@@ -132,8 +158,8 @@ __device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i,
             w = fma(u.w2[k], ge[k], w);
         }
         const T g1 = sm.g1[i][j];
-        const T a = fma(p, g1, sm.c1[i][j]);
-        T s, sg;
+        const V a = fma(p, g1, sm.c1[i][j]);
+        V s, sg;
         softplus_sigmoid(a, s, sg);
 #pragma unroll
         for (int k = 0; k < D; ++k) r[k] = fma(u.w2[k], s, r[k]);
@@ -156,12 +182,118 @@ struct CnfWrmsWork {
     double partial[CNF_MAX_BLOCKS];
 };
 
+// ---- step controller on the device: pnode_b200/controller.py (adapt_basic, TimeLoop.report, TimeLoop._matchstep) restated
+// in double precision; run by ONE thread of the last block of an attempt -------------------------------------------------
+namespace ctl {
+constexpr double SAFETY = 0.9, REJECT_SAFETY = 0.5, CLIP_LO = 0.1, CLIP_HI = 10.0, DT_MIN = 1e-20, DT_MAX = 1e50;
+constexpr double MATCH_NEAR = 0.01, MATCH_HALF = 2.0, SPAN_RELTOL = 1e-6, SPAN_ABSTOL = 10 * 2.220446049250313e-16;
+constexpr double SQRT_EPS = 1.4901161193847656e-08;
+
+__device__ inline double matchstep(pnode_cnf_ctl &c, double t_new, double h, double h_next) {
+    bool hit = false;
+    double tmax;
+    if (c.nspan > 0) {
+        const int k = min(c.ctr, c.nspan - 1);
+        if (fabs(t_new - c.span[k]) <= SPAN_RELTOL * h + SPAN_ABSTOL) {
+            hit = true;
+            tmax = (k + 1 < c.nspan) ? c.span[k + 1] : c.t_end;
+        } else {
+            tmax = c.span[k];
+        }
+    } else {
+        tmax = c.t_end;
+    }
+    double out = h_next;
+    const double tend = t_new + h_next, hmax = tmax - t_new;
+    if (t_new < tmax) {
+        if (tend > tmax) {
+            out = hmax;
+        } else if (tend < tmax) {
+            if (h_next * MATCH_HALF > hmax) out = hmax / 2;
+            if (h_next * (1.0 + MATCH_NEAR) > hmax) out = hmax;
+        }
+    }
+    if (c.nspan > 0) {
+        if (h != out && c.dt_span_cached == 0.0) c.dt_span_cached = h;
+        if (h == out && c.dt_span_cached != 0.0 && hit) {
+            out = c.dt_span_cached;
+            c.dt_span_cached = 0.0;
+        }
+    }
+    return out;
+}
+
+// one attempt's verdict: updates the control block for the next attempt
+__device__ inline void report(pnode_cnf_ctl &c, double sumsq) {
+    const double h = c.h, enorm = sqrt(sumsq / c.n_global);
+    double safety = SAFETY;
+    bool accept = true;
+    if (enorm > 1.0) {
+        if (!c.prev_ok) safety *= REJECT_SAFETY;
+        accept = h < (1.0 + SQRT_EPS) * DT_MIN;
+    }
+    double fac = enorm > 0.0 ? safety * pow(enorm, -1.0 / (double)c.order) : CLIP_HI;
+    fac = fmin(fmax(fac, CLIP_LO), CLIP_HI);
+    double h_next = fmin(fmax(h * fac, DT_MIN), DT_MAX);
+    const int a = c.attempts;
+    if (a < PNODE_CTL_MAX_LOG) {
+        c.log_t[a] = c.t, c.log_h[a] = h, c.log_enorm[a] = enorm, c.log_accepted[a] = accept ? 1 : 0;
+    }
+    c.attempts = a + 1;
+    if (!accept) {
+        c.h = h_next;
+        c.prev_ok = 0;
+        c.rejections += 1;
+        if (c.rejections > c.max_reject) c.done = 2;
+    } else {
+        const double t_new = c.t + h;
+        h_next = matchstep(c, t_new, h, h_next);
+        c.prev_ok = 1;
+        c.rejections = 0;
+        c.t = t_new;
+        c.steps += 1;
+        c.h = h_next;
+        if (c.nspan > 0 && c.cur_sol_index < c.nspan && fabs(t_new - c.span[c.cur_sol_index]) < c.delta) c.cur_sol_index += 1;
+        int slot = -1;
+        if (c.nspan > 0 && c.ctr < c.nspan && fabs(t_new - c.span[c.ctr]) <= SPAN_RELTOL * h + SPAN_ABSTOL) slot = c.ctr++;
+        c.pending_slot = slot;
+        c.cur ^= 1;       // the candidate becomes the state
+        c.kcur ^= 1;      // and its last stage slope the carried-over one
+        c.have_k = 1;
+        if (!(c.t < c.t_end && fabs(c.t - c.t_end) > SPAN_ABSTOL)) c.done = 1;
+    }
+    if (c.attempts >= PNODE_CTL_MAX_LOG && c.done == 0) c.done = 3;
+}
+}  // namespace ctl
+
 template <typename T, int D, int H, int S>
-__global__ void __launch_bounds__(CNF_THREADS, sizeof(T) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(CNF_THREADS, 2)
 cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u,
-                      const T *__restrict__ kfsal_in, const int64_t ntraj, const double t, const double h,
+                      const T *__restrict__ kfsal_in, const int64_t ntraj, double t, double h,
                       T *__restrict__ unew, T *__restrict__ kfsal_out, T *__restrict__ ckpt, const double atol,
-                      const double rtol, double *__restrict__ sumsq, CnfWrmsWork *__restrict__ work) {
+                      const double rtol, double *__restrict__ sumsq, CnfWrmsWork *__restrict__ work,
+                      pnode_cnf_ctl *__restrict__ dctl, T *__restrict__ ubuf, T *__restrict__ kbuf,
+                      const int64_t ckpt_step_elems, T *__restrict__ sol) {
+    typedef Pack<T> P;
+    typedef typename P::V V;
+    constexpr int W = P::W;  // trajectories per thread
+    T *sol_out = nullptr;
+    if (dctl != nullptr) {
+        // device-controlled attempt: time, step and buffers come from the control block the previous attempt's last block
+        // wrote (every block reads it before any block of THIS launch can modify it: the update happens behind the ticket)
+        const volatile pnode_cnf_ctl *vc = dctl;
+        if (vc->done != 0) return;
+        t = vc->t, h = vc->h;
+        const int64_t n = ntraj * (D + 1);
+        const int cur = vc->cur, kcur = vc->kcur;
+        u = ubuf + (int64_t)cur * n;
+        unew = ubuf + (int64_t)(cur ^ 1) * n;
+        kfsal_in = (tab.fsal && vc->have_k) ? kbuf + (int64_t)kcur * n : nullptr;
+        kfsal_out = tab.fsal ? kbuf + (int64_t)(kcur ^ 1) * n : nullptr;
+        if (ckpt != nullptr) ckpt += (int64_t)vc->steps * ckpt_step_elems;
+        const int slot = vc->pending_slot;
+        if (slot >= 0 && sol != nullptr) sol_out = sol + (int64_t)slot * n;
+    }
     __shared__ CnfShared<T, D, H, S> sm;
     cnf_setup<T, D, H, S>(sm, w, tab, t, h);
     __syncthreads();
@@ -169,50 +301,75 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
     const int s_eff = tab.fsal ? S - 1 : S;
     double local = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t traj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; traj < ntraj; traj += stride) {
-        T y[N], e[D], K[S][N];
+    const int64_t nslots = (ntraj + W - 1) / W;
+    for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < nslots; slot += stride) {
+        // trajectories tr[0..W) of this thread; a missing second one (odd ntraj) computes on zeros and stores nothing
+        int64_t tr[W];
+        bool ok[W];
+#pragma unroll
+        for (int x = 0; x < W; ++x) {
+            tr[x] = slot * W + x;
+            ok[x] = tr[x] < ntraj;
+            if (!ok[x]) tr[x] = ntraj - 1;
+        }
+        auto gather = [&](const T *base, int64_t mul, int64_t off) -> V {
+            T v[2] = {T(0), T(0)};
+#pragma unroll
+            for (int x = 0; x < W; ++x) v[x] = ok[x] ? base[tr[x] * mul + off] : T(0);
+            return P::make(v[0], v[1]);
+        };
+        auto scatter = [&](T *base, int64_t mul, int64_t off, V val) {
+#pragma unroll
+            for (int x = 0; x < W; ++x)
+                if (ok[x]) base[tr[x] * mul + off] = P::get(val, x);
+        };
+        V y[N], e[D], K[S][N];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            y[k] = u[traj * D + k];
-            e[k] = w.e[traj * D + k];
+            y[k] = gather(u, D, k);
+            e[k] = gather(w.e, D, k);
         }
-        y[D] = u[ntraj * D + traj];
+        y[D] = gather(u, 1, ntraj * D);
+        if (sol_out != nullptr) {  // the state this attempt starts from landed on an output time
+#pragma unroll
+            for (int k = 0; k < D; ++k) scatter(sol_out, D, k, y[k]);
+            scatter(sol_out, 1, ntraj * D, y[D]);
+        }
         // the stage loop is NOT unrolled: the slopes K live in a small local array (touched ~50 times per stage, against
         // ~3000 instructions of right-hand side), which keeps the kernel at ~1/7 of the unrolled code size and registers
 #pragma unroll 1
         for (int i = 0; i < S; ++i) {
-            T Y[N];
+            V Y[N];
 #pragma unroll
             for (int k = 0; k < N; ++k) Y[k] = y[k];
             for (int j = 0; j < i; ++j) {
-                const T ha = (T)(h * tab.a[i][j]);
+                const T ha = sm.ha[i][j];
 #pragma unroll
                 for (int k = 0; k < N; ++k) Y[k] = fma(ha, K[j][k], Y[k]);
             }
             if (ckpt != nullptr && i < s_eff) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) ckpt[((int64_t)i * D + k) * ntraj + traj] = Y[k];
+                for (int k = 0; k < D; ++k) scatter(ckpt, 1, ((int64_t)i * D + k) * ntraj, Y[k]);
             }
             if (i == 0 && kfsal_in != nullptr) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) K[0][k] = kfsal_in[traj * D + k];
-                K[0][D] = kfsal_in[ntraj * D + traj];
+                for (int k = 0; k < D; ++k) K[0][k] = gather(kfsal_in, D, k);
+                K[0][D] = gather(kfsal_in, 1, ntraj * D);
             } else {
-                T z[D];
+                V z[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) z[k] = Y[k];
-                cnf_eval<T, D, H, S>(sm, i, z, e, K[i]);
+                cnf_eval<T, D, H, S, V>(sm, i, z, e, K[i]);
             }
         }
-        T yn[N], err[N];
+        V yn[N], err[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             yn[k] = y[k];
-            err[k] = T(0);
+            err[k] = P::all(T(0));
         }
         for (int j = 0; j < S; ++j) {
-            const T hb = (T)(h * tab.b[j]);
-            const T he = (T)(h * (tab.be[j] - tab.b[j]));
+            const T hb = sm.hb[j], he = sm.he[j];
 #pragma unroll
             for (int k = 0; k < N; ++k) {
                 yn[k] = fma(hb, K[j][k], yn[k]);
@@ -220,20 +377,25 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
             }
         }
 #pragma unroll
-        for (int k = 0; k < D; ++k) unew[traj * D + k] = yn[k];
-        unew[ntraj * D + traj] = yn[D];
+        for (int k = 0; k < D; ++k) scatter(unew, D, k, yn[k]);
+        scatter(unew, 1, ntraj * D, yn[D]);
         if (kfsal_out != nullptr) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) kfsal_out[traj * D + k] = K[S - 1][k];
-            kfsal_out[ntraj * D + traj] = K[S - 1][D];
+            for (int k = 0; k < D; ++k) scatter(kfsal_out, D, k, K[S - 1][k]);
+            scatter(kfsal_out, 1, ntraj * D, K[S - 1][D]);
         }
         if (sumsq != nullptr) {
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                const double un = (double)yn[k], x = (double)(yn[k] + err[k]);
-                const double tol = atol + rtol * fmax(fabs(un), fabs(x));
-                const double rr = (un - x) / tol;
-                local = fma(rr, rr, local);
+                const V xs = yn[k] + err[k];
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    if (!ok[x]) continue;
+                    const double un = (double)P::get(yn[k], x), xv = (double)P::get(xs, x);
+                    const double tol = atol + rtol * fmax(fabs(un), fabs(xv));
+                    const double rr = (un - xv) / tol;
+                    local = fma(rr, rr, local);
+                }
             }
         }
     }
@@ -259,6 +421,10 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
         if (threadIdx.x == 0) {
             *sumsq = s;
             work->ticket = 0u;
+            if (dctl != nullptr) {
+                ctl::report(*dctl, s);
+                __threadfence();
+            }
         }
     }
 }
@@ -268,15 +434,23 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
 
 constexpr int CNF_ADJ_WARPS = 4;
 constexpr int CNF_ADJ_THREADS = CNF_ADJ_WARPS * 32;
-constexpr int CNF_NCHUNK = 2;
 
+// Shape of the warp-private reduction tile.  A warp carries NT = 32 W trajectories (W = Pack<T>::W per thread).  Phase 2
+// turns the tile: lane = (hidden unit u, trajectory group g), HALVES = W groups of 32/W lanes, each lane summing the
+// 16-byte vectors v = HALVES m + g of its unit's row -- so with two trajectories per thread the chunk holds 15 units and
+// all but two lanes work, instead of 15 of 32.
 template <typename T, int D, int H>
 struct CnfAdjShape {
-    static constexpr int JH = (H + CNF_NCHUNK - 1) / CNF_NCHUNK;  // 30 hidden units per chunk (lane = unit in phase 2)
+    static constexpr int W = Pack<T>::W;
+    static constexpr int NT = 32 * W;
+    static constexpr int HALVES = W;
+    static constexpr int LPH = 32 / HALVES;                      // lanes per trajectory group
+    static constexpr int NCH = (W == 1) ? 2 : 4;                  // chunks of hidden units per stage
+    static constexpr int JH = (H + NCH - 1) / NCH;                // 30 (fp64) / 15 (fp32) units per chunk
     static constexpr int VEC = 16 / sizeof(T);
-    static constexpr int PITCH = 32 + VEC;
+    static constexpr int PITCH = NT + VEC;                        // 16-byte row skew: conflict-free vector loads in phase 2
     static constexpr int NP = 2 * H * D + 4 * H + 4 * D;
-    static_assert(JH <= 32, "chunk too wide");
+    static_assert(JH <= LPH, "chunk too wide");
 };
 
 struct CnfAdjWork {
@@ -293,7 +467,7 @@ struct alignas(16) CnfTile {
     T th[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // theta_j  = dL/dg1_j
     T sp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // s_j      = softplus(a_j)
     T eg[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // -v_l sg_j q_j g1_j
-    T Z[D][32], E[D][32], VZ[D][32];
+    T Z[D][CnfAdjShape<T, D, H>::NT], E[D][CnfAdjShape<T, D, H>::NT], VZ[D][CnfAdjShape<T, D, H>::NT];
 };
 
 template <typename T>
@@ -312,6 +486,44 @@ __device__ __forceinline__ void cnf_lds16(const T *p, T (&r)[16 / sizeof(T)]) {
     memcpy(r, &v, 16);
 }
 
+// the thread's W trajectories side by side in a tile row (column = W lane + x)
+__device__ __forceinline__ void tile_put(double *row, int lane, double v) { row[lane] = v; }
+__device__ __forceinline__ void tile_put(float *row, int lane, F2 v) {
+    *reinterpret_cast<unsigned long long *>(row + 2 * lane) = v.v;
+}
+__device__ __forceinline__ double one_minus(double x) { return 1.0 - x; }
+__device__ __forceinline__ F2 one_minus(F2 x) { return fma(x, -1.0f, 1.0f); }
+
+// phase-2 accumulators: sums over a 16-byte vector of trajectories (fp32: the two halves of a packed register hold the
+// partial sums of even / odd trajectories)
+template <typename T>
+struct VecAcc;
+template <>
+struct VecAcc<double> {
+    typedef double A;
+    static __device__ __forceinline__ A zero() { return 0.0; }
+    static __device__ __forceinline__ void mac(A &acc, const double (&x)[2], const double (&y)[2]) {
+        acc = fma(x[0], y[0], acc);
+        acc = fma(x[1], y[1], acc);
+    }
+    static __device__ __forceinline__ void add(A &acc, const double (&x)[2]) { acc += x[0] + x[1]; }
+    static __device__ __forceinline__ double total(A a) { return a; }
+};
+template <>
+struct VecAcc<float> {
+    typedef F2 A;
+    static __device__ __forceinline__ A zero() { return splat(0.0f); }
+    static __device__ __forceinline__ void mac(A &acc, const float (&x)[4], const float (&y)[4]) {
+        acc = fma(pk(x[0], x[1]), pk(y[0], y[1]), acc);
+        acc = fma(pk(x[2], x[3]), pk(y[2], y[3]), acc);
+    }
+    static __device__ __forceinline__ void add(A &acc, const float (&x)[4]) {
+        acc = acc + pk(x[0], x[1]);
+        acc = acc + pk(x[2], x[3]);
+    }
+    static __device__ __forceinline__ float total(A a) { return lo(a) + hi(a); }
+};
+
 template <typename T, int D, int H, int S>
 __global__ void __launch_bounds__(CNF_ADJ_THREADS)
 cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
@@ -319,7 +531,11 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
                   T *__restrict__ mu_out, CnfAdjWork *__restrict__ work, const PeerComm pc) {
     typedef CnfAdjShape<T, D, H> Sh;
-    constexpr int JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP, VEC = Sh::VEC, NCH = CNF_NCHUNK;
+    typedef Pack<T> P;
+    typedef typename P::V V;
+    typedef VecAcc<T> VA;
+    constexpr int JH = Sh::JH, PITCH = Sh::PITCH, NP = Sh::NP, VEC = Sh::VEC, NCH = Sh::NCH, W = Sh::W, NT = Sh::NT;
+    constexpr int HALVES = Sh::HALVES, LPH = Sh::LPH;
     constexpr int NST = D + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CnfShared<T, D, H, S> &sm = *reinterpret_cast<CnfShared<T, D, H, S> *>(smem_raw);
@@ -327,11 +543,13 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
         reinterpret_cast<CnfTile<T, D, H> *>(smem_raw + ((sizeof(CnfShared<T, D, H, S>) + 15) / 16) * 16);
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pu = lane % LPH, pg = lane / LPH;  // phase 2: hidden unit within the chunk, trajectory group
     CnfTile<T, D, H> &tile = tiles[warp];
     const int s_eff = tab.fsal ? S - 1 : S;
     const int64_t state_n = ntraj * NST;
 
-    // per-lane accumulators, lane = hidden unit of chunk c (kept in a small local array: touched once per stage-chunk)
+    // per-lane accumulators, lane = (hidden unit of chunk c, trajectory group); kept in a small local array: touched once
+    // per stage-chunk
     double aW1[NCH][D], aW2[NCH][D], aB1[NCH], aHB1[NCH], aHGW1[NCH], aHGB1[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -340,21 +558,36 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
         for (int k = 0; k < D; ++k) aW1[c][k] = aW2[c][k] = 0.0;
     }
     // per-thread accumulators of the layer-2 bias / gate gradients (reduced over the warp at the end)
-    T aB2[D], aHB2[D], aHGW2[D], aHGB2[D];
+    V aB2[D], aHB2[D], aHGW2[D], aHGB2[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) aB2[k] = aHB2[k] = aHGW2[k] = aHGB2[k] = T(0);
+    for (int k = 0; k < D; ++k) aB2[k] = aHB2[k] = aHGW2[k] = aHGB2[k] = P::all(T(0));
 
-    const int64_t ntiles = (ntraj + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
+    const int64_t nslots = (ntraj + W - 1) / W;
+    const int64_t ntiles = (nslots + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
     for (int64_t tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
-        const int64_t traj = tidx * CNF_ADJ_THREADS + threadIdx.x;
-        const bool valid = traj < ntraj;
-        T lam[NST], e[D];
+        const int64_t slot = tidx * CNF_ADJ_THREADS + threadIdx.x;
+        // the thread's trajectories; the ones past the end carry zeros everywhere, which contribute nothing to any sum
+        int64_t tr[W];
+        bool ok[W];
+#pragma unroll
+        for (int x = 0; x < W; ++x) {
+            tr[x] = slot * W + x;
+            ok[x] = tr[x] < ntraj;
+            if (!ok[x]) tr[x] = 0;
+        }
+        auto gather = [&](const T *base, int64_t mul, int64_t off) -> V {
+            T v[2] = {T(0), T(0)};
+#pragma unroll
+            for (int x = 0; x < W; ++x) v[x] = ok[x] ? base[tr[x] * mul + off] : T(0);
+            return P::make(v[0], v[1]);
+        };
+        V lam[NST], e[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            lam[k] = valid ? gout[(int64_t)last_slot * state_n + traj * D + k] : T(0);
-            e[k] = valid ? w.e[traj * D + k] : T(0);
+            lam[k] = gather(gout, D, (int64_t)last_slot * state_n + k);
+            e[k] = gather(w.e, D, k);
         }
-        lam[D] = valid ? gout[(int64_t)last_slot * state_n + ntraj * D + traj] : T(0);
+        lam[D] = gather(gout, 1, (int64_t)last_slot * state_n + ntraj * D);
 
         for (int n = nsteps - 1; n >= 0; --n) {
             const double h = sched[n].h;
@@ -363,53 +596,53 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
             __syncthreads();  // every warp is done with the previous step's gates
             cnf_setup<T, D, H, S>(sm, w, tab, t, h);
             __syncthreads();
-            T ls[S][D];
+            V ls[S][D];
 #pragma unroll 1
             for (int i = S - 1; i >= 0; --i) {
                 if (tab.fsal && i == S - 1) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) ls[i][k] = T(0);
+                    for (int k = 0; k < D; ++k) ls[i][k] = P::all(T(0));
                     continue;
                 }
                 // cotangents of the stage slope, pre-multiplied by the step coefficient
                 const double bi = tab.b[i];
                 const bool has_b = bi != 0.0;
                 const T cstep = (T)(has_b ? h * bi : h);
-                T vz[D];
+                V vz[D];
 #pragma unroll
-                for (int k = 0; k < D; ++k) vz[k] = has_b ? lam[k] : T(0);
+                for (int k = 0; k < D; ++k) vz[k] = has_b ? lam[k] : P::all(T(0));
                 for (int j = i + 1; j < S; ++j) {
                     const T rr = (T)(has_b ? tab.a[j][i] / bi : tab.a[j][i]);
 #pragma unroll
                     for (int k = 0; k < D; ++k) vz[k] = fma(rr, ls[j][k], vz[k]);
                 }
                 // the logp row of the Jacobian is zero: its stage adjoints vanish, only lambda_logp itself feeds v_l
-                const T mvl = valid ? -(has_b ? lam[D] * cstep : T(0)) : T(0);  // = -v_l
-                T z[D], vg[D], ge[D], r[D], rho[D], dzk[D];
+                const V mvl = has_b ? lam[D] * (-cstep) : P::all(T(0));  // = -v_l
+                V z[D], vg[D], ge[D], r[D], rho[D], dzk[D];
                 const T tt = sm.tstage[i];
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    z[k] = valid ? ckpt[(((int64_t)n * s_eff + i) * D + k) * ntraj + traj] : T(0);
-                    vz[k] = valid ? vz[k] * cstep : T(0);
+                    z[k] = gather(ckpt, 1, (((int64_t)n * s_eff + i) * D + k) * ntraj);
+                    vz[k] = vz[k] * cstep;
                     vg[k] = vz[k] * sm.g2[i][k];
                     ge[k] = sm.g2[i][k] * e[k];
-                    r[k] = sm.b2[k];
-                    rho[k] = T(0);
-                    dzk[k] = T(0);
-                    tile.Z[k][lane] = z[k];
-                    tile.E[k][lane] = e[k];
-                    tile.VZ[k][lane] = vz[k];
+                    r[k] = P::all(sm.b2[k]);
+                    rho[k] = P::all(T(0));
+                    dzk[k] = P::all(T(0));
+                    tile_put(tile.Z[k], lane, z[k]);
+                    tile_put(tile.E[k], lane, e[k]);
+                    tile_put(tile.VZ[k], lane, vz[k]);
                 }
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
                     const int j0 = c * JH;
                     const int jn = (H - j0 < JH) ? (H - j0) : JH;
-                    // ---- phase 1 (lane = trajectory) ------------------------------------------------------------------
+                    // ---- phase 1 (lane = W trajectories) --------------------------------------------------------------
 #pragma unroll 2
                     for (int jj = 0; jj < jn; ++jj) {
                         const int j = j0 + jj;
                         const UnitC<T, D> u = sm.unit[j];
-                        T p = u.b1, q = T(0), ww = T(0), m = T(0);
+                        V p = P::all(u.b1), q = P::all(T(0)), ww = P::all(T(0)), m = P::all(T(0));
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
                             p = fma(u.w1[k], z[k], p);
@@ -418,74 +651,70 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                             m = fma(u.w2[k], vg[k], m);
                         }
                         const T g1 = sm.g1[i][j];
-                        const T a = fma(p, g1, sm.c1[i][j]);
-                        T s, sg;
+                        const V a = fma(p, g1, sm.c1[i][j]);
+                        V s, sg;
                         softplus_sigmoid(a, s, sg);
 #pragma unroll
                         for (int k = 0; k < D; ++k) r[k] = fma(u.w2[k], s, r[k]);
-                        const T bq = mvl * sg;     // -v_l sg
-                        const T betap = bq * ww;   // d(-v_l div)/d(g1 q) per unit
-                        const T epsp = bq * q;
-                        const T delta = fma(betap * g1 * q, T(1) - sg, m * sg);  // dL/da_j
-                        const T theta = fma(delta, p, betap * q);                // dL/dg1_j
-                        const T dg = delta * g1;
-                        const T egv = epsp * g1;
+                        const V bq = mvl * sg;     // -v_l sg
+                        const V betap = bq * ww;   // d(-v_l div)/d(g1 q) per unit
+                        const V epsp = bq * q;
+                        const V delta = fma(betap * g1 * q, one_minus(sg), m * sg);  // dL/da_j
+                        const V theta = fma(delta, p, betap * q);                    // dL/dg1_j
+                        const V dg = delta * g1;
+                        const V egv = epsp * g1;
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
                             dzk[k] = fma(u.w1[k], dg, dzk[k]);
                             rho[k] = fma(u.w2[k], egv, rho[k]);
                         }
-                        tile.dl[jj * PITCH + lane] = delta;
-                        tile.bp[jj * PITCH + lane] = betap;
-                        tile.th[jj * PITCH + lane] = theta;
-                        tile.sp[jj * PITCH + lane] = s;
-                        tile.eg[jj * PITCH + lane] = egv;
+                        tile_put(&tile.dl[jj * PITCH], lane, delta);
+                        tile_put(&tile.bp[jj * PITCH], lane, betap);
+                        tile_put(&tile.th[jj * PITCH], lane, theta);
+                        tile_put(&tile.sp[jj * PITCH], lane, s);
+                        tile_put(&tile.eg[jj * PITCH], lane, egv);
                     }
                     __syncwarp();
-                    // ---- phase 2 (lane = hidden unit): sums over the warp's 32 trajectories ---------------------------
-                    if (lane < jn) {
-                        T sW1[D], sW2[D], sD = T(0), sTh = T(0);
+                    // ---- phase 2 (lane = hidden unit x trajectory group): sums over the warp's trajectories -----------
+                    if (pu < jn) {
+                        typename VA::A sW1[D], sW2[D], sD = VA::zero(), sTh = VA::zero();
 #pragma unroll
-                        for (int k = 0; k < D; ++k) sW1[k] = sW2[k] = T(0);
+                        for (int k = 0; k < D; ++k) sW1[k] = sW2[k] = VA::zero();
 #pragma unroll 2
-                        for (int kk = 0; kk < 32; kk += VEC) {
+                        for (int mm = 0; mm < NT / VEC / HALVES; ++mm) {
+                            const int kk = (mm * HALVES + pg) * VEC;
                             T dl[VEC], bp[VEC], th[VEC], sp[VEC], eg[VEC];
-                            cnf_lds16(&tile.dl[lane * PITCH + kk], dl);
-                            cnf_lds16(&tile.bp[lane * PITCH + kk], bp);
-                            cnf_lds16(&tile.th[lane * PITCH + kk], th);
-                            cnf_lds16(&tile.sp[lane * PITCH + kk], sp);
-                            cnf_lds16(&tile.eg[lane * PITCH + kk], eg);
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                sD += dl[v];
-                                sTh += th[v];
-                            }
+                            cnf_lds16(&tile.dl[pu * PITCH + kk], dl);
+                            cnf_lds16(&tile.bp[pu * PITCH + kk], bp);
+                            cnf_lds16(&tile.th[pu * PITCH + kk], th);
+                            cnf_lds16(&tile.sp[pu * PITCH + kk], sp);
+                            cnf_lds16(&tile.eg[pu * PITCH + kk], eg);
+                            VA::add(sD, dl);
+                            VA::add(sTh, th);
 #pragma unroll
                             for (int k = 0; k < D; ++k) {
                                 T zz[VEC], ee[VEC], vv[VEC];
                                 cnf_lds16(&tile.Z[k][kk], zz);
                                 cnf_lds16(&tile.E[k][kk], ee);
                                 cnf_lds16(&tile.VZ[k][kk], vv);
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) {
-                                    sW1[k] = fma(dl[v], zz[v], sW1[k]);
-                                    sW1[k] = fma(bp[v], ee[v], sW1[k]);
-                                    sW2[k] = fma(vv[v], sp[v], sW2[k]);
-                                    sW2[k] = fma(eg[v], ee[v], sW2[k]);
-                                }
+                                VA::mac(sW1[k], dl, zz);
+                                VA::mac(sW1[k], bp, ee);
+                                VA::mac(sW2[k], vv, sp);
+                                VA::mac(sW2[k], eg, ee);
                             }
                         }
-                        const double g1 = (double)sm.g1[i][j0 + lane];
+                        const double g1 = (double)sm.g1[i][j0 + pu];
                         const double gd = g1 * (1.0 - g1);
+                        const double dD = (double)VA::total(sD), dTh = (double)VA::total(sTh);
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
-                            aW1[c][k] += g1 * (double)sW1[k];
-                            aW2[c][k] += (double)sm.g2[i][k] * (double)sW2[k];
+                            aW1[c][k] += g1 * (double)VA::total(sW1[k]);
+                            aW2[c][k] += (double)sm.g2[i][k] * (double)VA::total(sW2[k]);
                         }
-                        aB1[c] += g1 * (double)sD;
-                        aHB1[c] += (double)tt * (double)sD;
-                        aHGB1[c] += gd * (double)sTh;
-                        aHGW1[c] += (double)tt * gd * (double)sTh;
+                        aB1[c] += g1 * dD;
+                        aHB1[c] += (double)tt * dD;
+                        aHGB1[c] += gd * dTh;
+                        aHGW1[c] += (double)tt * gd * dTh;
                     }
                     __syncwarp();
                 }
@@ -493,7 +722,7 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                 for (int k = 0; k < D; ++k) {
                     ls[i][k] = dzk[k];
                     const T g2 = sm.g2[i][k];
-                    const T Gk = fma(vz[k], r[k], e[k] * rho[k]) * (g2 * (T(1) - g2));  // dL/d(gate-2 pre-activation)
+                    const V Gk = fma(vz[k], r[k], e[k] * rho[k]) * (g2 * (T(1) - g2));  // dL/d(gate-2 pre-activation)
                     aB2[k] += vg[k];
                     aHB2[k] = fma(vz[k], tt, aHB2[k]);
                     aHGB2[k] += Gk;
@@ -503,16 +732,18 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
             for (int i = 0; i < S; ++i)
 #pragma unroll
                 for (int k = 0; k < D; ++k) lam[k] += ls[i][k];
-            if (in_slot >= 0 && valid) {
+            if (in_slot >= 0) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) lam[k] += gout[(int64_t)in_slot * state_n + traj * D + k];
-                lam[D] += gout[(int64_t)in_slot * state_n + ntraj * D + traj];
+                for (int k = 0; k < D; ++k) lam[k] += gather(gout, D, (int64_t)in_slot * state_n + k);
+                lam[D] += gather(gout, 1, (int64_t)in_slot * state_n + ntraj * D);
             }
         }
-        if (valid) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) lambda_out[traj * D + k] = lam[k];
-            lambda_out[ntraj * D + traj] = lam[D];
+        for (int x = 0; x < W; ++x) {
+            if (!ok[x]) continue;
+#pragma unroll
+            for (int k = 0; k < D; ++k) lambda_out[tr[x] * D + k] = P::get(lam[k], x);
+            lambda_out[ntraj * D + tr[x]] = P::get(lam[D], x);
         }
     }
 
@@ -522,24 +753,40 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     static_assert(sizeof(CnfTile<T, D, H>) * CNF_ADJ_WARPS >= sizeof(double) * CNF_ADJ_WARPS * NP, "tile storage too small");
     constexpr int O_B1 = H * D, O_HB1 = O_B1 + H, O_HGW1 = O_HB1 + H, O_HGB1 = O_HGW1 + H, O_W2 = O_HGB1 + H,
                   O_B2 = O_W2 + D * H, O_HB2 = O_B2 + D, O_HGW2 = O_HB2 + D, O_HGB2 = O_HGW2 + D;
+    // the trajectory groups of a unit sit LPH lanes apart: group 0 collects
+    auto both = [&](double v) -> double {
+        if (HALVES == 2) v += __shfl_down_sync(0xffffffffu, v, LPH);
+        return v;
+    };
     for (int c = 0; c < NCH; ++c) {
-        const int j = c * JH + lane;
-        if (lane < JH && j < H) {
+        const int j = c * JH + pu;
+        const bool writer = pg == 0 && pu < JH && j < H;
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                blk[warp * NP + j * D + k] = aW1[c][k];
-                blk[warp * NP + O_W2 + k * H + j] = aW2[c][k];
+        for (int k = 0; k < D; ++k) {
+            const double v1 = both(aW1[c][k]), v2 = both(aW2[c][k]);
+            if (writer) {
+                blk[warp * NP + j * D + k] = v1;
+                blk[warp * NP + O_W2 + k * H + j] = v2;
             }
-            blk[warp * NP + O_B1 + j] = aB1[c];
-            blk[warp * NP + O_HB1 + j] = aHB1[c];
-            blk[warp * NP + O_HGW1 + j] = aHGW1[c];
-            blk[warp * NP + O_HGB1 + j] = aHGB1[c];
+        }
+        const double b1 = both(aB1[c]), hb1 = both(aHB1[c]), hgw1 = both(aHGW1[c]), hgb1 = both(aHGB1[c]);
+        if (writer) {
+            blk[warp * NP + O_B1 + j] = b1;
+            blk[warp * NP + O_HB1 + j] = hb1;
+            blk[warp * NP + O_HGW1 + j] = hgw1;
+            blk[warp * NP + O_HGB1 + j] = hgb1;
         }
     }
+    auto lanes = [&](V v) -> double {
+        double t = 0.0;
+#pragma unroll
+        for (int x = 0; x < W; ++x) t += (double)P::get(v, x);
+        return t;
+    };
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        const double b2 = warp_sum((double)aB2[k]), hb2 = warp_sum((double)aHB2[k]);
-        const double hgw2 = warp_sum((double)aHGW2[k]), hgb2 = warp_sum((double)aHGB2[k]);
+        const double b2 = warp_sum(lanes(aB2[k])), hb2 = warp_sum(lanes(aHB2[k]));
+        const double hgw2 = warp_sum(lanes(aHGW2[k])), hgb2 = warp_sum(lanes(aHGB2[k]));
         if (lane == 0) {
             blk[warp * NP + O_B2 + k] = b2;
             blk[warp * NP + O_HB2 + k] = hb2;
@@ -594,22 +841,27 @@ static CnfPtrs<T> cnf_ptrs(const pnode_cnf_desc *c) {
 template <typename T, int S>
 static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, const void *d_u, const void *d_kin,
                               int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
-                              double rtol, double *d_sumsq, void *d_work, cudaStream_t st) {
+                              double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl = nullptr,
+                              void *d_ubuf = nullptr, void *d_kbuf = nullptr, int64_t ckpt_step_elems = 0,
+                              void *d_sol = nullptr, int nlaunch = 1) {
     auto kern = cnf_rk_attempt_kernel<T, 6, 60, S>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, CNF_THREADS, 0));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    int64_t want = (ntraj + CNF_THREADS - 1) / CNF_THREADS;
+    const int64_t nslots = (ntraj + Pack<T>::W - 1) / Pack<T>::W;  // fp32: two trajectories per thread (csrc/f32x2.cuh)
+    int64_t want = (nslots + CNF_THREADS - 1) / CNF_THREADS;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (cap > CNF_MAX_BLOCKS) cap = CNF_MAX_BLOCKS;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, CNF_THREADS, 0, st>>>(cnf_ptrs<T>(c), *tab, static_cast<const T *>(d_u), static_cast<const T *>(d_kin),
-                                       ntraj, t, h, static_cast<T *>(d_unew), static_cast<T *>(d_kout),
-                                       static_cast<T *>(d_ckpt), atol, rtol, d_sumsq,
-                                       static_cast<CnfWrmsWork *>(d_work));
+    for (int l = 0; l < nlaunch; ++l)
+        kern<<<grid, CNF_THREADS, 0, st>>>(cnf_ptrs<T>(c), *tab, static_cast<const T *>(d_u), static_cast<const T *>(d_kin),
+                                           ntraj, t, h, static_cast<T *>(d_unew), static_cast<T *>(d_kout),
+                                           static_cast<T *>(d_ckpt), atol, rtol, d_sumsq,
+                                           static_cast<CnfWrmsWork *>(d_work), d_ctl, static_cast<T *>(d_ubuf),
+                                           static_cast<T *>(d_kbuf), ckpt_step_elems, static_cast<T *>(d_sol));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -627,7 +879,8 @@ static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *t
         PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, CNF_ADJ_THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    int64_t want = (ntraj + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
+    const int64_t nslots = (ntraj + Pack<T>::W - 1) / Pack<T>::W;
+    int64_t want = (nslots + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (cap > CNF_MAX_BLOCKS) cap = CNF_MAX_BLOCKS;
     int grid = (int)(want < cap ? want : cap);
@@ -676,6 +929,32 @@ int pnode_cnf_rk_attempt(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab,
     PNODE_CNF_STAGES(X)
 #undef X
     PNODE_REQUIRE(false, "pnode_cnf_rk_attempt: no kernel for %d stages", tab->s);
+}
+
+int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
+                              int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol,
+                              double rtol, pnode_cnf_ctl *d_ctl, void *d_work, int nlaunch, void *stream) {
+    PNODE_REQUIRE(cnf && tab && d_ubuf && d_ctl && d_work, "pnode_cnf_rk_attempts_ctl: null argument");
+    PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_attempts_ctl: unsupported shape D=%d H=%d s=%d",
+                  cnf->dim, cnf->hidden, tab->s);
+    PNODE_REQUIRE(tab->has_be, "pnode_cnf_rk_attempts_ctl: the device controller needs an embedded tableau");
+    PNODE_REQUIRE(!tab->fsal || d_kbuf, "pnode_cnf_rk_attempts_ctl: FSAL tableau without slope buffers");
+    PNODE_REQUIRE(ntraj > 0 && nlaunch >= 1 && nlaunch <= 64, "pnode_cnf_rk_attempts_ctl: bad ntraj / nlaunch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *d_sumsq = &d_ctl->sumsq;  // consumed on the device by the controller
+#define X(SS)                                                                                                         \
+    if (tab->s == SS) {                                                                                               \
+        if (cnf->dtype == PNODE_F32)                                                                                  \
+            return launch_cnf_attempt<float, SS>(cnf, tab, nullptr, nullptr, ntraj, 0.0, 0.0, nullptr, nullptr, d_ckpt_base, \
+                                                 atol, rtol, d_sumsq, d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems,    \
+                                                 d_sol, nlaunch);                                                      \
+        return launch_cnf_attempt<double, SS>(cnf, tab, nullptr, nullptr, ntraj, 0.0, 0.0, nullptr, nullptr, d_ckpt_base,    \
+                                              atol, rtol, d_sumsq, d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems,       \
+                                              d_sol, nlaunch);                                                         \
+    }
+    PNODE_CNF_STAGES(X)
+#undef X
+    PNODE_REQUIRE(false, "pnode_cnf_rk_attempts_ctl: no kernel for %d stages", tab->s);
 }
 
 int64_t pnode_cnf_rk_adjoint_work_bytes(const pnode_cnf_desc *cnf) {

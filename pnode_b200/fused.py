@@ -308,6 +308,8 @@ class FusedCnfRK:
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=device)
         self._adj_work = None
         self._ckpt = None
+        self._ctl_host = self._ctl_dev = None
+        self.device_controller = True  # -pnode_device_controller 0 falls back to one host read per attempt
         self.launches = 0
 
     @staticmethod
@@ -347,6 +349,9 @@ class FusedCnfRK:
 
     def forward(self, u0, loop, atol, rtol, save, comm=None):
         """u0 flat [B*(D+1)].  `loop` is a controller.TimeLoop.  Returns (sol dict, state)."""
+        if self.device_controller and loop.adaptive and comm is None and loop.step_list is None and \
+                (loop.span is None or len(loop.span) <= _lib.CTL_MAX_SPAN) and self.scheme.bembed is not None:
+            return self._forward_device_ctl(u0, loop, atol, rtol, save)
         sp = self.spec
         ntraj = sp.batch
         n = u0.numel()
@@ -391,6 +396,95 @@ class FusedCnfRK:
         state = {"steps": steps, "ckpt": self._ckpt if save else None, "ntraj": ntraj, "desc_keep": desc}
         if save:
             self._ckpt = None  # ownership moves to the autograd node; the next solve allocates afresh
+        return u, sols, state
+
+    # ---- adaptive run with the accept/reject decision and the next step size taken ON THE DEVICE --------------------------
+    CTL_BATCH = 8  # attempts launched between two host reads of the control block
+
+    def _forward_device_ctl(self, u0, loop, atol, rtol, save):
+        """Same contract as forward().  The attempt kernel's last block runs TSAdaptChoose_Basic + MATCHSTEP + the span
+        bookkeeping (csrc/cnf_rk.cu, namespace ctl) and publishes (t, h, buffers) for the next attempt, so CTL_BATCH
+        attempts go out back to back and the host reads the control block once per batch instead of once per attempt;
+        the host TimeLoop then follows the device's log (TimeLoop.follow) for the bookkeeping the caller reads."""
+        sp = self.spec
+        ntraj = sp.batch
+        n = u0.numel()
+        desc = self._desc()
+        fsal = bool(self.scheme.fsal)
+        ubuf = torch.empty(2, n, dtype=self.dtype, device=self.device)
+        ubuf[0].copy_(u0)
+        kbuf = torch.empty(2, n, dtype=self.dtype, device=self.device) if fsal else None
+        nspan = 0 if loop.span is None else len(loop.span)
+        sol = torch.empty(nspan, n, dtype=self.dtype, device=self.device) if nspan else None
+        ctl = _lib.CnfCtl()
+        ctl.t, ctl.h, ctl.t_end, ctl.dt_span_cached = loop.t, loop.h, loop.t_end, 0.0
+        for i in range(nspan):
+            ctl.span[i] = loop.span[i]
+        ctl.n_global, ctl.delta = float(n), loop.delta
+        ctl.nspan, ctl.order, ctl.max_reject = nspan, int(loop.order), int(loop.max_reject)
+        ctl.done = 1 if loop.done else 0
+        ctl.prev_ok, ctl.ctr, ctl.cur_sol_index, ctl.pending_slot = 1, 1, 1, -1
+        nbytes = C.sizeof(_lib.CnfCtl)
+        if self._ctl_host is None:
+            self._ctl_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            self._ctl_dev = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        host_view = _lib.CnfCtl.from_buffer(self._ctl_host.numpy())
+        head = _lib.CnfCtl.log_t.offset  # everything before the log is the controller's state
+
+        def upload(src):
+            C.memmove(C.addressof(host_view), C.addressof(src), head)
+            self._ctl_dev[:head].copy_(self._ctl_host[:head], non_blocking=True)
+
+        upload(ctl)
+        sols = {0: u0} if nspan else {}
+        steps = []
+        self._keep = 0
+        cap = 2 * self.CTL_BATCH
+        per_step = self._ckpt_buffer(cap, ntraj) if save else 0
+        seen = 0
+        while not loop.done:
+            if save and len(steps) + self.CTL_BATCH > cap:
+                self._keep = len(steps)
+                cap = max(2 * cap, len(steps) + self.CTL_BATCH)
+                per_step = self._ckpt_buffer(cap, ntraj)
+            _lib.check(self.lib.pnode_cnf_rk_attempts_ctl(
+                C.byref(desc), C.byref(self.tab), ubuf.data_ptr(), None if kbuf is None else kbuf.data_ptr(), ntraj,
+                self._ckpt.data_ptr() if save else None, per_step, None if sol is None else sol.data_ptr(), float(atol),
+                float(rtol), self._ctl_dev.data_ptr(), self._wrms_work.data_ptr(), self.CTL_BATCH, _stream()))
+            self._ctl_host.copy_(self._ctl_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the one host read per CTL_BATCH attempts
+            c = host_view
+            now = c.attempts
+            self.launches += self.CTL_BATCH
+            for a in range(seen, now):
+                last = a + 1 == now
+                t_next = c.t if last else c.log_t[a + 1]
+                h_next = c.h if last else c.log_h[a + 1]
+                t, h = loop.t, loop.h
+                if loop.follow(bool(c.log_accepted[a]), c.log_enorm[a], t_next, h_next):
+                    steps.append((t, h, loop.last_out_slot))
+            seen = now
+            if c.done == 2:
+                raise RuntimeError("TS_DIVERGED_STEP_REJECTED: %d consecutive rejections at t=%g" % (c.rejections, c.t))
+            if c.done == 3:  # attempt log full: restart it
+                keep = _lib.CnfCtl()
+                C.memmove(C.addressof(keep), C.addressof(c), head)
+                keep.attempts, keep.done = 0, 0
+                upload(keep)
+                seen = 0
+        c = host_view
+        assert c.steps == len(steps), "device controller and host bookkeeping disagree on the step count"
+        u = ubuf[c.cur]
+        for t_h_slot in steps:
+            slot = t_h_slot[2]
+            if slot >= 0:
+                # the state that landed on the LAST output time is the final one; earlier slots were copied by the
+                # attempt that followed them
+                sols[slot] = sol[slot] if not (t_h_slot is steps[-1]) else u.clone()
+        loop.check_complete()
+        state = {"steps": steps, "ckpt": self._ckpt if save else None, "ntraj": ntraj, "desc_keep": desc}
+        if save:
+            self._ckpt = None
         return u, sols, state
 
     def adjoint(self, gout, state, single, nadj=None, comm=None):

@@ -262,6 +262,8 @@ class ODEPetsc(object):
                 return None
             if self._fused is None or self._fused.scheme is not self._scheme:
                 self._fused = FusedCnfRK(self._fused_spec, self._scheme, self.tensor_dtype, self.device)
+                self._fused.device_controller = Options().getString("pnode_device_controller", "1") not in \
+                    ("0", "false", "no")
         return self._fused_kind, self._fused
 
     # ------------------------------------------------------------------------------------------------------------

@@ -135,3 +135,81 @@ def test_probe_is_sampled_like_the_reference_when_absent():
     ode2.setupTS(u0.cuda(), func, step_size=0.25, method="rk4")
     out2 = ode2.odeint_adjoint(u0.cuda(), torch.tensor([0.0, 1.0]).cuda())
     assert ode2.path == "generic" and rel_err(out, out2) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_device_controller_follows_the_host_controller(dtype):
+    """The accept/reject verdict and the next step size taken by the attempt kernel's last block (csrc/cnf_rk.cu, namespace
+    ctl) against the host TimeLoop fed the same kernel's error norm once per attempt: same attempts, same steps, same
+    output-time copies.  The case has rejected attempts, clamped steps and three output times."""
+    from pnode import petsc_adjoint
+
+    B = 300
+    func = CNFFunc(B, 6, (60,), dtype=dtype, seed=3)
+    with torch.no_grad():
+        for prm in func.parameters():
+            prm.mul_(4.0)
+    u0, gout = _inputs(B, 6, 4, dtype)
+    t = torch.tensor([0.0, 0.3, 0.35, 1.0], dtype=torch.float64)
+    tol = "1e-7" if dtype == torch.float64 else "1e-4"
+    argv = ["-ts_rtol", tol, "-ts_atol", tol]
+    d = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 0.5)
+    h = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + ["-pnode_device_controller", "0"], func, u0, t, gout, "dopri5",
+             0.5)
+    assert d[3].path == h[3].path == "fused-cnf-rk"
+    assert d[3]._fused.device_controller and not h[3]._fused.device_controller
+    la, lb = d[3]._loop.attempts, h[3]._loop.attempts
+    if dtype == torch.float64:
+        assert any(not a[2] for a in la), "case must contain a rejected attempt"
+    assert [a[2] for a in la] == [a[2] for a in lb]
+    # same kernel, same inputs; the step factor differs by the rounding of pow() on the two sides, and one ulp of h moves the
+    # NEXT error norm (a difference of nearly equal fp numbers) by ~eps/tol relative
+    rel = 1e-8 if dtype == torch.float64 else 2e-2
+    for a, b in zip(la, lb):
+        assert a[0] == pytest.approx(b[0], rel=rel, abs=1e-15) and a[1] == pytest.approx(b[1], rel=rel)
+    assert d[3]._loop.cur_sol_steps == h[3]._loop.cur_sol_steps
+    _compare(d, h, 1e-11 if dtype == torch.float64 else 1e-4)
+
+
+def test_device_controller_many_steps_and_single_end_time():
+    """More accepted steps than the first checkpoint allocation and than one launch batch; one-element t (no span).
+    Compared with the host-controlled run of the same kernels (at this tolerance the error estimate is too close to
+    rounding noise for the oracle's autograd evaluation to take the same decisions)."""
+    from pnode import petsc_adjoint
+
+    B = 64
+    func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=11)
+    u0, gout = _inputs(B, 6, 1, torch.float64)
+    t = torch.tensor([1.0], dtype=torch.float64)
+    argv = ["-ts_rtol", "1e-10", "-ts_atol", "1e-10"]
+    from pnode_b200.fused import FusedCnfRK
+
+    batch = FusedCnfRK.CTL_BATCH
+    FusedCnfRK.CTL_BATCH = 2  # 4 checkpoint slots to start with, a host read every 2 attempts
+    try:
+        d = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 0.01)
+    finally:
+        FusedCnfRK.CTL_BATCH = batch
+    h = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + ["-pnode_device_controller", "0"], func, u0, t, gout, "dopri5",
+             0.01)
+    assert d[3].path == "fused-cnf-rk" and d[3]._fused.device_controller and not h[3]._fused.device_controller
+    assert d[3]._loop.steps > 2 * 2
+    assert d[3]._loop.steps == h[3]._loop.steps
+    assert d[0].shape == (1, B * 7)
+    _compare(d, h, 1e-9)
+
+
+def test_device_controller_reports_divergence():
+    """[PETSc] TS_DIVERGED_STEP_REJECTED after more than -ts_adapt max_reject consecutive rejections."""
+    from pnode import petsc_adjoint
+
+    B = 32
+    func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=3)
+    with torch.no_grad():
+        for prm in func.parameters():
+            prm.mul_(40.0)
+    u0, gout = _inputs(B, 6, 2, torch.float64)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    argv = ["-ts_rtol", "1e-13", "-ts_atol", "1e-13", "-ts_max_reject", "2"]
+    with pytest.raises(RuntimeError, match="TS_DIVERGED_STEP_REJECTED"):
+        _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 1.0)

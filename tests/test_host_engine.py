@@ -475,3 +475,27 @@ def test_checkpoint_budget_is_respected_and_results_identical(monkeypatch):
     leana = run(["-ts_rtol", "1e-6", "-ts_atol", "1e-6", "-ts_trajectory_max_cps_ram", "4"], method="dopri5")
     assert torch.equal(fulla[0], leana[0]) and torch.equal(fulla[1], leana[1])
     assert leana[3]._engine.peak_checkpoints <= 4
+
+
+def test_timeloop_follow_mirrors_report():
+    """TimeLoop.follow (bookkeeping behind the device controller) reaches the same state as report() when it is fed the
+    verdicts and step sizes report() produced."""
+    import random
+
+    from pnode_b200.controller import TimeLoop
+
+    rng = random.Random(4)
+    for times in ([0.0, 0.3, 0.35, 1.0], [0.7], [0.0, 1.0]):
+        a = TimeLoop(times, 0.2, True, 5, True)
+        b = TimeLoop(times, 0.2, True, 5, True)
+        slots_a, slots_b = [], []
+        while not a.done:
+            enorm = rng.choice([0.01, 0.3, 0.9, 1.7, 3.0])
+            ok = a.report(enorm)
+            assert b.follow(ok, enorm, a.t, a.h) == ok
+            if ok:
+                slots_a.append(a.last_out_slot), slots_b.append(b.last_out_slot)
+        assert b.done and slots_a == slots_b
+        for k in ("t", "h", "steps", "ctr", "cur_sol_index", "cur_sol_steps", "attempts", "last_h"):
+            assert getattr(a, k) == getattr(b, k), k
+        b.check_complete()

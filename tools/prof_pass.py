@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--passes", type=int, default=1)
     ap.add_argument("--opt", nargs="*", default=[])
+    ap.add_argument("--cprofile", type=int, default=0, help="N > 0: cProfile N passes (host time) instead of the ncu window")
     args = ap.parse_args()
     from pnode import petsc_adjoint
     from pnode_b200.options import Options
@@ -40,6 +41,26 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    if args.cprofile:
+        import cProfile
+        import pstats
+        import time
+
+        t0 = time.perf_counter()
+        for _ in range(args.cprofile):
+            step()
+        torch.cuda.synchronize()
+        print("wall ms/pass (unprofiled): %.4f" % ((time.perf_counter() - t0) * 1e3 / args.cprofile))
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(args.cprofile):
+            step()
+        torch.cuda.synchronize()
+        pr.disable()
+        st = pstats.Stats(pr)
+        st.sort_stats("cumulative").print_stats(45)
+        st.sort_stats("tottime").print_stats(30)
+        return
     torch.cuda.profiler.start()
     for _ in range(args.passes):
         step()
