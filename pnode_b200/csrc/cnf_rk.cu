@@ -21,6 +21,34 @@
 #include "common.cuh"
 #include "f32x2.cuh"
 
+// tuning switches (tools/tune_cnf.py builds -D variants; the defaults are the measured best)
+#ifndef CNF_PREFETCH
+#define CNF_PREFETCH 1   // adjoint: fetch a stage's checkpoint one stage ahead of its use
+#endif
+#ifndef CNF_F32ACC
+#define CNF_F32ACC 1     // adjoint, fp32: per-lane parameter-gradient sums in fp32 (fp64 from the block combine on)
+#endif
+#ifndef CNF_ACC_EARLY
+#define CNF_ACC_EARLY 1  // adjoint: read the chunk's accumulators before the phase-2 loop, not after it
+#endif
+#ifndef CNF_P1_UNROLL
+#define CNF_P1_UNROLL 2  // adjoint phase 1: hidden units in flight per thread
+#endif
+#ifndef CNF_P2_UNROLL
+#define CNF_P2_UNROLL 2  // adjoint phase 2: 16-byte trajectory vectors in flight per lane
+#endif
+#ifndef CNF_HOIST_Q
+#define CNF_HOIST_Q 1    // attempt kernel: q_j = W1[j,:] e once per attempt (a shared-memory column per thread), not per stage
+#endif
+#ifndef CNF_ATT_MINB
+#define CNF_ATT_MINB 2   // attempt kernel: CTAs per SM the register allocation aims at
+#endif
+#ifndef CNF_EVAL_UNROLL
+#define CNF_EVAL_UNROLL 4  // attempt kernel: hidden units in flight per thread
+#endif
+#define CNF_PRAGMA_(x) _Pragma(#x)
+#define CNF_UNROLL(n) CNF_PRAGMA_(unroll n)
+
 namespace pnode {
 
 template <typename T>
@@ -84,6 +112,8 @@ struct CnfShared {
     T b2[D];
     T tstage[S];
     T ha[S][S], hb[S], he[S];  // h a_ij, h b_j, h (be_j - b_j): the stage / completion / error coefficients of this step
+    T adj_r[S][S], adj_c[S];   // adjoint stage recurrences: a_ji / b_i and h b_i (a_ji and h where b_i = 0)
+    int adj_has_b[S];
 };
 
 // Stage time as the module sees it.  FFJORD's ODEfunc does `t = torch.tensor(t).type_as(y)` (odefunc.py:356):
@@ -130,16 +160,24 @@ __device__ __forceinline__ void cnf_setup(CnfShared<T, D, H, S> &sm, const CnfPt
         sm.tstage[i] = stage_time<T>(t + tab.c[i] * h, w.t_f32);
         sm.hb[i] = (T)(h * tab.b[i]);
         sm.he[i] = (T)(h * (tab.be[i] - tab.b[i]));
+        const double bi = tab.b[i];
+        sm.adj_has_b[i] = bi != 0.0;
+        sm.adj_c[i] = (T)(bi != 0.0 ? h * bi : h);
 #pragma unroll
-        for (int j = 0; j < S; ++j) sm.ha[i][j] = (T)(h * tab.a[i][j]);
+        for (int j = 0; j < S; ++j) {
+            sm.ha[i][j] = (T)(h * tab.a[i][j]);
+            sm.adj_r[j][i] = (T)(bi != 0.0 ? tab.a[j][i] / bi : tab.a[j][i]);
+        }
     }
 }
 
 // f(t_i, (z, .)): out[0..D) = dz, out[D] = -e^T J e -- for the Pack<T>::W trajectories a thread carries (fp64: one, plain
 // doubles; fp32: two, in the halves of packed registers, every operation an FFMA2 / FMUL2 / FADD2)
+// qcol: the thread's column of q_j = W1[j,:] e (stride CNF_THREADS), which does not depend on the stage -- computed once
+// per attempt by the caller; nullptr: recomputed here.
 template <typename T, int D, int H, int S, typename V>
 __device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i, const V (&z)[D], const V (&e)[D],
-                                         V (&out)[D + 1]) {
+                                         V (&out)[D + 1], const V *__restrict__ qcol, int qstride) {
     V ge[D], r[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -147,16 +185,17 @@ __device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i,
         r[k] = Pack<T>::all(sm.b2[k]);
     }
     V div = Pack<T>::all(T(0));
-#pragma unroll 2
+    CNF_UNROLL(CNF_EVAL_UNROLL)
     for (int j = 0; j < H; ++j) {
         const UnitC<T, D> u = sm.unit[j];
         V p = Pack<T>::all(u.b1), q = Pack<T>::all(T(0)), w = Pack<T>::all(T(0));
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             p = fma(u.w1[k], z[k], p);
-            q = fma(u.w1[k], e[k], q);
+            if (!CNF_HOIST_Q) q = fma(u.w1[k], e[k], q);
             w = fma(u.w2[k], ge[k], w);
         }
+        if (CNF_HOIST_Q) q = qcol[j * qstride];
         const T g1 = sm.g1[i][j];
         const V a = fma(p, g1, sm.c1[i][j]);
         V s, sg;
@@ -267,7 +306,7 @@ __device__ inline void report(pnode_cnf_ctl &c, double sumsq) {
 }  // namespace ctl
 
 template <typename T, int D, int H, int S>
-__global__ void __launch_bounds__(CNF_THREADS, 2)
+__global__ void __launch_bounds__(CNF_THREADS, CNF_ATT_MINB)
 cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u,
                       const T *__restrict__ kfsal_in, const int64_t ntraj, double t, double h,
                       T *__restrict__ unew, T *__restrict__ kfsal_out, T *__restrict__ ckpt, const double atol,
@@ -295,6 +334,8 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
         if (slot >= 0 && sol != nullptr) sol_out = sol + (int64_t)slot * n;
     }
     __shared__ CnfShared<T, D, H, S> sm;
+    extern __shared__ __align__(16) unsigned char cnf_dyn_smem[];
+    V *qcol = reinterpret_cast<V *>(cnf_dyn_smem) + threadIdx.x;  // [H][CNF_THREADS], this thread's column
     cnf_setup<T, D, H, S>(sm, w, tab, t, h);
     __syncthreads();
     constexpr int N = D + 1;
@@ -330,6 +371,15 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
             e[k] = gather(w.e, D, k);
         }
         y[D] = gather(u, 1, ntraj * D);
+        if (CNF_HOIST_Q) {
+#pragma unroll 4
+            for (int j = 0; j < H; ++j) {
+                V q = P::all(T(0));
+#pragma unroll
+                for (int k = 0; k < D; ++k) q = fma(sm.unit[j].w1[k], e[k], q);
+                qcol[j * CNF_THREADS] = q;
+            }
+        }
         if (sol_out != nullptr) {  // the state this attempt starts from landed on an output time
 #pragma unroll
             for (int k = 0; k < D; ++k) scatter(sol_out, D, k, y[k]);
@@ -359,7 +409,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
                 V z[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) z[k] = Y[k];
-                cnf_eval<T, D, H, S, V>(sm, i, z, e, K[i]);
+                cnf_eval<T, D, H, S, V>(sm, i, z, e, K[i], qcol, CNF_THREADS);
             }
         }
         V yn[N], err[N];
@@ -459,12 +509,13 @@ struct CnfAdjWork {
     double partial[1];  // [blocks][NP]
 };
 
-// warp-private tile: five per-(unit, trajectory) arrays + the per-trajectory vectors phase 2 needs
+// warp-private tile: four per-(unit, trajectory) arrays + the per-trajectory vectors phase 2 needs.  (theta_j = dL/dg1_j =
+// delta_j p_j + beta'_j q_j needs no array of its own: p_j = W1[j,:] z + b1_j and q_j = W1[j,:] e, so its sum over the
+// trajectories is W1[j,:] . (sum delta_j z + sum beta'_j e) + b1_j sum delta_j -- quantities phase 2 forms anyway.)
 template <typename T, int D, int H>
 struct alignas(16) CnfTile {
     T dl[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // delta_j  = dL/da_j
     T bp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // beta'_j  = -v_l sg_j w_j
-    T th[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // theta_j  = dL/dg1_j
     T sp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // s_j      = softplus(a_j)
     T eg[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // -v_l sg_j q_j g1_j
     T Z[D][CnfAdjShape<T, D, H>::NT], E[D][CnfAdjShape<T, D, H>::NT], VZ[D][CnfAdjShape<T, D, H>::NT];
@@ -524,6 +575,17 @@ struct VecAcc<float> {
     static __device__ __forceinline__ float total(A a) { return lo(a) + hi(a); }
 };
 
+template <typename T>
+struct AccType {
+    typedef double type;
+};
+#if CNF_F32ACC
+template <>
+struct AccType<float> {
+    typedef float type;
+};
+#endif
+
 template <typename T, int D, int H, int S>
 __global__ void __launch_bounds__(CNF_ADJ_THREADS)
 cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
@@ -548,19 +610,26 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     const int s_eff = tab.fsal ? S - 1 : S;
     const int64_t state_n = ntraj * NST;
 
-    // per-lane accumulators, lane = (hidden unit of chunk c, trajectory group); kept in a small local array: touched once
-    // per stage-chunk
-    double aW1[NCH][D], aW2[NCH][D], aB1[NCH], aHB1[NCH], aHGW1[NCH], aHGB1[NCH];
+    // per-lane accumulators, lane = (hidden unit of chunk c, trajectory group): [0,D) dW1 row, [D,2D) dW2 column, then
+    // db1, dhb1, dhgw1, dhgb1.  They live in local memory (indexed by the chunk), are read into registers BEFORE the phase-2
+    // loop and written back after it, so the L2 round trip hides behind the loop.  fp32 path: fp32 sums (each term is
+    // already an fp32 sum over 32 trajectories; ~250 terms per lane and launch), converted for the fp64 block combine.
+    typedef typename AccType<T>::type AccT;
+    constexpr int NA = 2 * D + 4;
+    AccT acc[NCH][NA];
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c)
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        aB1[c] = aHB1[c] = aHGW1[c] = aHGB1[c] = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) aW1[c][k] = aW2[c][k] = 0.0;
-    }
+        for (int x = 0; x < NA; ++x) acc[c][x] = AccT(0);
     // per-thread accumulators of the layer-2 bias / gate gradients (reduced over the warp at the end)
-    V aB2[D], aHB2[D], aHGW2[D], aHGB2[D];
+    T aB2[D], aHB2[D], aHGW2[D], aHGB2[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) aB2[k] = aHB2[k] = aHGW2[k] = aHGB2[k] = P::all(T(0));
+    for (int k = 0; k < D; ++k) aB2[k] = aHB2[k] = aHGW2[k] = aHGB2[k] = T(0);
+    auto both_lanes = [](V v) -> T {
+        T t = P::get(v, 0);
+        if (W == 2) t += P::get(v, 1);
+        return t;
+    };
 
     const int64_t nslots = (ntraj + W - 1) / W;
     const int64_t ntiles = (nslots + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
@@ -588,6 +657,13 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
             e[k] = gather(w.e, D, k);
         }
         lam[D] = gather(gout, 1, (int64_t)last_slot * state_n + ntraj * D);
+        // stage checkpoints are fetched one stage ahead of their use
+        const int i_first = tab.fsal ? S - 2 : S - 1;
+        V znext[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            znext[k] = CNF_PREFETCH ? gather(ckpt, 1, (((int64_t)(nsteps - 1) * s_eff + i_first) * D + k) * ntraj)
+                                    : P::all(T(0));
 
         for (int n = nsteps - 1; n >= 0; --n) {
             const double h = sched[n].h;
@@ -605,14 +681,13 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     continue;
                 }
                 // cotangents of the stage slope, pre-multiplied by the step coefficient
-                const double bi = tab.b[i];
-                const bool has_b = bi != 0.0;
-                const T cstep = (T)(has_b ? h * bi : h);
+                const bool has_b = sm.adj_has_b[i] != 0;
+                const T cstep = sm.adj_c[i];
                 V vz[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) vz[k] = has_b ? lam[k] : P::all(T(0));
                 for (int j = i + 1; j < S; ++j) {
-                    const T rr = (T)(has_b ? tab.a[j][i] / bi : tab.a[j][i]);
+                    const T rr = sm.adj_r[j][i];
 #pragma unroll
                     for (int k = 0; k < D; ++k) vz[k] = fma(rr, ls[j][k], vz[k]);
                 }
@@ -621,8 +696,18 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                 V z[D], vg[D], ge[D], r[D], rho[D], dzk[D];
                 const T tt = sm.tstage[i];
 #pragma unroll
+                for (int k = 0; k < D; ++k)
+                    z[k] = CNF_PREFETCH ? znext[k] : gather(ckpt, 1, (((int64_t)n * s_eff + i) * D + k) * ntraj);
+                if (CNF_PREFETCH) {
+                    const int nn = i > 0 ? n : n - 1, in = i > 0 ? i - 1 : i_first;
+                    if (nn >= 0) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k)
+                            znext[k] = gather(ckpt, 1, (((int64_t)nn * s_eff + in) * D + k) * ntraj);
+                    }
+                }
+#pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    z[k] = gather(ckpt, 1, (((int64_t)n * s_eff + i) * D + k) * ntraj);
                     vz[k] = vz[k] * cstep;
                     vg[k] = vz[k] * sm.g2[i][k];
                     ge[k] = sm.g2[i][k] * e[k];
@@ -638,7 +723,7 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     const int j0 = c * JH;
                     const int jn = (H - j0 < JH) ? (H - j0) : JH;
                     // ---- phase 1 (lane = W trajectories) --------------------------------------------------------------
-#pragma unroll 2
+                    CNF_UNROLL(CNF_P1_UNROLL)
                     for (int jj = 0; jj < jn; ++jj) {
                         const int j = j0 + jj;
                         const UnitC<T, D> u = sm.unit[j];
@@ -660,7 +745,6 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                         const V betap = bq * ww;   // d(-v_l div)/d(g1 q) per unit
                         const V epsp = bq * q;
                         const V delta = fma(betap * g1 * q, one_minus(sg), m * sg);  // dL/da_j
-                        const V theta = fma(delta, p, betap * q);                    // dL/dg1_j
                         const V dg = delta * g1;
                         const V egv = epsp * g1;
 #pragma unroll
@@ -670,27 +754,30 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                         }
                         tile_put(&tile.dl[jj * PITCH], lane, delta);
                         tile_put(&tile.bp[jj * PITCH], lane, betap);
-                        tile_put(&tile.th[jj * PITCH], lane, theta);
                         tile_put(&tile.sp[jj * PITCH], lane, s);
                         tile_put(&tile.eg[jj * PITCH], lane, egv);
                     }
                     __syncwarp();
                     // ---- phase 2 (lane = hidden unit x trajectory group): sums over the warp's trajectories -----------
                     if (pu < jn) {
-                        typename VA::A sW1[D], sW2[D], sD = VA::zero(), sTh = VA::zero();
+                        constexpr bool EARLY = CNF_ACC_EARLY && W == 2;  // fp64 has no registers to spare for it
+                        AccT ar[NA];
+                        if (EARLY) {
+#pragma unroll
+                            for (int x = 0; x < NA; ++x) ar[x] = acc[c][x];
+                        }
+                        typename VA::A sW1[D], sW2[D], sD = VA::zero();
 #pragma unroll
                         for (int k = 0; k < D; ++k) sW1[k] = sW2[k] = VA::zero();
-#pragma unroll 2
+                        CNF_UNROLL(CNF_P2_UNROLL)
                         for (int mm = 0; mm < NT / VEC / HALVES; ++mm) {
                             const int kk = (mm * HALVES + pg) * VEC;
-                            T dl[VEC], bp[VEC], th[VEC], sp[VEC], eg[VEC];
+                            T dl[VEC], bp[VEC], sp[VEC], eg[VEC];
                             cnf_lds16(&tile.dl[pu * PITCH + kk], dl);
                             cnf_lds16(&tile.bp[pu * PITCH + kk], bp);
-                            cnf_lds16(&tile.th[pu * PITCH + kk], th);
                             cnf_lds16(&tile.sp[pu * PITCH + kk], sp);
                             cnf_lds16(&tile.eg[pu * PITCH + kk], eg);
                             VA::add(sD, dl);
-                            VA::add(sTh, th);
 #pragma unroll
                             for (int k = 0; k < D; ++k) {
                                 T zz[VEC], ee[VEC], vv[VEC];
@@ -703,18 +790,28 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                                 VA::mac(sW2[k], eg, ee);
                             }
                         }
-                        const double g1 = (double)sm.g1[i][j0 + pu];
-                        const double gd = g1 * (1.0 - g1);
-                        const double dD = (double)VA::total(sD), dTh = (double)VA::total(sTh);
+                        if (!EARLY) {
+#pragma unroll
+                            for (int x = 0; x < NA; ++x) ar[x] = acc[c][x];
+                        }
+                        const AccT g1 = (AccT)sm.g1[i][j0 + pu];
+                        const AccT gd = g1 * (AccT(1) - g1);
+                        const AccT dD = (AccT)VA::total(sD), ta = (AccT)tt;
+                        const UnitC<T, D> un = sm.unit[j0 + pu];
+                        AccT dTh = (AccT)un.b1 * dD;  // sum over the trajectories of theta_j
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
-                            aW1[c][k] += g1 * (double)VA::total(sW1[k]);
-                            aW2[c][k] += (double)sm.g2[i][k] * (double)VA::total(sW2[k]);
+                            const AccT s1 = (AccT)VA::total(sW1[k]);
+                            dTh = fma((AccT)un.w1[k], s1, dTh);
+                            ar[k] = fma(g1, s1, ar[k]);
+                            ar[D + k] = fma((AccT)sm.g2[i][k], (AccT)VA::total(sW2[k]), ar[D + k]);
                         }
-                        aB1[c] += g1 * dD;
-                        aHB1[c] += (double)tt * dD;
-                        aHGB1[c] += gd * dTh;
-                        aHGW1[c] += (double)tt * gd * dTh;
+                        ar[2 * D] = fma(g1, dD, ar[2 * D]);
+                        ar[2 * D + 1] = fma(ta, dD, ar[2 * D + 1]);
+                        ar[2 * D + 2] = fma(ta * gd, dTh, ar[2 * D + 2]);
+                        ar[2 * D + 3] = fma(gd, dTh, ar[2 * D + 3]);
+#pragma unroll
+                        for (int x = 0; x < NA; ++x) acc[c][x] = ar[x];
                     }
                     __syncwarp();
                 }
@@ -723,10 +820,11 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     ls[i][k] = dzk[k];
                     const T g2 = sm.g2[i][k];
                     const V Gk = fma(vz[k], r[k], e[k] * rho[k]) * (g2 * (T(1) - g2));  // dL/d(gate-2 pre-activation)
-                    aB2[k] += vg[k];
-                    aHB2[k] = fma(vz[k], tt, aHB2[k]);
-                    aHGB2[k] += Gk;
-                    aHGW2[k] = fma(Gk, tt, aHGW2[k]);
+                    const T svg = both_lanes(vg[k]), svz = both_lanes(vz[k]), sG = both_lanes(Gk);
+                    aB2[k] += svg;
+                    aHB2[k] = fma(svz, tt, aHB2[k]);
+                    aHGB2[k] += sG;
+                    aHGW2[k] = fma(sG, tt, aHGW2[k]);
                 }
             }
             for (int i = 0; i < S; ++i)
@@ -763,13 +861,14 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
         const bool writer = pg == 0 && pu < JH && j < H;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const double v1 = both(aW1[c][k]), v2 = both(aW2[c][k]);
+            const double v1 = both((double)acc[c][k]), v2 = both((double)acc[c][D + k]);
             if (writer) {
                 blk[warp * NP + j * D + k] = v1;
                 blk[warp * NP + O_W2 + k * H + j] = v2;
             }
         }
-        const double b1 = both(aB1[c]), hb1 = both(aHB1[c]), hgw1 = both(aHGW1[c]), hgb1 = both(aHGB1[c]);
+        const double b1 = both((double)acc[c][2 * D]), hb1 = both((double)acc[c][2 * D + 1]);
+        const double hgw1 = both((double)acc[c][2 * D + 2]), hgb1 = both((double)acc[c][2 * D + 3]);
         if (writer) {
             blk[warp * NP + O_B1 + j] = b1;
             blk[warp * NP + O_HB1 + j] = hb1;
@@ -777,16 +876,10 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
             blk[warp * NP + O_HGB1 + j] = hgb1;
         }
     }
-    auto lanes = [&](V v) -> double {
-        double t = 0.0;
-#pragma unroll
-        for (int x = 0; x < W; ++x) t += (double)P::get(v, x);
-        return t;
-    };
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        const double b2 = warp_sum(lanes(aB2[k])), hb2 = warp_sum(lanes(aHB2[k]));
-        const double hgw2 = warp_sum(lanes(aHGW2[k])), hgb2 = warp_sum(lanes(aHGB2[k]));
+        const double b2 = warp_sum((double)aB2[k]), hb2 = warp_sum((double)aHB2[k]);
+        const double hgw2 = warp_sum((double)aHGW2[k]), hgb2 = warp_sum((double)aHGB2[k]);
         if (lane == 0) {
             blk[warp * NP + O_B2 + k] = b2;
             blk[warp * NP + O_HB2 + k] = hb2;
@@ -845,9 +938,11 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
                               void *d_ubuf = nullptr, void *d_kbuf = nullptr, int64_t ckpt_step_elems = 0,
                               void *d_sol = nullptr, int nlaunch = 1) {
     auto kern = cnf_rk_attempt_kernel<T, 6, 60, S>;
+    const size_t smem = CNF_HOIST_Q ? sizeof(typename Pack<T>::V) * 60 * CNF_THREADS : 0;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
-        PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, CNF_THREADS, 0));
+        PNODE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNODE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, CNF_THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const int64_t nslots = (ntraj + Pack<T>::W - 1) / Pack<T>::W;  // fp32: two trajectories per thread (csrc/f32x2.cuh)
@@ -857,7 +952,7 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     for (int l = 0; l < nlaunch; ++l)
-        kern<<<grid, CNF_THREADS, 0, st>>>(cnf_ptrs<T>(c), *tab, static_cast<const T *>(d_u), static_cast<const T *>(d_kin),
+        kern<<<grid, CNF_THREADS, smem, st>>>(cnf_ptrs<T>(c), *tab, static_cast<const T *>(d_u), static_cast<const T *>(d_kin),
                                            ntraj, t, h, static_cast<T *>(d_unew), static_cast<T *>(d_kout),
                                            static_cast<T *>(d_ckpt), atol, rtol, d_sumsq,
                                            static_cast<CnfWrmsWork *>(d_work), d_ctl, static_cast<T *>(d_ubuf),
