@@ -202,12 +202,14 @@ typedef struct pnode_cnf_ctl {
     double n_global;                 /* length of the state vector in the WRMS norm */
     double delta;                    /* tspanPostStep hit tolerance: 1e-5 (fp64) / 1e-3 (fp32) */
     int32_t nspan, order, max_reject;
-    int32_t done;                    /* 0 running, 1 end time reached, 2 too many rejections, 3 log full */
+    int32_t done;                    /* 0 running, 1 end time reached, 2 too many rejections, 3 log full, 4 max_steps reached */
     int32_t cur, kcur, have_k;       /* ping-pong indices of d_ubuf / d_kbuf; have_k: a carried-over FSAL slope exists */
     int32_t steps, attempts, rejections, prev_ok;
     int32_t ctr, cur_sol_index;      /* [PETSc] tspan->spanctr; pnode's cur_sol_index */
     int32_t pending_slot;            /* output slot the state reached by the last accepted step belongs to (-1: none); the
                                         NEXT attempt copies its input state there (the final state is read from d_ubuf) */
+    int32_t max_steps;               /* room in the checkpoint buffer: the loop stops (done = 4) when ctl->steps reaches it and
+                                        the end time has not been reached (0: no limit) */
     double sumsq;                    /* the last attempt's weighted error sum of squares */
     double log_t[PNODE_CTL_MAX_LOG], log_h[PNODE_CTL_MAX_LOG], log_enorm[PNODE_CTL_MAX_LOG];
     int32_t log_accepted[PNODE_CTL_MAX_LOG];
@@ -215,6 +217,17 @@ typedef struct pnode_cnf_ctl {
 int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
                               int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol,
                               double rtol, pnode_cnf_ctl *d_ctl, void *d_work, int nlaunch, void *stream);
+
+/* The whole adaptive time loop in ONE launch: a CUDA graph whose WHILE node repeats the attempt kernel for as long as the
+ * last block of the previous attempt left ctl->done == 0 (it calls cudaGraphSetConditional on the node's handle).  Same
+ * arguments and state as pnode_cnf_rk_attempts_ctl; no host involvement until the loop ends -- with done = 1 (finished),
+ * 2 (more than max_reject rejections in a row), 3 (attempt log full: reset ctl->attempts and call again) or 4 (ctl->steps
+ * reached ctl->max_steps: provide more checkpoint room and call again).  Graphs are cached by their full argument list
+ * (the arguments are baked into the kernel node), so callers should reuse their buffers.  Must not be called on a stream
+ * that is itself being captured. */
+int pnode_cnf_rk_solve_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
+                           int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
+                           pnode_cnf_ctl *d_ctl, void *d_work, void *stream);
 
 /* Whole discrete-adjoint sweep over the accepted steps (same conventions as pnode_mlp_rk_adjoint); the per-stage VJP
  * (RHSJacShell.multTranspose, petsc_adjoint.py:52-82, which needs second-order autograd in the reference) is evaluated

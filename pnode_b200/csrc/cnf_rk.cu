@@ -18,6 +18,9 @@
 //  * cnf_rk_adj_kernel: ONE launch = the whole discrete-adjoint sweep.  Parameter gradients (984 scalars) are reduced with
 //    the same warp-private transposed SMEM tile as csrc/mlp_rk.cu (lane = hidden unit in the reduce phase), layer-2 gate /
 //    bias gradients in per-thread registers; per-block partials are combined in fixed order by the last block.
+#include <mutex>
+#include <string.h>
+
 #include "common.cuh"
 #include "f32x2.cuh"
 
@@ -299,7 +302,10 @@ __device__ inline void report(pnode_cnf_ctl &c, double sumsq) {
         c.cur ^= 1;       // the candidate becomes the state
         c.kcur ^= 1;      // and its last stage slope the carried-over one
         c.have_k = 1;
-        if (!(c.t < c.t_end && fabs(c.t - c.t_end) > SPAN_ABSTOL)) c.done = 1;
+        if (!(c.t < c.t_end && fabs(c.t - c.t_end) > SPAN_ABSTOL))
+            c.done = 1;
+        else if (c.max_steps > 0 && c.steps >= c.max_steps)
+            c.done = 4;
     }
     if (c.attempts >= PNODE_CTL_MAX_LOG && c.done == 0) c.done = 3;
 }
@@ -312,7 +318,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
                       T *__restrict__ unew, T *__restrict__ kfsal_out, T *__restrict__ ckpt, const double atol,
                       const double rtol, double *__restrict__ sumsq, CnfWrmsWork *__restrict__ work,
                       pnode_cnf_ctl *__restrict__ dctl, T *__restrict__ ubuf, T *__restrict__ kbuf,
-                      const int64_t ckpt_step_elems, T *__restrict__ sol) {
+                      const int64_t ckpt_step_elems, T *__restrict__ sol, const unsigned long long loop_cond) {
     typedef Pack<T> P;
     typedef typename P::V V;
     constexpr int W = P::W;  // trajectories per thread
@@ -321,7 +327,11 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
         // device-controlled attempt: time, step and buffers come from the control block the previous attempt's last block
         // wrote (every block reads it before any block of THIS launch can modify it: the update happens behind the ticket)
         const volatile pnode_cnf_ctl *vc = dctl;
-        if (vc->done != 0) return;
+        if (vc->done != 0) {
+            // the WHILE node runs its body once per launch whatever the state: end the loop
+            if (loop_cond != 0ull && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(loop_cond, 0u);
+            return;
+        }
         t = vc->t, h = vc->h;
         const int64_t n = ntraj * (D + 1);
         const int cur = vc->cur, kcur = vc->kcur;
@@ -474,6 +484,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
             if (dctl != nullptr) {
                 ctl::report(*dctl, s);
                 __threadfence();
+                if (loop_cond != 0ull) cudaGraphSetConditional(loop_cond, dctl->done == 0 ? 1u : 0u);
             }
         }
     }
@@ -936,7 +947,7 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
                               int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
                               double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl = nullptr,
                               void *d_ubuf = nullptr, void *d_kbuf = nullptr, int64_t ckpt_step_elems = 0,
-                              void *d_sol = nullptr, int nlaunch = 1) {
+                              void *d_sol = nullptr, int nlaunch = 1, unsigned long long loop_cond = 0ull) {
     auto kern = cnf_rk_attempt_kernel<T, 6, 60, S>;
     const size_t smem = CNF_HOIST_Q ? sizeof(typename Pack<T>::V) * 60 * CNF_THREADS : 0;
     static int ctas_per_sm = 0;
@@ -956,7 +967,7 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
                                            ntraj, t, h, static_cast<T *>(d_unew), static_cast<T *>(d_kout),
                                            static_cast<T *>(d_ckpt), atol, rtol, d_sumsq,
                                            static_cast<CnfWrmsWork *>(d_work), d_ctl, static_cast<T *>(d_ubuf),
-                                           static_cast<T *>(d_kbuf), ckpt_step_elems, static_cast<T *>(d_sol));
+                                           static_cast<T *>(d_kbuf), ckpt_step_elems, static_cast<T *>(d_sol), loop_cond);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1050,6 +1061,105 @@ int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau 
     PNODE_CNF_STAGES(X)
 #undef X
     PNODE_REQUIRE(false, "pnode_cnf_rk_attempts_ctl: no kernel for %d stages", tab->s);
+}
+
+// ---- the adaptive time loop as a CUDA graph with a device-driven WHILE node ---------------------------------------------
+namespace {
+struct CnfLoopKey {
+    pnode_cnf_desc cnf;
+    pnode_rk_tableau tab;
+    void *ubuf, *kbuf, *ckpt, *sol, *ctl, *work;
+    int64_t ntraj, ckpt_step_elems;
+    double atol, rtol;
+};
+struct CnfLoopGraph {
+    CnfLoopKey key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long last_use = 0;
+};
+constexpr int CNF_LOOP_CACHE = 8;
+CnfLoopGraph g_loops[CNF_LOOP_CACHE];
+unsigned long long g_loop_clock = 0;
+cudaStream_t g_loop_capture_stream = nullptr;
+std::mutex g_loop_mutex;
+
+int build_loop_graph(const CnfLoopKey &k, CnfLoopGraph &out) {
+    if (out.exec != nullptr) cudaGraphExecDestroy(out.exec);
+    if (out.graph != nullptr) cudaGraphDestroy(out.graph);
+    out.exec = nullptr, out.graph = nullptr;
+    if (g_loop_capture_stream == nullptr)
+        PNODE_CUDA_OK(cudaStreamCreateWithFlags(&g_loop_capture_stream, cudaStreamNonBlocking));
+    PNODE_CUDA_OK(cudaGraphCreate(&out.graph, 0));
+    cudaGraphConditionalHandle cond;
+    PNODE_CUDA_OK(cudaGraphConditionalHandleCreate(&cond, out.graph, 1u, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    PNODE_CUDA_OK(cudaGraphAddNode(&node, out.graph, nullptr, 0, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    PNODE_CUDA_OK(cudaStreamBeginCaptureToGraph(g_loop_capture_stream, body, nullptr, nullptr, 0,
+                                                cudaStreamCaptureModeRelaxed));
+    int rc = -1;
+    double *d_sumsq = &static_cast<pnode_cnf_ctl *>(k.ctl)->sumsq;
+#define X(SS)                                                                                                            \
+    if (k.tab.s == SS) {                                                                                                 \
+        rc = k.cnf.dtype == PNODE_F32                                                                                    \
+                 ? launch_cnf_attempt<float, SS>(&k.cnf, &k.tab, nullptr, nullptr, k.ntraj, 0.0, 0.0, nullptr, nullptr,  \
+                                                 k.ckpt, k.atol, k.rtol, d_sumsq, k.work, g_loop_capture_stream,         \
+                                                 static_cast<pnode_cnf_ctl *>(k.ctl), k.ubuf, k.kbuf, k.ckpt_step_elems, \
+                                                 k.sol, 1, (unsigned long long)cond)                                    \
+                 : launch_cnf_attempt<double, SS>(&k.cnf, &k.tab, nullptr, nullptr, k.ntraj, 0.0, 0.0, nullptr, nullptr, \
+                                                  k.ckpt, k.atol, k.rtol, d_sumsq, k.work, g_loop_capture_stream,        \
+                                                  static_cast<pnode_cnf_ctl *>(k.ctl), k.ubuf, k.kbuf,                   \
+                                                  k.ckpt_step_elems, k.sol, 1, (unsigned long long)cond);               \
+    }
+    PNODE_CNF_STAGES(X)
+#undef X
+    cudaError_t e = cudaStreamEndCapture(g_loop_capture_stream, nullptr);
+    if (rc != 0) return rc;
+    PNODE_CUDA_OK(e);
+    PNODE_CUDA_OK(cudaGraphInstantiate(&out.exec, out.graph, 0));
+    out.key = k;
+    return 0;
+}
+}  // namespace
+
+int pnode_cnf_rk_solve_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
+                           int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
+                           pnode_cnf_ctl *d_ctl, void *d_work, void *stream) {
+    PNODE_REQUIRE(cnf && tab && d_ubuf && d_ctl && d_work, "pnode_cnf_rk_solve_ctl: null argument");
+    PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_solve_ctl: unsupported shape D=%d H=%d s=%d",
+                  cnf->dim, cnf->hidden, tab->s);
+    PNODE_REQUIRE(tab->has_be, "pnode_cnf_rk_solve_ctl: the device controller needs an embedded tableau");
+    PNODE_REQUIRE(!tab->fsal || d_kbuf, "pnode_cnf_rk_solve_ctl: FSAL tableau without slope buffers");
+    PNODE_REQUIRE(ntraj > 0, "pnode_cnf_rk_solve_ctl: bad ntraj");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    PNODE_CUDA_OK(cudaStreamIsCapturing(st, &cap));
+    PNODE_REQUIRE(cap == cudaStreamCaptureStatusNone, "pnode_cnf_rk_solve_ctl: the stream is being captured");
+    CnfLoopKey k;
+    memset(&k, 0, sizeof(k));  // padding bytes take part in the comparison
+    k.cnf = *cnf, k.tab = *tab;
+    k.ubuf = d_ubuf, k.kbuf = d_kbuf, k.ckpt = d_ckpt_base, k.sol = d_sol, k.ctl = d_ctl, k.work = d_work;
+    k.ntraj = ntraj, k.ckpt_step_elems = ckpt_step_elems, k.atol = atol, k.rtol = rtol;
+    std::lock_guard<std::mutex> lock(g_loop_mutex);
+    CnfLoopGraph *hit = nullptr, *victim = &g_loops[0];
+    for (auto &g : g_loops) {
+        if (g.exec != nullptr && memcmp(&g.key, &k, sizeof(k)) == 0) hit = &g;
+        if (g.last_use < victim->last_use) victim = &g;
+    }
+    if (hit == nullptr) {
+        int rc = build_loop_graph(k, *victim);
+        if (rc != 0) return rc;
+        hit = victim;
+    }
+    hit->last_use = ++g_loop_clock;
+    PNODE_CUDA_OK(cudaGraphLaunch(hit->exec, st));
+    return 0;
 }
 
 int64_t pnode_cnf_rk_adjoint_work_bytes(const pnode_cnf_desc *cnf) {

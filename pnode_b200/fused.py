@@ -308,8 +308,9 @@ class FusedCnfRK:
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=device)
         self._adj_work = None
         self._ckpt = None
-        self._ctl_host = self._ctl_dev = None
+        self._ctl_key = None
         self.device_controller = True  # -pnode_device_controller 0 falls back to one host read per attempt
+        self.device_loop = True        # -pnode_device_loop 0: stream launches in batches instead of the WHILE graph
         self.launches = 0
 
     @staticmethod
@@ -399,23 +400,57 @@ class FusedCnfRK:
         return u, sols, state
 
     # ---- adaptive run with the accept/reject decision and the next step size taken ON THE DEVICE --------------------------
-    CTL_BATCH = 8  # attempts launched between two host reads of the control block
+    CTL_BATCH = 8        # -pnode_device_loop 0: attempts launched between two host reads of the control block
+    CKPT_STEPS0 = 16     # checkpoint room of a fresh buffer, in steps (doubled when a solve runs out of it)
+
+    class _Lease:
+        """A checkpoint buffer on loan to one solve's autograd state; it goes back to the pool when that state dies, so
+        solves of the same shape keep presenting the same addresses to the cached loop graphs (csrc/cnf_rk.cu)."""
+
+        def __init__(self, pool, buf):
+            self.pool, self.buf = pool, buf
+
+        def __del__(self):
+            pool = self.pool
+            if pool is not None and len(pool) < 4:
+                pool.append(self.buf)
+
+    def _ctl_buffers(self, n, nspan):
+        key = (n, nspan)
+        if self._ctl_key != key:
+            self._ctl_key = key
+            nbytes = C.sizeof(_lib.CnfCtl)
+            self._ctl_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            self._ctl_dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._ctl_view = _lib.CnfCtl.from_buffer(self._ctl_host.numpy())
+            self._ubuf = torch.empty(2, n, dtype=self.dtype, device=self.device)
+            self._kbuf = torch.empty(2, n, dtype=self.dtype, device=self.device) if self.scheme.fsal else None
+            self._solbuf = torch.empty(nspan, n, dtype=self.dtype, device=self.device) if nspan else None
+            self._ckpt_pool = []
+        return self._ubuf, self._kbuf, self._solbuf
 
     def _forward_device_ctl(self, u0, loop, atol, rtol, save):
         """Same contract as forward().  The attempt kernel's last block runs TSAdaptChoose_Basic + MATCHSTEP + the span
-        bookkeeping (csrc/cnf_rk.cu, namespace ctl) and publishes (t, h, buffers) for the next attempt, so CTL_BATCH
-        attempts go out back to back and the host reads the control block once per batch instead of once per attempt;
-        the host TimeLoop then follows the device's log (TimeLoop.follow) for the bookkeeping the caller reads."""
+        bookkeeping (csrc/cnf_rk.cu, namespace ctl) and publishes (t, h, buffers) for the next attempt.  The whole time
+        loop is ONE launch -- a CUDA graph whose WHILE node repeats the attempt kernel until the controller says stop
+        (pnode_cnf_rk_solve_ctl) -- and the host reads the control block once per solve; the host TimeLoop then follows
+        the device's log (TimeLoop.follow) for the bookkeeping the caller reads.  With -pnode_device_loop 0 the attempts
+        go out as CTL_BATCH stream launches between host reads instead."""
         sp = self.spec
         ntraj = sp.batch
         n = u0.numel()
         desc = self._desc()
-        fsal = bool(self.scheme.fsal)
-        ubuf = torch.empty(2, n, dtype=self.dtype, device=self.device)
-        ubuf[0].copy_(u0)
-        kbuf = torch.empty(2, n, dtype=self.dtype, device=self.device) if fsal else None
         nspan = 0 if loop.span is None else len(loop.span)
-        sol = torch.empty(nspan, n, dtype=self.dtype, device=self.device) if nspan else None
+        ubuf, kbuf, sol = self._ctl_buffers(n, nspan)
+        ubuf[0].copy_(u0)
+        per_step = self.s_eff * sp.dim * ntraj
+        lease = None
+        cap = 0
+        if save:
+            buf = self._ckpt_pool.pop() if self._ckpt_pool else \
+                torch.empty(self.CKPT_STEPS0 * per_step, dtype=self.dtype, device=self.device)
+            lease = self._Lease(self._ckpt_pool, buf)
+            cap = buf.numel() // per_step
         ctl = _lib.CnfCtl()
         ctl.t, ctl.h, ctl.t_end, ctl.dt_span_cached = loop.t, loop.h, loop.t_end, 0.0
         for i in range(nspan):
@@ -424,12 +459,10 @@ class FusedCnfRK:
         ctl.nspan, ctl.order, ctl.max_reject = nspan, int(loop.order), int(loop.max_reject)
         ctl.done = 1 if loop.done else 0
         ctl.prev_ok, ctl.ctr, ctl.cur_sol_index, ctl.pending_slot = 1, 1, 1, -1
-        nbytes = C.sizeof(_lib.CnfCtl)
-        if self._ctl_host is None:
-            self._ctl_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            self._ctl_dev = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        host_view = _lib.CnfCtl.from_buffer(self._ctl_host.numpy())
+        ctl.max_steps = cap
+        host_view = self._ctl_view
         head = _lib.CnfCtl.log_t.offset  # everything before the log is the controller's state
+        stream = torch.cuda.current_stream()
 
         def upload(src):
             C.memmove(C.addressof(host_view), C.addressof(src), head)
@@ -438,24 +471,22 @@ class FusedCnfRK:
         upload(ctl)
         sols = {0: u0} if nspan else {}
         steps = []
-        self._keep = 0
-        cap = 2 * self.CTL_BATCH
-        per_step = self._ckpt_buffer(cap, ntraj) if save else 0
         seen = 0
+        c = host_view
         while not loop.done:
-            if save and len(steps) + self.CTL_BATCH > cap:
-                self._keep = len(steps)
-                cap = max(2 * cap, len(steps) + self.CTL_BATCH)
-                per_step = self._ckpt_buffer(cap, ntraj)
-            _lib.check(self.lib.pnode_cnf_rk_attempts_ctl(
-                C.byref(desc), C.byref(self.tab), ubuf.data_ptr(), None if kbuf is None else kbuf.data_ptr(), ntraj,
-                self._ckpt.data_ptr() if save else None, per_step, None if sol is None else sol.data_ptr(), float(atol),
-                float(rtol), self._ctl_dev.data_ptr(), self._wrms_work.data_ptr(), self.CTL_BATCH, _stream()))
+            args = (C.byref(desc), C.byref(self.tab), ubuf.data_ptr(), None if kbuf is None else kbuf.data_ptr(), ntraj,
+                    lease.buf.data_ptr() if save else None, per_step, None if sol is None else sol.data_ptr(), float(atol),
+                    float(rtol), self._ctl_dev.data_ptr(), self._wrms_work.data_ptr())
+            if self.device_loop:
+                _lib.check(self.lib.pnode_cnf_rk_solve_ctl(*args, stream.cuda_stream))
+            else:
+                _lib.check(self.lib.pnode_cnf_rk_attempts_ctl(*args, self.CTL_BATCH, stream.cuda_stream))
+                self.launches += self.CTL_BATCH
             self._ctl_host.copy_(self._ctl_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the one host read per CTL_BATCH attempts
-            c = host_view
+            stream.synchronize()  # the one host read per solve (per CTL_BATCH attempts without the device loop)
             now = c.attempts
-            self.launches += self.CTL_BATCH
+            if self.device_loop:
+                self.launches += now - seen  # kernel nodes the graph's WHILE loop executed
             for a in range(seen, now):
                 last = a + 1 == now
                 t_next = c.t if last else c.log_t[a + 1]
@@ -466,25 +497,29 @@ class FusedCnfRK:
             seen = now
             if c.done == 2:
                 raise RuntimeError("TS_DIVERGED_STEP_REJECTED: %d consecutive rejections at t=%g" % (c.rejections, c.t))
-            if c.done == 3:  # attempt log full: restart it
+            if c.done in (3, 4):  # attempt log full / out of checkpoint room: make room and go on
                 keep = _lib.CnfCtl()
                 C.memmove(C.addressof(keep), C.addressof(c), head)
-                keep.attempts, keep.done = 0, 0
+                if c.done == 3:
+                    keep.attempts = 0
+                    seen = 0
+                else:
+                    grown = torch.empty(2 * lease.buf.numel(), dtype=self.dtype, device=self.device)
+                    grown[: len(steps) * per_step].copy_(lease.buf[: len(steps) * per_step])
+                    lease.buf = grown  # the bigger buffer is the one that returns to the pool
+                    keep.max_steps = grown.numel() // per_step
+                keep.done = 0
                 upload(keep)
-                seen = 0
-        c = host_view
-        assert c.steps == len(steps), "device controller and host bookkeeping disagree on the step count"
-        u = ubuf[c.cur]
+        assert c.steps == len(steps) or not steps, "device controller and host bookkeeping disagree on the step count"
+        u = ubuf[c.cur].clone() if steps else u0.clone()
         for t_h_slot in steps:
             slot = t_h_slot[2]
             if slot >= 0:
                 # the state that landed on the LAST output time is the final one; earlier slots were copied by the
                 # attempt that followed them
-                sols[slot] = sol[slot] if not (t_h_slot is steps[-1]) else u.clone()
+                sols[slot] = u if t_h_slot is steps[-1] else sol[slot].clone()
         loop.check_complete()
-        state = {"steps": steps, "ckpt": self._ckpt if save else None, "ntraj": ntraj, "desc_keep": desc}
-        if save:
-            self._ckpt = None
+        state = {"steps": steps, "ckpt": lease.buf if save else None, "ntraj": ntraj, "desc_keep": desc, "lease": lease}
         return u, sols, state
 
     def adjoint(self, gout, state, single, nadj=None, comm=None):

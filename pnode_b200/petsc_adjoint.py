@@ -262,8 +262,9 @@ class ODEPetsc(object):
                 return None
             if self._fused is None or self._fused.scheme is not self._scheme:
                 self._fused = FusedCnfRK(self._fused_spec, self._scheme, self.tensor_dtype, self.device)
-                self._fused.device_controller = Options().getString("pnode_device_controller", "1") not in \
-                    ("0", "false", "no")
+            off = ("0", "false", "no")
+            self._fused.device_controller = Options().getString("pnode_device_controller", "1") not in off
+            self._fused.device_loop = Options().getString("pnode_device_loop", "1") not in off
         return self._fused_kind, self._fused
 
     # ------------------------------------------------------------------------------------------------------------

@@ -137,11 +137,13 @@ def test_probe_is_sampled_like_the_reference_when_absent():
     assert ode2.path == "generic" and rel_err(out, out2) < 1e-5
 
 
+@pytest.mark.parametrize("loop_opt", [[], ["-pnode_device_loop", "0"]], ids=["while-graph", "launch-batches"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_device_controller_follows_the_host_controller(dtype):
+def test_device_controller_follows_the_host_controller(dtype, loop_opt):
     """The accept/reject verdict and the next step size taken by the attempt kernel's last block (csrc/cnf_rk.cu, namespace
     ctl) against the host TimeLoop fed the same kernel's error norm once per attempt: same attempts, same steps, same
-    output-time copies.  The case has rejected attempts, clamped steps and three output times."""
+    output-time copies.  The case has rejected attempts, clamped steps and three output times.  Both ways of issuing the
+    attempts: the CUDA-graph WHILE loop (one launch per solve) and batches of stream launches."""
     from pnode import petsc_adjoint
 
     B = 300
@@ -153,11 +155,12 @@ def test_device_controller_follows_the_host_controller(dtype):
     t = torch.tensor([0.0, 0.3, 0.35, 1.0], dtype=torch.float64)
     tol = "1e-7" if dtype == torch.float64 else "1e-4"
     argv = ["-ts_rtol", tol, "-ts_atol", tol]
-    d = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 0.5)
+    d = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + loop_opt, func, u0, t, gout, "dopri5", 0.5)
     h = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + ["-pnode_device_controller", "0"], func, u0, t, gout, "dopri5",
              0.5)
     assert d[3].path == h[3].path == "fused-cnf-rk"
     assert d[3]._fused.device_controller and not h[3]._fused.device_controller
+    assert d[3]._fused.device_loop == (not loop_opt)
     la, lb = d[3]._loop.attempts, h[3]._loop.attempts
     if dtype == torch.float64:
         assert any(not a[2] for a in la), "case must contain a rejected attempt"
@@ -171,32 +174,38 @@ def test_device_controller_follows_the_host_controller(dtype):
     _compare(d, h, 1e-11 if dtype == torch.float64 else 1e-4)
 
 
-def test_device_controller_many_steps_and_single_end_time():
-    """More accepted steps than the first checkpoint allocation and than one launch batch; one-element t (no span).
-    Compared with the host-controlled run of the same kernels (at this tolerance the error estimate is too close to
-    rounding noise for the oracle's autograd evaluation to take the same decisions)."""
+@pytest.mark.parametrize("loop_opt", [[], ["-pnode_device_loop", "0"]], ids=["while-graph", "launch-batches"])
+def test_device_controller_many_steps_and_single_end_time(loop_opt):
+    """More accepted steps than the checkpoint buffer starts with (the device loop stops with done = 4, the host doubles
+    the buffer and the loop goes on); one-element t (no span); two solves in a row on the same object (buffers and the
+    cached loop graph are reused).  Compared with the host-controlled run of the same kernels (at this tolerance the
+    error estimate is too close to rounding noise for the oracle's autograd evaluation to take the same decisions)."""
     from pnode import petsc_adjoint
+    from pnode_b200.fused import FusedCnfRK
 
     B = 64
     func = CNFFunc(B, 6, (60,), dtype=torch.float64, seed=11)
     u0, gout = _inputs(B, 6, 1, torch.float64)
     t = torch.tensor([1.0], dtype=torch.float64)
     argv = ["-ts_rtol", "1e-10", "-ts_atol", "1e-10"]
-    from pnode_b200.fused import FusedCnfRK
-
-    batch = FusedCnfRK.CTL_BATCH
-    FusedCnfRK.CTL_BATCH = 2  # 4 checkpoint slots to start with, a host read every 2 attempts
+    room, batch = FusedCnfRK.CKPT_STEPS0, FusedCnfRK.CTL_BATCH
+    FusedCnfRK.CKPT_STEPS0, FusedCnfRK.CTL_BATCH = 2, 3
     try:
-        d = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 0.01)
+        d = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + loop_opt, func, u0, t, gout, "dopri5", 0.01)
+        ode = d[3]
+        y0 = u0.to("cuda").clone().requires_grad_(True)
+        again = ode.odeint_adjoint(y0, t.to("cuda"))  # same object: pooled checkpoint buffer, cached graph
+        lam_again, = torch.autograd.grad((again * gout.to("cuda")).sum(), [y0])
     finally:
-        FusedCnfRK.CTL_BATCH = batch
+        FusedCnfRK.CKPT_STEPS0, FusedCnfRK.CTL_BATCH = room, batch
     h = _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv + ["-pnode_device_controller", "0"], func, u0, t, gout, "dopri5",
              0.01)
     assert d[3].path == "fused-cnf-rk" and d[3]._fused.device_controller and not h[3]._fused.device_controller
-    assert d[3]._loop.steps > 2 * 2
+    assert d[3]._loop.steps > 4
     assert d[3]._loop.steps == h[3]._loop.steps
     assert d[0].shape == (1, B * 7)
     _compare(d, h, 1e-9)
+    assert torch.equal(again.detach(), d[0]) and torch.equal(lam_again, d[1])
 
 
 def test_device_controller_reports_divergence():
