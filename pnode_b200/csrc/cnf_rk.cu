@@ -174,22 +174,40 @@ __device__ __forceinline__ void cnf_setup(CnfShared<T, D, H, S> &sm, const CnfPt
     }
 }
 
+// A trajectory slot may be spread over LPT adjacent lanes, each owning H / LPT hidden units (small batches: the dependent
+// chain of one evaluation is LPT times shorter).  The partial sums over units are combined by an xor butterfly, which
+// leaves bit-identical totals in all LPT lanes, so they carry identical copies of the state from then on.
+__device__ __forceinline__ double shfl_x(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ F2 shfl_x(F2 v, int m) {
+    F2 r;
+    r.v = __shfl_xor_sync(0xffffffffu, v.v, m);
+    return r;
+}
+template <int LPT, typename V>
+__device__ __forceinline__ V sub_sum(V v) {
+#pragma unroll
+    for (int m = 1; m < LPT; m <<= 1) v = v + shfl_x(v, m);
+    return v;
+}
+
 // f(t_i, (z, .)): out[0..D) = dz, out[D] = -e^T J e -- for the Pack<T>::W trajectories a thread carries (fp64: one, plain
 // doubles; fp32: two, in the halves of packed registers, every operation an FFMA2 / FMUL2 / FADD2)
 // qcol: the thread's column of q_j = W1[j,:] e (stride CNF_THREADS), which does not depend on the stage -- computed once
 // per attempt by the caller; nullptr: recomputed here.
-template <typename T, int D, int H, int S, typename V>
+template <typename T, int D, int H, int S, int LPT, typename V>
 __device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i, const V (&z)[D], const V (&e)[D],
-                                         V (&out)[D + 1], const V *__restrict__ qcol, int qstride) {
+                                         V (&out)[D + 1], const V *__restrict__ qcol, int qstride, int sub) {
+    static_assert(H % LPT == 0, "hidden units must split evenly over the lanes of a slot");
     V ge[D], r[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         ge[k] = sm.g2[i][k] * e[k];
-        r[k] = Pack<T>::all(sm.b2[k]);
+        r[k] = Pack<T>::all(sub == 0 ? sm.b2[k] : T(0));
     }
     V div = Pack<T>::all(T(0));
+    const int jbeg = sub * (H / LPT), jend = jbeg + H / LPT;
     CNF_UNROLL(CNF_EVAL_UNROLL)
-    for (int j = 0; j < H; ++j) {
+    for (int j = jbeg; j < jend; ++j) {
         const UnitC<T, D> u = sm.unit[j];
         V p = Pack<T>::all(u.b1), q = Pack<T>::all(T(0)), w = Pack<T>::all(T(0));
 #pragma unroll
@@ -208,8 +226,8 @@ __device__ __forceinline__ void cnf_eval(const CnfShared<T, D, H, S> &sm, int i,
         div = fma(g1 * sg, w * q, div);
     }
 #pragma unroll
-    for (int k = 0; k < D; ++k) out[k] = fma(r[k], sm.g2[i][k], sm.c2[i][k]);
-    out[D] = -div;
+    for (int k = 0; k < D; ++k) out[k] = fma(sub_sum<LPT>(r[k]), sm.g2[i][k], sm.c2[i][k]);
+    out[D] = -sub_sum<LPT>(div);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -311,7 +329,7 @@ __device__ inline void report(pnode_cnf_ctl &c, double sumsq) {
 }
 }  // namespace ctl
 
-template <typename T, int D, int H, int S>
+template <typename T, int D, int H, int S, int LPT>
 __global__ void __launch_bounds__(CNF_THREADS, CNF_ATT_MINB)
 cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u,
                       const T *__restrict__ kfsal_in, const int64_t ntraj, double t, double h,
@@ -351,16 +369,22 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
     constexpr int N = D + 1;
     const int s_eff = tab.fsal ? S - 1 : S;
     double local = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / LPT;
     const int64_t nslots = (ntraj + W - 1) / W;
-    for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < nslots; slot += stride) {
-        // trajectories tr[0..W) of this thread; a missing second one (odd ntraj) computes on zeros and stores nothing
+    const int sub = threadIdx.x % LPT;  // which share of the hidden units this lane owns
+    // the trip count is uniform over a warp (the butterfly sums need all its lanes); slots past the end compute on zeros
+    const int64_t wslot = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / LPT;
+    const int64_t myslot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPT;
+    for (int64_t it = 0; wslot + it * stride < nslots; ++it) {
+        const int64_t slot = myslot + it * stride;
+        // trajectories tr[0..W) of this thread; a missing one (odd ntraj, tail of the warp) computes on zeros and stores nothing
         int64_t tr[W];
-        bool ok[W];
+        bool ok[W], st[W];
 #pragma unroll
         for (int x = 0; x < W; ++x) {
             tr[x] = slot * W + x;
             ok[x] = tr[x] < ntraj;
+            st[x] = ok[x] && sub == 0;  // one lane of the slot stores
             if (!ok[x]) tr[x] = ntraj - 1;
         }
         auto gather = [&](const T *base, int64_t mul, int64_t off) -> V {
@@ -372,7 +396,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
         auto scatter = [&](T *base, int64_t mul, int64_t off, V val) {
 #pragma unroll
             for (int x = 0; x < W; ++x)
-                if (ok[x]) base[tr[x] * mul + off] = P::get(val, x);
+                if (st[x]) base[tr[x] * mul + off] = P::get(val, x);
         };
         V y[N], e[D], K[S][N];
 #pragma unroll
@@ -383,7 +407,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
         y[D] = gather(u, 1, ntraj * D);
         if (CNF_HOIST_Q) {
 #pragma unroll 4
-            for (int j = 0; j < H; ++j) {
+            for (int j = sub * (H / LPT); j < (sub + 1) * (H / LPT); ++j) {
                 V q = P::all(T(0));
 #pragma unroll
                 for (int k = 0; k < D; ++k) q = fma(sm.unit[j].w1[k], e[k], q);
@@ -419,7 +443,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
                 V z[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) z[k] = Y[k];
-                cnf_eval<T, D, H, S, V>(sm, i, z, e, K[i], qcol, CNF_THREADS);
+                cnf_eval<T, D, H, S, LPT, V>(sm, i, z, e, K[i], qcol, CNF_THREADS, sub);
             }
         }
         V yn[N], err[N];
@@ -450,7 +474,7 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
                 const V xs = yn[k] + err[k];
 #pragma unroll
                 for (int x = 0; x < W; ++x) {
-                    if (!ok[x]) continue;
+                    if (!st[x]) continue;
                     const double un = (double)P::get(yn[k], x), xv = (double)P::get(xs, x);
                     const double tol = atol + rtol * fmax(fabs(un), fabs(xv));
                     const double rr = (un - xv) / tol;
@@ -500,10 +524,10 @@ constexpr int CNF_ADJ_THREADS = CNF_ADJ_WARPS * 32;
 // turns the tile: lane = (hidden unit u, trajectory group g), HALVES = W groups of 32/W lanes, each lane summing the
 // 16-byte vectors v = HALVES m + g of its unit's row -- so with two trajectories per thread the chunk holds 15 units and
 // all but two lanes work, instead of 15 of 32.
-template <typename T, int D, int H>
+template <typename T, int D, int H, int LPT>
 struct CnfAdjShape {
     static constexpr int W = Pack<T>::W;
-    static constexpr int NT = 32 * W;
+    static constexpr int NT = 32 * W / LPT;
     static constexpr int HALVES = W;
     static constexpr int LPH = 32 / HALVES;                      // lanes per trajectory group
     static constexpr int NCH = (W == 1) ? 2 : 4;                  // chunks of hidden units per stage
@@ -523,13 +547,13 @@ struct CnfAdjWork {
 // warp-private tile: four per-(unit, trajectory) arrays + the per-trajectory vectors phase 2 needs.  (theta_j = dL/dg1_j =
 // delta_j p_j + beta'_j q_j needs no array of its own: p_j = W1[j,:] z + b1_j and q_j = W1[j,:] e, so its sum over the
 // trajectories is W1[j,:] . (sum delta_j z + sum beta'_j e) + b1_j sum delta_j -- quantities phase 2 forms anyway.)
-template <typename T, int D, int H>
+template <typename T, int D, int H, int LPT>
 struct alignas(16) CnfTile {
-    T dl[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // delta_j  = dL/da_j
-    T bp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // beta'_j  = -v_l sg_j w_j
-    T sp[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // s_j      = softplus(a_j)
-    T eg[CnfAdjShape<T, D, H>::JH * CnfAdjShape<T, D, H>::PITCH];  // -v_l sg_j q_j g1_j
-    T Z[D][CnfAdjShape<T, D, H>::NT], E[D][CnfAdjShape<T, D, H>::NT], VZ[D][CnfAdjShape<T, D, H>::NT];
+    T dl[CnfAdjShape<T, D, H, LPT>::JH * CnfAdjShape<T, D, H, LPT>::PITCH];  // delta_j  = dL/da_j
+    T bp[CnfAdjShape<T, D, H, LPT>::JH * CnfAdjShape<T, D, H, LPT>::PITCH];  // beta'_j  = -v_l sg_j w_j
+    T sp[CnfAdjShape<T, D, H, LPT>::JH * CnfAdjShape<T, D, H, LPT>::PITCH];  // s_j      = softplus(a_j)
+    T eg[CnfAdjShape<T, D, H, LPT>::JH * CnfAdjShape<T, D, H, LPT>::PITCH];  // -v_l sg_j q_j g1_j
+    T Z[D][CnfAdjShape<T, D, H, LPT>::NT], E[D][CnfAdjShape<T, D, H, LPT>::NT], VZ[D][CnfAdjShape<T, D, H, LPT>::NT];
 };
 
 template <typename T>
@@ -597,13 +621,13 @@ struct AccType<float> {
 };
 #endif
 
-template <typename T, int D, int H, int S>
+template <typename T, int D, int H, int S, int LPT>
 __global__ void __launch_bounds__(CNF_ADJ_THREADS)
 cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
                   T *__restrict__ mu_out, CnfAdjWork *__restrict__ work, const PeerComm pc) {
-    typedef CnfAdjShape<T, D, H> Sh;
+    typedef CnfAdjShape<T, D, H, LPT> Sh;
     typedef Pack<T> P;
     typedef typename P::V V;
     typedef VecAcc<T> VA;
@@ -612,12 +636,13 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     constexpr int NST = D + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CnfShared<T, D, H, S> &sm = *reinterpret_cast<CnfShared<T, D, H, S> *>(smem_raw);
-    CnfTile<T, D, H> *tiles =
-        reinterpret_cast<CnfTile<T, D, H> *>(smem_raw + ((sizeof(CnfShared<T, D, H, S>) + 15) / 16) * 16);
+    CnfTile<T, D, H, LPT> *tiles =
+        reinterpret_cast<CnfTile<T, D, H, LPT> *>(smem_raw + ((sizeof(CnfShared<T, D, H, S>) + 15) / 16) * 16);
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pu = lane % LPH, pg = lane / LPH;  // phase 2: hidden unit within the chunk, trajectory group
-    CnfTile<T, D, H> &tile = tiles[warp];
+    CnfTile<T, D, H, LPT> &tile = tiles[warp];
+    const int sub = lane % LPT, col = lane / LPT;  // share of the hidden units; the slot's column pair in the tile
     const int s_eff = tab.fsal ? S - 1 : S;
     const int64_t state_n = ntraj * NST;
 
@@ -643,9 +668,10 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     };
 
     const int64_t nslots = (ntraj + W - 1) / W;
-    const int64_t ntiles = (nslots + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
+    constexpr int SLOTS_PER_CTA = CNF_ADJ_THREADS / LPT;
+    const int64_t ntiles = (nslots + SLOTS_PER_CTA - 1) / SLOTS_PER_CTA;
     for (int64_t tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
-        const int64_t slot = tidx * CNF_ADJ_THREADS + threadIdx.x;
+        const int64_t slot = tidx * SLOTS_PER_CTA + threadIdx.x / LPT;
         // the thread's trajectories; the ones past the end carry zeros everywhere, which contribute nothing to any sum
         int64_t tr[W];
         bool ok[W];
@@ -722,12 +748,14 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     vz[k] = vz[k] * cstep;
                     vg[k] = vz[k] * sm.g2[i][k];
                     ge[k] = sm.g2[i][k] * e[k];
-                    r[k] = P::all(sm.b2[k]);
                     rho[k] = P::all(T(0));
                     dzk[k] = P::all(T(0));
-                    tile_put(tile.Z[k], lane, z[k]);
-                    tile_put(tile.E[k], lane, e[k]);
-                    tile_put(tile.VZ[k], lane, vz[k]);
+                    r[k] = P::all(sub == 0 ? sm.b2[k] : T(0));
+                    if (sub == 0) {
+                        tile_put(tile.Z[k], col, z[k]);
+                        tile_put(tile.E[k], col, e[k]);
+                        tile_put(tile.VZ[k], col, vz[k]);
+                    }
                 }
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
@@ -735,7 +763,7 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                     const int jn = (H - j0 < JH) ? (H - j0) : JH;
                     // ---- phase 1 (lane = W trajectories) --------------------------------------------------------------
                     CNF_UNROLL(CNF_P1_UNROLL)
-                    for (int jj = 0; jj < jn; ++jj) {
+                    for (int jj = sub; jj < jn; jj += LPT) {
                         const int j = j0 + jj;
                         const UnitC<T, D> u = sm.unit[j];
                         V p = P::all(u.b1), q = P::all(T(0)), ww = P::all(T(0)), m = P::all(T(0));
@@ -763,10 +791,10 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                             dzk[k] = fma(u.w1[k], dg, dzk[k]);
                             rho[k] = fma(u.w2[k], egv, rho[k]);
                         }
-                        tile_put(&tile.dl[jj * PITCH], lane, delta);
-                        tile_put(&tile.bp[jj * PITCH], lane, betap);
-                        tile_put(&tile.sp[jj * PITCH], lane, s);
-                        tile_put(&tile.eg[jj * PITCH], lane, egv);
+                        tile_put(&tile.dl[jj * PITCH], col, delta);
+                        tile_put(&tile.bp[jj * PITCH], col, betap);
+                        tile_put(&tile.sp[jj * PITCH], col, s);
+                        tile_put(&tile.eg[jj * PITCH], col, egv);
                     }
                     __syncwarp();
                     // ---- phase 2 (lane = hidden unit x trajectory group): sums over the warp's trajectories -----------
@@ -828,9 +856,13 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                 }
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
+                    dzk[k] = sub_sum<LPT>(dzk[k]);
+                    r[k] = sub_sum<LPT>(r[k]);
+                    rho[k] = sub_sum<LPT>(rho[k]);
                     ls[i][k] = dzk[k];
                     const T g2 = sm.g2[i][k];
                     const V Gk = fma(vz[k], r[k], e[k] * rho[k]) * (g2 * (T(1) - g2));  // dL/d(gate-2 pre-activation)
+                    if (sub != 0) continue;  // one lane of the slot feeds the per-thread sums
                     const T svg = both_lanes(vg[k]), svz = both_lanes(vz[k]), sG = both_lanes(Gk);
                     aB2[k] += svg;
                     aHB2[k] = fma(svz, tt, aHB2[k]);
@@ -849,7 +881,7 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
         }
 #pragma unroll
         for (int x = 0; x < W; ++x) {
-            if (!ok[x]) continue;
+            if (!ok[x] || sub != 0) continue;
 #pragma unroll
             for (int k = 0; k < D; ++k) lambda_out[tr[x] * D + k] = P::get(lam[k], x);
             lambda_out[ntraj * D + tr[x]] = P::get(lam[D], x);
@@ -859,7 +891,7 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
     // ---- combine: per-lane / per-thread accumulators -> block partial (fixed order) -> last block sums the grid ---------
     __syncthreads();
     double *blk = reinterpret_cast<double *>(tiles);  // [CNF_ADJ_WARPS][NP]
-    static_assert(sizeof(CnfTile<T, D, H>) * CNF_ADJ_WARPS >= sizeof(double) * CNF_ADJ_WARPS * NP, "tile storage too small");
+    // (the launcher sizes the dynamic shared memory for whichever is larger: the tiles or this combine buffer)
     constexpr int O_B1 = H * D, O_HB1 = O_B1 + H, O_HGW1 = O_HB1 + H, O_HGB1 = O_HGW1 + H, O_W2 = O_HGB1 + H,
                   O_B2 = O_W2 + D * H, O_HB2 = O_B2 + D, O_HGW2 = O_HB2 + D, O_HGB2 = O_HGW2 + D;
     // the trajectory groups of a unit sit LPH lanes apart: group 0 collects
@@ -942,13 +974,22 @@ static CnfPtrs<T> cnf_ptrs(const pnode_cnf_desc *c) {
                       p(c->d_b2), p(c->d_hb2), p(c->d_hgw2), p(c->d_hgb2), p(c->d_e), c->t_via_f32};
 }
 
-template <typename T, int S>
-static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, const void *d_u, const void *d_kin,
-                              int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
-                              double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl = nullptr,
-                              void *d_ubuf = nullptr, void *d_kbuf = nullptr, int64_t ckpt_step_elems = 0,
-                              void *d_sol = nullptr, int nlaunch = 1, unsigned long long loop_cond = 0ull) {
-    auto kern = cnf_rk_attempt_kernel<T, 6, 60, S>;
+// Small batches spread a trajectory slot over CNF_SMALL_LPT lanes: below this many slots the GPU has idle lanes to spare
+// and the launch is bound by the dependent chain of one thread, not by throughput.
+constexpr int CNF_SMALL_LPT = 4;
+template <typename T>
+static bool cnf_small_batch(int64_t ntraj) {
+    const int64_t nslots = (ntraj + Pack<T>::W - 1) / Pack<T>::W;
+    return nslots * CNF_SMALL_LPT <= (int64_t)sm_count() * 256;
+}
+
+template <typename T, int S, int LPT>
+static int launch_cnf_attempt_lpt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, const void *d_u, const void *d_kin,
+                                  int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
+                                  double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl,
+                                  void *d_ubuf, void *d_kbuf, int64_t ckpt_step_elems, void *d_sol, int nlaunch,
+                                  unsigned long long loop_cond) {
+    auto kern = cnf_rk_attempt_kernel<T, 6, 60, S, LPT>;
     const size_t smem = CNF_HOIST_Q ? sizeof(typename Pack<T>::V) * 60 * CNF_THREADS : 0;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
@@ -957,7 +998,7 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const int64_t nslots = (ntraj + Pack<T>::W - 1) / Pack<T>::W;  // fp32: two trajectories per thread (csrc/f32x2.cuh)
-    int64_t want = (nslots + CNF_THREADS - 1) / CNF_THREADS;
+    int64_t want = (nslots * LPT + CNF_THREADS - 1) / CNF_THREADS;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (cap > CNF_MAX_BLOCKS) cap = CNF_MAX_BLOCKS;
     int grid = (int)(want < cap ? want : cap);
@@ -973,12 +1014,28 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
 }
 
 template <typename T, int S>
-static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
-                              const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
-                              const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, const PeerComm &pc,
-                              cudaStream_t st) {
-    auto kern = cnf_rk_adj_kernel<T, 6, 60, S>;
-    const size_t smem = ((sizeof(CnfShared<T, 6, 60, S>) + 15) / 16) * 16 + sizeof(CnfTile<T, 6, 60>) * CNF_ADJ_WARPS;
+static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, const void *d_u, const void *d_kin,
+                              int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
+                              double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl = nullptr,
+                              void *d_ubuf = nullptr, void *d_kbuf = nullptr, int64_t ckpt_step_elems = 0,
+                              void *d_sol = nullptr, int nlaunch = 1, unsigned long long loop_cond = 0ull) {
+    if (cnf_small_batch<T>(ntraj))
+        return launch_cnf_attempt_lpt<T, S, CNF_SMALL_LPT>(c, tab, d_u, d_kin, ntraj, t, h, d_unew, d_kout, d_ckpt, atol, rtol,
+                                                           d_sumsq, d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems,
+                                                           d_sol, nlaunch, loop_cond);
+    return launch_cnf_attempt_lpt<T, S, 1>(c, tab, d_u, d_kin, ntraj, t, h, d_unew, d_kout, d_ckpt, atol, rtol, d_sumsq,
+                                           d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems, d_sol, nlaunch, loop_cond);
+}
+
+template <typename T, int S, int LPT>
+static int launch_cnf_adjoint_lpt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
+                                  const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
+                                  const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, const PeerComm &pc,
+                                  cudaStream_t st) {
+    auto kern = cnf_rk_adj_kernel<T, 6, 60, S, LPT>;
+    constexpr size_t tiles = sizeof(CnfTile<T, 6, 60, LPT>) * CNF_ADJ_WARPS;
+    constexpr size_t comb = sizeof(double) * CNF_ADJ_WARPS * CnfAdjShape<T, 6, 60, LPT>::NP;  // block combine reuses the tiles
+    const size_t smem = ((sizeof(CnfShared<T, 6, 60, S>) + 15) / 16) * 16 + (tiles > comb ? tiles : comb);
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         PNODE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -986,7 +1043,7 @@ static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *t
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const int64_t nslots = (ntraj + Pack<T>::W - 1) / Pack<T>::W;
-    int64_t want = (nslots + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
+    int64_t want = (nslots * LPT + CNF_ADJ_THREADS - 1) / CNF_ADJ_THREADS;
     int64_t cap = (int64_t)sm_count() * ctas_per_sm;
     if (cap > CNF_MAX_BLOCKS) cap = CNF_MAX_BLOCKS;
     int grid = (int)(want < cap ? want : cap);
@@ -997,6 +1054,18 @@ static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *t
                                               static_cast<CnfAdjWork *>(d_work), pc);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <typename T, int S>
+static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
+                              const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
+                              const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, const PeerComm &pc,
+                              cudaStream_t st) {
+    if (cnf_small_batch<T>(ntraj))
+        return launch_cnf_adjoint_lpt<T, S, CNF_SMALL_LPT>(c, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,
+                                                           d_lambda, d_mu, d_work, pc, st);
+    return launch_cnf_adjoint_lpt<T, S, 1>(c, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
+                                           pc, st);
 }
 
 }  // namespace pnode

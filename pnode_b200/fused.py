@@ -544,7 +544,7 @@ class FusedCnfRK:
             arr[i]["out_slot"] = slot
             arr[i]["in_slot"] = -1 if single else (0 if i == 0 else steps[i - 1][2])
         sched = torch.from_numpy(arr.view(np.uint8)).to(self.device)
-        desc = self._desc()
+        desc = state.get("desc_keep") or self._desc()  # the forward's descriptor: same weights, same probe
         per_step_bytes = self.s_eff * sp.dim * ntraj * gout.element_size()
         if self._adj_work is None:
             self._adj_work = torch.zeros(int(self.lib.pnode_cnf_rk_adjoint_work_bytes(C.byref(desc))), dtype=torch.uint8,
