@@ -276,7 +276,8 @@ def per_config_table(args, world, rank, comm):
             r = {"error": repr(e)[:300]}
         keep = {k: r[k] for k in ("workload", "dtype", "path", "n_gpus", "ms_per_pass", "traj_steps_per_s", "accepted_steps",
                                   "attempts", "algorithmic_tflops", "roofline", "cpu_baseline", "speedup_vs_cpu_port",
-                                  "rhs_evaluator", "error") if k in r}
+                                  "rhs_evaluator", "cuda_graph_replay_ms_per_pass", "cuda_graph_error", "error")
+                if k in r}
         out[name] = keep
     return out
 

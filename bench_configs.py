@@ -51,6 +51,21 @@ def _time_gpu(step, iters, world=1):
     return ts[len(ts) // 2]
 
 
+def _time_graph_replay(step, iters):
+    """The same pass captured once in a CUDA graph (torch.cuda.graph around the caller's step) and replayed: what is left
+    when the host side of the fixed-step paths (Python, ctypes, launch gaps) is taken out."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    return _time_gpu(g.replay, iters)
+
+
 def _time_cpu(step, reps=2):
     step()
     t0 = time.perf_counter()
@@ -127,6 +142,14 @@ def run_config(name, build, args, peaks, world=1, comm=None):
                                      "tf32 tcgen05 (3xTF32)", "executed_tops": tops,
                                      "peak_tops": ratio * peaks["bf16_tensor"], "frac": tops / (ratio * peaks["bf16_tensor"]),
                                      "peak_note": "%.1fx the measured bf16 peak (nominal type ratio)" % ratio}
+    if world == 1 and attempts == accepted and "cnf" not in str(ode.path) and not getattr(args, "no_graph", False):
+        # fixed-step solves launch without reading the device, so the whole pass replays from a CUDA graph
+        try:
+            out["cuda_graph_replay_ms_per_pass"] = _time_graph_replay(step, args.iters)
+        except Exception as exc:  # reported, never fatal for the bench line
+            out["cuda_graph_replay_ms_per_pass"] = None
+            out["cuda_graph_error"] = str(exc)[:200]
+            torch.cuda.synchronize()
     if spec.get("also_generic") and ode.path != "generic" and world == 1 and not getattr(args, "no_generic", False):
         Options.insert_args(["-pnode_fused", "0"])
         funcs_g = [to_dev(copy.deepcopy(f), dev) for f in spec["funcs"]]
