@@ -78,6 +78,23 @@ int64_t pnode_mdot_work_bytes(void);
 int pnode_mdot(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t n, void *d_work, int dtype,
                void *stream);
 
+/* Column-wise variants for the block Krylov solver behind linear_solver="hpddm" (pnode/hpddm_linearsolve.py:13-49: KSPHPDDM
+ * BGMRES on the state seen as a dense [n/batch x batch] matrix, one right-hand side per sample).  Vectors are
+ * [nseg][seglen], sample-major like the flattened batch.
+ *   pnode_mdot_seg:    d_out[j*nseg + s] = <vecs[j][s,:], w[s,:]> for j < nvec (<= 16), d_out[nvec*nseg + s] = <w[s,:], w[s,:]>
+ *                      (double accumulation, fixed order; the coefficients stay on the device)
+ *   pnode_lincomb_seg: out[s,:] = base_coef * base[s,:] + sum_j c_j[s] * vecs[j][s,:] with c_j[s] derived from the DEVICE array
+ *                      d_coef[j*nseg + s]: as is (COEF), negated (NEG: Gram-Schmidt with the dots just computed), or
+ *                      1/sqrt (RSQRT, 0 where the entry is 0: normalisation by a squared norm; a segment that broke down
+ *                      gets a zero basis vector and drops out).  base may be NULL; out may alias base. */
+#define PNODE_SEG_COEF 0
+#define PNODE_SEG_NEG 1
+#define PNODE_SEG_RSQRT 2
+int pnode_mdot_seg(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t nseg, int64_t seglen, int dtype,
+                   void *stream);
+int pnode_lincomb_seg(void *d_out, const void *d_base, double base_coef, const void *const *vecs, const double *d_coef,
+                      int nvec, int mode, int64_t nseg, int64_t seglen, int dtype, void *stream);
+
 /* ----------------------------------------------------------------------------------------------------------------
  * Fused path for tiny-state MLP right-hand sides  f(t,y) = W2 * tanh(W1 * phi(y) + b1) + b2,  phi = cube | identity
  * (the spiral model of examples-pnode/ode_demo_petsc.py:207-230: Linear(2,50)-Tanh-Linear(50,2) applied to y**3).

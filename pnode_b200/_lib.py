@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("PNODE_B200_LIB") or os.path.join(_HERE, "csrc", "libp
 
 F32, F64 = 0, 1
 MAX_TERMS, MAX_STAGES, MAX_SRCS = 16, 7, 32
+SEG_COEF, SEG_NEG, SEG_RSQRT = 0, 1, 2
 
 
 class RKTableau(C.Structure):
@@ -85,6 +86,8 @@ _SIGNATURES = {
     "pnode_multi_axpy": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i, _d, _i, _vp]),
     "pnode_mdot_work_bytes": (_i64, []),
     "pnode_mdot": (C.c_int, [_vp, C.POINTER(_vp), _i, _vp, _i64, _vp, _i, _vp]),
+    "pnode_mdot_seg": (C.c_int, [_vp, _vp, _i, _vp, _i64, _i64, _i, _vp]),
+    "pnode_lincomb_seg": (C.c_int, [_vp, _vp, _d, _vp, _vp, _i, _i, _i64, _i64, _i, _vp]),
     "pnode_mlp_rk_supported": (C.c_int, [_i, _i, _i, _i, _i]),
     "pnode_mlp_rk_forward": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RKTableau), _vp, _i64, _vp, _i, _vp, _vp, _vp]),
     "pnode_mlp_rk_adjoint_work_bytes": (_i64, [C.POINTER(MlpDesc)]),

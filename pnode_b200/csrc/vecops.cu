@@ -424,6 +424,87 @@ __global__ void __launch_bounds__(512) peak_fma_kernel(T *out, int iters, T a, T
 
 using namespace pnode;
 
+// ---- column-wise (one right-hand side per segment) variants for the block Krylov solver --------------------------------
+// The state is [nseg][seglen] (sample-major, as the flattened batch is); every segment has its own Krylov space, so the
+// Gram-Schmidt coefficients are per segment and stay on the device between the dot kernel and the update kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) mdot_seg_kernel(double *__restrict__ out, const MdotTable<T> tb,
+                                                       const T *__restrict__ w, int64_t nseg, int64_t seglen) {
+    const int64_t s = blockIdx.x;
+    const int64_t base = s * seglen;
+    double acc[MDOT_MAX + 1];
+#pragma unroll
+    for (int j = 0; j <= MDOT_MAX; ++j) acc[j] = 0.0;
+    for (int64_t i = threadIdx.x; i < seglen; i += blockDim.x) {
+        const double wi = (double)w[base + i];
+        acc[MDOT_MAX] = fma(wi, wi, acc[MDOT_MAX]);
+#pragma unroll
+        for (int j = 0; j < MDOT_MAX; ++j)
+            if (j < tb.n) acc[j] = fma((double)tb.v[j][base + i], wi, acc[j]);
+    }
+    __shared__ double wsum[8][MDOT_MAX + 1];
+#pragma unroll
+    for (int j = 0; j <= MDOT_MAX; ++j) {
+        const double v = warp_sum(acc[j]);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= MDOT_MAX) {
+        double v = 0.0;
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) v += wsum[wi][threadIdx.x];  // fixed order
+        const int j = threadIdx.x;
+        if (j < tb.n) out[(int64_t)j * nseg + s] = v;
+        if (j == MDOT_MAX) out[(int64_t)tb.n * nseg + s] = v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) lincomb_seg_kernel(T *__restrict__ out, const T *__restrict__ basev,
+                                                          const double base_coef, const MdotTable<T> tb,
+                                                          const double *__restrict__ coef, const int mode,
+                                                          const int64_t nseg, const int64_t seglen) {
+    const int64_t s = blockIdx.y;
+    __shared__ double c[MDOT_MAX];
+    if (threadIdx.x < tb.n) {
+        const double v = coef[(int64_t)threadIdx.x * nseg + s];
+        c[threadIdx.x] = mode == PNODE_SEG_COEF ? v : mode == PNODE_SEG_NEG ? -v : (v > 0.0 ? 1.0 / sqrt(v) : 0.0);
+    }
+    __syncthreads();
+    const int64_t base = s * seglen;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < seglen; i += (int64_t)gridDim.x * blockDim.x) {
+        double a = basev != nullptr ? base_coef * (double)basev[base + i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < MDOT_MAX; ++j)
+            if (j < tb.n) a = fma(c[j], (double)tb.v[j][base + i], a);
+        out[base + i] = (T)a;
+    }
+}
+
+template <typename T>
+static int mdot_seg_impl(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t nseg, int64_t seglen,
+                         cudaStream_t st) {
+    MdotTable<T> tb;
+    tb.n = nvec;
+    for (int j = 0; j < nvec; ++j) tb.v[j] = static_cast<const T *>(vecs[j]);
+    mdot_seg_kernel<T><<<(unsigned)nseg, 256, 0, st>>>(d_out, tb, static_cast<const T *>(d_w), nseg, seglen);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int lincomb_seg_impl(void *d_out, const void *d_base, double base_coef, const void *const *vecs,
+                            const double *d_coef, int nvec, int mode, int64_t nseg, int64_t seglen, cudaStream_t st) {
+    MdotTable<T> tb;
+    tb.n = nvec;
+    for (int j = 0; j < nvec; ++j) tb.v[j] = static_cast<const T *>(vecs[j]);
+    int gx = (int)((seglen + 255) / 256);
+    if (gx > 64) gx = 64;
+    lincomb_seg_kernel<T><<<dim3(gx, (unsigned)nseg), 256, 0, st>>>(static_cast<T *>(d_out), static_cast<const T *>(d_base),
+                                                                     base_coef, tb, d_coef, mode, nseg, seglen);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" {
 
 int pnode_abi_version(void) { return PNODE_ABI_VERSION; }
@@ -474,6 +555,7 @@ int pnode_multi_axpy(void *d_mu, const void *const *srcs, const int64_t *sizes, 
 
 int64_t pnode_mdot_work_bytes(void) { return (int64_t)sizeof(MdotWork); }
 
+
 int pnode_mdot(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t n, void *d_work, int dtype,
                void *stream) {
     PNODE_REQUIRE(nvec >= 0 && nvec <= MDOT_MAX, "pnode_mdot: nvec=%d out of range (max %d per call)", nvec, MDOT_MAX);
@@ -483,6 +565,31 @@ int pnode_mdot(double *d_out, const void *const *vecs, int nvec, const void *d_w
     if (dtype == PNODE_F64) return mdot_impl<double>(d_out, vecs, nvec, d_w, n, d_work, st);
     PNODE_REQUIRE(false, "pnode_mdot: unsupported dtype %d", dtype);
 }
+
+int pnode_mdot_seg(double *d_out, const void *const *vecs, int nvec, const void *d_w, int64_t nseg, int64_t seglen, int dtype,
+                   void *stream) {
+    PNODE_REQUIRE(nvec >= 0 && nvec <= MDOT_MAX, "pnode_mdot_seg: nvec=%d out of range (max %d per call)", nvec, MDOT_MAX);
+    PNODE_REQUIRE(d_out && d_w && nseg >= 1 && nseg <= 0x7fffffff && seglen >= 1, "pnode_mdot_seg: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PNODE_F32) return mdot_seg_impl<float>(d_out, vecs, nvec, d_w, nseg, seglen, st);
+    if (dtype == PNODE_F64) return mdot_seg_impl<double>(d_out, vecs, nvec, d_w, nseg, seglen, st);
+    PNODE_REQUIRE(false, "pnode_mdot_seg: unsupported dtype %d", dtype);
+}
+
+int pnode_lincomb_seg(void *d_out, const void *d_base, double base_coef, const void *const *vecs, const double *d_coef,
+                      int nvec, int mode, int64_t nseg, int64_t seglen, int dtype, void *stream) {
+    PNODE_REQUIRE(nvec >= 0 && nvec <= MDOT_MAX, "pnode_lincomb_seg: nvec=%d out of range (max %d per call)", nvec, MDOT_MAX);
+    PNODE_REQUIRE(d_out && (nvec == 0 || d_coef) && nseg >= 1 && nseg <= 65535 && seglen >= 1, "pnode_lincomb_seg: bad argument");
+    PNODE_REQUIRE(mode == PNODE_SEG_COEF || mode == PNODE_SEG_NEG || mode == PNODE_SEG_RSQRT, "pnode_lincomb_seg: bad mode %d",
+                  mode);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PNODE_F32)
+        return lincomb_seg_impl<float>(d_out, d_base, base_coef, vecs, d_coef, nvec, mode, nseg, seglen, st);
+    if (dtype == PNODE_F64)
+        return lincomb_seg_impl<double>(d_out, d_base, base_coef, vecs, d_coef, nvec, mode, nseg, seglen, st);
+    PNODE_REQUIRE(false, "pnode_lincomb_seg: unsupported dtype %d", dtype);
+}
+
 
 int pnode_peak_fma(int dtype, int iters, double *flops, float *ms) {
     const int threads = 512, blocks = sm_count() * 4;

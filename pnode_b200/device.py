@@ -108,6 +108,42 @@ class DeviceOps:
         self.launches += 1
 
     # [<v_j, w> for j] + [<w, w>] as a HOST list of floats (one device->host read): GMRES Gram-Schmidt coefficients
+    # column-wise variants (block Krylov solver): vectors are [nseg][n / nseg]; results / coefficients stay on the device
+    def mdot_seg(self, vecs, w, nseg):
+        """Returns a device tensor [len(vecs) + 1, nseg]: the per-segment dots with w, and ||w||^2 per segment last."""
+        n = w.numel()
+        out = torch.empty(len(vecs) + 1, nseg, dtype=torch.float64, device=w.device)
+        k = 0
+        while True:
+            chunk = vecs[k:k + 16]
+            vp = (C.c_void_p * max(len(chunk), 1))(*[v.data_ptr() for v in chunk])
+            tmp = out[k:] if k + len(chunk) == len(vecs) else torch.empty(len(chunk) + 1, nseg, dtype=torch.float64,
+                                                                           device=w.device)
+            _lib.check(self.lib.pnode_mdot_seg(tmp.data_ptr(), vp, len(chunk), w.data_ptr(), nseg, n // nseg, self.code,
+                                               _stream()))
+            self.launches += 1
+            if tmp.data_ptr() != out[k:].data_ptr():
+                out[k:k + len(chunk)].copy_(tmp[:len(chunk)])
+            k += 16
+            if k >= len(vecs):
+                return out
+
+    def lincomb_seg(self, out, base, base_coef, vecs, coef, mode, nseg):
+        """out[s,:] = base_coef base[s,:] + sum_j c_j[s] vecs[j][s,:], c from the device tensor coef [>= len(vecs), nseg]."""
+        n = out.numel()
+        k = 0
+        while True:
+            chunk = vecs[k:k + 16]
+            vp = (C.c_void_p * max(len(chunk), 1))(*[v.data_ptr() for v in chunk])
+            b, bc = (base, base_coef) if k == 0 else (out, 1.0)
+            _lib.check(self.lib.pnode_lincomb_seg(out.data_ptr(), None if b is None else b.data_ptr(), float(bc), vp,
+                                                  None if not chunk else coef[k:].data_ptr(), len(chunk), int(mode), nseg,
+                                                  n // nseg, self.code, _stream()))
+            self.launches += 1
+            k += 16
+            if k >= len(vecs):
+                return out
+
     def mdot(self, vecs, w):
         if self._mdot_work is None:
             self._mdot_work = torch.zeros(int(self.lib.pnode_mdot_work_bytes()), dtype=torch.uint8, device=self.device)

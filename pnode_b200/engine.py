@@ -212,13 +212,92 @@ def gmres(ops, apply_op, b, rtol=1e-5, atol=1e-50, restart=30, max_it=10000):
     return x, its, rnorm
 
 
+def block_gmres(ops, apply_op, b, nseg, rtol=1e-5, atol=1e-50, restart=30, max_it=10000):
+    """GMRES on `nseg` right-hand sides at once -- the reference's linear_solver="hpddm" (hpddm_linearsolve.py:13-49: KSPHPDDM,
+    type BGMRES, no preconditioner, the state seen as a dense [n/batch x batch] matrix and handed to KSPMatSolve).  Every
+    segment (sample) of the flattened state carries its own Krylov space and its own relative tolerance, as HPDDM's
+    per-column convergence test does; the segments advance in lockstep, so one iteration is ONE operator application on the
+    whole batch, one pnode_mdot_seg (all Gram-Schmidt coefficients of all segments, left on the device), one
+    pnode_lincomb_seg for the orthogonalisation, one more of each for the new norms and the normalisation, and one
+    (k+2) x nseg host read for the nseg small Hessenberg problems (Givens rotations, vectorised over the segments in numpy).
+    A segment that converges exactly (zero new basis vector) drops out by itself.  Zero initial guess (the reference
+    randomises the guess only when -ksp_initial_guess_nonzero is set).  Returns (x, iterations, max residual norm)."""
+    import numpy as np
+
+    n = b.numel()
+    x = torch.zeros_like(b)
+    bb = ops.mdot_seg([], b, nseg)
+    bnorm = np.sqrt(np.maximum(bb[0].cpu().numpy(), 0.0))
+    if not (bnorm > 0.0).any():
+        return x, 0, 0.0
+    tol = np.maximum(rtol * bnorm, atol)
+    r, rr_dev, rnorm, its = b, bb, bnorm.copy(), 0
+    while its < max_it:
+        V = [torch.empty_like(b)]
+        ops.lincomb_seg(V[0], None, 0.0, [r], rr_dev[-1:], 2, nseg)  # r / ||r|| per segment
+        H = np.zeros((nseg, restart + 1, restart))
+        cs, sn = np.zeros((nseg, restart)), np.zeros((nseg, restart))
+        g = np.zeros((nseg, restart + 1))
+        g[:, 0] = rnorm
+        k_used = 0
+        for k in range(restart):
+            w = apply_op(V[k])
+            hd = ops.mdot_seg(V[:k + 1], w, nseg)
+            wn = torch.empty_like(w)
+            ops.lincomb_seg(wn, w, 1.0, V[:k + 1], hd, 1, nseg)
+            nn = ops.mdot_seg([], wn, nseg)
+            host = torch.cat((hd[:k + 1], nn)).cpu().numpy()  # the one host read of the iteration
+            col = np.empty((nseg, k + 2))
+            col[:, :k + 1] = host[:k + 1].T
+            hk1 = np.sqrt(np.maximum(host[k + 1], 0.0))
+            col[:, k + 1] = hk1
+            for i in range(k):  # previous rotations on the new column
+                a, c = col[:, i].copy(), col[:, i + 1].copy()
+                col[:, i], col[:, i + 1] = cs[:, i] * a + sn[:, i] * c, -sn[:, i] * a + cs[:, i] * c
+            den = np.hypot(col[:, k], col[:, k + 1])
+            ok = den != 0.0
+            safe = np.where(ok, den, 1.0)
+            cs[:, k] = np.where(ok, col[:, k] / safe, 1.0)
+            sn[:, k] = np.where(ok, col[:, k + 1] / safe, 0.0)
+            col[:, k], col[:, k + 1] = den, 0.0
+            g[:, k + 1] = -sn[:, k] * g[:, k]
+            g[:, k] = cs[:, k] * g[:, k]
+            H[:, :k + 1, k] = col[:, :k + 1]
+            its += 1
+            k_used = k + 1
+            rnorm = np.abs(g[:, k + 1])
+            if ((rnorm <= tol) | (hk1 == 0.0)).all() or its >= max_it:
+                break
+            V.append(torch.empty_like(b))
+            ops.lincomb_seg(V[k + 1], None, 0.0, [wn], nn, 2, nseg)
+        y = np.zeros((nseg, k_used))
+        for i in range(k_used - 1, -1, -1):
+            acc = g[:, i] - (H[:, i, i + 1:k_used] * y[:, i + 1:]).sum(1)
+            d = H[:, i, i]
+            y[:, i] = np.where(d != 0.0, acc / np.where(d != 0.0, d, 1.0), 0.0)
+        yd = torch.from_numpy(np.ascontiguousarray(y.T)).to(b.device)
+        ops.lincomb_seg(x, x, 1.0, V[:k_used], yd, 0, nseg)
+        if (rnorm <= tol).all() or its >= max_it:
+            break
+        ax = apply_op(x)  # restart: true residuals
+        r = torch.empty_like(b)
+        ops.lincomb(r, b, 1.0, [ax], [-1.0])
+        rr_dev = ops.mdot_seg([], r, nseg)
+        rnorm = np.sqrt(np.maximum(rr_dev[0].cpu().numpy(), 0.0))
+        if (rnorm <= tol).all():
+            break
+    return x, its, float(rnorm.max())
+
+
 class ImplicitSolver:
     """Solve shift*(Y - Z) - f_I(t, Y) = 0 for one implicit stage, and the transposed linearised system for the adjoint.
 
     linear_solver == "torch" (torch_linearsolve.PCShell): f_I is sample-independent; the dense [N,N] Jacobian of sample 0
         (petsc_adjoint.py:479) is inverted once per shift and applied to all samples as ONE GEMM  X <- R @ inv(A)^T
         ("factor once per step size, inverse-apply as tensor-core GEMM").
-    otherwise ("petsc" / "hpddm"): Newton on the full state.  Small systems (n <= DENSE_SMALL, ROBER-like) assemble the
+    "hpddm" (hpddm_linearsolve.PCShell): Newton on the full state with the block solver `block_gmres` above, one right-hand
+        side per sample (batch_size segments).
+    otherwise ("petsc"): Newton on the full state.  Small systems (n <= DENSE_SMALL, ROBER-like) assemble the
         dense Jacobian and solve by LU; larger ones are matrix-free Newton-GMRES like the reference's IJacShell
         (petsc_adjoint.py:98-196): J x by forward-mode AD (torch.func.jvp; the reference uses the double-backward trick),
         J^T x by one reverse-mode pass, `gmres` above as the Krylov solver (-ksp_rtol, -ksp_max_it).
@@ -326,7 +405,7 @@ class ImplicitSolver:
             R = rhs.view(-1, N)
             # per sample x = A^{-1} r  <=>  X = R A^{-T};   transposed solve: X = R A^{-1}
             return (R @ (Ainv if transpose else Ainv.T)).reshape(-1)
-        if y.numel() > self.DENSE_SMALL:
+        if y.numel() > self.DENSE_SMALL or self.linear_solver == "hpddm":
             return self._krylov(t, y, shift, rhs.reshape(-1), transpose)
         A = self._dense_matrix(t, y, shift)
         return torch.linalg.solve(A.T if transpose else A, rhs.reshape(-1))
@@ -344,7 +423,10 @@ class ImplicitSolver:
             ops.lincomb(out, self._mass_times(v, transpose), shift, [jv], [-1.0])
             return out
 
-        x, its, _ = gmres(ops, op, rhs.contiguous(), rtol=self.ksp_rtol, max_it=self.ksp_max_it)
+        if self.linear_solver == "hpddm" and rhs.numel() % self.batch == 0:
+            x, its, _ = block_gmres(ops, op, rhs.contiguous(), self.batch, rtol=self.ksp_rtol, max_it=self.ksp_max_it)
+        else:
+            x, its, _ = gmres(ops, op, rhs.contiguous(), rtol=self.ksp_rtol, max_it=self.ksp_max_it)
         self.krylov_iterations += its
         return x
 

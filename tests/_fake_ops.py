@@ -50,6 +50,29 @@ def _mdot(self, vecs, w):
 FakeOps.mdot = _mdot
 
 
+def _mdot_seg(self, vecs, w, nseg):
+    self.launches += 1
+    wd = w.reshape(nseg, -1).double()
+    rows = [(v.reshape(nseg, -1).double() * wd).sum(1) for v in vecs] + [(wd * wd).sum(1)]
+    return torch.stack(rows)
+
+
+def _lincomb_seg(self, out, base, base_coef, vecs, coef, mode, nseg):
+    self.launches += 1
+    acc = torch.zeros(nseg, out.numel() // nseg, dtype=torch.float64) if base is None else \
+        base_coef * base.reshape(nseg, -1).double()
+    for j, v in enumerate(vecs):
+        c = coef[j].double()
+        c = c if mode == 0 else -c if mode == 1 else torch.where(c > 0, 1.0 / c.clamp_min(1e-300).sqrt(), torch.zeros_like(c))
+        acc = acc + c[:, None] * v.reshape(nseg, -1).double()
+    out.copy_(acc.reshape(out.shape).to(out.dtype))
+    return out
+
+
+FakeOps.mdot_seg = _mdot_seg
+FakeOps.lincomb_seg = _lincomb_seg
+
+
 def patch_cpu(monkeypatch):
     """Route ODEPetsc onto FakeOps and lift the CUDA-only gate -- for host-logic tests only."""
     import pnode_b200.petsc_adjoint as pa

@@ -129,6 +129,22 @@ def test_matrix_free_newton_gmres_on_gpu(method):
     _compare(p, o, 1e-7)
 
 
+@pytest.mark.parametrize("method", ["cn", "beuler"])
+def test_hpddm_block_krylov_on_gpu(method):
+    """linear_solver="hpddm" (pnode/hpddm_linearsolve.py:13-49, KSPHPDDM BGMRES on the batch as a block of right-hand sides):
+    engine.block_gmres on the pnode_mdot_seg / pnode_lincomb_seg kernels, one Krylov space per sample, vs the oracle's dense
+    Newton."""
+    from _problems import SpiralFunc, spiral_inputs
+
+    func = SpiralFunc(bias_std=0.1)
+    u0, _, gout = spiral_inputs(300)
+    t = torch.tensor([0.0, 0.1, 0.2], dtype=torch.float64)
+    o, p = _pair(["-ts_adapt_type", "none", "-ksp_rtol", "1e-12", "-pnode_fused", "0"], [func],
+                 dict(method=method, implicit_form=True, linear_solver="hpddm", batch_size=300), u0, t, gout[:3], 0.1)
+    assert p[3]._imp.krylov_iterations > 0
+    _compare(p, o, 1e-9)
+
+
 class _Pendulum(torch.nn.Module):
     """Index-1 pendulum DAE of examples-pnode/pendulum_DAE.py:108-117 with a trainable gravity constant."""
 

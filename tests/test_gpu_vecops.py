@@ -132,3 +132,36 @@ def test_mdot_matches_fp64_dots(dtype, n):
         for a, b in zip(vals, ref):
             assert abs(a - b) <= 1e-12 * scale
         assert ww == pytest.approx(float((w.double() ** 2).sum()), rel=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("nseg,seglen,nvec", [(1, 3, 2), (5, 1, 0), (37, 1000, 17), (256, 1024, 30), (3, 70001, 4)])
+def test_segmented_dots_and_updates(dtype, nseg, seglen, nvec):
+    """pnode_mdot_seg / pnode_lincomb_seg (block Krylov solver): per-segment dots in double, coefficients read from the
+    device in the three modes, more than 16 vectors per call, out aliasing base."""
+    ops = _ops(dtype)
+    g = torch.Generator().manual_seed(nseg + seglen)
+    vecs = [torch.randn(nseg * seglen, generator=g, dtype=torch.float64).to(dtype).cuda() for _ in range(nvec)]
+    w = torch.randn(nseg * seglen, generator=g, dtype=torch.float64).to(dtype).cuda()
+    got = ops.mdot_seg(vecs, w, nseg)
+    wd = w.double().view(nseg, seglen)
+    want = torch.stack([(v.double().view(nseg, seglen) * wd).sum(1) for v in vecs] + [(wd * wd).sum(1)])
+    assert got.shape == (nvec + 1, nseg)
+    scale = wd.norm(dim=1) * torch.stack([v.double().view(nseg, seglen).norm(dim=1) for v in vecs] + [wd.norm(dim=1)])
+    assert float(((got - want).abs() / scale).max()) < 1e-14
+    eps = 1e-15 if dtype == torch.float64 else 1e-6
+    # Gram-Schmidt update with the dots just computed (NEG), coefficients as is (COEF), normalisation (RSQRT)
+    out = torch.empty_like(w)
+    ops.lincomb_seg(out, w, 1.0, vecs, got, 1, nseg)
+    ref = wd - sum(want[j][:, None] * vecs[j].double().view(nseg, seglen) for j in range(nvec))
+    assert float((out.double().view(nseg, seglen) - ref).abs().max() / ref.abs().max()) < 50 * eps * max(nvec, 1)
+    acc = w.clone()
+    ops.lincomb_seg(acc, acc, 0.5, vecs, got, 0, nseg)
+    ref = 0.5 * wd + sum(want[j][:, None] * vecs[j].double().view(nseg, seglen) for j in range(nvec))
+    assert float((acc.double().view(nseg, seglen) - ref).abs().max() / ref.abs().max()) < 50 * eps * max(nvec, 1)
+    nn = got[-1:].clone()
+    nn[0, 0] = 0.0  # a segment that broke down: zero basis vector
+    ops.lincomb_seg(out, None, 0.0, [w], nn, 2, nseg)
+    ref = wd / wd.norm(dim=1, keepdim=True)
+    ref[0] = 0.0
+    assert float((out.double().view(nseg, seglen) - ref).abs().max()) < 10 * eps

@@ -499,3 +499,47 @@ def test_timeloop_follow_mirrors_report():
         for k in ("t", "h", "steps", "ctr", "cur_sol_index", "cur_sol_steps", "attempts", "last_h"):
             assert getattr(a, k) == getattr(b, k), k
         b.check_complete()
+
+
+def test_block_gmres_solves_every_column_to_its_own_tolerance():
+    """engine.block_gmres (linear_solver="hpddm"): one right-hand side per segment, per-segment Krylov spaces advanced in
+    lockstep; against a dense solve.  Restart shorter than the iteration count, one zero right-hand side, one segment whose
+    operator is the identity (converges in one iteration and drops out while the others go on)."""
+    from _fake_ops import FakeOps
+    from pnode_b200.engine import block_gmres
+
+    nseg, n = 7, 12
+    g = torch.Generator().manual_seed(11)
+    A = torch.eye(n, dtype=torch.float64).repeat(nseg, 1, 1) + 0.4 * torch.randn(nseg, n, n, generator=g,
+                                                                                 dtype=torch.float64) / n ** 0.5
+    A[3] = torch.eye(n, dtype=torch.float64)
+    B = torch.randn(nseg, n, generator=g, dtype=torch.float64)
+    B[5] = 0.0
+    B[2] *= 1e6  # per-column relative tolerance: a large column must not hide the small ones
+    ops = FakeOps()
+    calls = []
+
+    def op(v):
+        calls.append(1)
+        return torch.einsum("sij,sj->si", A, v.view(nseg, n)).reshape(-1)
+
+    x, its, res = block_gmres(ops, op, B.reshape(-1).clone(), nseg, rtol=1e-12, restart=5, max_it=200)
+    want = torch.linalg.solve(A, B.unsqueeze(-1)).squeeze(-1)
+    for s in range(nseg):
+        err = (x.view(nseg, n)[s] - want[s]).norm() / max(float(want[s].norm()), 1e-300)
+        assert err < 1e-10, (s, float(err))
+    assert torch.equal(x.view(nseg, n)[5], torch.zeros(n, dtype=torch.float64))
+    assert 12 <= its <= 40 and len(calls) >= its  # n = 12 unknowns per column; restarts add true-residual applications
+
+
+@pytest.mark.parametrize("method", ["cn", "beuler"])
+def test_hpddm_block_solver_matches_dense_oracle(monkeypatch, method):
+    """linear_solver="hpddm" (pnode/hpddm_linearsolve.py): Newton with the block Krylov solver, batch_size right-hand sides."""
+    func = SpiralFunc(bias_std=0.1)
+    u0, _, gout = spiral_inputs(40)
+    t = torch.tensor([0.0, 0.1, 0.2], dtype=torch.float64)
+    argv = ["-ts_adapt_type", "none", "-ksp_rtol", "1e-12"]
+    o, p = _both(monkeypatch, argv, dict(method=method, implicit_form=True, linear_solver="hpddm", batch_size=40), [func],
+                 u0, t, gout[:3], 0.1)
+    assert p[3]._imp.krylov_iterations > 0
+    _assert_close(p, o, 1e-8)
