@@ -46,6 +46,7 @@
 #endif
 
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace pnode {
 
@@ -60,6 +61,63 @@ template <typename T>
 struct V4 {
     T v[4];
 };
+
+// acc[0..4) += w * o[0..4): four pixels of one output channel.  fp32: two packed FFMA2 (csrc/f32x2.cuh; the scalar weight is
+// broadcast by the instruction, the pixel pairs are adjacent registers of the 128-bit load they came from) -- half the issue
+// slots of four FFMA, identical rounding.
+#ifndef PNODE_CONV_FFMA2
+#define PNODE_CONV_FFMA2 1
+#endif
+// acc += sum_e a[e] b[e] over four pixels (weight-gradient tiles).  fp32: the accumulator is a packed pair holding the sums of
+// the even and the odd pixels (two FFMA2 instead of four dependent FFMA), added together once at the end.
+template <typename T>
+struct DotAcc {
+    typedef T type;
+};
+#ifndef PNODE_WGRAD_FFMA2
+#define PNODE_WGRAD_FFMA2 0  // measured on block 1 / 2: 1.59 -> 1.62 / 1.30 -> 1.33 ms per replayed pass, so off
+#endif
+#if PNODE_WGRAD_FFMA2
+template <>
+struct DotAcc<float> {
+    typedef F2 type;
+};
+__device__ __forceinline__ void dot4_acc(const V4<float> &a, const V4<float> &b, F2 &acc) {
+    acc = fma(pk(a.v[0], a.v[1]), pk(b.v[0], b.v[1]), acc);
+    acc = fma(pk(a.v[2], a.v[3]), pk(b.v[2], b.v[3]), acc);
+}
+__device__ __forceinline__ float dot_total(F2 acc) { return lo(acc) + hi(acc); }
+__device__ __forceinline__ void dot_zero(F2 &acc) { acc = splat(0.0f); }
+#endif
+template <typename T>
+__device__ __forceinline__ void dot4_acc(const V4<T> &a, const V4<T> &b, T &acc) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc = fma(a.v[e], b.v[e], acc);
+}
+template <typename T>
+__device__ __forceinline__ T dot_total(T acc) {
+    return acc;
+}
+template <typename T>
+__device__ __forceinline__ void dot_zero(T &acc) {
+    acc = T(0);
+}
+
+__device__ __forceinline__ void fma_row4(double w, const V4<double> &o, double (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = fma(w, o.v[j], acc[j]);
+}
+__device__ __forceinline__ void fma_row4(float w, const V4<float> &o, float (&acc)[4]) {
+#if PNODE_CONV_FFMA2
+    const F2 a = fma(w, pk(o.v[0], o.v[1]), pk(acc[0], acc[1]));
+    const F2 b = fma(w, pk(o.v[2], o.v[3]), pk(acc[2], acc[3]));
+    unpk(a, acc[0], acc[1]);
+    unpk(b, acc[2], acc[3]);
+#else
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, o.v[j], acc[j]);
+#endif
+}
 
 // Programmatic dependent launch: every kernel of this file lets its successor start early (its prologue -- barrier init, weight
 // staging -- overlaps this kernel's tail) and waits for its predecessor's memory before touching anything that depends on it.
@@ -582,9 +640,7 @@ __global__ void __launch_bounds__(CB_PGX *CB_MAXCG) conv_kernel(const ConvArgs<T
                     for (int r4 = 0; r4 < RC; r4 += 4) {
                         const V4<T> wv = lds4<T>(wr + r4);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[r4 + r][j] = fma(wv.v[r], o[oi].v[j], acc[r4 + r][j]);
+                        for (int r = 0; r < 4; ++r) fma_row4(wv.v[r], o[oi], acc[r4 + r]);
                     }
                 }
             }
@@ -764,9 +820,7 @@ __global__ void __launch_bounds__(CP_CONSUMERS + 32) convp_kernel(const ConvArgs
                     for (int r4 = 0; r4 < RC; r4 += 4) {
                         const V4<T> wv = lds4<T>(wr + r4);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[r4 + r][j] = fma(wv.v[r], o[oi].v[j], acc[r4 + r][j]);
+                        for (int r = 0; r < 4; ++r) fma_row4(wv.v[r], o[oi], acc[r4 + r]);
                     }
                 }
             }
@@ -928,11 +982,11 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
     __syncthreads();
     SD dsrc(a.g, a.z, tdz, WG_CO);
     SY ysrc(a.yin, nullptr, ty, WG_CIT);
-    T acc[TM][TN];
+    typename DotAcc<T>::type acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+        for (int j = 0; j < TN; ++j) dot_zero(acc[i][j]);
     // this warp's rows of a chunk: NDZ dz rows (channels co0 + warp + 8 i) and NY source channels (ci_lo + warp + 8 u), clamped
     int rdz[NDZ], rci[NY];
 #pragma unroll
@@ -988,9 +1042,7 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[i][j] = fma(av[i].v[e], bv[j].v[e], acc[i][j]);
+                for (int j = 0; j < TN; ++j) dot4_acc(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -999,7 +1051,7 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const WgradArgs<
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) red[warp * WG_TILE + (cgp + 4 * i) * WG_CIT + cg8 + 8 * j] = acc[i][j];
+        for (int j = 0; j < TN; ++j) red[warp * WG_TILE + (cgp + 4 * i) * WG_CIT + cg8 + 8 * j] = dot_total(acc[i][j]);
     __syncthreads();
     for (int idx = threadIdx.x; idx < WG_TILE; idx += WG_THREADS) {
         T t = T(0);
