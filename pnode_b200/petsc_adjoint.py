@@ -51,6 +51,12 @@ def _check_device(tensor, what):
     if not tensor.is_cuda:
         raise Error(-11, "%s must be a CUDA tensor (got device %s); pnode_b200 has no CPU fallback" %
                     (what, tensor.device))
+    cur = torch.cuda.current_device()
+    if tensor.device.index is not None and tensor.device.index != cur:
+        # the kernels launch on the CURRENT device's current stream (device._stream): a tensor of another GPU would be read
+        # unordered with respect to the torch ops that produced it, or not at all without peer access
+        raise Error(-11, "%s lives on cuda:%d but the current CUDA device is cuda:%d; call torch.cuda.set_device(%d) (one "
+                         "process per GPU) before using ODEPetsc" % (what, tensor.device.index, cur, tensor.device.index))
 
 
 class ODEPetsc(object):

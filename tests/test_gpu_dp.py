@@ -21,3 +21,17 @@ def test_batch_sharded_matches_single_gpu(peer):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "dp_check ok" in p.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_state_on_another_gpu_than_the_current_one_is_refused():
+    """The kernels launch on the current device's stream: a state tensor of another GPU must fail loudly, not race."""
+    from pnode import petsc_adjoint
+    from pnode_b200.errors import Error
+    from _problems import SpiralFunc, spiral_inputs
+
+    torch.cuda.set_device(0)
+    u0 = spiral_inputs(8)[0].to("cuda:1")
+    ode = petsc_adjoint.ODEPetsc()
+    with pytest.raises(Error, match="current CUDA device"):
+        ode.setupTS(u0, SpiralFunc().to("cuda:1"), step_size=0.025, method="rk4", enable_adjoint=True)
