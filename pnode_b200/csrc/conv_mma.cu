@@ -123,6 +123,8 @@ __device__ __forceinline__ float tf32_hi(float x) {
 // ---- layout changes between the caller's NCHW state and the pixel-major matrices ------------------------------------
 // dst[n][hw][c] = src[n][c][hw]   (grid: hw tiles, c tiles, n)
 __global__ void nchw_to_nhwc_kernel(const float *src, float *dst, int C, int HW) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     __shared__ float t[32][33];
     const int n = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float *s = src + (long long)n * C * HW;
@@ -141,6 +143,8 @@ __global__ void nchw_to_nhwc_kernel(const float *src, float *dst, int C, int HW)
 // Output pass of the block: k[n][c][hw] = relu(a[c] z[n][hw][c] + b[c]);  out = base_coef * base + k_coef * k.
 __global__ void act_out_kernel(const float *z, const float *a, const float *b, int C, int HW, float *kout, float *out,
                                const float *base, float base_coef, float k_coef) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     __shared__ float t[32][33];
     const int n = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const long long img = (long long)n * C * HW;
@@ -167,6 +171,8 @@ __global__ void act_out_kernel(const float *z, const float *a, const float *b, i
 // grid: (P/128 tiles, c tiles); a tile never straddles... images may: HW is a divisor or a multiple of 32.
 __global__ void top_grad_kernel(const float *w, const float *z, const float *a, const float *b, const float *qa,
                                 const float *qb, int C, int HW, long long P, float *g, double *stats) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     __shared__ float t[32][33];
     __shared__ double s1[8][33], s2[8][33];
     const int c0 = blockIdx.y * 32;
@@ -236,6 +242,8 @@ __device__ __forceinline__ long long tap_source(const Gather &G, long long p, in
 
 // A[s][p][t*C + c] (row-major operand of the products over channels), 4 channels per thread.
 __global__ void gather_rows_kernel(Gather G, float *out, long long pitch_f, long long slice_f) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int c4n = G.C / 4;
     const long long total = G.P * G.taps * c4n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -264,6 +272,8 @@ __global__ void gather_rows_kernel(Gather G, float *out, long long pitch_f, long
 
 // AT[s][t*C + c][p] (operand of the products over pixels): 32 pixels x 32 channels per block and tap.
 __global__ void gather_cols_kernel(Gather G, float *out, long long pitch_f, long long slice_f) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     __shared__ float th[32][33], tl[32][33];
     const int t = blockIdx.z, c0 = blockIdx.y * 32;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -295,6 +305,8 @@ __global__ void gather_cols_kernel(Gather G, float *out, long long pitch_f, long
 // wf[s][co][t*cin + ci] = W[co][ci][t]  (forward / weight-gradient layout);  wd[s][ci][t*cout + co] = W[co][ci][t] (data gradient)
 __global__ void weight_operands_kernel(const float *w, int cin, int cout, int taps, float *wf, long long wf_pitch,
                                        long long wf_slice, float *wd, long long wd_pitch, long long wd_slice) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int total = cout * cin * taps;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int t = idx % taps, ci = (idx / taps) % cin, co = idx / (taps * cin);
@@ -347,6 +359,8 @@ struct BnFwd {
 };
 
 __global__ void bn_forward_finalize_kernel(BnFwd B, PeerComm pc) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int C = B.C;
     reduce_partials<16>(B.partials, B.mtiles, C, B.tot, B.scratch);
     const double *tot = B.tot;
@@ -377,6 +391,8 @@ __global__ void bn_forward_finalize_kernel(BnFwd B, PeerComm pc) {
 // still advance the BatchNorm buffers once: do that from the stored statistics.
 __global__ void bn_advance_running_kernel(const double *mean, const double *invstd, int C, double count, double eps,
                                           double momentum, float *running_mean, float *running_var, long long *nbt) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         if (!running_mean) break;
         const double var = fmax(1.0 / (invstd[c] * invstd[c]) - eps, 0.0);
@@ -401,6 +417,8 @@ struct BnBwd {
 };
 
 __global__ void bn_backward_finalize_kernel(BnBwd B, PeerComm pc) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int C = B.C;
     reduce_partials<16>(B.partials, B.mtiles, C, B.tot, B.scratch);
     const double *tot = B.tot;
@@ -434,6 +452,8 @@ __global__ void bn_backward_finalize_kernel(BnBwd B, PeerComm pc) {
 // slices, combined in lane order (fixed order => bit-reproducible)
 __global__ void wgrad_reduce_kernel(const float *part, int splits, int cout, int cin, int taps, float *gw, double coef,
                                     int accumulate) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int kc = cin * taps, total = cout * kc;
     const int sub = threadIdx.x & 7;
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -464,7 +484,7 @@ static int launch_gather_rows(const Gather &G, uint8_t *A, int kc, cudaStream_t 
     const long long pitch_f = umma::pitch_bytes(KIND, kc) / 4, slice_f = G.P * pitch_f;
     const long long total = G.P * G.taps * (G.C / 4);
     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    gather_rows_kernel<<<grid, 256, 0, st>>>(G, reinterpret_cast<float *>(A), pitch_f, slice_f);
+    PNODE_CUDA_OK(pdl::launch_pdl(gather_rows_kernel, dim3(grid), dim3(256), 0, st, G, reinterpret_cast<float *>(A), pitch_f, slice_f));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -472,7 +492,7 @@ static int launch_gather_rows(const Gather &G, uint8_t *A, int kc, cudaStream_t 
 static int launch_gather_cols(const Gather &G, uint8_t *AT, cudaStream_t st) {
     const long long pitch_f = umma::pitch_bytes(KIND, (int)G.P) / 4, slice_f = (long long)G.taps * G.C * pitch_f;
     dim3 grid((unsigned)((G.P + 31) / 32), (G.C + 31) / 32, G.taps);
-    gather_cols_kernel<<<grid, dim3(32, 8), 0, st>>>(G, reinterpret_cast<float *>(AT), pitch_f, slice_f);
+    PNODE_CUDA_OK(pdl::launch_pdl(gather_cols_kernel, dim3(grid), dim3(32, 8), 0, st, G, reinterpret_cast<float *>(AT), pitch_f, slice_f));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -500,7 +520,7 @@ static int forward_impl(const pnode_convblock_desc *d, const Plan &p, const uint
                         uint8_t *work, unsigned long long epoch, cudaStream_t st) {
     const int HW = p.H * p.W, C0 = p.g[0].cin;
     float *xin = reinterpret_cast<float *>(work + p.xin);
-    nchw_to_nhwc_kernel<<<dim3((HW + 31) / 32, (C0 + 31) / 32, p.N), dim3(32, 8), 0, st>>>(x, xin, C0, HW);
+    PNODE_CUDA_OK(pdl::launch_pdl(nchw_to_nhwc_kernel, dim3(dim3((HW + 31) / 32, (C0 + 31) / 32, p.N)), dim3(32, 8), 0, st, x, xin, C0, HW));
     for (int k = 0; k < p.L; ++k) {
         const Geom &g = p.g[k];
         const pnode_conv_layer &l = d->layer[k];
@@ -527,7 +547,7 @@ static int forward_impl(const pnode_convblock_desc *d, const Plan &p, const uint
         B.a = cur.a, B.b = cur.b, B.qa = cur.qa, B.qb = cur.qb;
         B.tot = reinterpret_cast<double *>(work + p.tot), B.tot_global = B.tot + 2 * p.cmax, B.update_running = 1;
         B.scratch = B.tot + 4 * p.cmax;
-        bn_forward_finalize_kernel<<<1, 1024, 0, st>>>(B, peer_of(d, epoch + k));
+        PNODE_CUDA_OK(pdl::launch_pdl(bn_forward_finalize_kernel, dim3(1), dim3(1024), 0, st, B, peer_of(d, epoch + k)));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -568,9 +588,8 @@ int pnode_convmma_prepare(const pnode_convblock_desc *desc, void *d_wbuf, void *
         const cmma::Geom &g = p.g[k];
         const int kc = g.taps * g.cin, kd = g.taps * g.cout;
         const long long fp = umma::pitch_bytes(cmma::KIND, kc) / 4, dp = umma::pitch_bytes(cmma::KIND, kd) / 4;
-        cmma::weight_operands_kernel<<<(g.cout * kc + 255) / 256, 256, 0, st>>>(
-            (const float *)desc->layer[k].d_weight, g.cin, g.cout, g.taps, (float *)(W + p.wf[k]), fp, (long long)g.cout * fp,
-            (float *)(W + p.wd[k]), dp, (long long)g.cin * dp);
+        PNODE_CUDA_OK(pdl::launch_pdl(cmma::weight_operands_kernel, dim3((g.cout * kc + 255) / 256), dim3(256), 0, st, (const float *)desc->layer[k].d_weight, g.cin, g.cout, g.taps, (float *)(W + p.wf[k]), fp, (long long)g.cout * fp,
+            (float *)(W + p.wd[k]), dp, (long long)g.cin * dp));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -587,9 +606,8 @@ int pnode_convmma_forward(const pnode_convblock_desc *desc, const void *d_wbuf, 
     if (int rc = cmma::forward_impl(desc, p, (const uint8_t *)d_wbuf, (const float *)d_x, act, work, desc->epoch, st)) return rc;
     const int HW = p.H * p.W, CL = p.g[p.L - 1].cout;
     const cmma::Bnp last = cmma::bnp_of(p, act, p.L - 1);
-    cmma::act_out_kernel<<<dim3((HW + 31) / 32, (CL + 31) / 32, p.N), dim3(32, 8), 0, st>>>(
-        (const float *)(act + p.z[p.L - 1]), last.a, last.b, CL, HW, (float *)d_k, (float *)d_out, (const float *)d_base,
-        (float)base_coef, (float)k_coef);
+    PNODE_CUDA_OK(pdl::launch_pdl(cmma::act_out_kernel, dim3(dim3((HW + 31) / 32, (CL + 31) / 32, p.N)), dim3(32, 8), 0, st, (const float *)(act + p.z[p.L - 1]), last.a, last.b, CL, HW, (float *)d_k, (float *)d_out, (const float *)d_base,
+        (float)base_coef, (float)k_coef));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -614,11 +632,11 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
         for (int k = 0; k < p.L; ++k) {
             const pnode_conv_layer &l = desc->layer[k];
             const cmma::Bnp b = cmma::bnp_of(p, act, k);
-            cmma::bn_advance_running_kernel<<<1, 256, 0, st>>>(b.mean, b.invstd, p.g[k].cout, (double)p.Pg, l.eps, l.momentum,
+            PNODE_CUDA_OK(pdl::launch_pdl(cmma::bn_advance_running_kernel, dim3(1), dim3(256), 0, st, b.mean, b.invstd, p.g[k].cout, (double)p.Pg, l.eps, l.momentum,
                                                                (float *)l.d_running_mean, (float *)l.d_running_var,
-                                                               (long long *)l.d_num_batches_tracked);
+                                                               (long long *)l.d_num_batches_tracked));
         }
-        cmma::nchw_to_nhwc_kernel<<<dim3((HW + 31) / 32, (C0 + 31) / 32, p.N), dim3(32, 8), 0, st>>>((const float *)d_x, xin, C0, HW);
+        PNODE_CUDA_OK(pdl::launch_pdl(cmma::nchw_to_nhwc_kernel, dim3(dim3((HW + 31) / 32, (C0 + 31) / 32, p.N)), dim3(32, 8), 0, st, (const float *)d_x, xin, C0, HW));
     }
     double *stats = reinterpret_cast<double *>(work + p.stats);
     double *tot = reinterpret_cast<double *>(work + p.tot);
@@ -629,8 +647,7 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
     {
         const int k = p.L - 1, C = p.g[k].cout;
         const cmma::Bnp b = cmma::bnp_of(p, act, k);
-        cmma::top_grad_kernel<<<dim3(p.mtiles, (C + 31) / 32), dim3(32, 8), 0, st>>>(
-            (const float *)d_w, (const float *)(act + p.z[k]), b.a, b.b, b.qa, b.qb, C, HW, p.P, gbuf[cur], stats);
+        PNODE_CUDA_OK(pdl::launch_pdl(cmma::top_grad_kernel, dim3(dim3(p.mtiles, (C + 31) / 32)), dim3(32, 8), 0, st, (const float *)d_w, (const float *)(act + p.z[k]), b.a, b.b, b.qa, b.qb, C, HW, p.P, gbuf[cur], stats));
     }
     for (int k = p.L - 1; k >= 0; --k) {
         const cmma::Geom &g = p.g[k];
@@ -643,7 +660,7 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
         if (grads) B.ggamma = grads + p.goff_gamma[k], B.gbeta = grads + p.goff_beta[k], B.gbias = grads + p.goff_b[k];
         B.coef = coef, B.accumulate = accumulate, B.contribute = (p.world == 1 || p.rank == 0) ? 1 : 0;
         B.tot = tot, B.tot_global = tot + 2 * p.cmax, B.scratch = tot + 4 * p.cmax;
-        cmma::bn_backward_finalize_kernel<<<1, 1024, 0, st>>>(B, cmma::peer_of(desc, epoch + (p.L - 1 - k)));
+        PNODE_CUDA_OK(pdl::launch_pdl(cmma::bn_backward_finalize_kernel, dim3(1), dim3(1024), 0, st, B, cmma::peer_of(desc, epoch + (p.L - 1 - k))));
         const int kc = g.taps * g.cin, kd = g.taps * g.cout;
         // dz_k = ca g_k + cb z_k + cc, formed inside the gathers
         cmma::Gather D = cmma::base_gather(p, g, g.cout, -1);
@@ -665,9 +682,9 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
             const int nsplit = cmma::wgrad_slices(g, p.P, &ep.kb_per_split);
             ep.split_stride = (long long)g.cout * kc;
             if (int rc = umma::gemm_ex(cmma::KIND, work + p.dzT, work + p.AT, g.cout, kc, (int)p.P, ep, st)) return rc;
-            cmma::wgrad_reduce_kernel<<<(g.cout * kc * 8 + 255) / 256, 256, 0, st>>>((const float *)(work + p.part), nsplit, g.cout,
+            PNODE_CUDA_OK(pdl::launch_pdl(cmma::wgrad_reduce_kernel, dim3((g.cout * kc * 8 + 255) / 256), dim3(256), 0, st, (const float *)(work + p.part), nsplit, g.cout,
                                                                                g.cin, g.taps, grads + p.goff_w[k], coef,
-                                                                               accumulate);
+                                                                               accumulate));
         }
         if (k > 0 || d_vu) {
             if (int rc = cmma::launch_gather_rows(D, work + p.A, kd, st)) return rc;
@@ -686,8 +703,7 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
         }
     }
     if (d_vu)  // pixel-major -> the caller's NCHW: the transpose kernel with the roles of C and HW exchanged
-        cmma::nchw_to_nhwc_kernel<<<dim3((C0 + 31) / 32, (HW + 31) / 32, p.N), dim3(32, 8), 0, st>>>(
-            (const float *)(work + p.win), (float *)d_vu, HW, C0);
+        PNODE_CUDA_OK(pdl::launch_pdl(cmma::nchw_to_nhwc_kernel, dim3(dim3((C0 + 31) / 32, (HW + 31) / 32, p.N)), dim3(32, 8), 0, st, (const float *)(work + p.win), (float *)d_vu, HW, C0));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }

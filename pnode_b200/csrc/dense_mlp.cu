@@ -93,6 +93,8 @@ struct Taps {
 // out[r][i] = sum_d coef[d] x[r][(i -/+ off[d]) mod n]   (J[i][j] = c[(i - j) mod n];  transpose: c[(j - i) mod n])
 template <typename T>
 __global__ void circ_apply_kernel(const T *x, T *out, int rows, int n, Taps taps, int transpose) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const long long total = (long long)rows * n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -113,6 +115,8 @@ __global__ void circ_apply_kernel(const T *x, T *out, int rows, int n, Taps taps
 // Spectrum of A = shift*I - J (circulant, first column a = shift*e0 - c):  lam_k = sum_j a_j w^{jk},  w = exp(-2 pi i / n);
 // stores 1 / lam_k.
 __global__ void circ_spectrum_kernel(const double *col, int n, double shift, double2 *inv_lam) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     double re = 0.0, im = 0.0, cre = 0.0, cim = 0.0;  // Kahan-compensated sums
@@ -133,6 +137,8 @@ __global__ void circ_spectrum_kernel(const double *col, int n, double shift, dou
 
 // First column of A^-1:  g_m = (1/n) sum_k (1/lam_k) w^{-mk}  (real for a real circulant).
 __global__ void circ_inverse_column_kernel(const double2 *inv_lam, int n, double *g) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n) return;
     double acc = 0.0, comp = 0.0;
@@ -149,6 +155,8 @@ __global__ void circ_inverse_column_kernel(const double2 *inv_lam, int n, double
 
 template <typename T>
 __global__ void circ_expand_kernel(const double *g, int n, T *dense) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const long long total = (long long)n * n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -290,9 +298,9 @@ int pnode_circulant_apply(const void *d_x, void *d_out, int rows, int n, const i
     const int grid = (int)((total + 255) / 256 < 8 * sm_count() ? (total + 255) / 256 : 8 * sm_count());
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PNODE_F64)
-        dmlp::circ_apply_kernel<double><<<grid, 256, 0, st>>>((const double *)d_x, (double *)d_out, rows, n, taps, transpose);
+        PNODE_CUDA_OK(pdl::launch_pdl(dmlp::circ_apply_kernel<double>, dim3(grid), dim3(256), 0, st, (const double *)d_x, (double *)d_out, rows, n, taps, transpose));
     else if (dtype == PNODE_F32)
-        dmlp::circ_apply_kernel<float><<<grid, 256, 0, st>>>((const float *)d_x, (float *)d_out, rows, n, taps, transpose);
+        PNODE_CUDA_OK(pdl::launch_pdl(dmlp::circ_apply_kernel<float>, dim3(grid), dim3(256), 0, st, (const float *)d_x, (float *)d_out, rows, n, taps, transpose));
     else
         PNODE_REQUIRE(false, "pnode_circulant_apply: dtype %d", dtype);
     PNODE_CUDA_OK(cudaGetLastError());
@@ -306,14 +314,14 @@ int pnode_circulant_inverse(const double *d_col, int n, double shift, void *d_in
     cudaStream_t st = (cudaStream_t)stream;
     double2 *inv_lam = (double2 *)d_work;
     double *g = (double *)((uint8_t *)d_work + (size_t)n * 16);
-    dmlp::circ_spectrum_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_col, n, shift, inv_lam);
-    dmlp::circ_inverse_column_kernel<<<(n + 127) / 128, 128, 0, st>>>(inv_lam, n, g);
+    PNODE_CUDA_OK(pdl::launch_pdl(dmlp::circ_spectrum_kernel, dim3((n + 127) / 128), dim3(128), 0, st, d_col, n, shift, inv_lam));
+    PNODE_CUDA_OK(pdl::launch_pdl(dmlp::circ_inverse_column_kernel, dim3((n + 127) / 128), dim3(128), 0, st, inv_lam, n, g));
     const long long total = (long long)n * n;
     const int grid = (int)((total + 255) / 256 < 8 * sm_count() ? (total + 255) / 256 : 8 * sm_count());
     if (dtype == PNODE_F64)
-        dmlp::circ_expand_kernel<double><<<grid, 256, 0, st>>>(g, n, (double *)d_inverse);
+        PNODE_CUDA_OK(pdl::launch_pdl(dmlp::circ_expand_kernel<double>, dim3(grid), dim3(256), 0, st, g, n, (double *)d_inverse));
     else if (dtype == PNODE_F32)
-        dmlp::circ_expand_kernel<float><<<grid, 256, 0, st>>>(g, n, (float *)d_inverse);
+        PNODE_CUDA_OK(pdl::launch_pdl(dmlp::circ_expand_kernel<float>, dim3(grid), dim3(256), 0, st, g, n, (float *)d_inverse));
     else
         PNODE_REQUIRE(false, "pnode_circulant_inverse: dtype %d", dtype);
     PNODE_CUDA_OK(cudaGetLastError());

@@ -1,6 +1,7 @@
 // Host-side interface of csrc/umma_gemm.cu for the other translation units (sliced operands + tensor-core products).
 #pragma once
 #include "common.cuh"
+#include "pdl.cuh"
 
 namespace pnode {
 namespace umma {
@@ -49,6 +50,10 @@ int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void 
 // ceil(rows / 32) * cols doubles, needed when colsum != NULL (colsum += coef * column sums, fixed summation order).
 int slice_both(int kind, const void *x, long long ldx, int rows, int cols, void *out_r, int *exp_r, void *out_c, int *exp_c,
                void *colsum, double coef, double *colpart, cudaStream_t stream);
+
+using pdl::launch_pdl;
+using pdl::pdl_launch_dependents;
+using pdl::pdl_wait;
 
 }  // namespace umma
 }  // namespace pnode

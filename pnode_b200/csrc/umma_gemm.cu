@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                               : (C::NACC * BN <= 256) ? 256 : 512;
     static_assert(C::NACC * BN <= 512, "accumulators exceed tensor memory");
 
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();  // barriers, tensor memory and descriptors are set up: from here on the predecessors' results are needed
     const uint32_t tmem_base = *tmem_slot;
 
     if (threadIdx.x == TMA_THREAD) {
@@ -433,6 +435,8 @@ __device__ __forceinline__ void digits(double (&res)[NV], uint32_t (&pack)[Cfg<K
 template <int KIND>
 __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int k, uint8_t *out, long long pitch,
                                   int *exps) {
+    pdl_launch_dependents();
+    pdl_wait();
     using C = Cfg<KIND>;
     const int r = blockIdx.x;
     const long long slice_stride = (long long)rows * pitch;
@@ -476,6 +480,8 @@ __global__ void slice_rows_kernel(const void *xin, long long ldx, int rows, int 
 //   col_sum_kernel       colsum[c] += coef * sum_r x[r][c] in a fixed order (bias gradients)
 __global__ void col_exponent_kernel(const double *x, long long ldx, int rows, int cols, int *exps, double *colsum,
                                     double coef) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     const int rbeg = blockIdx.y * 256 + rg * 32, rend = min(rows, rbeg + 32);
@@ -501,6 +507,8 @@ __global__ void col_exponent_kernel(const double *x, long long ldx, int rows, in
 template <int KIND>
 __global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int cols, uint8_t *out, long long pitch,
                                   int *exps) {
+    pdl_launch_dependents();
+    pdl_wait();
     using C = Cfg<KIND>;
     const long long slice_stride = (long long)cols * pitch;
     if constexpr (C::INT) {
@@ -551,6 +559,8 @@ __global__ void slice_cols_kernel(const void *xin, long long ldx, int rows, int 
 // colsum[c] += coef * sum_r x[r][c], fixed order: 32 columns x 8 row classes (r mod 8) per block.
 template <typename T>
 __global__ void col_sum_kernel(const T *x, long long ldx, int rows, int cols, T *colsum, double coef) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     __shared__ double ss[8][33];
@@ -575,12 +585,16 @@ __global__ void col_sum_kernel(const T *x, long long ldx, int rows, int cols, T 
 // ---- fused row + column slicing of one source (an activation is the A operand of the next product by rows and the
 // B operand of a weight-gradient product by columns): one read of the source per kernel, 32 x 64 tiles --------------------
 __global__ void fill_sentinel_kernel(int *a, int na, int *b, int nb) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < na) a[i] = EXP_SENTINEL;
     if (i < nb) b[i] = EXP_SENTINEL;
 }
 
 __global__ void exp_both_kernel(const double *x, long long ldx, int rows, int cols, int *exp_r, int *exp_c, double *colpart) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
     __shared__ double cm[8][64], cs[8][64];
@@ -619,6 +633,8 @@ template <int KIND>
 __global__ void slice_both_kernel(const double *x, long long ldx, int rows, int cols, uint8_t *out_r, long long pitch_r,
                                   uint8_t *out_c, long long pitch_c, int *exp_r, int *exp_c, double *colsum, double coef,
                                   const double *colpart, int nrt) {
+    pdl_launch_dependents();
+    pdl_wait();
     using C = Cfg<KIND>;
     __shared__ double tile[32][65];
     const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
@@ -677,6 +693,8 @@ __global__ void slice_both_kernel(const double *x, long long ldx, int rows, int 
 // fp32: hi / lo of every entry in both layouts; column sums of the tile's 32 rows into colpart.
 __global__ void slice_both_tf32_kernel(const float *x, long long ldx, int rows, int cols, float *out_r, long long pitch_r,
                                        float *out_c, long long pitch_c, double *colpart) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float th[32][65], tl[32][65];
     const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
     const long long slice_r = (long long)rows * pitch_r, slice_c = (long long)cols * pitch_c;
@@ -707,6 +725,8 @@ __global__ void slice_both_tf32_kernel(const float *x, long long ldx, int rows, 
 }
 
 __global__ void colsum_finalize_f32_kernel(const double *colpart, int nrt, int cols, float *colsum, double coef) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     double sum = 0.0;
@@ -769,7 +789,7 @@ static int launch_gemm(const void *a, const void *b, int M, int N, int K, const 
         splits = (total_kb + ep.kb_per_split - 1) / ep.kb_per_split;
     }
     dim3 grid((N + C::BN - 1) / C::BN, (M + 127) / 128, splits);
-    umma_gemm_kernel<KIND><<<grid, GEMM_THREADS, SMEM, stream>>>(ma, mb, M, N, K, ep);
+    PNODE_CUDA_OK(launch_pdl(umma_gemm_kernel<KIND>, dim3(grid), dim3(GEMM_THREADS), SMEM, stream, ma, mb, M, N, K, ep));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -803,11 +823,11 @@ int split_k_blocks(int kind, int K, int splits) {
 int slice_rows(int kind, const void *x, long long ldx, int rows, int k, void *out, int *exps, cudaStream_t stream) {
     const long long pitch = pitch_bytes(kind, k);
     if (kind == KIND_I8)
-        slice_rows_kernel<KIND_I8><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
+        PNODE_CUDA_OK(launch_pdl(slice_rows_kernel<KIND_I8>, dim3(rows), dim3(256), 0, stream, x, ldx, rows, k, (uint8_t *)out, pitch, exps));
     else if (kind == KIND_I8X)
-        slice_rows_kernel<KIND_I8X><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
+        PNODE_CUDA_OK(launch_pdl(slice_rows_kernel<KIND_I8X>, dim3(rows), dim3(256), 0, stream, x, ldx, rows, k, (uint8_t *)out, pitch, exps));
     else
-        slice_rows_kernel<KIND_TF32><<<rows, 256, 0, stream>>>(x, ldx, rows, k, (uint8_t *)out, pitch, exps);
+        PNODE_CUDA_OK(launch_pdl(slice_rows_kernel<KIND_TF32>, dim3(rows), dim3(256), 0, stream, x, ldx, rows, k, (uint8_t *)out, pitch, exps));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -817,21 +837,20 @@ int slice_cols(int kind, const void *x, long long ldx, int rows, int cols, void 
     const long long pitch = pitch_bytes(kind, rows);
     dim3 grid((cols + 31) / 32, (rows + 127) / 128);
     if (kind == KIND_TF32) {
-        slice_cols_kernel<KIND_TF32><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
+        PNODE_CUDA_OK(launch_pdl(slice_cols_kernel<KIND_TF32>, dim3(grid), dim3(256), 0, stream, x, ldx, rows, cols, (uint8_t *)out, pitch, exps));
         if (colsum)
-            col_sum_kernel<float><<<(cols + 31) / 32, 256, 0, stream>>>((const float *)x, ldx, rows, cols, (float *)colsum, coef);
+            PNODE_CUDA_OK(launch_pdl(col_sum_kernel<float>, dim3((cols + 31) / 32), dim3(256), 0, stream, (const float *)x, ldx, rows, cols, (float *)colsum, coef));
     } else {
         PNODE_CUDA_OK(cudaMemsetAsync(exps, 0x80, sizeof(int) * (size_t)cols, stream));
         const bool one_chunk = rows <= 256;
-        col_exponent_kernel<<<dim3((cols + 31) / 32, (rows + 255) / 256), 256, 0, stream>>>(
-            (const double *)x, ldx, rows, cols, exps, one_chunk ? (double *)colsum : nullptr, coef);
+        PNODE_CUDA_OK(launch_pdl(col_exponent_kernel, dim3(dim3((cols + 31) / 32, (rows + 255) / 256)), dim3(256), 0, stream, (const double *)x, ldx, rows, cols, exps, one_chunk ? (double *)colsum : nullptr, coef));
         if (kind == KIND_I8)
-            slice_cols_kernel<KIND_I8><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
+            PNODE_CUDA_OK(launch_pdl(slice_cols_kernel<KIND_I8>, dim3(grid), dim3(256), 0, stream, x, ldx, rows, cols, (uint8_t *)out, pitch, exps));
         else
-            slice_cols_kernel<KIND_I8X><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, (uint8_t *)out, pitch, exps);
+            PNODE_CUDA_OK(launch_pdl(slice_cols_kernel<KIND_I8X>, dim3(grid), dim3(256), 0, stream, x, ldx, rows, cols, (uint8_t *)out, pitch, exps));
         if (colsum && !one_chunk)
-            col_sum_kernel<double><<<(cols + 31) / 32, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (double *)colsum,
-                                                                         coef);
+            PNODE_CUDA_OK(launch_pdl(col_sum_kernel<double>, dim3((cols + 31) / 32), dim3(256), 0, stream, (const double *)x, ldx, rows, cols, (double *)colsum,
+                                                                         coef));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -844,22 +863,22 @@ int slice_both(int kind, const void *x, long long ldx, int rows, int cols, void 
     dim3 grid((cols + 63) / 64, (rows + 31) / 32);
     const int nrt = (int)grid.y;
     if (kind == KIND_TF32) {
-        slice_both_tf32_kernel<<<grid, 256, 0, stream>>>((const float *)x, ldx, rows, cols, (float *)out_r, pitch_r / 4,
-                                                         (float *)out_c, pitch_c / 4, colsum ? colpart : nullptr);
+        PNODE_CUDA_OK(launch_pdl(slice_both_tf32_kernel, dim3(grid), dim3(256), 0, stream, (const float *)x, ldx, rows, cols, (float *)out_r, pitch_r / 4,
+                                                         (float *)out_c, pitch_c / 4, colsum ? colpart : nullptr));
         if (colsum)
-            colsum_finalize_f32_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(colpart, nrt, cols, (float *)colsum, coef);
+            PNODE_CUDA_OK(launch_pdl(colsum_finalize_f32_kernel, dim3((cols + 127) / 128), dim3(128), 0, stream, colpart, nrt, cols, (float *)colsum, coef));
     } else {
         const int n = rows > cols ? rows : cols;
-        fill_sentinel_kernel<<<(n + 255) / 256, 256, 0, stream>>>(exp_r, rows, exp_c, cols);
-        exp_both_kernel<<<grid, 256, 0, stream>>>((const double *)x, ldx, rows, cols, exp_r, exp_c, colsum ? colpart : nullptr);
+        PNODE_CUDA_OK(launch_pdl(fill_sentinel_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, exp_r, rows, exp_c, cols));
+        PNODE_CUDA_OK(launch_pdl(exp_both_kernel, dim3(grid), dim3(256), 0, stream, (const double *)x, ldx, rows, cols, exp_r, exp_c, colsum ? colpart : nullptr));
         if (kind == KIND_I8)
-            slice_both_kernel<KIND_I8><<<grid, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (uint8_t *)out_r, pitch_r,
+            PNODE_CUDA_OK(launch_pdl(slice_both_kernel<KIND_I8>, dim3(grid), dim3(256), 0, stream, (const double *)x, ldx, rows, cols, (uint8_t *)out_r, pitch_r,
                                                                  (uint8_t *)out_c, pitch_c, exp_r, exp_c, (double *)colsum, coef,
-                                                                 colpart, nrt);
+                                                                 colpart, nrt));
         else
-            slice_both_kernel<KIND_I8X><<<grid, 256, 0, stream>>>((const double *)x, ldx, rows, cols, (uint8_t *)out_r, pitch_r,
+            PNODE_CUDA_OK(launch_pdl(slice_both_kernel<KIND_I8X>, dim3(grid), dim3(256), 0, stream, (const double *)x, ldx, rows, cols, (uint8_t *)out_r, pitch_r,
                                                                   (uint8_t *)out_c, pitch_c, exp_r, exp_c, (double *)colsum,
-                                                                  coef, colpart, nrt);
+                                                                  coef, colpart, nrt));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "pdl.cuh"
 
 namespace pnode {
 
@@ -69,6 +70,8 @@ __device__ __forceinline__ void vstore(T *p, const T (&r)[Vec16<T>::N]) {
 template <typename T, bool HAS_BASE>
 __global__ void __launch_bounds__(256) lincomb_kernel(T *__restrict__ out, const T *__restrict__ base, T base_coef,
                                                       const TermTable<T> tt, int64_t n) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     constexpr int N = Vec16<T>::N;
     const int64_t nvec = n / N;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -103,6 +106,8 @@ __global__ void __launch_bounds__(256) lincomb_kernel(T *__restrict__ out, const
 template <typename T, bool HAS_BASE>
 __global__ void __launch_bounds__(256) lincomb_scalar_kernel(T *__restrict__ out, const T *__restrict__ base,
                                                              T base_coef, const TermTable<T> tt, int64_t n) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         T acc = HAS_BASE ? base_coef * base[i] : T(0);
@@ -138,15 +143,15 @@ static int lincomb_impl(void *d_out, const void *d_base, double base_coef, const
     if (al) {
         int grid = stream_grid(n / Vec16<T>::N + 1, threads, 8);
         if (base)
-            lincomb_kernel<T, true><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+            PNODE_CUDA_OK(pdl::launch_pdl(lincomb_kernel<T, true>, dim3(grid), dim3(threads), 0, st, out, base, (T)base_coef, tt, n));
         else
-            lincomb_kernel<T, false><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+            PNODE_CUDA_OK(pdl::launch_pdl(lincomb_kernel<T, false>, dim3(grid), dim3(threads), 0, st, out, base, (T)base_coef, tt, n));
     } else {
         int grid = stream_grid(n, threads, 8);
         if (base)
-            lincomb_scalar_kernel<T, true><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+            PNODE_CUDA_OK(pdl::launch_pdl(lincomb_scalar_kernel<T, true>, dim3(grid), dim3(threads), 0, st, out, base, (T)base_coef, tt, n));
         else
-            lincomb_scalar_kernel<T, false><<<grid, threads, 0, st>>>(out, base, (T)base_coef, tt, n);
+            PNODE_CUDA_OK(pdl::launch_pdl(lincomb_scalar_kernel<T, false>, dim3(grid), dim3(threads), 0, st, out, base, (T)base_coef, tt, n));
     }
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -167,6 +172,8 @@ __global__ void __launch_bounds__(256) complete_wrms_kernel(T *__restrict__ unew
                                                             const TermTable<T> bw, const TermTable<T> ew, int64_t n,
                                                             double atol, double rtol, double *__restrict__ sumsq,
                                                             WrmsWork *__restrict__ work, int vec_ok) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     constexpr int N = Vec16<T>::N;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,12 +269,12 @@ static int complete_impl(void *d_unew, const void *d_u, const void *const *k, co
     int grid = stream_grid(n / Vec16<T>::N + 1, threads, 8);
     if (grid > WRMS_MAX_BLOCKS) grid = WRMS_MAX_BLOCKS;
     if (ewc)
-        complete_wrms_kernel<T, true><<<grid, threads, 0, st>>>(static_cast<T *>(d_unew), static_cast<const T *>(d_u),
+        PNODE_CUDA_OK(pdl::launch_pdl(complete_wrms_kernel<T, true>, dim3(grid), dim3(threads), 0, st, static_cast<T *>(d_unew), static_cast<const T *>(d_u),
                                                                 bw, ew, n, atol, rtol, d_sumsq,
-                                                                static_cast<WrmsWork *>(d_work), al ? 1 : 0);
+                                                                static_cast<WrmsWork *>(d_work), al ? 1 : 0));
     else
-        complete_wrms_kernel<T, false><<<grid, threads, 0, st>>>(static_cast<T *>(d_unew), static_cast<const T *>(d_u),
-                                                                 bw, ew, n, atol, rtol, nullptr, nullptr, al ? 1 : 0);
+        PNODE_CUDA_OK(pdl::launch_pdl(complete_wrms_kernel<T, false>, dim3(grid), dim3(threads), 0, st, static_cast<T *>(d_unew), static_cast<const T *>(d_u),
+                                                                 bw, ew, n, atol, rtol, nullptr, nullptr, al ? 1 : 0));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -285,6 +292,8 @@ struct SrcTable {
 template <typename T>
 __global__ void __launch_bounds__(256) multi_axpy_kernel(T *__restrict__ mu, const SrcTable<T> st, T coef,
                                                          int64_t total) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         int k = 0;
@@ -316,7 +325,7 @@ static int multi_axpy_impl(void *d_mu, const void *const *srcs, const int64_t *s
         st.n = m;
         if (run > 0) {
             int grid = stream_grid(run, 256, 8);
-            multi_axpy_kernel<T><<<grid, 256, 0, stream>>>(static_cast<T *>(d_mu) + base, st, (T)coef, run);
+            PNODE_CUDA_OK(pdl::launch_pdl(multi_axpy_kernel<T>, dim3(grid), dim3(256), 0, stream, static_cast<T *>(d_mu) + base, st, (T)coef, run));
             PNODE_CUDA_OK(cudaGetLastError());
         }
         base += run;
@@ -345,6 +354,8 @@ struct MdotTable {
 template <typename T>
 __global__ void __launch_bounds__(256) mdot_kernel(double *__restrict__ out, const MdotTable<T> tb,
                                                    const T *__restrict__ w, int64_t n, MdotWork *__restrict__ work) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     double acc[MDOT_MAX + 1];
 #pragma unroll
     for (int j = 0; j <= MDOT_MAX; ++j) acc[j] = 0.0;
@@ -392,7 +403,7 @@ static int mdot_impl(double *d_out, const void *const *vecs, int nvec, const voi
     for (int j = 0; j < nvec; ++j) tb.v[j] = static_cast<const T *>(vecs[j]);
     int grid = stream_grid(n, 256, 4);
     if (grid > MDOT_MAX_BLOCKS) grid = MDOT_MAX_BLOCKS;
-    mdot_kernel<T><<<grid, 256, 0, st>>>(d_out, tb, static_cast<const T *>(d_w), n, static_cast<MdotWork *>(d_work));
+    PNODE_CUDA_OK(pdl::launch_pdl(mdot_kernel<T>, dim3(grid), dim3(256), 0, st, d_out, tb, static_cast<const T *>(d_w), n, static_cast<MdotWork *>(d_work)));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -402,6 +413,8 @@ static int mdot_impl(double *d_out, const void *const *vecs, int nvec, const voi
 
 template <typename T>
 __global__ void __launch_bounds__(512) peak_fma_kernel(T *out, int iters, T a, T b) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -430,6 +443,8 @@ using namespace pnode;
 template <typename T>
 __global__ void __launch_bounds__(256) mdot_seg_kernel(double *__restrict__ out, const MdotTable<T> tb,
                                                        const T *__restrict__ w, int64_t nseg, int64_t seglen) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int64_t s = blockIdx.x;
     const int64_t base = s * seglen;
     double acc[MDOT_MAX + 1];
@@ -463,6 +478,8 @@ __global__ void __launch_bounds__(256) lincomb_seg_kernel(T *__restrict__ out, c
                                                           const double base_coef, const MdotTable<T> tb,
                                                           const double *__restrict__ coef, const int mode,
                                                           const int64_t nseg, const int64_t seglen) {
+    pdl::pdl_launch_dependents();
+    pdl::pdl_wait();
     const int64_t s = blockIdx.y;
     __shared__ double c[MDOT_MAX];
     if (threadIdx.x < tb.n) {
@@ -486,7 +503,7 @@ static int mdot_seg_impl(double *d_out, const void *const *vecs, int nvec, const
     MdotTable<T> tb;
     tb.n = nvec;
     for (int j = 0; j < nvec; ++j) tb.v[j] = static_cast<const T *>(vecs[j]);
-    mdot_seg_kernel<T><<<(unsigned)nseg, 256, 0, st>>>(d_out, tb, static_cast<const T *>(d_w), nseg, seglen);
+    PNODE_CUDA_OK(pdl::launch_pdl(mdot_seg_kernel<T>, dim3((unsigned)nseg), dim3(256), 0, st, d_out, tb, static_cast<const T *>(d_w), nseg, seglen));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -499,8 +516,8 @@ static int lincomb_seg_impl(void *d_out, const void *d_base, double base_coef, c
     for (int j = 0; j < nvec; ++j) tb.v[j] = static_cast<const T *>(vecs[j]);
     int gx = (int)((seglen + 255) / 256);
     if (gx > 64) gx = 64;
-    lincomb_seg_kernel<T><<<dim3(gx, (unsigned)nseg), 256, 0, st>>>(static_cast<T *>(d_out), static_cast<const T *>(d_base),
-                                                                     base_coef, tb, d_coef, mode, nseg, seglen);
+    PNODE_CUDA_OK(pdl::launch_pdl(lincomb_seg_kernel<T>, dim3(dim3(gx, (unsigned)nseg)), dim3(256), 0, st, static_cast<T *>(d_out), static_cast<const T *>(d_base),
+                                                                     base_coef, tb, d_coef, mode, nseg, seglen));
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
