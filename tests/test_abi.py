@@ -100,3 +100,21 @@ def test_convblock_plan_runs_without_a_gpu():
     d.layer[2].cin = 6
     assert lib.pnode_convblock_act_bytes(C.byref(d)) == -1 and b"multiples of 4" in lib.pnode_last_error()
     assert C.sizeof(_lib.ConvLayer) == 24 + 7 * 8 + 16 and C.sizeof(_lib.ConvBlockDesc) == 24 + 8 * C.sizeof(_lib.ConvLayer) + 32
+
+
+def test_control_block_layout_matches_a_c_compiler(tmp_path):
+    """pnode_cnf_ctl is written by the host and read / updated by the attempt kernel's step controller: the ctypes mirror
+    must agree with what a C compiler makes of include/pnode_b200.h (size and the offsets the host relies on)."""
+    import subprocess
+
+    src = tmp_path / "ctl.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pnode_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pnode_cnf_ctl), offsetof(pnode_cnf_ctl, span), '
+                   'offsetof(pnode_cnf_ctl, nspan), offsetof(pnode_cnf_ctl, max_steps), offsetof(pnode_cnf_ctl, sumsq), '
+                   'offsetof(pnode_cnf_ctl, log_t), offsetof(pnode_cnf_ctl, log_accepted)); return 0; }\n')
+    exe = tmp_path / "ctl"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    c = _lib.CnfCtl
+    assert got == [ctypes.sizeof(c), c.span.offset, c.nspan.offset, c.max_steps.offset, c.sumsq.offset, c.log_t.offset,
+                   c.log_accepted.offset]
