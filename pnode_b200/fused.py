@@ -404,16 +404,18 @@ class FusedCnfRK:
     CKPT_STEPS0 = 16     # checkpoint room of a fresh buffer, in steps (doubled when a solve runs out of it)
 
     class _Lease:
-        """A checkpoint buffer on loan to one solve's autograd state; it goes back to the pool when that state dies, so
-        solves of the same shape keep presenting the same addresses to the cached loop graphs (csrc/cnf_rk.cu)."""
+        """A checkpoint buffer and a copy of the Hutchinson probe on loan to one solve's autograd state; they go back to the
+        pool when that state dies, so solves of the same shape keep presenting the same addresses to the cached loop graphs
+        (csrc/cnf_rk.cu) -- FFJORD's driver draws a fresh probe tensor for every forward (cnf.py: before_odeint), and a
+        backward must still see the probe of ITS forward when other solves ran in between."""
 
-        def __init__(self, pool, buf):
-            self.pool, self.buf = pool, buf
+        def __init__(self, pool, buf, ebuf):
+            self.pool, self.buf, self.ebuf = pool, buf, ebuf
 
         def __del__(self):
             pool = self.pool
             if pool is not None and len(pool) < 4:
-                pool.append(self.buf)
+                pool.append((self.buf, self.ebuf))
 
     def _ctl_buffers(self, n, nspan):
         key = (n, nspan)
@@ -444,13 +446,15 @@ class FusedCnfRK:
         ubuf, kbuf, sol = self._ctl_buffers(n, nspan)
         ubuf[0].copy_(u0)
         per_step = self.s_eff * sp.dim * ntraj
-        lease = None
-        cap = 0
-        if save:
-            buf = self._ckpt_pool.pop() if self._ckpt_pool else \
-                torch.empty(self.CKPT_STEPS0 * per_step, dtype=self.dtype, device=self.device)
-            lease = self._Lease(self._ckpt_pool, buf)
-            cap = buf.numel() // per_step
+        buf, ebuf = self._ckpt_pool.pop() if self._ckpt_pool else (None, None)
+        if save and buf is None:
+            buf = torch.empty(self.CKPT_STEPS0 * per_step, dtype=self.dtype, device=self.device)
+        if ebuf is None:
+            ebuf = torch.empty(ntraj * sp.dim, dtype=self.dtype, device=self.device)
+        lease = self._Lease(self._ckpt_pool, buf, ebuf)
+        ebuf.copy_(self._e_keepalive.reshape(-1))
+        desc.d_e = ebuf.data_ptr()
+        cap = buf.numel() // per_step if save else 0
         ctl = _lib.CnfCtl()
         ctl.t, ctl.h, ctl.t_end, ctl.dt_span_cached = loop.t, loop.h, loop.t_end, 0.0
         for i in range(nspan):
@@ -520,6 +524,8 @@ class FusedCnfRK:
                 sols[slot] = u if t_h_slot is steps[-1] else sol[slot].clone()
         loop.check_complete()
         state = {"steps": steps, "ckpt": lease.buf if save else None, "ntraj": ntraj, "desc_keep": desc, "lease": lease}
+        if not save:
+            state["lease"] = None  # nothing will run an adjoint on this solve: the buffers go back at once
         return u, sols, state
 
     def adjoint(self, gout, state, single, nadj=None, comm=None):

@@ -222,3 +222,44 @@ def test_device_controller_reports_divergence():
     argv = ["-ts_rtol", "1e-13", "-ts_atol", "1e-13", "-ts_max_reject", "2"]
     with pytest.raises(RuntimeError, match="TS_DIVERGED_STEP_REJECTED"):
         _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 1.0)
+
+
+def test_backward_sees_the_probe_of_its_own_forward():
+    """FFJORD draws a fresh Hutchinson probe per forward (cnf.py: odefunc.before_odeint).  Two forwards with different
+    probes, then the two backwards in reverse order, on ONE ODEPetsc object: each must equal the solve done on its own
+    (the probe and the checkpoints of a solve travel with its autograd state, csrc buffers are pooled, not shared)."""
+    from pnode import petsc_adjoint
+
+    B = 48
+    func = cnf_to(CNFFunc(B, 6, (60,), dtype=torch.float64, seed=5), "cuda")
+    probes = [torch.randn(B, 6, generator=torch.Generator().manual_seed(s), dtype=torch.float64).cuda() for s in (1, 2)]
+    u0s = [_inputs(B, 6, 2, torch.float64, seed=s)[0].cuda() for s in (3, 4)]
+    gout = _inputs(B, 6, 2, torch.float64)[1].cuda()
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64).cuda()
+    Options.clear_all()
+    Options.insert_args(["-ts_rtol", "1e-7", "-ts_atol", "1e-7"])
+
+    def solve(ode, k):
+        func.base_func.before_odeint(e=probes[k])
+        y0 = u0s[k].clone().requires_grad_(True)
+        return y0, ode.odeint_adjoint(y0, t)
+
+    alone = []
+    for k in (0, 1):
+        ode = petsc_adjoint.ODEPetsc()
+        ode.setupTS(u0s[k], func, step_size=0.05, method="dopri5", enable_adjoint=True)
+        func.zero_grad(set_to_none=True)
+        y0, out = solve(ode, k)
+        (out * gout).sum().backward()
+        alone.append((out.detach().clone(), y0.grad.clone(), [p.grad.clone() for p in func.parameters()]))
+    ode = petsc_adjoint.ODEPetsc()
+    ode.setupTS(u0s[0], func, step_size=0.05, method="dopri5", enable_adjoint=True)
+    ya, outa = solve(ode, 0)
+    yb, outb = solve(ode, 1)
+    assert ode.path == "fused-cnf-rk" and ode._fused.device_loop
+    for k, (y0, out) in ((1, (yb, outb)), (0, (ya, outa))):  # backwards in reverse order
+        func.zero_grad(set_to_none=True)
+        (out * gout).sum().backward()
+        assert torch.equal(out.detach(), alone[k][0]) and torch.equal(y0.grad, alone[k][1])
+        for a, b in zip([p.grad for p in func.parameters()], alone[k][2]):
+            assert torch.equal(a, b)
