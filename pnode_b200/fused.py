@@ -394,7 +394,8 @@ class FusedCnfRK:
             if loop.last_out_slot >= 0:
                 sols[loop.last_out_slot] = u.clone()
         loop.check_complete()
-        state = {"steps": steps, "ckpt": self._ckpt if save else None, "ntraj": ntraj, "desc_keep": desc}
+        state = {"steps": steps, "ckpt": self._ckpt if save else None, "ntraj": ntraj, "desc_keep": desc,
+                 "e_keep": self._e_keepalive}  # the descriptor points into this solve's probe tensor
         if save:
             self._ckpt = None  # ownership moves to the autograd node; the next solve allocates afresh
         return u, sols, state
