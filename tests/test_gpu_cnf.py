@@ -224,7 +224,8 @@ def test_device_controller_reports_divergence():
         _run(lambda: petsc_adjoint.ODEPetsc(), "cuda", argv, func, u0, t, gout, "dopri5", 1.0)
 
 
-def test_backward_sees_the_probe_of_its_own_forward():
+@pytest.mark.parametrize("extra", [[], ["-pnode_device_controller", "0"]], ids=["device-loop", "host-loop"])
+def test_backward_sees_the_probe_of_its_own_forward(extra):
     """FFJORD draws a fresh Hutchinson probe per forward (cnf.py: odefunc.before_odeint).  Two forwards with different
     probes, then the two backwards in reverse order, on ONE ODEPetsc object: each must equal the solve done on its own
     (the probe and the checkpoints of a solve travel with its autograd state, csrc buffers are pooled, not shared)."""
@@ -237,7 +238,7 @@ def test_backward_sees_the_probe_of_its_own_forward():
     gout = _inputs(B, 6, 2, torch.float64)[1].cuda()
     t = torch.tensor([0.0, 1.0], dtype=torch.float64).cuda()
     Options.clear_all()
-    Options.insert_args(["-ts_rtol", "1e-7", "-ts_atol", "1e-7"])
+    Options.insert_args(["-ts_rtol", "1e-7", "-ts_atol", "1e-7"] + extra)
 
     def solve(ode, k):
         func.base_func.before_odeint(e=probes[k])
@@ -256,7 +257,7 @@ def test_backward_sees_the_probe_of_its_own_forward():
     ode.setupTS(u0s[0], func, step_size=0.05, method="dopri5", enable_adjoint=True)
     ya, outa = solve(ode, 0)
     yb, outb = solve(ode, 1)
-    assert ode.path == "fused-cnf-rk" and ode._fused.device_loop
+    assert ode.path == "fused-cnf-rk" and ode._fused.device_controller == (not extra)
     for k, (y0, out) in ((1, (yb, outb)), (0, (ya, outa))):  # backwards in reverse order
         func.zero_grad(set_to_none=True)
         (out * gout).sum().backward()
