@@ -227,7 +227,9 @@ typedef struct pnode_cnf_ctl {
                                         NEXT attempt copies its input state there (the final state is read from d_ubuf) */
     int32_t max_steps;               /* room in the checkpoint buffer: the loop stops (done = 4) when ctl->steps reaches it and
                                         the end time has not been reached (0: no limit) */
-    double sumsq;                    /* the last attempt's weighted error sum of squares */
+    double sumsq;                    /* the last attempt's weighted error sum of squares (the global one in sharded runs) */
+    uint64_t epoch_next;             /* sharded runs (pnode_cnf_rk_solve_ctl_dp): number of the next in-kernel collective; the
+                                        host sets it before the solve and reads back how far the loop got */
     double log_t[PNODE_CTL_MAX_LOG], log_h[PNODE_CTL_MAX_LOG], log_enorm[PNODE_CTL_MAX_LOG];
     int32_t log_accepted[PNODE_CTL_MAX_LOG];
 } pnode_cnf_ctl;
@@ -245,6 +247,14 @@ int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau 
 int pnode_cnf_rk_solve_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
                            int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
                            pnode_cnf_ctl *d_ctl, void *d_work, void *stream);
+/* Batch-sharded variant: every rank runs the loop on its shard; the last block of each attempt all-reduces the weighted error
+ * sum of squares over NVLink peer memory (same symmetric inbox and flag protocol as the *_adjoint_dp kernels, collective number
+ * ctl->epoch_next++), so all ranks take the same verdict and the same next step -- no NCCL call, no host in the loop.
+ * ctl->n_global is the state length of the WHOLE batch. */
+int pnode_cnf_rk_solve_ctl_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
+                              int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
+                              pnode_cnf_ctl *d_ctl, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                              void *stream);
 
 /* Whole discrete-adjoint sweep over the accepted steps (same conventions as pnode_mlp_rk_adjoint); the per-stage VJP
  * (RHSJacShell.multTranspose, petsc_adjoint.py:52-82, which needs second-order autograd in the reference) is evaluated

@@ -41,7 +41,7 @@ class CnfCtl(C.Structure):
                [(n, C.c_int32) for n in ("nspan", "order", "max_reject", "done", "cur", "kcur", "have_k", "steps",
                                          "attempts", "rejections", "prev_ok", "ctr", "cur_sol_index", "pending_slot",
                                          "max_steps")] + \
-               [("sumsq", C.c_double), ("log_t", C.c_double * CTL_MAX_LOG), ("log_h", C.c_double * CTL_MAX_LOG),
+               [("sumsq", C.c_double), ("epoch_next", C.c_uint64), ("log_t", C.c_double * CTL_MAX_LOG), ("log_h", C.c_double * CTL_MAX_LOG),
                 ("log_enorm", C.c_double * CTL_MAX_LOG), ("log_accepted", C.c_int32 * CTL_MAX_LOG)]
 
 
@@ -100,6 +100,8 @@ _SIGNATURES = {
                                             _vp, _vp, _i, _vp]),
     "pnode_cnf_rk_solve_ctl": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _vp, _i64, _vp, _d, _d,
                                          _vp, _vp, _vp]),
+    "pnode_cnf_rk_solve_ctl_dp": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _vp, _i64, _vp, _d, _d,
+                                            _vp, _vp, _vp, _i, _i, _vp]),
     "pnode_cnf_rk_adjoint_work_bytes": (_i64, [C.POINTER(CnfDesc)]),
     "pnode_cnf_rk_adjoint": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),

@@ -336,7 +336,8 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
                       T *__restrict__ unew, T *__restrict__ kfsal_out, T *__restrict__ ckpt, const double atol,
                       const double rtol, double *__restrict__ sumsq, CnfWrmsWork *__restrict__ work,
                       pnode_cnf_ctl *__restrict__ dctl, T *__restrict__ ubuf, T *__restrict__ kbuf,
-                      const int64_t ckpt_step_elems, T *__restrict__ sol, const unsigned long long loop_cond) {
+                      const int64_t ckpt_step_elems, T *__restrict__ sol, const unsigned long long loop_cond,
+                      const PeerComm pc) {
     typedef Pack<T> P;
     typedef typename P::V V;
     constexpr int W = P::W;  // trajectories per thread
@@ -497,12 +498,27 @@ cnf_rk_attempt_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const T *_
         is_last = (atomicAdd(&work->ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x < 32) {
-        __threadfence();
-        double s = 0.0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += ((volatile double *)work->partial)[b];
-        s = warp_sum(s);
+    if (is_last) {
+        __shared__ double sred[2];
+        if (threadIdx.x < 32) {
+            __threadfence();
+            double s = 0.0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += ((volatile double *)work->partial)[b];
+            s = warp_sum(s);
+            if (threadIdx.x == 0) sred[0] = s;
+        }
+        __syncthreads();
+        if (dctl != nullptr && pc.peer_bufs != nullptr && pc.world > 1) {
+            // sharded run: the verdict needs the error norm of the whole batch -- summed over the ranks here, through the
+            // peers' inboxes (identical bits on every rank: they all take the same decision)
+            PeerComm q = pc;
+            q.epoch = dctl->epoch_next;
+            peer_allreduce_and_store<double>(&sred[0], 1, q, &sred[1]);
+            __syncthreads();
+            if (threadIdx.x == 0) sred[0] = sred[1], dctl->epoch_next = q.epoch + 1ull;
+        }
         if (threadIdx.x == 0) {
+            const double s = sred[0];
             *sumsq = s;
             work->ticket = 0u;
             if (dctl != nullptr) {
@@ -988,7 +1004,7 @@ static int launch_cnf_attempt_lpt(const pnode_cnf_desc *c, const pnode_rk_tablea
                                   int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
                                   double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl,
                                   void *d_ubuf, void *d_kbuf, int64_t ckpt_step_elems, void *d_sol, int nlaunch,
-                                  unsigned long long loop_cond) {
+                                  unsigned long long loop_cond, const PeerComm &pc) {
     auto kern = cnf_rk_attempt_kernel<T, 6, 60, S, LPT>;
     const size_t smem = CNF_HOIST_Q ? sizeof(typename Pack<T>::V) * 60 * CNF_THREADS : 0;
     static int ctas_per_sm = 0;
@@ -1008,7 +1024,7 @@ static int launch_cnf_attempt_lpt(const pnode_cnf_desc *c, const pnode_rk_tablea
                                            ntraj, t, h, static_cast<T *>(d_unew), static_cast<T *>(d_kout),
                                            static_cast<T *>(d_ckpt), atol, rtol, d_sumsq,
                                            static_cast<CnfWrmsWork *>(d_work), d_ctl, static_cast<T *>(d_ubuf),
-                                           static_cast<T *>(d_kbuf), ckpt_step_elems, static_cast<T *>(d_sol), loop_cond);
+                                           static_cast<T *>(d_kbuf), ckpt_step_elems, static_cast<T *>(d_sol), loop_cond, pc);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1018,13 +1034,14 @@ static int launch_cnf_attempt(const pnode_cnf_desc *c, const pnode_rk_tableau *t
                               int64_t ntraj, double t, double h, void *d_unew, void *d_kout, void *d_ckpt, double atol,
                               double rtol, double *d_sumsq, void *d_work, cudaStream_t st, pnode_cnf_ctl *d_ctl = nullptr,
                               void *d_ubuf = nullptr, void *d_kbuf = nullptr, int64_t ckpt_step_elems = 0,
-                              void *d_sol = nullptr, int nlaunch = 1, unsigned long long loop_cond = 0ull) {
+                              void *d_sol = nullptr, int nlaunch = 1, unsigned long long loop_cond = 0ull,
+                              const PeerComm &pc = PeerComm{nullptr, 0, 1, 0ull}) {
     if (cnf_small_batch<T>(ntraj))
         return launch_cnf_attempt_lpt<T, S, CNF_SMALL_LPT>(c, tab, d_u, d_kin, ntraj, t, h, d_unew, d_kout, d_ckpt, atol, rtol,
                                                            d_sumsq, d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems,
-                                                           d_sol, nlaunch, loop_cond);
+                                                           d_sol, nlaunch, loop_cond, pc);
     return launch_cnf_attempt_lpt<T, S, 1>(c, tab, d_u, d_kin, ntraj, t, h, d_unew, d_kout, d_ckpt, atol, rtol, d_sumsq,
-                                           d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems, d_sol, nlaunch, loop_cond);
+                                           d_work, st, d_ctl, d_ubuf, d_kbuf, ckpt_step_elems, d_sol, nlaunch, loop_cond, pc);
 }
 
 template <typename T, int S, int LPT>
@@ -1140,6 +1157,8 @@ struct CnfLoopKey {
     void *ubuf, *kbuf, *ckpt, *sol, *ctl, *work;
     int64_t ntraj, ckpt_step_elems;
     double atol, rtol;
+    const unsigned long long *peer_bufs;
+    int rank, world;
 };
 struct CnfLoopGraph {
     CnfLoopKey key;
@@ -1174,17 +1193,18 @@ int build_loop_graph(const CnfLoopKey &k, CnfLoopGraph &out) {
                                                 cudaStreamCaptureModeRelaxed));
     int rc = -1;
     double *d_sumsq = &static_cast<pnode_cnf_ctl *>(k.ctl)->sumsq;
+    const PeerComm pc{k.peer_bufs, k.rank, k.world, 0ull};  // the collective number lives in the control block
 #define X(SS)                                                                                                            \
     if (k.tab.s == SS) {                                                                                                 \
         rc = k.cnf.dtype == PNODE_F32                                                                                    \
                  ? launch_cnf_attempt<float, SS>(&k.cnf, &k.tab, nullptr, nullptr, k.ntraj, 0.0, 0.0, nullptr, nullptr,  \
                                                  k.ckpt, k.atol, k.rtol, d_sumsq, k.work, g_loop_capture_stream,         \
                                                  static_cast<pnode_cnf_ctl *>(k.ctl), k.ubuf, k.kbuf, k.ckpt_step_elems, \
-                                                 k.sol, 1, (unsigned long long)cond)                                    \
+                                                 k.sol, 1, (unsigned long long)cond, pc)                                \
                  : launch_cnf_attempt<double, SS>(&k.cnf, &k.tab, nullptr, nullptr, k.ntraj, 0.0, 0.0, nullptr, nullptr, \
                                                   k.ckpt, k.atol, k.rtol, d_sumsq, k.work, g_loop_capture_stream,        \
                                                   static_cast<pnode_cnf_ctl *>(k.ctl), k.ubuf, k.kbuf,                   \
-                                                  k.ckpt_step_elems, k.sol, 1, (unsigned long long)cond);               \
+                                                  k.ckpt_step_elems, k.sol, 1, (unsigned long long)cond, pc);           \
     }
     PNODE_CNF_STAGES(X)
 #undef X
@@ -1200,7 +1220,17 @@ int build_loop_graph(const CnfLoopKey &k, CnfLoopGraph &out) {
 int pnode_cnf_rk_solve_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
                            int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
                            pnode_cnf_ctl *d_ctl, void *d_work, void *stream) {
+    return pnode_cnf_rk_solve_ctl_dp(cnf, tab, d_ubuf, d_kbuf, ntraj, d_ckpt_base, ckpt_step_elems, d_sol, atol, rtol, d_ctl,
+                                     d_work, nullptr, 0, 1, stream);
+}
+
+int pnode_cnf_rk_solve_ctl_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
+                              int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
+                              pnode_cnf_ctl *d_ctl, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                              void *stream) {
     PNODE_REQUIRE(cnf && tab && d_ubuf && d_ctl && d_work, "pnode_cnf_rk_solve_ctl: null argument");
+    PNODE_REQUIRE(world <= 1 || d_peer_bufs == nullptr || (rank >= 0 && rank < world && world <= 64),
+                  "pnode_cnf_rk_solve_ctl_dp: bad rank/world");
     PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_solve_ctl: unsupported shape D=%d H=%d s=%d",
                   cnf->dim, cnf->hidden, tab->s);
     PNODE_REQUIRE(tab->has_be, "pnode_cnf_rk_solve_ctl: the device controller needs an embedded tableau");
@@ -1215,6 +1245,7 @@ int pnode_cnf_rk_solve_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *ta
     k.cnf = *cnf, k.tab = *tab;
     k.ubuf = d_ubuf, k.kbuf = d_kbuf, k.ckpt = d_ckpt_base, k.sol = d_sol, k.ctl = d_ctl, k.work = d_work;
     k.ntraj = ntraj, k.ckpt_step_elems = ckpt_step_elems, k.atol = atol, k.rtol = rtol;
+    k.peer_bufs = reinterpret_cast<const unsigned long long *>(d_peer_bufs), k.rank = rank, k.world = world;
     std::lock_guard<std::mutex> lock(g_loop_mutex);
     CnfLoopGraph *hit = nullptr, *victim = &g_loops[0];
     for (auto &g : g_loops) {

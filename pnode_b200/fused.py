@@ -350,9 +350,11 @@ class FusedCnfRK:
 
     def forward(self, u0, loop, atol, rtol, save, comm=None):
         """u0 flat [B*(D+1)].  `loop` is a controller.TimeLoop.  Returns (sol dict, state)."""
-        if self.device_controller and loop.adaptive and comm is None and loop.step_list is None and \
+        peer = getattr(comm, "peer", None) if comm is not None else None
+        sharded_ok = comm is None or (peer is not None and self.device_loop)  # in-kernel all-reduce of the error norm
+        if self.device_controller and loop.adaptive and sharded_ok and loop.step_list is None and \
                 (loop.span is None or len(loop.span) <= _lib.CTL_MAX_SPAN) and self.scheme.bembed is not None:
-            return self._forward_device_ctl(u0, loop, atol, rtol, save)
+            return self._forward_device_ctl(u0, loop, atol, rtol, save, comm)
         sp = self.spec
         ntraj = sp.batch
         n = u0.numel()
@@ -432,7 +434,7 @@ class FusedCnfRK:
             self._ckpt_pool = []
         return self._ubuf, self._kbuf, self._solbuf
 
-    def _forward_device_ctl(self, u0, loop, atol, rtol, save):
+    def _forward_device_ctl(self, u0, loop, atol, rtol, save, comm=None):
         """Same contract as forward().  The attempt kernel's last block runs TSAdaptChoose_Basic + MATCHSTEP + the span
         bookkeeping (csrc/cnf_rk.cu, namespace ctl) and publishes (t, h, buffers) for the next attempt.  The whole time
         loop is ONE launch -- a CUDA graph whose WHILE node repeats the attempt kernel until the controller says stop
@@ -460,7 +462,12 @@ class FusedCnfRK:
         ctl.t, ctl.h, ctl.t_end, ctl.dt_span_cached = loop.t, loop.h, loop.t_end, 0.0
         for i in range(nspan):
             ctl.span[i] = loop.span[i]
-        ctl.n_global, ctl.delta = float(n), loop.delta
+        peer = getattr(comm, "peer", None) if comm is not None else None
+        ctl.n_global, ctl.delta = float(n if comm is None else comm.global_count(n)), loop.delta
+        if peer is not None:
+            # sharded: the ranks' loops meet in every attempt (error norm summed over NVLink inside the kernel); the
+            # collective numbers continue the communicator's sequence and are handed back after the solve
+            ctl.epoch_next = peer["epoch"] + 1
         ctl.nspan, ctl.order, ctl.max_reject = nspan, int(loop.order), int(loop.max_reject)
         ctl.done = 1 if loop.done else 0
         ctl.prev_ok, ctl.ctr, ctl.cur_sol_index, ctl.pending_slot = 1, 1, 1, -1
@@ -482,7 +489,10 @@ class FusedCnfRK:
             args = (C.byref(desc), C.byref(self.tab), ubuf.data_ptr(), None if kbuf is None else kbuf.data_ptr(), ntraj,
                     lease.buf.data_ptr() if save else None, per_step, None if sol is None else sol.data_ptr(), float(atol),
                     float(rtol), self._ctl_dev.data_ptr(), self._wrms_work.data_ptr())
-            if self.device_loop:
+            if peer is not None:
+                _lib.check(self.lib.pnode_cnf_rk_solve_ctl_dp(*args, peer["ptrs_dev"], comm.rank, comm.world,
+                                                              stream.cuda_stream))
+            elif self.device_loop:
                 _lib.check(self.lib.pnode_cnf_rk_solve_ctl(*args, stream.cuda_stream))
             else:
                 _lib.check(self.lib.pnode_cnf_rk_attempts_ctl(*args, self.CTL_BATCH, stream.cuda_stream))
@@ -490,6 +500,9 @@ class FusedCnfRK:
             self._ctl_host.copy_(self._ctl_dev, non_blocking=True)
             stream.synchronize()  # the one host read per solve (per CTL_BATCH attempts without the device loop)
             now = c.attempts
+            if peer is not None:
+                comm.collectives += int(c.epoch_next) - 1 - peer["epoch"]
+                peer["epoch"] = int(c.epoch_next) - 1
             if self.device_loop:
                 self.launches += now - seen  # kernel nodes the graph's WHILE loop executed
             for a in range(seen, now):

@@ -106,6 +106,61 @@ def main():
             ref = rv.clone()
             dist.broadcast(ref, 0)
             assert torch.equal(rv, ref), "BatchNorm statistics differ across ranks"
+    # 4. fused FFJORD CNF (BASELINE config 3), adaptive dopri5, batch sharded.  With the peer inbox the whole time loop runs on
+    #    the device of every rank (error norm summed over NVLink in the attempt kernel); without it the host drives the loop
+    #    with one NCCL scalar per attempt.  Either way: the step sequence of the single-GPU run of the whole batch.
+    from _workloads import CNFFunc, cnf_to
+
+    Bc, D = 96 * world + 0, 6
+    assert Bc % world == 0
+    fc = CNFFunc(Bc, D, (60,), dtype=torch.float64, seed=3)
+    with torch.no_grad():
+        for prm in fc.parameters():
+            prm.mul_(4.0)  # stiffer: the first big step is rejected
+    g = torch.Generator().manual_seed(9)
+    zc = torch.randn(Bc, D, generator=g, dtype=torch.float64)
+    gz = torch.randn(3, Bc, D, generator=g, dtype=torch.float64)
+    gl = torch.randn(3, Bc, generator=g, dtype=torch.float64)
+    tc = torch.tensor([0.0, 0.3, 1.0], dtype=torch.float64)
+    argv = ["-ts_rtol", "1e-7", "-ts_atol", "1e-7"]
+
+    def run_cnf(func, z, gz_, gl_, comm_):
+        Options.clear_all()
+        Options.insert_args(argv)
+        f = cnf_to(copy.deepcopy(func), dev)
+        nb = z.shape[0]
+        u = torch.cat((z.reshape(-1), torch.zeros(nb, dtype=torch.float64))).to(dev)
+        go = torch.cat((gz_.reshape(3, -1), gl_), dim=1).to(dev)
+        ode = petsc_adjoint.ODEPetsc()
+        ode.comm = comm_
+        ode.setupTS(u, f, step_size=0.5, method="dopri5", enable_adjoint=True)
+        y0 = u.clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, tc.to(dev))
+        (out * go).sum().backward()
+        torch.cuda.synchronize()
+        split = lambda v: (v[..., : nb * D].reshape(v.shape[:-1] + (nb, D)).cpu(), v[..., nb * D:].cpu())
+        return split(out.detach()), split(y0.grad), [p.grad.cpu() for p in f.parameters()], ode
+
+    full = run_cnf(fc, zc, gz, gl, None)
+    lo, hi = rank * (Bc // world), (rank + 1) * (Bc // world)
+    fs = copy.deepcopy(fc)
+    fs.base_func._e = fc.base_func._e[lo:hi].clone()
+    fs.y0 = tuple(x[lo:hi].clone() for x in fc.y0)
+    mine = run_cnf(fs, zc[lo:hi], gz[:, lo:hi], gl[:, lo:hi], comm)
+    assert mine[3].path == "fused-cnf-rk" and full[3].path == "fused-cnf-rk"
+    la, lb = full[3]._loop.attempts, mine[3]._loop.attempts
+    assert [a[2] for a in la] == [b[2] for b in lb] and any(not a[2] for a in la), (la, lb)
+    for a, b in zip(la, lb):
+        assert abs(a[1] - b[1]) <= 1e-9 * abs(a[1]), (a, b)
+    for k in (0, 1):  # trajectory, lambda: (z part, logp part)
+        assert rel_err(mine[k][0], full[k][0][..., lo:hi, :]) < 2e-9, ("cnf z", k)
+        assert rel_err(mine[k][1], full[k][1][..., lo:hi]) < 2e-9, ("cnf logp", k)
+    for a, b in zip(mine[2], full[2]):
+        assert rel_err(a, b) < 2e-9, rel_err(a, b)
+    if rank == 0:
+        print("cnf sharded vs full batch: %d attempts, device loop on every rank: %s" %
+              (len(lb), comm.peer is not None and mine[3]._fused.device_loop), flush=True)
+
     if comm.peer is not None:
         # the in-kernel all-reduce must be bit-identical on every rank and repeatable (epochs / double buffering)
         for rep in range(5):
