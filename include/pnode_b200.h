@@ -256,6 +256,11 @@ int pnode_cnf_rk_solve_ctl_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau 
                               pnode_cnf_ctl *d_ctl, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
                               void *stream);
 
+/* Test hook: feeds `n` weighted error sums of squares to the device step controller one after the other (one thread, the
+ * code path the attempt kernel's last block runs) -- so that its decisions can be compared with the host controller on
+ * sequences no real solve produces.  Stops early when ctl->done becomes non-zero. */
+int pnode_cnf_ctl_probe(pnode_cnf_ctl *d_ctl, const double *d_sumsq, int n, void *stream);
+
 /* Whole discrete-adjoint sweep over the accepted steps (same conventions as pnode_mlp_rk_adjoint); the per-stage VJP
  * (RHSJacShell.multTranspose, petsc_adjoint.py:52-82, which needs second-order autograd in the reference) is evaluated
  * analytically.  d_ckpt is [nsteps, s_eff, D, ntraj]; d_gout / d_lambda use the flattened state layout. */

@@ -102,6 +102,7 @@ _SIGNATURES = {
                                          _vp, _vp, _vp]),
     "pnode_cnf_rk_solve_ctl_dp": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _vp, _i64, _vp, _d, _d,
                                             _vp, _vp, _vp, _i, _i, _vp]),
+    "pnode_cnf_ctl_probe": (C.c_int, [_vp, _vp, _i, _vp]),
     "pnode_cnf_rk_adjoint_work_bytes": (_i64, [C.POINTER(CnfDesc)]),
     "pnode_cnf_rk_adjoint": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),

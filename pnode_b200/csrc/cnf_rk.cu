@@ -1149,6 +1149,10 @@ int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau 
     PNODE_REQUIRE(false, "pnode_cnf_rk_attempts_ctl: no kernel for %d stages", tab->s);
 }
 
+__global__ void ctl_probe_kernel(pnode_cnf_ctl *c, const double *sumsq, int n) {
+    for (int i = 0; i < n && c->done == 0; ++i) ctl::report(*c, sumsq[i]);
+}
+
 // ---- the adaptive time loop as a CUDA graph with a device-driven WHILE node ---------------------------------------------
 namespace {
 struct CnfLoopKey {
@@ -1216,6 +1220,13 @@ int build_loop_graph(const CnfLoopKey &k, CnfLoopGraph &out) {
     return 0;
 }
 }  // namespace
+
+int pnode_cnf_ctl_probe(pnode_cnf_ctl *d_ctl, const double *d_sumsq, int n, void *stream) {
+    PNODE_REQUIRE(d_ctl && d_sumsq && n >= 0, "pnode_cnf_ctl_probe: bad argument");
+    ctl_probe_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_ctl, d_sumsq, n);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int pnode_cnf_rk_solve_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
                            int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,

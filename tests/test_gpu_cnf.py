@@ -264,3 +264,69 @@ def test_backward_sees_the_probe_of_its_own_forward(extra):
         assert torch.equal(out.detach(), alone[k][0]) and torch.equal(y0.grad, alone[k][1])
         for a, b in zip([p.grad for p in func.parameters()], alone[k][2]):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_device_step_controller_takes_the_host_controller_s_decisions(seed):
+    """csrc/cnf_rk.cu namespace ctl against controller.TimeLoop on random error-norm sequences (pnode_cnf_ctl_probe runs the
+    code the attempt kernel's last block runs): verdicts, times, next step sizes (MATCHSTEP clamp / halving / restore after
+    an output-time hit), span counters and output slots -- branches a handful of real solves does not reach."""
+    import ctypes as C
+    import random
+
+    from pnode_b200 import _lib
+    from pnode_b200.controller import TimeLoop
+
+    rng = random.Random(seed)
+    lib = _lib.load()
+    nspan = rng.choice([0, 2, 3, 5, 9])
+    if nspan:
+        times = sorted(rng.uniform(0.0, 2.0) for _ in range(nspan))
+        if rng.random() < 0.5:
+            times[1] = times[0] + 1e-3  # a very short first interval
+    else:
+        times = [rng.uniform(0.3, 2.0)]
+    h0 = rng.choice([1e-3, 0.05, 0.4, 5.0])
+    order = rng.choice([3, 5])
+    double = rng.random() < 0.5
+    loop = TimeLoop(times, h0, True, order, double, max_reject=10)
+    n_global = 1000.0
+    c = _lib.CnfCtl()
+    c.t, c.h, c.t_end = loop.t, loop.h, loop.t_end
+    for i in range(nspan):
+        c.span[i] = loop.span[i]
+    c.n_global, c.delta = n_global, loop.delta
+    c.nspan, c.order, c.max_reject = nspan, order, 10
+    c.done = 1 if loop.done else 0
+    c.prev_ok, c.ctr, c.cur_sol_index, c.pending_slot = 1, 1, 1, -1
+    enorms = []
+    slots = []
+    for _ in range(600):  # the host controller on a random walk of error norms, mostly accepted
+        if loop.done:
+            break
+        e = rng.choice([0.0, 1e-6, 0.05, 0.3, 0.8, 0.999, 1.0, 1.0001, 1.5, 4.0, 50.0]) if rng.random() < 0.3 else \
+            rng.lognormvariate(-0.7, 0.8)
+        enorms.append(e)
+        try:
+            if loop.report(e):
+                slots.append(loop.last_out_slot)
+        except RuntimeError:
+            break
+    sumsq = torch.tensor([e * e * n_global for e in enorms], dtype=torch.float64, device="cuda")
+    dev = torch.frombuffer(bytearray(bytes(c)), dtype=torch.uint8).cuda()
+    _lib.check(lib.pnode_cnf_ctl_probe(dev.data_ptr(), sumsq.data_ptr(), len(enorms), None))
+    torch.cuda.synchronize()
+    got = _lib.CnfCtl.from_buffer_copy(dev.cpu().numpy().tobytes())
+    assert got.attempts == len(loop.attempts)
+    for a in range(got.attempts):
+        t, h, ok, _ = loop.attempts[a]
+        assert bool(got.log_accepted[a]) == ok, a
+        assert got.log_t[a] == pytest.approx(t, rel=1e-13, abs=1e-15) and got.log_h[a] == pytest.approx(h, rel=1e-12), a
+    assert got.steps == loop.steps and got.ctr == loop.ctr and got.cur_sol_index == loop.cur_sol_index
+    assert got.t == pytest.approx(loop.t, rel=1e-13, abs=1e-15)
+    if loop.done:
+        assert got.done == 1
+    elif loop._rejections > loop.max_reject:
+        assert got.done == 2
+    else:
+        assert got.done == 0 and got.h == pytest.approx(loop.h, rel=1e-12)
