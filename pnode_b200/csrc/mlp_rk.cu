@@ -21,6 +21,8 @@
 //    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 256-entry 2^(j/256) table in
 //    SMEM + degree-4 polynomial + cubic reciprocal refinement = 15 FP64 ops; fp32: one MUFU.EX2 per unit and ONE shared
 //    MUFU.RCP per four units (product trick).  Grids are persistent: SMs x resident CTAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pnode {
@@ -493,6 +495,10 @@ __device__ __forceinline__ void lds16(const T *p, T (&r)[16 / sizeof(T)]) {
     memcpy(r, &v, 16);
 }
 
+template <typename T, int NP>
+__device__ void adj_finish(double *blk, int nwarps, AdjWork *__restrict__ work, T *__restrict__ mu_out, const PeerComm &pc,
+                           bool *is_last);
+
 template <typename T, int D, int H, int S, int PHI>
 __global__ void __launch_bounds__(ADJ_THREADS, Cfg<T>::ADJ_MIN_CTAS)
 mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
@@ -726,21 +732,308 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
         }
     }
     if (lane < D) blk[warp * NP + 2 * H * D + H + lane] = accB2[lane];
+    adj_finish<T, NP>(blk, ADJ_WARPS, work, mu_out, pc, &is_last);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small batches (the reference's own spiral run is batch 20)
+//
+// With one trajectory per thread a batch of 20 is ONE warp that issues the 50 hidden units of every stage evaluation one
+// after the other: 70 us forward + 148 us adjoint of pure FP64-issue latency on one scheduler, the rest of the GPU idle
+// (profiles: tools/prof_pass.py --config 1).  Below SMALL_MAX_TRAJ trajectories a slot (one trajectory) is spread over
+// SMALL_LPT = 10 adjacent lanes, five hidden units each (one tanh group); the per-unit sums -- the slope, the state
+// cotangent -- are added up in lane order by every lane of the slot (bit-identical copies, so the ten lanes carry the same
+// state), lane 0 of the slot stores.  Three slots per warp, twelve per CTA: batch 20 becomes two CTAs of fully used warps.
+constexpr int SMALL_LPT = 10;
+constexpr int SMALL_SPW = 32 / SMALL_LPT;             // slots per warp
+constexpr int SMALL_WARPS = 4;
+constexpr int SMALL_THREADS = SMALL_WARPS * 32;
+constexpr int SMALL_SLOTS = SMALL_WARPS * SMALL_SPW;  // slots per CTA
+constexpr int64_t SMALL_MAX_TRAJ = 4096;
+
+template <typename T>
+__device__ __forceinline__ T slot_sum(T v, int base) {  // sum over the SMALL_LPT lanes base .. base + 9, fixed order
+    T t = __shfl_sync(0xffffffffu, v, base);
+#pragma unroll
+    for (int k = 1; k < SMALL_LPT; ++k) t += __shfl_sync(0xffffffffu, v, base + k);
+    return t;
+}
+
+template <typename T, int D, int H, int S, int PHI>
+__global__ void __launch_bounds__(SMALL_THREADS)
+mlp_rk_fwd_small_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u0, const int64_t ntraj,
+                        const pnode_step *__restrict__ sched, const int nsteps, T *__restrict__ sol, T *__restrict__ ckpt) {
+    static_assert(H % SMALL_LPT == 0, "hidden units must split evenly over the lanes of a slot");
+    constexpr int UPL = H / SMALL_LPT;
+    __shared__ Unit<T, D> sW[H];
+    __shared__ T sB2[D];
+    __shared__ T sTab[EXP_TAB];
+    load_weights<T, D, H>(sW, sB2, sTab, w);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane / SMALL_LPT, sub = lane % SMALL_LPT, base = sl * SMALL_LPT;
+    const int64_t nt = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
+    for (int64_t tidx = blockIdx.x; tidx < nt; tidx += gridDim.x) {
+        const int64_t traj = tidx * SMALL_SLOTS + warp * SMALL_SPW + sl;
+        const bool valid = sl < SMALL_SPW && traj < ntraj;
+        const bool writer = valid && sub == 0;
+        T y[1][D], K[S][1][D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[0][d] = valid ? u0[traj * D + d] : T(0);
+        for (int n = 0; n < nsteps; ++n) {
+            const double h = sched[n].h;
+            const int out_slot = sched[n].out_slot;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                T Y[1][D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) Y[0][d] = y[0][d];
+#pragma unroll
+                for (int j = 0; j < i; ++j) {
+                    const T ha = (T)(h * tab.a[i][j]);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) Y[0][d] = fma(ha, K[j][0][d], Y[0][d]);
+                }
+                if (ckpt != nullptr && writer) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj] = Y[0][d];
+                }
+                if (i == 0 && tab.fsal && n > 0) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) K[0][0][d] = K[S - 1][0][d];
+                } else {
+                    T x[1][D], part[1][D];
+                    apply_phi<T, D, PHI>(Y[0], x[0]);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) part[0][d] = sub == 0 ? get_b2<T, D, H>(sB2, w.slot, d) : T(0);
+                    mlp_eval_units<T, D, H, PHI, 1, UPL>(sW, sTab, w.slot, sub * UPL, x, part);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) K[i][0][d] = slot_sum(part[0][d], base);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const T hb = (T)(h * tab.b[j]);
+#pragma unroll
+                for (int d = 0; d < D; ++d) y[0][d] = fma(hb, K[j][0][d], y[0][d]);
+            }
+            if (out_slot >= 0 && writer) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) sol[((int64_t)out_slot * ntraj + traj) * D + d] = y[0][d];
+            }
+        }
+    }
+}
+
+// tile of one warp of the small-batch adjoint: all H units x (slots of the warp, padded to a 16-byte vector)
+template <typename T, int D, int H>
+struct alignas(16) SmallTile {
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr int NKP = (SMALL_SPW + VEC - 1) / VEC * VEC;
+    T A[H][NKP], Sg[H][NKP], V[D][NKP], X[D][NKP];
+};
+
+template <typename T, int D, int H, int S, int PHI>
+__global__ void __launch_bounds__(SMALL_THREADS)
+mlp_rk_adj_small_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
+                        const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
+                        const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
+                        T *__restrict__ mu_out, AdjWork *__restrict__ work, const PeerComm pc) {
+    typedef SmallTile<T, D, H> Tile;
+    constexpr int UPL = H / SMALL_LPT, NKP = Tile::NKP, VEC = Tile::VEC, NP = 2 * H * D + H + D;
+    constexpr int NU = (H + 31) / 32;  // hidden units per lane in phase 2 (lane, lane + 32)
+    __shared__ Unit<T, D> sW[H];
+    __shared__ T sB2[D];
+    __shared__ T sTab[EXP_TAB];
+    __shared__ Tile tiles[SMALL_WARPS];
+    __shared__ double blk[SMALL_WARPS * NP];
+    __shared__ bool is_last;
+    load_weights<T, D, H>(sW, sB2, sTab, w);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Tile &tile = tiles[warp];
+    for (int i = lane; i < (int)(sizeof(Tile) / sizeof(T)); i += 32) reinterpret_cast<T *>(&tile)[i] = T(0);  // pad columns
+    __syncthreads();
+    const int sl = lane / SMALL_LPT, sub = lane % SMALL_LPT, base = sl * SMALL_LPT;
+    const int col = sl < SMALL_SPW ? sl : 0;
+
+    double accW1[NU][D], accW2[NU][D], accB1[NU], accB2[D];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        accB1[c] = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) accW1[c][d] = accW2[c][d] = 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) accB2[d] = 0.0;
+
+    const int64_t nt = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
+    for (int64_t tidx = blockIdx.x; tidx < nt; tidx += gridDim.x) {
+        const int64_t traj = tidx * SMALL_SLOTS + warp * SMALL_SPW + sl;
+        const bool valid = sl < SMALL_SPW && traj < ntraj;
+        const bool writer = valid && sub == 0;
+        T lam[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] = valid ? gout[((int64_t)last_slot * ntraj + traj) * D + d] : T(0);
+        for (int n = nsteps - 1; n >= 0; --n) {
+            const double h = sched[n].h;
+            const int in_slot = sched[n].in_slot;
+            T ls[S][D];
+#pragma unroll
+            for (int i = S - 1; i >= 0; --i) {
+                if (tab.fsal && i == S - 1) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) ls[i][d] = T(0);
+                    continue;
+                }
+                T v[D];
+                const double bi = tab.b[i];
+                const bool has_b = bi != 0.0;
+                const T cstep = (T)(has_b ? h * bi : h);
+#pragma unroll
+                for (int d = 0; d < D; ++d) v[d] = has_b ? lam[d] : T(0);
+#pragma unroll
+                for (int j = i + 1; j < S; ++j) {
+                    const T r = (T)(has_b ? tab.a[j][i] / bi : tab.a[j][i]);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) v[d] = fma(r, ls[j][d], v[d]);
+                }
+                T Y[D], x[D], dx[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    Y[d] = valid ? ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj] : T(0);
+                    v[d] = valid ? v[d] * cstep : T(0);
+                    dx[d] = T(0);
+                }
+                apply_phi<T, D, PHI>(Y, x);
+                if (sub == 0 && sl < SMALL_SPW) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        tile.V[d][col] = v[d];
+                        tile.X[d][col] = x[d];
+                        accB2[d] += (double)v[d];
+                    }
+                }
+                // ---- phase 1 (lane = one tenth of a trajectory's hidden units) ------------------------------------------
+                {
+                    Unit<T, D> u[UPL];
+                    T z[UPL], a[UPL];
+#pragma unroll
+                    for (int g = 0; g < UPL; ++g) {
+                        u[g] = get_unit<T, D, H>(sW, w.slot, sub * UPL + g);
+                        z[g] = u[g].b1;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) z[g] = fma(u[g].w1[d], x[d], z[g]);
+                    }
+                    tanh_group<UPL>(z, a, sTab);
+#pragma unroll
+                    for (int g = 0; g < UPL; ++g) {
+                        T gg = T(0);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) gg = fma(u[g].w2[d], v[d], gg);
+                        const T sg = gg * fma(-a[g], a[g], T(1));
+#pragma unroll
+                        for (int d = 0; d < D; ++d) dx[d] = fma(sg, u[g].w1[d], dx[d]);
+                        if (sl < SMALL_SPW) {
+                            tile.A[sub * UPL + g][col] = a[g];
+                            tile.Sg[sub * UPL + g][col] = sg;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) dx[d] = slot_sum(dx[d], base);
+                __syncwarp();
+                // ---- phase 2 (lane = hidden unit): outer products summed over the warp's trajectories -------------------
+#pragma unroll
+                for (int c = 0; c < NU; ++c) {
+                    const int j = c * 32 + lane;
+                    if (j < H) {
+                        T pW2[D], pW1[D], pB1 = T(0);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) pW2[d] = pW1[d] = T(0);
+#pragma unroll
+                        for (int k = 0; k < NKP; k += VEC) {
+                            T a[VEC], s[VEC], vv[D][VEC], xx[D][VEC];
+                            lds16(&tile.A[j][k], a);
+                            lds16(&tile.Sg[j][k], s);
+#pragma unroll
+                            for (int d = 0; d < D; ++d) {
+                                lds16(&tile.V[d][k], vv[d]);
+                                lds16(&tile.X[d][k], xx[d]);
+                            }
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) {
+                                pB1 += s[e];
+#pragma unroll
+                                for (int d = 0; d < D; ++d) {
+                                    pW2[d] = fma(vv[d][e], a[e], pW2[d]);
+                                    pW1[d] = fma(s[e], xx[d][e], pW1[d]);
+                                }
+                            }
+                        }
+                        accB1[c] += (double)pB1;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            accW2[c][d] += (double)pW2[d];
+                            accW1[c][d] += (double)pW1[d];
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < D; ++d) ls[i][d] = (PHI == 1) ? dx[d] * (T(3) * Y[d] * Y[d]) : dx[d];
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i)
+#pragma unroll
+                for (int d = 0; d < D; ++d) lam[d] += ls[i][d];
+            if (in_slot >= 0 && valid) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) lam[d] += gout[((int64_t)in_slot * ntraj + traj) * D + d];
+            }
+        }
+        if (writer) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) lambda_out[traj * D + d] = lam[d];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < D; ++d) accB2[d] = warp_sum(accB2[d]);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        const int j = c * 32 + lane;
+        if (j < H) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                blk[warp * NP + j * D + d] = accW1[c][d];
+                blk[warp * NP + H * D + H + d * H + j] = accW2[c][d];
+            }
+            blk[warp * NP + H * D + j] = accB1[c];
+        }
+    }
+    if (lane < D) blk[warp * NP + 2 * H * D + H + lane] = accB2[lane];
+    adj_finish<T, NP>(blk, SMALL_WARPS, work, mu_out, pc, &is_last);
+}
+
+// block partial (fixed order over the warps) -> grid partials -> the last block sums them in block order (and, in sharded
+// runs, all-reduces the result over the peers' inboxes) -- shared by both adjoint kernels
+template <typename T, int NP>
+__device__ void adj_finish(double *blk, int nwarps, AdjWork *__restrict__ work, T *__restrict__ mu_out, const PeerComm &pc,
+                           bool *is_last) {
     __syncthreads();
     for (int p = threadIdx.x; p < NP; p += blockDim.x) {
         double s = 0.0;
-#pragma unroll
-        for (int wi = 0; wi < ADJ_WARPS; ++wi) s += blk[wi * NP + p];
+        for (int wi = 0; wi < nwarps; ++wi) s += blk[wi * NP + p];
         work->partial[(int64_t)blockIdx.x * NP + p] = s;
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(&work->ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        *is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last) {
+    if (*is_last) {
         __threadfence();
         const bool dp = pc.peer_bufs != nullptr && pc.world > 1;
         for (int p = threadIdx.x; p < NP; p += blockDim.x) {
@@ -769,6 +1062,14 @@ static size_t adj_smem_bytes() {
 
 static int g_slot_counter = 0;
 
+static bool small_batch_enabled() {
+    static const int on = [] {
+        const char *e = getenv("PNODE_MLP_SMALL");
+        return e ? atoi(e) : 1;
+    }();
+    return on != 0;
+}
+
 template <typename T>
 static int upload_weights(const pnode_mlp_desc *m, int *slot_out, cudaStream_t st) {
     const int slot = (g_slot_counter++) % W_SLOTS;
@@ -796,6 +1097,14 @@ static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, cons
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
                  static_cast<const T *>(m->d_b2), slot};
+    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled()) {
+        const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
+        const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+        mlp_rk_fwd_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
+            w, *tab, static_cast<const T *>(d_u0), ntraj, d_sched, nsteps, static_cast<T *>(d_sol), static_cast<T *>(d_ckpt));
+        PNODE_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     auto kern = mlp_rk_fwd_kernel<T, D, H, S, PHI>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
@@ -821,6 +1130,17 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
                  static_cast<const T *>(m->d_b2), slot};
+    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled()) {
+        const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
+        int64_t cap = (int64_t)sm_count() * 4;
+        if (cap > ADJ_MAX_BLOCKS) cap = ADJ_MAX_BLOCKS;
+        const int grid = (int)(want < cap ? want : cap);
+        mlp_rk_adj_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
+            w, *tab, ntraj, d_sched, nsteps, last_slot, static_cast<const T *>(d_gout), static_cast<const T *>(d_ckpt),
+            static_cast<T *>(d_lambda), static_cast<T *>(d_mu), static_cast<AdjWork *>(d_work), pc);
+        PNODE_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     auto kern = mlp_rk_adj_kernel<T, D, H, S, PHI>;
     const size_t smem = adj_smem_bytes<T, D, H>();
     static int ctas_per_sm = 0;
