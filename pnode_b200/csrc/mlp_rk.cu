@@ -848,7 +848,13 @@ mlp_rk_adj_small_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const in
     __shared__ Tile tiles[SMALL_WARPS];
     __shared__ double blk[SMALL_WARPS * NP];
     __shared__ bool is_last;
+    __shared__ T sR[S][S];  // a_ji / b_i (a_ji where b_i = 0): the stage recurrences' coefficients, once per launch
     load_weights<T, D, H>(sW, sB2, sTab, w);
+    if (threadIdx.x < S * S) {
+        const int j = threadIdx.x / S, i = threadIdx.x % S;
+        const double bi = tab.b[i];
+        sR[j][i] = (T)(bi != 0.0 ? tab.a[j][i] / bi : tab.a[j][i]);
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Tile &tile = tiles[warp];
     for (int i = lane; i < (int)(sizeof(Tile) / sizeof(T)); i += 32) reinterpret_cast<T *>(&tile)[i] = T(0);  // pad columns
@@ -874,6 +880,15 @@ mlp_rk_adj_small_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const in
         T lam[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) lam[d] = valid ? gout[((int64_t)last_slot * ntraj + traj) * D + d] : T(0);
+        // stage values are fetched one stage ahead of their use
+        const int s_top = (tab.fsal ? S - 2 : S - 1);
+        T Ynext[D];
+        auto fetch_Y = [&](int nn, int ii) {
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                Ynext[d] = (valid && nn >= 0) ? ckpt[(((int64_t)nn * S + ii) * D + d) * ntraj + traj] : T(0);
+        };
+        fetch_Y(nsteps - 1, s_top);
         for (int n = nsteps - 1; n >= 0; --n) {
             const double h = sched[n].h;
             const int in_slot = sched[n].in_slot;
@@ -893,17 +908,18 @@ mlp_rk_adj_small_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const in
                 for (int d = 0; d < D; ++d) v[d] = has_b ? lam[d] : T(0);
 #pragma unroll
                 for (int j = i + 1; j < S; ++j) {
-                    const T r = (T)(has_b ? tab.a[j][i] / bi : tab.a[j][i]);
+                    const T r = sR[j][i];
 #pragma unroll
                     for (int d = 0; d < D; ++d) v[d] = fma(r, ls[j][d], v[d]);
                 }
                 T Y[D], x[D], dx[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    Y[d] = valid ? ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj] : T(0);
+                    Y[d] = Ynext[d];
                     v[d] = valid ? v[d] * cstep : T(0);
                     dx[d] = T(0);
                 }
+                if (i > 0) fetch_Y(n, i - 1); else fetch_Y(n - 1, s_top);
                 apply_phi<T, D, PHI>(Y, x);
                 if (sub == 0 && sl < SMALL_SPW) {
 #pragma unroll
