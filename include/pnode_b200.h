@@ -457,6 +457,12 @@ int pnode_dmlp_forward(const pnode_dmlp_desc *desc, const void *d_wslices, const
                        void *d_work, void *stream);
 int pnode_dmlp_vjp(const pnode_dmlp_desc *desc, const void *d_wslices, const void *d_act, const void *d_w, void *d_vu,
                    void *d_mu, double coef, void *d_work, void *stream);
+/* Same, recording layer_events[l] (HOST array of nlayers cudaEvent_t, entries may be NULL) on the stream right after the last
+ * kernel that adds to layer l's slice of mu (weight and bias gradient).  Layers are processed last to first, so a
+ * batch-sharded caller can start the all-reduce of a layer's gradient while the earlier layers are still being
+ * differentiated (pnode_b200/petsc_adjoint.py, the 298 MB mu of BASELINE config 5). */
+int pnode_dmlp_vjp_ev(const pnode_dmlp_desc *desc, const void *d_wslices, const void *d_act, const void *d_w, void *d_vu,
+                      void *d_mu, double coef, void *d_work, void *const *layer_events, void *stream);
 
 /* Circulant linear operator J[i][j] = c[(i - j) mod n] applied to every row of d_x[rows][n] (the implicit half of the
  * SINODE pair: a circular-padding Conv1d stencil, imex.py:6-44; replaces evalIFunction's func(t, u), petsc_adjoint.py:

@@ -136,6 +136,7 @@ _SIGNATURES = {
     "pnode_dmlp_prepare": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp]),
     "pnode_dmlp_forward": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnode_dmlp_vjp": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp]),
+    "pnode_dmlp_vjp_ev": (C.c_int, [C.POINTER(DmlpDesc), _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp]),
     "pnode_circulant_apply": (C.c_int, [_vp, _vp, _i, _i, C.POINTER(C.c_int32), C.POINTER(_d), _i, _i, _i, _vp]),
     "pnode_circulant_work_bytes": (_i64, [_i]),
     "pnode_circulant_inverse": (C.c_int, [_vp, _i, _d, _vp, _i, _vp, _vp]),

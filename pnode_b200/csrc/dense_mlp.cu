@@ -234,6 +234,11 @@ int pnode_dmlp_forward(const pnode_dmlp_desc *desc, const void *d_wslices, const
 
 int pnode_dmlp_vjp(const pnode_dmlp_desc *desc, const void *d_wslices, const void *d_act, const void *d_w, void *d_vu,
                    void *d_mu, double coef, void *d_work, void *stream) {
+    return pnode_dmlp_vjp_ev(desc, d_wslices, d_act, d_w, d_vu, d_mu, coef, d_work, nullptr, stream);
+}
+
+int pnode_dmlp_vjp_ev(const pnode_dmlp_desc *desc, const void *d_wslices, const void *d_act, const void *d_w, void *d_vu,
+                      void *d_mu, double coef, void *d_work, void *const *layer_events, void *stream) {
     Layout lay;
     if (int rc = dmlp::make_layout(desc, lay)) return rc;
     PNODE_REQUIRE(d_wslices && d_act && d_w && d_work, "pnode_dmlp_vjp: null argument");
@@ -267,6 +272,8 @@ int pnode_dmlp_vjp(const pnode_dmlp_desc *desc, const void *d_wslices, const voi
                                         mu + desc->mu_w_off[l] * lay.esz, in, coef * gscale, nullptr, 0, nullptr, 0, 1, st))
                     return rc;
         }
+        if (layer_events != nullptr && layer_events[l] != nullptr)  // layer l's slice of mu is complete for this call
+            PNODE_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(layer_events[l]), st));
         if (l > 0) {
             void *Y = work + ((l & 1) ? lay.d1 : lay.d0);
             if (int rc = umma::gemm(lay.kind, work + lay.gs, (const int *)(work + lay.gs_exp), W + lay.wb[l],

@@ -190,10 +190,45 @@ class DenseMlpCallbacks(Callbacks):
             self._forward(u, act)
         if not w.is_contiguous():
             w = w.contiguous()
-        _lib.check(self.lib.pnode_dmlp_vjp(C.byref(self._desc), self._wbuf.data_ptr(), act.data_ptr(), w.data_ptr(),
-                                           None if vu is None else vu.data_ptr(), None if mu is None else mu.data_ptr(),
-                                           float(coef), self._work.data_ptr(), _stream()))
+        ev = None
+        if mu is not None and self.record_layer_events:
+            # batch-sharded runs: mark the moment each layer's slice of mu is complete for this call, so that the caller
+            # can all-reduce the slices of the LAST call layer by layer behind the rest of the sweep (layer_slices())
+            if self._layer_events is None:
+                self._layer_events = [torch.cuda.Event() for _ in self.lins]
+                self._ev_handles = (C.c_void_p * len(self.lins))()
+            for l, e in enumerate(self._layer_events):
+                if not e.cuda_event:
+                    e.record()  # materialise the handle
+                self._ev_handles[l] = e.cuda_event
+            ev = self._ev_handles
+            self._events_mu_ptr = mu.data_ptr()
+        _lib.check(self.lib.pnode_dmlp_vjp_ev(C.byref(self._desc), self._wbuf.data_ptr(), act.data_ptr(), w.data_ptr(),
+                                              None if vu is None else vu.data_ptr(), None if mu is None else mu.data_ptr(),
+                                              float(coef), self._work.data_ptr(), ev, _stream()))
         self.launches += 4 * len(self.lins)
+
+    record_layer_events = False
+    _layer_events = None
+    _events_mu_ptr = None
+
+    def layer_slices(self, mu):
+        """[(event, offset, length)] last layer first: after `event`, mu[offset : offset + length] (this function's slice of
+        the parameter-gradient vector handed to the LAST vjp_accumulate call) receives no further contribution.  None when
+        no call recorded events into this very mu."""
+        if self._layer_events is None or self._events_mu_ptr != mu.data_ptr():
+            return None
+        out = []
+        for l in range(len(self.lins) - 1, -1, -1):
+            offs = [o for o in (self._desc.mu_w_off[l], self._desc.mu_b_off[l]) if o >= 0]
+            if not offs:
+                continue
+            lin = self.lins[l]
+            lo = min(offs)
+            hi = max(self._desc.mu_w_off[l] + lin.weight.numel() if self._desc.mu_w_off[l] >= 0 else 0,
+                     self._desc.mu_b_off[l] + lin.bias.numel() if self._desc.mu_b_off[l] >= 0 else 0)
+            out.append((self._layer_events[l], lo, hi - lo))
+        return out
 
     def vjp(self, t, u, w, want_u=True, want_params=True):
         self.nvjp += 1

@@ -62,6 +62,37 @@ class BatchComm:
             self.collectives += 1
         return tensor
 
+    _comm_stream = None
+
+    def allreduce_sum_layered(self, mu, cb, offset):
+        """All-reduce of mu where the part owned by the evaluator `cb` (mu[offset:], csrc/dense_mlp.cu) goes out LAYER BY
+        LAYER on a side stream, each slice as soon as the event of its last contribution has fired -- the sweep's last
+        vector-Jacobian product differentiates the layers last to first, so the collective of layer l runs while layers
+        l-1 .. 0 are still being computed (BASELINE config 5: 298 MB of mu, five slices).  The rest of mu follows on the
+        caller's stream, which then waits for the side stream."""
+        slices = cb.layer_slices(mu[offset:]) if (self.world > 1 and hasattr(cb, "layer_slices")) else None
+        if not slices:
+            return self.allreduce_sum(mu)
+        main = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        cs = self._comm_stream
+        covered = []
+        with torch.cuda.stream(cs):
+            for ev, lo, n in slices:
+                cs.wait_event(ev)
+                dist.all_reduce(mu[offset + lo: offset + lo + n], op=dist.ReduceOp.SUM, group=self.group)
+                self.collectives += 1
+                covered.append((offset + lo, offset + lo + n))
+        pos = 0
+        for lo, hi in sorted(covered) + [(mu.numel(), mu.numel())]:
+            if lo > pos:
+                dist.all_reduce(mu[pos:lo], op=dist.ReduceOp.SUM, group=self.group)
+                self.collectives += 1
+            pos = max(pos, hi)
+        main.wait_stream(cs)
+        return mu
+
     def allreduce_scalar(self, tensor):
         return self.allreduce_sum(tensor)
 

@@ -327,6 +327,9 @@ class ODEPetsc(object):
         loop = TimeLoop(times, self.step_size, self._adaptive(), self._scheme.order if self._scheme else 1,
                         self.tensor_dtype == torch.float64, self._max_reject)
         cb_ex, cb_im = self._active_callbacks()
+        if hasattr(self._cb_ex, "layer_slices"):  # sharded runs all-reduce the wide MLP's gradient layer by layer
+            self._cb_ex.record_layer_events = self.comm is not None and getattr(self.comm, "world", 1) > 1 and \
+                Options().getString("pnode_layered_allreduce", "1") not in ("0", "false", "no")
         uf, sols = self._engine.solve(cb_ex, cb_im, self._imp, u_flat, loop, self.enable_adjoint)
         self._loop = loop
         if self._monitor:
@@ -410,7 +413,13 @@ class _OdeintAdjoint(torch.autograd.Function):
                 lam, mu = ode._adjoint_generic(ctx.state[1], ctx.state[2], grad, T)
                 reduced = False
             if ode.comm is not None and not reduced:
-                ode.comm.allreduce_sum(mu)  # the loss sums over the global batch (NCCL; the fused sweeps do it in-kernel)
+                # the loss sums over the global batch (NCCL; the fused sweeps do it in-kernel)
+                cb = ode._cb_ex
+                if ctx.state[0] not in ("fused", "fused-cnf") and getattr(cb, "record_layer_events", False):
+                    np_im = ode.npIM if ode.imex else 0
+                    ode.comm.allreduce_sum_layered(mu, cb, np_im)
+                else:
+                    ode.comm.allreduce_sum(mu)
             outs = []
             off = 0
             plist = list(ode._cb_im.params) + (list(ode._cb_ex.params) if ode._cb_ex is not ode._cb_im else [])

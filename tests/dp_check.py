@@ -161,6 +161,46 @@ def main():
         print("cnf sharded vs full batch: %d attempts, device loop on every rank: %s" %
               (len(lb), comm.peer is not None and mine[3]._fused.device_loop), flush=True)
 
+    # 5. SINODE pair (BASELINE config 5 in small: circulant implicit half + wide ReLU MLP on the tensor-core evaluator), batch
+    #    sharded: no exchange inside the sweep; the MLP's parameter gradient is all-reduced LAYER BY LAYER on a side stream as
+    #    the last vector-Jacobian product finishes each layer (BatchComm.allreduce_sum_layered)
+    from _workloads import KSExplicit, KSImplicit, ks_dx
+
+    N5, B5 = 64, 8 * world
+    g = torch.Generator().manual_seed(4)
+    u5 = 0.5 * torch.randn(B5, N5, generator=g, dtype=torch.float64)
+    go5 = torch.randn(2, B5, N5, generator=g, dtype=torch.float64)
+    t5 = torch.tensor([0.0, 0.2], dtype=torch.float64)
+    f_im0, f_ex0 = KSImplicit(ks_dx(N5)), KSExplicit(N5, hidden=200)
+
+    def run_ks(u, go, comm_, nb):
+        Options.clear_all()
+        Options.insert_args(["-ts_adapt_type", "none", "-snes_type", "ksponly"])
+        f_im, f_ex = copy.deepcopy(f_im0).to(dev), copy.deepcopy(f_ex0).to(dev)
+        ode = petsc_adjoint.ODEPetsc()
+        ode.comm = comm_
+        ode.setupTS(u.to(dev), f_im, step_size=0.1, method="imex", imex_form=True, func2=f_ex, batch_size=nb,
+                    linear_solver="torch")
+        y0 = u.to(dev).clone().requires_grad_(True)
+        out = ode.odeint_adjoint(y0, t5.to(dev))
+        (out * go.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        return out.detach().cpu(), y0.grad.cpu(), [p.grad.cpu() for p in f_ex.parameters()], ode
+
+    full = run_ks(u5, go5, None, B5)
+    before = comm.collectives
+    mine = run_ks(shard_batch(u5, rank, world).contiguous(), shard_batch(go5, rank, world, dim=1).contiguous(), comm,
+                  B5 // world)
+    assert "dense-mlp" in mine[3].path, mine[3].path
+    assert mine[3]._cb_ex.record_layer_events
+    assert comm.collectives - before >= len(mine[3]._cb_ex.lins), "mu was not all-reduced layer by layer"
+    assert rel_err(mine[0], shard_batch(full[0], rank, world, dim=1)) < 1e-11
+    assert rel_err(mine[1], shard_batch(full[1], rank, world)) < 1e-10
+    for a, b in zip(mine[2], full[2]):
+        assert rel_err(a, b) < 1e-10, rel_err(a, b)
+    if rank == 0:
+        print("KS pair sharded vs full batch: mu all-reduced in %d layer slices" % len(mine[3]._cb_ex.lins), flush=True)
+
     if comm.peer is not None:
         # the in-kernel all-reduce must be bit-identical on every rank and repeatable (epochs / double buffering)
         for rep in range(5):
