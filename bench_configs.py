@@ -265,7 +265,7 @@ def cfg4(C=32, HW=32, Nt=1):
     return build
 
 
-def cfg5(N=1024, B=256, dtype="f64"):
+def cfg5(N=1024, B=256, dtype="f64", ark="3"):
     from _workloads import KSExplicit, KSImplicit, ks_dx
 
     def build():
@@ -278,14 +278,17 @@ def cfg5(N=1024, B=256, dtype="f64"):
         kw = dict(method="imex", imex_form=True, batch_size=B, linear_solver="torch", fixed_jacobian_across_solves=True)
         f_ex = 2 * (2 * N * H + 3 * H * H)
         bs = 32
-        return dict(desc="cfg5 SINODE KS: N=%d, MLP hidden %d, batch %d, ARKIMEX-3 h=0.2 one step, torch LU-type solver, "
-                         "-snes_type ksponly, %s" % (N, H, B, dtype), dtype=dtype,
-                    argv=["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_trajectory_type", "memory"],
+        ns = {"3": 4, "l2": 3}[ark]  # stages: ns explicit evaluations + ns - 1 implicit solves forward, as many VJPs / transposed solves back
+        return dict(desc="cfg5 SINODE KS: N=%d, MLP hidden %d, batch %d, ARKIMEX-%s h=0.2 one step, torch LU-type solver, "
+                         "-snes_type ksponly, %s" % (N, H, B, ark, dtype), dtype=dtype,
+                    argv=["-ts_adapt_type", "none", "-snes_type", "ksponly", "-ts_trajectory_type", "memory",
+                          "-ts_arkimex_type", ark],
                     funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)], u0=u0, t=t, target=target, kw=kw,
-                    step=0.2, batch=B, flops_per_unit=16 * f_ex + 6 * 2 * N * N, bytes_per_unit=12 * 37.3e6 * 8 / B,
+                    step=0.2, batch=B, flops_per_unit=4 * ns * f_ex + 2 * (ns - 1) * 2 * N * N,
+                    bytes_per_unit=3 * ns * 37.3e6 * 8 / B,
                     pipe="fp64_fma" if dtype == "f64" else "fp32_fma", also_generic=True,
                     # executed by the products: 4 forward + 8 backward layer sweeps of F_f / 2 MACs, (21 | 3) slice pairs, 2 ops
-                    tensor_ops_per_unit=12 * (f_ex / 2) * (21 if dtype == "f64" else 3) * 2,
+                    tensor_ops_per_unit=3 * ns * (f_ex / 2) * (21 if dtype == "f64" else 3) * 2,
                     cpu_sample=lambda: dict(funcs=[KSImplicit(ks_dx(N), dtype=td), KSExplicit(N, dtype=td)],
                                             u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
                                             kw=dict(kw, batch_size=bs), batch=bs, desc="%d of %d samples" % (bs, B)))
@@ -327,7 +330,8 @@ def config_table():
     return {"1": ("cfg1", cfg1), "2S": ("cfg2-f32", cfg2("f32")), "2D": ("cfg2-f64", cfg2("f64")), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
             "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)),
-            "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32")), "B": ("burgers", burgers())}
+            "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32")), "5L": ("cfg5-l2", cfg5(ark="l2")),
+            "B": ("burgers", burgers())}
 
 
 def main():
