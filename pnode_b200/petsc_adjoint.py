@@ -62,6 +62,18 @@ def _check_device(tensor, what):
 class ODEPetsc(object):
     comm = None  # reference: PETSc.COMM_SELF (petsc_adjoint.py:367).  Set to a pnode_b200.parallel.BatchComm for DP.
 
+    def _modules_of(self, f):
+        """list(f.modules()), kept per function object: FFJORD and the CIFAR driver call setupTS on every forward and the
+        recursive walk was a tenth of a small-batch pass.  The walk is redone when the number of direct children changes."""
+        cache = self.__dict__.setdefault("_mod_cache", {})
+        ent = cache.get(id(f))
+        if ent is None or ent[0]() is not f or ent[1] != len(f._modules):
+            import weakref
+
+            ent = (weakref.ref(f), len(f._modules), list(f.modules()))
+            cache[id(f)] = ent
+        return ent[2]
+
     def __init__(self):
         self.n = 0
         self.tensor_size = None
@@ -116,7 +128,7 @@ class ODEPetsc(object):
                         or u_tensor.device != self.device)
         # train()/eval() switches change what the modules compute (BatchNorm statistics, Dropout): the evaluators chosen below
         # -- and Callbacks' decision to keep stage graphs -- are re-derived whenever any sub-module's mode flips
-        mode_sig = tuple(m.training for f in (func, func_ex) if isinstance(f, nn.Module) for m in f.modules())
+        mode_sig = tuple(m.training for f in (func, func_ex) if isinstance(f, nn.Module) for m in self._modules_of(f))
         mode_changed = mode_sig != getattr(self, "_mode_sig", None)
         self._mode_sig = mode_sig
         if funcs_changed:
