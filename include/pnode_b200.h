@@ -227,11 +227,14 @@ typedef struct pnode_cnf_ctl {
                                         NEXT attempt copies its input state there (the final state is read from d_ubuf) */
     int32_t max_steps;               /* room in the checkpoint buffer: the loop stops (done = 4) when ctl->steps reaches it and
                                         the end time has not been reached (0: no limit) */
+    int32_t single;                  /* 1: one-element t (no forcing at interior output times: in_slot = -1 everywhere) */
+    int32_t prev_out_slot;           /* output slot of the previous accepted step (forcing slot of the next one) */
     double sumsq;                    /* the last attempt's weighted error sum of squares (the global one in sharded runs) */
     uint64_t epoch_next;             /* sharded runs (pnode_cnf_rk_solve_ctl_dp): number of the next in-kernel collective; the
                                         host sets it before the solve and reads back how far the loop got */
     double log_t[PNODE_CTL_MAX_LOG], log_h[PNODE_CTL_MAX_LOG], log_enorm[PNODE_CTL_MAX_LOG];
     int32_t log_accepted[PNODE_CTL_MAX_LOG];
+    pnode_step sched[PNODE_CTL_MAX_LOG]; /* the accepted steps, in the form the adjoint sweep consumes (first ctl->steps entries) */
 } pnode_cnf_ctl;
 int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, void *d_ubuf, void *d_kbuf,
                               int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol,
@@ -255,6 +258,18 @@ int pnode_cnf_rk_solve_ctl_dp(const pnode_cnf_desc *cnf, const pnode_rk_tableau 
                               int64_t ntraj, void *d_ckpt_base, int64_t ckpt_step_elems, void *d_sol, double atol, double rtol,
                               pnode_cnf_ctl *d_ctl, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
                               void *stream);
+
+/* An adaptive solve with NO host in it at all (so that the caller's whole training step can be captured in a CUDA graph):
+ *   pnode_cnf_rk_attempts_ctl(..., nlaunch)   a fixed budget of attempts (the ones after the end time return at once);
+ *   pnode_cnf_rk_gather_ctl                   d_out[k] (k = 1 .. nout-1; [nout][ntraj*(D+1)]) <- the states at the output times
+ *                                             (the last one from d_ubuf); NaN everywhere if the budget did not reach the end
+ *                                             time (ctl->done != 1), so that an unfinished solve cannot pass unnoticed;
+ *   pnode_cnf_rk_adjoint_ctl                  the adjoint sweep over ctl->sched[0 .. ctl->steps), read on the device. */
+int pnode_cnf_rk_gather_ctl(const pnode_cnf_ctl *d_ctl, const void *d_ubuf, const void *d_sol, void *d_out, int nout,
+                            int64_t n, int dtype, void *stream);
+int pnode_cnf_rk_adjoint_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_cnf_ctl *d_ctl,
+                             int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work,
+                             void *stream);
 
 /* Test hook: feeds `n` weighted error sums of squares to the device step controller one after the other (one thread, the
  * code path the attempt kernel's last block runs) -- so that its decisions can be compared with the host controller on

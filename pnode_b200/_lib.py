@@ -34,15 +34,20 @@ CTL_MAX_SPAN = 16
 CTL_MAX_LOG = 1024
 
 
+class Step(C.Structure):
+    _fields_ = [("t", C.c_double), ("h", C.c_double), ("out_slot", C.c_int32), ("in_slot", C.c_int32)]
+
+
 class CnfCtl(C.Structure):
     """include/pnode_b200.h: pnode_cnf_ctl (the device-resident step controller's state and attempt log)."""
     _fields_ = [("t", C.c_double), ("h", C.c_double), ("t_end", C.c_double), ("dt_span_cached", C.c_double),
                 ("span", C.c_double * CTL_MAX_SPAN), ("n_global", C.c_double), ("delta", C.c_double)] + \
                [(n, C.c_int32) for n in ("nspan", "order", "max_reject", "done", "cur", "kcur", "have_k", "steps",
                                          "attempts", "rejections", "prev_ok", "ctr", "cur_sol_index", "pending_slot",
-                                         "max_steps")] + \
+                                         "max_steps", "single", "prev_out_slot")] + \
                [("sumsq", C.c_double), ("epoch_next", C.c_uint64), ("log_t", C.c_double * CTL_MAX_LOG), ("log_h", C.c_double * CTL_MAX_LOG),
-                ("log_enorm", C.c_double * CTL_MAX_LOG), ("log_accepted", C.c_int32 * CTL_MAX_LOG)]
+                ("log_enorm", C.c_double * CTL_MAX_LOG), ("log_accepted", C.c_int32 * CTL_MAX_LOG),
+                ("sched", Step * CTL_MAX_LOG)]
 
 
 CONV_MAX_LAYERS = 8
@@ -68,10 +73,6 @@ class ConvBlockDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("nlayers", "dtype", "N", "H", "W", "reserved")] + \
                [("layer", ConvLayer * CONV_MAX_LAYERS), ("d_peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
                 ("epoch", C.c_uint64), ("global_pixels", C.c_int64)]
-
-
-class Step(C.Structure):
-    _fields_ = [("t", C.c_double), ("h", C.c_double), ("out_slot", C.c_int32), ("in_slot", C.c_int32)]
 
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -103,6 +104,9 @@ _SIGNATURES = {
     "pnode_cnf_rk_solve_ctl_dp": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _vp, _vp, _i64, _vp, _i64, _vp, _d, _d,
                                             _vp, _vp, _vp, _i, _i, _vp]),
     "pnode_cnf_ctl_probe": (C.c_int, [_vp, _vp, _i, _vp]),
+    "pnode_cnf_rk_gather_ctl": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i64, _i, _vp]),
+    "pnode_cnf_rk_adjoint_ctl": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp,
+                                           _vp]),
     "pnode_cnf_rk_adjoint_work_bytes": (_i64, [C.POINTER(CnfDesc)]),
     "pnode_cnf_rk_adjoint": (C.c_int, [C.POINTER(CnfDesc), C.POINTER(RKTableau), _i64, _vp, _i, _i, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),

@@ -306,7 +306,7 @@ __device__ inline void report(pnode_cnf_ctl &c, double sumsq) {
         c.rejections += 1;
         if (c.rejections > c.max_reject) c.done = 2;
     } else {
-        const double t_new = c.t + h;
+        const double t_old = c.t, t_new = c.t + h;
         h_next = matchstep(c, t_new, h, h_next);
         c.prev_ok = 1;
         c.rejections = 0;
@@ -317,6 +317,12 @@ __device__ inline void report(pnode_cnf_ctl &c, double sumsq) {
         int slot = -1;
         if (c.nspan > 0 && c.ctr < c.nspan && fabs(t_new - c.span[c.ctr]) <= SPAN_RELTOL * h + SPAN_ABSTOL) slot = c.ctr++;
         c.pending_slot = slot;
+        const int idx = c.steps - 1;  // this step, as the adjoint sweep will read it
+        if (idx < PNODE_CTL_MAX_LOG) {
+            c.sched[idx].t = t_old, c.sched[idx].h = h, c.sched[idx].out_slot = slot;
+            c.sched[idx].in_slot = c.single ? -1 : (idx == 0 ? 0 : c.prev_out_slot);
+        }
+        c.prev_out_slot = slot;
         c.cur ^= 1;       // the candidate becomes the state
         c.kcur ^= 1;      // and its last stage slope the carried-over one
         c.have_k = 1;
@@ -640,9 +646,11 @@ struct AccType<float> {
 template <typename T, int D, int H, int S, int LPT>
 __global__ void __launch_bounds__(CNF_ADJ_THREADS)
 cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
-                  const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
+                  const pnode_step *__restrict__ sched, const int nsteps_arg, const int last_slot,
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
-                  T *__restrict__ mu_out, CnfAdjWork *__restrict__ work, const PeerComm pc) {
+                  T *__restrict__ mu_out, CnfAdjWork *__restrict__ work, const PeerComm pc,
+                  const int *__restrict__ d_nsteps) {
+    const int nsteps = d_nsteps != nullptr ? *d_nsteps : nsteps_arg;  // device-resident schedule: the step count too
     typedef CnfAdjShape<T, D, H, LPT> Sh;
     typedef Pack<T> P;
     typedef typename P::V V;
@@ -979,6 +987,24 @@ cnf_rk_adj_kernel(const CnfPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
 // ---------------------------------------------------------------------------------------------------------------------
 // host dispatch
 
+// states at the output times of a solve that ran without the host: slot k < nout - 1 from the solution buffer (copied there
+// by the attempt that followed the hit), the last one from the current state buffer; NaN if the attempt budget ran out
+template <typename T>
+__global__ void cnf_gather_kernel(const pnode_cnf_ctl *__restrict__ c, const T *__restrict__ ubuf, const T *__restrict__ sol,
+                                  T *__restrict__ out, int nout, int64_t n) {
+    const int k = nout == 1 ? 0 : 1 + (int)blockIdx.y;  // nout == 1: single end time, out[0] is the final state
+    const bool last = k == nout - 1;
+    const bool finished = c->done == 1;
+    const T *src = last ? ubuf + (int64_t)c->cur * n : sol + (int64_t)k * n;
+    const T bad = (T)NAN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)k * n + i] = finished ? src[i] : bad;
+}
+
+__global__ void ctl_probe_kernel(pnode_cnf_ctl *c, const double *sumsq, int n) {
+    for (int i = 0; i < n && c->done == 0; ++i) ctl::report(*c, sumsq[i]);
+}
+
 static bool cnf_shape_ok(int dim, int hidden, int stages) {
     return dim == 6 && hidden == 60 && (stages == 4 || stages == 7 || stages == 1 || stages == 2 || stages == 3);
 }
@@ -1048,7 +1074,7 @@ template <typename T, int S, int LPT>
 static int launch_cnf_adjoint_lpt(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
                                   const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
                                   const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, const PeerComm &pc,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const int *d_nsteps) {
     auto kern = cnf_rk_adj_kernel<T, 6, 60, S, LPT>;
     constexpr size_t tiles = sizeof(CnfTile<T, 6, 60, LPT>) * CNF_ADJ_WARPS;
     constexpr size_t comb = sizeof(double) * CNF_ADJ_WARPS * CnfAdjShape<T, 6, 60, LPT>::NP;  // block combine reuses the tiles
@@ -1068,7 +1094,7 @@ static int launch_cnf_adjoint_lpt(const pnode_cnf_desc *c, const pnode_rk_tablea
     kern<<<grid, CNF_ADJ_THREADS, smem, st>>>(cnf_ptrs<T>(c), *tab, ntraj, d_sched, nsteps, last_slot,
                                               static_cast<const T *>(d_gout), static_cast<const T *>(d_ckpt),
                                               static_cast<T *>(d_lambda), static_cast<T *>(d_mu),
-                                              static_cast<CnfAdjWork *>(d_work), pc);
+                                              static_cast<CnfAdjWork *>(d_work), pc, d_nsteps);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1077,12 +1103,12 @@ template <typename T, int S>
 static int launch_cnf_adjoint(const pnode_cnf_desc *c, const pnode_rk_tableau *tab, int64_t ntraj,
                               const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
                               const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work, const PeerComm &pc,
-                              cudaStream_t st) {
+                              cudaStream_t st, const int *d_nsteps = nullptr) {
     if (cnf_small_batch<T>(ntraj))
         return launch_cnf_adjoint_lpt<T, S, CNF_SMALL_LPT>(c, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,
-                                                           d_lambda, d_mu, d_work, pc, st);
+                                                           d_lambda, d_mu, d_work, pc, st, d_nsteps);
     return launch_cnf_adjoint_lpt<T, S, 1>(c, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
-                                           pc, st);
+                                           pc, st, d_nsteps);
 }
 
 }  // namespace pnode
@@ -1147,10 +1173,6 @@ int pnode_cnf_rk_attempts_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau 
     PNODE_CNF_STAGES(X)
 #undef X
     PNODE_REQUIRE(false, "pnode_cnf_rk_attempts_ctl: no kernel for %d stages", tab->s);
-}
-
-__global__ void ctl_probe_kernel(pnode_cnf_ctl *c, const double *sumsq, int n) {
-    for (int i = 0; i < n && c->done == 0; ++i) ctl::report(*c, sumsq[i]);
 }
 
 // ---- the adaptive time loop as a CUDA graph with a device-driven WHILE node ---------------------------------------------
@@ -1220,6 +1242,46 @@ int build_loop_graph(const CnfLoopKey &k, CnfLoopGraph &out) {
     return 0;
 }
 }  // namespace
+
+int pnode_cnf_rk_gather_ctl(const pnode_cnf_ctl *d_ctl, const void *d_ubuf, const void *d_sol, void *d_out, int nout,
+                            int64_t n, int dtype, void *stream) {
+    PNODE_REQUIRE(d_ctl && d_ubuf && d_out && nout >= 1 && n > 0, "pnode_cnf_rk_gather_ctl: bad argument");
+    PNODE_REQUIRE(nout <= 2 || d_sol, "pnode_cnf_rk_gather_ctl: interior output times without the solution buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    if (dtype == PNODE_F32)
+        cnf_gather_kernel<float><<<dim3(grid, nout - 1 > 0 ? nout - 1 : 1), 256, 0, st>>>(
+            d_ctl, static_cast<const float *>(d_ubuf), static_cast<const float *>(d_sol), static_cast<float *>(d_out), nout, n);
+    else if (dtype == PNODE_F64)
+        cnf_gather_kernel<double><<<dim3(grid, nout - 1 > 0 ? nout - 1 : 1), 256, 0, st>>>(
+            d_ctl, static_cast<const double *>(d_ubuf), static_cast<const double *>(d_sol), static_cast<double *>(d_out), nout,
+            n);
+    else
+        PNODE_REQUIRE(false, "pnode_cnf_rk_gather_ctl: unsupported dtype %d", dtype);
+    PNODE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pnode_cnf_rk_adjoint_ctl(const pnode_cnf_desc *cnf, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_cnf_ctl *d_ctl,
+                             int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu, void *d_work,
+                             void *stream) {
+    PNODE_REQUIRE(cnf && tab && d_ctl && d_work && d_ckpt, "pnode_cnf_rk_adjoint_ctl: null argument");
+    PNODE_REQUIRE(cnf_shape_ok(cnf->dim, cnf->hidden, tab->s), "pnode_cnf_rk_adjoint_ctl: unsupported shape D=%d H=%d s=%d",
+                  cnf->dim, cnf->hidden, tab->s);
+    const PeerComm pc{nullptr, 0, 1, 0ull};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(SS)                                                                                                            \
+    if (tab->s == SS) {                                                                                                  \
+        if (cnf->dtype == PNODE_F32)                                                                                     \
+            return launch_cnf_adjoint<float, SS>(cnf, tab, ntraj, d_ctl->sched, 0, last_slot, d_gout, d_ckpt, d_lambda,  \
+                                                 d_mu, d_work, pc, st, &d_ctl->steps);                                   \
+        return launch_cnf_adjoint<double, SS>(cnf, tab, ntraj, d_ctl->sched, 0, last_slot, d_gout, d_ckpt, d_lambda,     \
+                                              d_mu, d_work, pc, st, &d_ctl->steps);                                      \
+    }
+    PNODE_CNF_STAGES(X)
+#undef X
+    PNODE_REQUIRE(false, "pnode_cnf_rk_adjoint_ctl: no kernel for %d stages", tab->s);
+}
 
 int pnode_cnf_ctl_probe(pnode_cnf_ctl *d_ctl, const double *d_sumsq, int n, void *stream) {
     PNODE_REQUIRE(d_ctl && d_sumsq && n >= 0, "pnode_cnf_ctl_probe: bad argument");

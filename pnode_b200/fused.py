@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import _lib
 from .controller import fixed_schedule
 from .device import _stream, dtype_code
+from .errors import Error
 
 _STEP_DTYPE = np.dtype([("t", "<f8"), ("h", "<f8"), ("out_slot", "<i4"), ("in_slot", "<i4")])
 assert _STEP_DTYPE.itemsize == C.sizeof(_lib.Step)
@@ -350,6 +351,8 @@ class FusedCnfRK:
 
     def forward(self, u0, loop, atol, rtol, save, comm=None):
         """u0 flat [B*(D+1)].  `loop` is a controller.TimeLoop.  Returns (sol dict, state)."""
+        if loop.adaptive and torch.cuda.is_current_stream_capturing():
+            return self._forward_captured(u0, loop, atol, rtol, save, comm)
         peer = getattr(comm, "peer", None) if comm is not None else None
         sharded_ok = comm is None or (peer is not None and self.device_loop)  # in-kernel all-reduce of the error norm
         if self.device_controller and loop.adaptive and sharded_ok and loop.step_list is None and \
@@ -471,8 +474,9 @@ class FusedCnfRK:
         ctl.nspan, ctl.order, ctl.max_reject = nspan, int(loop.order), int(loop.max_reject)
         ctl.done = 1 if loop.done else 0
         ctl.prev_ok, ctl.ctr, ctl.cur_sol_index, ctl.pending_slot = 1, 1, 1, -1
-        ctl.max_steps = cap
+        ctl.max_steps, ctl.single, ctl.prev_out_slot = cap, 0, -1
         host_view = self._ctl_view
+        nread = _lib.CnfCtl.sched.offset  # the host reads state + attempt log; the device-side schedule stays on the device
         head = _lib.CnfCtl.log_t.offset  # everything before the log is the controller's state
         stream = torch.cuda.current_stream()
 
@@ -497,7 +501,7 @@ class FusedCnfRK:
             else:
                 _lib.check(self.lib.pnode_cnf_rk_attempts_ctl(*args, self.CTL_BATCH, stream.cuda_stream))
                 self.launches += self.CTL_BATCH
-            self._ctl_host.copy_(self._ctl_dev, non_blocking=True)
+            self._ctl_host[:nread].copy_(self._ctl_dev[:nread], non_blocking=True)
             stream.synchronize()  # the one host read per solve (per CTL_BATCH attempts without the device loop)
             now = c.attempts
             if peer is not None:
@@ -542,9 +546,87 @@ class FusedCnfRK:
             state["lease"] = None  # nothing will run an adjoint on this solve: the buffers go back at once
         return u, sols, state
 
+    CAPTURE_ATTEMPTS = 24  # -pnode_capture_attempts: attempt budget of an adaptive solve recorded into a CUDA graph
+
+    def _forward_captured(self, u0, loop, atol, rtol, save, comm):
+        """An adaptive solve while the caller records a CUDA graph (torch.cuda.graph around the training step): nothing may
+        read the device, so a fixed budget of attempts is recorded (those after the end time return at once), the states at
+        the output times are gathered on the device, and the adjoint sweep will take its schedule from the control block
+        (pnode_cnf_rk_adjoint_ctl).  A replay whose solve needs more attempts than the budget returns NaN, not a wrong
+        answer.  The host TimeLoop is not advanced: `ode._loop` statistics describe eager solves only."""
+        if comm is not None or loop.step_list is not None or self.scheme.bembed is None or loop.span is None or \
+                len(loop.span) > _lib.CTL_MAX_SPAN or not self.device_controller:
+            raise Error(-60, "this adaptive solve cannot be recorded into a CUDA graph (needs the device step controller, "
+                             "a single rank, a scalar step size and 2..%d output times)" % _lib.CTL_MAX_SPAN)
+        sp = self.spec
+        ntraj, n, nspan = sp.batch, u0.numel(), len(loop.span)
+        nb = int(self.CAPTURE_ATTEMPTS)
+        if not (1 <= nb <= _lib.CTL_MAX_LOG):
+            raise Error(-60, "-pnode_capture_attempts must be in 1..%d" % _lib.CTL_MAX_LOG)
+        desc = self._desc()
+        per_step = self.s_eff * sp.dim * ntraj
+        dev = self.device
+        ubuf = torch.empty(2, n, dtype=self.dtype, device=dev)
+        kbuf = torch.empty(2, n, dtype=self.dtype, device=dev) if self.scheme.fsal else None
+        sol = torch.empty(nspan, n, dtype=self.dtype, device=dev)
+        ckpt = torch.empty(nb * per_step, dtype=self.dtype, device=dev) if save else None
+        ebuf = torch.empty(ntraj * sp.dim, dtype=self.dtype, device=dev)
+        ebuf.copy_(self._e_keepalive.reshape(-1))
+        desc.d_e = ebuf.data_ptr()
+        ctl = _lib.CnfCtl()
+        ctl.t, ctl.h, ctl.t_end, ctl.dt_span_cached = loop.t, loop.h, loop.t_end, 0.0
+        for i in range(nspan):
+            ctl.span[i] = loop.span[i]
+        ctl.n_global, ctl.delta = float(n), loop.delta
+        ctl.nspan, ctl.order, ctl.max_reject = nspan, int(loop.order), int(loop.max_reject)
+        ctl.prev_ok, ctl.ctr, ctl.cur_sol_index, ctl.pending_slot = 1, 1, 1, -1
+        ctl.max_steps, ctl.single, ctl.prev_out_slot = nb if save else 0, 0, -1
+        head = _lib.CnfCtl.log_t.offset
+        pinned = torch.empty(head, dtype=torch.uint8).pin_memory()  # re-read by the copy node at every replay
+        C.memmove(pinned.data_ptr(), C.addressof(ctl), head)
+        ctl_dev = torch.empty(C.sizeof(_lib.CnfCtl), dtype=torch.uint8, device=dev)
+        ctl_dev[:head].copy_(pinned, non_blocking=True)
+        ubuf[0].copy_(u0)
+        stream = torch.cuda.current_stream().cuda_stream
+        left = nb
+        while left > 0:
+            k = min(left, 64)
+            _lib.check(self.lib.pnode_cnf_rk_attempts_ctl(
+                C.byref(desc), C.byref(self.tab), ubuf.data_ptr(), None if kbuf is None else kbuf.data_ptr(), ntraj,
+                None if ckpt is None else ckpt.data_ptr(), per_step, sol.data_ptr(), float(atol), float(rtol),
+                ctl_dev.data_ptr(), self._wrms_work.data_ptr(), k, stream))
+            left -= k
+        self.launches += nb
+        out = torch.empty(nspan, n, dtype=self.dtype, device=dev)
+        out[0].copy_(u0)
+        _lib.check(self.lib.pnode_cnf_rk_gather_ctl(ctl_dev.data_ptr(), ubuf.data_ptr(), sol.data_ptr(), out.data_ptr(), nspan, n,
+                                                    self.code, stream))
+        sols = {k: out[k] for k in range(nspan)}
+        state = {"captured": True, "ctl": ctl_dev, "ckpt": ckpt, "ntraj": ntraj, "desc_keep": desc, "steps": [],
+                 "keep": (pinned, ubuf, kbuf, sol, ebuf, out)}
+        return out[nspan - 1], sols, state
+
+    def _adjoint_captured(self, gout, state):
+        sp = self.spec
+        ntraj = state["ntraj"]
+        npar = 2 * sp.hidden * sp.dim + 4 * sp.hidden + 4 * sp.dim
+        lam = torch.empty(ntraj * (sp.dim + 1), dtype=self.dtype, device=self.device)
+        mu = torch.empty(npar, dtype=self.dtype, device=self.device)
+        desc = state["desc_keep"]
+        if "adj_work" not in state:  # owned by the recorded solve (allocated from the graph's pool when recording)
+            state["adj_work"] = torch.zeros(int(self.lib.pnode_cnf_rk_adjoint_work_bytes(C.byref(desc))), dtype=torch.uint8,
+                                            device=self.device)
+        _lib.check(self.lib.pnode_cnf_rk_adjoint_ctl(C.byref(desc), C.byref(self.tab), ntraj, state["ctl"].data_ptr(),
+                                                     gout.shape[0] - 1, gout.data_ptr(), state["ckpt"].data_ptr(),
+                                                     lam.data_ptr(), mu.data_ptr(), state["adj_work"].data_ptr(), _stream()))
+        self.launches += 1
+        return lam, mu, False
+
     def adjoint(self, gout, state, single, nadj=None, comm=None):
         """gout contiguous [T, B*(D+1)].  `nadj`: run only the last nadj steps (the reference's one-element-t rule).
         Returns (lambda, mu, reduced)."""
+        if state.get("captured"):
+            return self._adjoint_captured(gout, state)
         sp = self.spec
         steps, ntraj = state["steps"], state["ntraj"]
         first = 0 if nadj is None else max(len(steps) - nadj, 0)

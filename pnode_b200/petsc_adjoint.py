@@ -283,6 +283,7 @@ class ODEPetsc(object):
             off = ("0", "false", "no")
             self._fused.device_controller = Options().getString("pnode_device_controller", "1") not in off
             self._fused.device_loop = Options().getString("pnode_device_loop", "1") not in off
+            self._fused.CAPTURE_ATTEMPTS = Options().getInt("pnode_capture_attempts", type(self._fused).CAPTURE_ATTEMPTS)
         return self._fused_kind, self._fused
 
     # ------------------------------------------------------------------------------------------------------------
