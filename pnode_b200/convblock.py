@@ -199,6 +199,11 @@ class ConvBlockCallbacks(Callbacks):
         if self._comm is not None:
             if not self._comm.enable_peer_reduce():
                 raise Error(-41, "batch-sharded conv ODE blocks need NVLink peer (symmetric) memory for the BatchNorm statistics")
+            if not self._comm.same_on_all_ranks(int(d.N)):
+                # the in-kernel statistics exchanges are matched one to one across the ranks; a rank with a bigger shard can
+                # run out of its activation budget and re-evaluate (more exchanges) where the others do not
+                raise Error(-42, "batch-sharded conv ODE blocks need shards of equal size on every rank (this rank holds %d "
+                                 "samples)" % int(d.N))
             d.d_peer_bufs = self._comm.peer["ptrs_dev"]
             d.rank, d.world = self._comm.rank, self._comm.world
             d.global_pixels = self._comm.global_count(int(d.N) * int(d.H) * int(d.W))

@@ -96,6 +96,18 @@ class BatchComm:
     def allreduce_scalar(self, tensor):
         return self.allreduce_sum(tensor)
 
+    def same_on_all_ranks(self, n_local):
+        """True when every rank holds the same count (one MAX all-reduce of (n, -n), remembered per n)."""
+        if self.world == 1:
+            return True
+        key = ("same", n_local)
+        if key not in self._count_cache:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else "cpu"
+            c = torch.tensor([n_local, -n_local], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.MAX, group=self.group)
+            self._count_cache[key] = int(c[0].item()) == -int(c[1].item())
+        return self._count_cache[key]
+
     def global_count(self, n_local):
         """Global state length N of the WRMS norm (ranks may hold ragged shards)."""
         if self.world == 1:

@@ -77,6 +77,11 @@ def _worker(rank, world, port, ragged, q):
             if not torch.allclose(a, b, rtol=1e-11, atol=1e-13):
                 ok = False
                 msgs.append("mu differs")
+        # shard sizes: the ragged split (26 / 25 samples) is noticed by every rank, the even one passes on every rank
+        local = shard_batch(u0, rank, world).shape[0]
+        if comm.same_on_all_ranks(local) != (not ragged):
+            ok = False
+            msgs.append("same_on_all_ranks(%d) is wrong" % local)
         q.put((rank, ok, msgs[:3], comm.collectives))
     finally:
         dist.destroy_process_group()
