@@ -142,7 +142,7 @@ def run_config(name, build, args, peaks, world=1, comm=None):
                                      "tf32 tcgen05 (3xTF32)", "executed_tops": tops,
                                      "peak_tops": ratio * peaks["bf16_tensor"], "frac": tops / (ratio * peaks["bf16_tensor"]),
                                      "peak_note": "%.1fx the measured bf16 peak (nominal type ratio)" % ratio}
-    if world == 1 and not getattr(args, "no_graph", False):
+    if world == 1 and ode.path != "generic" and not getattr(args, "no_graph", False):
         # fixed-step solves launch without reading the device, and the adaptive FFJORD solve decides on the device (recorded
         # as a fixed budget of attempts): the whole pass replays from a CUDA graph
         try:
@@ -214,17 +214,20 @@ def cfg2(dtype="f32", ntraj=1 << 20):
     return build
 
 
-def _cnf(B, dtype):
+def _cnf(B, dtype, D=6, hidden=(60,), fixed_rk4=None):
+    """FFJORD tabular CNF.  Default: the POWER shape of BASELINE config 3 (fused kernels, dopri5 adaptive).  Other shapes --
+    e.g. the reference's own usage line, train_tabular.py:5: miniboone, D=43, two hidden layers of 860, RK4 h=0.25 -- are
+    outside the fused recognisers and show what the generic stage loop does with them."""
     from _workloads import CNFFunc, cnf_to
 
     def build():
         td = torch.float32 if dtype == "f32" else torch.float64
         g = torch.Generator().manual_seed(2 + SEED_OFFSET)
         mk = lambda b: dict(
-            func=CNFFunc(b, 6, (60,), dtype=td),
-            u0=torch.cat((torch.randn(b, 6, generator=g, dtype=torch.float64).view(-1),
+            func=CNFFunc(b, D, hidden, dtype=td),
+            u0=torch.cat((torch.randn(b, D, generator=g, dtype=torch.float64).view(-1),
                           torch.zeros(b, dtype=torch.float64))).to(td),
-            target=torch.randn(2, b * 7, generator=g, dtype=torch.float64).to(td))
+            target=torch.randn(2, b * (D + 1), generator=g, dtype=torch.float64).to(td))
         full = mk(B)
         t = torch.tensor([0.0, 1.0], dtype=torch.float64)
         bs = min(B, 1 << 14)
@@ -234,6 +237,18 @@ def _cnf(B, dtype):
             return dict(funcs=[s["func"]], u0=s["u0"], t=t, target=s["target"], kw=dict(method="dopri5"), batch=bs,
                         desc="%d of %d samples" % (bs, B))
 
+        if fixed_rk4 is not None:
+            dims = (D,) + tuple(hidden) + (D,)
+            f_f = 2 * 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))  # network + Hutchinson VJP
+            return dict(desc="FFJORD tabular CNF D=%d hidden %s, B=%d, RK4 h=%g, t=[0,1], Hutchinson trace, %s (outside the "
+                             "fused recognisers)" % (D, "x".join(map(str, hidden)), B, fixed_rk4, dtype), dtype=dtype,
+                        argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"], funcs=[full["func"]], u0=full["u0"],
+                        t=t, target=full["target"], kw=dict(method="rk4"), step=fixed_rk4, batch=B, flops_per_unit=16 * f_f,
+                        bytes_per_unit=(2 * 4 + 2) * (D + 1) * (4 if dtype == "f32" else 8),
+                        pipe="fp32_fma" if dtype == "f32" else "fp64_fma", each_call_setup=True, to_dev=cnf_to,
+                        cpu_sample=lambda: dict(funcs=[mk(min(B, 256))["func"]], u0=mk(min(B, 256))["u0"], t=t,
+                                                target=mk(min(B, 256))["target"], kw=dict(method="rk4"), batch=min(B, 256),
+                                                desc="%d of %d samples" % (min(B, 256), B)))
         return dict(desc="cfg3 FFJORD tabular CNF, POWER-shaped D=6 H=60, B=%d, dopri5 adaptive rtol=atol=1e-4, h0=0.05, "
                          "t=[0,1], Hutchinson trace, %s" % (B, dtype), dtype=dtype, argv=["-ts_trajectory_type", "memory"],
                     funcs=[full["func"]], u0=full["u0"], t=t, target=full["target"], kw=dict(method="dopri5"), step=0.05,
@@ -329,7 +344,8 @@ def burgers(N=1024, B=200, dtype="f64"):
 
 def config_table():
     return {"1": ("cfg1", cfg1), "2S": ("cfg2-f32", cfg2("f32")), "2D": ("cfg2-f64", cfg2("f64")), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
-            "3D": ("cfg3-f64", _cnf(1000, "f64")), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
+            "3D": ("cfg3-f64", _cnf(1000, "f64")),
+            "3M": ("ffjord-miniboone", _cnf(1000, "f32", 43, (860, 860), 0.25)), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)),
             "5": ("cfg5", cfg5()), "5S": ("cfg5-f32", cfg5(dtype="f32")), "5L": ("cfg5-l2", cfg5(ark="l2")),
             "B": ("burgers", burgers())}
