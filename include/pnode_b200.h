@@ -162,6 +162,19 @@ int pnode_mlp_rk_adjoint(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab,
                          const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
                          void *d_lambda, void *d_mu, void *d_work, void *stream);
 
+/* Bounded checkpoint storage for the fused sweeps: [PETSc] -ts_trajectory_solution_only 1 (TSTrajectory "memory" keeping
+ * the step solutions only; the reference reaches it through ts.setFromOptions(), petsc_adjoint.py:775).
+ * The forward sweep keeps u_n per step -- d_usteps [nsteps, dim, ntraj], 1/s of the stage checkpoints -- and the adjoint
+ * sweep recomputes the s stage values of a step from u_n with the forward sweep's own arithmetic before it runs the
+ * step's adjoint stages (same results as the stage-checkpoint sweeps, bit for bit).  d_peer_bufs NULL / world 1: single
+ * GPU; otherwise as pnode_mlp_rk_adjoint_dp. */
+int pnode_mlp_rk_forward_so(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, void *d_sol, void *d_usteps, void *stream);
+int pnode_mlp_rk_adjoint_so(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
+                            const void *d_usteps, void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs,
+                            int rank, int world, uint64_t epoch, void *stream);
+
 /* ----------------------------------------------------------------------------------------------------------------
  * Fused path for FFJORD continuous-normalising-flow right-hand sides (ffjord-pnode/lib/layers/odefunc.py:322-385 with
  * an ODEnet of two ConcatSquashLinear layers + softplus, diffeq_layers/basic.py:76-86):

@@ -366,7 +366,8 @@ constexpr int FWD_THREADS = 128;
 template <typename T, int D, int H, int S, int PHI>
 __global__ void __launch_bounds__(FWD_THREADS, Cfg<T>::FWD_MIN_CTAS)
 mlp_rk_fwd_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u0, const int64_t ntraj,
-                  const pnode_step *__restrict__ sched, const int nsteps, T *__restrict__ sol, T *__restrict__ ckpt) {
+                  const pnode_step *__restrict__ sched, const int nsteps, T *__restrict__ sol, T *__restrict__ ckpt,
+                  const int solution_only) {
     constexpr int TPT = Cfg<T>::TPT;
     __shared__ Unit<T, D> sW[H];
     __shared__ T sB2[D];
@@ -406,12 +407,14 @@ mlp_rk_fwd_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const T *__res
 #pragma unroll
                         for (int d = 0; d < D; ++d) Y[q][d] = fma(ha, K[j][q][d], Y[q][d]);
                 }
-                if (ckpt != nullptr) {
+                // -ts_trajectory_solution_only: keep u_n alone ([step][dim][traj]); the adjoint sweep recomputes the stages
+                if (ckpt != nullptr && (!solution_only || i == 0)) {
+                    const int64_t row = solution_only ? (int64_t)n : (int64_t)n * S + i;
 #pragma unroll
                     for (int q = 0; q < TPT; ++q)
                         if (valid[q]) {
 #pragma unroll
-                            for (int d = 0; d < D; ++d) ckpt[(((int64_t)n * S + i) * D + d) * ntraj + traj[q]] = Y[q][d];
+                            for (int d = 0; d < D; ++d) ckpt[(row * D + d) * ntraj + traj[q]] = Y[q][d];
                         }
                 }
                 if (i == 0 && tab.fsal && n > 0) {
@@ -499,7 +502,9 @@ template <typename T, int NP>
 __device__ void adj_finish(double *blk, int nwarps, AdjWork *__restrict__ work, T *__restrict__ mu_out, const PeerComm &pc,
                            bool *is_last);
 
-template <typename T, int D, int H, int S, int PHI>
+// SO: the forward sweep kept u_n per step only (-ts_trajectory_solution_only 1, [step][dim][traj]); the stage values of a
+// step are recomputed from u_n with the forward sweep's own arithmetic before its adjoint stages run.
+template <typename T, int D, int H, int S, int PHI, bool SO>
 __global__ void __launch_bounds__(ADJ_THREADS, Cfg<T>::ADJ_MIN_CTAS)
 mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
@@ -553,11 +558,12 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
         const int s_top = (tab.fsal ? S - 2 : S - 1);
         T Ynext[TPT][D];
         auto fetch_Y = [&](int nn, int ii) {
+            const int64_t row = SO ? (int64_t)nn : (int64_t)nn * S + ii;
 #pragma unroll
             for (int q = 0; q < TPT; ++q)
 #pragma unroll
                 for (int d = 0; d < D; ++d)
-                    Ynext[q][d] = (valid[q] && nn >= 0) ? ckpt[(((int64_t)nn * S + ii) * D + d) * ntraj + traj[q]] : T(0);
+                    Ynext[q][d] = (valid[q] && nn >= 0) ? ckpt[(row * D + d) * ntraj + traj[q]] : T(0);
         };
         fetch_Y(nsteps - 1, s_top);
 
@@ -565,6 +571,36 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
             const double h = sched[n].h;
             const int in_slot = sched[n].in_slot;
             T ls[S][TPT][D];
+            T Yst[SO ? S : 1][TPT][D];
+            if (SO) {
+                T yn[TPT][D], K[S][TPT][D];
+#pragma unroll
+                for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) yn[q][d] = Ynext[q][d];
+                fetch_Y(n - 1, 0);  // u_{n-1} is on its way while this step's stages are recomputed
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    T Yi[TPT][D];
+#pragma unroll
+                    for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) Yi[q][d] = yn[q][d];
+#pragma unroll
+                    for (int j = 0; j < i; ++j) {
+                        const T ha = (T)(h * tab.a[i][j]);
+#pragma unroll
+                        for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                            for (int d = 0; d < D; ++d) Yi[q][d] = fma(ha, K[j][q][d], Yi[q][d]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < TPT; ++q)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) Yst[SO ? i : 0][q][d] = Yi[q][d];
+                    if (i < S - 1) mlp_eval<T, D, H, PHI, TPT>(sW, sB2, sTab, w.slot, Yi, K[i]);
+                }
+            }
             // the stage loop is deliberately NOT unrolled (ls becomes a small local array, touched a few times per stage):
             // the loop body stays resident in the instruction cache; the chunk loop IS unrolled so that the
             // parameter-gradient accumulators stay in registers
@@ -603,7 +639,7 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                 for (int q = 0; q < TPT; ++q) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                        Y[q][d] = Ynext[q][d];
+                        Y[q][d] = SO ? Yst[SO ? i : 0][q][d] : Ynext[q][d];
                         v[q][d] = valid[q] ? v[q][d] * cstep : T(0);
                         dx[q][d] = T(0);
                     }
@@ -615,7 +651,9 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                         accB2[d] += (double)v[q][d];
                     }
                 }
-                if (i > 0) fetch_Y(n, i - 1); else fetch_Y(n - 1, s_top);
+                if (!SO) {
+                    if (i > 0) fetch_Y(n, i - 1); else fetch_Y(n - 1, s_top);
+                }
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int j0 = c * JH;
@@ -1108,12 +1146,12 @@ static int upload_weights(const pnode_mlp_desc *m, int *slot_out, cudaStream_t s
 
 template <typename T, int D, int H, int S, int PHI>
 static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
-                      const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, cudaStream_t st) {
+                      const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, int so, cudaStream_t st) {
     int slot = 0;
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
                  static_cast<const T *>(m->d_b2), slot};
-    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled()) {
+    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled() && !so) {  // bounded storage is for large batches
         const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
         const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
         mlp_rk_fwd_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
@@ -1133,12 +1171,12 @@ static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, cons
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     kern<<<grid, FWD_THREADS, 0, st>>>(w, *tab, static_cast<const T *>(d_u0), ntraj, d_sched, nsteps,
-                                       static_cast<T *>(d_sol), static_cast<T *>(d_ckpt));
+                                       static_cast<T *>(d_sol), static_cast<T *>(d_ckpt), so);
     PNODE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <typename T, int D, int H, int S, int PHI>
+template <typename T, int D, int H, int S, int PHI, bool SO = false>
 static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_step *d_sched,
                       int nsteps, int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu,
                       void *d_work, const PeerComm &pc, cudaStream_t st) {
@@ -1146,7 +1184,7 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
                  static_cast<const T *>(m->d_b2), slot};
-    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled()) {
+    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled() && !SO) {
         const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
         int64_t cap = (int64_t)sm_count() * 4;
         if (cap > ADJ_MAX_BLOCKS) cap = ADJ_MAX_BLOCKS;
@@ -1157,7 +1195,7 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
         PNODE_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    auto kern = mlp_rk_adj_kernel<T, D, H, S, PHI>;
+    auto kern = mlp_rk_adj_kernel<T, D, H, S, PHI, SO>;
     const size_t smem = adj_smem_bytes<T, D, H>();
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
@@ -1189,29 +1227,29 @@ static bool shape_ok(int dim, int hidden, int phi, int stages) {
 
 template <typename T>
 static int dispatch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
-                        const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, cudaStream_t st) {
+                        const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, int so, cudaStream_t st) {
 #define X(SS)                                                                                                     \
     if (tab->s == SS) {                                                                                           \
         if (m->phi == 1)                                                                                          \
-            return launch_fwd<T, 2, 50, SS, 1>(m, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, st);          \
-        return launch_fwd<T, 2, 50, SS, 0>(m, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, st);              \
+            return launch_fwd<T, 2, 50, SS, 1>(m, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);      \
+        return launch_fwd<T, 2, 50, SS, 0>(m, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);          \
     }
     PNODE_FOR_STAGES(X)
 #undef X
     PNODE_REQUIRE(false, "pnode_mlp_rk_forward: no kernel for %d stages", tab->s);
 }
 
-template <typename T>
+template <typename T, bool SO>
 static int dispatch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_step *d_sched,
                         int nsteps, int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu,
                         void *d_work, const PeerComm &pc, cudaStream_t st) {
 #define X(SS)                                                                                                     \
     if (tab->s == SS) {                                                                                           \
         if (m->phi == 1)                                                                                          \
-            return launch_adj<T, 2, 50, SS, 1>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,         \
+            return launch_adj<T, 2, 50, SS, 1, SO>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,     \
+                                                   d_lambda, d_mu, d_work, pc, st);                               \
+        return launch_adj<T, 2, 50, SS, 0, SO>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,         \
                                                d_lambda, d_mu, d_work, pc, st);                                   \
-        return launch_adj<T, 2, 50, SS, 0>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda,   \
-                                           d_mu, d_work, pc, st);                                                 \
     }
     PNODE_FOR_STAGES(X)
 #undef X
@@ -1238,18 +1276,30 @@ int pnode_mlp_rk_supported(int dim, int hidden, int phi, int dtype, int stages) 
     return (dtype == PNODE_F32 || dtype == PNODE_F64) && shape_ok(dim, hidden, phi, stages) ? 1 : 0;
 }
 
-int pnode_mlp_rk_forward(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
-                         const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, void *stream) {
+static int mlp_rk_forward_any(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
+                              const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, int so, void *stream) {
     PNODE_REQUIRE(mlp && tab && d_sched, "pnode_mlp_rk_forward: null argument");
     PNODE_REQUIRE(shape_ok(mlp->dim, mlp->hidden, mlp->phi, tab->s),
                   "pnode_mlp_rk_forward: unsupported shape dim=%d hidden=%d phi=%d stages=%d", mlp->dim, mlp->hidden,
                   mlp->phi, tab->s);
     if (ntraj == 0 || nsteps == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mlp->dtype == PNODE_F32) return dispatch_fwd<float>(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, st);
+    if (mlp->dtype == PNODE_F32)
+        return dispatch_fwd<float>(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);
     if (mlp->dtype == PNODE_F64)
-        return dispatch_fwd<double>(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, st);
+        return dispatch_fwd<double>(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);
     PNODE_REQUIRE(false, "pnode_mlp_rk_forward: unsupported dtype %d", mlp->dtype);
+}
+
+int pnode_mlp_rk_forward(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
+                         const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, void *stream) {
+    return mlp_rk_forward_any(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, 0, stream);
+}
+
+int pnode_mlp_rk_forward_so(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, void *d_sol, void *d_usteps, void *stream) {
+    PNODE_REQUIRE(d_usteps != nullptr || nsteps == 0, "pnode_mlp_rk_forward_so: solution checkpoints missing");
+    return mlp_rk_forward_any(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_usteps, 1, stream);
 }
 
 int64_t pnode_mlp_rk_adjoint_work_bytes(const pnode_mlp_desc *mlp) {
@@ -1257,10 +1307,10 @@ int64_t pnode_mlp_rk_adjoint_work_bytes(const pnode_mlp_desc *mlp) {
     return 64 + (int64_t)ADJ_MAX_BLOCKS * np * (int64_t)sizeof(double);
 }
 
-int pnode_mlp_rk_adjoint_dp(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
-                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
-                            void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
-                            uint64_t epoch, void *stream) {
+static int mlp_rk_adjoint_any(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                              const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                              void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                              uint64_t epoch, bool so, void *stream) {
     PNODE_REQUIRE(mlp && tab && d_sched && d_work, "pnode_mlp_rk_adjoint: null argument");
     PNODE_REQUIRE(shape_ok(mlp->dim, mlp->hidden, mlp->phi, tab->s),
                   "pnode_mlp_rk_adjoint: unsupported shape dim=%d hidden=%d phi=%d stages=%d", mlp->dim, mlp->hidden,
@@ -1270,13 +1320,31 @@ int pnode_mlp_rk_adjoint_dp(const pnode_mlp_desc *mlp, const pnode_rk_tableau *t
                   "pnode_mlp_rk_adjoint_dp: bad rank/world/epoch");
     PeerComm pc{reinterpret_cast<const unsigned long long *>(d_peer_bufs), rank, world, (unsigned long long)epoch};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mlp->dtype == PNODE_F32)
-        return dispatch_adj<float>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
-                                   pc, st);
-    if (mlp->dtype == PNODE_F64)
-        return dispatch_adj<double>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu,
-                                    d_work, pc, st);
+#define PNODE_ADJ_GO(TT)                                                                                               \
+    return so ? dispatch_adj<TT, true>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu,    \
+                                       d_work, pc, st)                                                                 \
+              : dispatch_adj<TT, false>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu,   \
+                                        d_work, pc, st)
+    if (mlp->dtype == PNODE_F32) PNODE_ADJ_GO(float);
+    if (mlp->dtype == PNODE_F64) PNODE_ADJ_GO(double);
+#undef PNODE_ADJ_GO
     PNODE_REQUIRE(false, "pnode_mlp_rk_adjoint: unsupported dtype %d", mlp->dtype);
+}
+
+int pnode_mlp_rk_adjoint_dp(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout, const void *d_ckpt,
+                            void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs, int rank, int world,
+                            uint64_t epoch, void *stream) {
+    return mlp_rk_adjoint_any(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
+                              d_peer_bufs, rank, world, epoch, false, stream);
+}
+
+int pnode_mlp_rk_adjoint_so(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
+                            const pnode_step *d_sched, int nsteps, int last_slot, const void *d_gout,
+                            const void *d_usteps, void *d_lambda, void *d_mu, void *d_work, const uint64_t *d_peer_bufs,
+                            int rank, int world, uint64_t epoch, void *stream) {
+    return mlp_rk_adjoint_any(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_usteps, d_lambda, d_mu, d_work,
+                              d_peer_bufs, rank, world, epoch, true, stream);
 }
 
 int pnode_mlp_rk_adjoint(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,

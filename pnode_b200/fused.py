@@ -101,6 +101,9 @@ class FusedMlpRK:
         self._sched_cache = {}
         self._work = None
         self.launches = 0
+        # -ts_trajectory_solution_only 1: keep u_n per step ([nsteps, dim, ntraj]) instead of the s stage values; the
+        # adjoint sweep recomputes the stages (pnode_mlp_rk_forward_so / _adjoint_so)
+        self.solution_only = False
 
     @staticmethod
     def supported(spec, scheme, dtype):
@@ -149,14 +152,16 @@ class FusedMlpRK:
         if T > 1:
             sol[0].copy_(u0)
         ckpt = None
+        so = bool(self.solution_only and save)
         if save:
-            ckpt = torch.empty((max(nsteps, 1), self.scheme.s, sp.dim, ntraj), dtype=self.dtype, device=self.device)
+            shape = (max(nsteps, 1), sp.dim, ntraj) if so else (max(nsteps, 1), self.scheme.s, sp.dim, ntraj)
+            ckpt = torch.empty(shape, dtype=self.dtype, device=self.device)
         if nsteps == 0:
             sol[-1].copy_(u0)
         desc = self._desc()
-        _lib.check(self.lib.pnode_mlp_rk_forward(C.byref(desc), C.byref(self.tab), u0.data_ptr(), ntraj,
-                                                 sched.data_ptr(), nsteps, sol.data_ptr(),
-                                                 None if ckpt is None else ckpt.data_ptr(), _stream()))
+        fwd = self.lib.pnode_mlp_rk_forward_so if so else self.lib.pnode_mlp_rk_forward
+        _lib.check(fwd(C.byref(desc), C.byref(self.tab), u0.data_ptr(), ntraj, sched.data_ptr(), nsteps, sol.data_ptr(),
+                       None if ckpt is None else ckpt.data_ptr(), _stream()))
         self.launches += 1
         return sol, ckpt, (sched, nsteps, loop)
 
@@ -178,7 +183,13 @@ class FusedMlpRK:
             mu.zero_()
             return lam, mu, False
         peer = getattr(comm, "peer", None) if comm is not None else None
-        if peer is not None:
+        if ckpt.dim() == 3:  # solution checkpoints ([nsteps, dim, ntraj]): the sweep recomputes the stages
+            _lib.check(self.lib.pnode_mlp_rk_adjoint_so(
+                C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps, T - 1, gout.data_ptr(), ckpt.data_ptr(),
+                lam.data_ptr(), mu.data_ptr(), self._work.data_ptr(), None if peer is None else peer["ptrs_dev"],
+                comm.rank if peer is not None else 0, comm.world if peer is not None else 1,
+                comm.next_epoch() if peer is not None else 0, _stream()))
+        elif peer is not None:
             _lib.check(self.lib.pnode_mlp_rk_adjoint_dp(C.byref(desc), C.byref(self.tab), ntraj, sched.data_ptr(), nsteps,
                                                         T - 1, gout.data_ptr(), ckpt.data_ptr(), lam.data_ptr(),
                                                         mu.data_ptr(), self._work.data_ptr(), peer["ptrs_dev"], comm.rank,

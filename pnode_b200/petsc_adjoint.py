@@ -233,8 +233,12 @@ class ODEPetsc(object):
         self._imp.mass = self.mass
         self._engine = GenericTS(self._ops, self._scheme, kind, self._atol, self._rtol, comm=self.comm,
                                  solution_only=sol_only, max_cps=max_cps)
-        if sol_only or max_cps is not None:
-            self._allow_fused = False  # the fused sweeps always keep stage checkpoints in HBM
+        # the fused tiny-MLP sweeps honour -ts_trajectory_solution_only themselves (u_n per step in HBM, stages recomputed
+        # inside the adjoint kernel); a checkpoint budget (-ts_trajectory_max_cps_ram) and the FFJORD sweeps take the
+        # generic path with those options
+        self._fused_sol_only = sol_only and max_cps is None
+        if max_cps is not None:
+            self._allow_fused = False
 
     def _active_callbacks(self):
         """(explicit, implicit) right-hand sides the active scheme integrates.  Without imex_form the reference registers ONE
@@ -275,7 +279,10 @@ class ODEPetsc(object):
                 return None
             if self._fused is None or self._fused.scheme is not self._scheme:
                 self._fused = FusedMlpRK(self._fused_spec, self._scheme, self.tensor_dtype, self.device)
+            self._fused.solution_only = self._fused_sol_only
         else:
+            if self._fused_sol_only:
+                return None
             if not FusedCnfRK.supported(self._fused_spec, self._scheme, self.tensor_dtype):
                 return None
             if self._fused is None or self._fused.scheme is not self._scheme:

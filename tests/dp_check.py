@@ -53,6 +53,15 @@ def main():
     for a, b in zip(mine[2], full[2]):
         assert rel_err(a, b) < 1e-11, rel_err(a, b)
 
+    # 1b. the same with -ts_trajectory_solution_only 1: u_n per step in HBM, stages recomputed inside the adjoint kernel
+    lean = run(func, shard_batch(u0, rank, world).contiguous(), shard_batch(gout, rank, world, dim=1).contiguous(), t,
+               "rk4", 0.025, comm, ["-ts_adapt_type", "none", "-ts_trajectory_solution_only", "1"])
+    assert lean[3].path == "fused-mlp-rk" and lean[3]._fused.solution_only
+    assert rel_err(lean[0], shard_batch(full[0], rank, world, dim=1)) < 1e-13
+    assert rel_err(lean[1], shard_batch(full[1], rank, world)) < 1e-12
+    for a, b in zip(lean[2], full[2]):
+        assert rel_err(a, b) < 1e-11, rel_err(a, b)
+
     # 2. generic adaptive dopri5: one scalar all-reduce per attempt => same step sequence as the single-rank run
     g = torch.Generator().manual_seed(5)
     u1 = torch.randn(1000, 6, generator=g, dtype=torch.float64)

@@ -154,3 +154,25 @@ def test_full_size_2pow20_properties(dtype):
     assert rel_err(lam[0], o[1]) < tol and float((lam - lam[:1]).abs().max()) == 0.0
     for a, b in zip(p[2], o[2]):
         assert rel_err(a, b * reps) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("method,batch", [("rk4", 5000), ("rk4", 37), ("fixed_dopri5", 4500), ("bosh3", 4200),
+                                          ("rk2", 4300), ("euler", 4100)])
+def test_solution_only_checkpoints_inside_the_fused_sweep(dtype, method, batch):
+    """-ts_trajectory_solution_only 1 on the fused path: the forward sweep keeps u_n per step (1/s of the
+    stage checkpoints), the adjoint kernel recomputes the stages with the forward sweep's arithmetic -- bit-identical to
+    the stage-checkpoint sweeps, and to the oracle within the bar."""
+    func = SpiralFunc(dtype=dtype)
+    u0, t, gout = spiral_inputs(batch, dtype=dtype)
+    argv = ["-ts_adapt_type", "none"]
+    full = _product(func, u0, t, gout, method, 0.025, argv)
+    lean = _product(func, u0, t, gout, method, 0.025, argv + ["-ts_trajectory_solution_only", "1"])
+    assert full[3].path == "fused-mlp-rk" and lean[3].path == "fused-mlp-rk"
+    assert lean[3]._fused.solution_only and not full[3]._fused.solution_only
+    if batch > 4096:  # below, the stage-checkpoint run uses the small-batch kernels (different summation order)
+        assert torch.equal(full[0], lean[0])
+        assert torch.equal(full[1], lean[1])
+        assert all(torch.equal(a, b) for a, b in zip(full[2], lean[2]))
+    o = _oracle(func, u0, t, gout, method, 0.025, argv)
+    _compare(lean, o, TOL[dtype])
