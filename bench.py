@@ -264,7 +264,7 @@ def per_config_table(args, world, rank, comm):
         fl, ms = C.c_double(), C.c_float()
         _lib.check(lib.pnode_peak_fma(code, 20000, C.byref(fl), C.byref(ms)))
         pk[key] = fl.value / (ms.value * 1e-3) / 1e12
-    names = ["1", "2S", "3", "3L", "4", "4n", "4b", "4c", "4d", "5", "5L", "5S"] if world == 1 else ["3L", "4", "5"]
+    names = ["1", "2S", "2L", "3", "3L", "4", "4n", "4b", "4c", "4d", "5", "5L", "5S"] if world == 1 else ["3L", "4", "5"]
     a = types.SimpleNamespace(iters=args.config_iters, cpu=(world == 1 and not args.no_cpu_baseline), no_generic=True)
     bc.SEED_OFFSET = 100 * rank
     table, out = bc.config_table(), {"peaks": pk}

@@ -161,7 +161,7 @@ def run_config(name, build, args, peaks, world=1, comm=None):
         out["fused_speedup_vs_generic_path"] = ms_g / ms
         Options.clear_all()
         Options.insert_args(spec["argv"])
-    if args.cpu and world == 1:
+    if args.cpu and world == 1 and spec.get("cpu_sample") is not None:
         from oracle import OracleODEPetsc
 
         torch.set_num_threads(os.cpu_count() or 1)
@@ -192,7 +192,9 @@ def cfg1():
                                         desc="full size"))
 
 
-def cfg2(dtype="f32", ntraj=1 << 20):
+def cfg2(dtype="f32", ntraj=1 << 20, lean=False):
+    """lean: -ts_trajectory_solution_only 1 -- u_n per step in HBM (2 scalars per trajectory-step instead of 8), the stages
+    recomputed inside the adjoint kernel; the CPU baseline of the plain entry applies."""
     def build():
         from _problems import SpiralFunc
 
@@ -204,11 +206,14 @@ def cfg2(dtype="f32", ntraj=1 << 20):
         target = torch.randn(T, ntraj, 1, 2, generator=g, dtype=torch.float64).to(td)
         bs = 1 << 16
         w = 4 if dtype == "f32" else 8
-        return dict(desc="cfg2 spiral MLP 2-50-2 on y**3, 2^%d trajectories, RK4 9 steps h=0.025, %s" % (ntraj.bit_length() - 1, dtype),
-                    dtype=dtype, argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"], funcs=[SpiralFunc(dtype=td)],
+        return dict(desc="cfg2 spiral MLP 2-50-2 on y**3, 2^%d trajectories, RK4 9 steps h=0.025, %s%s" %
+                    (ntraj.bit_length() - 1, dtype, ", -ts_trajectory_solution_only 1 (u_n checkpoints, stages recomputed in "
+                     "the adjoint kernel)" if lean else ""),
+                    dtype=dtype, argv=["-ts_adapt_type", "none", "-ts_trajectory_type", "memory"] +
+                    (["-ts_trajectory_solution_only", "1"] if lean else []), funcs=[SpiralFunc(dtype=td)],
                     u0=u0, t=t, target=target, kw=dict(method="rk4"), step=H, batch=ntraj, flops_per_unit=6400,
-                    bytes_per_unit=20 * w, pipe="fp32_fma" if dtype == "f32" else "fp64_fma", peer_reduce=True,
-                    cpu_sample=lambda: dict(funcs=[SpiralFunc(dtype=td)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
+                    bytes_per_unit=(8 if lean else 20) * w, pipe="fp32_fma" if dtype == "f32" else "fp64_fma", peer_reduce=True,
+                    cpu_sample=None if lean else lambda: dict(funcs=[SpiralFunc(dtype=td)], u0=u0[:bs].clone(), t=t, target=target[:, :bs].clone(),
                                             kw=dict(method="rk4"), batch=bs, desc="%d of %d trajectories" % (bs, ntraj)))
 
     return build
@@ -343,7 +348,8 @@ def burgers(N=1024, B=200, dtype="f64"):
 
 
 def config_table():
-    return {"1": ("cfg1", cfg1), "2S": ("cfg2-f32", cfg2("f32")), "2D": ("cfg2-f64", cfg2("f64")), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
+    return {"1": ("cfg1", cfg1), "2S": ("cfg2-f32", cfg2("f32")), "2D": ("cfg2-f64", cfg2("f64")),
+            "2L": ("cfg2-f64-solution-only", cfg2("f64", lean=True)), "3": ("cfg3", _cnf(1000, "f32")), "3L": ("cfg3-2^20", _cnf(1 << 20, "f32")),
             "3D": ("cfg3-f64", _cnf(1000, "f64")),
             "3M": ("ffjord-miniboone", _cnf(1000, "f32", 43, (860, 860), 0.25)), "4": ("cfg4", cfg4()), "4b": ("cfg4-block2", cfg4(64, 16)),
             "4n": ("cfg4-Nt4", cfg4(32, 32, 4)), "4c": ("cfg4-block3", cfg4(128, 8)), "4d": ("cfg4-block4", cfg4(256, 4)),
