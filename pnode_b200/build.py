@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 # (source, object, extra flags): conv_block.cu is the long pole, so its fp32 and fp64 instantiations compile as two objects
-UNITS = [("vecops.cu", "vecops.o", []), ("mlp_rk.cu", "mlp_rk.o", []), ("cnf_rk.cu", "cnf_rk.o", []),
+# and mlp_rk.cu compiles once per group of (dim, hidden) shapes (part 0 = the spiral shape + the C entry points)
+UNITS = [("vecops.cu", "vecops.o", []), ("mlp_rk.cu", "mlp_rk.o", ["-DPNODE_MLP_PART=0"]),
+         ("mlp_rk.cu", "mlp_rk_p1.o", ["-DPNODE_MLP_PART=1"]), ("mlp_rk.cu", "mlp_rk_p2.o", ["-DPNODE_MLP_PART=2"]),
+         ("mlp_rk.cu", "mlp_rk_p3.o", ["-DPNODE_MLP_PART=3"]), ("cnf_rk.cu", "cnf_rk.o", []),
          ("bn_relu.cu", "bn_relu.o", []), ("umma_gemm.cu", "umma_gemm.o", []),
          ("dense_mlp.cu", "dense_mlp.o", []), ("conv_mma.cu", "conv_mma.o", []), ("conv_block.cu", "conv_block_f32.o", ["-DPNODE_CB_PART=1"]),
          ("conv_block.cu", "conv_block_f64.o", ["-DPNODE_CB_PART=2"])]

@@ -248,6 +248,7 @@ struct Cfg<double> {
 #define PNODE_CONST_WEIGHTS 0
 #endif
 constexpr int W_SLOTS = 4;
+#if PNODE_CONST_WEIGHTS
 constexpr int W_MAXP = 2 * 50 * 2 + 50 + 2;
 __constant__ float cWf[W_SLOTS][W_MAXP];
 __constant__ double cWd[W_SLOTS][W_MAXP];
@@ -261,6 +262,7 @@ template <>
 __device__ __forceinline__ double cwget<double>(int slot, int idx) {
     return cWd[slot][idx];
 }
+#endif
 
 template <typename T, int D, int H>
 __device__ __forceinline__ Unit<T, D> get_unit(const Unit<T, D> *__restrict__ sW, int slot, int j) {
@@ -364,7 +366,7 @@ __device__ __forceinline__ void mlp_eval(const Unit<T, D> *__restrict__ sW, cons
 constexpr int FWD_THREADS = 128;
 
 template <typename T, int D, int H, int S, int PHI>
-__global__ void __launch_bounds__(FWD_THREADS, Cfg<T>::FWD_MIN_CTAS)
+__global__ void __launch_bounds__(FWD_THREADS, (D == 2 && H == 50) ? Cfg<T>::FWD_MIN_CTAS : 2)
 mlp_rk_fwd_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const T *__restrict__ u0, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, T *__restrict__ sol, T *__restrict__ ckpt,
                   const int solution_only) {
@@ -456,7 +458,8 @@ constexpr int ADJ_MAX_BLOCKS = 148 * 8;
 template <typename T, int D, int H>
 struct AdjShape {
     static constexpr int TPT = Cfg<T>::TPT;
-    static constexpr int NCHUNK = Cfg<T>::ADJ_CHUNKS;
+    // hidden units in chunks of <= 32 (lane = unit in phase 2): the tuned count for H = 50, one chunk per 25 units beyond
+    static constexpr int NCHUNK = (H <= 50) ? Cfg<T>::ADJ_CHUNKS : (H + 24) / 25;
     static constexpr int G = Cfg<T>::ADJ_GROUP;
     // hidden units per chunk: <= 32 (lane = unit in phase 2), a multiple of the tanh group width
     static constexpr int JH = ((H + NCHUNK - 1) / NCHUNK + G - 1) / G * G;
@@ -505,7 +508,7 @@ __device__ void adj_finish(double *blk, int nwarps, AdjWork *__restrict__ work, 
 // SO: the forward sweep kept u_n per step only (-ts_trajectory_solution_only 1, [step][dim][traj]); the stage values of a
 // step are recomputed from u_n with the forward sweep's own arithmetic before its adjoint stages run.
 template <typename T, int D, int H, int S, int PHI, bool SO>
-__global__ void __launch_bounds__(ADJ_THREADS, Cfg<T>::ADJ_MIN_CTAS)
+__global__ void __launch_bounds__(ADJ_THREADS, (D == 2 && H == 50) ? Cfg<T>::ADJ_MIN_CTAS : 2)
 mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t ntraj,
                   const pnode_step *__restrict__ sched, const int nsteps, const int last_slot,
                   const T *__restrict__ gout, const T *__restrict__ ckpt, T *__restrict__ lambda_out,
@@ -1116,6 +1119,13 @@ static size_t adj_smem_bytes() {
 
 static int g_slot_counter = 0;
 
+// the small-batch kernels (ten lanes per trajectory) exist for the spiral shape only; other shapes run the large-batch
+// kernels at every batch size
+template <int D, int H>
+struct HasSmall {
+    static constexpr bool value = (D == 2 && H == 50);
+};
+
 static bool small_batch_enabled() {
     static const int on = [] {
         const char *e = getenv("PNODE_MLP_SMALL");
@@ -1151,13 +1161,16 @@ static int launch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, cons
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
                  static_cast<const T *>(m->d_b2), slot};
-    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled() && !so) {  // bounded storage is for large batches
-        const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
-        const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
-        mlp_rk_fwd_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
-            w, *tab, static_cast<const T *>(d_u0), ntraj, d_sched, nsteps, static_cast<T *>(d_sol), static_cast<T *>(d_ckpt));
-        PNODE_CUDA_OK(cudaGetLastError());
-        return 0;
+    if constexpr (HasSmall<D, H>::value) {
+        if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled() && !so) {  // bounded storage is for large batches
+            const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
+            const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+            mlp_rk_fwd_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
+                w, *tab, static_cast<const T *>(d_u0), ntraj, d_sched, nsteps, static_cast<T *>(d_sol),
+                static_cast<T *>(d_ckpt));
+            PNODE_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
     }
     auto kern = mlp_rk_fwd_kernel<T, D, H, S, PHI>;
     static int ctas_per_sm = 0;
@@ -1184,16 +1197,19 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
     if (int rc = upload_weights<T>(m, &slot, st)) return rc;
     MlpPtrs<T> w{static_cast<const T *>(m->d_w1), static_cast<const T *>(m->d_b1), static_cast<const T *>(m->d_w2),
                  static_cast<const T *>(m->d_b2), slot};
-    if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled() && !SO) {
-        const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
-        int64_t cap = (int64_t)sm_count() * 4;
-        if (cap > ADJ_MAX_BLOCKS) cap = ADJ_MAX_BLOCKS;
-        const int grid = (int)(want < cap ? want : cap);
-        mlp_rk_adj_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
-            w, *tab, ntraj, d_sched, nsteps, last_slot, static_cast<const T *>(d_gout), static_cast<const T *>(d_ckpt),
-            static_cast<T *>(d_lambda), static_cast<T *>(d_mu), static_cast<AdjWork *>(d_work), pc);
-        PNODE_CUDA_OK(cudaGetLastError());
-        return 0;
+    if constexpr (HasSmall<D, H>::value) {
+        if (ntraj <= SMALL_MAX_TRAJ && small_batch_enabled() && !SO) {
+            const int64_t want = (ntraj + SMALL_SLOTS - 1) / SMALL_SLOTS;
+            int64_t cap = (int64_t)sm_count() * 4;
+            if (cap > ADJ_MAX_BLOCKS) cap = ADJ_MAX_BLOCKS;
+            const int grid = (int)(want < cap ? want : cap);
+            mlp_rk_adj_small_kernel<T, D, H, S, PHI><<<grid, SMALL_THREADS, 0, st>>>(
+                w, *tab, ntraj, d_sched, nsteps, last_slot, static_cast<const T *>(d_gout),
+                static_cast<const T *>(d_ckpt), static_cast<T *>(d_lambda), static_cast<T *>(d_mu),
+                static_cast<AdjWork *>(d_work), pc);
+            PNODE_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
     }
     auto kern = mlp_rk_adj_kernel<T, D, H, S, PHI, SO>;
     const size_t smem = adj_smem_bytes<T, D, H>();
@@ -1216,44 +1232,136 @@ static int launch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int6
     return 0;
 }
 
-// the compiled instantiations: (dim, hidden) = (2, 50) -- the spiral model -- for every explicit tableau PETSc's
-// TSRK offers through pnode's method= table (1fe, 2a/2b, 3, 3bs/4, 5dp) and phi in {identity, cube}
+// The compiled instantiations.  (dim, hidden) = (2, 50) is the spiral model; the other shapes widen the recogniser to
+// 1- to 4-dimensional states and up to 100 hidden units (the host zero-pads narrower layers to the next compiled width --
+// a padded unit contributes fma(0, tanh(0), acc) = acc, so results are unchanged bit for bit).  Every shape is compiled for
+// every explicit tableau PETSc's TSRK offers through pnode's method= table (1fe, 2a/2b, 3, 3bs/4, 5dp) and phi in
+// {identity, cube}.  The file is compiled once per PART, in parallel (pnode_b200/build.py): part 0 holds the C entry points.
 #define PNODE_FOR_STAGES(X) X(1) X(2) X(3) X(4) X(7)
+#ifndef PNODE_MLP_PART
+#define PNODE_MLP_PART 0
+#endif
+#if PNODE_MLP_PART == 0
+#define PNODE_FOR_SHAPES(X) X(2, 50)
+#define PNODE_PART_NAME(f) f##_part0
+#elif PNODE_MLP_PART == 1
+#define PNODE_FOR_SHAPES(X) X(2, 100)
+#define PNODE_PART_NAME(f) f##_part1
+#elif PNODE_MLP_PART == 2
+#define PNODE_FOR_SHAPES(X) X(3, 50)
+#define PNODE_PART_NAME(f) f##_part2
+#elif PNODE_MLP_PART == 3
+#define PNODE_FOR_SHAPES(X) X(4, 50) X(1, 50)
+#define PNODE_PART_NAME(f) f##_part3
+#endif
+constexpr int MLP_PARTS = 4;
+constexpr int NO_KERNEL_HERE = -1000;  // this part holds no kernel for the shape: the caller tries the next part
 
 static bool shape_ok(int dim, int hidden, int phi, int stages) {
     bool s_ok = stages == 1 || stages == 2 || stages == 3 || stages == 4 || stages == 7;
-    return dim == 2 && hidden == 50 && (phi == 0 || phi == 1) && s_ok;
+    bool dh_ok = (hidden == 50 && dim >= 1 && dim <= 4) || (hidden == 100 && dim == 2);
+    return dh_ok && (phi == 0 || phi == 1) && s_ok;
 }
 
-template <typename T>
-static int dispatch_fwd(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
-                        const pnode_step *d_sched, int nsteps, void *d_sol, void *d_ckpt, int so, cudaStream_t st) {
-#define X(SS)                                                                                                     \
-    if (tab->s == SS) {                                                                                           \
-        if (m->phi == 1)                                                                                          \
-            return launch_fwd<T, 2, 50, SS, 1>(m, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);      \
-        return launch_fwd<T, 2, 50, SS, 0>(m, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);          \
+struct FwdArgs {
+    const pnode_mlp_desc *m;
+    const pnode_rk_tableau *tab;
+    const void *d_u0;
+    int64_t ntraj;
+    const pnode_step *d_sched;
+    int nsteps;
+    void *d_sol, *d_ckpt;
+    int so;
+    cudaStream_t st;
+};
+struct AdjArgs {
+    const pnode_mlp_desc *m;
+    const pnode_rk_tableau *tab;
+    int64_t ntraj;
+    const pnode_step *d_sched;
+    int nsteps, last_slot;
+    const void *d_gout, *d_ckpt;
+    void *d_lambda, *d_mu, *d_work;
+    PeerComm pc;
+    bool so;
+    cudaStream_t st;
+};
+
+template <typename T, int D, int H>
+static int dispatch_fwd(const FwdArgs &a) {
+#define X(SS)                                                                                                      \
+    if (a.tab->s == SS) {                                                                                          \
+        if (a.m->phi == 1)                                                                                         \
+            return launch_fwd<T, D, H, SS, 1>(a.m, a.tab, a.d_u0, a.ntraj, a.d_sched, a.nsteps, a.d_sol, a.d_ckpt, \
+                                              a.so, a.st);                                                         \
+        return launch_fwd<T, D, H, SS, 0>(a.m, a.tab, a.d_u0, a.ntraj, a.d_sched, a.nsteps, a.d_sol, a.d_ckpt,     \
+                                          a.so, a.st);                                                             \
     }
     PNODE_FOR_STAGES(X)
 #undef X
-    PNODE_REQUIRE(false, "pnode_mlp_rk_forward: no kernel for %d stages", tab->s);
+    PNODE_REQUIRE(false, "pnode_mlp_rk_forward: no kernel for %d stages", a.tab->s);
 }
 
-template <typename T, bool SO>
-static int dispatch_adj(const pnode_mlp_desc *m, const pnode_rk_tableau *tab, int64_t ntraj, const pnode_step *d_sched,
-                        int nsteps, int last_slot, const void *d_gout, const void *d_ckpt, void *d_lambda, void *d_mu,
-                        void *d_work, const PeerComm &pc, cudaStream_t st) {
-#define X(SS)                                                                                                     \
-    if (tab->s == SS) {                                                                                           \
-        if (m->phi == 1)                                                                                          \
-            return launch_adj<T, 2, 50, SS, 1, SO>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,     \
-                                                   d_lambda, d_mu, d_work, pc, st);                               \
-        return launch_adj<T, 2, 50, SS, 0, SO>(m, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt,         \
-                                               d_lambda, d_mu, d_work, pc, st);                                   \
+template <typename T, int D, int H, bool SO>
+static int dispatch_adj(const AdjArgs &a) {
+#define X(SS)                                                                                                      \
+    if (a.tab->s == SS) {                                                                                          \
+        if (a.m->phi == 1)                                                                                         \
+            return launch_adj<T, D, H, SS, 1, SO>(a.m, a.tab, a.ntraj, a.d_sched, a.nsteps, a.last_slot, a.d_gout, \
+                                                  a.d_ckpt, a.d_lambda, a.d_mu, a.d_work, a.pc, a.st);             \
+        return launch_adj<T, D, H, SS, 0, SO>(a.m, a.tab, a.ntraj, a.d_sched, a.nsteps, a.last_slot, a.d_gout,     \
+                                              a.d_ckpt, a.d_lambda, a.d_mu, a.d_work, a.pc, a.st);                 \
     }
     PNODE_FOR_STAGES(X)
 #undef X
-    PNODE_REQUIRE(false, "pnode_mlp_rk_adjoint: no kernel for %d stages", tab->s);
+    PNODE_REQUIRE(false, "pnode_mlp_rk_adjoint: no kernel for %d stages", a.tab->s);
+}
+
+int PNODE_PART_NAME(mlp_rk_fwd)(const FwdArgs &a) {
+#define X(DD, HH)                                                                 \
+    if (a.m->dim == DD && a.m->hidden == HH) {                                    \
+        if (a.m->dtype == PNODE_F32) return dispatch_fwd<float, DD, HH>(a);       \
+        if (a.m->dtype == PNODE_F64) return dispatch_fwd<double, DD, HH>(a);      \
+    }
+    PNODE_FOR_SHAPES(X)
+#undef X
+    return NO_KERNEL_HERE;
+}
+
+int PNODE_PART_NAME(mlp_rk_adj)(const AdjArgs &a) {
+#define X(DD, HH)                                                                                                   \
+    if (a.m->dim == DD && a.m->hidden == HH) {                                                                      \
+        if (a.m->dtype == PNODE_F32) return a.so ? dispatch_adj<float, DD, HH, true>(a) : dispatch_adj<float, DD, HH, false>(a);   \
+        if (a.m->dtype == PNODE_F64) return a.so ? dispatch_adj<double, DD, HH, true>(a) : dispatch_adj<double, DD, HH, false>(a); \
+    }
+    PNODE_FOR_SHAPES(X)
+#undef X
+    return NO_KERNEL_HERE;
+}
+
+#if PNODE_MLP_PART == 0
+int mlp_rk_fwd_part1(const FwdArgs &a);
+int mlp_rk_fwd_part2(const FwdArgs &a);
+int mlp_rk_fwd_part3(const FwdArgs &a);
+int mlp_rk_adj_part1(const AdjArgs &a);
+int mlp_rk_adj_part2(const AdjArgs &a);
+int mlp_rk_adj_part3(const AdjArgs &a);
+
+static int mlp_rk_fwd_any_part(const FwdArgs &a) {
+    int (*const parts[MLP_PARTS])(const FwdArgs &) = {mlp_rk_fwd_part0, mlp_rk_fwd_part1, mlp_rk_fwd_part2, mlp_rk_fwd_part3};
+    for (int p = 0; p < MLP_PARTS; ++p) {
+        const int rc = parts[p](a);
+        if (rc != NO_KERNEL_HERE) return rc;
+    }
+    PNODE_REQUIRE(false, "pnode_mlp_rk_forward: unsupported dtype %d", a.m->dtype);
+}
+static int mlp_rk_adj_any_part(const AdjArgs &a) {
+    int (*const parts[MLP_PARTS])(const AdjArgs &) = {mlp_rk_adj_part0, mlp_rk_adj_part1, mlp_rk_adj_part2, mlp_rk_adj_part3};
+    for (int p = 0; p < MLP_PARTS; ++p) {
+        const int rc = parts[p](a);
+        if (rc != NO_KERNEL_HERE) return rc;
+    }
+    PNODE_REQUIRE(false, "pnode_mlp_rk_adjoint: unsupported dtype %d", a.m->dtype);
 }
 
 template <typename T>
@@ -1266,8 +1374,11 @@ __global__ void tanh_probe_kernel(const T *in, T *out, int64_t n) {
         out[i] = tanh_acc(in[i], sTab);
 }
 
+#endif  // PNODE_MLP_PART == 0
+
 }  // namespace pnode
 
+#if PNODE_MLP_PART == 0
 using namespace pnode;
 
 extern "C" {
@@ -1283,12 +1394,10 @@ static int mlp_rk_forward_any(const pnode_mlp_desc *mlp, const pnode_rk_tableau 
                   "pnode_mlp_rk_forward: unsupported shape dim=%d hidden=%d phi=%d stages=%d", mlp->dim, mlp->hidden,
                   mlp->phi, tab->s);
     if (ntraj == 0 || nsteps == 0) return 0;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mlp->dtype == PNODE_F32)
-        return dispatch_fwd<float>(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);
-    if (mlp->dtype == PNODE_F64)
-        return dispatch_fwd<double>(mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so, st);
-    PNODE_REQUIRE(false, "pnode_mlp_rk_forward: unsupported dtype %d", mlp->dtype);
+    PNODE_REQUIRE(mlp->dtype == PNODE_F32 || mlp->dtype == PNODE_F64, "pnode_mlp_rk_forward: unsupported dtype %d",
+                  mlp->dtype);
+    return mlp_rk_fwd_any_part(FwdArgs{mlp, tab, d_u0, ntraj, d_sched, nsteps, d_sol, d_ckpt, so,
+                                       static_cast<cudaStream_t>(stream)});
 }
 
 int pnode_mlp_rk_forward(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, const void *d_u0, int64_t ntraj,
@@ -1318,17 +1427,11 @@ static int mlp_rk_adjoint_any(const pnode_mlp_desc *mlp, const pnode_rk_tableau 
     PNODE_REQUIRE(d_ckpt != nullptr || nsteps == 0, "pnode_mlp_rk_adjoint: stage checkpoints missing");
     PNODE_REQUIRE(world <= 1 || d_peer_bufs == nullptr || (epoch >= 1 && rank >= 0 && rank < world && world <= 64),
                   "pnode_mlp_rk_adjoint_dp: bad rank/world/epoch");
+    PNODE_REQUIRE(mlp->dtype == PNODE_F32 || mlp->dtype == PNODE_F64, "pnode_mlp_rk_adjoint: unsupported dtype %d",
+                  mlp->dtype);
     PeerComm pc{reinterpret_cast<const unsigned long long *>(d_peer_bufs), rank, world, (unsigned long long)epoch};
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define PNODE_ADJ_GO(TT)                                                                                               \
-    return so ? dispatch_adj<TT, true>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu,    \
-                                       d_work, pc, st)                                                                 \
-              : dispatch_adj<TT, false>(mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu,   \
-                                        d_work, pc, st)
-    if (mlp->dtype == PNODE_F32) PNODE_ADJ_GO(float);
-    if (mlp->dtype == PNODE_F64) PNODE_ADJ_GO(double);
-#undef PNODE_ADJ_GO
-    PNODE_REQUIRE(false, "pnode_mlp_rk_adjoint: unsupported dtype %d", mlp->dtype);
+    return mlp_rk_adj_any_part(AdjArgs{mlp, tab, ntraj, d_sched, nsteps, last_slot, d_gout, d_ckpt, d_lambda, d_mu, d_work,
+                                       pc, so, static_cast<cudaStream_t>(stream)});
 }
 
 int pnode_mlp_rk_adjoint_dp(const pnode_mlp_desc *mlp, const pnode_rk_tableau *tab, int64_t ntraj,
@@ -1370,3 +1473,4 @@ int pnode_tanh_probe(const void *d_in, void *d_out, int64_t n, int dtype, void *
 }
 
 }  // extern "C"
+#endif  // PNODE_MLP_PART == 0

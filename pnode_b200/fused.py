@@ -104,19 +104,55 @@ class FusedMlpRK:
         # -ts_trajectory_solution_only 1: keep u_n per step ([nsteps, dim, ntraj]) instead of the s stage values; the
         # adjoint sweep recomputes the stages (pnode_mlp_rk_forward_so / _adjoint_so)
         self.solution_only = False
+        # compiled hidden width the layer runs at: narrower layers are zero-padded (a padded unit adds
+        # fma(0, tanh(0), acc) = acc to the slope and gets a gradient nobody reads: results are unchanged bit for bit)
+        self.hidden = self.compiled_hidden(spec, scheme, dtype)
+        self._pad = None
+        if self.hidden != spec.hidden:
+            z = dict(dtype=dtype, device=device)
+            self._pad = (torch.zeros(self.hidden, spec.dim, **z), torch.zeros(self.hidden, **z),
+                         torch.zeros(spec.dim, self.hidden, **z))
+
+    COMPILED_HIDDEN = (50, 100)  # csrc/mlp_rk.cu PNODE_FOR_SHAPES
+
+    @staticmethod
+    def compiled_hidden(spec, scheme, dtype):
+        lib = _lib.load()
+        for h in FusedMlpRK.COMPILED_HIDDEN:
+            if h >= spec.hidden and lib.pnode_mlp_rk_supported(spec.dim, h, spec.phi, dtype_code(dtype), scheme.s):
+                return h
+        return None
 
     @staticmethod
     def supported(spec, scheme, dtype):
-        return bool(_lib.load().pnode_mlp_rk_supported(spec.dim, spec.hidden, spec.phi, dtype_code(dtype), scheme.s))
+        return FusedMlpRK.compiled_hidden(spec, scheme, dtype) is not None
 
     def _desc(self):
         sp = self.spec
         d = _lib.MlpDesc()
-        d.dim, d.hidden, d.phi, d.dtype = sp.dim, sp.hidden, sp.phi, self.code
+        d.dim, d.hidden, d.phi, d.dtype = sp.dim, self.hidden, sp.phi, self.code
         # live parameter storage: optimiser updates are seen by the next launch without a new setupTS
-        d.d_w1, d.d_b1 = sp.lin1.weight.data_ptr(), sp.lin1.bias.data_ptr()
-        d.d_w2, d.d_b2 = sp.lin2.weight.data_ptr(), sp.lin2.bias.data_ptr()
+        if self._pad is None:
+            d.d_w1, d.d_b1 = sp.lin1.weight.data_ptr(), sp.lin1.bias.data_ptr()
+            d.d_w2 = sp.lin2.weight.data_ptr()
+        else:
+            w1, b1, w2 = self._pad
+            h = sp.hidden
+            w1[:h].copy_(sp.lin1.weight.detach())
+            b1[:h].copy_(sp.lin1.bias.detach())
+            w2[:, :h].copy_(sp.lin2.weight.detach())
+            d.d_w1, d.d_b1, d.d_w2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr()
+        d.d_b2 = sp.lin2.bias.data_ptr()
         return d
+
+    def _unpad_mu(self, mu):
+        """mu of the padded layer (W1 [hidden, dim] | b1 | W2 [dim, hidden] | b2) -> the module's parameter order and sizes."""
+        if self._pad is None:
+            return mu
+        sp, hp = self.spec, self.hidden
+        h, dm = sp.hidden, sp.dim
+        o1, o2, o3 = hp * dm, hp * dm + hp, 2 * hp * dm + hp
+        return torch.cat((mu[:h * dm], mu[o1:o1 + h], mu[o2:o3].view(dm, hp)[:, :h].reshape(-1), mu[o3:]))
 
     def _schedule(self, times, step_size):
         key = (tuple(times), tuple(step_size) if isinstance(step_size, list) else float(step_size))
@@ -172,7 +208,7 @@ class FusedMlpRK:
         sched, nsteps, _ = sched_entry
         T = gout.shape[0]
         lam = torch.empty(ntraj * sp.dim, dtype=self.dtype, device=self.device)
-        npar = 2 * sp.hidden * sp.dim + sp.hidden + sp.dim
+        npar = 2 * self.hidden * sp.dim + self.hidden + sp.dim
         mu = torch.empty(npar, dtype=self.dtype, device=self.device)
         desc = self._desc()
         if self._work is None:
@@ -181,7 +217,7 @@ class FusedMlpRK:
         if nsteps == 0:
             lam.copy_(gout[-1])
             mu.zero_()
-            return lam, mu, False
+            return lam, self._unpad_mu(mu), False
         peer = getattr(comm, "peer", None) if comm is not None else None
         if ckpt.dim() == 3:  # solution checkpoints ([nsteps, dim, ntraj]): the sweep recomputes the stages
             _lib.check(self.lib.pnode_mlp_rk_adjoint_so(
@@ -199,7 +235,7 @@ class FusedMlpRK:
                                                      T - 1, gout.data_ptr(), ckpt.data_ptr(), lam.data_ptr(),
                                                      mu.data_ptr(), self._work.data_ptr(), _stream()))
         self.launches += 1
-        return lam, mu, peer is not None
+        return lam, self._unpad_mu(mu), peer is not None
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -76,9 +76,9 @@ class RoberEX(nn.Module):
 class SpiralFunc(nn.Module):
     """ODEFunc of ode_demo_petsc.py:207-230: Linear(2,50)-Tanh-Linear(50,2) on y**3, weights N(0, 0.1^2), biases 0."""
 
-    def __init__(self, dtype=torch.float64, seed=0, hidden=50, cube=True, bias_std=0.0):
+    def __init__(self, dtype=torch.float64, seed=0, hidden=50, cube=True, bias_std=0.0, dim=2):
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(2, hidden), nn.Tanh(), nn.Linear(hidden, 2)).to(dtype)
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.Tanh(), nn.Linear(hidden, dim)).to(dtype)
         g = torch.Generator().manual_seed(seed)
         for m in self.net.modules():
             if isinstance(m, nn.Linear):
@@ -93,11 +93,11 @@ class SpiralFunc(nn.Module):
         return self.net(y ** 3 if self.cube else y)
 
 
-def spiral_inputs(batch, T=10, dtype=torch.float64, seed=0, h=0.025):
+def spiral_inputs(batch, T=10, dtype=torch.float64, seed=0, h=0.025, dim=2):
     g = torch.Generator().manual_seed(seed)
-    u0 = (torch.rand(batch, 1, 2, generator=g, dtype=torch.float64) * 2 - 1) * 2
+    u0 = (torch.rand(batch, 1, dim, generator=g, dtype=torch.float64) * 2 - 1) * 2
     t = torch.arange(T, dtype=torch.float64) * h
-    gout = torch.randn(T, batch, 1, 2, generator=g, dtype=torch.float64)
+    gout = torch.randn(T, batch, 1, dim, generator=g, dtype=torch.float64)
     return u0.to(dtype), t, gout.to(dtype)
 
 

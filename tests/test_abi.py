@@ -32,7 +32,8 @@ def test_loads_and_reports_version():
     assert lib.pnode_wrms_work_bytes() > 0
     assert lib.pnode_mlp_rk_supported(2, 50, 1, _lib.F64, 4) == 1
     assert lib.pnode_mlp_rk_supported(2, 50, 1, _lib.F32, 7) == 1
-    assert lib.pnode_mlp_rk_supported(3, 50, 1, _lib.F64, 4) == 0
+    assert lib.pnode_mlp_rk_supported(3, 50, 1, _lib.F64, 4) == 1 and lib.pnode_mlp_rk_supported(2, 100, 0, _lib.F32, 7) == 1
+    assert lib.pnode_mlp_rk_supported(5, 50, 1, _lib.F64, 4) == 0 and lib.pnode_mlp_rk_supported(2, 64, 1, _lib.F64, 4) == 0
 
 
 def test_struct_layouts_match_header():

@@ -176,3 +176,33 @@ def test_solution_only_checkpoints_inside_the_fused_sweep(dtype, method, batch):
         assert all(torch.equal(a, b) for a, b in zip(full[2], lean[2]))
     o = _oracle(func, u0, t, gout, method, 0.025, argv)
     _compare(lean, o, TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("dim,hidden,cube,method,batch", [
+    (2, 100, True, "rk4", 700), (2, 64, False, "fixed_dopri5", 300), (2, 16, True, "rk4", 5000), (2, 51, True, "bosh3", 130),
+    (3, 50, True, "rk4", 600), (3, 20, False, "rk2", 4200), (4, 50, True, "rk4", 515), (4, 33, True, "fixed_dopri5", 100),
+    (1, 50, False, "rk4", 333), (1, 8, True, "euler", 64)])
+def test_other_state_sizes_and_widths_take_the_fused_sweeps(dtype, dim, hidden, cube, method, batch):
+    """The recogniser beyond the spiral shape: 1- to 4-dimensional states, any hidden width up to the compiled ones
+    (narrower layers are zero-padded on the host: csrc/mlp_rk.cu PNODE_FOR_SHAPES), with and without stage checkpoints."""
+    func = SpiralFunc(dtype=dtype, hidden=hidden, cube=cube, bias_std=0.2, dim=dim, seed=3)
+    u0, t, gout = spiral_inputs(batch, dtype=dtype, dim=dim)
+    argv = ["-ts_adapt_type", "none"]
+    o = _oracle(func, u0, t, gout, method, 0.025, argv)
+    p = _product(func, u0, t, gout, method, 0.025, argv)
+    assert p[3].path == "fused-mlp-rk"
+    assert [g.shape for g in p[2]] == [g.shape for g in o[2]]
+    _compare(p, o, TOL[dtype])
+    lean = _product(func, u0, t, gout, method, 0.025, argv + ["-ts_trajectory_solution_only", "1"])
+    assert lean[3].path == "fused-mlp-rk"
+    assert torch.equal(lean[0], p[0]) and torch.equal(lean[1], p[1]) and all(torch.equal(a, b) for a, b in zip(lean[2], p[2]))
+
+
+def test_layers_wider_than_the_compiled_shapes_take_the_generic_path():
+    func = SpiralFunc(hidden=128)
+    u0, t, gout = spiral_inputs(40)
+    argv = ["-ts_adapt_type", "none"]
+    p = _product(func, u0, t, gout, "rk4", 0.025, argv)
+    assert p[3].path == "generic"
+    _compare(p, _oracle(func, u0, t, gout, "rk4", 0.025, argv), 1e-10)
