@@ -320,23 +320,40 @@ __global__ void weight_operands_kernel(const float *w, int cin, int cout, int ta
 
 // Totals of the per-row-block partial sums, fixed order: RG threads per channel take contiguous ranges of the row blocks,
 // their sums are combined in range order.  tot[c] = sum of [.][c][0], tot[C + c] = sum of [.][c][1].  All threads of the block.
-template <int RG>
-__device__ void reduce_partials(const double *partials, int mtiles, int C, double *tot, double *scratch /* [2][RG][C] */) {
+template <int RGMAX>
+__device__ void reduce_partials(const double *partials, int mtiles, int C, double *tot, double *scratch /* [2][RGMAX][C] */) {
+    // One block sums [mtiles][C][2] partials.  The block is alone on its SM and every load is an L2 round trip, so the loads
+    // of a range are issued eight row blocks at a time before they are added (in range order), and the per-range sums go
+    // through shared memory when they fit (32 KB) instead of the global scratch: 22 us -> a few us per layer at C = 128.
+    constexpr int SH = 2048;
+    __shared__ double sh[2 * SH];
+    const bool in_smem = C <= SH;
+    const int RG = in_smem ? max(1, min(RGMAX, SH / C)) : RGMAX;
+    double *s1buf = in_smem ? sh : scratch, *s2buf = in_smem ? sh + RG * C : scratch + (long long)RG * C;
+    const int per = (mtiles + RG - 1) / RG;
     for (int i = threadIdx.x; i < C * RG; i += blockDim.x) {
         const int c = i % C, g = i / C;
-        const int per = (mtiles + RG - 1) / RG, m0 = g * per, m1 = min(mtiles, m0 + per);
+        const int m0 = g * per, m1 = min(mtiles, m0 + per);
         double s1 = 0.0, s2 = 0.0;
-        for (int m = m0; m < m1; ++m) {
-            s1 += partials[((long long)m * C + c) * 2];
-            s2 += partials[((long long)m * C + c) * 2 + 1];
+        for (int m = m0; m < m1; m += 8) {
+            double a[8], b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool in = m + u < m1;
+                const double *q = partials + ((long long)(in ? m + u : m) * C + c) * 2;
+                a[u] = in ? q[0] : 0.0;
+                b[u] = in ? q[1] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s1 += a[u], s2 += b[u];
         }
-        scratch[(long long)g * C + c] = s1;
-        scratch[(long long)(RG + g) * C + c] = s2;
+        s1buf[(long long)g * C + c] = s1;
+        s2buf[(long long)g * C + c] = s2;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double s1 = 0.0, s2 = 0.0;
-        for (int g = 0; g < RG; ++g) s1 += scratch[(long long)g * C + c], s2 += scratch[(long long)(RG + g) * C + c];
+        for (int g = 0; g < RG; ++g) s1 += s1buf[(long long)g * C + c], s2 += s2buf[(long long)g * C + c];
         tot[c] = s1, tot[C + c] = s2;
     }
     __syncthreads();
@@ -387,22 +404,6 @@ __global__ void bn_forward_finalize_kernel(BnFwd B, PeerComm pc) {
     if (threadIdx.x == 0 && B.update_running && B.num_batches_tracked) *B.num_batches_tracked += 1;
 }
 
-// The adjoint of an evaluation whose activation set was kept does not re-run the forward; the module's re-evaluation would
-// still advance the BatchNorm buffers once: do that from the stored statistics.
-__global__ void bn_advance_running_kernel(const double *mean, const double *invstd, int C, double count, double eps,
-                                          double momentum, float *running_mean, float *running_var, long long *nbt) {
-    pdl::pdl_launch_dependents();
-    pdl::pdl_wait();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        if (!running_mean) break;
-        const double var = fmax(1.0 / (invstd[c] * invstd[c]) - eps, 0.0);
-        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean[c]);
-        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
-    }
-    if (threadIdx.x == 0 && nbt) *nbt += 1;
-}
-
 struct BnBwd {
     const double *partials;  // [mtiles][C][2] = {sum g, sum g zhat}
     int mtiles, C;
@@ -414,12 +415,29 @@ struct BnBwd {
     double coef;
     int accumulate, contribute;    // contribute == 0: another rank reports the (global) affine gradients
     double *tot, *tot_global, *scratch;
+    // adjoint of an evaluation whose activation set was kept: the module's re-evaluation would have advanced the BatchNorm
+    // buffers once more -- done here from the stored statistics instead of in a launch of its own
+    int advance_running;
+    double eps, momentum;
+    float *running_mean, *running_var;
+    long long *num_batches_tracked;
 };
 
 __global__ void bn_backward_finalize_kernel(BnBwd B, PeerComm pc) {
     pdl::pdl_launch_dependents();
     pdl::pdl_wait();
     const int C = B.C;
+    if (B.advance_running) {
+        if (B.running_mean) {
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const double var = fmax(1.0 / (B.invstd[c] * B.invstd[c]) - B.eps, 0.0);
+                const double unbiased = B.count > 1.0 ? var * B.count / (B.count - 1.0) : var;
+                B.running_mean[c] = (float)((1.0 - B.momentum) * (double)B.running_mean[c] + B.momentum * B.mean[c]);
+                B.running_var[c] = (float)((1.0 - B.momentum) * (double)B.running_var[c] + B.momentum * unbiased);
+            }
+        }
+        if (threadIdx.x == 0 && B.num_batches_tracked) *B.num_batches_tracked += 1;
+    }
     reduce_partials<16>(B.partials, B.mtiles, C, B.tot, B.scratch);
     const double *tot = B.tot;
     if (pc.world > 1 && pc.peer_bufs) {
@@ -628,14 +646,8 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
         if (int rc = cmma::forward_impl(desc, p, W, (const float *)d_x, act, work, epoch, st)) return rc;
         epoch += p.L;
     } else {
-        // no re-evaluation: the module's forward would still have advanced the BatchNorm buffers once
-        for (int k = 0; k < p.L; ++k) {
-            const pnode_conv_layer &l = desc->layer[k];
-            const cmma::Bnp b = cmma::bnp_of(p, act, k);
-            PNODE_CUDA_OK(pdl::launch_pdl(cmma::bn_advance_running_kernel, dim3(1), dim3(256), 0, st, b.mean, b.invstd, p.g[k].cout, (double)p.Pg, l.eps, l.momentum,
-                                                               (float *)l.d_running_mean, (float *)l.d_running_var,
-                                                               (long long *)l.d_num_batches_tracked));
-        }
+        // no re-evaluation: the module's forward would still have advanced the BatchNorm buffers once (done by the
+        // backward-finalize launch of each layer below)
         PNODE_CUDA_OK(pdl::launch_pdl(cmma::nchw_to_nhwc_kernel, dim3(dim3((HW + 31) / 32, (C0 + 31) / 32, p.N)), dim3(32, 8), 0, st, (const float *)d_x, xin, C0, HW));
     }
     double *stats = reinterpret_cast<double *>(work + p.stats);
@@ -660,6 +672,9 @@ int pnode_convmma_vjp(const pnode_convblock_desc *desc, const void *d_wbuf, cons
         if (grads) B.ggamma = grads + p.goff_gamma[k], B.gbeta = grads + p.goff_beta[k], B.gbias = grads + p.goff_b[k];
         B.coef = coef, B.accumulate = accumulate, B.contribute = (p.world == 1 || p.rank == 0) ? 1 : 0;
         B.tot = tot, B.tot_global = tot + 2 * p.cmax, B.scratch = tot + 4 * p.cmax;
+        B.advance_running = act_valid ? 1 : 0, B.eps = l.eps, B.momentum = l.momentum;
+        B.running_mean = (float *)l.d_running_mean, B.running_var = (float *)l.d_running_var;
+        B.num_batches_tracked = (long long *)l.d_num_batches_tracked;
         PNODE_CUDA_OK(pdl::launch_pdl(cmma::bn_backward_finalize_kernel, dim3(1), dim3(1024), 0, st, B, cmma::peer_of(desc, epoch + (p.L - 1 - k))));
         const int kc = g.taps * g.cin, kd = g.taps * g.cout;
         // dz_k = ca g_k + cb z_k + cc, formed inside the gathers
