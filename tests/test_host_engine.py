@@ -543,3 +543,30 @@ def test_hpddm_block_solver_matches_dense_oracle(monkeypatch, method):
                  u0, t, gout[:3], 0.1)
     assert p[3]._imp.krylov_iterations > 0
     _assert_close(p, o, 1e-8)
+
+
+@pytest.mark.parametrize("dim,hidden,hpad", [(2, 16, 50), (3, 50, 50), (4, 33, 50), (2, 64, 100)])
+def test_fused_mlp_padding_round_trip(dim, hidden, hpad):
+    """Host side of the widened tiny-MLP shapes (fused.FusedMlpRK): a layer narrower than the compiled width runs zero-padded;
+    mu comes back in the padded layout and is cut to the module's parameter order and sizes."""
+    from pnode_b200.fused import FusedMlpRK, MlpSpec
+
+    lin1, lin2 = torch.nn.Linear(dim, hidden).double(), torch.nn.Linear(hidden, dim).double()
+    f = FusedMlpRK.__new__(FusedMlpRK)
+    f.spec, f.hidden = MlpSpec(lin1, lin2, 1, dim, hidden), hpad
+    f._pad = None if hpad == hidden else (torch.zeros(hpad, dim, dtype=torch.float64), torch.zeros(hpad, dtype=torch.float64),
+                                          torch.zeros(dim, hpad, dtype=torch.float64))
+    g = torch.Generator().manual_seed(0)
+    want = [torch.randn(p.shape, generator=g, dtype=torch.float64) for p in (lin1.weight, lin1.bias, lin2.weight, lin2.bias)]
+    w1p, b1p, w2p = torch.full((hpad, dim), 7.0).double(), torch.full((hpad,), 7.0).double(), torch.full((dim, hpad), 7.0).double()
+    w1p[:hidden], b1p[:hidden], w2p[:, :hidden] = want[0], want[1], want[2]
+    mu = torch.cat([w1p.reshape(-1), b1p, w2p.reshape(-1), want[3]])
+    got = f._unpad_mu(mu)
+    assert got.numel() == sum(w.numel() for w in want)
+    assert torch.equal(got, torch.cat([w.reshape(-1) for w in want]))
+    if f._pad is not None:
+        f.code = 1
+        d = f._desc()  # copies the live parameters into the padded buffers
+        assert d.hidden == hpad and torch.equal(f._pad[0][:hidden], lin1.weight.detach())
+        assert float(f._pad[0][hidden:].abs().sum() + f._pad[1][hidden:].abs().sum() + f._pad[2][:, hidden:].abs().sum()) == 0.0
+        assert torch.equal(f._pad[2][:, :hidden], lin2.weight.detach())
