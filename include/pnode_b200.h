@@ -124,7 +124,11 @@ typedef struct pnode_mlp_desc {
     const void *d_b2;   /* [dim] */
 } pnode_mlp_desc;
 
-/* 1 if a fused kernel is compiled for (dim, hidden, phi, dtype, stages), else 0 (caller uses the generic path). */
+/* 1 if a fused kernel is compiled for (dim, hidden, phi, dtype, stages), else 0 (caller uses the generic path).
+ * Compiled (dim, hidden): (2,50) -- the spiral model, with tuned occupancy and small-batch kernels -- and (2,100), (3,50),
+ * (4,50), (1,50); stages 1, 2, 3, 4, 7 (PETSc TSRK 1fe, 2a/2b, 3, 3bs/4, 5dp).  A layer with fewer hidden units than a
+ * compiled width runs on that width with zero weights for the missing units (the caller pads W1 / b1 / W2 and cuts the
+ * padded entries out of mu; pnode_b200/fused.py does): a padded unit changes no result bit. */
 int pnode_mlp_rk_supported(int dim, int hidden, int phi, int dtype, int stages);
 
 /* One entry of the step schedule the host controller hands to a fused sweep.  In fixed-step runs (-ts_adapt_type none,
