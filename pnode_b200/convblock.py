@@ -104,6 +104,9 @@ class ConvBlockCallbacks(Callbacks):
         self._cwork = None
         from .options import Options
 
+        if Options().hasName("pnode_conv_graphs"):  # optional per-call CUDA graphs of the launch sequences (csrc/graph_cache.cuh)
+            on = Options().getString("pnode_conv_graphs", "0") not in ("0", "false", "no")
+            _lib.check(self.lib.pnode_graph_cache_enable(int(on)))
         mode = Options().getString("pnode_convblock_native", "auto")  # auto | 1 (whenever the shape is supported) | 0
         # Tensor-core evaluator (csrc/conv_mma.cu, fp32 as 3xTF32) for GEMM-sized shapes: every layer at least 32 channels
         # wide (the CIFAR blocks [256,128,8,8] and [256,256,4,4]).  -pnode_convblock_mma auto | 1 (whenever supported) | 0
