@@ -131,11 +131,13 @@ def test_parameters_are_borrowed_not_copied():
     assert rel_err(y2, ref.odeint(u0, t)) < 1e-10 and rel_err(y1, y2) > 1e-4
 
 
+@pytest.mark.parametrize("lean", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_full_size_2pow20_properties(dtype):
+def test_full_size_2pow20_properties(dtype, lean):
     """BASELINE config 2 at full size through size-independent properties: the batch is the 20-trajectory base case
     tiled 2^20/20 times (+ remainder), so every replica must reproduce the oracle's base trajectories / lambda and mu must
-    be the replica-count-weighted sum of the oracle's per-trajectory contributions."""
+    be the replica-count-weighted sum of the oracle's per-trajectory contributions.  lean: with solution checkpoints only
+    (-ts_trajectory_solution_only 1, stages recomputed inside the adjoint kernel)."""
     B = 1 << 20
     func = SpiralFunc(dtype=dtype)
     u0b, t, goutb = spiral_inputs(32, dtype=dtype)
@@ -144,8 +146,8 @@ def test_full_size_2pow20_properties(dtype):
     gout = goutb.repeat(1, reps, 1, 1)
     argv = ["-ts_adapt_type", "none"]
     o = _oracle(func, u0b, t, goutb, "rk4", 0.025, argv)
-    p = _product(func, u0, t, gout, "rk4", 0.025, argv)
-    assert p[3].path == "fused-mlp-rk"
+    p = _product(func, u0, t, gout, "rk4", 0.025, argv + (["-ts_trajectory_solution_only", "1"] if lean else []))
+    assert p[3].path == "fused-mlp-rk" and p[3]._fused.solution_only == lean
     tol = TOL[dtype]
     out = p[0].view(10, reps, 32, 1, 2)
     assert rel_err(out[:, 0], o[0]) < tol and rel_err(out[:, reps - 1], o[0]) < tol and rel_err(out[:, reps // 2], o[0]) < tol
