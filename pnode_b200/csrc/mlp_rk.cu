@@ -18,8 +18,8 @@
 //    (double) live across all stages, steps and tiles of the persistent kernel.  Per-block partials are combined in a
 //    fixed order by the last block (bit-reproducible mu).
 //  * both kernels are bound by instruction issue of tanh (fp64: FP64 pipe; fp32: MUFU/issue), not by HBM (arithmetic
-//    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 256-entry 2^(j/256) table in
-//    SMEM + degree-4 polynomial + cubic reciprocal refinement = 15 FP64 ops; fp32: one MUFU.EX2 per unit and ONE shared
+//    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 1024-entry 2^(j/1024) table in
+//    SMEM + degree-3 polynomial + cubic reciprocal refinement = 12 FP64 ops (see PNODE_F64_TANH_V below); fp32: one MUFU.EX2 per unit and ONE shared
 //    MUFU.RCP per four units (product trick).  Grids are persistent: SMs x resident CTAs.
 #include <stdlib.h>
 
@@ -30,17 +30,44 @@ namespace pnode {
 // ---------------------------------------------------------------------------------------------------------------------
 // tanh
 
+// Two evaluations of the fp64 tanh (PNODE_F64_TANH_V).  ncu on the fp64 sweeps: the warp schedulers are busy 98.5 % of the
+// cycles in the forward sweep (an FP64 instruction holds the dispatch port for two cycles: issue-active 64.7 % + FP64 33.9 %)
+// and 81 % in the adjoint -- the sweeps are bound by the NUMBER of instructions, two slots per FP64 instruction, one per
+// integer / load instruction, and a tanh is four fifths of them.
+//   0  relative accuracy everywhere: em1 / (em1 + 2), 256-entry table, degree-4 polynomial, two-step argument reduction:
+//      15 FP64 + 9 integer instructions + 1 table load + 1 MUFU = 41 slots
+//   1  absolute accuracy (6e-16, all the state and the gradients need: tanh enters through W2 a and 1 - a^2):
+//      1 - 2 / (e^{2x} + 1), 1024-entry table (8 KB), degree-3 polynomial whose r^2 coefficient absorbs most of the r^4 term,
+//      one-step argument reduction (the product kf * c is exact inside the FMA; c is ln2/2048 correctly rounded), clamp as
+//      two FMNMX on the high word: 12 FP64 + 7 integer + 1 load + 1 MUFU = 33 slots
+#ifndef PNODE_F64_TANH_V
+#define PNODE_F64_TANH_V 1
+#endif
+#if PNODE_F64_TANH_V == 0
 constexpr int EXP_TAB = 256;  // 2^(j/256), j = 0..255  (2 KB of shared memory per CTA)
 constexpr int EXP_TAB_LOG2 = 8;
+#else
+constexpr int EXP_TAB = 1024;  // 2^(j/1024)  (8 KB of shared memory per CTA)
+constexpr int EXP_TAB_LOG2 = 10;
+#endif
 
 // |x| clamped to 24 on the high word (tanh(24) rounds to 1; keeps k = rint(x 512/ln2) small; NaN also saturates -- the
 // state that produced it stays NaN through the AXPYs, so divergence is still visible to the caller)
 __device__ __forceinline__ double clamp24(double x) {
+#if PNODE_F64_TANH_V == 0
     const int hx = __double2hiint(x);
     const int ha = min(hx & 0x7fffffff, 0x40380000);
     return __hiloint2double(ha | (hx & 0x80000000), __double2loint(x));
+#else
+    // the magnitude of a double's high word orders like a float with the same bits: 0x40380000 (24.0) reads 2.875f; one FMNMX
+    // with |.| on its source (high words that read as float NaN -- |x| >= 2^1017, inf, NaN -- come out as 2.875f), one LOP3
+    const int hx = __double2hiint(x);
+    const float ha = fminf(fabsf(__int_as_float(hx)), 2.875f);
+    return __hiloint2double(__float_as_int(ha) | (hx & 0x80000000), __double2loint(x));
+#endif
 }
 
+#if PNODE_F64_TANH_V == 0
 // fp64: tanh(x) = em1 / (em1 + 2), em1 = e^{2x} - 1 without cancellation.
 //   2x = k ln2/256 + r, |r| <= ln2/512;  e^{2x} = 2^(k>>8) * T[k&255] * (1 + P(r)),  P(r) = e^r - 1 (degree 4: truncation
 //   r^5/120 < 4e-17 absolute, < 3e-14 relative to tanh near 0)
@@ -68,6 +95,39 @@ __device__ __forceinline__ double tanh_acc(double xin, const double *__restrict_
     const double rc = fma(r0, fma(e0, e0, e0), r0);   // cubic refinement: error e0^3
     return em1 * rc;
 }
+#else
+// fp64: tanh(x) = 1 - 2 / (e^{2x} + 1).
+//   2x = k ln2/1024 + r, |r| <= ln2/2048;  e^{2x} = 2^(k>>10) * T[k&1023] * (1 + P(r));  with rh = r/2:
+//   P = rh (2 + rh (C2 + rh 4/3)),  C2 = 2 + 4 delta, delta = (sqrt2 - 1) h^2 / 12 (h = ln2/2048): the r^2 coefficient takes the
+//   r^4/24 term of e^r with it, leaving 0.0071 h^4 = 1e-16.
+constexpr double TANH_C = 2954.639443740597;         // 2048 / ln2
+constexpr double TANH_NEG_STEP = -0.0003384507717577858;  // -ln2 / 2048, correctly rounded
+constexpr double TANH_C2 = 2.000000015815906;
+// scaled table value 2^(k/1024): the exponent part of k is added into the high word ((k >> 10) << 20 = (8k - 8(k & 1023)) << 7)
+__device__ __forceinline__ double exp_tab(const double *__restrict__ tab, int k) {
+    const int a8 = k << 3, i8 = a8 & ((EXP_TAB - 1) << 3);
+    const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + i8);
+    return __hiloint2double(__double2hiint(T) + ((a8 - i8) << (20 - EXP_TAB_LOG2 - 3)), __double2loint(T));
+}
+__device__ __forceinline__ double tanh_acc(double xin, const double *__restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52
+    const double x = clamp24(xin);
+    double kf = fma(x, TANH_C, MAGIC);
+    const int k = __double2loint(kf);
+    kf -= MAGIC;
+    const double rh = fma(kf, TANH_NEG_STEP, x);
+    double p = fma(rh, 1.3333333333333333, TANH_C2);
+    p = fma(p, rh, 2.0);
+    p *= rh;
+    const double s = exp_tab(tab, k);
+    const double d = fma(s, p, s + 1.0);
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    const double e0 = fma(-d, r0, 1.0);
+    const double rc = fma(r0, fma(e0, e0, e0), r0);   // cubic refinement: error e0^3
+    return fma(-2.0, rc, 1.0);
+}
+#endif
 
 __device__ __forceinline__ float ex2_approx(float a) {
     float e;
@@ -117,6 +177,7 @@ __device__ __forceinline__ void tanh_group(const float (&z)[G], float (&a)[G], c
 template <int G>
 __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G], const double *__restrict__ tab) {
     const double MAGIC = 6755399441055744.0;
+#if PNODE_F64_TANH_V == 0
     double x[G], kf[G], rh[G], p[G], s[G], em1[G], d[G], r0[G], e0[G];
     int k[G];
 #pragma unroll
@@ -157,6 +218,39 @@ __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G],
     for (int g = 0; g < G; ++g) r0[g] = fma(r0[g], fma(e0[g], e0[g], e0[g]), r0[g]);
 #pragma unroll
     for (int g = 0; g < G; ++g) a[g] = em1[g] * r0[g];
+#else
+    double x[G], kf[G], rh[G], p[G], s[G], d[G], r0[G], e0[G];
+    int k[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) x[g] = clamp24(z[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) kf[g] = fma(x[g], TANH_C, MAGIC);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        k[g] = __double2loint(kf[g]);
+        kf[g] -= MAGIC;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) s[g] = exp_tab(tab, k[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) rh[g] = fma(kf[g], TANH_NEG_STEP, x[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(rh[g], 1.3333333333333333, TANH_C2);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 2.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) p[g] *= rh[g];
+#pragma unroll
+    for (int g = 0; g < G; ++g) d[g] = fma(s[g], p[g], s[g] + 1.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0[g]) : "d"(d[g]));
+#pragma unroll
+    for (int g = 0; g < G; ++g) e0[g] = fma(-d[g], r0[g], 1.0);
+#pragma unroll
+    for (int g = 0; g < G; ++g) r0[g] = fma(r0[g], fma(e0[g], e0[g], e0[g]), r0[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = fma(-2.0, r0[g], 1.0);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
