@@ -473,7 +473,7 @@ def run_native(args):
                         "frac": adj_flops / (ta * 1e-3) / 1e12 / fma_peak},
             "forward": {"ms": tf, "algorithmic_tflops": fwd_flops / (tf * 1e-3) / 1e12,
                         "frac": fwd_flops / (tf * 1e-3) / 1e12 / fma_peak, "hbm_gbs": fwd_bytes / (tf * 1e-3) / 1e9},
-            "note": "algorithmic flops exclude tanh (400 evaluations per trajectory-step; fp64: 12 FP64 + 7 integer "
+            "note": "algorithmic flops exclude tanh (400 evaluations per trajectory-step; fp64: 11 FP64 + 7 integer "
                     "instructions each).  ncu: an FP64 instruction holds the dispatch port two cycles, the port is busy "
                     "98.5 % of the forward sweep's cycles (issue-active + FP64 share) -- the sweep is bound by its "
                     "instruction count; the adjoint by shared-memory wavefronts (0.91 per cycle).  DESIGN.md section 8.6"}

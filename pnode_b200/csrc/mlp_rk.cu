@@ -19,8 +19,8 @@
 //    fixed order by the last block (bit-reproducible mu).
 //  * both kernels are bound by instruction issue of tanh (fp64: FP64 pipe; fp32: MUFU/issue), not by HBM (arithmetic
 //    intensity ~80 flop/B): the work went into shrinking tanh -- fp64: 1024-entry 2^(j/1024) table in
-//    SMEM + degree-3 polynomial + cubic reciprocal refinement = 12 FP64 ops (see PNODE_F64_TANH_V below); fp32: one MUFU.EX2 per unit and ONE shared
-//    MUFU.RCP per four units (product trick).  Grids are persistent: SMs x resident CTAs.
+//    SMEM + degree-3 polynomial + cubic reciprocal refinement = 11 FP64 ops (see PNODE_F64_TANH_V below); fp32: one
+//    MUFU.EX2 per unit and ONE shared MUFU.RCP per four units (product trick).  Grids are persistent: SMs x resident CTAs.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -39,7 +39,7 @@ namespace pnode {
 //   1  absolute accuracy (6e-16, all the state and the gradients need: tanh enters through W2 a and 1 - a^2):
 //      1 - 2 / (e^{2x} + 1), 1024-entry table (8 KB), degree-3 polynomial whose r^2 coefficient absorbs most of the r^4 term,
 //      one-step argument reduction (the product kf * c is exact inside the FMA; c is ln2/2048 correctly rounded), clamp as
-//      two FMNMX on the high word: 12 FP64 + 7 integer + 1 load + 1 MUFU = 33 slots
+//      one FMNMX + one LOP3 on the high word: 11 FP64 + 7 integer + 1 load + 1 MUFU = 31 slots
 #ifndef PNODE_F64_TANH_V
 #define PNODE_F64_TANH_V 1
 #endif
@@ -98,8 +98,8 @@ __device__ __forceinline__ double tanh_acc(double xin, const double *__restrict_
 #else
 // fp64: tanh(x) = 1 - 2 / (e^{2x} + 1).
 //   2x = k ln2/1024 + r, |r| <= ln2/2048;  e^{2x} = 2^(k>>10) * T[k&1023] * (1 + P(r));  with rh = r/2:
-//   P = rh (2 + rh (C2 + rh 4/3)),  C2 = 2 + 4 delta, delta = (sqrt2 - 1) h^2 / 12 (h = ln2/2048): the r^2 coefficient takes the
-//   r^4/24 term of e^r with it, leaving 0.0071 h^4 = 1e-16.
+//   e^r = 1 + rh (2 + rh (C2 + rh 4/3)),  C2 = 2 + 4 delta, delta = (sqrt2 - 1) h^2 / 12 (h = ln2/2048): the r^2 coefficient takes
+//   the r^4/24 term of e^r with it, leaving 0.0071 h^4 = 1e-16;  e^{2x} + 1 = fma(s, e^r, 1).
 constexpr double TANH_C = 2954.639443740597;         // 2048 / ln2
 constexpr double TANH_NEG_STEP = -0.0003384507717577858;  // -ln2 / 2048, correctly rounded
 constexpr double TANH_C2 = 2.000000015815906;
@@ -118,9 +118,9 @@ __device__ __forceinline__ double tanh_acc(double xin, const double *__restrict_
     const double rh = fma(kf, TANH_NEG_STEP, x);
     double p = fma(rh, 1.3333333333333333, TANH_C2);
     p = fma(p, rh, 2.0);
-    p *= rh;
+    p = fma(p, rh, 1.0);                               // e^r
     const double s = exp_tab(tab, k);
-    const double d = fma(s, p, s + 1.0);
+    const double d = fma(s, p, 1.0);
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
     const double e0 = fma(-d, r0, 1.0);
@@ -239,9 +239,9 @@ __device__ __forceinline__ void tanh_group(const double (&z)[G], double (&a)[G],
 #pragma unroll
     for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 2.0);
 #pragma unroll
-    for (int g = 0; g < G; ++g) p[g] *= rh[g];
+    for (int g = 0; g < G; ++g) p[g] = fma(p[g], rh[g], 1.0);
 #pragma unroll
-    for (int g = 0; g < G; ++g) d[g] = fma(s[g], p[g], s[g] + 1.0);
+    for (int g = 0; g < G; ++g) d[g] = fma(s[g], p[g], 1.0);
 #pragma unroll
     for (int g = 0; g < G; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0[g]) : "d"(d[g]));
 #pragma unroll
