@@ -571,10 +571,26 @@ struct AdjWork {
     double partial[1];  // [blocks][NP]
 };
 
+// PNODE_ADJ_RECOMPUTE_S 1: phase 2 forms s_j = (W2[:,j] . v)(1 - a_j^2) again from the parked a_j, the lane's own W2 column and
+// the broadcast v instead of reading a parked copy -- the same three instructions as phase 1, so the same bits.  The fp64
+// adjoint sweep issues 0.91 shared-memory wavefronts per cycle and is bound there: the parked copy costs 2.1 (store) + 2.6
+// (transposed re-read) of its 25.2 wavefronts per hidden unit and warp, the recomputation four FP64 instructions per
+// (unit, trajectory) in lanes that were waiting for the loads.
+// fp64 only: measured at 2^20 trajectories 5.55 -> 5.30 ms; the fp32 sweep (MUFU / issue bound) 2.61 -> 2.66 ms, so it keeps
+// the parked copy.
+#ifndef PNODE_ADJ_RECOMPUTE_S
+#define PNODE_ADJ_RECOMPUTE_S 1
+#endif
+template <typename T>
+struct AdjRecompute {
+    static constexpr bool value = PNODE_ADJ_RECOMPUTE_S && sizeof(T) == 8;
+};
+
 template <typename T, int D, int H>
 struct alignas(16) WarpTile {
     T A[AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];   // tanh(z_j)           per (unit, trajectory)
-    T Sg[AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];  // s_j = g_j(1-a_j^2)   per (unit, trajectory)
+    // s_j = g_j(1-a_j^2) per (unit, trajectory); one 16-byte placeholder when phase 2 recomputes it
+    T Sg[AdjRecompute<T>::value ? AdjShape<T, D, H>::VEC : AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];
     T V[D][AdjShape<T, D, H>::NK];                           // stage cotangent v, per trajectory
     T X[D][AdjShape<T, D, H>::NK];                           // phi(Y_i)
 };
@@ -782,7 +798,7 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
 #pragma unroll
                                     for (int d = 0; d < D; ++d) dx[q][d] = fma(s, u[g].w1[d], dx[q][d]);
                                     tile.A[(jb + g) * PITCH + q * 32 + lane] = a[g];
-                                    tile.Sg[(jb + g) * PITCH + q * 32 + lane] = s;
+                                    if (!AdjRecompute<T>::value) tile.Sg[(jb + g) * PITCH + q * 32 + lane] = s;
                                 }
                             }
                         }
@@ -793,15 +809,25 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                         T pW2[D], pW1[D], pB1 = T(0);
 #pragma unroll
                         for (int d = 0; d < D; ++d) pW2[d] = pW1[d] = T(0);
+                        const Unit<T, D> own = get_unit<T, D, H>(sW, w.slot, j0 + lane);  // used when s is recomputed
 #pragma unroll 4
                         for (int k = 0; k < NK; k += VEC) {
                             T a[VEC], s[VEC], vv[D][VEC], xx[D][VEC];
                             lds16(&tile.A[lane * PITCH + k], a);
-                            lds16(&tile.Sg[lane * PITCH + k], s);
+                            if (!AdjRecompute<T>::value) lds16(&tile.Sg[lane * PITCH + k], s);
 #pragma unroll
                             for (int d = 0; d < D; ++d) {
                                 lds16(&tile.V[d][k], vv[d]);
                                 lds16(&tile.X[d][k], xx[d]);
+                            }
+                            if (AdjRecompute<T>::value) {
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) {  // phase 1's three instructions, operand for operand
+                                    T gg = T(0);
+#pragma unroll
+                                    for (int d = 0; d < D; ++d) gg = fma(own.w2[d], vv[d][e], gg);
+                                    s[e] = gg * fma(-a[e], a[e], T(1));
+                                }
                             }
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) {
