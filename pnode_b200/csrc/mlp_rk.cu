@@ -586,9 +586,18 @@ struct AdjRecompute {
     static constexpr bool value = PNODE_ADJ_RECOMPUTE_S && sizeof(T) == 8;
 };
 
+// With s recomputed the tile has room for the tanh values of BOTH 25-unit chunks of a stage (the footprint the parked copy of
+// s had): one phase 2 per stage in which a lane serves its unit of every chunk, so the v / x broadcasts -- 8 bytes per
+// shared-memory wavefront whatever the load width, 5.1 wavefronts per hidden unit and warp -- are read once per stage.
+template <typename T, int D, int H>
+struct AdjMerge {
+    static constexpr bool value = AdjRecompute<T>::value && AdjShape<T, D, H>::NCHUNK == 2 && AdjShape<T, D, H>::TPT == 1;
+    static constexpr int ROWS = (value ? AdjShape<T, D, H>::NCHUNK : 1) * AdjShape<T, D, H>::JH;
+};
+
 template <typename T, int D, int H>
 struct alignas(16) WarpTile {
-    T A[AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];   // tanh(z_j)           per (unit, trajectory)
+    T A[AdjMerge<T, D, H>::ROWS * AdjShape<T, D, H>::PITCH];  // tanh(z_j)           per (unit, trajectory)
     // s_j = g_j(1-a_j^2) per (unit, trajectory); one 16-byte placeholder when phase 2 recomputes it
     T Sg[AdjRecompute<T>::value ? AdjShape<T, D, H>::VEC : AdjShape<T, D, H>::JH * AdjShape<T, D, H>::PITCH];
     T V[D][AdjShape<T, D, H>::NK];                           // stage cotangent v, per trajectory
@@ -767,6 +776,98 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                 if (!SO) {
                     if (i > 0) fetch_Y(n, i - 1); else fetch_Y(n - 1, s_top);
                 }
+                if constexpr (AdjMerge<T, D, H>::value) {
+                    // ---- phase 1 (lane = trajectory): VJP through every hidden unit of the stage, tanh parked per unit ----
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c) {
+                        const int j0 = c * JH;
+                        const int jn = (H - j0 < JH) ? (H - j0) : JH;
+#pragma unroll 1
+                        for (int jb = 0; jb < jn; jb += G) {
+                            Unit<T, D> u[G];
+#pragma unroll
+                            for (int g = 0; g < G; ++g)
+                                u[g] = get_unit<T, D, H>(sW, w.slot, j0 + ((jb + g < jn) ? jb + g : jn - 1));
+                            T z[G], a[G];
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                z[g] = u[g].b1;
+#pragma unroll
+                                for (int d = 0; d < D; ++d) z[g] = fma(u[g].w1[d], x[0][d], z[g]);
+                            }
+                            tanh_group<G>(z, a, sTab);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                if (jb + g < jn) {
+                                    T gg = T(0);
+#pragma unroll
+                                    for (int d = 0; d < D; ++d) gg = fma(u[g].w2[d], v[0][d], gg);
+                                    const T s = gg * fma(-a[g], a[g], T(1));
+#pragma unroll
+                                    for (int d = 0; d < D; ++d) dx[0][d] = fma(s, u[g].w1[d], dx[0][d]);
+                                    tile.A[(j0 + jb + g) * PITCH + lane] = a[g];
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // ---- phase 2 (lane = one hidden unit of every chunk): outer products over the warp's trajectories -----
+                    if (lane < JH) {
+                        T pW2[NCHUNK][D], pW1[NCHUNK][D], pB1[NCHUNK];
+                        Unit<T, D> own[NCHUNK];
+                        bool act[NCHUNK];
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            const int jn = (H - c * JH < JH) ? (H - c * JH) : JH;
+                            act[c] = lane < jn;
+                            own[c] = get_unit<T, D, H>(sW, w.slot, c * JH + (act[c] ? lane : 0));
+                            pB1[c] = T(0);
+#pragma unroll
+                            for (int d = 0; d < D; ++d) pW2[c][d] = pW1[c][d] = T(0);
+                        }
+#pragma unroll 2
+                        for (int k = 0; k < NK; k += VEC) {
+                            T vv[D][VEC], xx[D][VEC];
+#pragma unroll
+                            for (int d = 0; d < D; ++d) {
+                                lds16(&tile.V[d][k], vv[d]);
+                                lds16(&tile.X[d][k], xx[d]);
+                            }
+#pragma unroll
+                            for (int c = 0; c < NCHUNK; ++c) {
+                                if (act[c]) {
+                                    T a[VEC];
+                                    lds16(&tile.A[(c * JH + lane) * PITCH + k], a);
+#pragma unroll
+                                    for (int e = 0; e < VEC; ++e) {  // phase 1's three instructions, operand for operand
+                                        T gg = T(0);
+#pragma unroll
+                                        for (int d = 0; d < D; ++d) gg = fma(own[c].w2[d], vv[d][e], gg);
+                                        const T s = gg * fma(-a[e], a[e], T(1));
+                                        pB1[c] += s;
+#pragma unroll
+                                        for (int d = 0; d < D; ++d) {
+                                            pW2[c][d] = fma(vv[d][e], a[e], pW2[c][d]);
+                                            pW1[c][d] = fma(s, xx[d][e], pW1[c][d]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; ++c) {
+                            if (act[c]) {
+                                accB1[c] += (double)pB1[c];
+#pragma unroll
+                                for (int d = 0; d < D; ++d) {
+                                    accW2[c][d] += (double)pW2[c][d];
+                                    accW1[c][d] += (double)pW1[c][d];
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int j0 = c * JH;
@@ -847,6 +948,7 @@ mlp_rk_adj_kernel(const MlpPtrs<T> w, const pnode_rk_tableau tab, const int64_t 
                         }
                     }
                     __syncwarp();
+                }
                 }
 #pragma unroll
                 for (int q = 0; q < TPT; ++q)
