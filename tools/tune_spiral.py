@@ -14,6 +14,8 @@ TUNE = os.path.join(CSRC, "tune")
 
 VARIANTS = {
     "base": {},
+    "f64_tanh_v0": {"PNODE_F64_TANH_V": 0},       # relative-accuracy tanh (15 FP64 instructions)
+    "f64_park_s": {"PNODE_ADJ_RECOMPUTE_S": 0},   # adjoint phase 2 reads a parked copy of s
     "f32_t1c2": {"PNODE_F32_TPT": 1, "PNODE_F32_CHUNKS": 2, "PNODE_F32_ADJ_CTAS": 5},
     "f32_t1c2_ag1": {"PNODE_F32_TPT": 1, "PNODE_F32_CHUNKS": 2, "PNODE_F32_ADJ_CTAS": 5, "PNODE_F32_ADJ_GROUP": 1},
     "f32_t1c2_ag2": {"PNODE_F32_TPT": 1, "PNODE_F32_CHUNKS": 2, "PNODE_F32_ADJ_CTAS": 5, "PNODE_F32_ADJ_GROUP": 2},
@@ -37,20 +39,32 @@ VARIANTS = {
 
 
 def build():
+    """Part 0 of mlp_rk.cu (the spiral shape + the C entry points) is compiled per variant and linked against the objects of
+    the in-tree build (pnode_b200/csrc/_obj, `python -m pnode_b200.build` first) for everything else."""
     os.makedirs(TUNE, exist_ok=True)
+    objdir = os.path.join(CSRC, "_obj")
+    others = [os.path.join(objdir, f) for f in sorted(os.listdir(objdir)) if f.endswith(".o") and f != "mlp_rk.o"]
     procs = []
     for name, defs in VARIANTS.items():
-        out = os.path.join(TUNE, "lib_%s.so" % name)
-        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-shared",
-               "-Xcompiler", "-fPIC", "-cudart", "static", "-o", out, "vecops.cu", "mlp_rk.cu"]
-        cmd += ["-D%s=%s" % kv for kv in defs.items()]
-        procs.append((name, subprocess.Popen(cmd, cwd=CSRC, stderr=subprocess.PIPE, text=True)))
+        obj = os.path.join(TUNE, "mlp_rk_%s.o" % name)
+        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+               "-DPNODE_MLP_PART=0", "-c", "mlp_rk.cu", "-o", obj] + ["-D%s=%s" % kv for kv in defs.items()]
+        procs.append((name, obj, subprocess.Popen(cmd, cwd=CSRC, stderr=subprocess.PIPE, text=True)))
         if len(procs) % 4 == 0:
-            for n, p in procs[-4:]:
+            for _, _, p in procs[-4:]:
                 p.wait()
-    for n, p in procs:
+    for name, obj, p in procs:
+        err = p.stderr.read()
         p.wait()
-        print(n, "ok" if p.returncode == 0 else "FAILED\n" + p.stderr.read()[-2000:])
+        if p.returncode != 0:
+            print(name, "FAILED\n" + err[-2000:])
+            continue
+        out = os.path.join(TUNE, "lib_%s.so" % name)
+        link = ["nvcc", "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, obj] + others + \
+            ["-lcuda"]
+        r = subprocess.run(link, capture_output=True, text=True)
+        print(name, "ok" if r.returncode == 0 else "LINK FAILED\n" + r.stderr[-2000:])
+        os.remove(obj)
 
 
 def time_one(dtype):
