@@ -94,7 +94,7 @@ def time_one(dtype):
         ev[0].record()
         sol, ckpt, sched = fused.forward(u0.reshape(-1), times, 0.025, True)
         ev[1].record()
-        lam, mu = fused.adjoint(gout, ckpt, sched, n)
+        lam, mu, _ = fused.adjoint(gout, ckpt, sched, n)
         ev[2].record()
         torch.cuda.synchronize()
         if i >= 2:
